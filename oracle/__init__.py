@@ -1,0 +1,151 @@
+"""TEST INFRASTRUCTURE — ctypes front end of the CPU oracle (oracle/sdf_oracle.c).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this package; the product package codecad_b200 never does.
+
+`build()` compiles liboracle.so in place (gcc, OpenMP, explicit-FMA arithmetic, no
+implicit contraction); the built file travels to the GPU box with the repo snapshot.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liboracle.so")
+_SRC = [os.path.join(_HERE, "sdf_oracle.c"), os.path.join(_HERE, "cc_math_ref.h")]
+
+# -mavx2 -mfma: hardware FMA so fmaf() is one instruction (x86-64-v3; any host that
+# carries a B200 has it).  -ffp-contract=off: nothing is fused behind our back.
+CFLAGS = ["-O3", "-mavx2", "-mfma", "-ffp-contract=off", "-fno-fast-math", "-fopenmp",
+          "-shared", "-fPIC", "-Wall", "-Wextra"]
+
+
+def build(force=False):
+    if not force and os.path.exists(_SO) and all(
+        os.path.getmtime(_SO) >= os.path.getmtime(s) for s in _SRC
+    ):
+        return _SO
+    cmd = ["gcc"] + CFLAGS + ["-o", _SO, _SRC[0], "-lm"]
+    subprocess.run(cmd, check=True)
+    return _SO
+
+
+_lib = None
+_fp = ctypes.POINTER(ctypes.c_float)
+_u32p = ctypes.POINTER(ctypes.c_uint32)
+_u8p = ctypes.POINTER(ctypes.c_uint8)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        L = ctypes.CDLL(_SO)
+        L.oracle_validate.argtypes = [_fp, ctypes.c_int]
+        L.oracle_evaluate_points.argtypes = [_fp, ctypes.c_int, _fp, ctypes.c_long, _fp]
+        L.oracle_grid_eval.argtypes = [_fp, ctypes.c_int, _fp, ctypes.c_float] + [ctypes.c_int] * 4 + [_fp]
+        L.oracle_grid_eval_pymcubes.argtypes = [_fp, ctypes.c_int, _fp, ctypes.c_float] + [ctypes.c_int] * 3 + [_fp]
+        L.oracle_subdivision_step.argtypes = (
+            [_fp, ctypes.c_int, _fp, ctypes.c_float, ctypes.c_float] + [ctypes.c_int] * 3 + [_u32p, _u8p]
+        )
+        L.oracle_mass_properties_step.argtypes = (
+            [_fp, ctypes.c_int, _fp, ctypes.c_float, ctypes.c_float] + [ctypes.c_int] * 3 + [_u32p, _u32p, _u8p]
+        )
+        L.oracle_math_probe.argtypes = [ctypes.c_int, _fp, _fp, ctypes.c_long, _fp, _fp]
+        L.oracle_num_threads.restype = ctypes.c_int
+        L.oracle_set_num_threads.argtypes = [ctypes.c_int]
+        _lib = L
+    return _lib
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a, t=_fp):
+    return a.ctypes.data_as(t)
+
+
+def _check(rc):
+    if rc < 0:
+        raise ValueError("oracle: malformed program (code %d)" % rc)
+    return rc
+
+
+def num_threads():
+    return lib().oracle_num_threads()
+
+
+def set_num_threads(n):
+    lib().oracle_set_num_threads(int(n))
+
+
+def validate(words):
+    w = _f32(words)
+    return _check(lib().oracle_validate(_p(w), len(w)))
+
+
+def evaluate_points(words, pts):
+    w = _f32(words)
+    pts = _f32(pts).reshape(-1, 3)
+    out = np.empty((len(pts), 4), np.float32)
+    _check(lib().oracle_evaluate_points(_p(w), len(w), _p(pts), len(pts), _p(out)))
+    return out
+
+
+def grid_eval(words, corner, step, dims, x_offset=0):
+    """float4 grid in the reference's INDEX3 layout: out[x][y][z] = (grad.xyz, dist)."""
+    w = _f32(words)
+    c = _f32(corner)[:3].copy()
+    nx, ny, nz = (int(d) for d in dims)
+    out = np.empty((nx, ny, nz, 4), np.float32)
+    _check(lib().oracle_grid_eval(_p(w), len(w), _p(c), np.float32(step), nx, ny, nz, int(x_offset), _p(out)))
+    return out
+
+
+def grid_eval_pymcubes(words, corner, step, dims):
+    """distance-only grid in the PyMCubes layout of grid_eval.cl:18: flat index
+    z + (x + (ny-1-y)*nx)*nz, i.e. array [ny (flipped)][nx][nz]."""
+    w = _f32(words)
+    c = _f32(corner)[:3].copy()
+    nx, ny, nz = (int(d) for d in dims)
+    out = np.empty((ny, nx, nz), np.float32)
+    _check(lib().oracle_grid_eval_pymcubes(_p(w), len(w), _p(c), np.float32(step), nx, ny, nz, _p(out)))
+    return out
+
+
+def subdivision_step(words, corner, step, threshold, dims):
+    """-> uint8 array [count][4] of (x, y, z, 0) in INDEX3 order."""
+    w = _f32(words)
+    c = _f32(corner)[:3].copy()
+    nx, ny, nz = (int(d) for d in dims)
+    counter = np.zeros(1, np.uint32)
+    lst = np.zeros((nx * ny * nz, 4), np.uint8)
+    _check(lib().oracle_subdivision_step(_p(w), len(w), _p(c), np.float32(step), np.float32(threshold),
+                                         nx, ny, nz, _p(counter, _u32p), _p(lst, _u8p)))
+    return lst[: int(counter[0])].copy()
+
+
+def mass_properties_step(words, corner, step, threshold, dims):
+    """-> (sums uint32[10] in order xx,xy,xz,x,yy,yz,y,zz,z,n ; list uint8[count][4])."""
+    w = _f32(words)
+    c = _f32(corner)[:3].copy()
+    nx, ny, nz = (int(d) for d in dims)
+    counter = np.zeros(1, np.uint32)
+    sums = np.zeros(10, np.uint32)
+    lst = np.zeros((nx * ny * nz, 4), np.uint8)
+    _check(lib().oracle_mass_properties_step(_p(w), len(w), _p(c), np.float32(step), np.float32(threshold),
+                                             nx, ny, nz, _p(sums, _u32p), _p(counter, _u32p), _p(lst, _u8p)))
+    return sums, lst[: int(counter[0])].copy()
+
+
+def math_probe(which, a, b=None):
+    a = _f32(a).ravel()
+    b = _f32(np.zeros_like(a) if b is None else b).ravel()
+    out = np.empty_like(a)
+    out2 = np.empty_like(a)
+    lib().oracle_math_probe(int(which), _p(a), _p(b), len(a), _p(out), _p(out2))
+    return out, out2

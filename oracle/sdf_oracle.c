@@ -1,0 +1,662 @@
+/* TEST INFRASTRUCTURE — CPU oracle for the codecad SDF hot path.  Not product code:
+ * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+ * reference legs may load this library.
+ *
+ * It is a plain-C restatement of the reference's OpenCL device code, consuming the
+ * reference's own float32 program words:
+ *   interpreter  /root/reference/codecad/nodes/codegen.py:17-63 (+ handlers :91-134)
+ *   opcodes      /root/reference/codecad/nodes/node.py:12-56
+ *   encoding     /root/reference/codecad/nodes/program.py:39-71
+ *   op library   /root/reference/codecad/shapes/{common,simple2d,simple3d,polygons2d,unsafe,gears}.cl
+ *                /root/reference/codecad/cl_util/util.cl:1-15
+ *   kernels      /root/reference/codecad/grid_eval.cl:2-34, subdivision.cl:12-30,
+ *                mass_properties.cl:7-56, cl_util/indexing.h:4
+ *
+ * Arithmetic: the canonical "cc-arith" of DESIGN.md (see cc_math_ref.h).  Parameter-
+ * only sub-expressions (quaternion -> 3x3 matrix, polygon edge tables, gear
+ * constants) are evaluated once per instruction, in double where stated, exactly as
+ * the device program loader does; everything per point is fp32.
+ *
+ * Pinning: no OpenCL runtime exists in the build container or on the GPU box, so
+ * bit-level parity with a vendor OpenCL build is UNPINNED.  The oracle is pinned
+ * (a) against every known-answer test the reference holds for this path
+ * (tests/test_oracle_known_answers.py: tests/test_mass_properties.py:16-108,
+ * tests/test_subdivision.py:110-161, tests/test_dsdf.py:113-192 of the reference) and
+ * (b) against oracle/_ref, the reference's own .cl sources compiled for the CPU
+ * (oracle/build_ref.py), within the north-star tolerance.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "cc_math_ref.h"
+
+#define REGISTER_COUNT 512
+
+typedef struct { float x, y, z, w; } v4;
+
+enum {
+    OP_RETURN = 0, OP_STORE, OP_LOAD, OP_RECTANGLE, OP_CIRCLE, OP_REGULAR_POLYGON2D,
+    OP_POLYGON2D, OP_SPHERE, OP_HALF_SPACE, OP_REVOLUTION_TO, OP_TWIST_REVOLUTION_TO,
+    OP_INITIAL_TRANSFORMATION_TO, OP_TRANSFORMATION_TO, OP_TRANSFORMATION_FROM,
+    OP_MIRROR, OP_SYMMETRICAL_TO, OP_OFFSET, OP_SHELL, OP_REPETITION,
+    OP_CIRCULAR_REPETITION_TO, OP_CIRCULAR_REPETITION_FROM, OP_INVOLUTE_GEAR,
+    OP_EXTRUSION, OP_REVOLUTION_FROM, OP_TWIST_REVOLUTION_FROM, OP_SYMMETRICAL_FROM,
+    OP_UNION, OP_INTERSECTION, OP_SUBTRACTION, OP_COUNT
+};
+
+/* parameter words per opcode (node.py:18-52); -1 = polygon2d (1 + 2n) */
+static const int NPARAMS[OP_COUNT] = {0, 0, 0, 2, 1, 2, -1, 1, 0, 0, 2, 7, 7, 4, 0, 0,
+                                      1, 1, 3, 1, 1, 2, 1, 0, 3, 0, 1, 1, 1};
+
+typedef struct {
+    int op;
+    int reg;
+    const float *p; /* parameters inside the caller's word array */
+    float k[16];    /* per-instruction constants derived from the parameters */
+    float *edges;   /* polygon2d: 5 floats per edge (px, py, dx, dy, 1/|d|^2) */
+    int n;
+} ins_t;
+
+typedef struct {
+    ins_t *ins;
+    int count;
+    long flops; /* not used by parity, kept for the bench's executed-flop estimate */
+} prog_t;
+
+/* ---- per-instruction constants (mirrors the device loader) -------------------- */
+
+/* quaternion (x,y,z,w) -> row-major 3x3 of  v -> 2 v(v.p) + 2 w (v x p) + (w^2-v.v) p
+ * (common.cl:1-6), in double, optionally divided by |q|^2 (common.cl:100-110). */
+static void quat_matrix(const float *q, int divide_by_scale, float *m, float *scale)
+{
+    double x = q[0], y = q[1], z = q[2], w = q[3];
+    double k = w * w - (x * x + y * y + z * z);
+    double d[9];
+    d[0] = 2.0 * (x * x) + k;
+    d[1] = 2.0 * (x * y - w * z);
+    d[2] = 2.0 * (x * z + w * y);
+    d[3] = 2.0 * (x * y + w * z);
+    d[4] = 2.0 * (y * y) + k;
+    d[5] = 2.0 * (y * z - w * x);
+    d[6] = 2.0 * (x * z - w * y);
+    d[7] = 2.0 * (y * z + w * x);
+    d[8] = 2.0 * (z * z) + k;
+    double s = (x * x + y * y) + (z * z + w * w);
+    for (int i = 0; i < 9; ++i)
+        m[i] = (float)(divide_by_scale ? d[i] / s : d[i]);
+    if (scale) *scale = (float)s;
+}
+
+static int prepare(const float *words, int n_words, prog_t *prog)
+{
+    int cap = 64, count = 0, pc = 0;
+    ins_t *ins = (ins_t *)calloc((size_t)cap, sizeof(ins_t));
+    for (;;) {
+        if (pc >= n_words) { free(ins); return -1; }
+        float wf = words[pc];
+        if (!(wf >= 0.0f) || wf >= (float)(OP_COUNT * REGISTER_COUNT)) { free(ins); return -2; }
+        unsigned instruction = (unsigned)wf;
+        int op = (int)(instruction / REGISTER_COUNT);
+        int reg = (int)(instruction % REGISTER_COUNT);
+        int np = NPARAMS[op];
+        if (np < 0) {
+            if (pc + 1 >= n_words) { free(ins); return -1; }
+            np = 1 + 2 * (int)words[pc + 1];
+        }
+        if (pc + 1 + np > n_words) { free(ins); return -1; }
+        if (count == cap) {
+            cap *= 2;
+            ins = (ins_t *)realloc(ins, (size_t)cap * sizeof(ins_t));
+        }
+        ins_t *I = &ins[count++];
+        memset(I, 0, sizeof(*I));
+        I->op = op;
+        I->reg = reg;
+        I->p = words + pc + 1;
+        const float *p = I->p;
+        switch (op) {
+        case OP_INITIAL_TRANSFORMATION_TO:
+        case OP_TRANSFORMATION_TO:
+            quat_matrix(p, 0, I->k, NULL);
+            I->k[9] = p[4]; I->k[10] = p[5]; I->k[11] = p[6];
+            break;
+        case OP_TRANSFORMATION_FROM:
+            quat_matrix(p, 1, I->k, &I->k[9]);
+            break;
+        case OP_REGULAR_POLYGON2D:
+            I->k[0] = p[1] * (float)sin((double)p[0]); /* r * sin(pi/n)  simple2d.cl:25 */
+            I->k[1] = p[1] * (float)cos((double)p[0]); /* r * cos(pi/n)  simple2d.cl:45 */
+            I->k[2] = 2.0f * p[0];
+            break;
+        case OP_CIRCULAR_REPETITION_TO:
+        case OP_CIRCULAR_REPETITION_FROM:
+            I->k[2] = 2.0f * p[0];
+            break;
+        case OP_INVOLUTE_GEAR: {
+            float pa = p[1];
+            I->k[0] = (float)cos((double)pa);                 /* baseRadius   gears.cl:2 */
+            I->k[1] = cc_div(CC_PI_F, p[0]);                  /* toothAngle   gears.cl:3 */
+            I->k[2] = (I->k[1] * 0.5f + (float)tan((double)pa)) - pa; /* gears.cl:6 */
+            I->k[3] = 2.0f * I->k[1];
+            I->k[4] = I->k[0] * I->k[0];
+            break;
+        }
+        case OP_TWIST_REVOLUTION_FROM: {
+            float minorR = p[0], r = p[1], twist = p[2];
+            float arg = fminf(CC_PI_F, cc_div(CC_PI_2_F * CC_PI_2_F, fabsf(twist)));
+            float lip = cc_div(((r - minorR) * 2.0f) * (float)sin((double)arg), minorR);
+            I->k[0] = fminf(1.0f, lip);  /* simple3d.cl:86-88 */
+            I->k[1] = 0.05f * r;         /* wrapperPadding simple3d.cl:70 */
+            break;
+        }
+        case OP_POLYGON2D: {
+            int n = (int)p[0];
+            I->n = n;
+            I->edges = (float *)malloc(sizeof(float) * 5 * (size_t)(n > 0 ? n : 1));
+            for (int i = 0; i < n; ++i) {
+                int j = (i + n - 1) % n; /* previous point: polygons2d.cl:13,17-18 */
+                float px = p[1 + 2 * j], py = p[2 + 2 * j];
+                float cx = p[1 + 2 * i], cy = p[2 + 2 * i];
+                float dx = cx - px, dy = cy - py;
+                float *e = I->edges + 5 * i;
+                e[0] = px; e[1] = py; e[2] = dx; e[3] = dy;
+                e[4] = cc_rcp(cc_fma(dx, dx, dy * dy));
+            }
+            break;
+        }
+        default:
+            break;
+        }
+        pc += 1 + np;
+        if (op == OP_RETURN) break;
+    }
+    prog->ins = ins;
+    prog->count = count;
+    return 0;
+}
+
+static void release(prog_t *prog)
+{
+    for (int i = 0; i < prog->count; ++i) free(prog->ins[i].edges);
+    free(prog->ins);
+    prog->ins = NULL;
+}
+
+/* ---- op library ----------------------------------------------------------------- */
+
+static inline v4 mk(float x, float y, float z, float w) { v4 r = {x, y, z, w}; return r; }
+static inline v4 neg(v4 a) { return mk(-a.x, -a.y, -a.z, -a.w); }
+
+/* common.cl:15-31 */
+static inline v4 perpendicular_intersection(v4 a, v4 b)
+{
+    if (a.w > 0.0f && b.w > 0.0f) {
+        float dist = cc_len2(a.w, b.w);
+        float inv = cc_rcp(dist);
+        float m1 = a.w * inv, m2 = b.w * inv;
+        return mk(cc_fma(a.x, m1, b.x * m2), cc_fma(a.y, m1, b.y * m2),
+                  cc_fma(a.z, m1, b.z * m2), dist);
+    }
+    return (a.w > b.w) ? a : b;
+}
+
+/* common.cl:33-43 */
+static inline v4 slab_x(float h, v4 p) { return mk(copysignf(1.0f, p.x), 0, 0, fabsf(p.x) - h); }
+static inline v4 slab_y(float h, v4 p) { return mk(0, copysignf(1.0f, p.y), 0, fabsf(p.y) - h); }
+static inline v4 slab_z(float h, v4 p) { return mk(0, 0, copysignf(1.0f, p.z), fabsf(p.z) - h); }
+
+/* common.cl:45-64 */
+static inline v4 rounded_union(float r, v4 o1, v4 o2)
+{
+    if (r >= 0.0f) {
+        float c = cc_dot3(o1.x, o1.y, o1.z, o2.x, o2.y, o2.z);
+        float x1 = r - o1.w, x2 = r - o2.w;
+        if (c * x1 < x2 && c * x2 < x1) {
+            float num = cc_fma(-((2.0f * c) * x1), x2, cc_fma(x1, x1, x2 * x2));
+            float den = cc_fma(-c, c, 1.0f);
+            float d = r - cc_sqrt(cc_div(num, den));
+            return mk(0, 0, 0, d);
+        }
+    }
+    return (o1.w < o2.w) ? o1 : o2;
+}
+
+static inline v4 apply_matrix(const float *m, float x, float y, float z, float ox, float oy, float oz)
+{
+    return mk(cc_fma(m[0], x, cc_fma(m[1], y, cc_fma(m[2], z, ox))),
+              cc_fma(m[3], x, cc_fma(m[4], y, cc_fma(m[5], z, oy))),
+              cc_fma(m[6], x, cc_fma(m[7], y, cc_fma(m[8], z, oz))), 0.0f);
+}
+
+/* simple2d.cl:16-46 */
+static inline v4 regular_polygon2d(const ins_t *I, v4 co)
+{
+    float piOverN = I->p[0], r = I->p[1];
+    float len = cc_len2(co.x, co.y);
+    float alpha = (cc_atan2(co.y, co.x) + CC_2PI_F) + piOverN;
+    int side = (int)cc_floor(cc_div(alpha, I->k[2]));
+    float t = (float)(side * 2) * piOverN;
+    float modAlpha = (alpha - t) - piOverN;
+    float s, c;
+    cc_sincos(modAlpha, &s, &c);
+    if (fabsf(s * len) > I->k[0]) {
+        float ny, nx;
+        cc_sincos(cc_fma(cc_sign(s), piOverN, t), &ny, &nx);
+        float dx = co.x - nx * r, dy = co.y - ny * r;
+        float dist = cc_len2(dx, dy);
+        if (dist > 0.0f) {
+            float inv = cc_rcp(dist);
+            return mk(dx * inv, dy * inv, 0, dist);
+        }
+    }
+    float dy, dx;
+    cc_sincos(t, &dy, &dx);
+    return mk(dx, dy, 0, cc_fma(len, c, -I->k[1]));
+}
+
+/* polygons2d.cl:1-74 */
+static inline v4 polygon2d(const ins_t *I, v4 co)
+{
+    float nnx = 0.0f, nny = 0.0f, nearest = INFINITY, outside = 1.0f;
+    int nearest_is_vertex = 0;
+    for (int i = 0; i < I->n; ++i) {
+        const float *e = I->edges + 5 * i;
+        float px = e[0], py = e[1], dx = e[2], dy = e[3];
+        float cy = I->p[2 + 2 * i];
+        float tqx = co.x - px, tqy = co.y - py;
+        float snx = -dy, sny = dx;
+        if (((py < co.y) != (cy < co.y)) && (dy * cc_fma(snx, tqx, sny * tqy) > 0.0f))
+            outside = -outside;
+        float t = cc_fma(dx, tqx, dy * tqy) * e[4];
+        if (t > 1.0f) continue;
+        float cnx, cny, cd;
+        int civ;
+        if (t >= 0.0f) {
+            float tcx = cc_fma(-t, dx, tqx), tcy = cc_fma(-t, dy, tqy);
+            cd = cc_fma(tcx, tcx, tcy * tcy);
+            cnx = snx; cny = sny; civ = 0;
+        } else {
+            cnx = tqx; cny = tqy;
+            cd = cc_fma(cnx, cnx, cny * cny);
+            civ = cd > 1.1920928955078125e-7f; /* FLT_EPSILON */
+            if (!civ) { cnx = snx; cny = sny; }
+        }
+        if (cd < nearest) { nearest = cd; nnx = cnx; nny = cny; nearest_is_vertex = civ; }
+    }
+    float distance = outside * cc_sqrt(nearest);
+    float inv = nearest_is_vertex ? cc_rcp(distance) : cc_rcp(cc_len2(nnx, nny));
+    return mk(nnx * inv, nny * inv, 0, distance);
+}
+
+/* gears.cl:1-42 */
+static inline v4 involute_gear(const ins_t *I, v4 co)
+{
+    float baseRadius = I->k[0], toothAngle = I->k[1], halfTooth = I->k[2];
+    float len = cc_len2(co.x, co.y);
+    float alpha = cc_atan2(co.y, co.x);
+    float wrapped = cc_fmod_pos(alpha + CC_2PI_F, I->k[3]);
+    float d = fabsf(wrapped - toothAngle);
+    float involuteAlpha = halfTooth - d;
+    if (len < baseRadius) {
+        float inv = cc_rcp(len);
+        float nx = co.y * inv, ny = -(co.x * inv);
+        if (wrapped > toothAngle) { nx = -nx; ny = -ny; }
+        return mk(nx, ny, 0, (d - halfTooth) * len);
+    }
+    float phi = involuteAlpha + cc_acos(cc_div(baseRadius, len));
+    float base = alpha - involuteAlpha;
+    float normalAngle = (wrapped < toothAngle) ? (CC_PI_F - phi) - base : phi - base;
+    float nx, ny;
+    cc_sincos(normalAngle, &nx, &ny);
+    float distance = cc_fma(-baseRadius, phi, cc_sqrt(cc_fma(len, len, -I->k[4])));
+    return mk(nx, ny, 0, distance);
+}
+
+/* simple3d.cl:42-51 */
+static inline v4 twist_revolution_to(const ins_t *I, v4 co)
+{
+    float r = I->p[0], twist = I->p[1];
+    float alpha = cc_fmod_pos(cc_atan2(co.z, co.x) + CC_PI_F, CC_2PI_F);
+    float beta = cc_div(twist * alpha, CC_2PI_F);
+    float ipx = cc_len2(co.x, co.z) - r, ipy = co.y;
+    float s, c;
+    cc_sincos(-beta, &s, &c);
+    return mk(cc_fma(c, ipx, -(s * ipy)), cc_fma(s, ipx, c * ipy), 0, 0);
+}
+
+/* simple3d.cl:53-97 */
+static inline v4 twist_revolution_from(const ins_t *I, v4 inPlane, v4 co)
+{
+    float minorR = I->p[0], r = I->p[1], twist = I->p[2];
+    float ad = cc_len2(co.x, co.z);
+    float ipx = ad - r, ipy = co.y;
+    float icd = cc_len2(ipx, ipy);
+    float wd = icd - minorR;
+    float bound, dx, dy;
+    if (ad == 0.0f) return mk(1, 0, 0, r - minorR);
+    if (wd > I->k[1]) {
+        float inv = cc_rcp(icd);
+        bound = wd; dx = ipx * inv; dy = ipy * inv;
+    } else {
+        float alpha = cc_fmod_pos(cc_atan2(co.z, co.x) + CC_PI_F, CC_2PI_F);
+        float beta = cc_div(twist * alpha, CC_2PI_F);
+        float s, c;
+        cc_sincos(beta, &s, &c);
+        bound = inPlane.w * I->k[0];
+        dx = cc_fma(c, inPlane.x, -(s * inPlane.y));
+        dy = cc_fma(s, inPlane.x, c * inPlane.y);
+    }
+    float mult = cc_div(dx, ad);
+    return mk(co.x * mult, dy, co.z * mult, bound);
+}
+
+/* unsafe.cl:8-23 */
+static inline v4 circular_repetition_to(const ins_t *I, v4 co)
+{
+    float piOverN = I->p[0];
+    float len = cc_len2(co.x, co.y);
+    float alpha = (cc_atan2(co.y, co.x) + CC_2PI_F) + piOverN;
+    int side = (int)cc_floor(cc_div(alpha, I->k[2]));
+    float modAlpha = (alpha - (float)(side * 2) * piOverN) - piOverN;
+    float s, c;
+    cc_sincos(modAlpha, &s, &c);
+    return mk(len * c, len * s, co.z, 0);
+}
+
+static inline v4 circular_repetition_from(const ins_t *I, v4 dist, v4 co)
+{
+    float piOverN = I->p[0];
+    float alpha = (cc_atan2(co.y, co.x) + CC_2PI_F) + piOverN;
+    int side = (int)cc_floor(cc_div(alpha, I->k[2]));
+    float s, c;
+    cc_sincos((float)(side * 2) * piOverN, &s, &c);
+    return mk(cc_fma(c, dist.x, -(s * dist.y)), cc_fma(s, dist.x, c * dist.y), dist.z, dist.w);
+}
+
+/* ---- interpreter: codegen.py:17-63 ---------------------------------------------- */
+
+static v4 evaluate(const prog_t *prog, float px, float py, float pz)
+{
+    v4 registers[REGISTER_COUNT];
+    v4 last = mk(0, 0, 0, 0);
+    const ins_t *I = prog->ins;
+    for (;; ++I) {
+        const float *p = I->p;
+#define in2 (registers[I->reg]) /* second operand of arity-2 ops / source of _load */
+        switch (I->op) {
+        case OP_RETURN: return last;
+        case OP_STORE: registers[I->reg] = last; break;
+        case OP_LOAD: last = in2; break;
+        case OP_RECTANGLE: /* simple2d.cl:1-4 */
+            last = perpendicular_intersection(slab_x(p[0], last), slab_y(p[1], last));
+            break;
+        case OP_CIRCLE: { /* simple2d.cl:6-14 */
+            float len = cc_len2(last.x, last.y);
+            if (len == 0.0f) last = mk(1, 0, 0, len - p[0]);
+            else { float inv = cc_rcp(len); last = mk(last.x * inv, last.y * inv, 0, len - p[0]); }
+            break;
+        }
+        case OP_REGULAR_POLYGON2D: last = regular_polygon2d(I, last); break;
+        case OP_POLYGON2D: last = polygon2d(I, last); break;
+        case OP_SPHERE: { /* simple3d.cl:1-12 */
+            float len = cc_len3(last.x, last.y, last.z);
+            if (len == 0.0f) last = mk(1, 0, 0, len - p[0]);
+            else { float inv = cc_rcp(len); last = mk(last.x * inv, last.y * inv, last.z * inv, len - p[0]); }
+            break;
+        }
+        case OP_HALF_SPACE: last = mk(0, -1, 0, -last.y); break; /* simple3d.cl:14-16 */
+        case OP_REVOLUTION_TO: last = mk(cc_len2(last.x, last.z), last.y, 0, 0); break; /* :23-26 */
+        case OP_TWIST_REVOLUTION_TO: last = twist_revolution_to(I, last); break;
+        case OP_INITIAL_TRANSFORMATION_TO: /* common.cl:78-87 */
+            last = apply_matrix(I->k, px, py, pz, I->k[9], I->k[10], I->k[11]);
+            break;
+        case OP_TRANSFORMATION_TO: /* common.cl:89-98 */
+            last = apply_matrix(I->k, last.x, last.y, last.z, I->k[9], I->k[10], I->k[11]);
+            break;
+        case OP_TRANSFORMATION_FROM: { /* common.cl:100-110 */
+            const float *m = I->k;
+            float x = last.x, y = last.y, z = last.z;
+            last = mk(cc_fma(m[0], x, cc_fma(m[1], y, m[2] * z)),
+                      cc_fma(m[3], x, cc_fma(m[4], y, m[5] * z)),
+                      cc_fma(m[6], x, cc_fma(m[7], y, m[8] * z)), last.w * I->k[9]);
+            break;
+        }
+        case OP_MIRROR: last.x = -last.x; break;          /* common.cl:112-114 */
+        case OP_SYMMETRICAL_TO: last.x = fabsf(last.x); break; /* :116-118 */
+        case OP_OFFSET: last.w = last.w - p[0]; break;    /* :124-126 */
+        case OP_SHELL: /* :128-131 */
+            if (!(last.w >= 0.0f)) last = neg(last);
+            last.w = last.w - p[0];
+            break;
+        case OP_REPETITION: /* unsafe.cl:1-6 */
+            last = mk(cc_remainder(last.x, p[0]), cc_remainder(last.y, p[1]),
+                      cc_remainder(last.z, p[2]), 0);
+            break;
+        case OP_CIRCULAR_REPETITION_TO: last = circular_repetition_to(I, last); break;
+        case OP_CIRCULAR_REPETITION_FROM: last = circular_repetition_from(I, last, in2); break;
+        case OP_INVOLUTE_GEAR: last = involute_gear(I, last); break;
+        case OP_EXTRUSION: /* simple3d.cl:18-21 */
+            last = perpendicular_intersection(slab_z(p[0], in2), last);
+            break;
+        case OP_REVOLUTION_FROM: { /* simple3d.cl:28-39 */
+            float cx = in2.x, cz = in2.z;
+            float len = cc_len2(cx, cz), mult;
+            if (len == 0.0f) { cx = 1.0f; mult = last.x; }
+            else mult = cc_div(last.x, len);
+            last = mk(cx * mult, last.y, cz * mult, last.w);
+            break;
+        }
+        case OP_TWIST_REVOLUTION_FROM: last = twist_revolution_from(I, last, in2); break;
+        case OP_SYMMETRICAL_FROM: /* common.cl:120-122 */
+            if (in2.x < 0.0f) last.x = -last.x;
+            break;
+        case OP_UNION: last = rounded_union(p[0], last, in2); break;              /* :66-68 */
+        case OP_INTERSECTION: last = neg(rounded_union(p[0], neg(last), neg(in2))); break; /* :70-72 */
+        case OP_SUBTRACTION: last = neg(rounded_union(p[0], neg(last), in2)); break;       /* :74-76 */
+        default: return mk(NAN, NAN, NAN, NAN);
+        }
+    }
+#undef in2
+}
+
+static inline float grid_coord(float corner, float step, unsigned i)
+{
+    /* grid_eval.cl:13,31  corner + step * convert_float(i), contracted to one FMA */
+    return cc_fma(step, (float)i, corner);
+}
+
+/* ---- exported entry points -------------------------------------------------------- */
+
+int oracle_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+void oracle_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
+/* returns the number of instructions, <0 on a malformed program */
+int oracle_validate(const float *words, int n_words)
+{
+    prog_t prog;
+    int rc = prepare(words, n_words, &prog);
+    if (rc < 0) return rc;
+    rc = prog.count;
+    release(&prog);
+    return rc;
+}
+
+/* evaluate at arbitrary points: pts[n][3] -> out[n][4] */
+int oracle_evaluate_points(const float *words, int n_words, const float *pts, long n, float *out)
+{
+    prog_t prog;
+    int rc = prepare(words, n_words, &prog);
+    if (rc < 0) return rc;
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < n; ++i) {
+        v4 r = evaluate(&prog, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
+        memcpy(out + 4 * i, &r, sizeof(r));
+    }
+    release(&prog);
+    return 0;
+}
+
+/* grid_eval.cl:23-34; the x index of the launch is x_offset + [0, nx) so that a
+ * slab of a larger grid evaluates bit-identically to the unsharded launch. */
+int oracle_grid_eval(const float *words, int n_words, const float *corner, float step,
+                     int nx, int ny, int nz, int x_offset, float *out)
+{
+    prog_t prog;
+    int rc = prepare(words, n_words, &prog);
+    if (rc < 0) return rc;
+#pragma omp parallel for collapse(2) schedule(dynamic, 4)
+    for (int x = 0; x < nx; ++x)
+        for (int y = 0; y < ny; ++y) {
+            float px = grid_coord(corner[0], step, (unsigned)(x + x_offset));
+            float py = grid_coord(corner[1], step, (unsigned)y);
+            for (int z = 0; z < nz; ++z) {
+                v4 r = evaluate(&prog, px, py, grid_coord(corner[2], step, (unsigned)z));
+                size_t idx = (size_t)z + (size_t)nz * ((size_t)y + (size_t)ny * (size_t)x);
+                memcpy(out + 4 * idx, &r, sizeof(r));
+            }
+        }
+    release(&prog);
+    return 0;
+}
+
+/* grid_eval.cl:2-21 (distance only, y-flipped PyMCubes layout) */
+int oracle_grid_eval_pymcubes(const float *words, int n_words, const float *corner, float step,
+                              int nx, int ny, int nz, float *out)
+{
+    prog_t prog;
+    int rc = prepare(words, n_words, &prog);
+    if (rc < 0) return rc;
+#pragma omp parallel for collapse(2) schedule(dynamic, 4)
+    for (int x = 0; x < nx; ++x)
+        for (int y = 0; y < ny; ++y) {
+            float px = grid_coord(corner[0], step, (unsigned)x);
+            float py = grid_coord(corner[1], step, (unsigned)y);
+            for (int z = 0; z < nz; ++z) {
+                v4 r = evaluate(&prog, px, py, grid_coord(corner[2], step, (unsigned)z));
+                size_t idx = (size_t)z + ((size_t)x + (size_t)(ny - y - 1) * (size_t)nx) * (size_t)nz;
+                out[idx] = r.w;
+            }
+        }
+    release(&prog);
+    return 0;
+}
+
+/* subdivision.cl:12-30.  The reference appends with atomic_inc (arbitrary order);
+ * the oracle emits in INDEX3 order (x slowest, z fastest), which is also the order
+ * of the device's prefix-sum compaction. list = uchar4 (x, y, z, 0). */
+int oracle_subdivision_step(const float *words, int n_words, const float *corner, float step,
+                            float threshold, int nx, int ny, int nz, uint32_t *counter,
+                            uint8_t *list)
+{
+    prog_t prog;
+    int rc = prepare(words, n_words, &prog);
+    if (rc < 0) return rc;
+    size_t total = (size_t)nx * ny * nz;
+    uint8_t *flag = (uint8_t *)malloc(total);
+#pragma omp parallel for collapse(2) schedule(dynamic, 4)
+    for (int x = 0; x < nx; ++x)
+        for (int y = 0; y < ny; ++y) {
+            float px = grid_coord(corner[0], step, (unsigned)x);
+            float py = grid_coord(corner[1], step, (unsigned)y);
+            for (int z = 0; z < nz; ++z) {
+                float v = evaluate(&prog, px, py, grid_coord(corner[2], step, (unsigned)z)).w;
+                flag[(size_t)z + (size_t)nz * ((size_t)y + (size_t)ny * (size_t)x)] =
+                    (v > -threshold && v < threshold);
+            }
+        }
+    uint32_t c = *counter; /* list[atomic_inc(counter)]: append after existing entries */
+    for (int x = 0; x < nx; ++x)
+        for (int y = 0; y < ny; ++y)
+            for (int z = 0; z < nz; ++z)
+                if (flag[(size_t)z + (size_t)nz * ((size_t)y + (size_t)ny * (size_t)x)]) {
+                    list[4 * c + 0] = (uint8_t)x; list[4 * c + 1] = (uint8_t)y;
+                    list[4 * c + 2] = (uint8_t)z; list[4 * c + 3] = 0;
+                    ++c;
+                }
+    *counter = c;
+    free(flag);
+    release(&prog);
+    return 0;
+}
+
+/* mass_properties.cl:7-56.  sums (uint32, wrap-around like the device) in the
+ * reference's order xx,xy,xz,x,yy,yz,y,zz,z,n (:34-41). */
+int oracle_mass_properties_step(const float *words, int n_words, const float *corner, float step,
+                                float threshold, int nx, int ny, int nz, uint32_t *sums,
+                                uint32_t *counter, uint8_t *list)
+{
+    prog_t prog;
+    int rc = prepare(words, n_words, &prog);
+    if (rc < 0) return rc;
+    size_t total = (size_t)nx * ny * nz;
+    uint8_t *flag = (uint8_t *)malloc(total);
+#pragma omp parallel for collapse(2) schedule(dynamic, 4)
+    for (int x = 0; x < nx; ++x)
+        for (int y = 0; y < ny; ++y) {
+            float px = grid_coord(corner[0], step, (unsigned)x);
+            float py = grid_coord(corner[1], step, (unsigned)y);
+            for (int z = 0; z < nz; ++z) {
+                float v = evaluate(&prog, px, py, grid_coord(corner[2], step, (unsigned)z)).w;
+                uint8_t f = 0;
+                if (v <= -threshold) f = 1;
+                else if (v < threshold) f = 2;
+                flag[(size_t)z + (size_t)nz * ((size_t)y + (size_t)ny * (size_t)x)] = f;
+            }
+        }
+    uint32_t c = *counter, s[10] = {0};
+    for (int x = 0; x < nx; ++x)
+        for (int y = 0; y < ny; ++y)
+            for (int z = 0; z < nz; ++z) {
+                uint8_t f = flag[(size_t)z + (size_t)nz * ((size_t)y + (size_t)ny * (size_t)x)];
+                if (f == 1) {
+                    uint32_t co[4] = {(uint32_t)x, (uint32_t)y, (uint32_t)z, 1u};
+                    int i = 0;
+                    for (int j = 0; j < 4; ++j)
+                        for (int k = j; k < 4; ++k) s[i++] += co[j] * co[k];
+                } else if (f == 2) {
+                    list[4 * c + 0] = (uint8_t)x; list[4 * c + 1] = (uint8_t)y;
+                    list[4 * c + 2] = (uint8_t)z; list[4 * c + 3] = 0;
+                    ++c;
+                }
+            }
+    for (int i = 0; i < 10; ++i) sums[i] += s[i];
+    *counter = c;
+    free(flag);
+    release(&prog);
+    return 0;
+}
+
+/* scalar access to the canonical math layer, for tests/test_oracle_math.py */
+void oracle_math_probe(int which, const float *a, const float *b, long n, float *out, float *out2)
+{
+    for (long i = 0; i < n; ++i) {
+        switch (which) {
+        case 0: out[i] = cc_atan2(a[i], b[i]); break;
+        case 1: cc_sincos(a[i], &out[i], &out2[i]); break;
+        case 2: out[i] = cc_acos(a[i]); break;
+        case 3: out[i] = cc_fmod_pos(a[i], b[i]); break;
+        case 4: out[i] = cc_remainder(a[i], b[i]); break;
+        default: out[i] = NAN;
+        }
+    }
+}

@@ -1,0 +1,144 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/scenes.npz from the reference's own Python front end.
+
+Runs ONLY in the build container (needs /root/reference, which does not exist on
+the GPU box).  It imports the reference's shape API and node compiler
+(codecad/nodes/program.py:74-76 `make_program`) with the import-time stubs in
+tools/refstub/ standing in for pyopencl / py-flags, and stores for every scene:
+
+  <name>.words      float32 program words exactly as the reference emits them
+  <name>.meta       float64 [dimension, bbox.a.xyz, bbox.b.xyz, feature_size]
+
+`random.seed(0)` is set immediately before every make_program() because the
+reference scheduler shuffles with the unseeded global RNG
+(codecad/nodes/scheduler.py:165-178, SURVEY.md §7 hard part 4).
+
+Usage:  python tools/make_fixtures.py            (writes tests/golden/scenes.npz)
+"""
+import math
+import os
+import random
+import sys
+import warnings
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+REF = os.environ.get("CODECAD_REFERENCE", "/root/reference")
+
+sys.path.insert(0, os.path.join(HERE, "refstub"))
+sys.path.insert(1, REF)
+sys.path.insert(2, os.path.join(REF, "examples"))
+sys.path.insert(3, os.path.join(REF, "tests"))
+warnings.simplefilter("ignore")
+
+import numpy  # noqa: E402
+
+import codecad  # noqa: E402
+import codecad.shapes as s  # noqa: E402
+from codecad.shapes import simple2d, polygons2d  # noqa: E402
+
+# SURVEY.md §7 hard part 8: examples/airfoil.py is broken at reference HEAD
+# (shapes/airfoils.py:9 names simple2d.Polygon2D).  Harness-side alias only.
+simple2d.Polygon2D = polygons2d.Polygon2D
+
+
+def synthetic_deep_csg(n=500, seed=1234):
+    """BASELINE.json config 5 / SURVEY.md §8(d) C5: n rounded boxes, rotated and
+    translated, joined by a balanced binary tree of smooth unions (r=0.5)."""
+    rng = random.Random(seed)
+    parts = []
+    for _ in range(n):
+        b = s.box(rng.uniform(2, 8), rng.uniform(2, 8), rng.uniform(2, 8))
+        b = b.offset(rng.uniform(0.1, 0.5))
+        axis = (rng.uniform(-1, 1), rng.uniform(-1, 1), rng.uniform(-1, 1))
+        b = b.rotated(axis, rng.uniform(0, 360))
+        b = b.translated(rng.uniform(-50, 50), rng.uniform(-50, 50), rng.uniform(-50, 50))
+        parts.append(b)
+    while len(parts) > 1:
+        nxt = []
+        for i in range(0, len(parts) - 1, 2):
+            nxt.append(s.union([parts[i], parts[i + 1]], r=0.5))
+        if len(parts) % 2:
+            nxt.append(parts[-1])
+        parts = nxt
+    return parts[0]
+
+
+def collect():
+    scenes = {}
+
+    # --- the five BASELINE.json configs -------------------------------------
+    import csg_example
+    import menger_sponge
+    import airfoil
+    import planetary
+
+    scenes["cfg_csg_example"] = csg_example.o
+    scenes["cfg_menger_sponge"] = menger_sponge.o
+    scenes["cfg_airfoil"] = airfoil.o
+    scenes["cfg_planetary"] = planetary.Planetary(11, 60, 13, 41, 18, 53).make_assembly().shape()
+    scenes["cfg_synthetic500"] = synthetic_deep_csg(500)
+    scenes["cfg_synthetic32"] = synthetic_deep_csg(32)
+
+    # --- tests/data.py shapes (tests/test_dsdf.py) ---------------------------
+    import data
+
+    for k, v in sorted(data.shapes_2d.items()):
+        scenes["dsdf2d_" + k] = v
+    for k, v in sorted(data.shapes_3d.items()):
+        scenes["dsdf3d_" + k] = v
+
+    # --- tests/test_mass_properties.py:16-96 ---------------------------------
+    hemi = s.sphere(r=2) - s.half_space()
+    scenes["mp_unit_box"] = s.box(1)
+    scenes["mp_cylinder"] = s.cylinder(h=2, r=4, symmetrical=False)
+    scenes["mp_sphere"] = s.sphere(d=2)
+    scenes["mp_two_boxes"] = s.box(2).translated(-15, 0, 0) + s.box(2).translated(15, 0, 0)
+    scenes["mp_hemisphere"] = hemi
+    scenes["mp_translated_sphere"] = s.sphere(d=2).translated(10, 11, 7)
+    scenes["mp_translated_and_rotated_hemisphere"] = hemi.translated(2, 0, 0).rotated((1, 0, 0), 90)
+    scenes["mp_not_hammer"] = s.box(4).translated(0, 0, 2) + s.box(2, 2, 9).translated(0, 0, -3.5)
+    scenes["mp_drunk_box"] = s.box(2, 3, 5).rotated((7, 11, 13), 17)
+
+    # --- tests/test_subdivision.py:110-161 -----------------------------------
+    scenes["sub_box10"] = s.box(10)
+    res, gs = 0.1, 8
+    step = res * (gs - 1)
+    scenes["sub_circle"] = s.circle(gs * step - res)
+
+    # --- a few extras exercising ops the above do not ------------------------
+    scenes["x_shell_sphere"] = s.sphere(d=6).shell(0.5)
+    scenes["x_smooth_isect"] = s.intersection([s.box(4), s.sphere(d=5)], r=0.4)
+    scenes["x_scaled_rot"] = s.box(1, 2, 3).scaled(1.7).rotated((1, 1, 0), 33).translated(1, 2, 3)
+    scenes["x_twist"] = s.rectangle(2, 1).revolved(4, 90)
+    scenes["x_gear3d"] = s.gears.InvoluteGear(13, 1.0).extruded(2)
+    scenes["x_repetition"] = codecad.shapes.unsafe.Repetition(s.sphere(d=1), (2, 2, None)) & s.box(7, 7, 2)
+    return scenes
+
+
+def main():
+    out = {}
+    scenes = collect()
+    for name, shape in scenes.items():
+        random.seed(0)
+        words = codecad.nodes.make_program(shape)
+        assert words.dtype == numpy.float32
+        box = shape.bounding_box()
+        try:
+            fs = float(shape.feature_size())
+        except Exception:  # noqa: BLE001 - some shapes have no feature size
+            fs = float("nan")
+        meta = numpy.array(
+            [shape.dimension(), box.a.x, box.a.y, box.a.z, box.b.x, box.b.y, box.b.z, fs],
+            dtype=numpy.float64,
+        )
+        out[name + ".words"] = words
+        out[name + ".meta"] = meta
+        print("%-46s dim %d  %5d words  bbox %s .. %s" % (name, shape.dimension(), len(words), box.a, box.b))
+    path = os.path.join(REPO, "tests", "golden", "scenes.npz")
+    numpy.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()
