@@ -1,0 +1,150 @@
+"""ctypes binding of libcodecad_b200.so (include/codecad_b200.h).
+
+The product path goes through this module only.  If the shared library is missing or no
+CUDA device is usable, every entry point raises: there is no CPU or PyTorch fallback.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libcodecad_b200.so")
+
+c_float_p = ctypes.POINTER(ctypes.c_float)
+c_u32_p = ctypes.POINTER(ctypes.c_uint32)
+c_u8_p = ctypes.POINTER(ctypes.c_uint8)
+c_void_pp = ctypes.POINTER(ctypes.c_void_p)
+
+LAYOUT_INDEX3_FLOAT4 = 0
+LAYOUT_PYMCUBES_FLOAT = 1
+
+
+class CodecadB200Error(RuntimeError):
+    pass
+
+
+class DeviceInfo(ctypes.Structure):
+    _fields_ = [("device", ctypes.c_int), ("sm_count", ctypes.c_int), ("sm_clock_khz", ctypes.c_int),
+                ("l2_bytes", ctypes.c_int), ("total_mem", ctypes.c_size_t), ("name", ctypes.c_char * 64)]
+
+
+class ProgramInfo(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint32) for n in (
+        "n_words", "n_instructions", "n_micro_ops", "n_micro_words", "n_wire_registers",
+        "n_slots", "n_p_stores", "flops_min", "flops_max")]
+
+
+class Level(ctypes.Structure):
+    _fields_ = [("cell_size", ctypes.c_int64), ("nx", ctypes.c_uint32), ("ny", ctypes.c_uint32),
+                ("nz", ctypes.c_uint32)]
+
+
+# every exported symbol of include/codecad_b200.h: name -> (restype, argtypes)
+_V = ctypes.c_void_p
+_I = ctypes.c_int
+_U = ctypes.c_uint32
+_F = ctypes.c_float
+SIGNATURES = {
+    "cc_init": (_I, [_I]),
+    "cc_shutdown": (None, []),
+    "cc_device_count": (_I, []),
+    "cc_last_error": (ctypes.c_char_p, []),
+    "cc_get_device_info": (_I, [ctypes.POINTER(DeviceInfo)]),
+    "cc_synchronize": (_I, []),
+    "cc_get_counters": (_I, [ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
+    "cc_reset_counters": (None, []),
+    "cc_set_tuning": (_I, [_I, _I]),
+    "cc_program_create": (_I, [c_float_p, _U, c_void_pp]),
+    "cc_program_destroy": (None, [_V]),
+    "cc_program_get_info": (_I, [_V, ctypes.POINTER(ProgramInfo)]),
+    "cc_program_get_microcode": (_I, [_V, c_u32_p, _U]),
+    "cc_buffer_alloc": (_I, [ctypes.c_size_t, c_void_pp]),
+    "cc_buffer_free": (_I, [_V]),
+    "cc_host_alloc": (_I, [ctypes.c_size_t, c_void_pp]),
+    "cc_host_free": (_I, [_V]),
+    "cc_memcpy_h2d_async": (_I, [_V, _V, ctypes.c_size_t, c_void_pp]),
+    "cc_memcpy_d2h_async": (_I, [_V, _V, ctypes.c_size_t, c_void_pp]),
+    "cc_memset_async": (_I, [_V, _I, ctypes.c_size_t, c_void_pp]),
+    "cc_event_record": (_I, [c_void_pp]),
+    "cc_event_wait": (_I, [_V]),
+    "cc_event_elapsed_ms": (_I, [_V, _V, c_float_p]),
+    "cc_event_destroy": (None, [_V]),
+    "cc_grid_eval": (_I, [_V, c_float_p, _F, _U, _U, _U, _U, _I, _V, c_void_pp]),
+    "cc_grid_eval_to_host": (_I, [_V, c_float_p, _F, _U, _U, _U, _U, _I, _V]),
+    "cc_subdivision_step": (_I, [_V, c_float_p, _F, _F, _U, _U, _U, _V, _V, c_void_pp]),
+    "cc_mass_properties_step": (_I, [_V, c_float_p, _F, _F, _U, _U, _U, _V, _V, _V, c_void_pp]),
+    "cc_subdivide": (_I, [_V, ctypes.POINTER(ctypes.c_double), ctypes.c_double, ctypes.POINTER(Level), _U, _I,
+                          _U, _U, ctypes.POINTER(ctypes.POINTER(ctypes.c_int64)), ctypes.POINTER(ctypes.c_uint64)]),
+    "cc_mass_properties": (_I, [_V, ctypes.POINTER(ctypes.c_double), ctypes.c_double, ctypes.POINTER(Level), _U,
+                                _U, _U, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]),
+    "cc_free": (None, [_V]),
+}
+
+_lib = None
+_initialized_device = None
+
+
+def load():
+    """Load the shared library (no CUDA call yet)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise CodecadB200Error(
+                "%s is missing: build it with `python -m codecad_b200.build` "
+                "(there is no fallback path)" % SO_PATH)
+        L = ctypes.CDLL(SO_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc < 0:
+        raise CodecadB200Error("libcodecad_b200: %s (code %d)" % (load().cc_last_error().decode(), rc))
+    return rc
+
+
+def init(device=None):
+    """Create the CUDA context on `device` (default: LOCAL_RANK, else 0)."""
+    global _initialized_device
+    L = load()
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    if _initialized_device is None:
+        check(L.cc_init(int(device)))
+        _initialized_device = int(device)
+    elif _initialized_device != int(device):
+        raise CodecadB200Error("already initialised on device %d" % _initialized_device)
+    return L
+
+
+def lib():
+    """Library with an initialised context."""
+    return init(_initialized_device)
+
+
+def device_info():
+    info = DeviceInfo()
+    check(lib().cc_get_device_info(ctypes.byref(info)))
+    return info
+
+
+def counters():
+    a, b = ctypes.c_uint64(), ctypes.c_uint64()
+    check(lib().cc_get_counters(ctypes.byref(a), ctypes.byref(b)))
+    return a.value, b.value
+
+
+def f3(v):
+    """corner argument: accepts a numpy structured float4 scalar (Vector.as_float4()), or
+    any 3/4-sequence; returns a ctypes float[3] rounded to fp32 like as_float4()."""
+    a = np.asarray(v)
+    if a.dtype.names:
+        a = np.array([a["x"], a["y"], a["z"]], dtype=np.float32)
+    else:
+        a = np.asarray(a, dtype=np.float64).astype(np.float32).ravel()[:3]
+    return (ctypes.c_float * 3)(*[float(x) for x in a])

@@ -1,0 +1,231 @@
+"""Device buffers with the interface of the reference's `cl_util.Buffer`
+(/root/reference/codecad/cl_util/cl_buffer.py:9-158), backed by libcodecad_b200.
+
+Ownership follows the reference: the Buffer owns a device allocation and an optional host
+mirror `.array`; here the mirror is PINNED host memory (the reference asks OpenCL for
+ALLOC_HOST_PTR, cl_buffer.py:36-40), so reads and writes are true async DMA.
+"""
+import contextlib
+import ctypes
+
+import numpy as np
+
+from .. import _lib
+from ..geometry import FLOAT2, FLOAT4, UCHAR4  # noqa: F401  (re-exported dtypes)
+from .manager import Event, _new_event_ref
+
+
+class _Pinned:
+    """numpy view over cudaMallocHost memory; freed when the last view dies."""
+
+    def __init__(self, nbytes):
+        self.ptr = ctypes.c_void_p()
+        _lib.check(_lib.lib().cc_host_alloc(max(int(nbytes), 1), ctypes.byref(self.ptr)))
+        self.nbytes = int(nbytes)
+
+    def array(self, dtype, shape):
+        buf = (ctypes.c_uint8 * max(self.nbytes, 1)).from_address(self.ptr.value)
+        arr = np.frombuffer(buf, dtype=np.uint8, count=self.nbytes).view(dtype).reshape(shape)
+        self._keep = buf
+        return arr
+
+    def __del__(self):
+        try:
+            if self.ptr and _lib._lib is not None:
+                _lib._lib.cc_host_free(self.ptr)
+        except Exception:  # noqa: BLE001
+            pass
+
+
+class Buffer:
+    @staticmethod
+    def dual_dtype(scalar):
+        return np.dtype([(name, scalar) for name in "xy"])
+
+    @staticmethod
+    def quad_dtype(scalar):
+        return np.dtype([(name, scalar) for name in "xyzw"])
+
+    def __init__(self, dtype, shape, mem_flags=None, queue=None):
+        self.queue = queue
+        self.dtype = np.dtype(dtype)
+        self.nitems = 1
+        try:
+            for s in shape:
+                self.nitems *= int(s)
+            self.shape = tuple(int(s) for s in shape)
+        except TypeError:
+            self.nitems = int(shape)
+            self.shape = (int(shape),)
+        self.size = self.nitems * self.dtype.itemsize
+        self.array = None
+        self._pinned = None
+        self._dptr = ctypes.c_void_p()
+        _lib.check(_lib.lib().cc_buffer_alloc(self.size, ctypes.byref(self._dptr)))
+
+    @property
+    def device_ptr(self):
+        if not self._dptr:
+            raise RuntimeError("Buffer has been released")
+        return self._dptr
+
+    def release(self):
+        if self._dptr and _lib._lib is not None:
+            _lib._lib.cc_buffer_free(self._dptr)
+        self._dptr = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def create_host_side_array(self):
+        self._pinned = _Pinned(self.size)
+        self.array = self._pinned.array(self.dtype, self.shape)
+
+    def _process_array(self, array):
+        if array is None:
+            if self.array is None:
+                self.create_host_side_array()
+            return self.array
+        return array
+
+    def enqueue_read(self, out=None, wait_for=None):
+        array = self._process_array(out)
+        if array.nbytes < self.size:
+            raise RuntimeError("Not enough space to store contents of the buffer")
+        ev = _new_event_ref()
+        _lib.check(_lib.lib().cc_memcpy_d2h_async(array.ctypes.data, self.device_ptr, self.size, ctypes.byref(ev)))
+        return Event(ev)
+
+    def read(self, out=None, wait_for=None):
+        array = self._process_array(out)
+        self.enqueue_read(array).wait()
+        return array
+
+    def enqueue_write(self, a=None, wait_for=None):
+        array = self._process_array(a)
+        array = np.ascontiguousarray(array)
+        if array.nbytes > self.size:
+            raise RuntimeError("Not enough space to store contents in the buffer")
+        ev = _new_event_ref()
+        if a is not None:
+            # pageable source: the copy must have consumed it before we return
+            _lib.check(_lib.lib().cc_memcpy_h2d_async(self.device_ptr, array.ctypes.data, array.nbytes, ctypes.byref(ev)))
+            e = Event(ev)
+            e.wait()
+            return e
+        _lib.check(_lib.lib().cc_memcpy_h2d_async(self.device_ptr, array.ctypes.data, array.nbytes, ctypes.byref(ev)))
+        return Event(ev)
+
+    def enqueue_zero_fill_compatible(self, wait_for=None):
+        ev = _new_event_ref()
+        _lib.check(_lib.lib().cc_memset_async(self.device_ptr, 0, self.size, ctypes.byref(ev)))
+        return Event(ev)
+
+    @contextlib.contextmanager
+    def map(self, map_flags=None, offset=None, shape=None, wait_for=None):
+        """Maps the buffer as a numpy array: read on entry, written back on exit."""
+        arr = self.read()
+        if offset is None:
+            offset = 0
+        view = arr.reshape(-1)[offset:] if offset else arr
+        if shape is not None:
+            n = int(np.prod(shape))
+            view = arr.reshape(-1)[offset:offset + n].reshape(shape)
+        yield view
+        self.enqueue_write().wait()
+
+    def __getitem__(self, key):
+        return self.array[key]
+
+    def __setitem__(self, key, value):
+        self.array[key] = value
+
+    def __len__(self):
+        return self.nitems
+
+
+class ProgramBuffer:
+    """What `nodes.make_program_buffer(shape)` returns: the reference returns a read-only
+    pyopencl.Buffer holding the float32 words (nodes/program.py:79-84); here it is the
+    decoded, device-resident program (cc_program)."""
+
+    def __init__(self, words):
+        self.words = np.ascontiguousarray(words, dtype=np.float32)
+        self._h = ctypes.c_void_p()
+        _lib.check(_lib.lib().cc_program_create(
+            self.words.ctypes.data_as(_lib.c_float_p), len(self.words), ctypes.byref(self._h)))
+        self.size = self.words.nbytes
+
+    @property
+    def handle(self):
+        if not self._h:
+            raise RuntimeError("ProgramBuffer has been released")
+        return self._h
+
+    @property
+    def info(self):
+        info = _lib.ProgramInfo()
+        _lib.check(_lib.lib().cc_program_get_info(self.handle, ctypes.byref(info)))
+        return info
+
+    def microcode(self):
+        n = _lib.lib().cc_program_get_microcode(self.handle, None, 0)
+        out = np.zeros(n, np.uint32)
+        _lib.lib().cc_program_get_microcode(self.handle, out.ctypes.data_as(_lib.c_u32_p), n)
+        return out
+
+    def release(self):
+        if self._h and _lib._lib is not None:
+            _lib._lib.cc_program_destroy(self._h)
+        self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+class BufferList:
+    """cl_buffer.py:134-158"""
+
+    def __init__(self, buffers=()):
+        self.buffers = list(buffers)
+
+    def add(self, buff):
+        self.buffers.append(buff)
+
+    def release(self):
+        try:
+            for buff in self.buffers:
+                buff.release()
+        finally:
+            self.buffers = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc_info):
+        self.release()
+
+
+class OpenClAssertionError(Exception):
+    """cl_assert.py:8-30 — never raised: the CUDA kernels carry no device-side asserts."""
+
+
+class AssertBuffer:
+    """cl_assert.py:33-92, inert."""
+
+    ASSERT_ENABLED = False
+
+    def __init__(self, queue=None):
+        pass
+
+    def reset(self):
+        return Event()
+
+    def check(self, wait_for=None):
+        return None

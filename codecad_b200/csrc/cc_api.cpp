@@ -1,0 +1,803 @@
+// C ABI of libcodecad_b200 (see include/codecad_b200.h): context, programs, buffers,
+// events, the four reference-semantics kernels and the device-resident hierarchy drivers.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "cc_internal.h"
+
+struct cc_event {
+    cudaEvent_t ev;
+};
+
+namespace {
+
+thread_local std::string g_err;
+
+struct Context {
+    bool ready = false;
+    int device = -1;
+    cudaDeviceProp prop;
+    cudaStream_t compute = nullptr, copy = nullptr;
+    uint64_t launches = 0, points = 0;
+    int pts = 0, prog_space = 0;  // tuning overrides, 0 = auto
+    uint64_t next_program_id = 1;
+    uint64_t constant_program = 0;  // id of the program in the __constant__ window
+    // look-back scratch
+    uint32_t *d_ticket = nullptr;
+    unsigned long long *d_status = nullptr;
+    size_t status_cap = 0;
+    // pinned bounce word for counters
+    uint32_t *h_word = nullptr;
+};
+Context g;
+std::mutex g_mu;
+
+int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char *what)
+{
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return CC_ERR_CUDA;
+}
+
+#define CU(call)                                        \
+    do {                                                \
+        cudaError_t e_ = (call);                        \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+    } while (0)
+
+#define NEED_INIT()                                                             \
+    do {                                                                        \
+        if (!g.ready) return fail(CC_ERR_NOT_INITIALIZED, "cc_init() has not succeeded"); \
+    } while (0)
+
+int make_event(cc_event **ev, cudaStream_t st)
+{
+    if (!ev) return CC_OK;
+    cc_event *e = new cc_event;
+    cudaError_t r = cudaEventCreate(&e->ev);
+    if (r == cudaSuccess) r = cudaEventRecord(e->ev, st);
+    if (r != cudaSuccess) {
+        delete e;
+        return cuda_fail(r, "cudaEventRecord");
+    }
+    *ev = e;
+    return CC_OK;
+}
+
+int ensure_status(size_t tiles)
+{
+    if (!g.d_ticket) CU(cudaMalloc(&g.d_ticket, 4));
+    if (tiles > g.status_cap) {
+        if (g.d_status) CU(cudaFree(g.d_status));
+        size_t cap = std::max<size_t>(tiles, 1 << 16);
+        CU(cudaMalloc(&g.d_status, cap * sizeof(unsigned long long)));
+        g.status_cap = cap;
+    }
+    return CC_OK;
+}
+
+// pick points-per-thread / program space for a program
+int choose_cfg(const cc_program *prog, uint64_t total_points, cc_launch_cfg *cfg)
+{
+    const uint32_t words = prog->dec.info.n_micro_words;
+    const uint32_t slots = prog->dec.info.n_slots;
+    const size_t smem_max = g.prop.sharedMemPerBlockOptin;
+    int space = g.prog_space;
+    if (space == 0) space = 2;
+    if (space == 1 && words > CC_CONST_WORDS) space = 2;
+    int pts = g.pts ? g.pts : 4;
+    if (pts != 1 && pts != 2 && pts != 4) pts = 4;
+    // small launches: fewer points per thread keeps more SMs busy
+    if (!g.pts) {
+        while (pts > 1 && total_points < (uint64_t)g.prop.multiProcessorCount * 128u * pts * 2u) pts >>= 1;
+    }
+    for (;;) {
+        cfg->pts = pts;
+        cfg->prog_space = space;
+        size_t need = cc_eval_smem_bytes(*cfg, slots, words);
+        // want at least two CTAs per SM when possible
+        if (need * 2 <= (size_t)g.prop.sharedMemPerMultiprocessor - 2048 || pts == 1) {
+            if (need > smem_max) {
+                if (space == 2 && words <= CC_CONST_WORDS) {
+                    space = 1;
+                    continue;
+                }
+                return fail(CC_ERR_TOO_LARGE, "program needs " + std::to_string(need) +
+                                                  " bytes of shared memory per CTA (limit " +
+                                                  std::to_string(smem_max) + ")");
+            }
+            return CC_OK;
+        }
+        pts >>= 1;
+    }
+}
+
+int prepare_program(const cc_program *prog, const cc_launch_cfg &cfg)
+{
+    if (cfg.prog_space == 1 && g.constant_program != prog->id) {
+        int e = cc_upload_constant_program(prog->dec.microcode.data(), prog->dec.info.n_micro_words, g.compute);
+        if (e) return cuda_fail((cudaError_t)e, "cudaMemcpyToSymbolAsync");
+        g.constant_program = prog->id;
+    }
+    return CC_OK;
+}
+
+void fill_common(cc_eval_args *a, const cc_program *prog)
+{
+    std::memset(a, 0, sizeof(*a));
+    a->code = prog->d_code;
+    a->code_words = prog->dec.info.n_micro_words;
+    a->n_slots = prog->dec.info.n_slots;
+}
+
+int check_dims(uint32_t nx, uint32_t ny, uint32_t nz)
+{
+    if (nx == 0 || ny == 0 || nz == 0) return fail(CC_ERR_INVALID_ARGUMENT, "empty grid");
+    uint64_t cells = (uint64_t)nx * ny * nz;
+    if (cells > (1ull << 31)) return fail(CC_ERR_INVALID_ARGUMENT, "more than 2^31 cells in one launch");
+    return CC_OK;
+}
+
+int launch(int sink, const cc_program *prog, cc_eval_args &a, uint64_t points)
+{
+    cc_launch_cfg cfg;
+    int rc = choose_cfg(prog, points, &cfg);
+    if (rc) return rc;
+    rc = prepare_program(prog, cfg);
+    if (rc) return rc;
+    const uint32_t tile = cc_tile_points(cfg);
+    const uint64_t cells = (uint64_t)a.nx * a.ny * a.nz;
+    a.tiles_per_block = (uint32_t)((cells + tile - 1) / tile);
+    const uint64_t tiles = (uint64_t)a.tiles_per_block * a.n_blocks;
+    if (tiles >= (1ull << 31)) return fail(CC_ERR_INVALID_ARGUMENT, "too many tiles in one launch");
+    if (sink == CC_SINK_CLASSIFY || sink == CC_SINK_MASS) {
+        rc = ensure_status((size_t)tiles);
+        if (rc) return rc;
+        CU(cudaMemsetAsync(g.d_ticket, 0, 4, g.compute));
+        CU(cudaMemsetAsync(g.d_status, 0, (size_t)tiles * sizeof(unsigned long long), g.compute));
+        a.ticket = g.d_ticket;
+        a.tile_status = g.d_status;
+    }
+    int e = cc_launch_eval(sink, cfg, a, g.compute);
+    if (e) return cuda_fail((cudaError_t)e, "cc_eval_kernel launch");
+    g.launches += 1;
+    g.points += points;
+    return CC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *cc_last_error(void) { return g_err.c_str(); }
+
+int cc_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int cc_init(int device)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g.ready) {
+        if (g.device == device) return CC_OK;
+        return fail(CC_ERR_INVALID_ARGUMENT, "already initialised on another device");
+    }
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(CC_ERR_CUDA, "no CUDA device available; libcodecad_b200 has no CPU fallback");
+    }
+    if (device < 0 || device >= n) return fail(CC_ERR_INVALID_ARGUMENT, "no such device");
+    CU(cudaSetDevice(device));
+    CU(cudaGetDeviceProperties(&g.prop, device));
+    if (g.prop.major < 10)
+        return fail(CC_ERR_CUDA, std::string("device ") + g.prop.name + " is not sm_100 (built for sm_100a only)");
+    CU(cudaStreamCreateWithFlags(&g.compute, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&g.copy, cudaStreamNonBlocking));
+    CU(cudaMallocHost(&g.h_word, 64));
+    g.device = device;
+    g.ready = true;
+    const char *p = getenv("CODECAD_B200_PTS");
+    if (p) g.pts = atoi(p);
+    p = getenv("CODECAD_B200_PROG_SPACE");
+    if (p) g.prog_space = atoi(p);
+    return CC_OK;
+}
+
+void cc_shutdown(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g.ready) return;
+    cudaDeviceSynchronize();
+    if (g.d_ticket) cudaFree(g.d_ticket);
+    if (g.d_status) cudaFree(g.d_status);
+    if (g.h_word) cudaFreeHost(g.h_word);
+    cudaStreamDestroy(g.compute);
+    cudaStreamDestroy(g.copy);
+    g = Context();
+}
+
+int cc_get_device_info(cc_device_info *out)
+{
+    NEED_INIT();
+    std::memset(out, 0, sizeof(*out));
+    out->device = g.device;
+    out->sm_count = g.prop.multiProcessorCount;
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, g.device);
+    out->sm_clock_khz = khz;
+    out->l2_bytes = g.prop.l2CacheSize;
+    out->total_mem = g.prop.totalGlobalMem;
+    std::strncpy(out->name, g.prop.name, sizeof(out->name) - 1);
+    return CC_OK;
+}
+
+int cc_synchronize(void)
+{
+    NEED_INIT();
+    CU(cudaStreamSynchronize(g.compute));
+    CU(cudaStreamSynchronize(g.copy));
+    return CC_OK;
+}
+
+int cc_get_counters(uint64_t *kernel_launches, uint64_t *points_evaluated)
+{
+    if (kernel_launches) *kernel_launches = g.launches;
+    if (points_evaluated) *points_evaluated = g.points;
+    return CC_OK;
+}
+
+void cc_reset_counters(void) { g.launches = g.points = 0; }
+
+int cc_set_tuning(int points_per_thread, int program_space)
+{
+    if (points_per_thread != 0 && points_per_thread != 1 && points_per_thread != 2 && points_per_thread != 4)
+        return fail(CC_ERR_INVALID_ARGUMENT, "points_per_thread must be 0, 1, 2 or 4");
+    if (program_space < 0 || program_space > 2) return fail(CC_ERR_INVALID_ARGUMENT, "program_space must be 0, 1 or 2");
+    g.pts = points_per_thread;
+    g.prog_space = program_space;
+    return CC_OK;
+}
+
+// ---- programs -------------------------------------------------------------------------------------
+
+int cc_program_create(const float *words, uint32_t n_words, cc_program **out)
+{
+    NEED_INIT();
+    if (!words || !out) return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
+    cc_program *p = new cc_program();
+    std::string err;
+    int rc = cc_decode_program(words, n_words, &p->dec, &err);
+    if (rc != CC_OK) {
+        delete p;
+        return fail(rc, err);
+    }
+    size_t bytes = p->dec.microcode.size() * 4;
+    cudaError_t e = cudaMalloc(&p->d_code, bytes);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(p->d_code, p->dec.microcode.data(), bytes, cudaMemcpyHostToDevice, g.compute);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g.compute);
+    if (e != cudaSuccess) {
+        delete p;
+        return cuda_fail(e, "program upload");
+    }
+    p->id = g.next_program_id++;
+    *out = p;
+    return CC_OK;
+}
+
+void cc_program_destroy(cc_program *prog)
+{
+    if (!prog) return;
+    if (g.ready) {
+        cudaStreamSynchronize(g.compute);
+        cudaFree(prog->d_code);
+        if (g.constant_program == prog->id) g.constant_program = 0;
+    }
+    delete prog;
+}
+
+int cc_program_get_info(const cc_program *prog, cc_program_info *out)
+{
+    if (!prog || !out) return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
+    *out = prog->dec.info;
+    return CC_OK;
+}
+
+int cc_program_get_microcode(const cc_program *prog, uint32_t *out, uint32_t capacity)
+{
+    if (!prog) return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
+    uint32_t n = (uint32_t)prog->dec.microcode.size();
+    if (out) std::memcpy(out, prog->dec.microcode.data(), (size_t)std::min(n, capacity) * 4);
+    return (int)n;
+}
+
+// ---- buffers / events ---------------------------------------------------------------------------------
+
+int cc_buffer_alloc(size_t bytes, void **dptr)
+{
+    NEED_INIT();
+    CU(cudaMalloc(dptr, bytes ? bytes : 1));
+    return CC_OK;
+}
+
+int cc_buffer_free(void *dptr)
+{
+    NEED_INIT();
+    if (!dptr) return CC_OK;
+    CU(cudaStreamSynchronize(g.compute));
+    CU(cudaStreamSynchronize(g.copy));
+    CU(cudaFree(dptr));
+    return CC_OK;
+}
+
+int cc_host_alloc(size_t bytes, void **hptr)
+{
+    NEED_INIT();
+    CU(cudaMallocHost(hptr, bytes ? bytes : 1));
+    return CC_OK;
+}
+
+int cc_host_free(void *hptr)
+{
+    NEED_INIT();
+    if (hptr) CU(cudaFreeHost(hptr));
+    return CC_OK;
+}
+
+int cc_memcpy_h2d_async(void *dptr, const void *hptr, size_t bytes, cc_event **ev)
+{
+    NEED_INIT();
+    CU(cudaMemcpyAsync(dptr, hptr, bytes, cudaMemcpyHostToDevice, g.compute));
+    return make_event(ev, g.compute);
+}
+
+int cc_memcpy_d2h_async(void *hptr, const void *dptr, size_t bytes, cc_event **ev)
+{
+    NEED_INIT();
+    CU(cudaMemcpyAsync(hptr, dptr, bytes, cudaMemcpyDeviceToHost, g.compute));
+    return make_event(ev, g.compute);
+}
+
+int cc_memset_async(void *dptr, int value, size_t bytes, cc_event **ev)
+{
+    NEED_INIT();
+    CU(cudaMemsetAsync(dptr, value, bytes, g.compute));
+    return make_event(ev, g.compute);
+}
+
+int cc_event_record(cc_event **ev)
+{
+    NEED_INIT();
+    if (!ev) return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
+    return make_event(ev, g.compute);
+}
+
+int cc_event_wait(cc_event *ev)
+{
+    NEED_INIT();
+    if (!ev) return CC_OK;
+    CU(cudaEventSynchronize(ev->ev));
+    return CC_OK;
+}
+
+int cc_event_elapsed_ms(cc_event *start, cc_event *end, float *ms)
+{
+    NEED_INIT();
+    if (!start || !end || !ms) return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
+    CU(cudaEventElapsedTime(ms, start->ev, end->ev));
+    return CC_OK;
+}
+
+void cc_event_destroy(cc_event *ev)
+{
+    if (!ev) return;
+    cudaEventDestroy(ev->ev);
+    delete ev;
+}
+
+void cc_free(void *p) { free(p); }
+
+// ---- reference-semantics kernels ---------------------------------------------------------------------
+
+int cc_grid_eval(const cc_program *prog, const float corner[3], float step, uint32_t nx, uint32_t ny,
+                 uint32_t nz, uint32_t x_offset, int layout, void *d_out, cc_event **ev)
+{
+    NEED_INIT();
+    if (!prog || !corner || !d_out) return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
+    if (layout != CC_LAYOUT_INDEX3_FLOAT4 && layout != CC_LAYOUT_PYMCUBES_FLOAT)
+        return fail(CC_ERR_INVALID_ARGUMENT, "unknown layout");
+    if (nx == 0 || ny == 0 || nz == 0) return fail(CC_ERR_INVALID_ARGUMENT, "empty grid");
+    const uint64_t plane = (uint64_t)ny * nz;
+    if (plane > (1ull << 31)) return fail(CC_ERR_INVALID_ARGUMENT, "y*z plane too large");
+    // split along x so that every launch has <= 2^30 cells (the PyMCubes layout is not
+    // x-separable, so it must fit one launch)
+    uint32_t max_x = (uint32_t)std::max<uint64_t>(1, (1ull << 30) / plane);
+    if (layout == CC_LAYOUT_PYMCUBES_FLOAT && nx > max_x)
+        return fail(CC_ERR_INVALID_ARGUMENT, "PyMCubes-layout grid too large for one launch");
+    const size_t elem = layout == CC_LAYOUT_INDEX3_FLOAT4 ? 16 : 4;
+    for (uint32_t x0 = 0; x0 < nx; x0 += max_x) {
+        uint32_t cnt = std::min(max_x, nx - x0);
+        cc_eval_args a;
+        fill_common(&a, prog);
+        a.cx = corner[0]; a.cy = corner[1]; a.cz = corner[2]; a.step = step;
+        a.nx = cnt; a.ny = ny; a.nz = nz; a.x_offset = x_offset + x0;
+        a.n_blocks = 1;
+        a.out = (char *)d_out + (size_t)x0 * plane * elem;
+        int rc = launch(layout == CC_LAYOUT_INDEX3_FLOAT4 ? CC_SINK_FLOAT4 : CC_SINK_PYMCUBES, prog, a,
+                        (uint64_t)cnt * plane);
+        if (rc) return rc;
+    }
+    return make_event(ev, g.compute);
+}
+
+int cc_grid_eval_to_host(const cc_program *prog, const float corner[3], float step, uint32_t nx, uint32_t ny,
+                         uint32_t nz, uint32_t x_offset, int layout, void *h_out)
+{
+    NEED_INIT();
+    if (!prog || !corner || !h_out) return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
+    if (nx == 0 || ny == 0 || nz == 0) return fail(CC_ERR_INVALID_ARGUMENT, "empty grid");
+    const uint64_t plane = (uint64_t)ny * nz;
+    const size_t elem = layout == CC_LAYOUT_INDEX3_FLOAT4 ? 16 : 4;
+    if (layout == CC_LAYOUT_PYMCUBES_FLOAT) {
+        // y-flipped layout is not x-separable: evaluate whole, then one copy
+        void *d = nullptr;
+        CU(cudaMalloc(&d, (size_t)nx * plane * elem));
+        int rc = cc_grid_eval(prog, corner, step, nx, ny, nz, x_offset, layout, d, nullptr);
+        if (rc == CC_OK) {
+            cudaError_t e = cudaMemcpyAsync(h_out, d, (size_t)nx * plane * elem, cudaMemcpyDeviceToHost, g.compute);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(g.compute);
+            if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync D2H");
+        }
+        cudaFree(d);
+        return rc;
+    }
+    // slabs of ~64 MiB: compute on the compute stream into a 3-deep device ring, copy out on the
+    // copy stream; a slab is re-used only after its copy has finished.
+    const int RING = 3;
+    uint32_t slab_x = (uint32_t)std::max<uint64_t>(1, (64ull << 20) / (plane * elem));
+    slab_x = std::min(slab_x, nx);
+    const size_t slab_bytes = (size_t)slab_x * plane * elem;
+    void *d_ring[RING] = {nullptr, nullptr, nullptr};
+    cudaEvent_t computed[RING], copied[RING];
+    int rc = CC_OK;
+    for (int i = 0; i < RING; ++i) {
+        CU(cudaMalloc(&d_ring[i], slab_bytes));
+        CU(cudaEventCreateWithFlags(&computed[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
+    }
+    int slot = 0;
+    for (uint32_t x0 = 0; x0 < nx && rc == CC_OK; x0 += slab_x, slot = (slot + 1) % RING) {
+        uint32_t cnt = std::min(slab_x, nx - x0);
+        if (x0 >= (uint32_t)RING * slab_x) CU(cudaStreamWaitEvent(g.compute, copied[slot], 0));
+        rc = cc_grid_eval(prog, corner, step, cnt, ny, nz, x_offset + x0, layout, d_ring[slot], nullptr);
+        if (rc) break;
+        CU(cudaEventRecord(computed[slot], g.compute));
+        CU(cudaStreamWaitEvent(g.copy, computed[slot], 0));
+        CU(cudaMemcpyAsync((char *)h_out + (size_t)x0 * plane * elem, d_ring[slot], (size_t)cnt * plane * elem,
+                           cudaMemcpyDeviceToHost, g.copy));
+        CU(cudaEventRecord(copied[slot], g.copy));
+    }
+    cudaStreamSynchronize(g.compute);
+    cudaError_t e = cudaStreamSynchronize(g.copy);
+    for (int i = 0; i < RING; ++i) {
+        cudaFree(d_ring[i]);
+        cudaEventDestroy(computed[i]);
+        cudaEventDestroy(copied[i]);
+    }
+    if (rc == CC_OK && e != cudaSuccess) rc = cuda_fail(e, "grid_eval_to_host");
+    return rc;
+}
+
+int cc_subdivision_step(const cc_program *prog, const float corner[3], float step, float threshold,
+                        uint32_t nx, uint32_t ny, uint32_t nz, uint32_t *d_counter, uint8_t *d_list,
+                        cc_event **ev)
+{
+    NEED_INIT();
+    if (!prog || !corner || !d_counter || !d_list) return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
+    int rc = check_dims(nx, ny, nz);
+    if (rc) return rc;
+    if (nx > 256 || ny > 256 || nz > 256)
+        return fail(CC_ERR_INVALID_ARGUMENT, "grid dimension > 256 overflows the uchar4 index list");
+    cc_eval_args a;
+    fill_common(&a, prog);
+    a.cx = corner[0]; a.cy = corner[1]; a.cz = corner[2]; a.step = step;
+    a.nx = nx; a.ny = ny; a.nz = nz; a.n_blocks = 1;
+    a.threshold = threshold; a.counter = d_counter; a.list = d_list;
+    rc = launch(CC_SINK_CLASSIFY, prog, a, (uint64_t)nx * ny * nz);
+    if (rc) return rc;
+    return make_event(ev, g.compute);
+}
+
+int cc_mass_properties_step(const cc_program *prog, const float corner[3], float step, float threshold,
+                            uint32_t nx, uint32_t ny, uint32_t nz, uint32_t *d_sums, uint32_t *d_counter,
+                            uint8_t *d_list, cc_event **ev)
+{
+    NEED_INIT();
+    if (!prog || !corner || !d_sums || !d_counter || !d_list) return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
+    int rc = check_dims(nx, ny, nz);
+    if (rc) return rc;
+    if (nx > 256 || ny > 256 || nz > 256)
+        return fail(CC_ERR_INVALID_ARGUMENT, "grid dimension > 256 overflows the uchar4 index list");
+    cc_eval_args a;
+    fill_common(&a, prog);
+    a.cx = corner[0]; a.cy = corner[1]; a.cz = corner[2]; a.step = step;
+    a.nx = nx; a.ny = ny; a.nz = nz; a.n_blocks = 1;
+    a.threshold = threshold; a.counter = d_counter; a.list = d_list; a.sums = d_sums;
+    rc = launch(CC_SINK_MASS, prog, a, (uint64_t)nx * ny * nz);
+    if (rc) return rc;
+    return make_event(ev, g.compute);
+}
+
+}  // extern "C"
+
+// ---- hierarchy fast paths --------------------------------------------------------------------------------
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int reserve(size_t bytes)
+    {
+        if (bytes <= cap) return CC_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc (hierarchy work list)");
+        cap = bytes;
+        return CC_OK;
+    }
+    template <class T> T *as() { return static_cast<T *>(p); }
+};
+
+int read_counter(uint32_t *d_counter, uint32_t *out)
+{
+    CU(cudaMemcpyAsync(g.h_word, d_counter, 4, cudaMemcpyDeviceToHost, g.compute));
+    CU(cudaStreamSynchronize(g.compute));
+    *out = *g.h_word;
+    return CC_OK;
+}
+
+// Blocks of one level are processed in chunks so that hit lists stay bounded:
+// a chunk evaluates at most `kChunkCells` cells and can emit at most that many hits.
+const uint64_t kChunkCells = 1ull << 27;
+
+}  // namespace
+
+extern "C" {
+
+int cc_subdivide(const cc_program *prog, const double origin[3], double resolution, const cc_level *levels,
+                 uint32_t n_levels, int dimension, uint32_t rank, uint32_t world, int64_t **out_corners,
+                 uint64_t *out_count)
+{
+    NEED_INIT();
+    if (!prog || !origin || !levels || !out_corners || !out_count)
+        return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
+    if (n_levels < 2) return fail(CC_ERR_INVALID_ARGUMENT, "cc_subdivide needs at least two levels");
+    if (dimension != 2 && dimension != 3) return fail(CC_ERR_INVALID_ARGUMENT, "dimension must be 2 or 3");
+    if (world == 0 || rank >= world) return fail(CC_ERR_INVALID_ARGUMENT, "bad rank/world");
+    for (uint32_t l = 0; l < n_levels; ++l)
+        if (levels[l].nx > 256 || levels[l].ny > 256 || levels[l].nz > 256 || !levels[l].nx || !levels[l].ny ||
+            !levels[l].nz)
+            return fail(CC_ERR_INVALID_ARGUMENT, "level grid dimensions must be in 1..256");
+
+    DevBuf corners_a, corners_b, blocks, hit_xyz, hit_block, counter;
+    int rc;
+    if ((rc = counter.reserve(4))) return rc;
+    // level 0: one block at int corner (0,0,0)
+    std::vector<int64_t> cur_host(3, 0);
+    uint64_t n_cur = 1;
+    if ((rc = corners_a.reserve(3 * sizeof(int64_t)))) return rc;
+    CU(cudaMemcpyAsync(corners_a.p, cur_host.data(), 3 * sizeof(int64_t), cudaMemcpyHostToDevice, g.compute));
+    DevBuf *cur = &corners_a, *nxt = &corners_b;
+
+    for (uint32_t l = 0; l + 1 < n_levels; ++l) {
+        const cc_level &L = levels[l];
+        const uint64_t cells = (uint64_t)L.nx * L.ny * L.nz;
+        const uint64_t chunk_blocks = std::max<uint64_t>(1, kChunkCells / cells);
+        const double box_step = (double)L.cell_size * resolution;
+        const float thr = (float)(box_step * std::sqrt((double)dimension) / 2);  // subdivision.py:67
+        cc_level_geom geo{origin[0], origin[1], origin[2], resolution, (double)L.cell_size / 2, dimension};
+        // children of this level, gathered chunk by chunk
+        uint64_t n_next = 0;
+        size_t next_cap = 0;
+        const uint32_t w = (l == 0) ? world : 1u, r = (l == 0) ? rank : 0u;
+        for (uint64_t b0 = 0; b0 < n_cur; b0 += chunk_blocks) {
+            const uint32_t nb = (uint32_t)std::min<uint64_t>(chunk_blocks, n_cur - b0);
+            if ((rc = blocks.reserve((size_t)nb * sizeof(cc_block_desc)))) return rc;
+            if ((rc = hit_xyz.reserve((size_t)nb * cells * 4))) return rc;
+            if ((rc = hit_block.reserve((size_t)nb * cells * 4))) return rc;
+            int e = cc_launch_make_blocks_subdiv(cur->as<int64_t>() + 3 * b0, nb, geo, blocks.as<cc_block_desc>(), g.compute);
+            if (e) return cuda_fail((cudaError_t)e, "make_blocks");
+            CU(cudaMemsetAsync(counter.p, 0, 4, g.compute));
+            cc_eval_args a;
+            fill_common(&a, prog);
+            a.step = (float)box_step;
+            a.nx = L.nx; a.ny = L.ny; a.nz = L.nz; a.n_blocks = nb;
+            a.blocks = blocks.as<cc_block_desc>();
+            a.threshold = thr;
+            a.counter = counter.as<uint32_t>();
+            a.list = hit_xyz.as<uint8_t>();
+            a.list_block = hit_block.as<uint32_t>();
+            if ((rc = launch(CC_SINK_CLASSIFY, prog, a, (uint64_t)nb * cells))) return rc;
+            uint32_t hits = 0;
+            if ((rc = read_counter(counter.as<uint32_t>(), &hits))) return rc;
+            const uint64_t mine = (hits > r) ? ((uint64_t)hits - r + w - 1) / w : 0;
+            if (mine) {
+                size_t need = (size_t)(n_next + mine) * 3 * sizeof(int64_t);
+                if (need > next_cap) {
+                    // grow, preserving what earlier chunks produced
+                    DevBuf bigger;
+                    size_t cap = std::max(need, next_cap * 2);
+                    if ((rc = bigger.reserve(cap))) return rc;
+                    if (n_next) CU(cudaMemcpyAsync(bigger.p, nxt->p, (size_t)n_next * 3 * sizeof(int64_t),
+                                                   cudaMemcpyDeviceToDevice, g.compute));
+                    CU(cudaStreamSynchronize(g.compute));
+                    std::swap(nxt->p, bigger.p);
+                    std::swap(nxt->cap, bigger.cap);
+                    next_cap = cap;
+                }
+                e = cc_launch_expand_children(cur->as<int64_t>() + 3 * b0, hit_block.as<uint32_t>(),
+                                              hit_xyz.as<uint8_t>(), hits, L.cell_size, r, w,
+                                              nxt->as<int64_t>() + 3 * n_next, g.compute);
+                if (e) return cuda_fail((cudaError_t)e, "expand_children");
+                g.launches += 1;
+                n_next += mine;
+            }
+            g.launches += 1;  // make_blocks
+        }
+        std::swap(cur, nxt);
+        n_cur = n_next;
+        if (n_cur == 0) break;
+    }
+    // `cur` now holds the int corners of the leaf blocks
+    *out_count = n_cur;
+    *out_corners = nullptr;
+    if (n_cur) {
+        int64_t *h = (int64_t *)malloc((size_t)n_cur * 3 * sizeof(int64_t));
+        if (!h) return fail(CC_ERR_INVALID_ARGUMENT, "out of host memory");
+        cudaError_t e = cudaMemcpyAsync(h, cur->p, (size_t)n_cur * 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, g.compute);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(g.compute);
+        if (e != cudaSuccess) {
+            free(h);
+            return cuda_fail(e, "leaf list D2H");
+        }
+        *out_corners = h;
+    }
+    return CC_OK;
+}
+
+int cc_mass_properties(const cc_program *prog, const double box_a[3], double resolution, const cc_level *levels,
+                       uint32_t n_levels, uint32_t rank, uint32_t world, double integrals[10], uint64_t stats[4])
+{
+    NEED_INIT();
+    if (!prog || !box_a || !levels || !integrals) return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
+    if (n_levels < 1) return fail(CC_ERR_INVALID_ARGUMENT, "no levels");
+    if (world == 0 || rank >= world) return fail(CC_ERR_INVALID_ARGUMENT, "bad rank/world");
+    for (uint32_t l = 0; l < n_levels; ++l)
+        if (levels[l].nx > 256 || levels[l].ny > 256 || levels[l].nz > 256 || !levels[l].nx || !levels[l].ny ||
+            !levels[l].nz)
+            return fail(CC_ERR_INVALID_ARGUMENT, "level grid dimensions must be in 1..256");
+
+    DevBuf corners_a, corners_b, blocks, hit_xyz, hit_block, counter, sums, acc;
+    int rc;
+    if ((rc = counter.reserve(4))) return rc;
+    if ((rc = acc.reserve(20 * sizeof(double)))) return rc;
+    CU(cudaMemsetAsync(acc.p, 0, 20 * sizeof(double), g.compute));
+    double root[3] = {box_a[0], box_a[1], box_a[2]};
+    if ((rc = corners_a.reserve(3 * sizeof(double)))) return rc;
+    CU(cudaMemcpyAsync(corners_a.p, root, sizeof(root), cudaMemcpyHostToDevice, g.compute));
+    CU(cudaStreamSynchronize(g.compute));
+    DevBuf *cur = &corners_a, *nxt = &corners_b;
+    uint64_t n_cur = 1, n_launch = 0, n_cells = 0, n_blocks_total = 0;
+
+    for (uint32_t l = 0; l < n_levels && n_cur; ++l) {
+        const cc_level &L = levels[l];
+        const bool leaf = (l + 1 == n_levels);
+        const uint64_t cells = (uint64_t)L.nx * L.ny * L.nz;
+        const uint64_t chunk_blocks = std::max<uint64_t>(1, kChunkCells / cells);
+        const double s = resolution * (double)L.cell_size;                       // mass_properties.py:51-53
+        const float thr = leaf ? 0.0f : (float)(s * std::sqrt(3.0) / 2);         // :87-90
+        const uint32_t w = (l == 0) ? world : 1u, r = (l == 0) ? rank : 0u;
+        uint64_t n_next = 0;
+        size_t next_cap = 0;
+        for (uint64_t b0 = 0; b0 < n_cur; b0 += chunk_blocks) {
+            const uint32_t nb = (uint32_t)std::min<uint64_t>(chunk_blocks, n_cur - b0);
+            if ((rc = blocks.reserve((size_t)nb * sizeof(cc_block_desc)))) return rc;
+            if ((rc = sums.reserve((size_t)nb * 10 * 4))) return rc;
+            if (!leaf) {
+                if ((rc = hit_xyz.reserve((size_t)nb * cells * 4))) return rc;
+                if ((rc = hit_block.reserve((size_t)nb * cells * 4))) return rc;
+            } else {
+                if ((rc = hit_xyz.reserve(16))) return rc;
+                if ((rc = hit_block.reserve(16))) return rc;
+            }
+            int e = cc_launch_mass_make_blocks(cur->as<double>() + 3 * b0, nb, s, blocks.as<cc_block_desc>(), g.compute);
+            if (e) return cuda_fail((cudaError_t)e, "mass make_blocks");
+            CU(cudaMemsetAsync(counter.p, 0, 4, g.compute));
+            CU(cudaMemsetAsync(sums.p, 0, (size_t)nb * 10 * 4, g.compute));
+            cc_eval_args a;
+            fill_common(&a, prog);
+            a.step = (float)s;
+            a.nx = L.nx; a.ny = L.ny; a.nz = L.nz; a.n_blocks = nb;
+            a.blocks = blocks.as<cc_block_desc>();
+            a.threshold = thr;
+            a.counter = counter.as<uint32_t>();
+            a.list = hit_xyz.as<uint8_t>();
+            a.list_block = hit_block.as<uint32_t>();
+            a.sums = sums.as<uint32_t>();
+            if ((rc = launch(CC_SINK_MASS, prog, a, (uint64_t)nb * cells))) return rc;
+            n_launch += 1;
+            n_cells += (uint64_t)nb * cells;
+            n_blocks_total += nb;
+            // every rank evaluates level 0, but only rank 0 counts its inside cells
+            if (l > 0 || rank == 0) {
+                e = cc_launch_mass_integrals(cur->as<double>() + 3 * b0, sums.as<uint32_t>(), nb, s, acc.as<double>(), g.compute);
+                if (e) return cuda_fail((cudaError_t)e, "mass integrals");
+            }
+            if (leaf) continue;
+            uint32_t hits = 0;
+            if ((rc = read_counter(counter.as<uint32_t>(), &hits))) return rc;
+            const uint64_t mine = (hits > r) ? ((uint64_t)hits - r + w - 1) / w : 0;
+            if (mine) {
+                size_t need = (size_t)(n_next + mine) * 3 * sizeof(double);
+                if (need > next_cap) {
+                    DevBuf bigger;
+                    size_t cap = std::max(need, next_cap * 2);
+                    if ((rc = bigger.reserve(cap))) return rc;
+                    if (n_next) CU(cudaMemcpyAsync(bigger.p, nxt->p, (size_t)n_next * 3 * sizeof(double),
+                                                   cudaMemcpyDeviceToDevice, g.compute));
+                    CU(cudaStreamSynchronize(g.compute));
+                    std::swap(nxt->p, bigger.p);
+                    std::swap(nxt->cap, bigger.cap);
+                    next_cap = cap;
+                }
+                e = cc_launch_mass_expand_children(cur->as<double>() + 3 * b0, hit_block.as<uint32_t>(),
+                                                   hit_xyz.as<uint8_t>(), hits, s, r, w,
+                                                   nxt->as<double>() + 3 * n_next, g.compute);
+                if (e) return cuda_fail((cudaError_t)e, "mass expand_children");
+                n_next += mine;
+            }
+        }
+        g.launches += 3;
+        std::swap(cur, nxt);
+        n_cur = n_next;
+    }
+    double h_acc[20];
+    CU(cudaMemcpyAsync(h_acc, acc.p, sizeof(h_acc), cudaMemcpyDeviceToHost, g.compute));
+    CU(cudaStreamSynchronize(g.compute));
+    for (int i = 0; i < 10; ++i) integrals[i] = h_acc[i];
+    if (stats) {
+        stats[0] = n_launch;
+        stats[1] = n_cells;
+        stats[2] = n_blocks_total;
+        stats[3] = n_levels;
+    }
+    return CC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,770 @@
+// sm_100a kernels of the codecad SDF hot path.
+//
+//   cc_eval_kernel<PTS, SMEM_PROG, SINK>   the SDF interpreter (replaces the generated
+//       OpenCL `evaluate()`  /root/reference/codecad/nodes/codegen.py:17-63) fused with
+//       one of four sinks that replace the reference's __kernel entry points:
+//         FLOAT4    grid_eval            grid_eval.cl:23-34
+//         PYMCUBES  grid_eval_pymcubes   grid_eval.cl:2-21
+//         CLASSIFY  subdivision_step     subdivision.cl:12-30
+//         MASS      mass_properties      mass_properties.cl:7-56
+//
+// Execution model.  Every thread of a warp walks the SAME microcode stream (the program is
+// identical for all grid points), so instruction fetch/decode is warp-uniform: header and
+// parameters are broadcast reads from shared memory (program staged once per CTA with
+// cp.async) or from the constant bank.  Each thread owns PTS grid points that differ
+// only in their linear cell index (stride = CTA size, so that every global store of the
+// warp is one contiguous 512-byte float4 run); the points' running values (`lastValue` of
+// the reference) live in registers and independent points interleave in the FP32 pipes,
+// which amortises decode over PTS points and hides the 4-cycle FMA latency.  The
+// reference's 512-entry private register array becomes a handful of liveness-renamed
+// slots in shared memory, laid out [slot][point][thread] as float4 so that a warp's
+// access is a conflict-free 512-byte LDS.128/STS.128; point values consumed by the very
+// next extrusion / *_from op never leave registers (the P register).
+//
+// Compile with -fmad=false (see cc_math.cuh).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "cc_internal.h"
+#include "cc_ops.cuh"
+
+#define CC_THREADS 128
+
+__constant__ uint32_t c_code[CC_CONST_WORDS];
+
+template <bool SMEM>
+struct Prog {
+    const uint32_t *s;
+    CC_DEV uint32_t u(uint32_t i) const { return SMEM ? s[i] : c_code[i]; }
+    CC_DEV float f(uint32_t i) const { return __uint_as_float(u(i)); }
+    // 16-byte aligned group of four words
+    CC_DEV float4 f4(uint32_t i) const
+    {
+        if (SMEM) return *reinterpret_cast<const float4 *>(s + i);
+        return *reinterpret_cast<const float4 *>(c_code + i);
+    }
+};
+
+// polygons2d.cl:1-74 over the precomputed edge table (px, py, dx, dy, 1/|d|^2, cy)
+template <bool SMEM>
+CC_DEV float4 cc_polygon2d(const Prog<SMEM> &P, uint32_t pc, float4 co)
+{
+    uint32_t n = (uint32_t)P.f(pc + 1);
+    float nnx = 0.0f, nny = 0.0f, nearest = INFINITY, outside = 1.0f;
+    bool nearest_is_vertex = false;
+    uint32_t e = pc + 4;
+    for (uint32_t i = 0; i < n; ++i, e += CC_POLY_EDGE_WORDS) {
+        float px = P.f(e), py = P.f(e + 1), dx = P.f(e + 2), dy = P.f(e + 3), inv = P.f(e + 4), cy = P.f(e + 5);
+        float tqx = co.x - px, tqy = co.y - py;
+        float snx = -dy, sny = dx;
+        if (((py < co.y) != (cy < co.y)) && (dy * cc_fma(snx, tqx, sny * tqy) > 0.0f)) outside = -outside;
+        float t = cc_fma(dx, tqx, dy * tqy) * inv;
+        if (t > 1.0f) continue;
+        float cnx, cny, cd;
+        bool civ;
+        if (t >= 0.0f) {
+            float tcx = cc_fma(-t, dx, tqx), tcy = cc_fma(-t, dy, tqy);
+            cd = cc_fma(tcx, tcx, tcy * tcy);
+            cnx = snx; cny = sny; civ = false;
+        } else {
+            cnx = tqx; cny = tqy;
+            cd = cc_fma(cnx, cnx, cny * cny);
+            civ = cd > 1.1920928955078125e-7f;
+            if (!civ) { cnx = snx; cny = sny; }
+        }
+        if (cd < nearest) { nearest = cd; nnx = cnx; nny = cny; nearest_is_vertex = civ; }
+    }
+    float distance = outside * cc_sqrt(nearest);
+    float inv = nearest_is_vertex ? cc_rcp(distance) : cc_rcp(cc_len2(nnx, nny));
+    return make_float4(nnx * inv, nny * inv, 0.0f, distance);
+}
+
+// ---- the interpreter ------------------------------------------------------------------------
+template <int PTS, bool SMEM>
+CC_DEV void cc_interpret(const Prog<SMEM> P, float4 *__restrict__ regs, const float (&gx)[PTS],
+                         const float (&gy)[PTS], const float (&gz)[PTS], float4 (&L)[PTS])
+{
+    float4 Pr[PTS];  // the P register: last point value kept out of shared memory
+    const uint32_t tid = threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < PTS; ++j) {
+        L[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        Pr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    uint32_t pc = 0;
+    for (;;) {
+        const uint32_t h = P.u(pc);
+        const uint32_t op = CC_HDR_OP(h), src = CC_HDR_SRC(h), dst = CC_HDR_DST(h);
+        float4 B[PTS];
+        if (src != CC_SLOT_NONE) {
+            if (src == CC_SLOT_P) {
+#pragma unroll
+                for (int j = 0; j < PTS; ++j) B[j] = Pr[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < PTS; ++j) B[j] = regs[(src * PTS + j) * CC_THREADS + tid];
+            }
+        }
+        switch (op) {
+        case MOP_RETURN: return;
+        case MOP_LOAD:
+#pragma unroll
+            for (int j = 0; j < PTS; ++j) L[j] = B[j];
+            pc += CC_LEN_0;
+            break;
+        case MOP_NOP: pc += CC_LEN_0; break;
+        case MOP_RECTANGLE: {
+            const float4 q = P.f4(pc);
+#pragma unroll
+            for (int j = 0; j < PTS; ++j) L[j] = cc_rectangle(q.y, q.z, L[j]);
+            pc += CC_LEN_0;
+            break;
+        }
+        case MOP_CIRCLE: {
+            const float r = P.f(pc + 1);
+#pragma unroll
+            for (int j = 0; j < PTS; ++j) L[j] = cc_circle(r, L[j]);
+            pc += CC_LEN_0;
+            break;
+        }
+        case MOP_REGPOLY: {
+            float k[5];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) k[i] = P.f(pc + 1 + i);
+#pragma unroll
+            for (int j = 0; j < PTS; ++j) L[j] = cc_regular_polygon2d(k, L[j]);
+            pc += CC_LEN_7;
+            break;
+        }
+        case MOP_POLYGON: {
+            const uint32_t n = (uint32_t)P.f(pc + 1);
+#pragma unroll
+            for (int j = 0; j < PTS; ++j) L[j] = cc_polygon2d<SMEM>(P, pc, L[j]);
+            pc += 4 + ((CC_POLY_EDGE_WORDS * n + 3) / 4) * 4;
+            break;
+        }
+        case MOP_SPHERE: {
+            const float r = P.f(pc + 1);
+#pragma unroll
+            for (int j = 0; j < PTS; ++j) L[j] = cc_sphere(r, L[j]);
+            pc += CC_LEN_0;
+            break;
+        }
+        case MOP_HALF_SPACE:  // simple3d.cl:14-16
+#pragma unroll
+            for (int j = 0; j < PTS; ++j) L[j] = make_float4(0.0f, -1.0f, 0.0f, -L[j].y);
+            pc += CC_LEN_0;
+            break;
+        case MOP_REV_TO:  // simple3d.cl:23-26
+#pragma unroll
+            for (int j = 0; j < PTS; ++j) L[j] = make_float4(cc_len2(L[j].x, L[j].z), L[j].y, 0.0f, 0.0f);
+            pc += CC_LEN_0;
+            break;
+        case MOP_TWIST_TO: {
+            const float r = P.f(pc + 1), twist = P.f(pc + 2);
+#pragma unroll
+            for (int j = 0; j < PTS; ++j) L[j] = cc_twist_revolution_to(r, twist, L[j]);
+            pc += CC_LEN_0;
+            break;
+        }
+        case MOP_T_INIT:
+        case MOP_T_TO: {
+            float m[12];
+            {
+                const float4 a = P.f4(pc), b = P.f4(pc + 4), c = P.f4(pc + 8), d = P.f4(pc + 12);
+                m[0] = a.y; m[1] = a.z; m[2] = a.w; m[3] = b.x; m[4] = b.y; m[5] = b.z;
+                m[6] = b.w; m[7] = c.x; m[8] = c.y; m[9] = c.z; m[10] = c.w; m[11] = d.x;
+            }
+            if (op == MOP_T_INIT) {
+#pragma unroll
+                for (int j = 0; j < PTS; ++j) L[j] = cc_transform(m, gx[j], gy[j], gz[j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < PTS; ++j) L[j] = cc_transform(m, L[j].x, L[j].y, L[j].z);
+            }
+            pc += CC_LEN_T;
+            break;
+        }
+        case MOP_T_FROM: {
+            float m[12];
+            {
+                const float4 a = P.f4(pc), b = P.f4(pc + 4), c = P.f4(pc + 8);
+                m[0] = a.y; m[1] = a.z; m[2] = a.w; m[3] = b.x; m[4] = b.y; m[5] = b.z;
+                m[6] = b.w; m[7] = c.x; m[8] = c.y; m[9] = c.z; m[10] = 0.f; m[11] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < PTS; ++j) L[j] = cc_transform_from(m, L[j]);
+            pc += CC_LEN_T;
+            break;
+        }
+        case MOP_MIRROR:  // common.cl:112-114
+#pragma unroll
+            for (int j = 0; j < PTS; ++j) L[j].x = -L[j].x;
+            pc += CC_LEN_0;
+            break;
+        case MOP_SYM_TO:  // common.cl:116-118
+#pragma unroll
+            for (int j = 0; j < PTS; ++j) L[j].x = fabsf(L[j].x);
+            pc += CC_LEN_0;
+            break;
+        case MOP_OFFSET: {  // common.cl:124-126
+            const float d = P.f(pc + 1);
+#pragma unroll
+            for (int j = 0; j < PTS; ++j) L[j].w = L[j].w - d;
+            pc += CC_LEN_0;
+            break;
+        }
+        case MOP_SHELL: {  // common.cl:128-131
+            const float d = P.f(pc + 1);
+#pragma unroll
+            for (int j = 0; j < PTS; ++j) {
+                float4 s = (L[j].w >= 0.0f) ? L[j] : cc_neg4(L[j]);
+                s.w = s.w - d;
+                L[j] = s;
+            }
+            pc += CC_LEN_0;
+            break;
+        }
+        case MOP_REPETITION: {  // unsafe.cl:1-6
+            const float4 q = P.f4(pc);
+#pragma unroll
+            for (int j = 0; j < PTS; ++j)
+                L[j] = make_float4(cc_remainder(L[j].x, q.y), cc_remainder(L[j].y, q.z),
+                                   cc_remainder(L[j].z, q.w), 0.0f);
+            pc += CC_LEN_0;
+            break;
+        }
+        case MOP_CREP_TO: {
+            const float a = P.f(pc + 1), b = P.f(pc + 2);
+#pragma unroll
+            for (int j = 0; j < PTS; ++j) L[j] = cc_circular_repetition_to(a, b, L[j]);
+            pc += CC_LEN_0;
+            break;
+        }
+        case MOP_CREP_FROM: {
+            const float a = P.f(pc + 1), b = P.f(pc + 2);
+#pragma unroll
+            for (int j = 0; j < PTS; ++j) L[j] = cc_circular_repetition_from(a, b, L[j], B[j]);
+            pc += CC_LEN_0;
+            break;
+        }
+        case MOP_GEAR: {
+            float k[5];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) k[i] = P.f(pc + 1 + i);
+#pragma unroll
+            for (int j = 0; j < PTS; ++j) L[j] = cc_involute_gear(k, L[j]);
+            pc += CC_LEN_7;
+            break;
+        }
+        case MOP_EXTRUSION: {
+            const float hh = P.f(pc + 1);
+#pragma unroll
+            for (int j = 0; j < PTS; ++j) L[j] = cc_extrusion(hh, L[j], B[j].z);
+            pc += CC_LEN_0;
+            break;
+        }
+        case MOP_REV_FROM:
+#pragma unroll
+            for (int j = 0; j < PTS; ++j) L[j] = cc_revolution_from(L[j], B[j]);
+            pc += CC_LEN_0;
+            break;
+        case MOP_TWIST_FROM: {
+            float k[5];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) k[i] = P.f(pc + 1 + i);
+#pragma unroll
+            for (int j = 0; j < PTS; ++j) L[j] = cc_twist_revolution_from(k, L[j], B[j]);
+            pc += CC_LEN_7;
+            break;
+        }
+        case MOP_SYM_FROM:  // common.cl:120-122
+#pragma unroll
+            for (int j = 0; j < PTS; ++j) L[j].x = (B[j].x < 0.0f) ? -L[j].x : L[j].x;
+            pc += CC_LEN_0;
+            break;
+        case MOP_UNION:  // common.cl:60-68 with r < 0
+#pragma unroll
+            for (int j = 0; j < PTS; ++j) L[j] = (L[j].w < B[j].w) ? L[j] : B[j];
+            pc += CC_LEN_0;
+            break;
+        case MOP_UNION_R: {
+            const float r = P.f(pc + 1);
+#pragma unroll
+            for (int j = 0; j < PTS; ++j) L[j] = cc_rounded_union(r, L[j], B[j]);
+            pc += CC_LEN_0;
+            break;
+        }
+        case MOP_ISECT:  // common.cl:70-72: -min(-a, -b) = the operand with the larger distance
+#pragma unroll
+            for (int j = 0; j < PTS; ++j) L[j] = (-L[j].w < -B[j].w) ? L[j] : B[j];
+            pc += CC_LEN_0;
+            break;
+        case MOP_ISECT_R: {
+            const float r = P.f(pc + 1);
+#pragma unroll
+            for (int j = 0; j < PTS; ++j) L[j] = cc_neg4(cc_rounded_union(r, cc_neg4(L[j]), cc_neg4(B[j])));
+            pc += CC_LEN_0;
+            break;
+        }
+        case MOP_SUB:  // common.cl:74-76: -min(-a, b)
+#pragma unroll
+            for (int j = 0; j < PTS; ++j) L[j] = (-L[j].w < B[j].w) ? L[j] : cc_neg4(B[j]);
+            pc += CC_LEN_0;
+            break;
+        case MOP_SUB_R: {
+            const float r = P.f(pc + 1);
+#pragma unroll
+            for (int j = 0; j < PTS; ++j) L[j] = cc_neg4(cc_rounded_union(r, cc_neg4(L[j]), B[j]));
+            pc += CC_LEN_0;
+            break;
+        }
+        default: return;  // unreachable: the loader only emits the micro-ops above
+        }
+        if (dst != CC_SLOT_NONE) {
+            if (dst == CC_SLOT_P) {
+#pragma unroll
+                for (int j = 0; j < PTS; ++j) Pr[j] = L[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < PTS; ++j) regs[(dst * PTS + j) * CC_THREADS + tid] = L[j];
+            }
+        }
+    }
+}
+
+// ---- ordered compaction: warp-ballot scan inside the CTA + decoupled look-back across CTAs ----
+// tile_status word = (state << 62) | value, state 1 = tile aggregate, 2 = inclusive prefix.
+#define CC_ST_AGG 1ull
+#define CC_ST_INC 2ull
+
+CC_DEV unsigned long long cc_ld_status(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+CC_DEV void cc_st_status(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Returns the exclusive prefix (number of hits in all earlier tiles, plus the list's initial
+// length) for this tile.  Called by warp 0 only; `tile` is the ticket-ordered tile id.
+CC_DEV uint32_t cc_lookback(unsigned long long *status, uint32_t tile, uint32_t aggregate,
+                            const uint32_t *counter)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    if (tile == 0) {
+        uint32_t base = *counter;  // list[atomic_inc(counter)]: continue after existing entries
+        if (lane == 0) cc_st_status(status, (CC_ST_INC << 62) | (unsigned long long)(base + aggregate));
+        return base;
+    }
+    if (lane == 0) cc_st_status(status + tile, (CC_ST_AGG << 62) | (unsigned long long)aggregate);
+    uint32_t exclusive = 0;
+    int look = (int)tile - 1;  // lanes inspect tiles look - lane
+    for (;;) {
+        int t = look - (int)lane;
+        unsigned long long s = (t >= 0) ? cc_ld_status(status + t) : ((CC_ST_INC << 62));
+        uint32_t state = (uint32_t)(s >> 62);
+        // all inspected predecessors must be published before we can use the window
+        if (__any_sync(0xffffffffu, state == 0)) continue;
+        uint32_t inc_mask = __ballot_sync(0xffffffffu, state == CC_ST_INC);
+        uint32_t val = (uint32_t)s;
+        if (inc_mask) {
+            int first = __ffs(inc_mask) - 1;  // nearest tile with an inclusive prefix
+            uint32_t contrib = (lane <= (uint32_t)first) ? val : 0u;
+            exclusive += __reduce_add_sync(0xffffffffu, contrib);
+            break;
+        }
+        exclusive += __reduce_add_sync(0xffffffffu, val);
+        look -= 32;
+    }
+    if (lane == 0)
+        cc_st_status(status + tile, (CC_ST_INC << 62) | (unsigned long long)(exclusive + aggregate));
+    return exclusive;
+}
+
+// ---- the kernel -----------------------------------------------------------------------------
+template <int PTS, bool SMEM, int SINK>
+__global__ void __launch_bounds__(CC_THREADS) cc_eval_kernel(const cc_eval_args a)
+{
+    extern __shared__ float4 smem4[];
+    float4 *regs = smem4;  // [n_slots][PTS][CC_THREADS]
+    uint32_t *s_code = reinterpret_cast<uint32_t *>(smem4 + (size_t)a.n_slots * PTS * CC_THREADS);
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_warp[PTS * (CC_THREADS / 32)];
+    __shared__ uint32_t s_base;
+
+    const uint32_t tid = threadIdx.x;
+    constexpr bool ORDERED = (SINK == CC_SINK_CLASSIFY || SINK == CC_SINK_MASS);
+
+    if (SMEM) {
+        // stage the microcode once per CTA: 16-byte cp.async, all threads
+        const uint32_t n4 = a.code_words / 4;
+        for (uint32_t i = tid; i < n4; i += CC_THREADS) {
+            uint32_t dsts = (uint32_t)__cvta_generic_to_shared(s_code + 4 * i);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dsts), "l"(a.code + 4 * i) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+
+    // tile id: launch order for pure stores; ticket order where tiles wait on predecessors
+    uint32_t tile = blockIdx.x;
+    if (ORDERED) {
+        if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
+        __syncthreads();
+        tile = s_tile;
+    }
+    const uint32_t block = tile / a.tiles_per_block;
+    const uint32_t tile_in_block = tile - block * a.tiles_per_block;
+    float cx = a.cx, cy = a.cy, cz = a.cz;
+    if (a.blocks) {
+        const cc_block_desc bd = a.blocks[block];
+        cx = bd.cx; cy = bd.cy; cz = bd.cz;
+    }
+    const uint32_t cells = a.nx * a.ny * a.nz;  // <= 2^31 per launch (host checks)
+    const uint32_t nyz = a.ny * a.nz;
+
+    float gx[PTS], gy[PTS], gz[PTS];
+    uint32_t ix[PTS], iy[PTS], iz[PTS];
+    bool valid[PTS];
+#pragma unroll
+    for (int j = 0; j < PTS; ++j) {
+        uint32_t c = tile_in_block * (CC_THREADS * PTS) + j * CC_THREADS + tid;
+        valid[j] = c < cells;
+        c = valid[j] ? c : 0u;
+        ix[j] = c / nyz;
+        uint32_t r = c - ix[j] * nyz;
+        iy[j] = r / a.nz;
+        iz[j] = r - iy[j] * a.nz;
+        // grid_eval.cl:13,31: corner + step * convert_float(id), one FMA per axis
+        gx[j] = cc_fma(a.step, (float)(ix[j] + a.x_offset), cx);
+        gy[j] = cc_fma(a.step, (float)iy[j], cy);
+        gz[j] = cc_fma(a.step, (float)iz[j], cz);
+    }
+
+    if (SMEM) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+    }
+
+    float4 L[PTS];
+    Prog<SMEM> P{s_code};
+    cc_interpret<PTS, SMEM>(P, regs, gx, gy, gz, L);
+
+    if (SINK == CC_SINK_FLOAT4) {
+        float4 *out = reinterpret_cast<float4 *>(a.out) + (size_t)block * cells;
+#pragma unroll
+        for (int j = 0; j < PTS; ++j) {
+            uint32_t c = tile_in_block * (CC_THREADS * PTS) + j * CC_THREADS + tid;
+            if (valid[j]) __stcs(out + c, L[j]);  // INDEX3: z + nz*(y + ny*x) == linear cell index
+        }
+    } else if (SINK == CC_SINK_PYMCUBES) {
+        float *out = reinterpret_cast<float *>(a.out) + (size_t)block * cells;
+#pragma unroll
+        for (int j = 0; j < PTS; ++j) {
+            // grid_eval.cl:18: z + (x + (ny - y - 1) * nx) * nz
+            size_t idx = (size_t)iz[j] + ((size_t)ix[j] + (size_t)(a.ny - iy[j] - 1) * a.nx) * a.nz;
+            if (valid[j]) __stcs(out + idx, L[j].w);
+        }
+    } else {
+        // ---- classification ----
+        const uint32_t lane = tid & 31, warp = tid >> 5;
+        bool hit[PTS];
+        uint32_t sum[10];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) sum[i] = 0;
+#pragma unroll
+        for (int j = 0; j < PTS; ++j) {
+            const float v = L[j].w;
+            if (SINK == CC_SINK_CLASSIFY) {
+                hit[j] = valid[j] && (v > -a.threshold && v < a.threshold);  // subdivision.cl:25
+            } else {
+                const bool inside = valid[j] && (v <= -a.threshold);  // mass_properties.cl:31
+                hit[j] = valid[j] && !inside && (v < a.threshold);    // mass_properties.cl:43
+                if (inside) {
+                    // mass_properties.cl:34-41, order xx,xy,xz,x,yy,yz,y,zz,z,n
+                    const uint32_t x = ix[j], y = iy[j], z = iz[j];
+                    sum[0] += x * x; sum[1] += x * y; sum[2] += x * z; sum[3] += x;
+                    sum[4] += y * y; sum[5] += y * z; sum[6] += y; sum[7] += z * z;
+                    sum[8] += z; sum[9] += 1u;
+                }
+            }
+        }
+        if (SINK == CC_SINK_MASS) {
+            // hierarchical reduction: REDUX across the warp, one atomic per warp and moment
+            uint32_t *dst = a.sums + (a.blocks ? (size_t)block * 10 : 0);
+#pragma unroll
+            for (int i = 0; i < 10; ++i) {
+                uint32_t w = __reduce_add_sync(0xffffffffu, sum[i]);
+                if (lane == 0 && w) atomicAdd(dst + i, w);
+            }
+        }
+        // ranks inside the tile, in cell order (j major, then warp, then lane)
+        uint32_t ballot[PTS];
+#pragma unroll
+        for (int j = 0; j < PTS; ++j) {
+            ballot[j] = __ballot_sync(0xffffffffu, hit[j]);
+            if (lane == 0) s_warp[j * (CC_THREADS / 32) + warp] = __popc(ballot[j]);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // exclusive scan of the PTS * 4 warp counts (<= 32 entries) with shuffles
+            constexpr int NW = PTS * (CC_THREADS / 32);
+            uint32_t v = (lane < NW) ? s_warp[lane] : 0u;
+            uint32_t incl = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            if (lane < NW) s_warp[lane] = incl - v;
+            uint32_t base = cc_lookback(a.tile_status, tile, total, a.counter);
+            if (lane == 0) {
+                s_base = base;
+                if (tile == gridDim.x - 1) *a.counter = base + total;  // final list length
+            }
+        }
+        __syncthreads();
+        const uint32_t base = s_base;
+#pragma unroll
+        for (int j = 0; j < PTS; ++j) {
+            if (hit[j]) {
+                uint32_t pos = base + s_warp[j * (CC_THREADS / 32) + warp] + __popc(ballot[j] & ((1u << lane) - 1u));
+                reinterpret_cast<uchar4 *>(a.list)[pos] =
+                    make_uchar4((unsigned char)ix[j], (unsigned char)iy[j], (unsigned char)iz[j], 0);
+                if (a.list_block) a.list_block[pos] = block;
+            }
+        }
+    }
+}
+
+// ---- host-side launch ---------------------------------------------------------------------------
+
+uint32_t cc_tile_points(const cc_launch_cfg &cfg) { return (uint32_t)(CC_THREADS * cfg.pts); }
+
+size_t cc_eval_smem_bytes(const cc_launch_cfg &cfg, uint32_t n_slots, uint32_t code_words)
+{
+    size_t b = (size_t)n_slots * cfg.pts * CC_THREADS * sizeof(float4);
+    if (cfg.prog_space == 2) b += (size_t)code_words * 4;
+    return b;
+}
+
+int cc_upload_constant_program(const uint32_t *h_code, uint32_t n_words, void *stream)
+{
+    return (int)cudaMemcpyToSymbolAsync(c_code, h_code, (size_t)n_words * 4, 0, cudaMemcpyHostToDevice,
+                                        (cudaStream_t)stream);
+}
+
+template <int PTS, bool SMEM, int SINK>
+static int launch_one(const cc_eval_args &a, size_t smem, uint32_t grid, cudaStream_t st)
+{
+    auto k = cc_eval_kernel<PTS, SMEM, SINK>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    k<<<grid, CC_THREADS, smem, st>>>(a);
+    return (int)cudaGetLastError();
+}
+
+template <int SINK>
+static int launch_sink(const cc_launch_cfg &cfg, const cc_eval_args &a, size_t smem, uint32_t grid, cudaStream_t st)
+{
+    const bool sm = cfg.prog_space == 2;
+    switch (cfg.pts) {
+    case 1: return sm ? launch_one<1, true, SINK>(a, smem, grid, st) : launch_one<1, false, SINK>(a, smem, grid, st);
+    case 2: return sm ? launch_one<2, true, SINK>(a, smem, grid, st) : launch_one<2, false, SINK>(a, smem, grid, st);
+    default: return sm ? launch_one<4, true, SINK>(a, smem, grid, st) : launch_one<4, false, SINK>(a, smem, grid, st);
+    }
+}
+
+int cc_launch_eval(int sink, const cc_launch_cfg &cfg, const cc_eval_args &a, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = cc_eval_smem_bytes(cfg, a.n_slots, a.code_words);
+    const uint32_t grid = a.n_blocks * a.tiles_per_block;
+    if (grid == 0) return 0;
+    switch (sink) {
+    case CC_SINK_FLOAT4: return launch_sink<CC_SINK_FLOAT4>(cfg, a, smem, grid, st);
+    case CC_SINK_PYMCUBES: return launch_sink<CC_SINK_PYMCUBES>(cfg, a, smem, grid, st);
+    case CC_SINK_CLASSIFY: return launch_sink<CC_SINK_CLASSIFY>(cfg, a, smem, grid, st);
+    default: return launch_sink<CC_SINK_MASS>(cfg, a, smem, grid, st);
+    }
+}
+
+// ---- hierarchy helper kernels (float64 host math of the reference, moved on device) ----------
+
+// subdivision.py:55-65: shifted_corner = (int_corner + int_step/2) * resolution + origin,
+// rounded to fp32 per block by Vector.as_float4() (util/geometry.py:98-99).
+__global__ void cc_make_blocks_subdiv_kernel(const int64_t *__restrict__ corners, uint32_t n, cc_level_geom g,
+                                             cc_block_desc *__restrict__ out)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double x = __dadd_rn((double)corners[3 * i + 0], g.half_cell);
+    double y = __dadd_rn((double)corners[3 * i + 1], g.half_cell);
+    double z = __dadd_rn((double)corners[3 * i + 2], g.dimension == 3 ? g.half_cell : 0.0);
+    cc_block_desc b;
+    b.cx = (float)__dadd_rn(__dmul_rn(x, g.resolution), g.ox);
+    b.cy = (float)__dadd_rn(__dmul_rn(y, g.resolution), g.oy);
+    b.cz = (float)__dadd_rn(__dmul_rn(z, g.resolution), g.oz);
+    b.pad = 0;
+    out[i] = b;
+}
+
+// subdivision.py:91-94: child int corner = (i,j,k) * int_step + parent int corner.
+// With world > 1 hit h goes to rank h % world (round-robin deal of the first refined level).
+__global__ void cc_expand_children_kernel(const int64_t *__restrict__ parents, const uint32_t *__restrict__ hit_block,
+                                          const uchar4 *__restrict__ hit_xyz, uint32_t n_hits, int64_t int_step,
+                                          uint32_t rank, uint32_t world, int64_t *__restrict__ out)
+{
+    uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= n_hits || (h % world) != rank) return;
+    uint32_t o = h / world;
+    uint32_t b = hit_block[h];
+    uchar4 c = hit_xyz[h];
+    out[3 * o + 0] = parents[3 * b + 0] + (int64_t)c.x * int_step;
+    out[3 * o + 1] = parents[3 * b + 1] + (int64_t)c.y * int_step;
+    out[3 * o + 2] = parents[3 * b + 2] + (int64_t)c.z * int_step;
+}
+
+// mass_properties.py:86: shifted_corner = box_corner + box_step / 2 (float64), then as_float4()
+__global__ void cc_mass_make_blocks_kernel(const double *__restrict__ corners, uint32_t n, double half,
+                                           cc_block_desc *__restrict__ out)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    cc_block_desc b;
+    b.cx = (float)__dadd_rn(corners[3 * i + 0], half);
+    b.cy = (float)__dadd_rn(corners[3 * i + 1], half);
+    b.cz = (float)__dadd_rn(corners[3 * i + 2], half);
+    b.pad = 0;
+    out[i] = b;
+}
+
+// mass_properties.py:154-157: child corner = Vector(i,j,k) * s + box_corner (float64)
+__global__ void cc_mass_expand_children_kernel(const double *__restrict__ parents,
+                                               const uint32_t *__restrict__ hit_block,
+                                               const uchar4 *__restrict__ hit_xyz, uint32_t n_hits, double s,
+                                               uint32_t rank, uint32_t world, double *__restrict__ out)
+{
+    uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= n_hits || (h % world) != rank) return;
+    uint32_t o = h / world;
+    uint32_t b = hit_block[h];
+    uchar4 c = hit_xyz[h];
+    out[3 * o + 0] = __dadd_rn(__dmul_rn((double)c.x, s), parents[3 * b + 0]);
+    out[3 * o + 1] = __dadd_rn(__dmul_rn((double)c.y, s), parents[3 * b + 1]);
+    out[3 * o + 2] = __dadd_rn(__dmul_rn((double)c.z, s), parents[3 * b + 2]);
+}
+
+// mass_properties.py:119-148: per block, index sums -> the ten integrals, in float64 with the
+// reference's expression order; blocks are then combined by a fixed-shape (deterministic)
+// reduction: strided Kahan partials per thread, pairwise tree across the CTA, Kahan into the
+// running totals acc[0..9] (+ compensation acc[10..19]).
+__global__ void __launch_bounds__(256) cc_mass_integrals_kernel(const double *__restrict__ corners,
+                                                                const uint32_t *__restrict__ sums,
+                                                                uint32_t n_blocks, double s,
+                                                                double *__restrict__ acc)
+{
+    __shared__ double red[256];
+    const double s2 = __dmul_rn(s, s);
+    const double s3 = __dmul_rn(s, s2);
+    const double half = __ddiv_rn(s, 2.0);
+    const double s2_12 = __ddiv_rn(s2, 12.0);
+    double part[10], comp[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) { part[i] = 0.0; comp[i] = 0.0; }
+    for (uint32_t b = threadIdx.x; b < n_blocks; b += 256) {
+        const uint32_t *q = sums + (size_t)b * 10;
+        const double sxx = q[0], sxy = q[1], sxz = q[2], sx = q[3], syy = q[4], syz = q[5], sy = q[6],
+                     szz = q[7], sz = q[8], n = q[9];
+        if (q[9] == 0) continue;
+        const double bx = __dadd_rn(corners[3 * b + 0], half);
+        const double by = __dadd_rn(corners[3 * b + 1], half);
+        const double bz = __dadd_rn(corners[3 * b + 2], half);
+        const double tx = s * sx, ty = s * sy, tz = s * sz;
+        const double txx = s2 * sxx, tyy = s2 * syy, tzz = s2 * szz;
+        const double txy = s2 * sxy, txz = s2 * sxz, tyz = s2 * syz;
+        double v[10];
+        v[0] = s3 * n;
+        v[1] = s3 * (n * bx + tx);
+        v[2] = s3 * (n * by + ty);
+        v[3] = s3 * (n * bz + tz);
+        v[4] = s3 * (n * (bx * bx + s2_12) + 2.0 * bx * tx + txx);
+        v[5] = s3 * (n * (by * by + s2_12) + 2.0 * by * ty + tyy);
+        v[6] = s3 * (n * (bz * bz + s2_12) + 2.0 * bz * tz + tzz);
+        v[7] = s3 * (n * bx * by + bx * ty + by * tx + txy);
+        v[8] = s3 * (n * bx * bz + bx * tz + bz * tx + txz);
+        v[9] = s3 * (n * by * bz + by * tz + bz * ty + tyz);
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {  // util/math.py:12-17
+            double y = v[i] - comp[i];
+            double t = part[i] + y;
+            comp[i] = (t - part[i]) - y;
+            part[i] = t;
+        }
+    }
+    for (int i = 0; i < 10; ++i) {
+        red[threadIdx.x] = part[i];
+        __syncthreads();
+        for (int d = 128; d > 0; d >>= 1) {
+            if (threadIdx.x < d) red[threadIdx.x] = red[threadIdx.x] + red[threadIdx.x + d];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            double y = red[0] - acc[10 + i];
+            double t = acc[i] + y;
+            acc[10 + i] = (t - acc[i]) - y;
+            acc[i] = t;
+        }
+        __syncthreads();
+    }
+}
+
+int cc_launch_make_blocks_subdiv(const int64_t *d_int_corners, uint32_t n, cc_level_geom g,
+                                 cc_block_desc *d_blocks, void *stream)
+{
+    if (!n) return 0;
+    cc_make_blocks_subdiv_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_int_corners, n, g, d_blocks);
+    return (int)cudaGetLastError();
+}
+
+int cc_launch_expand_children(const int64_t *d_parent_corners, const uint32_t *d_hit_block,
+                              const uint8_t *d_hit_xyz, uint32_t n_hits, int64_t int_step, uint32_t rank,
+                              uint32_t world, int64_t *d_child_corners, void *stream)
+{
+    if (!n_hits) return 0;
+    cc_expand_children_kernel<<<(n_hits + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        d_parent_corners, d_hit_block, reinterpret_cast<const uchar4 *>(d_hit_xyz), n_hits, int_step, rank,
+        world, d_child_corners);
+    return (int)cudaGetLastError();
+}
+
+int cc_launch_mass_make_blocks(const double *d_corners, uint32_t n, double s, cc_block_desc *d_blocks,
+                               void *stream)
+{
+    if (!n) return 0;
+    cc_mass_make_blocks_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_corners, n, s / 2, d_blocks);
+    return (int)cudaGetLastError();
+}
+
+int cc_launch_mass_expand_children(const double *d_parent_corners, const uint32_t *d_hit_block,
+                                   const uint8_t *d_hit_xyz, uint32_t n_hits, double s, uint32_t rank,
+                                   uint32_t world, double *d_child_corners, void *stream)
+{
+    if (!n_hits) return 0;
+    cc_mass_expand_children_kernel<<<(n_hits + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        d_parent_corners, d_hit_block, reinterpret_cast<const uchar4 *>(d_hit_xyz), n_hits, s, rank, world,
+        d_child_corners);
+    return (int)cudaGetLastError();
+}
+
+int cc_launch_mass_integrals(const double *d_corners, const uint32_t *d_sums, uint32_t n_blocks, double s,
+                             double *d_integrals, void *stream)
+{
+    if (!n_blocks) return 0;
+    cc_mass_integrals_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d_corners, d_sums, n_blocks, s, d_integrals);
+    return (int)cudaGetLastError();
+}

@@ -1,0 +1,222 @@
+// SDF op library, device side: one __device__ function per node type of
+// /root/reference/codecad/shapes/*.cl, evaluated in the canonical arithmetic of
+// cc_math.cuh.  Values follow the reference convention: .xyz = unit direction
+// (gradient) or point coordinates, .w = signed distance (negative inside).
+//
+// Each function handles ONE point; the interpreter calls it in an unrolled loop over the
+// thread's points so that independent points interleave in the FP32 pipes.  Parameters
+// arrive as warp-uniform values decoded from the microcode.
+#ifndef CC_OPS_CUH
+#define CC_OPS_CUH
+
+#include "cc_math.cuh"
+
+CC_DEV float4 cc_neg4(float4 a) { return make_float4(-a.x, -a.y, -a.z, -a.w); }
+CC_DEV float4 cc_sel4(bool c, float4 a, float4 b)
+{
+    return make_float4(c ? a.x : b.x, c ? a.y : b.y, c ? a.z : b.z, c ? a.w : b.w);
+}
+
+// shapes/simple2d.cl:1-4 = perpendicular_intersection(slab_x, slab_y)  (common.cl:15-43)
+CC_DEV float4 cc_rectangle(float hw, float hh, float4 p)
+{
+    float sx = copysignf(1.0f, p.x), sy = copysignf(1.0f, p.y);
+    float ax = fabsf(p.x) - hw, ay = fabsf(p.y) - hh;
+    float dist = cc_len2(ax, ay);
+    float inv = cc_rcp(dist);
+    bool both = ax > 0.0f && ay > 0.0f;
+    bool first = ax > ay;
+    float4 r;
+    r.x = both ? sx * (ax * inv) : (first ? sx : 0.0f);
+    r.y = both ? sy * (ay * inv) : (first ? 0.0f : sy);
+    r.z = 0.0f;
+    r.w = both ? dist : (first ? ax : ay);
+    return r;
+}
+
+// shapes/simple3d.cl:18-21 = perpendicular_intersection(slab_z(h, coords), input)
+CC_DEV float4 cc_extrusion(float h, float4 in, float cz)
+{
+    float sz = copysignf(1.0f, cz);
+    float az = fabsf(cz) - h;
+    float dist = cc_len2(az, in.w);
+    float inv = cc_rcp(dist);
+    float m1 = az * inv, m2 = in.w * inv;
+    bool both = az > 0.0f && in.w > 0.0f;
+    bool first = az > in.w;
+    float4 r;
+    r.x = both ? in.x * m2 : (first ? 0.0f : in.x);
+    r.y = both ? in.y * m2 : (first ? 0.0f : in.y);
+    r.z = both ? cc_fma(sz, m1, in.z * m2) : (first ? sz : in.z);
+    r.w = both ? dist : (first ? az : in.w);
+    return r;
+}
+
+// shapes/simple2d.cl:6-14
+CC_DEV float4 cc_circle(float r, float4 p)
+{
+    float len = cc_len2(p.x, p.y);
+    float inv = cc_rcp(len);
+    bool zero = len == 0.0f;
+    return make_float4(zero ? 1.0f : p.x * inv, zero ? 0.0f : p.y * inv, 0.0f, len - r);
+}
+
+// shapes/simple3d.cl:1-12
+CC_DEV float4 cc_sphere(float r, float4 p)
+{
+    float len = cc_len3(p.x, p.y, p.z);
+    float inv = cc_rcp(len);
+    bool zero = len == 0.0f;
+    return make_float4(zero ? 1.0f : p.x * inv, zero ? 0.0f : p.y * inv, zero ? 0.0f : p.z * inv, len - r);
+}
+
+// shapes/common.cl:45-64
+CC_DEV float4 cc_rounded_union(float r, float4 o1, float4 o2)
+{
+    float4 res = (o1.w < o2.w) ? o1 : o2;
+    float c = cc_dot3(o1.x, o1.y, o1.z, o2.x, o2.y, o2.z);
+    float x1 = r - o1.w, x2 = r - o2.w;
+    if (c * x1 < x2 && c * x2 < x1) {  // rare: only within r of both surfaces
+        float num = cc_fma(-((2.0f * c) * x1), x2, cc_fma(x1, x1, x2 * x2));
+        float den = cc_fma(-c, c, 1.0f);
+        res = make_float4(0.0f, 0.0f, 0.0f, r - cc_sqrt(cc_div(num, den)));
+    }
+    return res;
+}
+
+// 3x3 (row-major) * v + o   — common.cl:78-98 in matrix form
+CC_DEV float4 cc_transform(const float (&m)[12], float x, float y, float z)
+{
+    return make_float4(cc_fma(m[0], x, cc_fma(m[1], y, cc_fma(m[2], z, m[9]))),
+                       cc_fma(m[3], x, cc_fma(m[4], y, cc_fma(m[5], z, m[10]))),
+                       cc_fma(m[6], x, cc_fma(m[7], y, cc_fma(m[8], z, m[11]))), 0.0f);
+}
+
+// common.cl:100-110 (matrix already divided by |q|^2; m[9] = |q|^2)
+CC_DEV float4 cc_transform_from(const float (&m)[12], float4 in)
+{
+    return make_float4(cc_fma(m[0], in.x, cc_fma(m[1], in.y, m[2] * in.z)),
+                       cc_fma(m[3], in.x, cc_fma(m[4], in.y, m[5] * in.z)),
+                       cc_fma(m[6], in.x, cc_fma(m[7], in.y, m[8] * in.z)), in.w * m[9]);
+}
+
+// shapes/simple2d.cl:16-46; k = (piOverN, r, r*sin, r*cos, 2*piOverN)
+CC_DEV float4 cc_regular_polygon2d(const float (&k)[5], float4 co)
+{
+    float piOverN = k[0], r = k[1];
+    float len = cc_len2(co.x, co.y);
+    float alpha = (cc_atan2(co.y, co.x) + CC_2PI_F) + piOverN;
+    int side = (int)floorf(cc_div(alpha, k[4]));
+    float t = (float)(side * 2) * piOverN;
+    float modAlpha = (alpha - t) - piOverN;
+    float s, c;
+    cc_sincos(modAlpha, &s, &c);
+    if (fabsf(s * len) > k[2]) {
+        float ny, nx;
+        cc_sincos(cc_fma(cc_sign(s), piOverN, t), &ny, &nx);
+        float dx = co.x - nx * r, dy = co.y - ny * r;
+        float dist = cc_len2(dx, dy);
+        if (dist > 0.0f) {
+            float inv = cc_rcp(dist);
+            return make_float4(dx * inv, dy * inv, 0.0f, dist);
+        }
+    }
+    float dy, dx;
+    cc_sincos(t, &dy, &dx);
+    return make_float4(dx, dy, 0.0f, cc_fma(len, c, -k[3]));
+}
+
+// shapes/gears.cl:1-42; k = (baseRadius, toothAngle, halfToothBaseAngle, 2*toothAngle, baseRadius^2)
+CC_DEV float4 cc_involute_gear(const float (&k)[5], float4 co)
+{
+    float baseRadius = k[0], toothAngle = k[1], halfTooth = k[2];
+    float len = cc_len2(co.x, co.y);
+    float alpha = cc_atan2(co.y, co.x);
+    float wrapped = cc_fmod_pos(alpha + CC_2PI_F, k[3]);
+    float d = fabsf(wrapped - toothAngle);
+    float involuteAlpha = halfTooth - d;
+    if (len < baseRadius) {
+        float inv = cc_rcp(len);
+        float nx = co.y * inv, ny = -(co.x * inv);
+        if (wrapped > toothAngle) { nx = -nx; ny = -ny; }
+        return make_float4(nx, ny, 0.0f, (d - halfTooth) * len);
+    }
+    float phi = involuteAlpha + cc_acos(cc_div(baseRadius, len));
+    float base = alpha - involuteAlpha;
+    float normalAngle = (wrapped < toothAngle) ? (CC_PI_F - phi) - base : phi - base;
+    float nx, ny;
+    cc_sincos(normalAngle, &nx, &ny);
+    float distance = cc_fma(-baseRadius, phi, cc_sqrt(cc_fma(len, len, -k[4])));
+    return make_float4(nx, ny, 0.0f, distance);
+}
+
+// shapes/simple3d.cl:42-51
+CC_DEV float4 cc_twist_revolution_to(float r, float twist, float4 co)
+{
+    float alpha = cc_fmod_pos(cc_atan2(co.z, co.x) + CC_PI_F, CC_2PI_F);
+    float beta = cc_div(twist * alpha, CC_2PI_F);
+    float ipx = cc_len2(co.x, co.z) - r, ipy = co.y;
+    float s, c;
+    cc_sincos(-beta, &s, &c);
+    return make_float4(cc_fma(c, ipx, -(s * ipy)), cc_fma(s, ipx, c * ipy), 0.0f, 0.0f);
+}
+
+// shapes/simple3d.cl:53-97; k = (minorR, r, twist, min(1, lipschitz), padding)
+CC_DEV float4 cc_twist_revolution_from(const float (&k)[5], float4 inPlane, float4 co)
+{
+    float minorR = k[0], r = k[1], twist = k[2];
+    float ad = cc_len2(co.x, co.z);
+    float ipx = ad - r, ipy = co.y;
+    float icd = cc_len2(ipx, ipy);
+    float wd = icd - minorR;
+    float bound, dx, dy;
+    if (ad == 0.0f) return make_float4(1.0f, 0.0f, 0.0f, r - minorR);
+    if (wd > k[4]) {
+        float inv = cc_rcp(icd);
+        bound = wd; dx = ipx * inv; dy = ipy * inv;
+    } else {
+        float alpha = cc_fmod_pos(cc_atan2(co.z, co.x) + CC_PI_F, CC_2PI_F);
+        float beta = cc_div(twist * alpha, CC_2PI_F);
+        float s, c;
+        cc_sincos(beta, &s, &c);
+        bound = inPlane.w * k[3];
+        dx = cc_fma(c, inPlane.x, -(s * inPlane.y));
+        dy = cc_fma(s, inPlane.x, c * inPlane.y);
+    }
+    float mult = cc_div(dx, ad);
+    return make_float4(co.x * mult, dy, co.z * mult, bound);
+}
+
+// shapes/unsafe.cl:8-15
+CC_DEV float4 cc_circular_repetition_to(float piOverN, float twoPiOverN, float4 co)
+{
+    float len = cc_len2(co.x, co.y);
+    float alpha = (cc_atan2(co.y, co.x) + CC_2PI_F) + piOverN;
+    int side = (int)floorf(cc_div(alpha, twoPiOverN));
+    float modAlpha = (alpha - (float)(side * 2) * piOverN) - piOverN;
+    float s, c;
+    cc_sincos(modAlpha, &s, &c);
+    return make_float4(len * c, len * s, co.z, 0.0f);
+}
+
+// shapes/unsafe.cl:17-23
+CC_DEV float4 cc_circular_repetition_from(float piOverN, float twoPiOverN, float4 dist, float4 co)
+{
+    float alpha = (cc_atan2(co.y, co.x) + CC_2PI_F) + piOverN;
+    int side = (int)floorf(cc_div(alpha, twoPiOverN));
+    float s, c;
+    cc_sincos((float)(side * 2) * piOverN, &s, &c);
+    return make_float4(cc_fma(c, dist.x, -(s * dist.y)), cc_fma(s, dist.x, c * dist.y), dist.z, dist.w);
+}
+
+// shapes/simple3d.cl:28-39
+CC_DEV float4 cc_revolution_from(float4 flat, float4 co)
+{
+    float len = cc_len2(co.x, co.z);
+    bool zero = len == 0.0f;
+    float mult = zero ? flat.x : cc_div(flat.x, len);
+    float cx = zero ? 1.0f : co.x;
+    return make_float4(cx * mult, flat.y, co.z * mult, flat.w);
+}
+
+#endif

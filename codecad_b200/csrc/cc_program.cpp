@@ -1,0 +1,392 @@
+// Program loader: codecad wire format -> device microcode (see cc_microcode.h).
+//
+// Wire format: /root/reference/codecad/nodes/program.py:39-71 (encoding),
+// /root/reference/codecad/nodes/node.py:12-56 (opcode table), interpreter semantics
+// /root/reference/codecad/nodes/codegen.py:17-63.  Host-only code; compiled with
+// -ffp-contract=off because the per-instruction constants below are part of the
+// canonical arithmetic (DESIGN.md "cc-arith") and must not be fused.
+#include "cc_internal.h"
+
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+enum WireOp {
+    W_RETURN = 0, W_STORE, W_LOAD, W_RECTANGLE, W_CIRCLE, W_REGULAR_POLYGON2D, W_POLYGON2D,
+    W_SPHERE, W_HALF_SPACE, W_REVOLUTION_TO, W_TWIST_REVOLUTION_TO,
+    W_INITIAL_TRANSFORMATION_TO, W_TRANSFORMATION_TO, W_TRANSFORMATION_FROM, W_MIRROR,
+    W_SYMMETRICAL_TO, W_OFFSET, W_SHELL, W_REPETITION, W_CIRCULAR_REPETITION_TO,
+    W_CIRCULAR_REPETITION_FROM, W_INVOLUTE_GEAR, W_EXTRUSION, W_REVOLUTION_FROM,
+    W_TWIST_REVOLUTION_FROM, W_SYMMETRICAL_FROM, W_UNION, W_INTERSECTION, W_SUBTRACTION,
+    W_COUNT
+};
+
+// parameter words and arity per wire opcode (node.py:18-52); -1 = polygon2d (1 + 2n)
+const int kParams[W_COUNT] = {0, 0, 0, 2, 1, 2, -1, 1, 0, 0, 2, 7, 7, 4, 0, 0,
+                              1, 1, 3, 1, 1, 2, 1, 0, 3, 0, 1, 1, 1};
+const int kArity[W_COUNT] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 1, 1, 1, 1,
+                             1, 1, 1, 1, 2, 1, 2, 2, 2, 2, 2, 2, 2};
+const unsigned kRegisterCount = 512;  // EVAL_REGISTER_COUNT, nodes/__init__.py:6
+
+const float kPiF = 3.14159274101257324f;
+const float kPi2F = 1.57079637050628662f;
+
+struct WireIns {
+    int op;
+    unsigned reg;
+    const float *p;
+    int np;
+};
+
+struct Interval {
+    int store_idx;  // wire instruction index of the _store
+    int last_read;  // wire instruction index of the last read, -1 = dead
+    bool point_only;  // every read is the point operand of a *_from / extrusion op
+    unsigned slot;
+};
+
+bool is_point_consumer(int op)
+{
+    return op == W_EXTRUSION || op == W_REVOLUTION_FROM || op == W_TWIST_REVOLUTION_FROM ||
+           op == W_SYMMETRICAL_FROM || op == W_CIRCULAR_REPETITION_FROM;
+}
+
+// quaternion (x,y,z,w) -> row-major 3x3 of the map  p -> 2 v (v.p) + 2 w (v x p) + (w^2 - v.v) p
+// (shapes/common.cl:1-6) evaluated in double, optionally divided by |q|^2
+// (shapes/common.cl:100-110), then rounded to fp32.  Same expression tree as the
+// oracle's quat_matrix().
+void quat_matrix(const float *q, bool divide_by_scale, float *m, float *scale)
+{
+    double x = q[0], y = q[1], z = q[2], w = q[3];
+    double k = w * w - (x * x + y * y + z * z);
+    double d[9];
+    d[0] = 2.0 * (x * x) + k;
+    d[1] = 2.0 * (x * y - w * z);
+    d[2] = 2.0 * (x * z + w * y);
+    d[3] = 2.0 * (x * y + w * z);
+    d[4] = 2.0 * (y * y) + k;
+    d[5] = 2.0 * (y * z - w * x);
+    d[6] = 2.0 * (x * z - w * y);
+    d[7] = 2.0 * (y * z + w * x);
+    d[8] = 2.0 * (z * z) + k;
+    double s = (x * x + y * y) + (z * z + w * w);
+    for (int i = 0; i < 9; ++i) m[i] = (float)(divide_by_scale ? d[i] / s : d[i]);
+    if (scale) *scale = (float)s;
+}
+
+struct Emitter {
+    std::vector<uint32_t> code;
+    size_t last_header = (size_t)-1;  // index of the most recent instruction header
+
+    float *emit(uint32_t op, uint32_t src, uint32_t len_words)
+    {
+        last_header = code.size();
+        code.resize(code.size() + len_words, 0u);
+        code[last_header] = CC_HDR(op, src, CC_SLOT_NONE);
+        return reinterpret_cast<float *>(&code[last_header + 1]);
+    }
+    bool can_fold_store() const
+    {
+        if (last_header == (size_t)-1) return false;
+        uint32_t h = code[last_header];
+        return CC_HDR_DST(h) == CC_SLOT_NONE && CC_HDR_OP(h) != MOP_RETURN;
+    }
+    void fold_store(uint32_t dst)
+    {
+        uint32_t h = code[last_header];
+        code[last_header] = CC_HDR(CC_HDR_OP(h), CC_HDR_SRC(h), dst);
+    }
+};
+
+}  // namespace
+
+int cc_decode_program(const float *words, uint32_t n_words, cc_decoded *out, std::string *err)
+{
+    // ---- 1. parse + validate ------------------------------------------------------------
+    std::vector<WireIns> ins;
+    uint32_t pc = 0;
+    unsigned max_reg = 0;
+    bool any_reg = false;
+    for (;;) {
+        if (pc >= n_words) {
+            *err = "program ends without _return";
+            return CC_ERR_INVALID_PROGRAM;
+        }
+        float wf = words[pc];
+        if (!(wf >= 0.0f) || wf >= (float)(W_COUNT * kRegisterCount) || wf != std::floor(wf)) {
+            *err = "invalid instruction word at " + std::to_string(pc);
+            return CC_ERR_INVALID_PROGRAM;
+        }
+        unsigned instruction = (unsigned)wf;
+        int op = (int)(instruction / kRegisterCount);
+        unsigned reg = instruction % kRegisterCount;
+        int np = kParams[op];
+        if (np < 0) {
+            if (pc + 1 >= n_words || !(words[pc + 1] >= 1.0f) || words[pc + 1] > 65536.0f ||
+                words[pc + 1] != std::floor(words[pc + 1])) {
+                *err = "invalid polygon2d vertex count at " + std::to_string(pc);
+                return CC_ERR_INVALID_PROGRAM;
+            }
+            np = 1 + 2 * (int)words[pc + 1];
+        }
+        if (pc + 1 + (uint32_t)np > n_words) {
+            *err = "truncated parameters at " + std::to_string(pc);
+            return CC_ERR_INVALID_PROGRAM;
+        }
+        ins.push_back(WireIns{op, reg, words + pc + 1, np});
+        if (op == W_STORE || op == W_LOAD || kArity[op] == 2) {
+            if (reg + 1 > max_reg) max_reg = reg + 1;
+            any_reg = true;
+        }
+        pc += 1 + (uint32_t)np;
+        if (op == W_RETURN) break;
+    }
+    if (ins.size() < 2 || kArity[ins[0].op] != 0) {
+        // the first instruction must produce a value from the grid point
+        *err = "program must start with initial_transformation_to";
+        return CC_ERR_INVALID_PROGRAM;
+    }
+    (void)any_reg;
+
+    // ---- 2. liveness of the wire registers ------------------------------------------------
+    std::vector<Interval> intervals;
+    std::vector<int> open(kRegisterCount, -1);       // reg -> interval index
+    std::vector<int> read_interval(ins.size(), -1);  // wire idx -> interval it reads
+    std::vector<int> store_interval(ins.size(), -1);
+    for (size_t i = 0; i < ins.size(); ++i) {
+        const WireIns &w = ins[i];
+        if (w.op == W_STORE) {
+            intervals.push_back(Interval{(int)i, -1, true, CC_SLOT_NONE});
+            open[w.reg] = (int)intervals.size() - 1;
+            store_interval[i] = open[w.reg];
+        } else if (w.op == W_LOAD || kArity[w.op] == 2) {
+            int iv = open[w.reg];
+            if (iv < 0) {
+                *err = "instruction " + std::to_string(i) + " reads register " +
+                       std::to_string(w.reg) + " before any _store";
+                return CC_ERR_INVALID_PROGRAM;
+            }
+            intervals[iv].last_read = (int)i;
+            if (!is_point_consumer(w.op)) intervals[iv].point_only = false;
+            read_interval[i] = iv;
+        }
+    }
+
+    // ---- 3. P register: short point values stay in hardware registers -----------------------
+    int p_busy_until = -1;
+    uint32_t n_p = 0;
+    for (Interval &iv : intervals) {
+        if (iv.last_read < 0 || !iv.point_only) continue;
+        if (iv.store_idx > p_busy_until) {
+            iv.slot = CC_SLOT_P;
+            p_busy_until = iv.last_read;
+            ++n_p;
+        }
+    }
+
+    // ---- 4. linear-scan slot allocation for everything else ---------------------------------
+    uint32_t n_slots = 0;
+    {
+        std::vector<unsigned> free_slots;
+        // intervals are already sorted by store_idx; expire by last_read
+        std::vector<int> active;
+        for (size_t k = 0; k < intervals.size(); ++k) {
+            Interval &iv = intervals[k];
+            if (iv.last_read < 0 || iv.slot == CC_SLOT_P) continue;
+            for (size_t a = 0; a < active.size();) {
+                if (intervals[active[a]].last_read < iv.store_idx) {
+                    free_slots.push_back(intervals[active[a]].slot);
+                    active[a] = active.back();
+                    active.pop_back();
+                } else {
+                    ++a;
+                }
+            }
+            if (!free_slots.empty()) {
+                // lowest free slot keeps the hot set dense
+                size_t best = 0;
+                for (size_t f = 1; f < free_slots.size(); ++f)
+                    if (free_slots[f] < free_slots[best]) best = f;
+                iv.slot = free_slots[best];
+                free_slots[best] = free_slots.back();
+                free_slots.pop_back();
+            } else {
+                iv.slot = n_slots++;
+            }
+            active.push_back((int)k);
+        }
+    }
+    if (n_slots > CC_MAX_SLOTS) {
+        *err = "program needs " + std::to_string(n_slots) + " live values";
+        return CC_ERR_TOO_LARGE;
+    }
+
+    // ---- 5. emit microcode ------------------------------------------------------------------
+    Emitter e;
+    uint32_t fmin = 0, fmax = 0, n_micro = 0;
+    auto cost = [&](uint32_t lo, uint32_t hi) { fmin += lo; fmax += hi; };
+    for (size_t i = 0; i < ins.size(); ++i) {
+        const WireIns &w = ins[i];
+        const float *p = w.p;
+        uint32_t src = CC_SLOT_NONE;
+        if (read_interval[i] >= 0) src = intervals[read_interval[i]].slot;
+        float *q;
+        switch (w.op) {
+        case W_RETURN: e.emit(MOP_RETURN, CC_SLOT_NONE, CC_LEN_0); break;
+        case W_STORE: {
+            const Interval &iv = intervals[store_interval[i]];
+            if (iv.last_read < 0) continue;  // dead store
+            if (e.can_fold_store()) {
+                e.fold_store(iv.slot);
+                continue;
+            }
+            e.emit(MOP_NOP, CC_SLOT_NONE, CC_LEN_0);
+            e.fold_store(iv.slot);
+            break;
+        }
+        case W_LOAD: e.emit(MOP_LOAD, src, CC_LEN_0); break;
+        case W_RECTANGLE:
+            q = e.emit(MOP_RECTANGLE, src, CC_LEN_0);
+            q[0] = p[0]; q[1] = p[1];
+            cost(2, 17);
+            break;
+        case W_CIRCLE:
+            q = e.emit(MOP_CIRCLE, src, CC_LEN_0);
+            q[0] = p[0];
+            cost(7, 7);
+            break;
+        case W_REGULAR_POLYGON2D:
+            q = e.emit(MOP_REGPOLY, src, CC_LEN_7);
+            q[0] = p[0]; q[1] = p[1];
+            q[2] = p[1] * (float)std::sin((double)p[0]);  // simple2d.cl:25
+            q[3] = p[1] * (float)std::cos((double)p[0]);  // simple2d.cl:45
+            q[4] = 2.0f * p[0];
+            cost(25, 40);
+            break;
+        case W_POLYGON2D: {
+            int n = (int)p[0];
+            uint32_t len = 4 + (uint32_t)((CC_POLY_EDGE_WORDS * n + 3) / 4) * 4;
+            q = e.emit(MOP_POLYGON, src, len);
+            q[0] = (float)n;
+            float *eg = q + 3;  // edges start at word 4 of the instruction
+            for (int k = 0; k < n; ++k) {
+                int j = (k + n - 1) % n;  // previous vertex, polygons2d.cl:13,17-18
+                float px = p[1 + 2 * j], py = p[2 + 2 * j];
+                float cx = p[1 + 2 * k], cy = p[2 + 2 * k];
+                float dx = cx - px, dy = cy - py;
+                eg[0] = px; eg[1] = py; eg[2] = dx; eg[3] = dy;
+                eg[4] = 1.0f / std::fmaf(dx, dx, dy * dy);
+                eg[5] = cy;
+                eg += CC_POLY_EDGE_WORDS;
+            }
+            cost(10 + 15u * (uint32_t)n, 10 + 22u * (uint32_t)n);
+            break;
+        }
+        case W_SPHERE:
+            q = e.emit(MOP_SPHERE, src, CC_LEN_0);
+            q[0] = p[0];
+            cost(11, 11);
+            break;
+        case W_HALF_SPACE: e.emit(MOP_HALF_SPACE, src, CC_LEN_0); break;
+        case W_REVOLUTION_TO: e.emit(MOP_REV_TO, src, CC_LEN_0); cost(4, 4); break;
+        case W_TWIST_REVOLUTION_TO:
+            q = e.emit(MOP_TWIST_TO, src, CC_LEN_0);
+            q[0] = p[0]; q[1] = p[1];
+            cost(16, 16);
+            break;
+        case W_INITIAL_TRANSFORMATION_TO:
+        case W_TRANSFORMATION_TO:
+            q = e.emit(w.op == W_TRANSFORMATION_TO ? MOP_T_TO : MOP_T_INIT, src, CC_LEN_T);
+            quat_matrix(p, false, q, nullptr);
+            q[9] = p[4]; q[10] = p[5]; q[11] = p[6];
+            cost(42, 42);
+            break;
+        case W_TRANSFORMATION_FROM:
+            q = e.emit(MOP_T_FROM, src, CC_LEN_T);
+            quat_matrix(p, true, q, &q[9]);
+            cost(50, 50);
+            break;
+        case W_MIRROR: e.emit(MOP_MIRROR, src, CC_LEN_0); break;
+        case W_SYMMETRICAL_TO: e.emit(MOP_SYM_TO, src, CC_LEN_0); break;
+        case W_OFFSET:
+            q = e.emit(MOP_OFFSET, src, CC_LEN_0);
+            q[0] = p[0];
+            cost(1, 1);
+            break;
+        case W_SHELL:
+            q = e.emit(MOP_SHELL, src, CC_LEN_0);
+            q[0] = p[0];
+            cost(1, 1);
+            break;
+        case W_REPETITION:
+            q = e.emit(MOP_REPETITION, src, CC_LEN_0);
+            q[0] = p[0]; q[1] = p[1]; q[2] = p[2];
+            cost(3, 3);
+            break;
+        case W_CIRCULAR_REPETITION_TO:
+        case W_CIRCULAR_REPETITION_FROM:
+            q = e.emit(w.op == W_CIRCULAR_REPETITION_TO ? MOP_CREP_TO : MOP_CREP_FROM, src, CC_LEN_0);
+            q[0] = p[0]; q[1] = 2.0f * p[0];
+            cost(14, 14);
+            break;
+        case W_INVOLUTE_GEAR: {
+            q = e.emit(MOP_GEAR, src, CC_LEN_7);
+            float pa = p[1];
+            q[0] = (float)std::cos((double)pa);                          // gears.cl:2
+            q[1] = kPiF / p[0];                                          // gears.cl:3
+            q[2] = (q[1] * 0.5f + (float)std::tan((double)pa)) - pa;     // gears.cl:6
+            q[3] = 2.0f * q[1];
+            q[4] = q[0] * q[0];
+            cost(20, 30);
+            break;
+        }
+        case W_EXTRUSION:
+            q = e.emit(MOP_EXTRUSION, src, CC_LEN_0);
+            q[0] = p[0];
+            cost(1, 16);
+            break;
+        case W_REVOLUTION_FROM: e.emit(MOP_REV_FROM, src, CC_LEN_0); cost(7, 7); break;
+        case W_TWIST_REVOLUTION_FROM: {
+            q = e.emit(MOP_TWIST_FROM, src, CC_LEN_7);
+            float minorR = p[0], r = p[1], twist = p[2];
+            float arg = std::fmin(kPiF, (kPi2F * kPi2F) / std::fabs(twist));
+            float lip = (((r - minorR) * 2.0f) * (float)std::sin((double)arg)) / minorR;
+            q[0] = minorR; q[1] = r; q[2] = twist;
+            q[3] = std::fmin(1.0f, lip);  // simple3d.cl:86-88
+            q[4] = 0.05f * r;             // simple3d.cl:70
+            cost(15, 40);
+            break;
+        }
+        case W_SYMMETRICAL_FROM: e.emit(MOP_SYM_FROM, src, CC_LEN_0); break;
+        case W_UNION:
+        case W_INTERSECTION:
+        case W_SUBTRACTION: {
+            bool rounded = p[0] >= 0.0f;  // common.cl:47
+            uint32_t base = w.op == W_UNION ? MOP_UNION : (w.op == W_INTERSECTION ? MOP_ISECT : MOP_SUB);
+            q = e.emit(base + (rounded ? 1u : 0u), src, CC_LEN_0);
+            q[0] = p[0];
+            if (rounded) cost(9, 21);
+            break;
+        }
+        default:
+            *err = "internal: unhandled opcode";
+            return CC_ERR_INVALID_PROGRAM;
+        }
+        ++n_micro;
+    }
+
+    out->microcode.swap(e.code);
+    out->info.n_words = pc;
+    out->info.n_instructions = (uint32_t)ins.size();
+    out->info.n_micro_ops = n_micro;
+    out->info.n_micro_words = (uint32_t)out->microcode.size();
+    out->info.n_wire_registers = max_reg;
+    out->info.n_slots = n_slots;
+    out->info.n_p_stores = n_p;
+    out->info.flops_min = fmin;
+    out->info.flops_max = fmax;
+    return CC_OK;
+}

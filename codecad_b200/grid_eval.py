@@ -1,0 +1,79 @@
+"""Dense-grid evaluation: the reference's `grid_eval` / `grid_eval_pymcubes` kernels
+(/root/reference/codecad/grid_eval.cl:2-34; the reference's grid_eval.py only registers
+the .cl).  Besides the `.k.` kernel proxy (cl_util) this module offers the call a user
+of a dense grid actually wants: evaluate a (slab of a) grid into host memory.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .cl_util.buffer import Buffer
+from .geometry import FLOAT4
+from .nodes import make_program_buffer
+
+
+def slab_range(nx, rank, world):
+    """x-range [x0, x1) of the slab owned by `rank` when nx planes are split over `world`
+    ranks (contiguous in the INDEX3 layout, cl_util/indexing.h:4)."""
+    base, rem = divmod(int(nx), int(world))
+    x0 = rank * base + min(rank, rem)
+    return x0, x0 + base + (1 if rank < rem else 0)
+
+
+def _eval(shape, corner, step, dims, layout, x_offset, out, to_host):
+    program = make_program_buffer(shape)
+    nx, ny, nz = (int(d) for d in dims)
+    if to_host:
+        if layout == _lib.LAYOUT_INDEX3_FLOAT4:
+            want_shape, dtype = (nx, ny, nz), FLOAT4
+        else:
+            want_shape, dtype = (ny, nx, nz), np.float32
+        if out is None:
+            holder = Buffer.__new__(Buffer)  # pinned host array without a device twin
+            from .cl_util.buffer import _Pinned
+            pin = _Pinned(nx * ny * nz * np.dtype(dtype).itemsize)
+            out = pin.array(dtype, want_shape)
+            _PINS[id(out)] = pin
+            del holder
+        if out.nbytes < nx * ny * nz * np.dtype(dtype).itemsize:
+            raise RuntimeError("Not enough space to store the grid")
+        _lib.check(_lib.lib().cc_grid_eval_to_host(program.handle, _lib.f3(corner), float(np.float32(step)),
+                                                   nx, ny, nz, int(x_offset), layout, out.ctypes.data))
+        return out
+    if out.size < nx * ny * nz * (16 if layout == _lib.LAYOUT_INDEX3_FLOAT4 else 4):
+        raise RuntimeError("Output buffer too small for the grid")
+    _lib.check(_lib.lib().cc_grid_eval(program.handle, _lib.f3(corner), float(np.float32(step)),
+                                       nx, ny, nz, int(x_offset), layout, out.device_ptr, None))
+    return out
+
+
+_PINS = {}
+
+
+def release_host_grid(arr):
+    """Free the pinned memory behind an array returned by grid_eval(out=None)."""
+    _PINS.pop(id(arr), None)
+
+
+def grid_eval(shape, corner, step, dims, x_offset=0, out=None, device_out=None):
+    """Evaluate `shape` on the grid corner + step*(x + x_offset, y, z), x < dims[0] ...
+
+    Returns a host array [nx][ny][nz] of float4 (grad.x, grad.y, grad.z, distance) — the
+    reference kernel's INDEX3 layout.  `out` may be a pre-allocated (ideally pinned) host
+    array.  With `device_out` (a cl_util.Buffer) the result stays on the device."""
+    if device_out is not None:
+        return _eval(shape, corner, step, dims, _lib.LAYOUT_INDEX3_FLOAT4, x_offset, device_out, False)
+    return _eval(shape, corner, step, dims, _lib.LAYOUT_INDEX3_FLOAT4, x_offset, out, True)
+
+
+def grid_eval_pymcubes(shape, corner, step, dims, out=None, device_out=None):
+    """Distance-only grid in the y-flipped layout PyMCubes wants (grid_eval.cl:16-18):
+    host array [ny (flipped)][nx][nz] of float32."""
+    if device_out is not None:
+        return _eval(shape, corner, step, dims, _lib.LAYOUT_PYMCUBES_FLOAT, 0, device_out, False)
+    return _eval(shape, corner, step, dims, _lib.LAYOUT_PYMCUBES_FLOAT, 0, out, True)
+
+
+def synchronize():
+    _lib.check(_lib.lib().cc_synchronize())

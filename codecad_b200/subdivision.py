@@ -1,0 +1,124 @@
+"""Adaptive block subdivision — same signatures and results as the reference's
+/root/reference/codecad/subdivision.py (calculate_block_sizes :116-166, subdivision
+:169-253); the per-block `_Helper` launch/readback loop (:14-113) is replaced by one
+device-resident pass per level inside libcodecad_b200 (cc_subdivide).
+"""
+import ctypes
+import math
+
+import numpy as np
+
+from . import _lib
+from .geometry import BoundingBox, Vector, as_vector
+from .nodes import make_program_buffer
+
+
+def _round_up_to(x, y):
+    return ((x + y - 1) // y) * y
+
+
+def _clamp(v, lower, upper):
+    return max(lower, min(v, upper))
+
+
+def calculate_block_sizes(box, dimension, resolution, grid_size, overlap, level_size_multiplier=1):
+    """subdivision.py:116-166 — top..leaf list of (cell_size, Vector level_dims)."""
+    if grid_size % level_size_multiplier != 0:
+        raise ValueError("Grid size must be divisible by level_size_multiplier")
+
+    block_sizes = []
+    if dimension == 2:
+        level_size = Vector(grid_size, grid_size, 1)
+        box = BoundingBox(as_vector(box[0]).flattened(), as_vector(box[1]).flattened())
+    elif dimension == 3:
+        level_size = Vector.splat(grid_size)
+    else:
+        assert False
+
+    box_int_size = ((as_vector(box[1]) - as_vector(box[0])) / resolution).applyfunc(math.ceil)
+    box_max_int_size = box_int_size.max()
+    cell_size = 1
+
+    while True:
+        block_sizes.append((cell_size, level_size))
+        overlap_delta = 1 if overlap and len(block_sizes) == 1 else 0
+        next_cell_size = cell_size * (grid_size - overlap_delta)
+        if next_cell_size >= box_max_int_size:
+            break
+        cell_size = next_cell_size
+
+    block_sizes[-1] = (
+        cell_size,
+        Vector(*(
+            _clamp(_round_up_to(math.ceil(x) + overlap_delta, level_size_multiplier), 1, s)
+            for x, s in zip(box_int_size / cell_size, level_size)
+        )),
+    )
+    block_sizes.reverse()
+    return block_sizes
+
+
+def _levels(block_sizes):
+    arr = (_lib.Level * len(block_sizes))()
+    for i, (cell, dims) in enumerate(block_sizes):
+        arr[i].cell_size = int(cell)
+        arr[i].nx, arr[i].ny, arr[i].nz = int(dims[0]), int(dims[1]), int(dims[2])
+    return arr
+
+
+def subdivide_int_corners(program, origin, resolution, block_sizes, dimension, rank=0, world=1):
+    """int64 array [n][3]: int corners (resolution units) of this rank's leaf blocks, in
+    deterministic breadth-first order."""
+    out = ctypes.POINTER(ctypes.c_int64)()
+    count = ctypes.c_uint64()
+    org = (ctypes.c_double * 3)(float(origin[0]), float(origin[1]), float(origin[2]))
+    _lib.check(_lib.lib().cc_subdivide(program.handle, org, float(resolution), _levels(block_sizes),
+                                       len(block_sizes), int(dimension), int(rank), int(world),
+                                       ctypes.byref(out), ctypes.byref(count)))
+    n = int(count.value)
+    if n == 0:
+        return np.zeros((0, 3), np.int64)
+    try:
+        return np.ctypeslib.as_array(out, shape=(n, 3)).copy()
+    finally:
+        _lib.lib().cc_free(out)
+
+
+def subdivision(shape, resolution, overlap_edge_samples=True, grid_size=None, rank=0, world=1):
+    """subdivision.py:169-253.  Returns (program_buffer, max_grid_dims,
+    [(grid_dims, corner, step, int_corner, int_step), ...]) for the leaf blocks.
+
+    `rank` / `world` (not in the reference) select the share of one rank when the first
+    refined level is dealt round-robin over several GPUs; the union over ranks is the
+    reference's block set."""
+    if grid_size is None:
+        grid_size = 128
+
+    assert resolution > 0, "Non-positive resolution makes no sense"
+    assert grid_size > 1, "Grid needs to be at least 2x2x2"
+    assert grid_size <= 256, "Grid size > 256 would cause overflows in returned index list."
+
+    program_buffer = make_program_buffer(shape)
+
+    bb = shape.bounding_box()
+    box = BoundingBox(as_vector(bb[0]), as_vector(bb[1])).expanded_additive(resolution / 2)
+    dimension = shape.dimension()
+    if dimension == 2:
+        box = box.flattened()
+
+    block_sizes = calculate_block_sizes(box, dimension, resolution, grid_size, overlap_edge_samples)
+
+    if len(block_sizes) == 1:
+        blocks = [(block_sizes[0][1], box.a, resolution, Vector(0, 0, 0), 1)] if rank == 0 else []
+        return program_buffer, block_sizes[0][1], blocks
+
+    corners = subdivide_int_corners(program_buffer, box.a, resolution, block_sizes, dimension, rank, world)
+    leaf_step_int, leaf_dims = block_sizes[-1]
+    leaf_step = leaf_step_int * resolution
+    final_blocks = []
+    for ix, iy, iz in corners.tolist():
+        int_pos = Vector(ix, iy, iz)
+        # subdivision.py:101  pos = int_pos * resolution + origin   (float64)
+        pos = int_pos * resolution + box.a
+        final_blocks.append((leaf_dims, pos, leaf_step, int_pos, leaf_step_int))
+    return program_buffer, leaf_dims, final_blocks

@@ -1,0 +1,157 @@
+/* libcodecad_b200 — C ABI of the B200-native codecad SDF hot path.
+ *
+ * This library replaces the reference's OpenCL layer (codecad/cl_util + the .cl
+ * kernels).  Every entry point is what a foreign-function binding of the reference
+ * would bind in place of a pyopencl call; the reference interface each one replaces is
+ * cited as /root/reference-relative file:line.  The Python ctypes binding lives in
+ * codecad_b200/_lib.py; INTEGRATION.md shows the reference-side shim.
+ *
+ * Conventions: plain pointers and sizes only.  Every function returning `int` returns
+ * 0 on success and a negative cc_status on failure; cc_last_error() then returns a
+ * thread-local message.  One process drives one GPU (one rank per GPU under
+ * torchrun); the library owns one CUDA context, one compute stream and one copy
+ * stream.  Host pointers are caller-owned; device pointers and handles are
+ * library-owned until the matching *_free / *_destroy.  There is NO CPU fallback: with
+ * no usable CUDA device cc_init() fails and every other call fails after it.
+ */
+#ifndef CODECAD_B200_H
+#define CODECAD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum cc_status {
+    CC_OK = 0,
+    CC_ERR_CUDA = -1,          /* a CUDA runtime call failed (message has the detail)   */
+    CC_ERR_NOT_INITIALIZED = -2,
+    CC_ERR_INVALID_PROGRAM = -3, /* malformed word stream (bad opcode / truncated)      */
+    CC_ERR_INVALID_ARGUMENT = -4,
+    CC_ERR_TOO_LARGE = -5      /* program or register demand exceeds device limits      */
+} cc_status;
+
+typedef struct cc_program cc_program; /* decoded node program resident on the device */
+typedef struct cc_event cc_event;     /* completion marker on a library stream        */
+
+/* output layouts of cc_grid_eval */
+#define CC_LAYOUT_INDEX3_FLOAT4 0 /* grid_eval.cl:23-34  out[z + nz*(y + ny*x)] = (grad.xyz, dist) */
+#define CC_LAYOUT_PYMCUBES_FLOAT 1 /* grid_eval.cl:2-21   out[z + (x + (ny-1-y)*nx)*nz] = dist      */
+
+/* ---- context: replaces OpenCLManager.__init__  cl_util/opencl_manager.py:87-98 ------- */
+int cc_init(int device);            /* idempotent for the same device */
+void cc_shutdown(void);
+int cc_device_count(void);          /* 0 when no CUDA device/driver is usable */
+const char *cc_last_error(void);
+typedef struct cc_device_info {
+    int device, sm_count, sm_clock_khz, l2_bytes;
+    size_t total_mem;
+    char name[64];
+} cc_device_info;
+int cc_get_device_info(cc_device_info *out);
+int cc_synchronize(void);
+/* counters since cc_init / the last reset: kernels launched by this library and grid
+ * points evaluated (the reference's dead `kernel_invocations` / `function_evaluations`
+ * mass_properties.py:66-67,110-111). */
+int cc_get_counters(uint64_t *kernel_launches, uint64_t *points_evaluated);
+void cc_reset_counters(void);
+/* tuning knobs, mainly for bench.py / profiling: points per thread (1,2,4; 0 = auto),
+ * and where the microcode is fetched from (0 = auto, 1 = __constant__, 2 = shared). */
+int cc_set_tuning(int points_per_thread, int program_space);
+
+/* ---- programs: replaces make_program_buffer  nodes/program.py:79-84 ------------------- */
+/* Copies and validates `n_words` float32 words (opcode table nodes/node.py:12-56,
+ * encoding nodes/program.py:39-71), decodes them to device microcode, renames the
+ * 512 wire registers to a dense slot set, uploads. */
+int cc_program_create(const float *words, uint32_t n_words, cc_program **out);
+void cc_program_destroy(cc_program *prog);
+typedef struct cc_program_info {
+    uint32_t n_words;        /* wire words consumed (up to and including _return)   */
+    uint32_t n_instructions; /* wire instructions                                    */
+    uint32_t n_micro_ops;    /* decoded instructions (stores folded)                 */
+    uint32_t n_micro_words;  /* decoded length in 32-bit words                       */
+    uint32_t n_wire_registers; /* highest wire register used + 1                     */
+    uint32_t n_slots;        /* shared-memory value slots after liveness renaming    */
+    uint32_t n_p_stores;     /* stores redirected to the hardware P register         */
+    uint32_t flops_min;      /* static algorithmic flop/point, SURVEY.md 8(a3) rules */
+    uint32_t flops_max;
+} cc_program_info;
+int cc_program_get_info(const cc_program *prog, cc_program_info *out);
+/* copies the decoded microcode (for tests / disassembly); returns words written */
+int cc_program_get_microcode(const cc_program *prog, uint32_t *out, uint32_t capacity);
+
+/* ---- buffers and events: replaces cl_util.Buffer  cl_util/cl_buffer.py:9-131 ---------- */
+int cc_buffer_alloc(size_t bytes, void **dptr);
+int cc_buffer_free(void *dptr);
+int cc_host_alloc(size_t bytes, void **hptr); /* pinned; ALLOC_HOST_PTR cl_buffer.py:36-40 */
+int cc_host_free(void *hptr);
+int cc_memcpy_h2d_async(void *dptr, const void *hptr, size_t bytes, cc_event **ev);
+int cc_memcpy_d2h_async(void *hptr, const void *dptr, size_t bytes, cc_event **ev);
+int cc_memset_async(void *dptr, int value, size_t bytes, cc_event **ev);
+int cc_event_record(cc_event **ev);     /* on the compute stream */
+int cc_event_wait(cc_event *ev);        /* pyopencl.Event.wait()  */
+int cc_event_elapsed_ms(cc_event *start, cc_event *end, float *ms); /* Event.profile */
+void cc_event_destroy(cc_event *ev);
+
+/* ---- kernels with the reference's per-launch semantics (the `opencl_manager.k.*`
+ *      proxy, cl_util/opencl_manager.py:73-84).  `ev` may be NULL. ---------------------- */
+
+/* grid_eval / grid_eval_pymcubes  grid_eval.cl:2-34.
+ * point(x,y,z) = corner + step * (x + x_offset, y, z); d_out holds nx*ny*nz elements of
+ * the layout's type.  x_offset lets a rank evaluate a slab of a larger grid with
+ * bit-identical coordinates. */
+int cc_grid_eval(const cc_program *prog, const float corner[3], float step,
+                 uint32_t nx, uint32_t ny, uint32_t nz, uint32_t x_offset, int layout,
+                 void *d_out, cc_event **ev);
+
+/* Same, result delivered to HOST memory: slabs of the grid are evaluated into a device
+ * ring and copied out on the copy stream while the next slab computes.  Blocking.
+ * Replaces kernel + Buffer.read()  (rendering/mesh.py:53-61). */
+int cc_grid_eval_to_host(const cc_program *prog, const float corner[3], float step,
+                         uint32_t nx, uint32_t ny, uint32_t nz, uint32_t x_offset, int layout,
+                         void *h_out);
+
+/* subdivision_step  subdivision.cl:12-30: cells with -thr < dist < thr are appended to
+ * d_list as uchar4 (x,y,z,0) starting at *d_counter, which is advanced.  Unlike the
+ * reference's atomic_inc the order is deterministic: INDEX3 order (x slowest). */
+int cc_subdivision_step(const cc_program *prog, const float corner[3], float step, float threshold,
+                        uint32_t nx, uint32_t ny, uint32_t nz,
+                        uint32_t *d_counter, uint8_t *d_list, cc_event **ev);
+
+/* mass_properties  mass_properties.cl:7-56: dist <= -thr adds the 10 index products
+ * (order xx,xy,xz,x,yy,yz,y,zz,z,n) to d_sums; -thr < dist < thr appends to d_list. */
+int cc_mass_properties_step(const cc_program *prog, const float corner[3], float step, float threshold,
+                            uint32_t nx, uint32_t ny, uint32_t nz, uint32_t *d_sums,
+                            uint32_t *d_counter, uint8_t *d_list, cc_event **ev);
+
+/* ---- whole-hierarchy fast paths (device-resident work lists, one launch per level) ---- */
+typedef struct cc_level {
+    int64_t cell_size;   /* in leaf units (subdivision.calculate_block_sizes [i][0]) */
+    uint32_t nx, ny, nz; /* grid dims of a block at this level ([i][1])              */
+} cc_level;
+
+/* subdivision()  subdivision.py:169-253 for n_levels >= 2.  origin = expanded bbox.a,
+ * float64 like the reference's host math.  Returns the int corners (resolution units)
+ * of the leaf blocks owned by `rank` of `world` (blocks of the first refined level are
+ * dealt round-robin; every rank evaluates the tiny top level).  *out_corners is a
+ * malloc'ed int64[n][3] released with cc_free. */
+int cc_subdivide(const cc_program *prog, const double origin[3], double resolution,
+                 const cc_level *levels, uint32_t n_levels, int dimension,
+                 uint32_t rank, uint32_t world, int64_t **out_corners, uint64_t *out_count);
+
+/* mass_properties()  mass_properties.py:30-177: returns the ten integrals
+ * (one,x,y,z,xx,yy,zz,xy,xz,yz) over the part of the hierarchy owned by `rank`; the
+ * caller sums them over ranks (NCCL all-reduce of 10 doubles) and finishes with
+ * mass_properties.py:179-229.  stats[0..3] = launches, evaluated cells, blocks, levels. */
+int cc_mass_properties(const cc_program *prog, const double box_a[3], double resolution,
+                       const cc_level *levels, uint32_t n_levels,
+                       uint32_t rank, uint32_t world, double integrals[10], uint64_t stats[4]);
+
+void cc_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CODECAD_B200_H */

@@ -1,0 +1,38 @@
+"""Loader for tests/golden/scenes.npz (made by tools/make_fixtures.py from the
+reference's own node compiler)."""
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+class Scene:
+    def __init__(self, name, words, meta):
+        self.name = name
+        self.words = np.ascontiguousarray(words, dtype=np.float32)
+        self.dimension = int(meta[0])
+        self.box_a = tuple(float(v) for v in meta[1:4])
+        self.box_b = tuple(float(v) for v in meta[4:7])
+        self.feature_size = float(meta[7])
+
+    def compiled(self):
+        from codecad_b200 import CompiledScene
+        return CompiledScene(self.words, self.dimension, self.box_a, self.box_b, self.feature_size, self.name)
+
+    def grid(self, n, margin=1.02):
+        """cubic n^3 grid covering the bounding box: SURVEY.md 8(d) convention."""
+        size = max(b - a for a, b in zip(self.box_a, self.box_b))
+        step = margin * size / n
+        mid = [(a + b) / 2 for a, b in zip(self.box_a, self.box_b)]
+        corner = [m - step * (n - 1) / 2 for m in mid]
+        return np.array(corner, np.float64).astype(np.float32), np.float32(step)
+
+
+def load_scenes():
+    z = np.load(os.path.join(GOLDEN, "scenes.npz"))
+    names = sorted(k[:-6] for k in z.files if k.endswith(".words"))
+    return {n: Scene(n, z[n + ".words"], z[n + ".meta"]) for n in names}
+
+
+ALL_NAMES = sorted(k[:-6] for k in np.load(os.path.join(GOLDEN, "scenes.npz")).files if k.endswith(".words"))
