@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libcodecad_b200.so")
+SO_PATH = os.environ.get("CODECAD_B200_LIB") or os.path.join(_HERE, "libcodecad_b200.so")
 
 c_float_p = ctypes.POINTER(ctypes.c_float)
 c_u32_p = ctypes.POINTER(ctypes.c_uint32)
@@ -32,7 +32,7 @@ class DeviceInfo(ctypes.Structure):
 class ProgramInfo(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint32) for n in (
         "n_words", "n_instructions", "n_micro_ops", "n_micro_words", "n_wire_registers",
-        "n_slots", "n_p_stores", "flops_min", "flops_max")]
+        "n_slots", "n_fused", "flops_min", "flops_max")]
 
 
 class Level(ctypes.Structure):
@@ -59,6 +59,7 @@ SIGNATURES = {
     "cc_program_destroy": (None, [_V]),
     "cc_program_get_info": (_I, [_V, ctypes.POINTER(ProgramInfo)]),
     "cc_program_get_microcode": (_I, [_V, c_u32_p, _U]),
+    "cc_program_decode": (_I, [c_float_p, _U, ctypes.POINTER(ProgramInfo), c_u32_p, _U]),
     "cc_buffer_alloc": (_I, [ctypes.c_size_t, c_void_pp]),
     "cc_buffer_free": (_I, [_V]),
     "cc_host_alloc": (_I, [ctypes.c_size_t, c_void_pp]),
@@ -148,3 +149,14 @@ def f3(v):
     else:
         a = np.asarray(a, dtype=np.float64).astype(np.float32).ravel()[:3]
     return (ctypes.c_float * 3)(*[float(x) for x in a])
+
+
+def decode_program(words):
+    """Host-only decode of a wire program: (ProgramInfo, microcode uint32 array)."""
+    w = np.ascontiguousarray(words, dtype=np.float32)
+    info = ProgramInfo()
+    n = check(load().cc_program_decode(w.ctypes.data_as(c_float_p), len(w), ctypes.byref(info), None, 0))
+    out = np.zeros(n, np.uint32)
+    check(load().cc_program_decode(w.ctypes.data_as(c_float_p), len(w), ctypes.byref(info),
+                                   out.ctypes.data_as(c_u32_p), n))
+    return info, out

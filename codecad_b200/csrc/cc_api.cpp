@@ -96,8 +96,10 @@ int choose_cfg(const cc_program *prog, uint64_t total_points, cc_launch_cfg *cfg
     const uint32_t words = prog->dec.info.n_micro_words;
     const uint32_t slots = prog->dec.info.n_slots;
     const size_t smem_max = g.prop.sharedMemPerBlockOptin;
+    // microcode in the constant bank (uniform loads, parameters stay in uniform registers)
+    // whenever it fits the 63 KB window; larger programs are staged in shared memory
     int space = g.prog_space;
-    if (space == 0) space = 2;
+    if (space == 0) space = 1;
     if (space == 1 && words > CC_CONST_WORDS) space = 2;
     int pts = g.pts ? g.pts : 4;
     if (pts != 1 && pts != 2 && pts != 4) pts = 4;
@@ -330,6 +332,20 @@ int cc_program_get_microcode(const cc_program *prog, uint32_t *out, uint32_t cap
     if (!prog) return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
     uint32_t n = (uint32_t)prog->dec.microcode.size();
     if (out) std::memcpy(out, prog->dec.microcode.data(), (size_t)std::min(n, capacity) * 4);
+    return (int)n;
+}
+
+int cc_program_decode(const float *words, uint32_t n_words, cc_program_info *info, uint32_t *out,
+                      uint32_t capacity)
+{
+    if (!words) return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
+    cc_decoded dec;
+    std::string err;
+    int rc = cc_decode_program(words, n_words, &dec, &err);
+    if (rc != CC_OK) return fail(rc, err);
+    if (info) *info = dec.info;
+    uint32_t n = (uint32_t)dec.microcode.size();
+    if (out) std::memcpy(out, dec.microcode.data(), (size_t)std::min(n, capacity) * 4);
     return (int)n;
 }
 

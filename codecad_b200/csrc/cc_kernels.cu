@@ -18,8 +18,9 @@
 // which amortises decode over PTS points and hides the 4-cycle FMA latency.  The
 // reference's 512-entry private register array becomes a handful of liveness-renamed
 // slots in shared memory, laid out [slot][point][thread] as float4 so that a warp's
-// access is a conflict-free 512-byte LDS.128/STS.128; point values consumed by the very
-// next extrusion / *_from op never leave registers (the P register).
+// access is a conflict-free 512-byte LDS.128/STS.128; the commonest producer/consumer chain
+// (transform -> 2-D primitive -> extrusion -> offset -> inverse rotation) is fused into one
+// micro-op by the loader so that its intermediate point never leaves registers.
 //
 // Compile with -fmad=false (see cc_math.cuh).
 #include <cuda_runtime.h>
@@ -41,13 +42,15 @@ struct Prog {
     CC_DEV float4 f4(uint32_t i) const
     {
         if (SMEM) return *reinterpret_cast<const float4 *>(s + i);
+        // constant bank: vector LDC.64 pairs.  (Measured on B200, profiles/r1_ab_variants.md:
+        // four scalar uniform LDCU reads instead are 17 % slower on the planetary scene.)
         return *reinterpret_cast<const float4 *>(c_code + i);
     }
 };
 
 // polygons2d.cl:1-74 over the precomputed edge table (px, py, dx, dy, 1/|d|^2, cy)
 template <bool SMEM>
-CC_DEV float4 cc_polygon2d(const Prog<SMEM> &P, uint32_t pc, float4 co)
+CC_DEV_HEAVY float4 cc_polygon2d(const Prog<SMEM> &P, uint32_t pc, float4 co)
 {
     uint32_t n = (uint32_t)P.f(pc + 1);
     float nnx = 0.0f, nny = 0.0f, nearest = INFINITY, outside = 1.0f;
@@ -80,50 +83,70 @@ CC_DEV float4 cc_polygon2d(const Prog<SMEM> &P, uint32_t pc, float4 co)
 }
 
 // ---- the interpreter ------------------------------------------------------------------------
+// Fused primitive (loader pattern: initial_transformation_to -> [store p] -> circle|rectangle
+// -> extrusion p -> [offset] -> [transformation_from]): one dispatch, the transformed point
+// never leaves registers.  Bit-identical to the unfused sequence (absent offset = 0, absent
+// transformation_from = identity matrix and scale 1).
+// words: 1..12 m,o | 13 a | 14 b | 15 h | 16 d | 17..25 m' | 26 scale
+template <bool RECT, bool SMEM>
+CC_DEV float4 cc_prim(const Prog<SMEM> &P, uint32_t pc, float x, float y, float z)
+{
+    float m[12], mf[12];
+    const float4 a = P.f4(pc), b = P.f4(pc + 4), c = P.f4(pc + 8), d = P.f4(pc + 12), e = P.f4(pc + 16),
+                 f = P.f4(pc + 20), g = P.f4(pc + 24);
+    m[0] = a.y; m[1] = a.z; m[2] = a.w; m[3] = b.x; m[4] = b.y; m[5] = b.z;
+    m[6] = b.w; m[7] = c.x; m[8] = c.y; m[9] = c.z; m[10] = c.w; m[11] = d.x;
+    mf[0] = e.y; mf[1] = e.z; mf[2] = e.w; mf[3] = f.x; mf[4] = f.y; mf[5] = f.z;
+    mf[6] = f.w; mf[7] = g.x; mf[8] = g.y; mf[9] = g.z; mf[10] = 0.f; mf[11] = 0.f;
+    const float4 p = cc_transform(m, x, y, z);
+    float4 v = RECT ? cc_rectangle(d.y, d.z, p) : cc_circle(d.y, p);
+    v = cc_extrusion(d.w, v, p.z);
+    v.w = v.w - e.x;
+    return cc_transform_from(mf, v);
+}
+
 template <int PTS, bool SMEM>
 CC_DEV void cc_interpret(const Prog<SMEM> P, float4 *__restrict__ regs, const float (&gx)[PTS],
                          const float (&gy)[PTS], const float (&gz)[PTS], float4 (&L)[PTS])
 {
-    float4 Pr[PTS];  // the P register: last point value kept out of shared memory
-    const uint32_t tid = threadIdx.x;
+    float4 *const myregs = regs + threadIdx.x;
 #pragma unroll
-    for (int j = 0; j < PTS; ++j) {
-        L[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        Pr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    for (int j = 0; j < PTS; ++j) L[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#define CC_SLOT(slot, j) myregs[((slot) * PTS + (j)) * CC_THREADS]
+#define CC_EACH for (int j = 0; j < PTS; ++j)
     uint32_t pc = 0;
     for (;;) {
         const uint32_t h = P.u(pc);
         const uint32_t op = CC_HDR_OP(h), src = CC_HDR_SRC(h), dst = CC_HDR_DST(h);
-        float4 B[PTS];
-        if (src != CC_SLOT_NONE) {
-            if (src == CC_SLOT_P) {
-#pragma unroll
-                for (int j = 0; j < PTS; ++j) B[j] = Pr[j];
-            } else {
-#pragma unroll
-                for (int j = 0; j < PTS; ++j) B[j] = regs[(src * PTS + j) * CC_THREADS + tid];
-            }
-        }
         switch (op) {
         case MOP_RETURN: return;
         case MOP_LOAD:
 #pragma unroll
-            for (int j = 0; j < PTS; ++j) L[j] = B[j];
+            CC_EACH L[j] = CC_SLOT(src, j);
             pc += CC_LEN_0;
             break;
         case MOP_NOP: pc += CC_LEN_0; break;
+        case MOP_PRIM_CIRCLE:
+#pragma unroll
+            CC_EACH L[j] = cc_prim<false, SMEM>(P, pc, gx[j], gy[j], gz[j]);
+            pc += CC_LEN_PRIM;
+            break;
+        case MOP_PRIM_RECT:
+#pragma unroll
+            CC_EACH L[j] = cc_prim<true, SMEM>(P, pc, gx[j], gy[j], gz[j]);
+            pc += CC_LEN_PRIM;
+            break;
         case MOP_RECTANGLE: {
             const float4 q = P.f4(pc);
 #pragma unroll
-            for (int j = 0; j < PTS; ++j) L[j] = cc_rectangle(q.y, q.z, L[j]);
+            CC_EACH L[j] = cc_rectangle(q.y, q.z, L[j]);
             pc += CC_LEN_0;
             break;
         }
         case MOP_CIRCLE: {
             const float r = P.f(pc + 1);
 #pragma unroll
-            for (int j = 0; j < PTS; ++j) L[j] = cc_circle(r, L[j]);
+            CC_EACH L[j] = cc_circle(r, L[j]);
             pc += CC_LEN_0;
             break;
         }
@@ -132,38 +155,38 @@ CC_DEV void cc_interpret(const Prog<SMEM> P, float4 *__restrict__ regs, const fl
 #pragma unroll
             for (int i = 0; i < 5; ++i) k[i] = P.f(pc + 1 + i);
 #pragma unroll
-            for (int j = 0; j < PTS; ++j) L[j] = cc_regular_polygon2d(k, L[j]);
+            CC_EACH L[j] = cc_regular_polygon2d(k[0], k[1], k[2], k[3], k[4], L[j]);
             pc += CC_LEN_7;
             break;
         }
         case MOP_POLYGON: {
             const uint32_t n = (uint32_t)P.f(pc + 1);
 #pragma unroll
-            for (int j = 0; j < PTS; ++j) L[j] = cc_polygon2d<SMEM>(P, pc, L[j]);
+            CC_EACH L[j] = cc_polygon2d<SMEM>(P, pc, L[j]);
             pc += 4 + ((CC_POLY_EDGE_WORDS * n + 3) / 4) * 4;
             break;
         }
         case MOP_SPHERE: {
             const float r = P.f(pc + 1);
 #pragma unroll
-            for (int j = 0; j < PTS; ++j) L[j] = cc_sphere(r, L[j]);
+            CC_EACH L[j] = cc_sphere(r, L[j]);
             pc += CC_LEN_0;
             break;
         }
         case MOP_HALF_SPACE:  // simple3d.cl:14-16
 #pragma unroll
-            for (int j = 0; j < PTS; ++j) L[j] = make_float4(0.0f, -1.0f, 0.0f, -L[j].y);
+            CC_EACH L[j] = make_float4(0.0f, -1.0f, 0.0f, -L[j].y);
             pc += CC_LEN_0;
             break;
         case MOP_REV_TO:  // simple3d.cl:23-26
 #pragma unroll
-            for (int j = 0; j < PTS; ++j) L[j] = make_float4(cc_len2(L[j].x, L[j].z), L[j].y, 0.0f, 0.0f);
+            CC_EACH L[j] = make_float4(cc_len2(L[j].x, L[j].z), L[j].y, 0.0f, 0.0f);
             pc += CC_LEN_0;
             break;
         case MOP_TWIST_TO: {
             const float r = P.f(pc + 1), twist = P.f(pc + 2);
 #pragma unroll
-            for (int j = 0; j < PTS; ++j) L[j] = cc_twist_revolution_to(r, twist, L[j]);
+            CC_EACH L[j] = cc_twist_revolution_to(r, twist, L[j]);
             pc += CC_LEN_0;
             break;
         }
@@ -177,10 +200,10 @@ CC_DEV void cc_interpret(const Prog<SMEM> P, float4 *__restrict__ regs, const fl
             }
             if (op == MOP_T_INIT) {
 #pragma unroll
-                for (int j = 0; j < PTS; ++j) L[j] = cc_transform(m, gx[j], gy[j], gz[j]);
+                CC_EACH L[j] = cc_transform(m, gx[j], gy[j], gz[j]);
             } else {
 #pragma unroll
-                for (int j = 0; j < PTS; ++j) L[j] = cc_transform(m, L[j].x, L[j].y, L[j].z);
+                CC_EACH L[j] = cc_transform(m, L[j].x, L[j].y, L[j].z);
             }
             pc += CC_LEN_T;
             break;
@@ -193,31 +216,31 @@ CC_DEV void cc_interpret(const Prog<SMEM> P, float4 *__restrict__ regs, const fl
                 m[6] = b.w; m[7] = c.x; m[8] = c.y; m[9] = c.z; m[10] = 0.f; m[11] = 0.f;
             }
 #pragma unroll
-            for (int j = 0; j < PTS; ++j) L[j] = cc_transform_from(m, L[j]);
+            CC_EACH L[j] = cc_transform_from(m, L[j]);
             pc += CC_LEN_T;
             break;
         }
         case MOP_MIRROR:  // common.cl:112-114
 #pragma unroll
-            for (int j = 0; j < PTS; ++j) L[j].x = -L[j].x;
+            CC_EACH L[j].x = -L[j].x;
             pc += CC_LEN_0;
             break;
         case MOP_SYM_TO:  // common.cl:116-118
 #pragma unroll
-            for (int j = 0; j < PTS; ++j) L[j].x = fabsf(L[j].x);
+            CC_EACH L[j].x = fabsf(L[j].x);
             pc += CC_LEN_0;
             break;
         case MOP_OFFSET: {  // common.cl:124-126
             const float d = P.f(pc + 1);
 #pragma unroll
-            for (int j = 0; j < PTS; ++j) L[j].w = L[j].w - d;
+            CC_EACH L[j].w = L[j].w - d;
             pc += CC_LEN_0;
             break;
         }
         case MOP_SHELL: {  // common.cl:128-131
             const float d = P.f(pc + 1);
 #pragma unroll
-            for (int j = 0; j < PTS; ++j) {
+            CC_EACH {
                 float4 s = (L[j].w >= 0.0f) ? L[j] : cc_neg4(L[j]);
                 s.w = s.w - d;
                 L[j] = s;
@@ -228,23 +251,15 @@ CC_DEV void cc_interpret(const Prog<SMEM> P, float4 *__restrict__ regs, const fl
         case MOP_REPETITION: {  // unsafe.cl:1-6
             const float4 q = P.f4(pc);
 #pragma unroll
-            for (int j = 0; j < PTS; ++j)
-                L[j] = make_float4(cc_remainder(L[j].x, q.y), cc_remainder(L[j].y, q.z),
-                                   cc_remainder(L[j].z, q.w), 0.0f);
+            CC_EACH L[j] = make_float4(cc_remainder(L[j].x, q.y), cc_remainder(L[j].y, q.z),
+                                       cc_remainder(L[j].z, q.w), 0.0f);
             pc += CC_LEN_0;
             break;
         }
         case MOP_CREP_TO: {
             const float a = P.f(pc + 1), b = P.f(pc + 2);
 #pragma unroll
-            for (int j = 0; j < PTS; ++j) L[j] = cc_circular_repetition_to(a, b, L[j]);
-            pc += CC_LEN_0;
-            break;
-        }
-        case MOP_CREP_FROM: {
-            const float a = P.f(pc + 1), b = P.f(pc + 2);
-#pragma unroll
-            for (int j = 0; j < PTS; ++j) L[j] = cc_circular_repetition_from(a, b, L[j], B[j]);
+            CC_EACH L[j] = cc_circular_repetition_to(a, b, L[j]);
             pc += CC_LEN_0;
             break;
         }
@@ -253,20 +268,26 @@ CC_DEV void cc_interpret(const Prog<SMEM> P, float4 *__restrict__ regs, const fl
 #pragma unroll
             for (int i = 0; i < 5; ++i) k[i] = P.f(pc + 1 + i);
 #pragma unroll
-            for (int j = 0; j < PTS; ++j) L[j] = cc_involute_gear(k, L[j]);
+            CC_EACH L[j] = cc_involute_gear(k[0], k[1], k[2], k[3], k[4], L[j]);
             pc += CC_LEN_7;
             break;
         }
+        // ---- ops whose second operand is a point held in a slot ----
         case MOP_EXTRUSION: {
             const float hh = P.f(pc + 1);
 #pragma unroll
-            for (int j = 0; j < PTS; ++j) L[j] = cc_extrusion(hh, L[j], B[j].z);
+            CC_EACH L[j] = cc_extrusion(hh, L[j], CC_SLOT(src, j).z);
             pc += CC_LEN_0;
             break;
         }
         case MOP_REV_FROM:
 #pragma unroll
-            for (int j = 0; j < PTS; ++j) L[j] = cc_revolution_from(L[j], B[j]);
+            CC_EACH L[j] = cc_revolution_from(L[j], CC_SLOT(src, j));
+            pc += CC_LEN_0;
+            break;
+        case MOP_SYM_FROM:  // common.cl:120-122
+#pragma unroll
+            CC_EACH L[j].x = (CC_SLOT(src, j).x < 0.0f) ? -L[j].x : L[j].x;
             pc += CC_LEN_0;
             break;
         case MOP_TWIST_FROM: {
@@ -274,63 +295,72 @@ CC_DEV void cc_interpret(const Prog<SMEM> P, float4 *__restrict__ regs, const fl
 #pragma unroll
             for (int i = 0; i < 5; ++i) k[i] = P.f(pc + 1 + i);
 #pragma unroll
-            for (int j = 0; j < PTS; ++j) L[j] = cc_twist_revolution_from(k, L[j], B[j]);
+            CC_EACH L[j] = cc_twist_revolution_from(k[0], k[1], k[2], k[3], k[4], L[j], CC_SLOT(src, j));
             pc += CC_LEN_7;
             break;
         }
-        case MOP_SYM_FROM:  // common.cl:120-122
+        case MOP_CREP_FROM: {
+            const float a = P.f(pc + 1), b = P.f(pc + 2);
 #pragma unroll
-            for (int j = 0; j < PTS; ++j) L[j].x = (B[j].x < 0.0f) ? -L[j].x : L[j].x;
+            CC_EACH L[j] = cc_circular_repetition_from(a, b, L[j], CC_SLOT(src, j));
             pc += CC_LEN_0;
             break;
+        }
+        // ---- CSG combinators: second operand is always a slot ----
         case MOP_UNION:  // common.cl:60-68 with r < 0
 #pragma unroll
-            for (int j = 0; j < PTS; ++j) L[j] = (L[j].w < B[j].w) ? L[j] : B[j];
+            CC_EACH {
+                const float4 b = CC_SLOT(src, j);
+                L[j] = (L[j].w < b.w) ? L[j] : b;
+            }
             pc += CC_LEN_0;
             break;
         case MOP_UNION_R: {
             const float r = P.f(pc + 1);
 #pragma unroll
-            for (int j = 0; j < PTS; ++j) L[j] = cc_rounded_union(r, L[j], B[j]);
+            CC_EACH L[j] = cc_rounded_union(r, L[j], CC_SLOT(src, j));
             pc += CC_LEN_0;
             break;
         }
         case MOP_ISECT:  // common.cl:70-72: -min(-a, -b) = the operand with the larger distance
 #pragma unroll
-            for (int j = 0; j < PTS; ++j) L[j] = (-L[j].w < -B[j].w) ? L[j] : B[j];
+            CC_EACH {
+                const float4 b = CC_SLOT(src, j);
+                L[j] = (-L[j].w < -b.w) ? L[j] : b;
+            }
             pc += CC_LEN_0;
             break;
         case MOP_ISECT_R: {
             const float r = P.f(pc + 1);
 #pragma unroll
-            for (int j = 0; j < PTS; ++j) L[j] = cc_neg4(cc_rounded_union(r, cc_neg4(L[j]), cc_neg4(B[j])));
+            CC_EACH L[j] = cc_neg4(cc_rounded_union(r, cc_neg4(L[j]), cc_neg4(CC_SLOT(src, j))));
             pc += CC_LEN_0;
             break;
         }
         case MOP_SUB:  // common.cl:74-76: -min(-a, b)
 #pragma unroll
-            for (int j = 0; j < PTS; ++j) L[j] = (-L[j].w < B[j].w) ? L[j] : cc_neg4(B[j]);
+            CC_EACH {
+                const float4 b = CC_SLOT(src, j);
+                L[j] = (-L[j].w < b.w) ? L[j] : cc_neg4(b);
+            }
             pc += CC_LEN_0;
             break;
         case MOP_SUB_R: {
             const float r = P.f(pc + 1);
 #pragma unroll
-            for (int j = 0; j < PTS; ++j) L[j] = cc_neg4(cc_rounded_union(r, cc_neg4(L[j]), B[j]));
+            CC_EACH L[j] = cc_neg4(cc_rounded_union(r, cc_neg4(L[j]), CC_SLOT(src, j)));
             pc += CC_LEN_0;
             break;
         }
-        default: return;  // unreachable: the loader only emits the micro-ops above
+        default: __builtin_unreachable();  // the loader only emits the micro-ops above
         }
         if (dst != CC_SLOT_NONE) {
-            if (dst == CC_SLOT_P) {
 #pragma unroll
-                for (int j = 0; j < PTS; ++j) Pr[j] = L[j];
-            } else {
-#pragma unroll
-                for (int j = 0; j < PTS; ++j) regs[(dst * PTS + j) * CC_THREADS + tid] = L[j];
-            }
+            CC_EACH CC_SLOT(dst, j) = L[j];
         }
     }
+#undef CC_SLOT
+#undef CC_EACH
 }
 
 // ---- ordered compaction: warp-ballot scan inside the CTA + decoupled look-back across CTAs ----

@@ -10,9 +10,8 @@
 //     fetches header + parameters with a few 128-bit broadcast loads;
 //   * header = micro-op (8 bit) | src slot (12 bit) | dst slot (12 bit);
 //     `_store` instructions of the wire format are folded into the producing
-//     instruction's dst field, registers are renamed to a dense set of "slots" by a
-//     liveness pass, and short-lived point values go to the hardware P register
-//     (CC_SLOT_P) instead of shared memory;
+//     instruction's dst field and registers are renamed to a dense set of "slots" by a
+//     liveness pass;
 //   * parameter-only arithmetic is hoisted here (quaternion -> 3x3 matrix, polygon
 //     edge tables, gear constants) — the canonical cc-arith definitions of DESIGN.md.
 #ifndef CC_MICROCODE_H
@@ -53,6 +52,8 @@ enum cc_mop : uint32_t {
     MOP_ISECT_R,
     MOP_SUB,
     MOP_SUB_R,
+    MOP_PRIM_CIRCLE,   // fused T_INIT -> circle -> extrusion -> offset -> T_FROM   (28 words)
+    MOP_PRIM_RECT,     // fused T_INIT -> rectangle -> extrusion -> offset -> T_FROM
     MOP_COUNT
 };
 
@@ -69,6 +70,7 @@ enum cc_mop : uint32_t {
 #define CC_LEN_0 4   // up to 3 parameters
 #define CC_LEN_7 8   // up to 7 parameters
 #define CC_LEN_T 16  // 12 parameters (+3 spare)
+#define CC_LEN_PRIM 28
 #define CC_POLY_EDGE_WORDS 6
 
 #define CC_CONST_WORDS 16128  // microcode words that fit the 63 KB __constant__ window

@@ -11,6 +11,17 @@
 
 #include "cc_math.cuh"
 
+// heavy, rarely dominant ops are real functions: inlining them PTS times per kernel variant
+// would push the interpreter out of the instruction cache
+#ifndef CC_OPT_NOINLINE_HEAVY
+#define CC_OPT_NOINLINE_HEAVY 1
+#endif
+#if CC_OPT_NOINLINE_HEAVY
+#define CC_DEV_HEAVY __device__ __noinline__
+#else
+#define CC_DEV_HEAVY __device__ __forceinline__
+#endif
+
 CC_DEV float4 cc_neg4(float4 a) { return make_float4(-a.x, -a.y, -a.z, -a.w); }
 CC_DEV float4 cc_sel4(bool c, float4 a, float4 b)
 {
@@ -101,8 +112,9 @@ CC_DEV float4 cc_transform_from(const float (&m)[12], float4 in)
 }
 
 // shapes/simple2d.cl:16-46; k = (piOverN, r, r*sin, r*cos, 2*piOverN)
-CC_DEV float4 cc_regular_polygon2d(const float (&k)[5], float4 co)
+CC_DEV_HEAVY float4 cc_regular_polygon2d(float k0, float k1, float k2, float k3, float k4, float4 co)
 {
+    const float k[5] = {k0, k1, k2, k3, k4};
     float piOverN = k[0], r = k[1];
     float len = cc_len2(co.x, co.y);
     float alpha = (cc_atan2(co.y, co.x) + CC_2PI_F) + piOverN;
@@ -127,8 +139,9 @@ CC_DEV float4 cc_regular_polygon2d(const float (&k)[5], float4 co)
 }
 
 // shapes/gears.cl:1-42; k = (baseRadius, toothAngle, halfToothBaseAngle, 2*toothAngle, baseRadius^2)
-CC_DEV float4 cc_involute_gear(const float (&k)[5], float4 co)
+CC_DEV_HEAVY float4 cc_involute_gear(float k0, float k1, float k2, float k3, float k4, float4 co)
 {
+    const float k[5] = {k0, k1, k2, k3, k4};
     float baseRadius = k[0], toothAngle = k[1], halfTooth = k[2];
     float len = cc_len2(co.x, co.y);
     float alpha = cc_atan2(co.y, co.x);
@@ -151,7 +164,7 @@ CC_DEV float4 cc_involute_gear(const float (&k)[5], float4 co)
 }
 
 // shapes/simple3d.cl:42-51
-CC_DEV float4 cc_twist_revolution_to(float r, float twist, float4 co)
+CC_DEV_HEAVY float4 cc_twist_revolution_to(float r, float twist, float4 co)
 {
     float alpha = cc_fmod_pos(cc_atan2(co.z, co.x) + CC_PI_F, CC_2PI_F);
     float beta = cc_div(twist * alpha, CC_2PI_F);
@@ -162,8 +175,10 @@ CC_DEV float4 cc_twist_revolution_to(float r, float twist, float4 co)
 }
 
 // shapes/simple3d.cl:53-97; k = (minorR, r, twist, min(1, lipschitz), padding)
-CC_DEV float4 cc_twist_revolution_from(const float (&k)[5], float4 inPlane, float4 co)
+CC_DEV_HEAVY float4 cc_twist_revolution_from(float k0, float k1, float k2, float k3, float k4, float4 inPlane,
+                                             float4 co)
 {
+    const float k[5] = {k0, k1, k2, k3, k4};
     float minorR = k[0], r = k[1], twist = k[2];
     float ad = cc_len2(co.x, co.z);
     float ipx = ad - r, ipy = co.y;
@@ -188,7 +203,7 @@ CC_DEV float4 cc_twist_revolution_from(const float (&k)[5], float4 inPlane, floa
 }
 
 // shapes/unsafe.cl:8-15
-CC_DEV float4 cc_circular_repetition_to(float piOverN, float twoPiOverN, float4 co)
+CC_DEV_HEAVY float4 cc_circular_repetition_to(float piOverN, float twoPiOverN, float4 co)
 {
     float len = cc_len2(co.x, co.y);
     float alpha = (cc_atan2(co.y, co.x) + CC_2PI_F) + piOverN;
@@ -200,7 +215,7 @@ CC_DEV float4 cc_circular_repetition_to(float piOverN, float twoPiOverN, float4 
 }
 
 // shapes/unsafe.cl:17-23
-CC_DEV float4 cc_circular_repetition_from(float piOverN, float twoPiOverN, float4 dist, float4 co)
+CC_DEV_HEAVY float4 cc_circular_repetition_from(float piOverN, float twoPiOverN, float4 dist, float4 co)
 {
     float alpha = (cc_atan2(co.y, co.x) + CC_2PI_F) + piOverN;
     int side = (int)floorf(cc_div(alpha, twoPiOverN));

@@ -46,6 +46,7 @@ struct Interval {
     int last_read;  // wire instruction index of the last read, -1 = dead
     bool point_only;  // every read is the point operand of a *_from / extrusion op
     unsigned slot;
+    int n_reads;
 };
 
 bool is_point_consumer(int op)
@@ -159,7 +160,7 @@ int cc_decode_program(const float *words, uint32_t n_words, cc_decoded *out, std
     for (size_t i = 0; i < ins.size(); ++i) {
         const WireIns &w = ins[i];
         if (w.op == W_STORE) {
-            intervals.push_back(Interval{(int)i, -1, true, CC_SLOT_NONE});
+            intervals.push_back(Interval{(int)i, -1, true, CC_SLOT_NONE, 0});
             open[w.reg] = (int)intervals.size() - 1;
             store_interval[i] = open[w.reg];
         } else if (w.op == W_LOAD || kArity[w.op] == 2) {
@@ -170,22 +171,32 @@ int cc_decode_program(const float *words, uint32_t n_words, cc_decoded *out, std
                 return CC_ERR_INVALID_PROGRAM;
             }
             intervals[iv].last_read = (int)i;
+            intervals[iv].n_reads += 1;
             if (!is_point_consumer(w.op)) intervals[iv].point_only = false;
             read_interval[i] = iv;
         }
     }
 
-    // ---- 3. P register: short point values stay in hardware registers -----------------------
-    int p_busy_until = -1;
-    uint32_t n_p = 0;
-    for (Interval &iv : intervals) {
-        if (iv.last_read < 0 || !iv.point_only) continue;
-        if (iv.store_idx > p_busy_until) {
-            iv.slot = CC_SLOT_P;
-            p_busy_until = iv.last_read;
-            ++n_p;
-        }
+    // ---- 2b. fused primitives --------------------------------------------------------------------
+    // initial_transformation_to ; _store p ; circle|rectangle ; extrusion p ; [offset] ;
+    // [transformation_from]   with p read by that extrusion only  ->  one MOP_PRIM_* micro-op.
+    // fuse_len[i] = number of wire instructions consumed by the fused op starting at i.
+    std::vector<int> fuse_len(ins.size(), 0);
+    for (size_t i = 0; i + 3 < ins.size(); ++i) {
+        if (ins[i].op != W_INITIAL_TRANSFORMATION_TO || ins[i + 1].op != W_STORE) continue;
+        if (ins[i + 2].op != W_CIRCLE && ins[i + 2].op != W_RECTANGLE) continue;
+        if (ins[i + 3].op != W_EXTRUSION) continue;
+        const int iv = store_interval[i + 1];
+        if (iv < 0 || read_interval[i + 3] != iv || intervals[iv].n_reads != 1) continue;
+        size_t j = i + 4;
+        if (j < ins.size() && ins[j].op == W_OFFSET) ++j;
+        if (j < ins.size() && ins[j].op == W_TRANSFORMATION_FROM) ++j;
+        fuse_len[i] = (int)(j - i);
+        intervals[iv].last_read = -1;  // the point lives in registers inside the fused op
+        i = j - 1;
     }
+
+    uint32_t n_p = 0;  // fused primitives emitted
 
     // ---- 4. linear-scan slot allocation for everything else ---------------------------------
     uint32_t n_slots = 0;
@@ -195,7 +206,7 @@ int cc_decode_program(const float *words, uint32_t n_words, cc_decoded *out, std
         std::vector<int> active;
         for (size_t k = 0; k < intervals.size(); ++k) {
             Interval &iv = intervals[k];
-            if (iv.last_read < 0 || iv.slot == CC_SLOT_P) continue;
+            if (iv.last_read < 0) continue;
             for (size_t a = 0; a < active.size();) {
                 if (intervals[active[a]].last_read < iv.store_idx) {
                     free_slots.push_back(intervals[active[a]].slot);
@@ -234,6 +245,36 @@ int cc_decode_program(const float *words, uint32_t n_words, cc_decoded *out, std
         uint32_t src = CC_SLOT_NONE;
         if (read_interval[i] >= 0) src = intervals[read_interval[i]].slot;
         float *q;
+        if (fuse_len[i]) {
+            const bool rect = ins[i + 2].op == W_RECTANGLE;
+            q = e.emit(rect ? MOP_PRIM_RECT : MOP_PRIM_CIRCLE, CC_SLOT_NONE, CC_LEN_PRIM);
+            quat_matrix(p, false, q, nullptr);
+            q[9] = p[4]; q[10] = p[5]; q[11] = p[6];
+            q[12] = ins[i + 2].p[0];
+            q[13] = rect ? ins[i + 2].p[1] : 0.0f;
+            q[14] = ins[i + 3].p[0];
+            cost(42, 42);
+            if (rect) cost(2, 17); else cost(7, 7);
+            cost(1, 16);
+            size_t j = i + 4;
+            q[15] = 0.0f;  // no offset: w - 0 == w
+            if (j < i + (size_t)fuse_len[i] && ins[j].op == W_OFFSET) {
+                q[15] = ins[j].p[0];
+                cost(1, 1);
+                ++j;
+            }
+            if (j < i + (size_t)fuse_len[i] && ins[j].op == W_TRANSFORMATION_FROM) {
+                quat_matrix(ins[j].p, true, q + 16, &q[25]);
+                cost(50, 50);
+            } else {  // identity: 1*x + 0*y + 0*z == x, w * 1 == w
+                for (int k = 0; k < 9; ++k) q[16 + k] = (k % 4 == 0) ? 1.0f : 0.0f;
+                q[25] = 1.0f;
+            }
+            i += (size_t)fuse_len[i] - 1;
+            ++n_micro;
+            ++n_p;
+            continue;
+        }
         switch (w.op) {
         case W_RETURN: e.emit(MOP_RETURN, CC_SLOT_NONE, CC_LEN_0); break;
         case W_STORE: {
@@ -385,7 +426,7 @@ int cc_decode_program(const float *words, uint32_t n_words, cc_decoded *out, std
     out->info.n_micro_words = (uint32_t)out->microcode.size();
     out->info.n_wire_registers = max_reg;
     out->info.n_slots = n_slots;
-    out->info.n_p_stores = n_p;
+    out->info.n_fused = n_p;
     out->info.flops_min = fmin;
     out->info.flops_max = fmax;
     return CC_OK;

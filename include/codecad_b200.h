@@ -74,13 +74,18 @@ typedef struct cc_program_info {
     uint32_t n_micro_words;  /* decoded length in 32-bit words                       */
     uint32_t n_wire_registers; /* highest wire register used + 1                     */
     uint32_t n_slots;        /* shared-memory value slots after liveness renaming    */
-    uint32_t n_p_stores;     /* stores redirected to the hardware P register         */
+    uint32_t n_fused;        /* fused primitive micro-ops (MOP_PRIM_*)               */
     uint32_t flops_min;      /* static algorithmic flop/point, SURVEY.md 8(a3) rules */
     uint32_t flops_max;
 } cc_program_info;
 int cc_program_get_info(const cc_program *prog, cc_program_info *out);
-/* copies the decoded microcode (for tests / disassembly); returns words written */
+/* copies the decoded microcode (for tests / disassembly); returns the microcode length */
 int cc_program_get_microcode(const cc_program *prog, uint32_t *out, uint32_t capacity);
+/* Host-only decode (no device, no cc_init needed): validates `words`, fills `info` and
+ * copies up to `capacity` microcode words to `out` (may be NULL).  Returns the microcode
+ * length in words, or a negative cc_status.  Lets the loader be tested without a GPU. */
+int cc_program_decode(const float *words, uint32_t n_words, cc_program_info *info,
+                      uint32_t *out, uint32_t capacity);
 
 /* ---- buffers and events: replaces cl_util.Buffer  cl_util/cl_buffer.py:9-131 ---------- */
 int cc_buffer_alloc(size_t bytes, void **dptr);

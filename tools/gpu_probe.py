@@ -26,6 +26,8 @@ def main():
     names = sys.argv[1].split(",") if len(sys.argv) > 1 else ["cfg_csg_example", "cfg_menger_sponge", "cfg_airfoil", "cfg_planetary", "cfg_synthetic500"]
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 512
     variants = [(4, 2), (2, 2), (1, 2), (4, 1), (2, 1), (1, 1)]
+    if os.environ.get("PROBE_VARIANTS"):
+        variants = [tuple(int(x) for x in v.split(":")) for v in os.environ["PROBE_VARIANTS"].split(",")]
     out = Buffer(FLOAT4, (n, n, n))
     for name in names:
         s = scenes[name]
@@ -33,8 +35,8 @@ def main():
         pi = prog.info
         corner, step = s.grid(n)
         nx = n if name != "cfg_synthetic500" else max(8, n // 8)
-        print("%s: %d micro-ops, %d words, %d slots, %d P-stores, flops %d..%d" % (
-            name, pi.n_micro_ops, pi.n_micro_words, pi.n_slots, pi.n_p_stores, pi.flops_min, pi.flops_max))
+        print("%s: %d micro-ops, %d words, %d slots, %d fused, flops %d..%d" % (
+            name, pi.n_micro_ops, pi.n_micro_words, pi.n_slots, pi.n_fused, pi.flops_min, pi.flops_max))
         for pts, space in variants:
             _lib.check(L.cc_set_tuning(pts, space))
             best = None

@@ -1,0 +1,25 @@
+#!/usr/bin/env python3
+"""Launch the grid_eval kernel a few times for one scene (for ncu): scene n pts space [reps]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+
+from codecad_b200 import _lib  # noqa: E402
+from codecad_b200.cl_util import Buffer  # noqa: E402
+from codecad_b200.geometry import FLOAT4  # noqa: E402
+from scenes import load_scenes  # noqa: E402
+
+name, n, pts, space = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
+reps = int(sys.argv[5]) if len(sys.argv) > 5 else 3
+L = _lib.init(0)
+s = load_scenes()[name]
+prog = s.compiled().program_buffer()
+corner, step = s.grid(n)
+out = Buffer(FLOAT4, (n, n, n))
+_lib.check(L.cc_set_tuning(pts, space))
+for _ in range(reps):
+    _lib.check(L.cc_grid_eval(prog.handle, _lib.f3(corner), float(step), n, n, n, 0, 0, out.device_ptr, None))
+_lib.check(L.cc_synchronize())
+print("ok")
