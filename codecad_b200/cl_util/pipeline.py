@@ -10,26 +10,29 @@ package do not use them any more: their whole hierarchy runs device-resident.)
 """
 
 
-class _NoEvent:
-    def wait(self):
-        pass
-
-
 def interleave2(job_func, initial_jobs):
     stack = list(initial_jobs)
-    running = []  # [generator, pending event], oldest first, at most two
-    while stack or running:
-        while stack and len(running) < 2:
-            running.append([job_func(stack.pop()), _NoEvent()])
-        job = running.pop(0)
-        job[1].wait()
+    pending = []  # [generator, event] of jobs that have yielded, oldest first; at most two
+
+    def advance(gen):
         try:
-            job[1] = job[0].send(None)
+            event = gen.send(None)
         except StopIteration as stop:
             if stop.value is not None:
                 stack.extend(stop.value)
         else:
-            running.append(job)
+            pending.append([gen, event])
+
+    while True:
+        # top the pipeline up first: a new job runs to its first yield (its kernel is
+        # enqueued) before we block on the older job's event
+        while stack and len(pending) < 2:
+            advance(job_func(stack.pop()))
+        if not pending:
+            return
+        gen, event = pending.pop(0)
+        event.wait()
+        advance(gen)
 
 
 def interleave(initial_jobs, helper1, helper2):

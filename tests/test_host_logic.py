@@ -1,0 +1,206 @@
+"""Host-side logic of the drop-in modules (no GPU): block planner, pipelines, slabs, the
+mass-property post-processing."""
+import itertools
+import math
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from codecad_b200 import BoundingBox, Vector, calculate_block_sizes
+from codecad_b200 import mass_properties as mp_mod_fn  # noqa: F401 (function re-export exists)
+from codecad_b200.cl_util import interleave, interleave2
+from codecad_b200.grid_eval import slab_range
+from oracle import host
+
+import importlib
+mp_mod = importlib.import_module("codecad_b200.mass_properties")
+
+
+# ---- calculate_block_sizes: reference tests/test_subdivision.py:44-107 (80 cases) ------------
+@pytest.mark.parametrize("box_size", [Vector(10, 20, 30), Vector(16, 16, 16)])
+@pytest.mark.parametrize("dimension", [2, 3])
+@pytest.mark.parametrize("resolution", [1, 0.1])
+@pytest.mark.parametrize("grid_size, multiplier", [(2, 1), (2, 2), (21, 1), (256, 1), (256, 256)])
+@pytest.mark.parametrize("overlap", [True, False])
+def test_block_sizes(box_size, dimension, resolution, grid_size, overlap, multiplier):
+    box = BoundingBox(-box_size / 2, box_size / 2)
+    bs = calculate_block_sizes(box, dimension, resolution, grid_size, overlap, multiplier)
+
+    assert bs[-1][0] == 1, "Final block size must have block size 1"
+    for i, (level_resolution, level_size) in enumerate(bs):
+        if i > 0:
+            for j in range(dimension):
+                assert level_size[j] == grid_size
+        if dimension == 2:
+            assert level_size[2] == 1
+        assert level_size[0] > 1 or level_size[1] > 1 or level_size[2] > 1
+        for j in range(dimension):
+            assert level_size[j] % multiplier == 0
+
+    real_block_size = bs[0][0] * resolution
+    if overlap and len(bs) == 1:
+        for i in range(dimension):
+            assert bs[0][1][i] >= box_size[i] / real_block_size + 1
+            assert multiplier > 1 or box_size[i] / real_block_size + 1 > (bs[0][1][i] - 1)
+    else:
+        for i in range(dimension):
+            assert bs[0][1][i] >= box_size[i] / (bs[0][0] * resolution)
+            assert multiplier > 1 or box_size[i] / real_block_size > (bs[0][1][i] - 1)
+
+    for level_number, ((lr, ls), (pr, ps)) in enumerate(zip(bs[:-1], bs[1:])):
+        for i in range(dimension):
+            if overlap and level_number == len(bs) - 2:
+                assert lr == pr * (ps[i] - 1)
+            else:
+                assert lr == pr * ps[i]
+
+    # and it is the same plan as the oracle's restatement of subdivision.py:116-166
+    want = host.calculate_block_sizes(tuple(box.a), tuple(box.b), dimension, resolution, grid_size, overlap, multiplier)
+    assert [(c, tuple(d)) for c, d in bs] == [(c, tuple(d)) for c, d in want]
+
+
+def test_block_sizes_rejects_bad_multiplier():
+    with pytest.raises(ValueError):
+        calculate_block_sizes(BoundingBox(Vector(0, 0, 0), Vector(1, 1, 1)), 3, 0.1, 10, False, 3)
+
+
+def test_block_sizes_survey_values():
+    """SURVEY.md 8(a6) probed plans for csg_example at resolution 100/512"""
+    box = BoundingBox(Vector(-50, -50, -50), Vector(50, 50, 50)).expanded_additive(100 / 512 / 2)
+    bs = calculate_block_sizes(box, 3, 100 / 512, 128, True)
+    assert [(c, tuple(d)) for c, d in bs] == [(127, (5, 5, 5)), (1, (128, 128, 128))]
+    bs = calculate_block_sizes(box, 3, 100 / 512, 16, True)
+    assert [(c, tuple(d)) for c, d in bs] == [(240, (3, 3, 3)), (15, (16, 16, 16)), (1, (16, 16, 16))]
+
+
+def test_argument_contracts_match_the_reference():
+    """subdivision.py:204-208 and mass_properties.py:38-41 raise AssertionError before any
+    device work"""
+    import codecad_b200
+    from scenes import load_scenes
+    s = load_scenes()["mp_unit_box"].compiled()
+    s._buffer = object()  # must not be reached: no GPU here
+    for kw in ({"resolution": 0}, {"resolution": 1, "grid_size": 1}, {"resolution": 1, "grid_size": 257}):
+        with pytest.raises(AssertionError):
+            codecad_b200.subdivision(s, **kw)
+    for kw in ({"resolution": -1}, {"resolution": 1, "grid_size": 1}, {"resolution": 1, "grid_size": 85}):
+        with pytest.raises(AssertionError):
+            codecad_b200.mass_properties(s, **kw)
+    flat = load_scenes()["dsdf2d_circle"].compiled()
+    with pytest.raises(AssertionError):
+        codecad_b200.mass_properties(flat, 0.1)
+
+
+# ---- interleave2: reference tests/test_clutil.py:188-248 -------------------------------------------
+def test_interleave2_keeps_two_jobs_in_flight():
+    job_log = []
+
+    class MockEvent:
+        def __init__(self, job):
+            self.job = job
+
+        def wait(self):
+            job_log.append((self.job, "wait"))
+
+    def job_func(job):
+        job_log.append((job, 1))
+        yield MockEvent(job)
+        job_log.append((job, 2))
+        if job < 10:
+            return [2 * job, 2 * job + 1]
+        return None
+
+    interleave2(job_func, [2, 3])
+
+    checked = set()
+    working = set()
+    tics_working = 0
+    max_working = 0
+    for job, step in job_log:
+        if working:
+            tics_working += 1
+        max_working = max(max_working, len(working))
+        if step == 1:
+            working.add(job)
+        elif step == "wait":
+            working.remove(job)
+        elif step == 2:
+            assert (job, "wait") in checked
+        if job > 3:
+            assert (job // 2, 2) in checked, "Parent task must be finished before running a child"
+        checked.add((job, step))
+    assert (18, 2) in checked and (19, 2) in checked
+    assert max_working == 2
+    assert tics_working >= len(checked) - 4
+
+
+def test_interleave_helpers_alternate():
+    log = []
+
+    class Helper:
+        def __init__(self, name):
+            self.name = name
+
+        def enqueue(self, job):
+            log.append((self.name, "enqueue", job))
+            self.job = job
+            return job
+
+        def process_result(self, event):
+            log.append((self.name, "result", event))
+            return [(event * 2,), (event * 2 + 1,)] if event < 4 else []
+
+    interleave([(1,)], Helper("a"), Helper("b"))   # jobs are argument tuples (cl_buffer.py:182)
+    done = sorted(j for _, what, j in log if what == "result")
+    assert done == [1, 2, 3, 4, 5, 6, 7]
+    # a job's result is processed by the helper that enqueued it
+    for name, what, job in log:
+        if what == "result":
+            assert (name, "enqueue", job) in log
+
+
+# ---- slabs ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,world", [(1024, 1), (1024, 2), (1024, 8), (513, 4), (7, 8), (2048, 8)])
+def test_slab_range_partitions_the_axis(n, world):
+    edges = [slab_range(n, r, world) for r in range(world)]
+    assert edges[0][0] == 0 and edges[-1][1] == n
+    assert all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
+    sizes = [b - a for a, b in edges]
+    assert max(sizes) - min(sizes) <= 1
+
+
+# ---- mass-property post-processing (mass_properties.py:179-229) ---------------------------------------
+def test_finish_matches_oracle_and_analytic_box():
+    # integrals of the box [1,3] x [0,2] x [-1,5]
+    a, b = np.array([1.0, 0.0, -1.0]), np.array([3.0, 2.0, 5.0])
+    size = b - a
+    vol = size.prod()
+    first = vol * (a + b) / 2
+    second = vol * (a * a + a * b + b * b) / 3
+    c = (a + b) / 2
+    ints = [vol, first[0], first[1], first[2], second[0], second[1], second[2],
+            vol * c[0] * c[1], vol * c[0] * c[2], vol * c[1] * c[2]]
+    got = mp_mod.finish(ints)
+    want = host.finish_mass_properties(ints)
+    assert got.volume == want[0] and tuple(got.centroid) == tuple(want[1])
+    assert np.array_equal(got.inertia_tensor, want[2])
+    assert got.volume == pytest.approx(24.0)
+    assert tuple(got.centroid) == pytest.approx((2.0, 1.0, 2.0))
+    ex = vol / 12 * np.array([size[1] ** 2 + size[2] ** 2, size[0] ** 2 + size[2] ** 2, size[0] ** 2 + size[1] ** 2])
+    assert np.allclose(np.diag(got.inertia_tensor), ex)
+    assert np.allclose(got.inertia_tensor - np.diag(np.diag(got.inertia_tensor)), 0, atol=1e-9)
+
+
+def test_finish_zero_volume():
+    r = mp_mod.finish([0.0] * 10)
+    assert r.volume == 0 and tuple(r.centroid) == (0, 0, 0) and np.array_equal(r.inertia_tensor, np.zeros((3, 3)))
+
+
+def test_vector_matches_reference_semantics():
+    v = Vector(1, 2)
+    assert v.z == 0 and v == (1, 2, 0) and hash(v) == hash((1, 2, 0))
+    assert (Vector(1, 2, 3) * 2 + Vector(1, 1, 1)) == (3, 5, 7)
+    f4 = Vector(0.1, 0.2, 0.3).as_float4()
+    assert f4.dtype.names == ("x", "y", "z", "w") and f4["x"] == np.float32(0.1) and f4["w"] == 0

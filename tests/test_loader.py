@@ -1,0 +1,135 @@
+"""Program loader (wire format -> device microcode), host-only through cc_program_decode:
+no GPU needed.  Covers validation/error behaviour, liveness renaming, store folding,
+primitive fusion and the static flop count."""
+import collections
+
+import numpy as np
+import pytest
+
+from codecad_b200 import _lib
+from codecad_b200.opcodes import OPCODE, REGISTER_COUNT, disassemble, disassemble_microcode, SLOT_NONE
+from scenes import ALL_NAMES
+
+
+def ins(name, reg=0, *params):
+    return [float(OPCODE[name] * REGISTER_COUNT + reg)] + [float(p) for p in params]
+
+
+IDENT = (0, 0, 0, 1, 0, 0, 0)
+
+
+@pytest.mark.parametrize("name", ALL_NAMES)
+def test_every_fixture_decodes(scenes, name):
+    s = scenes[name]
+    info, code = _lib.decode_program(s.words)
+    wire = list(disassemble(s.words))
+    assert info.n_instructions == len(wire)
+    assert info.n_words == len(s.words)
+    assert len(code) == info.n_micro_words and len(code) % 4 == 0
+    ops = list(disassemble_microcode(code))
+    assert len(ops) == info.n_micro_ops and ops[-1][1] == "RETURN"
+    # every _store is folded away or dropped; slots are dense and never exceed the wire count
+    assert info.n_slots <= max(1, info.n_wire_registers)
+    used = {o[2] for o in ops if o[2] != SLOT_NONE} | {o[3] for o in ops if o[3] != SLOT_NONE}
+    assert used <= set(range(info.n_slots))
+    # a slot is written before it is read
+    written = set()
+    for _, opname, src, dst, _ in ops:
+        if src != SLOT_NONE:
+            assert src in written, "slot %d read before written" % src
+        if dst != SLOT_NONE:
+            written.add(dst)
+    assert info.flops_min <= info.flops_max
+
+
+def test_config_scene_statistics(scenes):
+    """SURVEY.md 8 scene table: instruction counts and the (much smaller) live sets."""
+    expect = {"cfg_csg_example": 28, "cfg_menger_sponge": 115, "cfg_airfoil": 119, "cfg_planetary": 467,
+              "cfg_synthetic500": 3999}
+    for name, n in expect.items():
+        info, _ = _lib.decode_program(scenes[name].words)
+        assert info.n_instructions == n
+        assert info.n_slots <= 10
+    info, code = _lib.decode_program(scenes["cfg_synthetic500"].words)
+    c = collections.Counter(o[1] for o in disassemble_microcode(code))
+    assert c["PRIM_RECT"] == 500 and c["UNION_R"] == 499 and info.n_micro_ops == 1000
+    assert info.n_wire_registers >= 500 and info.n_slots < 12   # the reference scheduler leaks registers
+
+
+def test_flop_count_matches_survey(scenes):
+    """static algorithmic flop/point, SURVEY.md 8(d): csg 264-339, menger 1714-1984,
+    planetary 6985-7600, synthetic 52 491-73 479"""
+    want = {"cfg_csg_example": (264, 339), "cfg_menger_sponge": (1714, 1984), "cfg_planetary": (6985, 7600),
+            "cfg_synthetic500": (52491, 73479)}
+    for name, (lo, hi) in want.items():
+        info, _ = _lib.decode_program(scenes[name].words)
+        assert (info.flops_min, info.flops_max) == (lo, hi)
+
+
+def test_box_is_one_fused_primitive():
+    # box(1): SURVEY.md appendix A worked example
+    words = ins("initial_transformation_to", 0, *IDENT) + ins("_store", 0) + ins("rectangle", 0, .5, .5) \
+        + ins("extrusion", 0, .5) + ins("_return")
+    info, code = _lib.decode_program(words)
+    ops = [o[1] for o in disassemble_microcode(code)]
+    assert ops == ["PRIM_RECT", "RETURN"] and info.n_fused == 1 and info.n_slots == 0
+    f = code.view(np.float32)
+    assert list(f[1:10]) == [1, 0, 0, 0, 1, 0, 0, 0, 1]            # rotation matrix of the unit quaternion
+    assert list(f[13:17]) == [.5, .5, .5, 0]                        # hw, hh, h, offset 0
+    assert list(f[17:27]) == [1, 0, 0, 0, 1, 0, 0, 0, 1, 1]         # identity transformation_from, scale 1
+
+
+def test_point_with_two_readers_is_not_fused():
+    words = ins("initial_transformation_to", 0, *IDENT) + ins("_store", 3) + ins("circle", 0, 2) \
+        + ins("extrusion", 3, 1) + ins("_store", 5) + ins("_load", 3) + ins("sphere", 0, 1) \
+        + ins("union", 5, -1) + ins("_return")
+    info, code = _lib.decode_program(words)
+    ops = list(disassemble_microcode(code))
+    assert [o[1] for o in ops] == ["T_INIT", "CIRCLE", "EXTRUSION", "LOAD", "SPHERE", "UNION", "RETURN"]
+    assert info.n_fused == 0 and info.n_slots == 2
+    assert ops[0][3] == 0 and ops[2][2] == 0 and ops[2][3] == 1 and ops[3][2] == 0 and ops[5][2] == 1
+
+
+def test_dead_store_is_dropped_and_registers_are_recycled():
+    words = ins("initial_transformation_to", 0, *IDENT)
+    for r in range(40):                       # 40 wire registers, one live at a time
+        words += ins("_store", r) + ins("sphere", 0, 1) + ins("union", r, -1)
+    words += ins("_store", 77) + ins("_return")   # never read
+    info, code = _lib.decode_program(words)
+    assert info.n_wire_registers == 78 and info.n_slots == 1
+    assert all(o[3] in (0, SLOT_NONE) for o in disassemble_microcode(code))
+
+
+def test_rounded_versus_sharp_combinators():
+    base = ins("initial_transformation_to", 0, *IDENT) + ins("_store", 0) + ins("sphere", 0, 1)
+    for name, sharp, rnd in (("union", "UNION", "UNION_R"), ("intersection", "ISECT", "ISECT_R"),
+                             ("subtraction", "SUB", "SUB_R")):
+        for r, want in ((-1.0, sharp), (0.0, rnd), (0.5, rnd)):
+            _, code = _lib.decode_program(base + ins(name, 0, r) + ins("_return"))
+            assert [o[1] for o in disassemble_microcode(code)][-2] == want
+
+
+@pytest.mark.parametrize("words,fragment", [
+    ([], "without _return"),
+    (ins("initial_transformation_to", 0, *IDENT), "without _return"),
+    (ins("initial_transformation_to", 0, 0, 0), "truncated"),
+    ([float(29 * 512)], "invalid instruction word"),
+    ([-1.0], "invalid instruction word"),
+    ([5632.5], "invalid instruction word"),
+    ([float("nan")], "invalid instruction word"),
+    (ins("sphere", 0, 1) + ins("_return"), "must start with"),
+    (ins("initial_transformation_to", 0, *IDENT) + ins("_load", 4) + ins("_return"), "before any _store"),
+    (ins("initial_transformation_to", 0, *IDENT) + ins("union", 2, -1) + ins("_return"), "before any _store"),
+    (ins("initial_transformation_to", 0, *IDENT) + ins("polygon2d", 0, 0) + ins("_return"), "polygon2d"),
+    (ins("initial_transformation_to", 0, *IDENT) + ins("polygon2d", 0, 3, 0, 0, 1, 0), "truncated"),
+])
+def test_malformed_programs_are_rejected(words, fragment):
+    with pytest.raises(_lib.CodecadB200Error) as e:
+        _lib.decode_program(np.array(words, np.float32))
+    assert fragment in str(e.value)
+
+
+def test_words_after_return_are_ignored():
+    words = ins("initial_transformation_to", 0, *IDENT) + ins("sphere", 0, 1) + ins("_return") + [123.0, 456.0]
+    info, _ = _lib.decode_program(words)
+    assert info.n_words == len(words) - 2 and info.n_instructions == 3
