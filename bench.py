@@ -225,7 +225,9 @@ def workload_config(n, world):
 
 def run_ours(args):
     rank, world, local, torch, dist = dist_setup(args.gpus)
-    from codecad_b200 import _lib, grid_eval as ge
+    import importlib
+    from codecad_b200 import _lib
+    ge = importlib.import_module("codecad_b200.grid_eval")  # (the package re-exports a function of that name)
     from codecad_b200.cl_util import Buffer
     from codecad_b200.cl_util.buffer import ProgramBuffer, _Pinned
     from codecad_b200.geometry import FLOAT4

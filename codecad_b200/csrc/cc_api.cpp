@@ -101,8 +101,10 @@ int choose_cfg(const cc_program *prog, uint64_t total_points, cc_launch_cfg *cfg
     int space = g.prog_space;
     if (space == 0) space = 1;
     if (space == 1 && words > CC_CONST_WORDS) space = 2;
-    int pts = g.pts ? g.pts : 4;
-    if (pts != 1 && pts != 2 && pts != 4) pts = 4;
+    // two points per thread measured best on B200 (profiles/r1_ab_variants.md): four halve the
+    // resident warps without enough extra ILP to pay for it
+    int pts = g.pts ? g.pts : 2;
+    if (pts != 1 && pts != 2 && pts != 4) pts = 2;
     // small launches: fewer points per thread keeps more SMs busy
     if (!g.pts) {
         while (pts > 1 && total_points < (uint64_t)g.prop.multiProcessorCount * 128u * pts * 2u) pts >>= 1;

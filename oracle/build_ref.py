@@ -159,7 +159,11 @@ def build(force=False):
         f.write(translate(collect_reference_program()))
     cmd = ["g++", "-std=c++17", "-O2", "-mavx2", "-mfma", "-ffp-contract=off", "-fno-fast-math", "-fopenmp",
            "-fpermissive", "-Wno-narrowing", "-w", "-shared", "-fPIC", "-o", SO, src]
-    subprocess.run(cmd, check=True)
+    try:
+        subprocess.run(cmd, check=True)
+    finally:
+        if not os.environ.get("CODECAD_KEEP_REF_TRANSLATION"):
+            os.remove(src)  # the translated unit is reference text: never left lying around
     return SO
 
 
