@@ -160,6 +160,12 @@ def cpu_sample_run(scene, n, target_seconds, steps=1, impl="auto"):
                 kind = "reference"
         except Exception:  # noqa: BLE001 - _ref not built: use the port
             pass
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every core it may run on
+    try:
+        usable = len(os.sched_getaffinity(0))
+    except AttributeError:
+        usable = os.cpu_count() or 1
+    oracle.set_num_threads(usable)   # same libgomp instance serves oracle/_ref
     threads = oracle.num_threads()
     corner, step = scene.grid(n)
     # probe one plane stripe to size the sample
