@@ -98,9 +98,10 @@ int choose_cfg(const cc_program *prog, uint64_t total_points, cc_launch_cfg *cfg
     const size_t smem_max = g.prop.sharedMemPerBlockOptin;
     // microcode in the constant bank (uniform loads, parameters stay in uniform registers)
     // whenever it fits the 63 KB window; larger programs are staged in shared memory
+    // 1 = constant bank, 2 = shared copy, 3 = hybrid (headers constant, parameters shared)
     int space = g.prog_space;
-    if (space == 0) space = 1;
-    if (space == 1 && words > CC_CONST_WORDS) space = 2;
+    if (space == 0) space = (words * 4 <= 16384) ? 3 : 1;
+    if (space != 2 && words > CC_CONST_WORDS) space = 2;
     // two points per thread measured best on B200 (profiles/r1_ab_variants.md): four halve the
     // resident warps without enough extra ILP to pay for it
     int pts = g.pts ? g.pts : 2;
@@ -116,7 +117,7 @@ int choose_cfg(const cc_program *prog, uint64_t total_points, cc_launch_cfg *cfg
         // want at least two CTAs per SM when possible
         if (need * 2 <= (size_t)g.prop.sharedMemPerMultiprocessor - 2048 || pts == 1) {
             if (need > smem_max) {
-                if (space == 2 && words <= CC_CONST_WORDS) {
+                if (space != 1 && words <= CC_CONST_WORDS) {
                     space = 1;
                     continue;
                 }
@@ -132,7 +133,7 @@ int choose_cfg(const cc_program *prog, uint64_t total_points, cc_launch_cfg *cfg
 
 int prepare_program(const cc_program *prog, const cc_launch_cfg &cfg)
 {
-    if (cfg.prog_space == 1 && g.constant_program != prog->id) {
+    if (cfg.prog_space != 2 && g.constant_program != prog->id) {
         int e = cc_upload_constant_program(prog->dec.microcode.data(), prog->dec.info.n_micro_words, g.compute);
         if (e) return cuda_fail((cudaError_t)e, "cudaMemcpyToSymbolAsync");
         g.constant_program = prog->id;
@@ -278,7 +279,7 @@ int cc_set_tuning(int points_per_thread, int program_space)
 {
     if (points_per_thread != 0 && points_per_thread != 1 && points_per_thread != 2 && points_per_thread != 4)
         return fail(CC_ERR_INVALID_ARGUMENT, "points_per_thread must be 0, 1, 2 or 4");
-    if (program_space < 0 || program_space > 2) return fail(CC_ERR_INVALID_ARGUMENT, "program_space must be 0, 1 or 2");
+    if (program_space < 0 || program_space > 3) return fail(CC_ERR_INVALID_ARGUMENT, "program_space must be 0..3");
     g.pts = points_per_thread;
     g.prog_space = program_space;
     return CC_OK;

@@ -33,15 +33,19 @@
 
 __constant__ uint32_t c_code[CC_CONST_WORDS];
 
-template <bool SMEM>
+// Where the microcode is read from.  MODE 0: everything from the constant bank.  MODE 1:
+// everything from the shared-memory copy.  MODE 2 (hybrid): instruction headers from the
+// constant bank — decode and dispatch stay in the uniform datapath — and parameters from the
+// shared-memory copy with one broadcast LDS.128 per four words.
+template <int MODE>
 struct Prog {
     const uint32_t *s;
-    CC_DEV uint32_t u(uint32_t i) const { return SMEM ? s[i] : c_code[i]; }
-    CC_DEV float f(uint32_t i) const { return __uint_as_float(u(i)); }
+    CC_DEV uint32_t u(uint32_t i) const { return MODE == 1 ? s[i] : c_code[i]; }
+    CC_DEV float f(uint32_t i) const { return __uint_as_float(MODE == 0 ? c_code[i] : s[i]); }
     // 16-byte aligned group of four words
     CC_DEV float4 f4(uint32_t i) const
     {
-        if (SMEM) return *reinterpret_cast<const float4 *>(s + i);
+        if (MODE != 0) return *reinterpret_cast<const float4 *>(s + i);
         // constant bank: vector LDC.64 pairs.  (Measured on B200, profiles/r1_ab_variants.md:
         // four scalar uniform LDCU reads instead are 17 % slower on the planetary scene.)
         return *reinterpret_cast<const float4 *>(c_code + i);
@@ -49,7 +53,7 @@ struct Prog {
 };
 
 // polygons2d.cl:1-74 over the precomputed edge table (px, py, dx, dy, 1/|d|^2, cy)
-template <bool SMEM>
+template <int SMEM>
 CC_DEV_HEAVY float4 cc_polygon2d(const Prog<SMEM> &P, uint32_t pc, float4 co)
 {
     uint32_t n = (uint32_t)P.f(pc + 1);
@@ -88,8 +92,9 @@ CC_DEV_HEAVY float4 cc_polygon2d(const Prog<SMEM> &P, uint32_t pc, float4 co)
 // never leaves registers.  Bit-identical to the unfused sequence (absent offset = 0, absent
 // transformation_from = identity matrix and scale 1).
 // words: 1..12 m,o | 13 a | 14 b | 15 h | 16 d | 17..25 m' | 26 scale
-template <bool RECT, bool SMEM>
-CC_DEV float4 cc_prim(const Prog<SMEM> &P, uint32_t pc, float x, float y, float z)
+template <bool RECT, int PTS, int SMEM>
+CC_DEV void cc_prim(const Prog<SMEM> &P, uint32_t pc, const float (&x)[PTS], const float (&y)[PTS],
+                    const float (&z)[PTS], float4 (&L)[PTS])
 {
     float m[12], mf[12];
     const float4 a = P.f4(pc), b = P.f4(pc + 4), c = P.f4(pc + 8), d = P.f4(pc + 12), e = P.f4(pc + 16),
@@ -98,14 +103,23 @@ CC_DEV float4 cc_prim(const Prog<SMEM> &P, uint32_t pc, float x, float y, float 
     m[6] = b.w; m[7] = c.x; m[8] = c.y; m[9] = c.z; m[10] = c.w; m[11] = d.x;
     mf[0] = e.y; mf[1] = e.z; mf[2] = e.w; mf[3] = f.x; mf[4] = f.y; mf[5] = f.z;
     mf[6] = f.w; mf[7] = g.x; mf[8] = g.y; mf[9] = g.z; mf[10] = 0.f; mf[11] = 0.f;
-    const float4 p = cc_transform(m, x, y, z);
-    float4 v = RECT ? cc_rectangle(d.y, d.z, p) : cc_circle(d.y, p);
-    v = cc_extrusion(d.w, v, p.z);
-    v.w = v.w - e.x;
-    return cc_transform_from(mf, v);
+    float pz[PTS];
+#pragma unroll
+    for (int j = 0; j < PTS; ++j) {
+        L[j] = cc_transform(m, x[j], y[j], z[j]);
+        pz[j] = L[j].z;
+    }
+    if (RECT) cc_rectangle_n<PTS>(d.y, d.z, L);
+    else cc_circle_n<PTS>(d.y, L);
+    cc_extrusion_n<PTS>(d.w, L, pz);
+#pragma unroll
+    for (int j = 0; j < PTS; ++j) {
+        L[j].w = L[j].w - e.x;
+        L[j] = cc_transform_from(mf, L[j]);
+    }
 }
 
-template <int PTS, bool SMEM>
+template <int PTS, int SMEM>
 CC_DEV void cc_interpret(const Prog<SMEM> P, float4 *__restrict__ regs, const float (&gx)[PTS],
                          const float (&gy)[PTS], const float (&gz)[PTS], float4 (&L)[PTS])
 {
@@ -126,27 +140,26 @@ CC_DEV void cc_interpret(const Prog<SMEM> P, float4 *__restrict__ regs, const fl
             pc += CC_LEN_0;
             break;
         case MOP_NOP: pc += CC_LEN_0; break;
+        // NB: pc is advanced AFTER each op, and the batched ops branch on a warp vote: both
+        // are needed for nvcc to keep pc warp-uniform, i.e. decode + dispatch in the uniform
+        // datapath (UISETP/BRA.U/LDCU).  Losing that costs ~11 % (profiles/r1_ab_variants.md).
         case MOP_PRIM_CIRCLE:
-#pragma unroll
-            CC_EACH L[j] = cc_prim<false, SMEM>(P, pc, gx[j], gy[j], gz[j]);
+            cc_prim<false, PTS, SMEM>(P, pc, gx, gy, gz, L);
             pc += CC_LEN_PRIM;
             break;
         case MOP_PRIM_RECT:
-#pragma unroll
-            CC_EACH L[j] = cc_prim<true, SMEM>(P, pc, gx[j], gy[j], gz[j]);
+            cc_prim<true, PTS, SMEM>(P, pc, gx, gy, gz, L);
             pc += CC_LEN_PRIM;
             break;
         case MOP_RECTANGLE: {
             const float4 q = P.f4(pc);
-#pragma unroll
-            CC_EACH L[j] = cc_rectangle(q.y, q.z, L[j]);
+            cc_rectangle_n<PTS>(q.y, q.z, L);
             pc += CC_LEN_0;
             break;
         }
         case MOP_CIRCLE: {
             const float r = P.f(pc + 1);
-#pragma unroll
-            CC_EACH L[j] = cc_circle(r, L[j]);
+            cc_circle_n<PTS>(r, L);
             pc += CC_LEN_0;
             break;
         }
@@ -168,8 +181,7 @@ CC_DEV void cc_interpret(const Prog<SMEM> P, float4 *__restrict__ regs, const fl
         }
         case MOP_SPHERE: {
             const float r = P.f(pc + 1);
-#pragma unroll
-            CC_EACH L[j] = cc_sphere(r, L[j]);
+            cc_sphere_n<PTS>(r, L);
             pc += CC_LEN_0;
             break;
         }
@@ -275,8 +287,10 @@ CC_DEV void cc_interpret(const Prog<SMEM> P, float4 *__restrict__ regs, const fl
         // ---- ops whose second operand is a point held in a slot ----
         case MOP_EXTRUSION: {
             const float hh = P.f(pc + 1);
+            float cz[PTS];
 #pragma unroll
-            CC_EACH L[j] = cc_extrusion(hh, L[j], CC_SLOT(src, j).z);
+            CC_EACH cz[j] = CC_SLOT(src, j).z;
+            cc_extrusion_n<PTS>(hh, L, cz);
             pc += CC_LEN_0;
             break;
         }
@@ -416,7 +430,7 @@ CC_DEV uint32_t cc_lookback(unsigned long long *status, uint32_t tile, uint32_t 
 }
 
 // ---- the kernel -----------------------------------------------------------------------------
-template <int PTS, bool SMEM, int SINK>
+template <int PTS, int SMEM, int SINK>
 __global__ void __launch_bounds__(CC_THREADS) cc_eval_kernel(const cc_eval_args a)
 {
     extern __shared__ float4 smem4[];
@@ -429,7 +443,7 @@ __global__ void __launch_bounds__(CC_THREADS) cc_eval_kernel(const cc_eval_args 
     const uint32_t tid = threadIdx.x;
     constexpr bool ORDERED = (SINK == CC_SINK_CLASSIFY || SINK == CC_SINK_MASS);
 
-    if (SMEM) {
+    if (SMEM != 0) {
         // stage the microcode once per CTA: 16-byte cp.async, all threads
         const uint32_t n4 = a.code_words / 4;
         for (uint32_t i = tid; i < n4; i += CC_THREADS) {
@@ -474,7 +488,7 @@ __global__ void __launch_bounds__(CC_THREADS) cc_eval_kernel(const cc_eval_args 
         gz[j] = cc_fma(a.step, (float)iz[j], cz);
     }
 
-    if (SMEM) {
+    if (SMEM != 0) {
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
     }
@@ -578,7 +592,7 @@ uint32_t cc_tile_points(const cc_launch_cfg &cfg) { return (uint32_t)(CC_THREADS
 size_t cc_eval_smem_bytes(const cc_launch_cfg &cfg, uint32_t n_slots, uint32_t code_words)
 {
     size_t b = (size_t)n_slots * cfg.pts * CC_THREADS * sizeof(float4);
-    if (cfg.prog_space == 2) b += (size_t)code_words * 4;
+    if (cfg.prog_space != 1) b += (size_t)code_words * 4;  // shared copy (2 = shared, 3 = hybrid)
     return b;
 }
 
@@ -588,7 +602,7 @@ int cc_upload_constant_program(const uint32_t *h_code, uint32_t n_words, void *s
                                         (cudaStream_t)stream);
 }
 
-template <int PTS, bool SMEM, int SINK>
+template <int PTS, int SMEM, int SINK>
 static int launch_one(const cc_eval_args &a, size_t smem, uint32_t grid, cudaStream_t st)
 {
     auto k = cc_eval_kernel<PTS, SMEM, SINK>;
@@ -601,12 +615,17 @@ static int launch_one(const cc_eval_args &a, size_t smem, uint32_t grid, cudaStr
 template <int SINK>
 static int launch_sink(const cc_launch_cfg &cfg, const cc_eval_args &a, size_t smem, uint32_t grid, cudaStream_t st)
 {
-    const bool sm = cfg.prog_space == 2;
+    // prog_space: 1 = constant bank, 2 = shared copy, 3 = hybrid  ->  Prog MODE 0 / 1 / 2
+#define CC_LAUNCH_PTS(P)                                                                \
+    (cfg.prog_space == 1 ? launch_one<P, 0, SINK>(a, smem, grid, st)                    \
+                         : cfg.prog_space == 2 ? launch_one<P, 1, SINK>(a, smem, grid, st) \
+                                               : launch_one<P, 2, SINK>(a, smem, grid, st))
     switch (cfg.pts) {
-    case 1: return sm ? launch_one<1, true, SINK>(a, smem, grid, st) : launch_one<1, false, SINK>(a, smem, grid, st);
-    case 2: return sm ? launch_one<2, true, SINK>(a, smem, grid, st) : launch_one<2, false, SINK>(a, smem, grid, st);
-    default: return sm ? launch_one<4, true, SINK>(a, smem, grid, st) : launch_one<4, false, SINK>(a, smem, grid, st);
+    case 1: return CC_LAUNCH_PTS(1);
+    case 2: return CC_LAUNCH_PTS(2);
+    default: return CC_LAUNCH_PTS(4);
     }
+#undef CC_LAUNCH_PTS
 }
 
 int cc_launch_eval(int sink, const cc_launch_cfg &cfg, const cc_eval_args &a, void *stream)

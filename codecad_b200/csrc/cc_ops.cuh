@@ -81,6 +81,129 @@ CC_DEV float4 cc_sphere(float r, float4 p)
     return make_float4(zero ? 1.0f : p.x * inv, zero ? 0.0f : p.y * inv, zero ? 0.0f : p.z * inv, len - r);
 }
 
+// ---- the same ops over all PTS points of a thread, with one combined special-operand test ----
+// Results are identical to the per-point forms above (which remain the slow path and the
+// reference for the oracle): in the fast path every sqrt/rcp operand is in the exact range of
+// cc_sqrt_fast / cc_rcp_fast, and a length in that range is never zero.
+__device__ __noinline__ float4 cc_rectangle_slow(float hw, float hh, float4 p) { return cc_rectangle(hw, hh, p); }
+__device__ __noinline__ float4 cc_circle_slow(float r, float4 p) { return cc_circle(r, p); }
+__device__ __noinline__ float4 cc_sphere_slow(float r, float4 p) { return cc_sphere(r, p); }
+__device__ __noinline__ float4 cc_extrusion_slow(float h, float4 in, float cz) { return cc_extrusion(h, in, cz); }
+
+template <int PTS>
+CC_DEV void cc_rectangle_n(float hw, float hh, float4 (&L)[PTS])
+{
+    float ax[PTS], ay[PTS], s[PTS];
+    bool sp = false;
+#pragma unroll
+    for (int j = 0; j < PTS; ++j) {
+        ax[j] = fabsf(L[j].x) - hw;
+        ay[j] = fabsf(L[j].y) - hh;
+        s[j] = cc_fma(ax[j], ax[j], ay[j] * ay[j]);
+        sp |= cc_special(s[j]);
+    }
+    if (__any_sync(0xffffffffu, sp)) {  // warp-uniform: keeps the interpreter's control flow convergent
+#pragma unroll
+        for (int j = 0; j < PTS; ++j) L[j] = cc_rectangle_slow(hw, hh, L[j]);
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < PTS; ++j) {
+        const float sx = copysignf(1.0f, L[j].x), sy = copysignf(1.0f, L[j].y);
+        const float dist = cc_sqrt_fast(s[j]);
+        const float inv = cc_rcp_fast(dist);
+        const bool both = ax[j] > 0.0f && ay[j] > 0.0f;
+        const bool first = ax[j] > ay[j];
+        float4 r;
+        r.x = both ? sx * (ax[j] * inv) : (first ? sx : 0.0f);
+        r.y = both ? sy * (ay[j] * inv) : (first ? 0.0f : sy);
+        r.z = 0.0f;
+        r.w = both ? dist : (first ? ax[j] : ay[j]);
+        L[j] = r;
+    }
+}
+
+template <int PTS>
+CC_DEV void cc_circle_n(float r, float4 (&L)[PTS])
+{
+    float s[PTS];
+    bool sp = false;
+#pragma unroll
+    for (int j = 0; j < PTS; ++j) {
+        s[j] = cc_fma(L[j].x, L[j].x, L[j].y * L[j].y);
+        sp |= cc_special(s[j]);
+    }
+    if (__any_sync(0xffffffffu, sp)) {  // warp-uniform: keeps the interpreter's control flow convergent
+#pragma unroll
+        for (int j = 0; j < PTS; ++j) L[j] = cc_circle_slow(r, L[j]);
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < PTS; ++j) {
+        const float len = cc_sqrt_fast(s[j]);
+        const float inv = cc_rcp_fast(len);
+        L[j] = make_float4(L[j].x * inv, L[j].y * inv, 0.0f, len - r);
+    }
+}
+
+template <int PTS>
+CC_DEV void cc_sphere_n(float r, float4 (&L)[PTS])
+{
+    float s[PTS];
+    bool sp = false;
+#pragma unroll
+    for (int j = 0; j < PTS; ++j) {
+        s[j] = cc_fma(L[j].x, L[j].x, cc_fma(L[j].y, L[j].y, L[j].z * L[j].z));
+        sp |= cc_special(s[j]);
+    }
+    if (__any_sync(0xffffffffu, sp)) {  // warp-uniform: keeps the interpreter's control flow convergent
+#pragma unroll
+        for (int j = 0; j < PTS; ++j) L[j] = cc_sphere_slow(r, L[j]);
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < PTS; ++j) {
+        const float len = cc_sqrt_fast(s[j]);
+        const float inv = cc_rcp_fast(len);
+        L[j] = make_float4(L[j].x * inv, L[j].y * inv, L[j].z * inv, len - r);
+    }
+}
+
+// cz[j] = z coordinate of the point operand
+template <int PTS>
+CC_DEV void cc_extrusion_n(float h, float4 (&L)[PTS], const float (&cz)[PTS])
+{
+    float az[PTS], s[PTS];
+    bool sp = false;
+#pragma unroll
+    for (int j = 0; j < PTS; ++j) {
+        az[j] = fabsf(cz[j]) - h;
+        s[j] = cc_fma(az[j], az[j], L[j].w * L[j].w);
+        sp |= cc_special(s[j]);
+    }
+    if (__any_sync(0xffffffffu, sp)) {  // warp-uniform: keeps the interpreter's control flow convergent
+#pragma unroll
+        for (int j = 0; j < PTS; ++j) L[j] = cc_extrusion_slow(h, L[j], cz[j]);
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < PTS; ++j) {
+        const float4 in = L[j];
+        const float sz = copysignf(1.0f, cz[j]);
+        const float dist = cc_sqrt_fast(s[j]);
+        const float inv = cc_rcp_fast(dist);
+        const float m1 = az[j] * inv, m2 = in.w * inv;
+        const bool both = az[j] > 0.0f && in.w > 0.0f;
+        const bool first = az[j] > in.w;
+        float4 r;
+        r.x = both ? in.x * m2 : (first ? 0.0f : in.x);
+        r.y = both ? in.y * m2 : (first ? 0.0f : in.y);
+        r.z = both ? cc_fma(sz, m1, in.z * m2) : (first ? sz : in.z);
+        r.w = both ? dist : (first ? az[j] : in.w);
+        L[j] = r;
+    }
+}
+
 // shapes/common.cl:45-64
 CC_DEV float4 cc_rounded_union(float r, float4 o1, float4 o2)
 {
