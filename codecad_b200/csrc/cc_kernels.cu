@@ -59,7 +59,7 @@ CC_DEV_HEAVY float4 cc_polygon2d(const Prog<SMEM> &P, uint32_t pc, float4 co)
     uint32_t n = (uint32_t)P.f(pc + 1);
     float nnx = 0.0f, nny = 0.0f, nearest = INFINITY, outside = 1.0f;
     bool nearest_is_vertex = false;
-    uint32_t e = pc + 4;
+    uint32_t e = P.u(pc + 2);  // edge table lives after the RETURN instruction
     for (uint32_t i = 0; i < n; ++i, e += CC_POLY_EDGE_WORDS) {
         float px = P.f(e), py = P.f(e + 1), dx = P.f(e + 2), dy = P.f(e + 3), inv = P.f(e + 4), cy = P.f(e + 5);
         float tqx = co.x - px, tqy = co.y - py;
@@ -140,9 +140,11 @@ CC_DEV void cc_interpret(const Prog<SMEM> P, float4 *__restrict__ regs, const fl
             pc += CC_LEN_0;
             break;
         case MOP_NOP: pc += CC_LEN_0; break;
-        // NB: pc is advanced AFTER each op, and the batched ops branch on a warp vote: both
-        // are needed for nvcc to keep pc warp-uniform, i.e. decode + dispatch in the uniform
-        // datapath (UISETP/BRA.U/LDCU).  Losing that costs ~11 % (profiles/r1_ab_variants.md).
+        // NB: pc only ever advances by IMMEDIATE amounts (every micro-op has a fixed length; the
+        // polygon edge table is out of line), after each op, and the batched ops branch on a warp
+        // vote.  That is what lets nvcc prove pc warp-uniform and keep decode + dispatch in the
+        // uniform datapath (LDCU/UISETP/BRA.U); deriving the increment from a loaded word or
+        // advancing before a per-thread branch silently demotes everything to vector code (-11 %).
         case MOP_PRIM_CIRCLE:
             cc_prim<false, PTS, SMEM>(P, pc, gx, gy, gz, L);
             pc += CC_LEN_PRIM;
@@ -173,10 +175,9 @@ CC_DEV void cc_interpret(const Prog<SMEM> P, float4 *__restrict__ regs, const fl
             break;
         }
         case MOP_POLYGON: {
-            const uint32_t n = (uint32_t)P.f(pc + 1);
 #pragma unroll
             CC_EACH L[j] = cc_polygon2d<SMEM>(P, pc, L[j]);
-            pc += 4 + ((CC_POLY_EDGE_WORDS * n + 3) / 4) * 4;
+            pc += CC_LEN_0;
             break;
         }
         case MOP_SPHERE: {
@@ -620,11 +621,15 @@ static int launch_sink(const cc_launch_cfg &cfg, const cc_eval_args &a, size_t s
     (cfg.prog_space == 1 ? launch_one<P, 0, SINK>(a, smem, grid, st)                    \
                          : cfg.prog_space == 2 ? launch_one<P, 1, SINK>(a, smem, grid, st) \
                                                : launch_one<P, 2, SINK>(a, smem, grid, st))
+#ifdef CC_EXPERIMENT_PTS  // compile-time experiments: instantiate a single variant
+    return launch_one<CC_EXPERIMENT_PTS, CC_EXPERIMENT_MODE, SINK>(a, smem, grid, st);
+#else
     switch (cfg.pts) {
     case 1: return CC_LAUNCH_PTS(1);
     case 2: return CC_LAUNCH_PTS(2);
     default: return CC_LAUNCH_PTS(4);
     }
+#endif
 #undef CC_LAUNCH_PTS
 }
 

@@ -8,7 +8,10 @@
 //   * every instruction starts on a 16-byte boundary: word 0 is the header, words
 //     1.. are fp32 parameters, length padded to a multiple of 4 words, so that a warp
 //     fetches header + parameters with a few 128-bit broadcast loads;
-//   * header = micro-op (8 bit) | src slot (12 bit) | dst slot (12 bit);
+//   * header = micro-op (8 bit) | src slot (9 bit) | dst slot (9 bit) | length/4 (6 bit);
+//     the length lives in the header so that the interpreter advances its program counter
+//     in ONE place (the loop latch) from a warp-uniform value — the shape of code for which
+//     nvcc keeps decode and dispatch in the uniform datapath;
 //     `_store` instructions of the wire format are folded into the producing
 //     instruction's dst field and registers are renamed to a dense set of "slots" by a
 //     liveness pass;
@@ -26,7 +29,7 @@ enum cc_mop : uint32_t {
     MOP_RECTANGLE,     // hw, hh
     MOP_CIRCLE,        // r
     MOP_REGPOLY,       // piOverN, r, r*sin, r*cos, 2*piOverN
-    MOP_POLYGON,       // n, then n * (px, py, dx, dy, 1/|d|^2, cy)   [variable length]
+    MOP_POLYGON,       // n, word offset of its edge table: n * (px, py, dx, dy, 1/|d|^2, cy), stored after RETURN
     MOP_SPHERE,        // r
     MOP_HALF_SPACE,
     MOP_REV_TO,
@@ -57,14 +60,15 @@ enum cc_mop : uint32_t {
     MOP_COUNT
 };
 
-#define CC_SLOT_NONE 0xFFFu
-#define CC_SLOT_P 0xFFEu
-#define CC_MAX_SLOTS 0xFF0u
+#define CC_SLOT_NONE 0x1FFu
+#define CC_MAX_SLOTS 0x1FEu
 
-#define CC_HDR(op, src, dst) ((uint32_t)(op) | ((uint32_t)(src) << 8) | ((uint32_t)(dst) << 20))
+#define CC_HDR(op, src, dst, len_words) \
+    ((uint32_t)(op) | ((uint32_t)(src) << 8) | ((uint32_t)(dst) << 17) | ((uint32_t)((len_words) / 4) << 26))
 #define CC_HDR_OP(h) ((h) & 0xFFu)
-#define CC_HDR_SRC(h) (((h) >> 8) & 0xFFFu)
-#define CC_HDR_DST(h) ((h) >> 20)
+#define CC_HDR_SRC(h) (((h) >> 8) & 0x1FFu)
+#define CC_HDR_DST(h) (((h) >> 17) & 0x1FFu)
+#define CC_HDR_LEN(h) (((h) >> 26) * 4u)
 
 // instruction length in 32-bit words (header included), multiple of 4
 #define CC_LEN_0 4   // up to 3 parameters

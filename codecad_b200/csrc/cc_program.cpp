@@ -86,7 +86,7 @@ struct Emitter {
     {
         last_header = code.size();
         code.resize(code.size() + len_words, 0u);
-        code[last_header] = CC_HDR(op, src, CC_SLOT_NONE);
+        code[last_header] = CC_HDR(op, src, CC_SLOT_NONE, len_words);
         return reinterpret_cast<float *>(&code[last_header + 1]);
     }
     bool can_fold_store() const
@@ -98,7 +98,7 @@ struct Emitter {
     void fold_store(uint32_t dst)
     {
         uint32_t h = code[last_header];
-        code[last_header] = CC_HDR(CC_HDR_OP(h), CC_HDR_SRC(h), dst);
+        code[last_header] = CC_HDR(CC_HDR_OP(h), CC_HDR_SRC(h), dst, CC_HDR_LEN(h));
     }
 };
 
@@ -237,6 +237,8 @@ int cc_decode_program(const float *words, uint32_t n_words, cc_decoded *out, std
 
     // ---- 5. emit microcode ------------------------------------------------------------------
     Emitter e;
+    std::vector<size_t> poly_fixups;              // header index of every MOP_POLYGON
+    std::vector<std::vector<float>> poly_tables;  // their edge tables, appended after RETURN
     uint32_t fmin = 0, fmax = 0, n_micro = 0;
     auto cost = [&](uint32_t lo, uint32_t hi) { fmin += lo; fmax += hi; };
     for (size_t i = 0; i < ins.size(); ++i) {
@@ -309,10 +311,11 @@ int cc_decode_program(const float *words, uint32_t n_words, cc_decoded *out, std
             break;
         case W_POLYGON2D: {
             int n = (int)p[0];
-            uint32_t len = 4 + (uint32_t)((CC_POLY_EDGE_WORDS * n + 3) / 4) * 4;
-            q = e.emit(MOP_POLYGON, src, len);
+            q = e.emit(MOP_POLYGON, src, CC_LEN_0);
             q[0] = (float)n;
-            float *eg = q + 3;  // edges start at word 4 of the instruction
+            poly_fixups.push_back(e.last_header);  // word 2 <- offset of the edge table
+            std::vector<float> &tab = poly_tables.emplace_back((size_t)CC_POLY_EDGE_WORDS * n);
+            float *eg = tab.data();
             for (int k = 0; k < n; ++k) {
                 int j = (k + n - 1) % n;  // previous vertex, polygons2d.cl:13,17-18
                 float px = p[1 + 2 * j], py = p[2 + 2 * j];
@@ -419,6 +422,13 @@ int cc_decode_program(const float *words, uint32_t n_words, cc_decoded *out, std
         ++n_micro;
     }
 
+    for (size_t k = 0; k < poly_fixups.size(); ++k) {
+        const uint32_t off = (uint32_t)e.code.size();  // multiple of 4: tables stay 16-byte aligned
+        e.code[poly_fixups[k] + 2] = off;
+        const std::vector<float> &tab = poly_tables[k];
+        e.code.resize(off + (tab.size() + 3) / 4 * 4, 0u);
+        std::memcpy(&e.code[off], tab.data(), tab.size() * sizeof(float));
+    }
     out->microcode.swap(e.code);
     out->info.n_words = pc;
     out->info.n_instructions = (uint32_t)ins.size();

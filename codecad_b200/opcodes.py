@@ -70,25 +70,19 @@ MICRO_OPS = [
     "REPETITION", "CREP_TO", "CREP_FROM", "GEAR", "EXTRUSION", "REV_FROM", "TWIST_FROM", "SYM_FROM",
     "UNION", "UNION_R", "ISECT", "ISECT_R", "SUB", "SUB_R", "PRIM_CIRCLE", "PRIM_RECT",
 ]
-_LEN = {"REGPOLY": 8, "GEAR": 8, "TWIST_FROM": 8, "T_INIT": 16, "T_TO": 16, "T_FROM": 16,
-        "PRIM_CIRCLE": 28, "PRIM_RECT": 28}
-SLOT_NONE, SLOT_P = 0xFFF, 0xFFE
+SLOT_NONE = 0x1FF
 
 
 def disassemble_microcode(code):
-    """Yield (pc, name, src, dst, length_words) for a decoded program."""
+    """Yield (pc, name, src, dst, length_words) for a decoded program.  Header layout
+    (csrc/cc_microcode.h): op 8 bit | src slot 9 bit | dst slot 9 bit | length/4 6 bit."""
     import numpy as _np
     code = _np.asarray(code, dtype=_np.uint32)
     pc = 0
     while pc < len(code):
         h = int(code[pc])
         name = MICRO_OPS[h & 0xFF]
-        src, dst = (h >> 8) & 0xFFF, h >> 20
-        if name == "POLYGON":
-            n = int(code[pc + 1:pc + 2].view(_np.float32)[0])
-            length = 4 + ((6 * n + 3) // 4) * 4
-        else:
-            length = _LEN.get(name, 4)
+        src, dst, length = (h >> 8) & 0x1FF, (h >> 17) & 0x1FF, (h >> 26) * 4
         yield pc, name, src, dst, length
         pc += length
         if name == "RETURN":

@@ -28,6 +28,8 @@ def test_every_fixture_decodes(scenes, name):
     assert len(code) == info.n_micro_words and len(code) % 4 == 0
     ops = list(disassemble_microcode(code))
     assert len(ops) == info.n_micro_ops and ops[-1][1] == "RETURN"
+    # polygon edge tables (6 words per vertex) live after RETURN
+    assert ops[-1][0] + 4 <= len(code)
     # every _store is folded away or dropped; slots are dense and never exceed the wire count
     assert info.n_slots <= max(1, info.n_wire_registers)
     used = {o[2] for o in ops if o[2] != SLOT_NONE} | {o[3] for o in ops if o[3] != SLOT_NONE}

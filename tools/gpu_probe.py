@@ -59,7 +59,7 @@ def main():
                 continue
             pts_s = nx * n * n / (best * 1e-3)
             print("   pts=%d space=%s: %8.3f ms  %8.3f Gpts/s  fp32 frac(min flops) %.3f  store GB/s %.0f" % (
-                pts, "const" if space == 1 else "smem", best, pts_s / 1e9, pts_s * pi.flops_min / peak, pts_s * 16 / 1e9))
+                pts, {1: "const", 2: "smem", 3: "hybrid"}[space], best, pts_s / 1e9, pts_s * pi.flops_min / peak, pts_s * 16 / 1e9))
     _lib.check(L.cc_set_tuning(0, 0))
 
 
