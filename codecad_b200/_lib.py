@@ -60,6 +60,9 @@ SIGNATURES = {
     "cc_program_get_info": (_I, [_V, ctypes.POINTER(ProgramInfo)]),
     "cc_program_get_microcode": (_I, [_V, c_u32_p, _U]),
     "cc_program_decode": (_I, [c_float_p, _U, ctypes.POINTER(ProgramInfo), c_u32_p, _U]),
+    "cc_program_specialize": (_I, [_V, _I, _U, ctypes.POINTER(ctypes.c_double)]),
+    "cc_program_use_specialized": (_I, [_V, _I]),
+    "cc_specialize_source": (_I, [c_float_p, _U, _I, _U, ctypes.c_char_p, _U, _I, ctypes.POINTER(ctypes.c_uint64)]),
     "cc_buffer_alloc": (_I, [ctypes.c_size_t, c_void_pp]),
     "cc_buffer_free": (_I, [_V]),
     "cc_host_alloc": (_I, [ctypes.c_size_t, c_void_pp]),
@@ -160,3 +163,16 @@ def decode_program(words):
     check(load().cc_program_decode(w.ctypes.data_as(c_float_p), len(w), ctypes.byref(info),
                                    out.ctypes.data_as(c_u32_p), n))
     return info, out
+
+
+def specialize_source(words, points_per_thread=2, compile=False, sink_mask=0):
+    """Host-only: CUDA source of the scene-specialised kernels for `words`; with compile=True
+    also run NVRTC on it and return (source, cubin_bytes)."""
+    w = np.ascontiguousarray(words, dtype=np.float32)
+    n = check(load().cc_specialize_source(w.ctypes.data_as(c_float_p), len(w), points_per_thread, sink_mask, None, 0, 0, None))
+    buf = ctypes.create_string_buffer(n + 1)
+    size = ctypes.c_uint64()
+    check(load().cc_specialize_source(w.ctypes.data_as(c_float_p), len(w), points_per_thread, sink_mask, buf, n + 1,
+                                      1 if compile else 0, ctypes.byref(size)))
+    src = buf.value.decode()
+    return (src, int(size.value)) if compile else src

@@ -171,6 +171,20 @@ class ProgramBuffer:
         _lib.check(_lib.lib().cc_program_get_info(self.handle, ctypes.byref(info)))
         return info
 
+    SINK_FLOAT4, SINK_PYMCUBES, SINK_CLASSIFY, SINK_MASS = 1, 2, 4, 8
+
+    def specialize(self, points_per_thread=0, sinks=0):
+        """Compile scene-specialised kernels for this program (NVRTC, seconds per sink); later
+        launches of those sinks use them.  `sinks`: OR of SINK_* (0 = all four).  Returns the
+        compile time in seconds."""
+        secs = ctypes.c_double()
+        _lib.check(_lib.lib().cc_program_specialize(self.handle, int(points_per_thread), int(sinks),
+                                                    ctypes.byref(secs)))
+        return secs.value
+
+    def use_specialized(self, enable=True):
+        return bool(_lib.lib().cc_program_use_specialized(self.handle, 1 if enable else 0))
+
     def microcode(self):
         n = _lib.lib().cc_program_get_microcode(self.handle, None, 0)
         out = np.zeros(n, np.uint32)

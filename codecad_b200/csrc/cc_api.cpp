@@ -159,6 +159,27 @@ int check_dims(uint32_t nx, uint32_t ny, uint32_t nz)
 
 int launch(int sink, const cc_program *prog, cc_eval_args &a, uint64_t points)
 {
+    if (prog->use_jit && prog->jit_kernel[sink]) {
+        // scene-specialised kernel: slots are registers, parameters immediates
+        const uint32_t tile = (uint32_t)(CC_THREADS * prog->jit_pts);
+        const uint64_t cells = (uint64_t)a.nx * a.ny * a.nz;
+        a.tiles_per_block = (uint32_t)((cells + tile - 1) / tile);
+        const uint64_t tiles = (uint64_t)a.tiles_per_block * a.n_blocks;
+        if (tiles >= (1ull << 31)) return fail(CC_ERR_INVALID_ARGUMENT, "too many tiles in one launch");
+        if (sink == CC_SINK_CLASSIFY || sink == CC_SINK_MASS) {
+            int rc = ensure_status((size_t)tiles);
+            if (rc) return rc;
+            CU(cudaMemsetAsync(g.d_ticket, 0, 4, g.compute));
+            CU(cudaMemsetAsync(g.d_status, 0, (size_t)tiles * sizeof(unsigned long long), g.compute));
+            a.ticket = g.d_ticket;
+            a.tile_status = g.d_status;
+        }
+        int e = cc_jit_launch(prog, sink, a, g.compute);
+        if (e) return cuda_fail((cudaError_t)e, "specialised kernel launch");
+        g.launches += 1;
+        g.points += points;
+        return CC_OK;
+    }
     cc_launch_cfg cfg;
     int rc = choose_cfg(prog, points, &cfg);
     if (rc) return rc;
@@ -317,6 +338,7 @@ void cc_program_destroy(cc_program *prog)
     if (!prog) return;
     if (g.ready) {
         cudaStreamSynchronize(g.compute);
+        cc_jit_release(prog);
         cudaFree(prog->d_code);
         if (g.constant_program == prog->id) g.constant_program = 0;
     }
@@ -350,6 +372,47 @@ int cc_program_decode(const float *words, uint32_t n_words, cc_program_info *inf
     uint32_t n = (uint32_t)dec.microcode.size();
     if (out) std::memcpy(out, dec.microcode.data(), (size_t)std::min(n, capacity) * 4);
     return (int)n;
+}
+
+int cc_program_specialize(cc_program *prog, int points_per_thread, unsigned sink_mask, double *compile_seconds)
+{
+    NEED_INIT();
+    if (!prog) return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
+    CU(cudaStreamSynchronize(g.compute));
+    std::string err;
+    int rc = cc_jit_compile(prog, points_per_thread, sink_mask, compile_seconds, &err);
+    if (rc) return fail(rc, err);
+    return CC_OK;
+}
+
+int cc_program_use_specialized(cc_program *prog, int enable)
+{
+    if (!prog) return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
+    prog->use_jit = enable != 0 && prog->jit_library != nullptr;
+    return prog->use_jit ? 1 : 0;
+}
+
+int cc_specialize_source(const float *words, uint32_t n_words, int points_per_thread, unsigned sink_mask,
+                         char *out, uint32_t capacity, int compile, uint64_t *cubin_bytes)
+{
+    if (!words) return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
+    cc_decoded dec;
+    std::string err, src;
+    int rc = cc_decode_program(words, n_words, &dec, &err);
+    if (rc == CC_OK) rc = cc_jit_source(dec, points_per_thread, sink_mask, &src, &err);
+    if (rc != CC_OK) return fail(rc, err);
+    if (out && capacity) {
+        size_t n = std::min<size_t>(src.size(), capacity - 1);
+        std::memcpy(out, src.data(), n);
+        out[n] = 0;
+    }
+    if (compile) {
+        std::vector<char> cubin;
+        rc = cc_jit_nvrtc(src, &cubin, &err);
+        if (rc != CC_OK) return fail(rc, err);
+        if (cubin_bytes) *cubin_bytes = cubin.size();
+    }
+    return (int)src.size();
 }
 
 // ---- buffers / events ---------------------------------------------------------------------------------

@@ -1,0 +1,203 @@
+// The part of the evaluation kernels that does not depend on HOW a point is evaluated:
+// tile -> cell indices -> grid coordinates, then one of the four sinks (dense float4 store,
+// PyMCubes store, ordered classification list, mass-property sums + list).  Shared by the
+// microcode interpreter (cc_kernels.cu) and the NVRTC scene-specialised kernels (cc_jit.cpp),
+// so that both produce bit-identical coordinates, layouts and list orders.
+#ifndef CC_BODY_CUH
+#define CC_BODY_CUH
+
+#include "cc_device_types.h"
+#include "cc_math.cuh"
+
+// ---- ordered compaction: warp-ballot scan inside the CTA + decoupled look-back across CTAs ----
+// tile_status word = (state << 62) | value, state 1 = tile aggregate, 2 = inclusive prefix.
+#define CC_ST_AGG 1ull
+#define CC_ST_INC 2ull
+
+CC_DEV unsigned long long cc_ld_status(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+CC_DEV void cc_st_status(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Returns the exclusive prefix (number of hits in all earlier tiles, plus the list's initial
+// length) for this tile.  Called by warp 0 only; `tile` is the ticket-ordered tile id.
+CC_DEV uint32_t cc_lookback(unsigned long long *status, uint32_t tile, uint32_t aggregate,
+                            const uint32_t *counter)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    if (tile == 0) {
+        uint32_t base = *counter;  // list[atomic_inc(counter)]: continue after existing entries
+        if (lane == 0) cc_st_status(status, (CC_ST_INC << 62) | (unsigned long long)(base + aggregate));
+        return base;
+    }
+    if (lane == 0) cc_st_status(status + tile, (CC_ST_AGG << 62) | (unsigned long long)aggregate);
+    uint32_t exclusive = 0;
+    int look = (int)tile - 1;  // lanes inspect tiles look - lane
+    for (;;) {
+        int t = look - (int)lane;
+        unsigned long long s = (t >= 0) ? cc_ld_status(status + t) : ((CC_ST_INC << 62));
+        uint32_t state = (uint32_t)(s >> 62);
+        // all inspected predecessors must be published before we can use the window
+        if (__any_sync(0xffffffffu, state == 0)) continue;
+        uint32_t inc_mask = __ballot_sync(0xffffffffu, state == CC_ST_INC);
+        uint32_t val = (uint32_t)s;
+        if (inc_mask) {
+            int first = __ffs(inc_mask) - 1;  // nearest tile with an inclusive prefix
+            uint32_t contrib = (lane <= (uint32_t)first) ? val : 0u;
+            exclusive += __reduce_add_sync(0xffffffffu, contrib);
+            break;
+        }
+        exclusive += __reduce_add_sync(0xffffffffu, val);
+        look -= 32;
+    }
+    if (lane == 0)
+        cc_st_status(status + tile, (CC_ST_INC << 62) | (unsigned long long)(exclusive + aggregate));
+    return exclusive;
+}
+
+
+// EVAL: functor  void operator()(const float (&gx)[PTS], const float (&gy)[PTS],
+//                                const float (&gz)[PTS], float4 (&L)[PTS])
+template <int PTS, int SINK, class EVAL>
+CC_DEV void cc_kernel_body(const cc_eval_args &a, EVAL &eval)
+{
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_warp[PTS * (CC_THREADS / 32)];
+    __shared__ uint32_t s_base;
+
+    const uint32_t tid = threadIdx.x;
+    constexpr bool ORDERED = (SINK == CC_SINK_CLASSIFY || SINK == CC_SINK_MASS);
+    // tile id: launch order for pure stores; ticket order where tiles wait on predecessors
+    uint32_t tile = blockIdx.x;
+    if (ORDERED) {
+        if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
+        __syncthreads();
+        tile = s_tile;
+    }
+    const uint32_t block = tile / a.tiles_per_block;
+    const uint32_t tile_in_block = tile - block * a.tiles_per_block;
+    float cx = a.cx, cy = a.cy, cz = a.cz;
+    if (a.blocks) {
+        const cc_block_desc bd = a.blocks[block];
+        cx = bd.cx; cy = bd.cy; cz = bd.cz;
+    }
+    const uint32_t cells = a.nx * a.ny * a.nz;  // <= 2^31 per launch (host checks)
+    const uint32_t nyz = a.ny * a.nz;
+
+    float gx[PTS], gy[PTS], gz[PTS];
+    uint32_t ix[PTS], iy[PTS], iz[PTS];
+    bool valid[PTS];
+#pragma unroll
+    for (int j = 0; j < PTS; ++j) {
+        uint32_t c = tile_in_block * (CC_THREADS * PTS) + j * CC_THREADS + tid;
+        valid[j] = c < cells;
+        c = valid[j] ? c : 0u;
+        ix[j] = c / nyz;
+        uint32_t r = c - ix[j] * nyz;
+        iy[j] = r / a.nz;
+        iz[j] = r - iy[j] * a.nz;
+        // grid_eval.cl:13,31: corner + step * convert_float(id), one FMA per axis
+        gx[j] = cc_fma(a.step, (float)(ix[j] + a.x_offset), cx);
+        gy[j] = cc_fma(a.step, (float)iy[j], cy);
+        gz[j] = cc_fma(a.step, (float)iz[j], cz);
+    }
+
+    float4 L[PTS];
+    eval(gx, gy, gz, L);
+
+    if (SINK == CC_SINK_FLOAT4) {
+        float4 *out = reinterpret_cast<float4 *>(a.out) + (size_t)block * cells;
+#pragma unroll
+        for (int j = 0; j < PTS; ++j) {
+            uint32_t c = tile_in_block * (CC_THREADS * PTS) + j * CC_THREADS + tid;
+            if (valid[j]) __stcs(out + c, L[j]);  // INDEX3: z + nz*(y + ny*x) == linear cell index
+        }
+    } else if (SINK == CC_SINK_PYMCUBES) {
+        float *out = reinterpret_cast<float *>(a.out) + (size_t)block * cells;
+#pragma unroll
+        for (int j = 0; j < PTS; ++j) {
+            // grid_eval.cl:18: z + (x + (ny - y - 1) * nx) * nz
+            size_t idx = (size_t)iz[j] + ((size_t)ix[j] + (size_t)(a.ny - iy[j] - 1) * a.nx) * a.nz;
+            if (valid[j]) __stcs(out + idx, L[j].w);
+        }
+    } else {
+        // ---- classification ----
+        const uint32_t lane = tid & 31, warp = tid >> 5;
+        bool hit[PTS];
+        uint32_t sum[10];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) sum[i] = 0;
+#pragma unroll
+        for (int j = 0; j < PTS; ++j) {
+            const float v = L[j].w;
+            if (SINK == CC_SINK_CLASSIFY) {
+                hit[j] = valid[j] && (v > -a.threshold && v < a.threshold);  // subdivision.cl:25
+            } else {
+                const bool inside = valid[j] && (v <= -a.threshold);  // mass_properties.cl:31
+                hit[j] = valid[j] && !inside && (v < a.threshold);    // mass_properties.cl:43
+                if (inside) {
+                    // mass_properties.cl:34-41, order xx,xy,xz,x,yy,yz,y,zz,z,n
+                    const uint32_t x = ix[j], y = iy[j], z = iz[j];
+                    sum[0] += x * x; sum[1] += x * y; sum[2] += x * z; sum[3] += x;
+                    sum[4] += y * y; sum[5] += y * z; sum[6] += y; sum[7] += z * z;
+                    sum[8] += z; sum[9] += 1u;
+                }
+            }
+        }
+        if (SINK == CC_SINK_MASS) {
+            // hierarchical reduction: REDUX across the warp, one atomic per warp and moment
+            uint32_t *dst = a.sums + (a.blocks ? (size_t)block * 10 : 0);
+#pragma unroll
+            for (int i = 0; i < 10; ++i) {
+                uint32_t w = __reduce_add_sync(0xffffffffu, sum[i]);
+                if (lane == 0 && w) atomicAdd(dst + i, w);
+            }
+        }
+        // ranks inside the tile, in cell order (j major, then warp, then lane)
+        uint32_t ballot[PTS];
+#pragma unroll
+        for (int j = 0; j < PTS; ++j) {
+            ballot[j] = __ballot_sync(0xffffffffu, hit[j]);
+            if (lane == 0) s_warp[j * (CC_THREADS / 32) + warp] = __popc(ballot[j]);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // exclusive scan of the PTS * 4 warp counts (<= 32 entries) with shuffles
+            constexpr int NW = PTS * (CC_THREADS / 32);
+            uint32_t v = (lane < NW) ? s_warp[lane] : 0u;
+            uint32_t incl = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            if (lane < NW) s_warp[lane] = incl - v;
+            uint32_t base = cc_lookback(a.tile_status, tile, total, a.counter);
+            if (lane == 0) {
+                s_base = base;
+                if (tile == gridDim.x - 1) *a.counter = base + total;  // final list length
+            }
+        }
+        __syncthreads();
+        const uint32_t base = s_base;
+#pragma unroll
+        for (int j = 0; j < PTS; ++j) {
+            if (hit[j]) {
+                uint32_t pos = base + s_warp[j * (CC_THREADS / 32) + warp] + __popc(ballot[j] & ((1u << lane) - 1u));
+                reinterpret_cast<uchar4 *>(a.list)[pos] =
+                    make_uchar4((unsigned char)ix[j], (unsigned char)iy[j], (unsigned char)iz[j], 0);
+                if (a.list_block) a.list_block[pos] = block;
+            }
+        }
+    }
+}
+
+
+#endif

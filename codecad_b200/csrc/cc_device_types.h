@@ -1,0 +1,48 @@
+// Plain-old-data types shared by host code, the precompiled kernels and the NVRTC-compiled
+// scene-specialised kernels (no standard headers: this file is also fed to NVRTC).
+#ifndef CC_DEVICE_TYPES_H
+#define CC_DEVICE_TYPES_H
+
+#ifdef __CUDACC_RTC__
+typedef unsigned char uint8_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+typedef unsigned long size_t;
+#else
+#include <stddef.h>
+#include <stdint.h>
+#endif
+
+#define CC_THREADS 128
+
+enum cc_sink_kind { CC_SINK_FLOAT4 = 0, CC_SINK_PYMCUBES, CC_SINK_CLASSIFY, CC_SINK_MASS };
+
+struct cc_block_desc {  // one block of a subdivision level (device resident)
+    float cx, cy, cz;   // fp32 corner of the first sample (cell centre), reference rounding
+    uint32_t pad;
+};
+
+struct cc_eval_args {
+    const uint32_t *code;
+    uint32_t code_words;
+    uint32_t n_slots;
+    // geometry: single grid (blocks == nullptr) or a list of equally sized blocks
+    float cx, cy, cz, step;
+    uint32_t nx, ny, nz, x_offset;
+    uint32_t n_blocks;
+    uint32_t tiles_per_block;
+    const cc_block_desc *blocks;
+    // sinks
+    void *out;            // float4* / float*            (FLOAT4, PYMCUBES)
+    float threshold;      // CLASSIFY, MASS
+    uint32_t *counter;    // running length of `list`   (CLASSIFY, MASS)
+    uint8_t *list;        // uchar4 (x,y,z,0) per hit
+    uint32_t *list_block; // optional: block index of every hit (hierarchy fast path)
+    uint32_t *sums;       // MASS: 10 uint32 per block (stride 10), or one set when blocks == nullptr
+    // decoupled look-back scratch (ordered compaction)
+    uint32_t *ticket;
+    unsigned long long *tile_status;
+};
+
+#endif

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../include/codecad_b200.h"
+#include "cc_device_types.h"
 #include "cc_microcode.h"
 
 struct cc_decoded {
@@ -19,40 +20,26 @@ int cc_decode_program(const float *words, uint32_t n_words, cc_decoded *out, std
 
 struct cc_program {
     cc_decoded dec;
-    uint32_t *d_code;  // device copy of the microcode
-    uint64_t id;       // identifies what is currently loaded in the __constant__ window
+    uint32_t *d_code = nullptr;  // device copy of the microcode
+    uint64_t id = 0;             // identifies what is currently loaded in the __constant__ window
+    // scene-specialised kernels (cc_jit.cpp), one per sink; null until cc_program_specialize()
+    void *jit_library = nullptr;
+    void *jit_kernel[4] = {nullptr, nullptr, nullptr, nullptr};
+    int jit_pts = 0;
+    size_t jit_cubin_bytes = 0;
+    bool use_jit = false;
 };
+
+// cc_jit.cpp
+int cc_jit_source(const cc_decoded &dec, int pts, unsigned sink_mask, std::string *src, std::string *err);
+int cc_jit_nvrtc(const std::string &src, std::vector<char> *cubin, std::string *err);
+int cc_jit_compile(cc_program *prog, int pts, unsigned sink_mask, double *seconds, std::string *err);
+void cc_jit_release(cc_program *prog);
+int cc_jit_launch(const cc_program *prog, int sink, const cc_eval_args &a, void *stream);
 
 // ---- kernel launch layer (cc_kernels.cu) ------------------------------------------------
 
-enum cc_sink_kind { CC_SINK_FLOAT4 = 0, CC_SINK_PYMCUBES, CC_SINK_CLASSIFY, CC_SINK_MASS };
-
-struct cc_block_desc {  // one block of a subdivision level (device resident)
-    float cx, cy, cz;   // fp32 corner of the first sample (cell centre), reference rounding
-    uint32_t pad;
-};
-
-struct cc_eval_args {
-    const uint32_t *code;
-    uint32_t code_words;
-    uint32_t n_slots;
-    // geometry: single grid (blocks == nullptr) or a list of equally sized blocks
-    float cx, cy, cz, step;
-    uint32_t nx, ny, nz, x_offset;
-    uint32_t n_blocks;
-    uint32_t tiles_per_block;
-    const cc_block_desc *blocks;
-    // sinks
-    void *out;            // float4* / float*            (FLOAT4, PYMCUBES)
-    float threshold;      // CLASSIFY, MASS
-    uint32_t *counter;    // running length of `list`   (CLASSIFY, MASS)
-    uint8_t *list;        // uchar4 (x,y,z,0) per hit, or with `list_block` the hierarchy form
-    uint32_t *list_block; // optional: block index of every hit (hierarchy fast path)
-    uint32_t *sums;       // MASS: 10 uint32 per block (stride 10), or one set when blocks == nullptr
-    // decoupled look-back scratch (ordered compaction)
-    uint32_t *ticket;
-    unsigned long long *tile_status;
-};
+#include "cc_device_types.h"
 
 struct cc_launch_cfg {
     int pts;         // points per thread: 1, 2, 4

@@ -357,4 +357,72 @@ CC_DEV float4 cc_revolution_from(float4 flat, float4 co)
     return make_float4(cx * mult, flat.y, co.z * mult, flat.w);
 }
 
+// Fused primitive (loader pattern initial_transformation_to -> [store p] -> circle|rectangle ->
+// extrusion p -> [offset] -> [transformation_from]); bit-identical to the unfused sequence.
+template <bool RECT, int PTS>
+CC_DEV void cc_prim_n(const float (&m)[12], const float (&mf)[12], float pa, float pb, float h, float d,
+                      const float (&x)[PTS], const float (&y)[PTS], const float (&z)[PTS], float4 (&L)[PTS])
+{
+    float pz[PTS];
+#pragma unroll
+    for (int j = 0; j < PTS; ++j) {
+        L[j] = cc_transform(m, x[j], y[j], z[j]);
+        pz[j] = L[j].z;
+    }
+    if (RECT) cc_rectangle_n<PTS>(pa, pb, L);
+    else cc_circle_n<PTS>(pa, L);
+    cc_extrusion_n<PTS>(h, L, pz);
+#pragma unroll
+    for (int j = 0; j < PTS; ++j) {
+        L[j].w = L[j].w - d;
+        L[j] = cc_transform_from(mf, L[j]);
+    }
+}
+
+// shapes/polygons2d.cl:1-74 over a precomputed edge table (px, py, dx, dy, 1/|d|^2, cy) per
+// edge; FETCH(i) returns table word i (the interpreter reads it from the microcode, the
+// specialised kernels from a __constant__ array).
+template <class FETCH>
+CC_DEV float4 cc_polygon2d_core(const FETCH &fetch, uint32_t n, float4 co)
+{
+    float nnx = 0.0f, nny = 0.0f, nearest = __int_as_float(0x7f800000), outside = 1.0f;
+    bool nearest_is_vertex = false;
+    uint32_t e = 0;
+    for (uint32_t i = 0; i < n; ++i, e += 6) {
+        float px = fetch(e), py = fetch(e + 1), dx = fetch(e + 2), dy = fetch(e + 3), inv = fetch(e + 4),
+              cy = fetch(e + 5);
+        float tqx = co.x - px, tqy = co.y - py;
+        float snx = -dy, sny = dx;
+        if (((py < co.y) != (cy < co.y)) && (dy * cc_fma(snx, tqx, sny * tqy) > 0.0f)) outside = -outside;
+        float t = cc_fma(dx, tqx, dy * tqy) * inv;
+        if (t > 1.0f) continue;
+        float cnx, cny, cd;
+        bool civ;
+        if (t >= 0.0f) {
+            float tcx = cc_fma(-t, dx, tqx), tcy = cc_fma(-t, dy, tqy);
+            cd = cc_fma(tcx, tcx, tcy * tcy);
+            cnx = snx; cny = sny; civ = false;
+        } else {
+            cnx = tqx; cny = tqy;
+            cd = cc_fma(cnx, cnx, cny * cny);
+            civ = cd > 1.1920928955078125e-7f;
+            if (!civ) { cnx = snx; cny = sny; }
+        }
+        if (cd < nearest) { nearest = cd; nnx = cnx; nny = cny; nearest_is_vertex = civ; }
+    }
+    float distance = outside * cc_sqrt(nearest);
+    float inv = nearest_is_vertex ? cc_rcp(distance) : cc_rcp(cc_len2(nnx, nny));
+    return make_float4(nnx * inv, nny * inv, 0.0f, distance);
+}
+
+struct cc_table_fetch {
+    const float *t;
+    CC_DEV float operator()(uint32_t i) const { return t[i]; }
+};
+__device__ __noinline__ float4 cc_polygon2d_table(const float *table, uint32_t n, float4 co)
+{
+    return cc_polygon2d_core(cc_table_fetch{table}, n, co);
+}
+
+
 #endif

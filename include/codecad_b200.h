@@ -87,6 +87,26 @@ int cc_program_get_microcode(const cc_program *prog, uint32_t *out, uint32_t cap
 int cc_program_decode(const float *words, uint32_t n_words, cc_program_info *info,
                       uint32_t *out, uint32_t capacity);
 
+/* ---- scene-specialised kernels (optional accelerator) -------------
+ * cc_program_specialize() turns the program's microcode into straight-line CUDA C++ that calls
+ * the same op library, compiles it with NVRTC for sm_100a (-fmad=false) and loads it; afterwards
+ * every kernel launched for this program uses the specialised code (bit-identical results, no
+ * instruction fetch/dispatch).  Costs seconds of compile time, so it is opt-in; without NVRTC it
+ * fails and the interpreter stays in use.  points_per_thread: 1, 2 or 4 (0 = default 2);
+ * sink_mask: which kernels to build, bit k = sink k (1 float4 grid, 2 PyMCubes grid,
+ * 4 subdivision_step, 8 mass_properties; 0 = all four) — each costs its own compile time,
+ * sinks left out keep using the interpreter.
+ * The reference can emit a straight-line C evaluator too: nodes/codegen.py:137-204. */
+int cc_program_specialize(cc_program *prog, int points_per_thread, unsigned sink_mask,
+                          double *compile_seconds);
+int cc_program_use_specialized(cc_program *prog, int enable); /* returns 1 if specialised code is active */
+/* Host-only (no device): generate the source for `words` (returns its length, copies up to
+ * `capacity` bytes incl. NUL), and optionally run NVRTC on it (compile != 0; returns the cubin
+ * size through *cubin_bytes).  For tests and inspection. */
+int cc_specialize_source(const float *words, uint32_t n_words, int points_per_thread,
+                         unsigned sink_mask, char *out, uint32_t capacity, int compile,
+                         uint64_t *cubin_bytes);
+
 /* ---- buffers and events: replaces cl_util.Buffer  cl_util/cl_buffer.py:9-131 ---------- */
 int cc_buffer_alloc(size_t bytes, void **dptr);
 int cc_buffer_free(void *dptr);

@@ -217,3 +217,49 @@ def test_mass_properties_known_answers(cb, scenes, name):
     assert tuple(got.centroid) == pytest.approx(centroid, abs=1e-4, rel=precision)
     if inertia is not None:
         assert np.allclose(got.inertia_tensor, inertia, rtol=precision)
+
+
+# ---- scene-specialised (NVRTC) kernels: same op library, same body -> same bits -----------------
+
+JIT_SCENES = ["cfg_csg_example", "cfg_menger_sponge", "cfg_airfoil", "cfg_planetary", "cfg_synthetic32",
+              "dsdf3d_extreme_twisted_revolve", "dsdf2d_gear", "dsdf2d_regular_polygon3", "dsdf3d_rotated_pattern_3d",
+              "dsdf3d_revolved_pentagon", "x_repetition", "x_smooth_isect", "dsdf2d_polygon2d_non_convex"]
+
+
+@pytest.mark.parametrize("pts", [1, 2])
+@pytest.mark.parametrize("name", JIT_SCENES)
+def test_specialized_grid_eval_bit_exact(cb, scenes, name, pts):
+    from codecad_b200.cl_util.buffer import ProgramBuffer
+    s = scenes[name]
+    prog = ProgramBuffer(s.words)
+    secs = prog.specialize(pts, ProgramBuffer.SINK_FLOAT4 | ProgramBuffer.SINK_PYMCUBES)
+    assert secs > 0 and prog.use_specialized(True)
+    dims = (16, 9, 37) if s.dimension == 3 else (33, 17, 2)
+    corner, step = s.grid(40)
+    want = oracle.grid_eval(s.words, corner, step, dims)
+    got = _f4(cb.grid_eval(prog, corner, step, dims))
+    assert _same(got, want)
+    assert _same(cb.grid_eval_pymcubes(prog, corner, step, dims), oracle.grid_eval_pymcubes(s.words, corner, step, dims))
+    # switching back to the interpreter gives the same bits again
+    assert not prog.use_specialized(False)
+    assert _same(_f4(cb.grid_eval(prog, corner, step, dims)), want)
+
+
+@pytest.mark.parametrize("name", ["cfg_airfoil", "cfg_csg_example", "cfg_planetary"])
+def test_specialized_hierarchy_matches_oracle(cb, scenes, name):
+    """subdivision() and mass_properties() through specialised classify / mass kernels."""
+    from oracle import host
+    from codecad_b200.cl_util.buffer import ProgramBuffer
+    from codecad_b200 import CompiledScene
+    s = scenes[name]
+    scene = s.compiled()
+    scene._buffer = ProgramBuffer(s.words)
+    scene._buffer.specialize(2, ProgramBuffer.SINK_CLASSIFY | ProgramBuffer.SINK_MASS)
+    res = {"cfg_airfoil": 1.0, "cfg_csg_example": 1.0, "cfg_planetary": 0.8}[name]
+    w_vol, w_cen, w_inertia = host.mass_properties(s.words, s.box_a, s.box_b, res, 32)
+    got = cb.mass_properties(scene, res, 32)
+    assert got.volume == pytest.approx(w_vol, rel=1e-12)
+    assert np.allclose(got.inertia_tensor, w_inertia, rtol=1e-9, atol=1e-9 * np.abs(w_inertia).max())
+    _, want = host.subdivision(s.words, s.box_a, s.box_b, s.dimension, res, True, 8)
+    got_blocks = cb.subdivision(scene, res, True, 8)[2]
+    assert sorted(tuple(b[3]) for b in got_blocks) == sorted(tuple(b[3]) for b in want)

@@ -60,6 +60,30 @@ def main():
             pts_s = nx * n * n / (best * 1e-3)
             print("   pts=%d space=%s: %8.3f ms  %8.3f Gpts/s  fp32 frac(min flops) %.3f  store GB/s %.0f" % (
                 pts, {1: "const", 2: "smem", 3: "hybrid"}[space], best, pts_s / 1e9, pts_s * pi.flops_min / peak, pts_s * 16 / 1e9))
+        # scene-specialised kernel (NVRTC)
+        if os.environ.get("PROBE_JIT", "1") != "0":
+            for jp in (2, 1):
+                _lib.check(L.cc_set_tuning(0, 0))
+                try:
+                    secs = prog.specialize(jp, 1)
+                except Exception as exc:  # noqa: BLE001
+                    print("   jit pts=%d: %s" % (jp, str(exc)[:300]))
+                    break
+                best = None
+                for it in range(3):
+                    e0, e1 = ctypes.c_void_p(), ctypes.c_void_p()
+                    _lib.check(L.cc_event_record(ctypes.byref(e0)))
+                    _lib.check(L.cc_grid_eval(prog.handle, _lib.f3(corner), float(step), nx, n, n, 0, 0, out.device_ptr, None))
+                    _lib.check(L.cc_event_record(ctypes.byref(e1)))
+                    _lib.check(L.cc_event_wait(e1))
+                    ms = ctypes.c_float()
+                    _lib.check(L.cc_event_elapsed_ms(e0, e1, ctypes.byref(ms)))
+                    if it and (best is None or ms.value < best):
+                        best = ms.value
+                pts_s = nx * n * n / (best * 1e-3)
+                print("   JIT pts=%d (compile %.1f s): %8.3f ms  %8.3f Gpts/s  fp32 frac(min flops) %.3f" % (
+                    jp, secs, best, pts_s / 1e9, pts_s * pi.flops_min / peak))
+            prog.use_specialized(False)
     _lib.check(L.cc_set_tuning(0, 0))
 
 
