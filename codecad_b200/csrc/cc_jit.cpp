@@ -16,6 +16,7 @@
 
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <sstream>
@@ -250,9 +251,12 @@ int generate(const cc_decoded &dec, int pts, unsigned sink_mask, std::string *sr
     s << "        CC_EACH L[j] = make_float4(0.f, 0.f, 0.f, 0.f);\n" << o.str() << "    }\n};\n";
     const char *names[4] = {"float4", "pymcubes", "classify", "mass"};
     const char *sinks[4] = {"CC_SINK_FLOAT4", "CC_SINK_PYMCUBES", "CC_SINK_CLASSIFY", "CC_SINK_MASS"};
+    // optional occupancy hint (tuning experiments): CODECAD_B200_JIT_MINB = min CTAs per SM
+    std::string bounds = "CC_THREADS";
+    if (const char *mb = getenv("CODECAD_B200_JIT_MINB")) bounds += std::string(", ") + std::to_string(atoi(mb));
     for (int k = 0; k < 4; ++k)
         if (sink_mask & (1u << k))
-        s << "extern \"C\" __global__ void __launch_bounds__(CC_THREADS) cc_jit_" << names[k]
+        s << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_" << names[k]
           << "(const cc_eval_args a)\n{\n    SceneEval e;\n    cc_kernel_body<PTS, " << sinks[k] << ">(a, e);\n}\n";
     *src = s.str();
     return CC_OK;

@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""Launch the grid_eval kernel a few times for one scene (for ncu): scene n pts space [reps]"""
+"""Launch the grid_eval kernel a few times for one scene (for ncu):
+   scene n pts space [reps] [jit_pts]      (jit_pts > 0: scene-specialised kernel)"""
 import os
 import sys
 
@@ -13,9 +14,12 @@ from scenes import load_scenes  # noqa: E402
 
 name, n, pts, space = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
 reps = int(sys.argv[5]) if len(sys.argv) > 5 else 3
+jit = int(sys.argv[6]) if len(sys.argv) > 6 else 0
 L = _lib.init(0)
 s = load_scenes()[name]
 prog = s.compiled().program_buffer()
+if jit:
+    print("compile %.2f s" % prog.specialize(jit, 1))
 corner, step = s.grid(n)
 out = Buffer(FLOAT4, (n, n, n))
 _lib.check(L.cc_set_tuning(pts, space))
