@@ -251,6 +251,11 @@ def run_ours(args):
     pinfo = prog.info
     out = Buffer(FLOAT4, (nx, n, n))   # slab output stays resident in HBM
     c3 = _lib.f3(corner)
+    # Tiered execution is the library default: the interpreter serves launches while the
+    # scene-specialised kernel compiles in the background.  The headline is measured in steady
+    # state, i.e. after the switch; the interpreter tier is timed separately below.
+    n_ready, specialize_s = prog.wait_specialized(ProgramBuffer.SINK_FLOAT4)
+    tier = "specialised" if n_ready else "interpreter"
 
     def kernel_step():
         _lib.check(L.cc_grid_eval(prog.handle, c3, float(step), nx, n, n, x0, 0, out.device_ptr, None))
@@ -287,6 +292,20 @@ def run_ours(args):
     total_points = float(n) ** 3
     value = total_points / (ms_step * 1e-3) / 1e9
     launches_total = int(sum_over_ranks(torch, dist, float(launches)))
+
+    # ---- the interpreter tier alone (what runs before the specialised kernel is ready) ----
+    interp = None
+    if n_ready:
+        prog.use_specialized(False)
+        kernel_step()
+        _lib.check(L.cc_synchronize())
+        barrier(torch, dist)
+        i_steps = max(1, min(args.steps, 2))
+        i_ms = max_over_ranks(torch, dist, timed(kernel_step, i_steps)) / i_steps
+        barrier(torch, dist)
+        prog.use_specialized(True)
+        interp = {"value": total_points / (i_ms * 1e-3) / 1e9, "unit": "Gpts/s", "ms_per_step": i_ms,
+                  "steps": i_steps, "kernel": "cc_eval_kernel<PTS,const,FLOAT4>"}
 
     # ---- end to end: fresh program upload + result into pinned host memory ----
     e2e = None
@@ -329,11 +348,13 @@ def run_ours(args):
     flops_pt = int(pinfo.flops_min)
     # per launch (= per rank-step): this rank's points / its kernel time; ranks are symmetric
     achieved = (total_points / world) * flops_pt / (ms_step * 1e-3) / 1e12
+    if interp:
+        interp["roofline_frac"] = (total_points / world) * flops_pt / (interp["ms_per_step"] * 1e-3) / 1e12 / peak_tflops
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "bench_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(str(n))
+            traffic = json.load(open(tpath)).get("%s_%d" % (tier, n))
         except Exception:  # noqa: BLE001
             traffic = None
     peaks = {}
@@ -345,7 +366,7 @@ def run_ours(args):
     roofline = {
         "bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
         "frac": achieved / peak_tflops, "traffic": traffic,
-        "kernel": "cc_eval_kernel<PTS,const,FLOAT4>",
+        "kernel": "cc_jit_float4 (scene-specialised, packed FFMA2 lanes)" if n_ready else "cc_eval_kernel<PTS,const,FLOAT4>",
         "flop_per_point": flops_pt,
         "peak_source": "derived: %d SMs x 128 FP32 lanes x 2 x %.0f MHz (no FP32 figure in MEASURED_PEAKS.json)"
                        % (info.sm_count, sm_max_mhz),
@@ -368,6 +389,7 @@ def run_ours(args):
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(n, world), "clocks": clk, "e2e": e2e,
         "gpu_launches": launches_total, "roofline": roofline, "cpu_baseline": cpu,
+        "tier": tier, "specialize_s": specialize_s, "interpreter_tier": interp,
         "device": info.name.decode(),
     }
     print(json.dumps(line))

@@ -62,6 +62,8 @@ SIGNATURES = {
     "cc_program_decode": (_I, [c_float_p, _U, ctypes.POINTER(ProgramInfo), c_u32_p, _U]),
     "cc_program_specialize": (_I, [_V, _I, _U, ctypes.POINTER(ctypes.c_double)]),
     "cc_program_use_specialized": (_I, [_V, _I]),
+    "cc_set_jit_mode": (_I, [_I]),
+    "cc_program_specialize_wait": (_I, [_V, _U, ctypes.POINTER(ctypes.c_double)]),
     "cc_specialize_source": (_I, [c_float_p, _U, _I, _U, ctypes.c_char_p, _U, _I, ctypes.POINTER(ctypes.c_uint64)]),
     "cc_buffer_alloc": (_I, [ctypes.c_size_t, c_void_pp]),
     "cc_buffer_free": (_I, [_V]),

@@ -185,6 +185,13 @@ class ProgramBuffer:
     def use_specialized(self, enable=True):
         return bool(_lib.lib().cc_program_use_specialized(self.handle, 1 if enable else 0))
 
+    def wait_specialized(self, sinks=0):
+        """Block until the background-compiled specialised kernels of `sinks` are loaded (starting
+        the compilation if needed).  Returns (number of sinks ready, compile seconds so far)."""
+        secs = ctypes.c_double()
+        n = _lib.check(_lib.lib().cc_program_specialize_wait(self.handle, int(sinks), ctypes.byref(secs)))
+        return n, secs.value
+
     def microcode(self):
         n = _lib.lib().cc_program_get_microcode(self.handle, None, 0)
         out = np.zeros(n, np.uint32)

@@ -29,6 +29,8 @@ struct Context {
     cudaStream_t compute = nullptr, copy = nullptr;
     uint64_t launches = 0, points = 0;
     int pts = 0, prog_space = 0;  // tuning overrides, 0 = auto
+    int jit_mode = 1;             // 0 never, 1 background (default), 2 compile at first use and wait
+    uint32_t jit_max_ops = 512;   // programs longer than this are not specialised automatically
     uint64_t next_program_id = 1;
     uint64_t constant_program = 0;  // id of the program in the __constant__ window
     // look-back scratch
@@ -157,11 +159,29 @@ int check_dims(uint32_t nx, uint32_t ny, uint32_t nz)
     return CC_OK;
 }
 
+// Tiered execution: a program starts on the interpreter; its scene-specialised kernel for `sink`
+// is compiled on a background thread (NVRTC, cached in memory and on disk) and takes over as soon
+// as it is ready.  Both tiers produce identical bits (same op library, same -fmad=false contract).
+bool jit_ready(cc_program *p, int sink)
+{
+    if (!p->use_jit) return false;
+    if (p->jit_kernel[sink]) return true;
+    if (g.jit_mode == 0 || p->jit_failed[sink]) return false;
+    if (p->dec.info.n_micro_ops > g.jit_max_ops) return false;
+    cc_jit_start(p, sink);
+    std::string err;
+    int r = cc_jit_poll(p, sink, g.jit_mode == 2, &err);
+    if (r < 0)
+        std::fprintf(stderr, "libcodecad_b200: kernel specialisation failed, staying on the interpreter: %s\n",
+                     err.c_str());
+    return r == 1;
+}
+
 int launch(int sink, const cc_program *prog, cc_eval_args &a, uint64_t points)
 {
-    if (prog->use_jit && prog->jit_kernel[sink]) {
+    if (jit_ready(const_cast<cc_program *>(prog), sink)) {
         // scene-specialised kernel: slots are registers, parameters immediates
-        const uint32_t tile = (uint32_t)(CC_THREADS * prog->jit_pts);
+        const uint32_t tile = (uint32_t)(prog->jit_cfg[sink].threads * prog->jit_cfg[sink].pts);
         const uint64_t cells = (uint64_t)a.nx * a.ny * a.nz;
         a.tiles_per_block = (uint32_t)((cells + tile - 1) / tile);
         const uint64_t tiles = (uint64_t)a.tiles_per_block * a.n_blocks;
@@ -248,6 +268,10 @@ int cc_init(int device)
     if (p) g.pts = atoi(p);
     p = getenv("CODECAD_B200_PROG_SPACE");
     if (p) g.prog_space = atoi(p);
+    p = getenv("CODECAD_B200_JIT");
+    if (p) g.jit_mode = std::max(0, std::min(2, atoi(p)));
+    p = getenv("CODECAD_B200_JIT_MAX_OPS");
+    if (p) g.jit_max_ops = (uint32_t)atoi(p);
     return CC_OK;
 }
 
@@ -388,8 +412,36 @@ int cc_program_specialize(cc_program *prog, int points_per_thread, unsigned sink
 int cc_program_use_specialized(cc_program *prog, int enable)
 {
     if (!prog) return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
-    prog->use_jit = enable != 0 && prog->jit_library != nullptr;
-    return prog->use_jit ? 1 : 0;
+    prog->use_jit = enable != 0;
+    bool any = false;
+    for (int k = 0; k < 4; ++k) any = any || prog->jit_kernel[k] != nullptr;
+    return (prog->use_jit && any) ? 1 : 0;
+}
+
+int cc_set_jit_mode(int mode)
+{
+    const int old = g.jit_mode;
+    if (mode < 0 || mode > 2) return fail(CC_ERR_INVALID_ARGUMENT, "jit mode must be 0, 1 or 2");
+    g.jit_mode = mode;
+    return old;
+}
+
+int cc_program_specialize_wait(cc_program *prog, unsigned sink_mask, double *compile_seconds)
+{
+    NEED_INIT();
+    if (!prog) return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
+    if ((sink_mask & 15u) == 0) sink_mask = 15u;
+    int ready = 0;
+    for (int k = 0; k < 4; ++k) {
+        if (!(sink_mask & (1u << k))) continue;
+        cc_jit_start(prog, k);
+        std::string err;
+        int r = cc_jit_poll(prog, k, true, &err);
+        if (r < 0) return fail(r, err);
+        ready += r;
+    }
+    if (compile_seconds) *compile_seconds = prog->jit_seconds;
+    return ready;
 }
 
 int cc_specialize_source(const float *words, uint32_t n_words, int points_per_thread, unsigned sink_mask,

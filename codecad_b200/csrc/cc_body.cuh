@@ -62,8 +62,9 @@ CC_DEV uint32_t cc_lookback(unsigned long long *status, uint32_t tile, uint32_t 
 }
 
 
-// EVAL: functor  void operator()(const float (&gx)[PTS], const float (&gy)[PTS],
-//                                const float (&gz)[PTS], float4 (&L)[PTS])
+// EVAL: functor  void operator()(const V (&gx)[G], const V (&gy)[G], const V (&gz)[G], cc_val<V> (&L)[G])
+// with V, G = cc_pts<PTS> (cc_math.cuh): for PTS >= 2 the points j = 2g, 2g+1 are the two lanes
+// of packed vector g.
 template <int PTS, int SINK, class EVAL>
 CC_DEV void cc_kernel_body(const cc_eval_args &a, EVAL &eval)
 {
@@ -90,6 +91,8 @@ CC_DEV void cc_kernel_body(const cc_eval_args &a, EVAL &eval)
     const uint32_t cells = a.nx * a.ny * a.nz;  // <= 2^31 per launch (host checks)
     const uint32_t nyz = a.ny * a.nz;
 
+    typedef typename cc_pts<PTS>::V V;
+    constexpr int G = cc_pts<PTS>::G, NL = cc_lane<V>::N;
     float gx[PTS], gy[PTS], gz[PTS];
     uint32_t ix[PTS], iy[PTS], iz[PTS];
     bool valid[PTS];
@@ -109,7 +112,19 @@ CC_DEV void cc_kernel_body(const cc_eval_args &a, EVAL &eval)
     }
 
     float4 L[PTS];
-    eval(gx, gy, gz, L);
+    {
+        V vx[G], vy[G], vz[G];
+        cc_val<V> LV[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            vx[g] = cc_pack<V>(gx + g * NL);
+            vy[g] = cc_pack<V>(gy + g * NL);
+            vz[g] = cc_pack<V>(gz + g * NL);
+        }
+        eval(vx, vy, vz, LV);
+#pragma unroll
+        for (int j = 0; j < PTS; ++j) L[j] = cc_lane_get(LV[j / NL], j % NL);
+    }
 
     if (SINK == CC_SINK_FLOAT4) {
         float4 *out = reinterpret_cast<float4 *>(a.out) + (size_t)block * cells;
@@ -170,6 +185,7 @@ CC_DEV void cc_kernel_body(const cc_eval_args &a, EVAL &eval)
         if (warp == 0) {
             // exclusive scan of the PTS * 4 warp counts (<= 32 entries) with shuffles
             constexpr int NW = PTS * (CC_THREADS / 32);
+            static_assert(NW <= 32, "the warp-count scan covers at most 32 entries");
             uint32_t v = (lane < NW) ? s_warp[lane] : 0u;
             uint32_t incl = v;
 #pragma unroll

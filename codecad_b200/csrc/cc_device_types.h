@@ -14,7 +14,9 @@ typedef unsigned long size_t;
 #include <stdint.h>
 #endif
 
-#define CC_THREADS 128
+#ifndef CC_THREADS
+#define CC_THREADS 128  // CTA size of the precompiled kernels; specialised kernels may override it
+#endif
 
 enum cc_sink_kind { CC_SINK_FLOAT4 = 0, CC_SINK_PYMCUBES, CC_SINK_CLASSIFY, CC_SINK_MASS };
 

@@ -18,22 +18,35 @@ struct cc_decoded {
 // cc_program.cpp
 int cc_decode_program(const float *words, uint32_t n_words, cc_decoded *out, std::string *err);
 
+struct cc_jit_cfg {
+    int pts = 2;         // points per thread
+    int threads = 512;   // CTA size
+    int min_blocks = 2;  // __launch_bounds__ min CTAs per SM (register cap)
+};
+struct cc_jit_job;
+
 struct cc_program {
     cc_decoded dec;
     uint32_t *d_code = nullptr;  // device copy of the microcode
     uint64_t id = 0;             // identifies what is currently loaded in the __constant__ window
-    // scene-specialised kernels (cc_jit.cpp), one per sink; null until cc_program_specialize()
-    void *jit_library = nullptr;
+    // scene-specialised kernels (cc_jit.cpp), one library per sink; null until compiled
+    void *jit_library[4] = {nullptr, nullptr, nullptr, nullptr};
     void *jit_kernel[4] = {nullptr, nullptr, nullptr, nullptr};
-    int jit_pts = 0;
+    cc_jit_cfg jit_cfg[4];
+    cc_jit_job *jit_job[4] = {nullptr, nullptr, nullptr, nullptr};  // background compiles in flight
+    bool jit_failed[4] = {false, false, false, false};
     size_t jit_cubin_bytes = 0;
-    bool use_jit = false;
+    double jit_seconds = 0;  // background compile time spent so far
+    bool use_jit = true;     // per-program switch (cc_program_use_specialized)
 };
 
 // cc_jit.cpp
+cc_jit_cfg cc_jit_default_cfg(int pts);
 int cc_jit_source(const cc_decoded &dec, int pts, unsigned sink_mask, std::string *src, std::string *err);
 int cc_jit_nvrtc(const std::string &src, std::vector<char> *cubin, std::string *err);
 int cc_jit_compile(cc_program *prog, int pts, unsigned sink_mask, double *seconds, std::string *err);
+void cc_jit_start(cc_program *prog, int sink);
+int cc_jit_poll(cc_program *prog, int sink, bool wait, std::string *err);
 void cc_jit_release(cc_program *prog);
 int cc_jit_launch(const cc_program *prog, int sink, const cc_eval_args &a, void *stream);
 

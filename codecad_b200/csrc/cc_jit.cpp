@@ -14,13 +14,21 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "cc_internal.h"
@@ -134,8 +142,14 @@ struct Gen {
     static std::string S(uint32_t slot) { return "S" + std::to_string(slot); }
 };
 
-int generate(const cc_decoded &dec, int pts, unsigned sink_mask, std::string *src, std::string *err)
+int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, std::string *src, std::string *err)
 {
+    const int pts = cfg.pts;
+    // debugging aids: stop after N micro-ops (bisecting a mismatch), force scalar lanes
+    const char *stop_env = getenv("CODECAD_B200_JIT_STOP");
+    const int stop_after = stop_env ? atoi(stop_env) : -1;
+    const bool no_pack = getenv("CODECAD_B200_JIT_NOPACK") != nullptr;
+    int n_emitted = 0;
     Gen g(dec.microcode);
     const std::vector<uint32_t> &c = dec.microcode;
     std::ostringstream &o = g.body;
@@ -146,23 +160,23 @@ int generate(const cc_decoded &dec, int pts, unsigned sink_mask, std::string *sr
             return CC_ERR_INVALID_PROGRAM;
         }
         const uint32_t h = c[pc], op = CC_HDR_OP(h), src_slot = CC_HDR_SRC(h), dst = CC_HDR_DST(h);
-        const std::string B = Gen::S(src_slot) + "[j]";
+        const std::string B = Gen::S(src_slot) + "[g]";
         o << "        // pc " << pc << "\n";
         switch (op) {
         case MOP_RETURN: break;
         case MOP_NOP: break;
-        case MOP_LOAD: o << "        CC_EACH L[j] = " << B << ";\n"; break;
+        case MOP_LOAD: o << "        CC_EACH L[g] = " << B << ";\n"; break;
         case MOP_PRIM_CIRCLE:
         case MOP_PRIM_RECT:
             o << "        { const float m[12] = {" << g.args(pc, 1, 12) << "};\n"
               << "          const float mf[12] = {" << g.args(pc, 17, 10) << ", 0.f, 0.f};\n"
-              << "          cc_prim_n<" << (op == MOP_PRIM_RECT ? "true" : "false") << ", PTS>(m, mf, " << g.args(pc, 13, 4)
+              << "          cc_prim_n<" << (op == MOP_PRIM_RECT ? "true" : "false") << ", V, G>(m, mf, " << g.args(pc, 13, 4)
               << ", gx, gy, gz, L); }\n";
             break;
-        case MOP_RECTANGLE: o << "        cc_rectangle_n<PTS>(" << g.args(pc, 1, 2) << ", L);\n"; break;
-        case MOP_CIRCLE: o << "        cc_circle_n<PTS>(" << g.F(pc + 1) << ", L);\n"; break;
-        case MOP_SPHERE: o << "        cc_sphere_n<PTS>(" << g.F(pc + 1) << ", L);\n"; break;
-        case MOP_REGPOLY: o << "        CC_EACH L[j] = cc_regular_polygon2d(" << g.args(pc, 1, 5) << ", L[j]);\n"; break;
+        case MOP_RECTANGLE: o << "        cc_rectangle_n(" << g.args(pc, 1, 2) << ", L);\n"; break;
+        case MOP_CIRCLE: o << "        cc_circle_n(" << g.F(pc + 1) << ", L);\n"; break;
+        case MOP_SPHERE: o << "        cc_sphere_n(" << g.F(pc + 1) << ", L);\n"; break;
+        case MOP_REGPOLY: o << "        CC_EACH L[g] = cc_op_regpoly(" << g.args(pc, 1, 5) << ", L[g]);\n"; break;
         case MOP_POLYGON: {
             const uint32_t n = (uint32_t)(*reinterpret_cast<const float *>(&c[pc + 1]));
             const uint32_t off = c[pc + 2];
@@ -170,90 +184,76 @@ int generate(const cc_decoded &dec, int pts, unsigned sink_mask, std::string *sr
             g.consts << "__constant__ float cc_poly_" << k << "[" << 6 * n << "] = {";
             for (uint32_t i = 0; i < 6 * n; ++i) g.consts << (i ? ", " : "") << g.C(off + i);
             g.consts << "};\n";
-            o << "        CC_EACH L[j] = cc_polygon2d_table(cc_poly_" << k << ", " << n << "u, L[j]);\n";
+            o << "        CC_EACH L[g] = cc_op_polygon_table(cc_poly_" << k << ", " << n << "u, L[g]);\n";
             break;
         }
-        case MOP_HALF_SPACE: o << "        CC_EACH L[j] = make_float4(0.0f, -1.0f, 0.0f, -L[j].y);\n"; break;
-        case MOP_REV_TO:
-            o << "        CC_EACH L[j] = make_float4(cc_len2(L[j].x, L[j].z), L[j].y, 0.0f, 0.0f);\n";
-            break;
-        case MOP_TWIST_TO: o << "        CC_EACH L[j] = cc_twist_revolution_to(" << g.args(pc, 1, 2) << ", L[j]);\n"; break;
+        case MOP_HALF_SPACE: o << "        CC_EACH L[g] = cc_op_half_space(L[g]);\n"; break;
+        case MOP_REV_TO: o << "        CC_EACH L[g] = cc_op_rev_to(L[g]);\n"; break;
+        case MOP_TWIST_TO: o << "        CC_EACH L[g] = cc_op_twist_to(" << g.args(pc, 1, 2) << ", L[g]);\n"; break;
         case MOP_T_INIT:
             o << "        { const float m[12] = {" << g.args(pc, 1, 12) << "};\n"
-              << "          CC_EACH L[j] = cc_transform(m, gx[j], gy[j], gz[j]); }\n";
+              << "          CC_EACH L[g] = cc_transform(m, gx[g], gy[g], gz[g]); }\n";
             break;
         case MOP_T_TO:
             o << "        { const float m[12] = {" << g.args(pc, 1, 12) << "};\n"
-              << "          CC_EACH L[j] = cc_transform(m, L[j].x, L[j].y, L[j].z); }\n";
+              << "          CC_EACH L[g] = cc_transform(m, L[g].x, L[g].y, L[g].z); }\n";
             break;
         case MOP_T_FROM:
             o << "        { const float m[12] = {" << g.args(pc, 1, 10) << ", 0.f, 0.f};\n"
-              << "          CC_EACH L[j] = cc_transform_from(m, L[j]); }\n";
+              << "          CC_EACH L[g] = cc_transform_from(m, L[g]); }\n";
             break;
-        case MOP_MIRROR: o << "        CC_EACH L[j].x = -L[j].x;\n"; break;
-        case MOP_SYM_TO: o << "        CC_EACH L[j].x = fabsf(L[j].x);\n"; break;
-        case MOP_OFFSET: o << "        CC_EACH L[j].w = L[j].w - " << g.F(pc + 1) << ";\n"; break;
-        case MOP_SHELL:
-            o << "        CC_EACH { float4 s = (L[j].w >= 0.0f) ? L[j] : cc_neg4(L[j]); s.w = s.w - " << g.F(pc + 1)
-              << "; L[j] = s; }\n";
-            break;
-        case MOP_REPETITION:
-            o << "        CC_EACH L[j] = make_float4(cc_remainder(L[j].x, " << g.F(pc + 1) << "), cc_remainder(L[j].y, "
-              << g.F(pc + 2) << "), cc_remainder(L[j].z, " << g.F(pc + 3) << "), 0.0f);\n";
-            break;
-        case MOP_CREP_TO: o << "        CC_EACH L[j] = cc_circular_repetition_to(" << g.args(pc, 1, 2) << ", L[j]);\n"; break;
+        case MOP_MIRROR: o << "        CC_EACH L[g].x = vneg(L[g].x);\n"; break;
+        case MOP_SYM_TO: o << "        CC_EACH L[g].x = vabs(L[g].x);\n"; break;
+        case MOP_OFFSET: o << "        CC_EACH L[g].w = vsub(L[g].w, vbc<V>(" << g.F(pc + 1) << "));\n"; break;
+        case MOP_SHELL: o << "        CC_EACH L[g] = cc_op_shell(" << g.F(pc + 1) << ", L[g]);\n"; break;
+        case MOP_REPETITION: o << "        CC_EACH L[g] = cc_op_repetition(" << g.args(pc, 1, 3) << ", L[g]);\n"; break;
+        case MOP_CREP_TO: o << "        CC_EACH L[g] = cc_op_crep_to(" << g.args(pc, 1, 2) << ", L[g]);\n"; break;
         case MOP_CREP_FROM:
-            o << "        CC_EACH L[j] = cc_circular_repetition_from(" << g.args(pc, 1, 2) << ", L[j], " << B << ");\n";
+            o << "        CC_EACH L[g] = cc_op_crep_from(" << g.args(pc, 1, 2) << ", L[g], " << B << ");\n";
             break;
-        case MOP_GEAR: o << "        CC_EACH L[j] = cc_involute_gear(" << g.args(pc, 1, 5) << ", L[j]);\n"; break;
+        case MOP_GEAR: o << "        CC_EACH L[g] = cc_op_gear(" << g.args(pc, 1, 5) << ", L[g]);\n"; break;
         case MOP_EXTRUSION:
-            o << "        { float cz[PTS]; CC_EACH cz[j] = " << B << ".z; cc_extrusion_n<PTS>(" << g.F(pc + 1)
-              << ", L, cz); }\n";
+            o << "        { V cz[G]; CC_EACH cz[g] = " << B << ".z; cc_extrusion_n(" << g.F(pc + 1) << ", L, cz); }\n";
             break;
-        case MOP_REV_FROM: o << "        CC_EACH L[j] = cc_revolution_from(L[j], " << B << ");\n"; break;
+        case MOP_REV_FROM: o << "        CC_EACH L[g] = cc_revolution_from(L[g], " << B << ");\n"; break;
         case MOP_TWIST_FROM:
-            o << "        CC_EACH L[j] = cc_twist_revolution_from(" << g.args(pc, 1, 5) << ", L[j], " << B << ");\n";
+            o << "        CC_EACH L[g] = cc_op_twist_from(" << g.args(pc, 1, 5) << ", L[g], " << B << ");\n";
             break;
-        case MOP_SYM_FROM: o << "        CC_EACH L[j].x = (" << B << ".x < 0.0f) ? -L[j].x : L[j].x;\n"; break;
-        case MOP_UNION: o << "        CC_EACH { const float4 b = " << B << "; L[j] = (L[j].w < b.w) ? L[j] : b; }\n"; break;
-        case MOP_UNION_R: o << "        CC_EACH L[j] = cc_rounded_union(" << g.F(pc + 1) << ", L[j], " << B << ");\n"; break;
-        case MOP_ISECT:
-            o << "        CC_EACH { const float4 b = " << B << "; L[j] = (-L[j].w < -b.w) ? L[j] : b; }\n";
-            break;
-        case MOP_ISECT_R:
-            o << "        CC_EACH L[j] = cc_neg4(cc_rounded_union(" << g.F(pc + 1) << ", cc_neg4(L[j]), cc_neg4(" << B
-              << ")));\n";
-            break;
-        case MOP_SUB:
-            o << "        CC_EACH { const float4 b = " << B << "; L[j] = (-L[j].w < b.w) ? L[j] : cc_neg4(b); }\n";
-            break;
-        case MOP_SUB_R:
-            o << "        CC_EACH L[j] = cc_neg4(cc_rounded_union(" << g.F(pc + 1) << ", cc_neg4(L[j]), " << B << "));\n";
-            break;
+        case MOP_SYM_FROM: o << "        CC_EACH L[g] = cc_op_sym_from(L[g], " << B << ");\n"; break;
+        case MOP_UNION: o << "        CC_EACH L[g] = cc_op_union(L[g], " << B << ");\n"; break;
+        case MOP_UNION_R: o << "        CC_EACH L[g] = cc_rounded_union(" << g.F(pc + 1) << ", L[g], " << B << ");\n"; break;
+        case MOP_ISECT: o << "        CC_EACH L[g] = cc_op_isect(L[g], " << B << ");\n"; break;
+        case MOP_ISECT_R: o << "        CC_EACH L[g] = cc_op_isect_r(" << g.F(pc + 1) << ", L[g], " << B << ");\n"; break;
+        case MOP_SUB: o << "        CC_EACH L[g] = cc_op_sub(L[g], " << B << ");\n"; break;
+        case MOP_SUB_R: o << "        CC_EACH L[g] = cc_op_sub_r(" << g.F(pc + 1) << ", L[g], " << B << ");\n"; break;
         default:
             *err = "internal: unknown micro-op " + std::to_string(op);
             return CC_ERR_INVALID_PROGRAM;
         }
         if (op == MOP_RETURN) break;
-        if (dst != CC_SLOT_NONE) o << "        CC_EACH " << Gen::S(dst) << "[j] = L[j];\n";
+        if (stop_after >= 0 && ++n_emitted > stop_after) break;
+        if (dst != CC_SLOT_NONE) o << "        CC_EACH " << Gen::S(dst) << "[g] = L[g];\n";
         pc += CC_HDR_LEN(h);
     }
 
     std::ostringstream s;
     s << "// generated by libcodecad_b200 (cc_jit.cpp) from " << dec.info.n_micro_ops << " micro-ops\n"
+      << "#define CC_THREADS " << cfg.threads << "\n"
+      << (no_pack ? "#define CC_OPT_PACKED 0\n" : "")
       << "#include \"cc_ops.cuh\"\n#include \"cc_body.cuh\"\n"
       << "#define PTS " << pts << "\n"
-      << "#define CC_EACH _Pragma(\"unroll\") for (int j = 0; j < PTS; ++j)\n"
+      << "typedef cc_pts<PTS>::V V;\nconstexpr int G = cc_pts<PTS>::G;\ntypedef cc_val<V> Val;\n"
+      << "#define CC_EACH _Pragma(\"unroll\") for (int g = 0; g < G; ++g)\n"
       << g.consts.str() << "struct SceneEval {\n"
-      << "    __device__ __forceinline__ void operator()(const float (&gx)[PTS], const float (&gy)[PTS],\n"
-      << "                                               const float (&gz)[PTS], float4 (&L)[PTS]) const\n    {\n";
-    for (uint32_t k = 0; k < dec.info.n_slots; ++k) s << "        float4 S" << k << "[PTS];\n";
-    s << "        CC_EACH L[j] = make_float4(0.f, 0.f, 0.f, 0.f);\n" << o.str() << "    }\n};\n";
+      << "    __device__ __forceinline__ void operator()(const V (&gx)[G], const V (&gy)[G], const V (&gz)[G],\n"
+      << "                                               Val (&L)[G]) const\n    {\n";
+    for (uint32_t k = 0; k < dec.info.n_slots; ++k) s << "        Val S" << k << "[G];\n";
+    s << "        CC_EACH L[g] = Val{vbc<V>(0.f), vbc<V>(0.f), vbc<V>(0.f), vbc<V>(0.f)};\n" << o.str() << "    }\n};\n";
     const char *names[4] = {"float4", "pymcubes", "classify", "mass"};
     const char *sinks[4] = {"CC_SINK_FLOAT4", "CC_SINK_PYMCUBES", "CC_SINK_CLASSIFY", "CC_SINK_MASS"};
-    // optional occupancy hint (tuning experiments): CODECAD_B200_JIT_MINB = min CTAs per SM
+    // min CTAs per SM: caps the registers so that the wanted number of warps stays resident
     std::string bounds = "CC_THREADS";
-    if (const char *mb = getenv("CODECAD_B200_JIT_MINB")) bounds += std::string(", ") + std::to_string(atoi(mb));
+    if (cfg.min_blocks > 0) bounds += ", " + std::to_string(cfg.min_blocks);
     for (int k = 0; k < 4; ++k)
         if (sink_mask & (1u << k))
         s << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_" << names[k]
@@ -264,12 +264,39 @@ int generate(const cc_decoded &dec, int pts, unsigned sink_mask, std::string *sr
 
 }  // namespace
 
-void cc_jit_release(cc_program *prog);
+// Default shape of the specialised kernels, measured on B200 (profiles/r1_jit_variants.md):
+// two points per thread as one packed lane pair, 512-thread CTAs (warps that start together stay
+// close together in the straight-line code and share instruction-cache lines), registers capped
+// at 64 so that two CTAs = 32 warps are resident per SM.  Environment overrides for experiments:
+// CODECAD_B200_JIT_PTS / _THREADS / _MINB.
+cc_jit_cfg cc_jit_default_cfg(int pts)
+{
+    cc_jit_cfg c;
+    c.pts = 2;
+    c.threads = 512;
+    c.min_blocks = 2;
+    if (const char *t = getenv("CODECAD_B200_JIT_PTS")) c.pts = atoi(t);
+    if (pts == 1 || pts == 2 || pts == 4) c.pts = pts;
+    if (c.pts != 1 && c.pts != 2 && c.pts != 4) c.pts = 2;
+    if (const char *t = getenv("CODECAD_B200_JIT_THREADS")) {
+        int n = atoi(t);
+        if (n >= 64 && n <= 1024 && n % 32 == 0) c.threads = n;
+    }
+    if (const char *t = getenv("CODECAD_B200_JIT_MINB")) c.min_blocks = atoi(t);
+    // the ordered-compaction sinks scan PTS * warps-per-CTA counters with one warp (cc_body.cuh)
+    while (c.pts * (c.threads / 32) > 32) c.threads /= 2;
+    if (c.min_blocks * c.threads > 2048) c.min_blocks = 2048 / c.threads;
+    return c;
+}
 
 int cc_jit_nvrtc(const std::string &src, std::vector<char> *cubin, std::string *err)
 {
     Nvrtc n;
-    if (!load_nvrtc(&n, err)) return CC_ERR_CUDA;
+    {
+        static std::mutex mu;  // dlopen + symbol table are set up once
+        std::lock_guard<std::mutex> lk(mu);
+        if (!load_nvrtc(&n, err)) return CC_ERR_CUDA;
+    }
     const char *hdr_names[] = {"cc_device_types.h", "cc_math.cuh", "cc_ops.cuh", "cc_body.cuh"};
     std::string hdr_src[4];
     const std::string dir = source_dir();
@@ -305,51 +332,216 @@ int cc_jit_nvrtc(const std::string &src, std::vector<char> *cubin, std::string *
     return CC_OK;
 }
 
-int cc_jit_compile(cc_program *prog, int pts, unsigned sink_mask, double *seconds, std::string *err)
-{
-    if (pts != 1 && pts != 2 && pts != 4) pts = 2;
-    if ((sink_mask & 15u) == 0) sink_mask = 15u;
-    auto t0 = std::chrono::steady_clock::now();
-    std::string src;
-    int rc = generate(prog->dec, pts, sink_mask, &src, err);
-    if (rc) return rc;
-    std::vector<char> cubin;
-    rc = cc_jit_nvrtc(src, &cubin, err);
-    if (rc) return rc;
-    const size_t sz = cubin.size();
-    cc_jit_release(prog);
+// ---- cubin cache: in memory (per process) and on disk ----------------------------------------------
+// Key = FNV-1a of the generated source, the op-library headers it includes and the compile options,
+// so that editing csrc/*.cuh invalidates old entries.  Disk: $CODECAD_B200_CACHE, else
+// ~/.cache/codecad_b200; unusable directories are ignored.
+namespace {
 
+typedef std::shared_ptr<const std::vector<char>> Cubin;
+std::mutex g_cache_mu;
+std::map<uint64_t, Cubin> g_cache;
+
+uint64_t fnv1a(uint64_t h, const std::string &s)
+{
+    for (unsigned char ch : s) {
+        h ^= ch;
+        h *= 1099511628211ull;
+    }
+    return h;
+}
+
+uint64_t source_key(const std::string &src)
+{
+    uint64_t h = 14695981039346656037ull;
+    h = fnv1a(h, src);
+    const char *hdr_names[] = {"cc_device_types.h", "cc_math.cuh", "cc_ops.cuh", "cc_body.cuh"};
+    const std::string dir = source_dir();
+    for (const char *n : hdr_names) {
+        std::string t;
+        if (read_file(dir + n, &t)) h = fnv1a(h, t);
+    }
+    return fnv1a(h, "sm_100a -fmad=false c++17 lineinfo v2");
+}
+
+std::string cache_dir()
+{
+    if (const char *d = getenv("CODECAD_B200_CACHE")) return *d ? std::string(d) : std::string();
+    if (const char *h = getenv("HOME")) return std::string(h) + "/.cache/codecad_b200";
+    return std::string();
+}
+
+std::string cache_path(uint64_t key)
+{
+    const std::string d = cache_dir();
+    if (d.empty()) return d;
+    char name[40];
+    std::snprintf(name, sizeof name, "/%016llx.cubin", (unsigned long long)key);
+    return d + name;
+}
+
+void mkdirs(const std::string &d)
+{
+    for (size_t i = 1; i <= d.size(); ++i)
+        if (i == d.size() || d[i] == '/') mkdir(d.substr(0, i).c_str(), 0755);
+}
+
+}  // namespace
+
+// source for ONE sink -> cubin, through the caches.  Host-only work: safe on a background thread.
+static int build_cubin(const cc_decoded &dec, const cc_jit_cfg &cfg, int sink, Cubin *out, bool *cached,
+                       std::string *err)
+{
+    std::string src;
+    int rc = generate(dec, cfg, 1u << sink, &src, err);
+    if (rc) return rc;
+    const uint64_t key = source_key(src);
+    if (cached) *cached = true;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        auto it = g_cache.find(key);
+        if (it != g_cache.end()) {
+            *out = it->second;
+            return CC_OK;
+        }
+    }
+    auto bin = std::make_shared<std::vector<char>>();
+    const std::string path = cache_path(key);
+    std::string blob;
+    if (!path.empty() && read_file(path, &blob) && blob.size() > 64) {
+        bin->assign(blob.begin(), blob.end());
+    } else {
+        if (cached) *cached = false;
+        rc = cc_jit_nvrtc(src, bin.get(), err);
+        if (rc) return rc;
+        if (!path.empty()) {
+            mkdirs(cache_dir());
+            const std::string tmp = path + ".tmp" + std::to_string((long)getpid());
+            std::ofstream f(tmp.c_str(), std::ios::binary);
+            if (f) {
+                f.write(bin->data(), (std::streamsize)bin->size());
+                f.close();
+                if (!f || rename(tmp.c_str(), path.c_str()) != 0) remove(tmp.c_str());
+            }
+        }
+    }
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    g_cache[key] = bin;
+    *out = bin;
+    return CC_OK;
+}
+
+static int load_cubin(cc_program *prog, int sink, const Cubin &bin, const cc_jit_cfg &cfg, std::string *err)
+{
+    static const char *names[4] = {"cc_jit_float4", "cc_jit_pymcubes", "cc_jit_classify", "cc_jit_mass"};
     cudaLibrary_t lib = nullptr;
-    cudaError_t ce = cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+    cudaError_t ce = cudaLibraryLoadData(&lib, bin->data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
     if (ce != cudaSuccess) {
         *err = std::string("cudaLibraryLoadData: ") + cudaGetErrorString(ce);
         return CC_ERR_CUDA;
     }
-    const char *names[4] = {"cc_jit_float4", "cc_jit_pymcubes", "cc_jit_classify", "cc_jit_mass"};
+    cudaKernel_t kern = nullptr;
+    ce = cudaLibraryGetKernel(&kern, lib, names[sink]);
+    if (ce != cudaSuccess) {
+        *err = std::string("cudaLibraryGetKernel: ") + cudaGetErrorString(ce);
+        cudaLibraryUnload(lib);
+        return CC_ERR_CUDA;
+    }
+    if (prog->jit_library[sink]) cudaLibraryUnload((cudaLibrary_t)prog->jit_library[sink]);
+    prog->jit_library[sink] = (void *)lib;
+    prog->jit_kernel[sink] = (void *)kern;
+    prog->jit_cfg[sink] = cfg;
+    prog->jit_cubin_bytes += bin->size();
+    return CC_OK;
+}
+
+// ---- background compilation ------------------------------------------------------------------------
+struct cc_jit_job {
+    std::thread th;
+    std::atomic<int> done{0};
+    int rc = CC_OK;
+    Cubin bin;
+    cc_jit_cfg cfg;
+    std::string err;
+    double seconds = 0;
+    bool cached = false;
+};
+
+static void join_job(cc_program *prog, int sink)
+{
+    cc_jit_job *j = prog->jit_job[sink];
+    if (!j) return;
+    if (j->th.joinable()) j->th.join();
+    delete j;
+    prog->jit_job[sink] = nullptr;
+}
+
+// synchronous: build + load every sink of the mask
+int cc_jit_compile(cc_program *prog, int pts, unsigned sink_mask, double *seconds, std::string *err)
+{
+    if ((sink_mask & 15u) == 0) sink_mask = 15u;
+    const cc_jit_cfg cfg = cc_jit_default_cfg(pts);
+    auto t0 = std::chrono::steady_clock::now();
     for (int k = 0; k < 4; ++k) {
         if (!(sink_mask & (1u << k))) continue;
-        cudaKernel_t kern = nullptr;
-        ce = cudaLibraryGetKernel(&kern, lib, names[k]);
-        if (ce != cudaSuccess) {
-            *err = std::string("cudaLibraryGetKernel: ") + cudaGetErrorString(ce);
-            cudaLibraryUnload(lib);
-            return CC_ERR_CUDA;
-        }
-        prog->jit_kernel[k] = (void *)kern;
+        join_job(prog, k);
+        Cubin bin;
+        int rc = build_cubin(prog->dec, cfg, k, &bin, nullptr, err);
+        if (rc == CC_OK) rc = load_cubin(prog, k, bin, cfg, err);
+        if (rc) return rc;
     }
-    prog->jit_library = (void *)lib;
-    prog->jit_pts = pts;
-    prog->jit_cubin_bytes = sz;
     prog->use_jit = true;
     if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     return CC_OK;
 }
 
+// start compiling `sink` on a background thread (no-op if already compiled, running or failed)
+void cc_jit_start(cc_program *prog, int sink)
+{
+    if (prog->jit_kernel[sink] || prog->jit_job[sink] || prog->jit_failed[sink]) return;
+    cc_jit_job *j = new cc_jit_job;
+    j->cfg = cc_jit_default_cfg(0);
+    prog->jit_job[sink] = j;
+    const cc_decoded *dec = &prog->dec;  // immutable; outlives the thread (destroy joins it)
+    j->th = std::thread([j, dec, sink]() {
+        auto t0 = std::chrono::steady_clock::now();
+        j->rc = build_cubin(*dec, j->cfg, sink, &j->bin, &j->cached, &j->err);
+        j->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        j->done.store(1, std::memory_order_release);
+    });
+}
+
+// If the background job of `sink` has finished (or `wait`), load its kernel.  Returns 1 when the
+// specialised kernel is usable, 0 when not (yet), negative on a compile/load error (reported once;
+// the interpreter stays in use).
+int cc_jit_poll(cc_program *prog, int sink, bool wait, std::string *err)
+{
+    if (prog->jit_kernel[sink]) return 1;
+    cc_jit_job *j = prog->jit_job[sink];
+    if (!j) return 0;
+    if (!wait && !j->done.load(std::memory_order_acquire)) return 0;
+    if (j->th.joinable()) j->th.join();
+    int rc = j->rc;
+    if (rc == CC_OK) rc = load_cubin(prog, sink, j->bin, j->cfg, &j->err);
+    prog->jit_seconds += j->seconds;
+    if (rc != CC_OK) {
+        if (err) *err = j->err;
+        prog->jit_failed[sink] = true;
+    }
+    delete j;
+    prog->jit_job[sink] = nullptr;
+    return rc == CC_OK ? 1 : rc;
+}
+
 void cc_jit_release(cc_program *prog)
 {
-    if (prog->jit_library) cudaLibraryUnload((cudaLibrary_t)prog->jit_library);
-    prog->jit_library = nullptr;
-    for (int k = 0; k < 4; ++k) prog->jit_kernel[k] = nullptr;
+    for (int k = 0; k < 4; ++k) {
+        join_job(prog, k);
+        if (prog->jit_library[k]) cudaLibraryUnload((cudaLibrary_t)prog->jit_library[k]);
+        prog->jit_library[k] = nullptr;
+        prog->jit_kernel[k] = nullptr;
+    }
+    prog->jit_cubin_bytes = 0;
 }
 
 int cc_jit_launch(const cc_program *prog, int sink, const cc_eval_args &a, void *stream)
@@ -357,13 +549,12 @@ int cc_jit_launch(const cc_program *prog, int sink, const cc_eval_args &a, void 
     const uint32_t grid = a.n_blocks * a.tiles_per_block;
     if (grid == 0) return 0;
     void *args[] = {(void *)&a};
-    return (int)cudaLaunchKernel((const void *)prog->jit_kernel[sink], dim3(grid), dim3(CC_THREADS), args, 0,
-                                 (cudaStream_t)stream);
+    return (int)cudaLaunchKernel((const void *)prog->jit_kernel[sink], dim3(grid), dim3(prog->jit_cfg[sink].threads),
+                                 args, 0, (cudaStream_t)stream);
 }
 
 int cc_jit_source(const cc_decoded &dec, int pts, unsigned sink_mask, std::string *src, std::string *err)
 {
-    if (pts != 1 && pts != 2 && pts != 4) pts = 2;
     if ((sink_mask & 15u) == 0) sink_mask = 15u;
-    return generate(dec, pts, sink_mask, src, err);
+    return generate(dec, cc_jit_default_cfg(pts), sink_mask, src, err);
 }

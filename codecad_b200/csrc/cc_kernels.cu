@@ -65,15 +65,37 @@ CC_DEV_HEAVY float4 cc_polygon2d(const Prog<MODE> &P, uint32_t pc, float4 co)
 }
 
 // ---- the interpreter ------------------------------------------------------------------------
+// Value slots in shared memory: float4 regs[slot][PTS][CC_THREADS].  A packed pair of points
+// (V = float2) occupies two consecutive float4 rows: (x0,x1,y0,y1) and (z0,z1,w0,w1).
+CC_DEV void cc_slot_store(float4 *base, const cc_val<float> &v) { base[0] = make_float4(v.x, v.y, v.z, v.w); }
+CC_DEV void cc_slot_store(float4 *base, const cc_val<float2> &v)
+{
+    base[0] = make_float4(v.x.x, v.x.y, v.y.x, v.y.y);
+    base[CC_THREADS] = make_float4(v.z.x, v.z.y, v.w.x, v.w.y);
+}
+CC_DEV void cc_slot_load(const float4 *base, cc_val<float> &v)
+{
+    const float4 f = base[0];
+    v = cc_val<float>{f.x, f.y, f.z, f.w};
+}
+CC_DEV void cc_slot_load(const float4 *base, cc_val<float2> &v)
+{
+    const float4 a = base[0], b = base[CC_THREADS];
+    v = cc_val<float2>{make_float2(a.x, a.y), make_float2(a.z, a.w), make_float2(b.x, b.y), make_float2(b.z, b.w)};
+}
+CC_DEV void cc_slot_load_x(const float4 *base, float &x) { x = base[0].x; }
+CC_DEV void cc_slot_load_x(const float4 *base, float2 &x) { x = *reinterpret_cast<const float2 *>(base); }
+CC_DEV void cc_slot_load_z(const float4 *base, float &z) { z = base[0].z; }
+CC_DEV void cc_slot_load_z(const float4 *base, float2 &z) { z = *reinterpret_cast<const float2 *>(base + CC_THREADS); }
+
 // Fused primitive (loader pattern: initial_transformation_to -> [store p] -> circle|rectangle
 // -> extrusion p -> [offset] -> [transformation_from]): one dispatch, the transformed point
 // never leaves registers.  Bit-identical to the unfused sequence (absent offset = 0, absent
 // transformation_from = identity matrix and scale 1).
 // words: 1..12 m,o | 13 a | 14 b | 15 h | 16 d | 17..25 m' | 26 scale
-// words: 1..12 m,o | 13 a | 14 b | 15 h | 16 d | 17..25 m' | 26 scale
-template <bool RECT, int PTS, int SMEM>
-CC_DEV void cc_prim(const Prog<SMEM> &P, uint32_t pc, const float (&x)[PTS], const float (&y)[PTS],
-                    const float (&z)[PTS], float4 (&L)[PTS])
+template <bool RECT, class V, int G, int SMEM>
+CC_DEV void cc_prim(const Prog<SMEM> &P, uint32_t pc, const V (&x)[G], const V (&y)[G], const V (&z)[G],
+                    cc_val<V> (&L)[G])
 {
     float m[12], mf[12];
     const float4 a = P.f4(pc), b = P.f4(pc + 4), c = P.f4(pc + 8), d = P.f4(pc + 12), e = P.f4(pc + 16),
@@ -82,18 +104,24 @@ CC_DEV void cc_prim(const Prog<SMEM> &P, uint32_t pc, const float (&x)[PTS], con
     m[6] = b.w; m[7] = c.x; m[8] = c.y; m[9] = c.z; m[10] = c.w; m[11] = d.x;
     mf[0] = e.y; mf[1] = e.z; mf[2] = e.w; mf[3] = f.x; mf[4] = f.y; mf[5] = f.z;
     mf[6] = f.w; mf[7] = g.x; mf[8] = g.y; mf[9] = g.z; mf[10] = 0.f; mf[11] = 0.f;
-    cc_prim_n<RECT, PTS>(m, mf, d.y, d.z, d.w, e.x, x, y, z, L);
+    cc_prim_n<RECT, V, G>(m, mf, d.y, d.z, d.w, e.x, x, y, z, L);
 }
 
 template <int PTS, int SMEM>
-CC_DEV void cc_interpret(const Prog<SMEM> P, float4 *__restrict__ regs, const float (&gx)[PTS],
-                         const float (&gy)[PTS], const float (&gz)[PTS], float4 (&L)[PTS])
+CC_DEV void cc_interpret(const Prog<SMEM> P, float4 *__restrict__ regs, const typename cc_pts<PTS>::V (&gx)[cc_pts<PTS>::G],
+                         const typename cc_pts<PTS>::V (&gy)[cc_pts<PTS>::G],
+                         const typename cc_pts<PTS>::V (&gz)[cc_pts<PTS>::G],
+                         cc_val<typename cc_pts<PTS>::V> (&L)[cc_pts<PTS>::G])
 {
+    typedef typename cc_pts<PTS>::V V;
+    typedef cc_val<V> Val;
+    constexpr int G = cc_pts<PTS>::G, NL = cc_lane<V>::N;
     float4 *const myregs = regs + threadIdx.x;
 #pragma unroll
-    for (int j = 0; j < PTS; ++j) L[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-#define CC_SLOT(slot, j) myregs[((slot) * PTS + (j)) * CC_THREADS]
-#define CC_EACH for (int j = 0; j < PTS; ++j)
+    for (int g = 0; g < G; ++g) L[g] = Val{vbc<V>(0.f), vbc<V>(0.f), vbc<V>(0.f), vbc<V>(0.f)};
+#define CC_SLOT_BASE(slot, g) (myregs + ((slot) * PTS + (g) * NL) * CC_THREADS)
+#define CC_EACH for (int g = 0; g < G; ++g)
+#define CC_LOAD_B(g) Val B; cc_slot_load(CC_SLOT_BASE(src, g), B)
     uint32_t pc = 0;
     for (;;) {
         const uint32_t h = P.u(pc);
@@ -102,7 +130,7 @@ CC_DEV void cc_interpret(const Prog<SMEM> P, float4 *__restrict__ regs, const fl
         case MOP_RETURN: return;
         case MOP_LOAD:
 #pragma unroll
-            CC_EACH L[j] = CC_SLOT(src, j);
+            CC_EACH cc_slot_load(CC_SLOT_BASE(src, g), L[g]);
             pc += CC_LEN_0;
             break;
         case MOP_NOP: pc += CC_LEN_0; break;
@@ -112,22 +140,22 @@ CC_DEV void cc_interpret(const Prog<SMEM> P, float4 *__restrict__ regs, const fl
         // uniform datapath (LDCU/UISETP/BRA.U); deriving the increment from a loaded word or
         // advancing before a per-thread branch silently demotes everything to vector code (-11 %).
         case MOP_PRIM_CIRCLE:
-            cc_prim<false, PTS, SMEM>(P, pc, gx, gy, gz, L);
+            cc_prim<false, V, G, SMEM>(P, pc, gx, gy, gz, L);
             pc += CC_LEN_PRIM;
             break;
         case MOP_PRIM_RECT:
-            cc_prim<true, PTS, SMEM>(P, pc, gx, gy, gz, L);
+            cc_prim<true, V, G, SMEM>(P, pc, gx, gy, gz, L);
             pc += CC_LEN_PRIM;
             break;
         case MOP_RECTANGLE: {
             const float4 q = P.f4(pc);
-            cc_rectangle_n<PTS>(q.y, q.z, L);
+            cc_rectangle_n(q.y, q.z, L);
             pc += CC_LEN_0;
             break;
         }
         case MOP_CIRCLE: {
             const float r = P.f(pc + 1);
-            cc_circle_n<PTS>(r, L);
+            cc_circle_n(r, L);
             pc += CC_LEN_0;
             break;
         }
@@ -136,36 +164,36 @@ CC_DEV void cc_interpret(const Prog<SMEM> P, float4 *__restrict__ regs, const fl
 #pragma unroll
             for (int i = 0; i < 5; ++i) k[i] = P.f(pc + 1 + i);
 #pragma unroll
-            CC_EACH L[j] = cc_regular_polygon2d(k[0], k[1], k[2], k[3], k[4], L[j]);
+            CC_EACH L[g] = cc_op_regpoly(k[0], k[1], k[2], k[3], k[4], L[g]);
             pc += CC_LEN_7;
             break;
         }
         case MOP_POLYGON: {
 #pragma unroll
-            CC_EACH L[j] = cc_polygon2d<SMEM>(P, pc, L[j]);
+            CC_EACH L[g] = cc_map1(L[g], [&](float4 p) { return cc_polygon2d<SMEM>(P, pc, p); });
             pc += CC_LEN_0;
             break;
         }
         case MOP_SPHERE: {
             const float r = P.f(pc + 1);
-            cc_sphere_n<PTS>(r, L);
+            cc_sphere_n(r, L);
             pc += CC_LEN_0;
             break;
         }
-        case MOP_HALF_SPACE:  // simple3d.cl:14-16
+        case MOP_HALF_SPACE:
 #pragma unroll
-            CC_EACH L[j] = make_float4(0.0f, -1.0f, 0.0f, -L[j].y);
+            CC_EACH L[g] = cc_op_half_space(L[g]);
             pc += CC_LEN_0;
             break;
-        case MOP_REV_TO:  // simple3d.cl:23-26
+        case MOP_REV_TO:
 #pragma unroll
-            CC_EACH L[j] = make_float4(cc_len2(L[j].x, L[j].z), L[j].y, 0.0f, 0.0f);
+            CC_EACH L[g] = cc_op_rev_to(L[g]);
             pc += CC_LEN_0;
             break;
         case MOP_TWIST_TO: {
             const float r = P.f(pc + 1), twist = P.f(pc + 2);
 #pragma unroll
-            CC_EACH L[j] = cc_twist_revolution_to(r, twist, L[j]);
+            CC_EACH L[g] = cc_op_twist_to(r, twist, L[g]);
             pc += CC_LEN_0;
             break;
         }
@@ -179,10 +207,10 @@ CC_DEV void cc_interpret(const Prog<SMEM> P, float4 *__restrict__ regs, const fl
             }
             if (op == MOP_T_INIT) {
 #pragma unroll
-                CC_EACH L[j] = cc_transform(m, gx[j], gy[j], gz[j]);
+                CC_EACH L[g] = cc_transform(m, gx[g], gy[g], gz[g]);
             } else {
 #pragma unroll
-                CC_EACH L[j] = cc_transform(m, L[j].x, L[j].y, L[j].z);
+                CC_EACH L[g] = cc_transform(m, L[g].x, L[g].y, L[g].z);
             }
             pc += CC_LEN_T;
             break;
@@ -195,50 +223,45 @@ CC_DEV void cc_interpret(const Prog<SMEM> P, float4 *__restrict__ regs, const fl
                 m[6] = b.w; m[7] = c.x; m[8] = c.y; m[9] = c.z; m[10] = 0.f; m[11] = 0.f;
             }
 #pragma unroll
-            CC_EACH L[j] = cc_transform_from(m, L[j]);
+            CC_EACH L[g] = cc_transform_from(m, L[g]);
             pc += CC_LEN_T;
             break;
         }
         case MOP_MIRROR:  // common.cl:112-114
 #pragma unroll
-            CC_EACH L[j].x = -L[j].x;
+            CC_EACH L[g].x = vneg(L[g].x);
             pc += CC_LEN_0;
             break;
         case MOP_SYM_TO:  // common.cl:116-118
 #pragma unroll
-            CC_EACH L[j].x = fabsf(L[j].x);
+            CC_EACH L[g].x = vabs(L[g].x);
             pc += CC_LEN_0;
             break;
         case MOP_OFFSET: {  // common.cl:124-126
             const float d = P.f(pc + 1);
 #pragma unroll
-            CC_EACH L[j].w = L[j].w - d;
+            CC_EACH L[g].w = vsub(L[g].w, vbc<V>(d));
             pc += CC_LEN_0;
             break;
         }
-        case MOP_SHELL: {  // common.cl:128-131
+        case MOP_SHELL: {
             const float d = P.f(pc + 1);
 #pragma unroll
-            CC_EACH {
-                float4 s = (L[j].w >= 0.0f) ? L[j] : cc_neg4(L[j]);
-                s.w = s.w - d;
-                L[j] = s;
-            }
+            CC_EACH L[g] = cc_op_shell(d, L[g]);
             pc += CC_LEN_0;
             break;
         }
-        case MOP_REPETITION: {  // unsafe.cl:1-6
+        case MOP_REPETITION: {
             const float4 q = P.f4(pc);
 #pragma unroll
-            CC_EACH L[j] = make_float4(cc_remainder(L[j].x, q.y), cc_remainder(L[j].y, q.z),
-                                       cc_remainder(L[j].z, q.w), 0.0f);
+            CC_EACH L[g] = cc_op_repetition(q.y, q.z, q.w, L[g]);
             pc += CC_LEN_0;
             break;
         }
         case MOP_CREP_TO: {
             const float a = P.f(pc + 1), b = P.f(pc + 2);
 #pragma unroll
-            CC_EACH L[j] = cc_circular_repetition_to(a, b, L[j]);
+            CC_EACH L[g] = cc_op_crep_to(a, b, L[g]);
             pc += CC_LEN_0;
             break;
         }
@@ -247,28 +270,35 @@ CC_DEV void cc_interpret(const Prog<SMEM> P, float4 *__restrict__ regs, const fl
 #pragma unroll
             for (int i = 0; i < 5; ++i) k[i] = P.f(pc + 1 + i);
 #pragma unroll
-            CC_EACH L[j] = cc_involute_gear(k[0], k[1], k[2], k[3], k[4], L[j]);
+            CC_EACH L[g] = cc_op_gear(k[0], k[1], k[2], k[3], k[4], L[g]);
             pc += CC_LEN_7;
             break;
         }
         // ---- ops whose second operand is a point held in a slot ----
         case MOP_EXTRUSION: {
             const float hh = P.f(pc + 1);
-            float cz[PTS];
+            V cz[G];
 #pragma unroll
-            CC_EACH cz[j] = CC_SLOT(src, j).z;
-            cc_extrusion_n<PTS>(hh, L, cz);
+            CC_EACH cc_slot_load_z(CC_SLOT_BASE(src, g), cz[g]);
+            cc_extrusion_n(hh, L, cz);
             pc += CC_LEN_0;
             break;
         }
         case MOP_REV_FROM:
 #pragma unroll
-            CC_EACH L[j] = cc_revolution_from(L[j], CC_SLOT(src, j));
+            CC_EACH {
+                CC_LOAD_B(g);
+                L[g] = cc_revolution_from(L[g], B);
+            }
             pc += CC_LEN_0;
             break;
-        case MOP_SYM_FROM:  // common.cl:120-122
+        case MOP_SYM_FROM:
 #pragma unroll
-            CC_EACH L[j].x = (CC_SLOT(src, j).x < 0.0f) ? -L[j].x : L[j].x;
+            CC_EACH {
+                Val B;
+                cc_slot_load_x(CC_SLOT_BASE(src, g), B.x);
+                L[g] = cc_op_sym_from(L[g], B);
+            }
             pc += CC_LEN_0;
             break;
         case MOP_TWIST_FROM: {
@@ -276,60 +306,75 @@ CC_DEV void cc_interpret(const Prog<SMEM> P, float4 *__restrict__ regs, const fl
 #pragma unroll
             for (int i = 0; i < 5; ++i) k[i] = P.f(pc + 1 + i);
 #pragma unroll
-            CC_EACH L[j] = cc_twist_revolution_from(k[0], k[1], k[2], k[3], k[4], L[j], CC_SLOT(src, j));
+            CC_EACH {
+                CC_LOAD_B(g);
+                L[g] = cc_op_twist_from(k[0], k[1], k[2], k[3], k[4], L[g], B);
+            }
             pc += CC_LEN_7;
             break;
         }
         case MOP_CREP_FROM: {
             const float a = P.f(pc + 1), b = P.f(pc + 2);
 #pragma unroll
-            CC_EACH L[j] = cc_circular_repetition_from(a, b, L[j], CC_SLOT(src, j));
+            CC_EACH {
+                CC_LOAD_B(g);
+                L[g] = cc_op_crep_from(a, b, L[g], B);
+            }
             pc += CC_LEN_0;
             break;
         }
         // ---- CSG combinators: second operand is always a slot ----
-        case MOP_UNION:  // common.cl:60-68 with r < 0
+        case MOP_UNION:
 #pragma unroll
             CC_EACH {
-                const float4 b = CC_SLOT(src, j);
-                L[j] = (L[j].w < b.w) ? L[j] : b;
+                CC_LOAD_B(g);
+                L[g] = cc_op_union(L[g], B);
             }
             pc += CC_LEN_0;
             break;
         case MOP_UNION_R: {
             const float r = P.f(pc + 1);
 #pragma unroll
-            CC_EACH L[j] = cc_rounded_union(r, L[j], CC_SLOT(src, j));
+            CC_EACH {
+                CC_LOAD_B(g);
+                L[g] = cc_rounded_union(r, L[g], B);
+            }
             pc += CC_LEN_0;
             break;
         }
-        case MOP_ISECT:  // common.cl:70-72: -min(-a, -b) = the operand with the larger distance
+        case MOP_ISECT:
 #pragma unroll
             CC_EACH {
-                const float4 b = CC_SLOT(src, j);
-                L[j] = (-L[j].w < -b.w) ? L[j] : b;
+                CC_LOAD_B(g);
+                L[g] = cc_op_isect(L[g], B);
             }
             pc += CC_LEN_0;
             break;
         case MOP_ISECT_R: {
             const float r = P.f(pc + 1);
 #pragma unroll
-            CC_EACH L[j] = cc_neg4(cc_rounded_union(r, cc_neg4(L[j]), cc_neg4(CC_SLOT(src, j))));
+            CC_EACH {
+                CC_LOAD_B(g);
+                L[g] = cc_op_isect_r(r, L[g], B);
+            }
             pc += CC_LEN_0;
             break;
         }
-        case MOP_SUB:  // common.cl:74-76: -min(-a, b)
+        case MOP_SUB:
 #pragma unroll
             CC_EACH {
-                const float4 b = CC_SLOT(src, j);
-                L[j] = (-L[j].w < b.w) ? L[j] : cc_neg4(b);
+                CC_LOAD_B(g);
+                L[g] = cc_op_sub(L[g], B);
             }
             pc += CC_LEN_0;
             break;
         case MOP_SUB_R: {
             const float r = P.f(pc + 1);
 #pragma unroll
-            CC_EACH L[j] = cc_neg4(cc_rounded_union(r, cc_neg4(L[j]), CC_SLOT(src, j)));
+            CC_EACH {
+                CC_LOAD_B(g);
+                L[g] = cc_op_sub_r(r, L[g], B);
+            }
             pc += CC_LEN_0;
             break;
         }
@@ -337,19 +382,21 @@ CC_DEV void cc_interpret(const Prog<SMEM> P, float4 *__restrict__ regs, const fl
         }
         if (dst != CC_SLOT_NONE) {
 #pragma unroll
-            CC_EACH CC_SLOT(dst, j) = L[j];
+            CC_EACH cc_slot_store(CC_SLOT_BASE(dst, g), L[g]);
         }
     }
-#undef CC_SLOT
+#undef CC_SLOT_BASE
 #undef CC_EACH
+#undef CC_LOAD_B
 }
 
 template <int PTS, int SMEM>
 struct InterpEval {
+    typedef typename cc_pts<PTS>::V V;
     Prog<SMEM> P;
     float4 *regs;
-    CC_DEV void operator()(const float (&gx)[PTS], const float (&gy)[PTS], const float (&gz)[PTS],
-                           float4 (&L)[PTS]) const
+    CC_DEV void operator()(const V (&gx)[cc_pts<PTS>::G], const V (&gy)[cc_pts<PTS>::G], const V (&gz)[cc_pts<PTS>::G],
+                           cc_val<V> (&L)[cc_pts<PTS>::G]) const
     {
         if (SMEM != 0) {
             asm volatile("cp.async.wait_group 0;" ::: "memory");

@@ -81,7 +81,8 @@ CC_DEV float4 cc_sphere(float r, float4 p)
     return make_float4(zero ? 1.0f : p.x * inv, zero ? 0.0f : p.y * inv, zero ? 0.0f : p.z * inv, len - r);
 }
 
-// ---- the same ops over all PTS points of a thread, with one combined special-operand test ----
+// ---- the same ops over all of a thread's points, with one combined special-operand test ----
+// L holds G lane vectors (cc_math.cuh: V = float2 packs two points into FFMA2/FMUL2/FADD2).
 // Results are identical to the per-point forms above (which remain the slow path and the
 // reference for the oracle): in the fast path every sqrt/rcp operand is in the exact range of
 // cc_sqrt_fast / cc_rcp_fast, and a length in that range is never zero.
@@ -90,148 +91,168 @@ __device__ __noinline__ float4 cc_circle_slow(float r, float4 p) { return cc_cir
 __device__ __noinline__ float4 cc_sphere_slow(float r, float4 p) { return cc_sphere(r, p); }
 __device__ __noinline__ float4 cc_extrusion_slow(float h, float4 in, float cz) { return cc_extrusion(h, in, cz); }
 
-template <int PTS>
-CC_DEV void cc_rectangle_n(float hw, float hh, float4 (&L)[PTS])
+// apply a one-point function to every lane of every vector
+template <class V, int G, class F>
+CC_DEV void cc_each_lane(cc_val<V> (&L)[G], F f)
 {
-    float ax[PTS], ay[PTS], s[PTS];
-    bool sp = false;
 #pragma unroll
-    for (int j = 0; j < PTS; ++j) {
-        ax[j] = fabsf(L[j].x) - hw;
-        ay[j] = fabsf(L[j].y) - hh;
-        s[j] = cc_fma(ax[j], ax[j], ay[j] * ay[j]);
-        sp |= cc_special(s[j]);
-    }
-    if (__any_sync(0xffffffffu, sp)) {  // warp-uniform: keeps the interpreter's control flow convergent
+    for (int g = 0; g < G; ++g) {
 #pragma unroll
-        for (int j = 0; j < PTS; ++j) L[j] = cc_rectangle_slow(hw, hh, L[j]);
-        return;
-    }
-#pragma unroll
-    for (int j = 0; j < PTS; ++j) {
-        const float sx = copysignf(1.0f, L[j].x), sy = copysignf(1.0f, L[j].y);
-        const float dist = cc_sqrt_fast(s[j]);
-        const float inv = cc_rcp_fast(dist);
-        const bool both = ax[j] > 0.0f && ay[j] > 0.0f;
-        const bool first = ax[j] > ay[j];
-        float4 r;
-        r.x = both ? sx * (ax[j] * inv) : (first ? sx : 0.0f);
-        r.y = both ? sy * (ay[j] * inv) : (first ? 0.0f : sy);
-        r.z = 0.0f;
-        r.w = both ? dist : (first ? ax[j] : ay[j]);
-        L[j] = r;
+        for (int l = 0; l < cc_lane<V>::N; ++l) cc_lane_put(L[g], l, f(cc_lane_get(L[g], l), g, l));
     }
 }
 
-template <int PTS>
-CC_DEV void cc_circle_n(float r, float4 (&L)[PTS])
+template <class V, int G>
+CC_DEV void cc_rectangle_n(float hw, float hh, cc_val<V> (&L)[G])
 {
-    float s[PTS];
+    typedef typename cc_lane<V>::mask M;
+    V ax[G], ay[G], s[G];
     bool sp = false;
 #pragma unroll
-    for (int j = 0; j < PTS; ++j) {
-        s[j] = cc_fma(L[j].x, L[j].x, L[j].y * L[j].y);
-        sp |= cc_special(s[j]);
+    for (int g = 0; g < G; ++g) {
+        ax[g] = vsub(vabs(L[g].x), vbc<V>(hw));
+        ay[g] = vsub(vabs(L[g].y), vbc<V>(hh));
+        s[g] = vfma(ax[g], ax[g], vmul(ay[g], ay[g]));
+        sp |= vspecial(s[g]);
     }
     if (__any_sync(0xffffffffu, sp)) {  // warp-uniform: keeps the interpreter's control flow convergent
-#pragma unroll
-        for (int j = 0; j < PTS; ++j) L[j] = cc_circle_slow(r, L[j]);
+        cc_each_lane(L, [&](float4 p, int, int) { return cc_rectangle_slow(hw, hh, p); });
         return;
     }
 #pragma unroll
-    for (int j = 0; j < PTS; ++j) {
-        const float len = cc_sqrt_fast(s[j]);
-        const float inv = cc_rcp_fast(len);
-        L[j] = make_float4(L[j].x * inv, L[j].y * inv, 0.0f, len - r);
+    for (int g = 0; g < G; ++g) {
+        const V one = vbc<V>(1.0f), zero = vbc<V>(0.0f);
+        const V sx = vcopysign(one, L[g].x), sy = vcopysign(one, L[g].y);
+        const V dist = vsqrt_fast(s[g]);
+        const V inv = vrcp_fast(dist);
+        const M both = mand(vgt(ax[g], zero), vgt(ay[g], zero));
+        const M first = vgt(ax[g], ay[g]);
+        cc_val<V> r;
+        r.x = vsel(both, vmul(sx, vmul(ax[g], inv)), vsel(first, sx, zero));
+        r.y = vsel(both, vmul(sy, vmul(ay[g], inv)), vsel(first, zero, sy));
+        r.z = zero;
+        r.w = vsel(both, dist, vsel(first, ax[g], ay[g]));
+        L[g] = r;
     }
 }
 
-template <int PTS>
-CC_DEV void cc_sphere_n(float r, float4 (&L)[PTS])
+template <class V, int G>
+CC_DEV void cc_circle_n(float r, cc_val<V> (&L)[G])
 {
-    float s[PTS];
+    V s[G];
     bool sp = false;
 #pragma unroll
-    for (int j = 0; j < PTS; ++j) {
-        s[j] = cc_fma(L[j].x, L[j].x, cc_fma(L[j].y, L[j].y, L[j].z * L[j].z));
-        sp |= cc_special(s[j]);
+    for (int g = 0; g < G; ++g) {
+        s[g] = vfma(L[g].x, L[g].x, vmul(L[g].y, L[g].y));
+        sp |= vspecial(s[g]);
     }
     if (__any_sync(0xffffffffu, sp)) {  // warp-uniform: keeps the interpreter's control flow convergent
-#pragma unroll
-        for (int j = 0; j < PTS; ++j) L[j] = cc_sphere_slow(r, L[j]);
+        cc_each_lane(L, [&](float4 p, int, int) { return cc_circle_slow(r, p); });
         return;
     }
 #pragma unroll
-    for (int j = 0; j < PTS; ++j) {
-        const float len = cc_sqrt_fast(s[j]);
-        const float inv = cc_rcp_fast(len);
-        L[j] = make_float4(L[j].x * inv, L[j].y * inv, L[j].z * inv, len - r);
+    for (int g = 0; g < G; ++g) {
+        const V len = vsqrt_fast(s[g]);
+        const V inv = vrcp_fast(len);
+        L[g] = cc_val<V>{vmul(L[g].x, inv), vmul(L[g].y, inv), vbc<V>(0.0f), vsub(len, vbc<V>(r))};
     }
 }
 
-// cz[j] = z coordinate of the point operand
-template <int PTS>
-CC_DEV void cc_extrusion_n(float h, float4 (&L)[PTS], const float (&cz)[PTS])
+template <class V, int G>
+CC_DEV void cc_sphere_n(float r, cc_val<V> (&L)[G])
 {
-    float az[PTS], s[PTS];
+    V s[G];
     bool sp = false;
 #pragma unroll
-    for (int j = 0; j < PTS; ++j) {
-        az[j] = fabsf(cz[j]) - h;
-        s[j] = cc_fma(az[j], az[j], L[j].w * L[j].w);
-        sp |= cc_special(s[j]);
+    for (int g = 0; g < G; ++g) {
+        s[g] = vfma(L[g].x, L[g].x, vfma(L[g].y, L[g].y, vmul(L[g].z, L[g].z)));
+        sp |= vspecial(s[g]);
     }
     if (__any_sync(0xffffffffu, sp)) {  // warp-uniform: keeps the interpreter's control flow convergent
-#pragma unroll
-        for (int j = 0; j < PTS; ++j) L[j] = cc_extrusion_slow(h, L[j], cz[j]);
+        cc_each_lane(L, [&](float4 p, int, int) { return cc_sphere_slow(r, p); });
         return;
     }
 #pragma unroll
-    for (int j = 0; j < PTS; ++j) {
-        const float4 in = L[j];
-        const float sz = copysignf(1.0f, cz[j]);
-        const float dist = cc_sqrt_fast(s[j]);
-        const float inv = cc_rcp_fast(dist);
-        const float m1 = az[j] * inv, m2 = in.w * inv;
-        const bool both = az[j] > 0.0f && in.w > 0.0f;
-        const bool first = az[j] > in.w;
-        float4 r;
-        r.x = both ? in.x * m2 : (first ? 0.0f : in.x);
-        r.y = both ? in.y * m2 : (first ? 0.0f : in.y);
-        r.z = both ? cc_fma(sz, m1, in.z * m2) : (first ? sz : in.z);
-        r.w = both ? dist : (first ? az[j] : in.w);
-        L[j] = r;
+    for (int g = 0; g < G; ++g) {
+        const V len = vsqrt_fast(s[g]);
+        const V inv = vrcp_fast(len);
+        L[g] = cc_val<V>{vmul(L[g].x, inv), vmul(L[g].y, inv), vmul(L[g].z, inv), vsub(len, vbc<V>(r))};
+    }
+}
+
+// cz[g] = z coordinate of the point operand
+template <class V, int G>
+CC_DEV void cc_extrusion_n(float h, cc_val<V> (&L)[G], const V (&cz)[G])
+{
+    typedef typename cc_lane<V>::mask M;
+    V az[G], s[G];
+    bool sp = false;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        az[g] = vsub(vabs(cz[g]), vbc<V>(h));
+        s[g] = vfma(az[g], az[g], vmul(L[g].w, L[g].w));
+        sp |= vspecial(s[g]);
+    }
+    if (__any_sync(0xffffffffu, sp)) {  // warp-uniform: keeps the interpreter's control flow convergent
+        cc_each_lane(L, [&](float4 p, int g, int l) { return cc_extrusion_slow(h, p, vlane(cz[g], l)); });
+        return;
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const V zero = vbc<V>(0.0f);
+        const cc_val<V> in = L[g];
+        const V sz = vcopysign(vbc<V>(1.0f), cz[g]);
+        const V dist = vsqrt_fast(s[g]);
+        const V inv = vrcp_fast(dist);
+        const V m1 = vmul(az[g], inv), m2 = vmul(in.w, inv);
+        const M both = mand(vgt(az[g], zero), vgt(in.w, zero));
+        const M first = vgt(az[g], in.w);
+        cc_val<V> r;
+        r.x = vsel(both, vmul(in.x, m2), vsel(first, zero, in.x));
+        r.y = vsel(both, vmul(in.y, m2), vsel(first, zero, in.y));
+        r.z = vsel(both, vfma(sz, m1, vmul(in.z, m2)), vsel(first, sz, in.z));
+        r.w = vsel(both, dist, vsel(first, az[g], in.w));
+        L[g] = r;
     }
 }
 
 // shapes/common.cl:45-64
-CC_DEV float4 cc_rounded_union(float r, float4 o1, float4 o2)
+template <class V>
+CC_DEV cc_val<V> cc_rounded_union(float r, cc_val<V> o1, cc_val<V> o2)
 {
-    float4 res = (o1.w < o2.w) ? o1 : o2;
-    float c = cc_dot3(o1.x, o1.y, o1.z, o2.x, o2.y, o2.z);
-    float x1 = r - o1.w, x2 = r - o2.w;
-    if (c * x1 < x2 && c * x2 < x1) {  // rare: only within r of both surfaces
-        float num = cc_fma(-((2.0f * c) * x1), x2, cc_fma(x1, x1, x2 * x2));
-        float den = cc_fma(-c, c, 1.0f);
-        res = make_float4(0.0f, 0.0f, 0.0f, r - cc_sqrt(cc_div(num, den)));
+    typedef typename cc_lane<V>::mask M;
+    cc_val<V> res = cc_val_sel(vlt(o1.w, o2.w), o1, o2);
+    const V c = vfma(o1.x, o2.x, vfma(o1.y, o2.y, vmul(o1.z, o2.z)));
+    const V x1 = vsub(vbc<V>(r), o1.w), x2 = vsub(vbc<V>(r), o2.w);
+    const M blend = mand(vlt(vmul(c, x1), x2), vlt(vmul(c, x2), x1));
+    if (many(blend)) {  // rare: only within r of both surfaces
+        const V num = vfma(vneg(vmul(vmul(vbc<V>(2.0f), c), x1)), x2, vfma(x1, x1, vmul(x2, x2)));
+        const V den = vfma(vneg(c), c, vbc<V>(1.0f));
+        const V zero = vbc<V>(0.0f);
+        const cc_val<V> b{zero, zero, zero, vsub(vbc<V>(r), vsqrt(vdiv(num, den)))};
+        res = cc_val_sel(blend, b, res);
     }
     return res;
 }
 
 // 3x3 (row-major) * v + o   — common.cl:78-98 in matrix form
-CC_DEV float4 cc_transform(const float (&m)[12], float x, float y, float z)
+template <class V>
+CC_DEV cc_val<V> cc_transform(const float (&m)[12], V x, V y, V z)
 {
-    return make_float4(cc_fma(m[0], x, cc_fma(m[1], y, cc_fma(m[2], z, m[9]))),
-                       cc_fma(m[3], x, cc_fma(m[4], y, cc_fma(m[5], z, m[10]))),
-                       cc_fma(m[6], x, cc_fma(m[7], y, cc_fma(m[8], z, m[11]))), 0.0f);
+    return cc_val<V>{vfma(vbc<V>(m[0]), x, vfma(vbc<V>(m[1]), y, vfma(vbc<V>(m[2]), z, vbc<V>(m[9])))),
+                     vfma(vbc<V>(m[3]), x, vfma(vbc<V>(m[4]), y, vfma(vbc<V>(m[5]), z, vbc<V>(m[10])))),
+                     vfma(vbc<V>(m[6]), x, vfma(vbc<V>(m[7]), y, vfma(vbc<V>(m[8]), z, vbc<V>(m[11])))),
+                     vbc<V>(0.0f)};
 }
 
 // common.cl:100-110 (matrix already divided by |q|^2; m[9] = |q|^2)
-CC_DEV float4 cc_transform_from(const float (&m)[12], float4 in)
+template <class V>
+CC_DEV cc_val<V> cc_transform_from(const float (&m)[12], cc_val<V> in)
 {
-    return make_float4(cc_fma(m[0], in.x, cc_fma(m[1], in.y, m[2] * in.z)),
-                       cc_fma(m[3], in.x, cc_fma(m[4], in.y, m[5] * in.z)),
-                       cc_fma(m[6], in.x, cc_fma(m[7], in.y, m[8] * in.z)), in.w * m[9]);
+    return cc_val<V>{vfma(vbc<V>(m[0]), in.x, vfma(vbc<V>(m[1]), in.y, vmul(vbc<V>(m[2]), in.z))),
+                     vfma(vbc<V>(m[3]), in.x, vfma(vbc<V>(m[4]), in.y, vmul(vbc<V>(m[5]), in.z))),
+                     vfma(vbc<V>(m[6]), in.x, vfma(vbc<V>(m[7]), in.y, vmul(vbc<V>(m[8]), in.z))),
+                     vmul(in.w, vbc<V>(m[9]))};
 }
 
 // shapes/simple2d.cl:16-46; k = (piOverN, r, r*sin, r*cos, 2*piOverN)
@@ -348,34 +369,36 @@ CC_DEV_HEAVY float4 cc_circular_repetition_from(float piOverN, float twoPiOverN,
 }
 
 // shapes/simple3d.cl:28-39
-CC_DEV float4 cc_revolution_from(float4 flat, float4 co)
+template <class V>
+CC_DEV cc_val<V> cc_revolution_from(cc_val<V> flat, cc_val<V> co)
 {
-    float len = cc_len2(co.x, co.z);
-    bool zero = len == 0.0f;
-    float mult = zero ? flat.x : cc_div(flat.x, len);
-    float cx = zero ? 1.0f : co.x;
-    return make_float4(cx * mult, flat.y, co.z * mult, flat.w);
+    typedef typename cc_lane<V>::mask M;
+    const V len = vlen2(co.x, co.z);
+    const M zero = veq(len, vbc<V>(0.0f));
+    const V mult = vsel(zero, flat.x, vdiv(flat.x, len));
+    const V cx = vsel(zero, vbc<V>(1.0f), co.x);
+    return cc_val<V>{vmul(cx, mult), flat.y, vmul(co.z, mult), flat.w};
 }
 
 // Fused primitive (loader pattern initial_transformation_to -> [store p] -> circle|rectangle ->
 // extrusion p -> [offset] -> [transformation_from]); bit-identical to the unfused sequence.
-template <bool RECT, int PTS>
+template <bool RECT, class V, int G>
 CC_DEV void cc_prim_n(const float (&m)[12], const float (&mf)[12], float pa, float pb, float h, float d,
-                      const float (&x)[PTS], const float (&y)[PTS], const float (&z)[PTS], float4 (&L)[PTS])
+                      const V (&x)[G], const V (&y)[G], const V (&z)[G], cc_val<V> (&L)[G])
 {
-    float pz[PTS];
+    V pz[G];
 #pragma unroll
-    for (int j = 0; j < PTS; ++j) {
-        L[j] = cc_transform(m, x[j], y[j], z[j]);
-        pz[j] = L[j].z;
+    for (int g = 0; g < G; ++g) {
+        L[g] = cc_transform(m, x[g], y[g], z[g]);
+        pz[g] = L[g].z;
     }
-    if (RECT) cc_rectangle_n<PTS>(pa, pb, L);
-    else cc_circle_n<PTS>(pa, L);
-    cc_extrusion_n<PTS>(h, L, pz);
+    if (RECT) cc_rectangle_n(pa, pb, L);
+    else cc_circle_n(pa, L);
+    cc_extrusion_n(h, L, pz);
 #pragma unroll
-    for (int j = 0; j < PTS; ++j) {
-        L[j].w = L[j].w - d;
-        L[j] = cc_transform_from(mf, L[j]);
+    for (int g = 0; g < G; ++g) {
+        L[g].w = vsub(L[g].w, vbc<V>(d));
+        L[g] = cc_transform_from(mf, L[g]);
     }
 }
 
@@ -424,5 +447,96 @@ __device__ __noinline__ float4 cc_polygon2d_table(const float *table, uint32_t n
     return cc_polygon2d_core(cc_table_fetch{table}, n, co);
 }
 
+// ---- one entry point per micro-op over lane vectors (shared by the interpreter and the
+//      scene-specialised kernels).  Cheap ops are packed; the heavy, rarely dominant ones run
+//      their one-point form lane by lane. ----------------------------------------------------
+template <class V, class F>
+CC_DEV cc_val<V> cc_map1(cc_val<V> a, F f)
+{
+    cc_val<V> r;
+#pragma unroll
+    for (int l = 0; l < cc_lane<V>::N; ++l) cc_lane_put(r, l, f(cc_lane_get(a, l)));
+    return r;
+}
+template <class V, class F>
+CC_DEV cc_val<V> cc_map2(cc_val<V> a, cc_val<V> b, F f)
+{
+    cc_val<V> r;
+#pragma unroll
+    for (int l = 0; l < cc_lane<V>::N; ++l) cc_lane_put(r, l, f(cc_lane_get(a, l), cc_lane_get(b, l)));
+    return r;
+}
+
+template <class V> CC_DEV cc_val<V> cc_op_half_space(cc_val<V> a)  // simple3d.cl:14-16
+{
+    return cc_val<V>{vbc<V>(0.0f), vbc<V>(-1.0f), vbc<V>(0.0f), vneg(a.y)};
+}
+template <class V> CC_DEV cc_val<V> cc_op_rev_to(cc_val<V> a)  // simple3d.cl:23-26
+{
+    return cc_val<V>{vlen2(a.x, a.z), a.y, vbc<V>(0.0f), vbc<V>(0.0f)};
+}
+template <class V> CC_DEV cc_val<V> cc_op_shell(float d, cc_val<V> a)  // common.cl:128-131
+{
+    cc_val<V> s = cc_val_sel(vge(a.w, vbc<V>(0.0f)), a, cc_val_neg(a));
+    s.w = vsub(s.w, vbc<V>(d));
+    return s;
+}
+template <class V> CC_DEV cc_val<V> cc_op_repetition(float ox, float oy, float oz, cc_val<V> a)  // unsafe.cl:1-6
+{
+    return cc_map1(a, [&](float4 p) { return make_float4(cc_remainder(p.x, ox), cc_remainder(p.y, oy), cc_remainder(p.z, oz), 0.0f); });
+}
+template <class V> CC_DEV cc_val<V> cc_op_sym_from(cc_val<V> a, cc_val<V> point)  // common.cl:120-122
+{
+    a.x = vsel(vlt(point.x, vbc<V>(0.0f)), vneg(a.x), a.x);
+    return a;
+}
+// CSG with r < 0 (common.cl:60-76): the second operand comes from a slot
+template <class V> CC_DEV cc_val<V> cc_op_union(cc_val<V> a, cc_val<V> b) { return cc_val_sel(vlt(a.w, b.w), a, b); }
+template <class V> CC_DEV cc_val<V> cc_op_isect(cc_val<V> a, cc_val<V> b)  // -min(-a, -b)
+{
+    return cc_val_sel(vlt(vneg(a.w), vneg(b.w)), a, b);
+}
+template <class V> CC_DEV cc_val<V> cc_op_sub(cc_val<V> a, cc_val<V> b)  // -min(-a, b)
+{
+    return cc_val_sel(vlt(vneg(a.w), b.w), a, cc_val_neg(b));
+}
+template <class V> CC_DEV cc_val<V> cc_op_isect_r(float r, cc_val<V> a, cc_val<V> b)
+{
+    return cc_val_neg(cc_rounded_union(r, cc_val_neg(a), cc_val_neg(b)));
+}
+template <class V> CC_DEV cc_val<V> cc_op_sub_r(float r, cc_val<V> a, cc_val<V> b)
+{
+    return cc_val_neg(cc_rounded_union(r, cc_val_neg(a), b));
+}
+// heavy ops, lane by lane
+template <class V> CC_DEV cc_val<V> cc_op_regpoly(float k0, float k1, float k2, float k3, float k4, cc_val<V> a)
+{
+    return cc_map1(a, [&](float4 p) { return cc_regular_polygon2d(k0, k1, k2, k3, k4, p); });
+}
+template <class V> CC_DEV cc_val<V> cc_op_gear(float k0, float k1, float k2, float k3, float k4, cc_val<V> a)
+{
+    return cc_map1(a, [&](float4 p) { return cc_involute_gear(k0, k1, k2, k3, k4, p); });
+}
+template <class V> CC_DEV cc_val<V> cc_op_twist_to(float r, float twist, cc_val<V> a)
+{
+    return cc_map1(a, [&](float4 p) { return cc_twist_revolution_to(r, twist, p); });
+}
+template <class V>
+CC_DEV cc_val<V> cc_op_twist_from(float k0, float k1, float k2, float k3, float k4, cc_val<V> a, cc_val<V> point)
+{
+    return cc_map2(a, point, [&](float4 p, float4 q) { return cc_twist_revolution_from(k0, k1, k2, k3, k4, p, q); });
+}
+template <class V> CC_DEV cc_val<V> cc_op_crep_to(float a0, float a1, cc_val<V> a)
+{
+    return cc_map1(a, [&](float4 p) { return cc_circular_repetition_to(a0, a1, p); });
+}
+template <class V> CC_DEV cc_val<V> cc_op_crep_from(float a0, float a1, cc_val<V> a, cc_val<V> point)
+{
+    return cc_map2(a, point, [&](float4 p, float4 q) { return cc_circular_repetition_from(a0, a1, p, q); });
+}
+template <class V> CC_DEV cc_val<V> cc_op_polygon_table(const float *table, uint32_t n, cc_val<V> a)
+{
+    return cc_map1(a, [&](float4 p) { return cc_polygon2d_table(table, n, p); });
+}
 
 #endif

@@ -100,6 +100,17 @@ int cc_program_decode(const float *words, uint32_t n_words, cc_program_info *inf
 int cc_program_specialize(cc_program *prog, int points_per_thread, unsigned sink_mask,
                           double *compile_seconds);
 int cc_program_use_specialized(cc_program *prog, int enable); /* returns 1 if specialised code is active */
+/* Tiered execution (default): every program starts on the interpreter kernels while its
+ * specialised kernel for the sink in use compiles on a background thread (cached in memory and in
+ * $CODECAD_B200_CACHE or ~/.cache/codecad_b200); launches switch over when it is ready.  Results
+ * are bit-identical in both tiers.  mode: 0 = interpreter only, 1 = background (default),
+ * 2 = compile at first use and wait.  Environment: CODECAD_B200_JIT.  Programs with more than
+ * CODECAD_B200_JIT_MAX_OPS (512) micro-ops are only specialised on request.  Returns the old mode. */
+int cc_set_jit_mode(int mode);
+/* Blocks until the specialised kernels of the sinks in `sink_mask` (0 = all) are compiled and
+ * loaded, starting their compilation if necessary; returns how many are ready.  compile_seconds
+ * receives the background compile time spent on this program so far. */
+int cc_program_specialize_wait(cc_program *prog, unsigned sink_mask, double *compile_seconds);
 /* Host-only (no device): generate the source for `words` (returns its length, copies up to
  * `capacity` bytes incl. NUL), and optionally run NVRTC on it (compile != 0; returns the cubin
  * size through *cubin_bytes).  For tests and inspection. */

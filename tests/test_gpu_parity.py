@@ -28,8 +28,12 @@ def cb():
     import codecad_b200
     from codecad_b200 import _lib
     _lib.init(0)
+    # interpreter tier only, so that every test below knows which kernels it exercises; the
+    # specialised tier is switched on explicitly by the tests at the end of this file
+    old = _lib.check(_lib.lib().cc_set_jit_mode(0))
     yield codecad_b200
     _lib.check(_lib.lib().cc_set_tuning(0, 0))
+    _lib.check(_lib.lib().cc_set_jit_mode(old))
 
 
 def _dims_for(scene):
@@ -263,3 +267,49 @@ def test_specialized_hierarchy_matches_oracle(cb, scenes, name):
     _, want = host.subdivision(s.words, s.box_a, s.box_b, s.dimension, res, True, 8)
     got_blocks = cb.subdivision(scene, res, True, 8)[2]
     assert sorted(tuple(b[3]) for b in got_blocks) == sorted(tuple(b[3]) for b in want)
+
+
+@pytest.mark.parametrize("pts", [4])
+@pytest.mark.parametrize("name", ["cfg_planetary", "cfg_synthetic32", "dsdf2d_gear"])
+def test_specialized_four_points_per_thread(cb, scenes, name, pts):
+    from codecad_b200.cl_util.buffer import ProgramBuffer
+    s = scenes[name]
+    prog = ProgramBuffer(s.words)
+    prog.specialize(pts, ProgramBuffer.SINK_FLOAT4)
+    dims = (16, 9, 37) if s.dimension == 3 else (33, 17, 2)
+    corner, step = s.grid(40)
+    assert _same(_f4(cb.grid_eval(prog, corner, step, dims)), oracle.grid_eval(s.words, corner, step, dims))
+
+
+def test_tiered_execution_modes(cb, scenes):
+    """Default behaviour: interpreter first, specialised kernel takes over when its background
+    compile has finished; mode 2 waits at first use.  Same bits in every tier."""
+    from codecad_b200 import _lib
+    from codecad_b200.cl_util.buffer import ProgramBuffer
+    L = _lib.lib()
+    s = scenes["cfg_menger_sponge"]
+    dims = (16, 9, 37)
+    corner, step = s.grid(40)
+    want = oracle.grid_eval(s.words, corner, step, dims)
+    try:
+        assert _lib.check(L.cc_set_jit_mode(1)) == 0
+        prog = ProgramBuffer(s.words)
+        assert _same(_f4(cb.grid_eval(prog, corner, step, dims)), want)      # interpreter or specialised
+        n, secs = prog.wait_specialized(ProgramBuffer.SINK_FLOAT4)
+        assert n == 1 and secs >= 0
+        assert prog.use_specialized(True)
+        launches0, _ = _lib.counters()
+        assert _same(_f4(cb.grid_eval(prog, corner, step, dims)), want)      # specialised now
+        assert _lib.counters()[0] == launches0 + 1
+        # a second program with the same words hits the in-memory cubin cache
+        assert _lib.check(L.cc_set_jit_mode(2)) == 1
+        prog2 = ProgramBuffer(s.words)
+        assert _same(_f4(cb.grid_eval(prog2, corner, step, dims)), want)
+        assert prog2.use_specialized(True)
+        # the hierarchy drivers go through the same switch
+        a = scenes["cfg_airfoil"]
+        from oracle import host
+        vol, _, _ = host.mass_properties(a.words, a.box_a, a.box_b, 1.0, 32)
+        assert cb.mass_properties(a.compiled(), 1.0, 32).volume == pytest.approx(vol, rel=1e-12)
+    finally:
+        _lib.check(L.cc_set_jit_mode(0))

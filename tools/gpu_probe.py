@@ -37,7 +37,7 @@ def main():
         nx = n if name != "cfg_synthetic500" else max(8, n // 8)
         print("%s: %d micro-ops, %d words, %d slots, %d fused, flops %d..%d" % (
             name, pi.n_micro_ops, pi.n_micro_words, pi.n_slots, pi.n_fused, pi.flops_min, pi.flops_max))
-        for pts, space in variants:
+        for pts, space in (variants if os.environ.get("PROBE_INTERP", "1") != "0" else []):
             _lib.check(L.cc_set_tuning(pts, space))
             best = None
             for it in range(3):
@@ -62,7 +62,7 @@ def main():
                 pts, {1: "const", 2: "smem", 3: "hybrid"}[space], best, pts_s / 1e9, pts_s * pi.flops_min / peak, pts_s * 16 / 1e9))
         # scene-specialised kernel (NVRTC)
         if os.environ.get("PROBE_JIT", "1") != "0":
-            for jp in (2, 1):
+            for jp in [int(x) for x in os.environ.get("PROBE_JIT_PTS", "2,1").split(",")]:
                 _lib.check(L.cc_set_tuning(0, 0))
                 try:
                     secs = prog.specialize(jp, 1)
@@ -81,8 +81,12 @@ def main():
                     if it and (best is None or ms.value < best):
                         best = ms.value
                 pts_s = nx * n * n / (best * 1e-3)
-                print("   JIT pts=%d (compile %.1f s): %8.3f ms  %8.3f Gpts/s  fp32 frac(min flops) %.3f" % (
-                    jp, secs, best, pts_s / 1e9, pts_s * pi.flops_min / peak))
+                import zlib
+                head = np.empty((2, n, n), dtype=FLOAT4)
+                _lib.check(L.cc_memcpy_d2h_async(head.ctypes.data, out.device_ptr, head.nbytes, None))
+                _lib.check(L.cc_synchronize())
+                print("   JIT pts=%d (compile %.1f s): %8.3f ms  %8.3f Gpts/s  fp32 frac(min flops) %.3f  crc %08x" % (
+                    jp, secs, best, pts_s / 1e9, pts_s * pi.flops_min / peak, zlib.crc32(head.tobytes())))
             prog.use_specialized(False)
     _lib.check(L.cc_set_tuning(0, 0))
 
