@@ -39,6 +39,11 @@ struct Context {
     size_t status_cap = 0;
     // pinned bounce word for counters
     uint32_t *h_word = nullptr;
+    // device ring + events of cc_grid_eval_to_host, kept between calls
+    static const int kRing = 4;
+    void *ring[kRing] = {nullptr, nullptr, nullptr, nullptr};
+    size_t ring_bytes = 0;
+    cudaEvent_t ring_computed[kRing] = {}, ring_copied[kRing] = {};
 };
 Context g;
 std::mutex g_mu;
@@ -102,7 +107,7 @@ int choose_cfg(const cc_program *prog, uint64_t total_points, cc_launch_cfg *cfg
     // whenever it fits the 63 KB window; larger programs are staged in shared memory
     // 1 = constant bank, 2 = shared copy, 3 = hybrid (headers constant, parameters shared)
     int space = g.prog_space;
-    if (space == 0) space = (words * 4 <= 16384) ? 3 : 1;
+    if (space == 0) space = 1;  // hybrid (3) measured slower on B200: 2.2 vs 2.7 Gpts/s on planetary
     if (space != 2 && words > CC_CONST_WORDS) space = 2;
     // two points per thread measured best on B200 (profiles/r1_ab_variants.md): four halve the
     // resident warps without enough extra ILP to pay for it
@@ -283,6 +288,11 @@ void cc_shutdown(void)
     if (g.d_ticket) cudaFree(g.d_ticket);
     if (g.d_status) cudaFree(g.d_status);
     if (g.h_word) cudaFreeHost(g.h_word);
+    for (int i = 0; i < Context::kRing; ++i) {
+        if (g.ring[i]) cudaFree(g.ring[i]);
+        if (g.ring_computed[i]) cudaEventDestroy(g.ring_computed[i]);
+        if (g.ring_copied[i]) cudaEventDestroy(g.ring_copied[i]);
+    }
     cudaStreamDestroy(g.compute);
     cudaStreamDestroy(g.copy);
     g = Context();
@@ -607,39 +617,41 @@ int cc_grid_eval_to_host(const cc_program *prog, const float corner[3], float st
         cudaFree(d);
         return rc;
     }
-    // slabs of ~64 MiB: compute on the compute stream into a 3-deep device ring, copy out on the
-    // copy stream; a slab is re-used only after its copy has finished.
-    const int RING = 3;
+    // slabs of ~64 MiB: compute on the compute stream into a device ring (kept between calls),
+    // copy out on the copy stream; a ring entry is re-used only after its copy has finished.
+    const int RING = Context::kRing;
     uint32_t slab_x = (uint32_t)std::max<uint64_t>(1, (64ull << 20) / (plane * elem));
     slab_x = std::min(slab_x, nx);
     const size_t slab_bytes = (size_t)slab_x * plane * elem;
-    void *d_ring[RING] = {nullptr, nullptr, nullptr};
-    cudaEvent_t computed[RING], copied[RING];
-    int rc = CC_OK;
-    for (int i = 0; i < RING; ++i) {
-        CU(cudaMalloc(&d_ring[i], slab_bytes));
-        CU(cudaEventCreateWithFlags(&computed[i], cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
+    if (slab_bytes > g.ring_bytes) {
+        for (int i = 0; i < RING; ++i) {
+            if (g.ring[i]) CU(cudaFree(g.ring[i]));
+            g.ring[i] = nullptr;
+        }
+        g.ring_bytes = 0;
+        for (int i = 0; i < RING; ++i) CU(cudaMalloc(&g.ring[i], slab_bytes));
+        g.ring_bytes = slab_bytes;
     }
+    if (!g.ring_computed[0])
+        for (int i = 0; i < RING; ++i) {
+            CU(cudaEventCreateWithFlags(&g.ring_computed[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&g.ring_copied[i], cudaEventDisableTiming));
+        }
+    int rc = CC_OK;
     int slot = 0;
     for (uint32_t x0 = 0; x0 < nx && rc == CC_OK; x0 += slab_x, slot = (slot + 1) % RING) {
         uint32_t cnt = std::min(slab_x, nx - x0);
-        if (x0 >= (uint32_t)RING * slab_x) CU(cudaStreamWaitEvent(g.compute, copied[slot], 0));
-        rc = cc_grid_eval(prog, corner, step, cnt, ny, nz, x_offset + x0, layout, d_ring[slot], nullptr);
+        if (x0 >= (uint32_t)RING * slab_x) CU(cudaStreamWaitEvent(g.compute, g.ring_copied[slot], 0));
+        rc = cc_grid_eval(prog, corner, step, cnt, ny, nz, x_offset + x0, layout, g.ring[slot], nullptr);
         if (rc) break;
-        CU(cudaEventRecord(computed[slot], g.compute));
-        CU(cudaStreamWaitEvent(g.copy, computed[slot], 0));
-        CU(cudaMemcpyAsync((char *)h_out + (size_t)x0 * plane * elem, d_ring[slot], (size_t)cnt * plane * elem,
+        CU(cudaEventRecord(g.ring_computed[slot], g.compute));
+        CU(cudaStreamWaitEvent(g.copy, g.ring_computed[slot], 0));
+        CU(cudaMemcpyAsync((char *)h_out + (size_t)x0 * plane * elem, g.ring[slot], (size_t)cnt * plane * elem,
                            cudaMemcpyDeviceToHost, g.copy));
-        CU(cudaEventRecord(copied[slot], g.copy));
+        CU(cudaEventRecord(g.ring_copied[slot], g.copy));
     }
     cudaStreamSynchronize(g.compute);
     cudaError_t e = cudaStreamSynchronize(g.copy);
-    for (int i = 0; i < RING; ++i) {
-        cudaFree(d_ring[i]);
-        cudaEventDestroy(computed[i]);
-        cudaEventDestroy(copied[i]);
-    }
     if (rc == CC_OK && e != cudaSuccess) rc = cuda_fail(e, "grid_eval_to_host");
     return rc;
 }

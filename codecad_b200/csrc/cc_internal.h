@@ -22,6 +22,8 @@ struct cc_jit_cfg {
     int pts = 2;         // points per thread
     int threads = 512;   // CTA size
     int min_blocks = 2;  // __launch_bounds__ min CTAs per SM (register cap)
+    int smem_min_len = 16;   // values live for at least this many micro-ops go to shared-memory cells
+    int smem_max_cells = 0;  // budget of cells (0 = keep everything in registers)
 };
 struct cc_jit_job;
 
@@ -33,6 +35,7 @@ struct cc_program {
     void *jit_library[4] = {nullptr, nullptr, nullptr, nullptr};
     void *jit_kernel[4] = {nullptr, nullptr, nullptr, nullptr};
     cc_jit_cfg jit_cfg[4];
+    size_t jit_smem[4] = {0, 0, 0, 0};  // dynamic shared memory of each specialised kernel
     cc_jit_job *jit_job[4] = {nullptr, nullptr, nullptr, nullptr};  // background compiles in flight
     bool jit_failed[4] = {false, false, false, false};
     size_t jit_cubin_bytes = 0;

@@ -17,6 +17,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cstdio>
@@ -114,6 +115,7 @@ struct Gen {
     const std::vector<uint32_t> &code;
     std::ostringstream body, consts;
     int n_tables = 0;
+    int n_cells = 0;
 
     explicit Gen(const std::vector<uint32_t> &c) : code(c) {}
 
@@ -139,10 +141,10 @@ struct Gen {
         std::snprintf(buf, sizeof buf, "%af", (double)f);  // C++17 hexadecimal floating literal: exact
         return buf;
     }
-    static std::string S(uint32_t slot) { return "S" + std::to_string(slot); }
 };
 
-int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, std::string *src, std::string *err)
+int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, std::string *src, size_t *smem_bytes,
+             std::string *err)
 {
     const int pts = cfg.pts;
     // debugging aids: stop after N micro-ops (bisecting a mismatch), force scalar lanes
@@ -153,15 +155,102 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
     Gen g(dec.microcode);
     const std::vector<uint32_t> &c = dec.microcode;
     std::ostringstream &o = g.body;
+
+    // ---- value intervals: one per slot definition, from the storing micro-op to its last reader.
+    // Each interval becomes its own variable (the microcode is straight-line, so this is SSA).
+    // Long-lived intervals are kept in shared memory cells instead of registers: two points per
+    // thread need 8 registers per live value, and what does not fit the register cap would be
+    // spilled to local memory, i.e. through L1/L2 to DRAM.
+    struct Interval {
+        int def, last_read, cell;
+        bool z_only;  // every reader is an extrusion (needs the point's z only)
+    };
+    std::vector<Interval> iv;
+    std::vector<int> op_def, op_use;  // per micro-op: interval defined / interval read (-1 = none)
+    {
+        std::vector<int> cur(CC_SLOT_NONE + 1, -1);
+        uint32_t q = 0;
+        for (int i = 0;; ++i) {
+            if (q >= c.size()) {
+                *err = "internal: microcode without RETURN";
+                return CC_ERR_INVALID_PROGRAM;
+            }
+            const uint32_t h = c[q], op = CC_HDR_OP(h), src_slot = CC_HDR_SRC(h), dst = CC_HDR_DST(h);
+            int use = -1;
+            if (src_slot != CC_SLOT_NONE && op != MOP_RETURN) {
+                use = cur[src_slot];
+                if (use < 0) {
+                    *err = "internal: micro-op reads an undefined slot";
+                    return CC_ERR_INVALID_PROGRAM;
+                }
+                iv[use].last_read = i;
+                if (op != MOP_EXTRUSION) iv[use].z_only = false;
+            }
+            op_use.push_back(use);
+            int def = -1;
+            if (dst != CC_SLOT_NONE && op != MOP_RETURN) {
+                def = (int)iv.size();
+                iv.push_back(Interval{i, i, -1, true});
+                cur[dst] = def;
+            }
+            op_def.push_back(def);
+            if (op == MOP_RETURN) break;
+            q += CC_HDR_LEN(h);
+        }
+    }
+    int n_cells = 0;
+    {
+        // cells: longest intervals first, interval-graph colouring within the budget
+        const int min_len = cfg.smem_min_len, max_cells = cfg.smem_max_cells;
+        std::vector<int> order;
+        for (int k = 0; k < (int)iv.size(); ++k)
+            if (max_cells > 0 && iv[k].last_read - iv[k].def >= min_len) order.push_back(k);
+        std::sort(order.begin(), order.end(), [&](int a, int b) {
+            return iv[a].last_read - iv[a].def > iv[b].last_read - iv[b].def;
+        });
+        std::vector<std::vector<int>> cell_members;
+        for (int k : order) {
+            int chosen = -1;
+            for (int cidx = 0; cidx < (int)cell_members.size() && chosen < 0; ++cidx) {
+                bool clash = false;
+                for (int m : cell_members[cidx])
+                    if (!(iv[m].last_read <= iv[k].def || iv[k].last_read <= iv[m].def)) clash = true;
+                if (!clash) chosen = cidx;
+            }
+            if (chosen < 0 && (int)cell_members.size() < max_cells) {
+                cell_members.emplace_back();
+                chosen = (int)cell_members.size() - 1;
+            }
+            if (chosen >= 0) {
+                cell_members[chosen].push_back(k);
+                iv[k].cell = chosen;
+            }
+        }
+        n_cells = (int)cell_members.size();
+    }
+    g.n_cells = n_cells;
+
     uint32_t pc = 0;
-    for (;;) {
+    for (int op_index = 0;; ++op_index) {
         if (pc >= c.size()) {
             *err = "internal: microcode without RETURN";
             return CC_ERR_INVALID_PROGRAM;
         }
         const uint32_t h = c[pc], op = CC_HDR_OP(h), src_slot = CC_HDR_SRC(h), dst = CC_HDR_DST(h);
-        const std::string B = Gen::S(src_slot) + "[g]";
         o << "        // pc " << pc << "\n";
+        std::string B = "?";
+        if (op_use[op_index] >= 0) {
+            const int u = op_use[op_index];
+            const std::string name = "I" + std::to_string(u);
+            if (iv[u].cell < 0) {
+                B = name + "[g]";
+            } else {  // operand lives in a shared-memory cell: fetch what this op needs
+                B = "B" + std::to_string(op_index) + "[g]";
+                o << "        Val B" << op_index << "[G]; CC_EACH "
+                  << (op == MOP_EXTRUSION ? "cc_slot_load_z(CC_CELL(" : op == MOP_SYM_FROM ? "cc_slot_load_x(CC_CELL(" : "cc_slot_load(CC_CELL(")
+                  << iv[u].cell << ", g), " << B << (op == MOP_EXTRUSION ? ".z" : op == MOP_SYM_FROM ? ".x" : "") << ");\n";
+            }
+        }
         switch (op) {
         case MOP_RETURN: break;
         case MOP_NOP: break;
@@ -232,7 +321,18 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
         }
         if (op == MOP_RETURN) break;
         if (stop_after >= 0 && ++n_emitted > stop_after) break;
-        if (dst != CC_SLOT_NONE) o << "        CC_EACH " << Gen::S(dst) << "[g] = L[g];\n";
+        if (op_def[op_index] >= 0) {
+            const int d = op_def[op_index];
+            if (iv[d].last_read == iv[d].def) {
+                // never read: nothing to keep
+            } else if (iv[d].cell < 0) {
+                o << "        Val I" << d << "[G]; CC_EACH I" << d << "[g] = L[g];\n";
+            } else if (iv[d].z_only) {
+                o << "        CC_EACH cc_slot_store_z(CC_CELL(" << iv[d].cell << ", g), L[g].z);\n";
+            } else {
+                o << "        CC_EACH cc_slot_store(CC_CELL(" << iv[d].cell << ", g), L[g]);\n";
+            }
+        }
         pc += CC_HDR_LEN(h);
     }
 
@@ -244,10 +344,11 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
       << "#define PTS " << pts << "\n"
       << "typedef cc_pts<PTS>::V V;\nconstexpr int G = cc_pts<PTS>::G;\ntypedef cc_val<V> Val;\n"
       << "#define CC_EACH _Pragma(\"unroll\") for (int g = 0; g < G; ++g)\n"
-      << g.consts.str() << "struct SceneEval {\n"
+      << "#define CC_CELL(cell, g) (sm + ((cell) * PTS + (g) * cc_lane<V>::N) * CC_THREADS)\n"
+      << "#define CC_JIT_SMEM_BYTES " << (size_t)n_cells * pts * cfg.threads * 16 << "\n"
+      << g.consts.str() << "struct SceneEval {\n    float4 *sm;  // this thread's column of the value cells\n"
       << "    __device__ __forceinline__ void operator()(const V (&gx)[G], const V (&gy)[G], const V (&gz)[G],\n"
       << "                                               Val (&L)[G]) const\n    {\n";
-    for (uint32_t k = 0; k < dec.info.n_slots; ++k) s << "        Val S" << k << "[G];\n";
     s << "        CC_EACH L[g] = Val{vbc<V>(0.f), vbc<V>(0.f), vbc<V>(0.f), vbc<V>(0.f)};\n" << o.str() << "    }\n};\n";
     const char *names[4] = {"float4", "pymcubes", "classify", "mass"};
     const char *sinks[4] = {"CC_SINK_FLOAT4", "CC_SINK_PYMCUBES", "CC_SINK_CLASSIFY", "CC_SINK_MASS"};
@@ -257,8 +358,10 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
     for (int k = 0; k < 4; ++k)
         if (sink_mask & (1u << k))
         s << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_" << names[k]
-          << "(const cc_eval_args a)\n{\n    SceneEval e;\n    cc_kernel_body<PTS, " << sinks[k] << ">(a, e);\n}\n";
+          << "(const cc_eval_args a)\n{\n    extern __shared__ float4 cc_cells[];\n    SceneEval e{cc_cells + threadIdx.x};\n"
+          << "    cc_kernel_body<PTS, " << sinks[k] << ">(a, e);\n}\n";
     *src = s.str();
+    if (smem_bytes) *smem_bytes = (size_t)n_cells * pts * cfg.threads * 16;
     return CC_OK;
 }
 
@@ -286,6 +389,18 @@ cc_jit_cfg cc_jit_default_cfg(int pts)
     // the ordered-compaction sinks scan PTS * warps-per-CTA counters with one warp (cc_body.cuh)
     while (c.pts * (c.threads / 32) > 32) c.threads /= 2;
     if (c.min_blocks * c.threads > 2048) c.min_blocks = 2048 / c.threads;
+    // Shared-memory cells for long-lived values (instead of letting ptxas spill what exceeds the
+    // register cap to local memory).  Measured on B200, planetary 512^3, two points per thread:
+    // 0 cells 7.29 Gpts/s, 3 cells 6.87, 6 cells 6.65 (profiles/r1_jit_variants.md) — the L1-cached
+    // spills ptxas places are cheaper than whole-value cells, so the default keeps everything in
+    // registers; CODECAD_B200_JIT_SMEM_CELLS=n opts in (it removes the spill write-back traffic).
+    c.smem_max_cells = 0;
+    if (const char *t = getenv("CODECAD_B200_JIT_SMEM_CELLS")) {
+        const int ctas = c.min_blocks > 0 ? c.min_blocks : 1;
+        const int fit = (int)((220u * 1024u / ctas - 2048u) / ((size_t)c.pts * c.threads * 16));
+        c.smem_max_cells = std::max(0, std::min(fit, atoi(t)));
+    }
+    if (const char *t = getenv("CODECAD_B200_JIT_SMEM_MIN_LEN")) c.smem_min_len = atoi(t);
     return c;
 }
 
@@ -389,11 +504,11 @@ void mkdirs(const std::string &d)
 }  // namespace
 
 // source for ONE sink -> cubin, through the caches.  Host-only work: safe on a background thread.
-static int build_cubin(const cc_decoded &dec, const cc_jit_cfg &cfg, int sink, Cubin *out, bool *cached,
-                       std::string *err)
+static int build_cubin(const cc_decoded &dec, const cc_jit_cfg &cfg, int sink, Cubin *out, size_t *smem_bytes,
+                       bool *cached, std::string *err)
 {
     std::string src;
-    int rc = generate(dec, cfg, 1u << sink, &src, err);
+    int rc = generate(dec, cfg, 1u << sink, &src, smem_bytes, err);
     if (rc) return rc;
     const uint64_t key = source_key(src);
     if (cached) *cached = true;
@@ -431,7 +546,8 @@ static int build_cubin(const cc_decoded &dec, const cc_jit_cfg &cfg, int sink, C
     return CC_OK;
 }
 
-static int load_cubin(cc_program *prog, int sink, const Cubin &bin, const cc_jit_cfg &cfg, std::string *err)
+static int load_cubin(cc_program *prog, int sink, const Cubin &bin, const cc_jit_cfg &cfg, size_t smem_bytes,
+                      std::string *err)
 {
     static const char *names[4] = {"cc_jit_float4", "cc_jit_pymcubes", "cc_jit_classify", "cc_jit_mass"};
     cudaLibrary_t lib = nullptr;
@@ -447,7 +563,16 @@ static int load_cubin(cc_program *prog, int sink, const Cubin &bin, const cc_jit
         cudaLibraryUnload(lib);
         return CC_ERR_CUDA;
     }
+    if (smem_bytes > 0) {
+        ce = cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        if (ce != cudaSuccess) {
+            *err = std::string("cudaFuncSetAttribute(MaxDynamicSharedMemorySize): ") + cudaGetErrorString(ce);
+            cudaLibraryUnload(lib);
+            return CC_ERR_CUDA;
+        }
+    }
     if (prog->jit_library[sink]) cudaLibraryUnload((cudaLibrary_t)prog->jit_library[sink]);
+    prog->jit_smem[sink] = smem_bytes;
     prog->jit_library[sink] = (void *)lib;
     prog->jit_kernel[sink] = (void *)kern;
     prog->jit_cfg[sink] = cfg;
@@ -462,6 +587,7 @@ struct cc_jit_job {
     int rc = CC_OK;
     Cubin bin;
     cc_jit_cfg cfg;
+    size_t smem = 0;
     std::string err;
     double seconds = 0;
     bool cached = false;
@@ -486,8 +612,9 @@ int cc_jit_compile(cc_program *prog, int pts, unsigned sink_mask, double *second
         if (!(sink_mask & (1u << k))) continue;
         join_job(prog, k);
         Cubin bin;
-        int rc = build_cubin(prog->dec, cfg, k, &bin, nullptr, err);
-        if (rc == CC_OK) rc = load_cubin(prog, k, bin, cfg, err);
+        size_t smem = 0;
+        int rc = build_cubin(prog->dec, cfg, k, &bin, &smem, nullptr, err);
+        if (rc == CC_OK) rc = load_cubin(prog, k, bin, cfg, smem, err);
         if (rc) return rc;
     }
     prog->use_jit = true;
@@ -505,7 +632,7 @@ void cc_jit_start(cc_program *prog, int sink)
     const cc_decoded *dec = &prog->dec;  // immutable; outlives the thread (destroy joins it)
     j->th = std::thread([j, dec, sink]() {
         auto t0 = std::chrono::steady_clock::now();
-        j->rc = build_cubin(*dec, j->cfg, sink, &j->bin, &j->cached, &j->err);
+        j->rc = build_cubin(*dec, j->cfg, sink, &j->bin, &j->smem, &j->cached, &j->err);
         j->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         j->done.store(1, std::memory_order_release);
     });
@@ -522,7 +649,7 @@ int cc_jit_poll(cc_program *prog, int sink, bool wait, std::string *err)
     if (!wait && !j->done.load(std::memory_order_acquire)) return 0;
     if (j->th.joinable()) j->th.join();
     int rc = j->rc;
-    if (rc == CC_OK) rc = load_cubin(prog, sink, j->bin, j->cfg, &j->err);
+    if (rc == CC_OK) rc = load_cubin(prog, sink, j->bin, j->cfg, j->smem, &j->err);
     prog->jit_seconds += j->seconds;
     if (rc != CC_OK) {
         if (err) *err = j->err;
@@ -550,11 +677,11 @@ int cc_jit_launch(const cc_program *prog, int sink, const cc_eval_args &a, void 
     if (grid == 0) return 0;
     void *args[] = {(void *)&a};
     return (int)cudaLaunchKernel((const void *)prog->jit_kernel[sink], dim3(grid), dim3(prog->jit_cfg[sink].threads),
-                                 args, 0, (cudaStream_t)stream);
+                                 args, prog->jit_smem[sink], (cudaStream_t)stream);
 }
 
 int cc_jit_source(const cc_decoded &dec, int pts, unsigned sink_mask, std::string *src, std::string *err)
 {
     if ((sink_mask & 15u) == 0) sink_mask = 15u;
-    return generate(dec, cc_jit_default_cfg(pts), sink_mask, src, err);
+    return generate(dec, cc_jit_default_cfg(pts), sink_mask, src, nullptr, err);
 }

@@ -65,29 +65,6 @@ CC_DEV_HEAVY float4 cc_polygon2d(const Prog<MODE> &P, uint32_t pc, float4 co)
 }
 
 // ---- the interpreter ------------------------------------------------------------------------
-// Value slots in shared memory: float4 regs[slot][PTS][CC_THREADS].  A packed pair of points
-// (V = float2) occupies two consecutive float4 rows: (x0,x1,y0,y1) and (z0,z1,w0,w1).
-CC_DEV void cc_slot_store(float4 *base, const cc_val<float> &v) { base[0] = make_float4(v.x, v.y, v.z, v.w); }
-CC_DEV void cc_slot_store(float4 *base, const cc_val<float2> &v)
-{
-    base[0] = make_float4(v.x.x, v.x.y, v.y.x, v.y.y);
-    base[CC_THREADS] = make_float4(v.z.x, v.z.y, v.w.x, v.w.y);
-}
-CC_DEV void cc_slot_load(const float4 *base, cc_val<float> &v)
-{
-    const float4 f = base[0];
-    v = cc_val<float>{f.x, f.y, f.z, f.w};
-}
-CC_DEV void cc_slot_load(const float4 *base, cc_val<float2> &v)
-{
-    const float4 a = base[0], b = base[CC_THREADS];
-    v = cc_val<float2>{make_float2(a.x, a.y), make_float2(a.z, a.w), make_float2(b.x, b.y), make_float2(b.z, b.w)};
-}
-CC_DEV void cc_slot_load_x(const float4 *base, float &x) { x = base[0].x; }
-CC_DEV void cc_slot_load_x(const float4 *base, float2 &x) { x = *reinterpret_cast<const float2 *>(base); }
-CC_DEV void cc_slot_load_z(const float4 *base, float &z) { z = base[0].z; }
-CC_DEV void cc_slot_load_z(const float4 *base, float2 &z) { z = *reinterpret_cast<const float2 *>(base + CC_THREADS); }
-
 // Fused primitive (loader pattern: initial_transformation_to -> [store p] -> circle|rectangle
 // -> extrusion p -> [offset] -> [transformation_from]): one dispatch, the transformed point
 // never leaves registers.  Bit-identical to the unfused sequence (absent offset = 0, absent

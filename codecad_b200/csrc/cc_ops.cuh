@@ -513,9 +513,64 @@ template <class V> CC_DEV cc_val<V> cc_op_regpoly(float k0, float k1, float k2, 
 {
     return cc_map1(a, [&](float4 p) { return cc_regular_polygon2d(k0, k1, k2, k3, k4, p); });
 }
-template <class V> CC_DEV cc_val<V> cc_op_gear(float k0, float k1, float k2, float k3, float k4, cc_val<V> a)
+CC_DEV cc_val<float> cc_op_gear(float k0, float k1, float k2, float k3, float k4, cc_val<float> a)
 {
     return cc_map1(a, [&](float4 p) { return cc_involute_gear(k0, k1, k2, k3, k4, p); });
+}
+// shapes/gears.cl:1-42 for two points at once: the operation sequence of cc_involute_gear lane by
+// lane, arithmetic packed.  Preconditions of the unchecked division / square-root steps (operand
+// magnitudes in [2^-40, 2^60], parameters in [2^-30, 2^30]) are tested up front; anything else
+// (points on an axis, degenerate parameters) takes the one-point form, whose results are identical.
+__device__ __noinline__ cc_val<float2> cc_involute_gear2(float k0, float k1, float k2, float k3, float k4, cc_val<float2> co)
+{
+    const float baseRadius = k0, toothAngle = k1, halfTooth = k2;
+    const uint32_t lo = 0x2b800000u /* 2^-40 */, span = 0x5d800000u /* 2^60 */ - 0x2b800000u;
+    const uint32_t plo = 0x30800000u /* 2^-30 */, pspan = 0x4e800000u /* 2^30 */ - 0x30800000u;
+    const bool lanes_ok = ((__float_as_uint(co.x.x) & 0x7fffffffu) - lo) <= span &&
+                          ((__float_as_uint(co.x.y) & 0x7fffffffu) - lo) <= span &&
+                          ((__float_as_uint(co.y.x) & 0x7fffffffu) - lo) <= span &&
+                          ((__float_as_uint(co.y.y) & 0x7fffffffu) - lo) <= span;
+    const bool params_ok = (__float_as_uint(baseRadius) - plo) <= pspan && (__float_as_uint(k3) - plo) <= pspan;
+    if (__builtin_expect(!(lanes_ok && params_ok), 0))
+        return cc_map1(co, [&](float4 p) { return cc_involute_gear(k0, k1, k2, k3, k4, p); });
+    typedef float2 V;
+    const V zero = vbc<V>(0.0f);
+    const V len = vsqrt_fast(vfma(co.x, co.x, vmul(co.y, co.y)));
+    V mn_, mx_;
+    const V alpha = vatan2_fast(co.y, co.x, &mn_, &mx_);  // operands are in range (lanes_ok)
+    const V wrapped = vfmod_pos_fast(vadd(alpha, vbc<V>(CC_2PI_F)), k3);
+    const V d = vabs(vsub(wrapped, vbc<V>(toothAngle)));
+    const V involuteAlpha = vsub(vbc<V>(halfTooth), d);
+    const cc_mask2 inner = vlt(len, vbc<V>(baseRadius));
+    cc_val<V> res{zero, zero, zero, zero};
+    if (many(inner)) {
+        const V inv = vrcp_fast(len);
+        V nx = vmul(co.y, inv), ny = vneg(vmul(co.x, inv));
+        const cc_mask2 flip = vgt(wrapped, vbc<V>(toothAngle));
+        nx = vsel(flip, vneg(nx), nx);
+        ny = vsel(flip, vneg(ny), ny);
+        res = cc_val<V>{nx, ny, zero, vmul(vsub(d, vbc<V>(halfTooth)), len)};
+    }
+    if (!mall(inner)) {
+        // lanes of the inner regime get a harmless length so that they stay on the fast paths
+        const V lenO = vsel(inner, vbc<V>(2.0f * baseRadius), len);
+        const V q = vdiv_fast(vbc<V>(baseRadius), lenO);
+        V t = vfma(vneg(q), q, vbc<V>(1.0f));
+        t = vsel(vlt(t, zero), zero, t);
+        const V phi = vadd(involuteAlpha, vatan2(vsqrt(t), q));  // cc_acos
+        const V base = vsub(alpha, involuteAlpha);
+        const V normalAngle = vsel(vlt(wrapped, vbc<V>(toothAngle)), vsub(vsub(vbc<V>(CC_PI_F), phi), base), vsub(phi, base));
+        V nx, ny;
+        vsincos(normalAngle, &nx, &ny);
+        const V distance = vfma(vbc<V>(-baseRadius), phi, vsqrt(vfma(lenO, lenO, vbc<V>(-k4))));
+        const cc_val<V> outer{nx, ny, zero, distance};
+        res = cc_val_sel(inner, res, outer);
+    }
+    return res;
+}
+CC_DEV cc_val<float2> cc_op_gear(float k0, float k1, float k2, float k3, float k4, cc_val<float2> a)
+{
+    return cc_involute_gear2(k0, k1, k2, k3, k4, a);
 }
 template <class V> CC_DEV cc_val<V> cc_op_twist_to(float r, float twist, cc_val<V> a)
 {
@@ -538,5 +593,33 @@ template <class V> CC_DEV cc_val<V> cc_op_polygon_table(const float *table, uint
 {
     return cc_map1(a, [&](float4 p) { return cc_polygon2d_table(table, n, p); });
 }
+
+// ---- shared-memory value slots (interpreter) / value cells (specialised kernels) ----
+// Value slots in shared memory: float4 regs[slot][PTS][CC_THREADS].  A packed pair of points
+// (V = float2) occupies two consecutive float4 rows: (x0,x1,y0,y1) and (z0,z1,w0,w1).
+CC_DEV void cc_slot_store(float4 *base, const cc_val<float> &v) { base[0] = make_float4(v.x, v.y, v.z, v.w); }
+CC_DEV void cc_slot_store(float4 *base, const cc_val<float2> &v)
+{
+    base[0] = make_float4(v.x.x, v.x.y, v.y.x, v.y.y);
+    base[CC_THREADS] = make_float4(v.z.x, v.z.y, v.w.x, v.w.y);
+}
+CC_DEV void cc_slot_load(const float4 *base, cc_val<float> &v)
+{
+    const float4 f = base[0];
+    v = cc_val<float>{f.x, f.y, f.z, f.w};
+}
+CC_DEV void cc_slot_load(const float4 *base, cc_val<float2> &v)
+{
+    const float4 a = base[0], b = base[CC_THREADS];
+    v = cc_val<float2>{make_float2(a.x, a.y), make_float2(a.z, a.w), make_float2(b.x, b.y), make_float2(b.z, b.w)};
+}
+CC_DEV void cc_slot_load_x(const float4 *base, float &x) { x = base[0].x; }
+CC_DEV void cc_slot_load_x(const float4 *base, float2 &x) { x = *reinterpret_cast<const float2 *>(base); }
+CC_DEV void cc_slot_load_z(const float4 *base, float &z) { z = base[0].z; }
+CC_DEV void cc_slot_load_z(const float4 *base, float2 &z) { z = *reinterpret_cast<const float2 *>(base + CC_THREADS); }
+// store only the z component (cells whose every reader is an extrusion)
+CC_DEV void cc_slot_store_z(float4 *base, float z) { reinterpret_cast<float *>(base)[2] = z; }
+CC_DEV void cc_slot_store_z(float4 *base, float2 z) { *reinterpret_cast<float2 *>(base + CC_THREADS) = z; }
+
 
 #endif
