@@ -48,7 +48,10 @@ struct Nvrtc {
     int (*GetCUBIN)(nvrtcProgram, char *);
     int (*DestroyProgram)(nvrtcProgram *);
     const char *(*GetErrorString)(int);
+    int (*Version)(int *, int *);
 };
+
+std::mutex g_nvrtc_mu;
 
 bool load_nvrtc(Nvrtc *n, std::string *err)
 {
@@ -57,11 +60,30 @@ bool load_nvrtc(Nvrtc *n, std::string *err)
         *n = cached;
         return true;
     }
-    const char *names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12",
-                           "/usr/local/cuda/lib64/libnvrtc.so"};
+    // Candidates: $CODECAD_B200_NVRTC, the CUDA toolkit's copy, whatever the loader finds by name.
+    // A process that imported PyTorch resolves "libnvrtc.so.12" to torch's bundled (older) NVRTC,
+    // whose code generator does not fold negations into the packed FFMA2 operands (+10 % executed
+    // instructions on the planetary scene), so the newest version among the candidates wins.
+    std::vector<std::string> names;
+    if (const char *e = getenv("CODECAD_B200_NVRTC")) names.push_back(e);
+    if (const char *e = getenv("CUDA_HOME")) names.push_back(std::string(e) + "/lib64/libnvrtc.so.12");
+    names.push_back("/usr/local/cuda/lib64/libnvrtc.so.12");
+    names.push_back("/usr/local/cuda/lib64/libnvrtc.so");
+    names.push_back("libnvrtc.so.12");
+    names.push_back("libnvrtc.so");
     void *h = nullptr;
-    for (const char *nm : names)
-        if ((h = dlopen(nm, RTLD_NOW | RTLD_LOCAL))) break;
+    int best = -1;
+    for (const std::string &nm : names) {
+        void *cand = dlopen(nm.c_str(), RTLD_NOW | RTLD_LOCAL);
+        if (!cand) continue;
+        int major = 0, minor = 0;
+        int (*ver)(int *, int *) = (int (*)(int *, int *))dlsym(cand, "nvrtcVersion");
+        if (ver) ver(&major, &minor);
+        if (major * 100 + minor > best) {
+            best = major * 100 + minor;
+            h = cand;
+        }
+    }
     if (!h) {
         *err = "NVRTC (libnvrtc.so.12) not found: scene-specialised kernels unavailable";
         return false;
@@ -82,6 +104,7 @@ bool load_nvrtc(Nvrtc *n, std::string *err)
     SYM(GetCUBIN, "nvrtcGetCUBIN")
     SYM(DestroyProgram, "nvrtcDestroyProgram")
     SYM(GetErrorString, "nvrtcGetErrorString")
+    SYM(Version, "nvrtcVersion")
 #undef SYM
     cached = r;
     *n = r;
@@ -408,8 +431,7 @@ int cc_jit_nvrtc(const std::string &src, std::vector<char> *cubin, std::string *
 {
     Nvrtc n;
     {
-        static std::mutex mu;  // dlopen + symbol table are set up once
-        std::lock_guard<std::mutex> lk(mu);
+        std::lock_guard<std::mutex> lk(g_nvrtc_mu);  // dlopen + symbol table are set up once
         if (!load_nvrtc(&n, err)) return CC_ERR_CUDA;
     }
     const char *hdr_names[] = {"cc_device_types.h", "cc_math.cuh", "cc_ops.cuh", "cc_body.cuh"};
@@ -444,6 +466,15 @@ int cc_jit_nvrtc(const std::string &src, std::vector<char> *cubin, std::string *
     cubin->resize(sz);
     n.GetCUBIN(p, cubin->data());
     n.DestroyProgram(&p);
+    if (const char *dump = getenv("CODECAD_B200_JIT_DUMP")) {  // debugging: keep source + cubin
+        std::ofstream(std::string(dump) + "/cc_scene.cu") << src;
+        std::ofstream(std::string(dump) + "/cc_scene.cubin", std::ios::binary).write(cubin->data(), (std::streamsize)sz);
+        int major = 0, minor = 0;
+        if (n.Version) n.Version(&major, &minor);
+        Dl_info info;
+        std::fprintf(stderr, "libcodecad_b200: NVRTC %d.%d from %s\n", major, minor,
+                     (dladdr((void *)n.CreateProgram, &info) && info.dli_fname) ? info.dli_fname : "?");
+    }
     return CC_OK;
 }
 
@@ -476,7 +507,14 @@ uint64_t source_key(const std::string &src)
         std::string t;
         if (read_file(dir + n, &t)) h = fnv1a(h, t);
     }
-    return fnv1a(h, "sm_100a -fmad=false c++17 lineinfo v2");
+    Nvrtc n;
+    std::string err;
+    int major = 0, minor = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_nvrtc_mu);
+        if (load_nvrtc(&n, &err) && n.Version) n.Version(&major, &minor);
+    }
+    return fnv1a(h, "sm_100a -fmad=false c++17 lineinfo nvrtc " + std::to_string(major) + "." + std::to_string(minor));
 }
 
 std::string cache_dir()

@@ -18,6 +18,7 @@ jit = int(sys.argv[6]) if len(sys.argv) > 6 else 0
 L = _lib.init(0)
 s = load_scenes()[name]
 prog = s.compiled().program_buffer()
+_lib.check(L.cc_set_jit_mode(0))   # profile exactly the tier asked for
 if jit:
     print("compile %.2f s" % prog.specialize(jit, 1))
 corner, step = s.grid(n)
