@@ -166,6 +166,22 @@ struct Gen {
     }
 };
 
+// experiments: CODECAD_B200_JIT_DEFINES="A=1,B=0" -> "#define A 1\n#define B 0\n" ahead of the headers
+std::string extra_defines()
+{
+    std::string out;
+    const char *e = getenv("CODECAD_B200_JIT_DEFINES");
+    if (!e) return out;
+    std::stringstream ss(e);
+    std::string item;
+    while (std::getline(ss, item, ',')) {
+        size_t k = item.find('=');
+        if (k == std::string::npos) out += "#define " + item + " 1\n";
+        else out += "#define " + item.substr(0, k) + " " + item.substr(k + 1) + "\n";
+    }
+    return out;
+}
+
 int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, std::string *src, size_t *smem_bytes,
              std::string *err)
 {
@@ -362,7 +378,7 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
     std::ostringstream s;
     s << "// generated by libcodecad_b200 (cc_jit.cpp) from " << dec.info.n_micro_ops << " micro-ops\n"
       << "#define CC_THREADS " << cfg.threads << "\n"
-      << (no_pack ? "#define CC_OPT_PACKED 0\n" : "")
+      << (no_pack ? "#define CC_OPT_PACKED 0\n" : "") << extra_defines()
       << "#include \"cc_ops.cuh\"\n#include \"cc_body.cuh\"\n"
       << "#define PTS " << pts << "\n"
       << "typedef cc_pts<PTS>::V V;\nconstexpr int G = cc_pts<PTS>::G;\ntypedef cc_val<V> Val;\n"

@@ -521,7 +521,15 @@ CC_DEV cc_val<float> cc_op_gear(float k0, float k1, float k2, float k3, float k4
 // lane, arithmetic packed.  Preconditions of the unchecked division / square-root steps (operand
 // magnitudes in [2^-40, 2^60], parameters in [2^-30, 2^30]) are tested up front; anything else
 // (points on an axis, degenerate parameters) takes the one-point form, whose results are identical.
-__device__ __noinline__ cc_val<float2> cc_involute_gear2(float k0, float k1, float k2, float k3, float k4, cc_val<float2> co)
+#ifndef CC_OPT_GEAR_INLINE
+#define CC_OPT_GEAR_INLINE 0
+#endif
+#if CC_OPT_GEAR_INLINE
+CC_DEV
+#else
+__device__ __noinline__
+#endif
+cc_val<float2> cc_involute_gear2(float k0, float k1, float k2, float k3, float k4, cc_val<float2> co)
 {
     const float baseRadius = k0, toothAngle = k1, halfTooth = k2;
     const uint32_t lo = 0x2b800000u /* 2^-40 */, span = 0x5d800000u /* 2^60 */ - 0x2b800000u;
