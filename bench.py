@@ -216,6 +216,40 @@ def run_reference(args):
     return 0
 
 
+def mass_properties_leg():
+    """Second half of BASELINE.json's metric ("mass_properties ms vs host CL"): configs[2], the
+    airfoil scene, volume/centroid/inertia at resolution 0.25 with 64^3 blocks, wall clock
+    through the public codecad_b200.mass_properties() call (program cached, result on the host);
+    beside it the CPU oracle driving the reference's host algorithm on the box's cores."""
+    import codecad_b200
+    from codecad_b200.cl_util.buffer import ProgramBuffer
+    from oracle import host
+    from scenes import load_scenes
+    a = load_scenes()["cfg_airfoil"]
+    scene = a.compiled()
+    res, grid = 0.25, 64
+    t0 = time.perf_counter()
+    first = codecad_b200.mass_properties(scene, res, grid)          # interpreter tier (compile in background)
+    first_ms = (time.perf_counter() - t0) * 1e3
+    n_ready, _ = scene.program_buffer().wait_specialized(ProgramBuffer.SINK_MASS)
+    times = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        got = codecad_b200.mass_properties(scene, res, grid)
+        times.append((time.perf_counter() - t0) * 1e3)
+    t0 = time.perf_counter()
+    vol, cen, _ = host.mass_properties(a.words, a.box_a, a.box_b, res, grid)
+    cpu_ms = (time.perf_counter() - t0) * 1e3
+    import oracle
+    return {"workload": "examples/airfoil.py mass_properties(resolution=0.25, grid_size=64)",
+            "ms": sorted(times)[len(times) // 2], "ms_best": min(times), "ms_first_call_interpreter_tier": first_ms,
+            "tier": "specialised" if n_ready else "interpreter",
+            "cpu_ms": cpu_ms, "cpu_cores": oracle.num_threads(), "cpu_kind": "port",
+            "volume": got.volume, "volume_rel_diff_vs_cpu": abs(got.volume - vol) / vol,
+            "centroid_abs_diff_vs_cpu": max(abs(g - w) for g, w in zip(got.centroid, cen)),
+            "first_equals_steady": first.volume == got.volume}
+
+
 def workload_config(n, world):
     return {
         "workload": "examples/planetary.py Planetary(11,60,13,41,18,53).make_assembly().shape(): "
@@ -383,13 +417,20 @@ def run_ours(args):
         r = cpu_sample_run(scene, n, 12.0, 1, "auto")
         cpu = {"value": r["value"], "unit": "Gpts/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
 
+    mass = None
+    if world == 1 and not args.no_cpu:
+        try:
+            mass = mass_properties_leg()
+        except Exception as exc:  # noqa: BLE001
+            mass = {"error": str(exc)[:200]}
+
     line = {
         "metric": METRIC, "value": value, "unit": "Gpts/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(n, world), "clocks": clk, "e2e": e2e,
         "gpu_launches": launches_total, "roofline": roofline, "cpu_baseline": cpu,
-        "tier": tier, "specialize_s": specialize_s, "interpreter_tier": interp,
+        "tier": tier, "specialize_s": specialize_s, "interpreter_tier": interp, "mass_properties": mass,
         "device": info.name.decode(),
     }
     print(json.dumps(line))
