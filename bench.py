@@ -250,6 +250,35 @@ def mass_properties_leg():
             "first_equals_steady": first.volume == got.volume}
 
 
+def subdivision_leg():
+    """configs[1]: examples/csg_example.py adaptive subdivision at 512^3 effective resolution
+    (resolution = 100/512) with 16^3 blocks (11 936 leaf blocks); wall clock of
+    the public codecad_b200.subdivision() call against the CPU oracle's host algorithm."""
+    import codecad_b200
+    from codecad_b200.cl_util.buffer import ProgramBuffer
+    from oracle import host
+    from scenes import load_scenes
+    c = load_scenes()["cfg_csg_example"]
+    scene = c.compiled()
+    res, grid = 100.0 / 512, 16
+    codecad_b200.subdivision(scene, res, True, grid)
+    n_ready, _ = scene.program_buffer().wait_specialized(ProgramBuffer.SINK_CLASSIFY)
+    times = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        blocks = codecad_b200.subdivision(scene, res, True, grid)[2]
+        times.append((time.perf_counter() - t0) * 1e3)
+    t0 = time.perf_counter()
+    _, want = host.subdivision(c.words, c.box_a, c.box_b, c.dimension, res, True, grid)
+    cpu_ms = (time.perf_counter() - t0) * 1e3
+    import oracle
+    same = sorted(tuple(b[3]) for b in blocks) == sorted(tuple(b[3]) for b in want)
+    return {"workload": "examples/csg_example.py subdivision(resolution=100/512, grid_size=16)",
+            "ms": sorted(times)[len(times) // 2], "ms_best": min(times), "leaf_blocks": len(blocks),
+            "tier": "specialised" if n_ready else "interpreter", "cpu_ms": cpu_ms, "cpu_cores": oracle.num_threads(),
+            "cpu_kind": "port", "leaf_blocks_identical_to_cpu": bool(same)}
+
+
 def workload_config(n, world):
     return {
         "workload": "examples/planetary.py Planetary(11,60,13,41,18,53).make_assembly().shape(): "
@@ -417,12 +446,16 @@ def run_ours(args):
         r = cpu_sample_run(scene, n, 12.0, 1, "auto")
         cpu = {"value": r["value"], "unit": "Gpts/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
 
-    mass = None
+    mass = subdiv = None
     if world == 1 and not args.no_cpu:
         try:
             mass = mass_properties_leg()
         except Exception as exc:  # noqa: BLE001
             mass = {"error": str(exc)[:200]}
+        try:
+            subdiv = subdivision_leg()
+        except Exception as exc:  # noqa: BLE001
+            subdiv = {"error": str(exc)[:200]}
 
     line = {
         "metric": METRIC, "value": value, "unit": "Gpts/s", "n_gpus": world, "steps": args.steps,
@@ -430,7 +463,7 @@ def run_ours(args):
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(n, world), "clocks": clk, "e2e": e2e,
         "gpu_launches": launches_total, "roofline": roofline, "cpu_baseline": cpu,
-        "tier": tier, "specialize_s": specialize_s, "interpreter_tier": interp, "mass_properties": mass,
+        "tier": tier, "specialize_s": specialize_s, "interpreter_tier": interp, "mass_properties": mass, "subdivision": subdiv,
         "device": info.name.decode(),
     }
     print(json.dumps(line))

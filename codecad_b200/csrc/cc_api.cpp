@@ -267,6 +267,16 @@ int cc_init(int device)
     CU(cudaStreamCreateWithFlags(&g.compute, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&g.copy, cudaStreamNonBlocking));
     CU(cudaMallocHost(&g.h_word, 64));
+    {
+        // keep freed work-list memory in the pool instead of returning it to the driver at every sync
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        } else {
+            cudaGetLastError();
+        }
+    }
     g.device = device;
     g.ready = true;
     const char *p = getenv("CODECAD_B200_PTS");
@@ -705,15 +715,17 @@ namespace {
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
-    ~DevBuf() { if (p) cudaFree(p); }
+    // stream-ordered allocations from the device's default pool (kept warm: cc_init raises the
+    // release threshold), all on the compute stream like every user of these buffers
+    ~DevBuf() { if (p) cudaFreeAsync(p, g.compute); }
     int reserve(size_t bytes)
     {
         if (bytes <= cap) return CC_OK;
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, g.compute);
         p = nullptr;
         cap = 0;
-        cudaError_t e = cudaMalloc(&p, bytes);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc (hierarchy work list)");
+        cudaError_t e = cudaMallocAsync(&p, bytes, g.compute);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync (hierarchy work list)");
         cap = bytes;
         return CC_OK;
     }
