@@ -959,3 +959,116 @@ int cc_mass_properties(const cc_program *prog, const double box_a[3], double res
 }
 
 }  // extern "C"
+
+// ---- mesh export: marching cubes over leaf blocks --------------------------------------------------------
+
+extern "C" {
+
+int cc_mesh_blocks(const cc_program *prog, const double *corners, double resolution, uint32_t nx, uint32_t ny,
+                   uint32_t nz, uint32_t n_blocks, double **out_vertices, uint32_t **out_triangle_block,
+                   uint64_t *out_triangles)
+{
+    NEED_INIT();
+    if (!prog || !corners || !out_vertices || !out_triangle_block || !out_triangles)
+        return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
+    if (nx < 2 || ny < 2 || nz < 2) return fail(CC_ERR_INVALID_ARGUMENT, "marching cubes needs at least 2 samples per axis");
+    const uint64_t cells = (uint64_t)nx * ny * nz;
+    if (cells > (1ull << 30)) return fail(CC_ERR_INVALID_ARGUMENT, "block too large");
+    *out_vertices = nullptr;
+    *out_triangle_block = nullptr;
+    *out_triangles = 0;
+    if (n_blocks == 0) return CC_OK;
+    static bool tables_uploaded = false;
+    if (!tables_uploaded) {
+        int e = cc_mesh_upload_tables(g.compute);
+        if (e) return cuda_fail((cudaError_t)e, "marching-cubes tables");
+        tables_uploaded = true;
+    }
+    std::vector<double> h_vertices;
+    std::vector<uint32_t> h_blocks;
+    DevBuf field, descs, d_corner, counter, d_vertices, d_tri_block;
+    int rc;
+    if ((rc = counter.reserve(4))) return rc;
+    // blocks per chunk: keep the field buffer around 1 GiB
+    const uint32_t chunk = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_blocks, (1ull << 28) / cells));
+    std::vector<cc_block_desc> h_desc(chunk);
+    const float step = (float)resolution;  // numpy.float32(box_resolution), rendering/mesh.py:58
+    for (uint32_t b0 = 0; b0 < n_blocks; b0 += chunk) {
+        const uint32_t nb = std::min(chunk, n_blocks - b0);
+        if ((rc = field.reserve((size_t)nb * cells * 4))) return rc;
+        if ((rc = descs.reserve((size_t)nb * sizeof(cc_block_desc)))) return rc;
+        if ((rc = d_corner.reserve((size_t)nb * 3 * sizeof(double)))) return rc;
+        for (uint32_t b = 0; b < nb; ++b) {  // Vector.as_float4(): float64 -> float32 per block
+            const double *c = corners + 3 * (size_t)(b0 + b);
+            h_desc[b] = cc_block_desc{(float)c[0], (float)c[1], (float)c[2], 0u};
+        }
+        CU(cudaMemcpyAsync(descs.p, h_desc.data(), (size_t)nb * sizeof(cc_block_desc), cudaMemcpyHostToDevice, g.compute));
+        CU(cudaMemcpyAsync(d_corner.p, corners + 3 * (size_t)b0, (size_t)nb * 3 * sizeof(double), cudaMemcpyHostToDevice,
+                           g.compute));
+        CU(cudaStreamSynchronize(g.compute));  // h_desc is reused by the next chunk
+        cc_eval_args a;
+        fill_common(&a, prog);
+        a.step = step;
+        a.nx = nx; a.ny = ny; a.nz = nz; a.n_blocks = nb;
+        a.blocks = descs.as<cc_block_desc>();
+        a.out = field.p;
+        if ((rc = launch(CC_SINK_PYMCUBES, prog, a, (uint64_t)nb * cells))) return rc;
+
+        cc_mesh_args m;
+        std::memset(&m, 0, sizeof(m));
+        m.field = field.as<float>();
+        m.d0 = nx; m.d1 = ny; m.d2 = nz;  // numpy.empty(max_box_size): the array shape mcubes sees
+        m.n_blocks = nb;
+        m.tiles_per_block = cc_mesh_tiles_per_block(nx, ny, nz);
+        m.corner = d_corner.as<double>();
+        m.resolution = resolution;
+        m.counter = counter.as<uint32_t>();
+        m.first_block = b0;
+        CU(cudaMemsetAsync(counter.p, 0, 4, g.compute));
+        int e = cc_launch_mesh(m, false, g.compute);
+        if (e) return cuda_fail((cudaError_t)e, "marching cubes (count)");
+        g.launches += 1;
+        uint32_t n_tri = 0;
+        if ((rc = read_counter(counter.as<uint32_t>(), &n_tri))) return rc;
+        if (n_tri == 0) continue;
+        const uint64_t tiles = (uint64_t)m.tiles_per_block * nb;
+        if ((rc = ensure_status((size_t)tiles))) return rc;
+        if ((rc = d_vertices.reserve((size_t)n_tri * 9 * sizeof(double)))) return rc;
+        if ((rc = d_tri_block.reserve((size_t)n_tri * 4))) return rc;
+        CU(cudaMemsetAsync(g.d_ticket, 0, 4, g.compute));
+        CU(cudaMemsetAsync(g.d_status, 0, (size_t)tiles * sizeof(unsigned long long), g.compute));
+        CU(cudaMemsetAsync(counter.p, 0, 4, g.compute));
+        m.ticket = g.d_ticket;
+        m.tile_status = g.d_status;
+        m.vertices = d_vertices.as<double>();
+        m.tri_block = d_tri_block.as<uint32_t>();
+        e = cc_launch_mesh(m, true, g.compute);
+        if (e) return cuda_fail((cudaError_t)e, "marching cubes (emit)");
+        g.launches += 1;
+        const size_t old = h_blocks.size();
+        h_vertices.resize((old + n_tri) * 9);
+        h_blocks.resize(old + n_tri);
+        CU(cudaMemcpyAsync(h_vertices.data() + old * 9, d_vertices.p, (size_t)n_tri * 9 * sizeof(double),
+                           cudaMemcpyDeviceToHost, g.compute));
+        CU(cudaMemcpyAsync(h_blocks.data() + old, d_tri_block.p, (size_t)n_tri * 4, cudaMemcpyDeviceToHost, g.compute));
+        CU(cudaStreamSynchronize(g.compute));
+    }
+    const size_t n = h_blocks.size();
+    *out_triangles = n;
+    if (n) {
+        double *v = (double *)malloc(n * 9 * sizeof(double));
+        uint32_t *b = (uint32_t *)malloc(n * sizeof(uint32_t));
+        if (!v || !b) {
+            free(v);
+            free(b);
+            return fail(CC_ERR_INVALID_ARGUMENT, "out of host memory");
+        }
+        std::memcpy(v, h_vertices.data(), n * 9 * sizeof(double));
+        std::memcpy(b, h_blocks.data(), n * sizeof(uint32_t));
+        *out_vertices = v;
+        *out_triangle_block = b;
+    }
+    return CC_OK;
+}
+
+}  // extern "C"

@@ -92,4 +92,24 @@ int cc_launch_mass_integrals(const double *d_corners, const uint32_t *d_sums, ui
                              double *d_integrals /* [10] accumulated with Kahan, single CTA */,
                              void *stream);
 
+// ---- marching cubes over leaf blocks (cc_mesh.cu) ---------------------------------------------
+struct cc_mesh_args {
+    const float *field;    // [n_blocks][d0*d1*d2], the array mcubes would receive: index (i*d1 + j)*d2 + k
+    uint32_t d0, d1, d2;   // its numpy shape (the reference passes max_box_size, rendering/mesh.py:20)
+    uint32_t n_blocks;
+    uint32_t tiles_per_block;
+    const double *corner;  // [n_blocks][3] box_corner (float64)
+    double resolution;     // box_resolution (float64)
+    uint32_t *counter;     // running number of triangles
+    double *vertices;      // [n_triangles][3 vertices][3]  (emit pass)
+    uint32_t *tri_block;   // [n_triangles] block of every triangle (emit pass)
+    uint32_t first_block;  // added to the block index written to tri_block
+    uint32_t *ticket;
+    unsigned long long *tile_status;
+};
+
+int cc_mesh_upload_tables(void *stream);
+uint32_t cc_mesh_tiles_per_block(uint32_t d0, uint32_t d1, uint32_t d2);
+int cc_launch_mesh(const cc_mesh_args &a, bool emit, void *stream);
+
 #endif

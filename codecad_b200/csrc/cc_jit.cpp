@@ -450,17 +450,18 @@ int cc_jit_nvrtc(const std::string &src, std::vector<char> *cubin, std::string *
         std::lock_guard<std::mutex> lk(g_nvrtc_mu);  // dlopen + symbol table are set up once
         if (!load_nvrtc(&n, err)) return CC_ERR_CUDA;
     }
-    const char *hdr_names[] = {"cc_device_types.h", "cc_math.cuh", "cc_ops.cuh", "cc_body.cuh"};
-    std::string hdr_src[4];
+    const char *hdr_names[] = {"cc_device_types.h", "cc_math.cuh", "cc_ops.cuh", "cc_body.cuh", "cc_scan.cuh"};
+    std::string hdr_src[5];
     const std::string dir = source_dir();
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 5; ++i)
         if (!read_file(dir + hdr_names[i], &hdr_src[i])) {
             *err = "cannot read " + dir + hdr_names[i] + " (needed to specialise kernels)";
             return CC_ERR_INVALID_ARGUMENT;
         }
-    const char *hdr_ptrs[4] = {hdr_src[0].c_str(), hdr_src[1].c_str(), hdr_src[2].c_str(), hdr_src[3].c_str()};
+    const char *hdr_ptrs[5] = {hdr_src[0].c_str(), hdr_src[1].c_str(), hdr_src[2].c_str(), hdr_src[3].c_str(),
+                               hdr_src[4].c_str()};
     nvrtcProgram p = nullptr;
-    int e = n.CreateProgram(&p, src.c_str(), "cc_scene.cu", 4, hdr_ptrs, hdr_names);
+    int e = n.CreateProgram(&p, src.c_str(), "cc_scene.cu", 5, hdr_ptrs, hdr_names);
     if (e) {
         *err = std::string("nvrtcCreateProgram: ") + n.GetErrorString(e);
         return CC_ERR_CUDA;
@@ -517,7 +518,7 @@ uint64_t source_key(const std::string &src)
 {
     uint64_t h = 14695981039346656037ull;
     h = fnv1a(h, src);
-    const char *hdr_names[] = {"cc_device_types.h", "cc_math.cuh", "cc_ops.cuh", "cc_body.cuh"};
+    const char *hdr_names[] = {"cc_device_types.h", "cc_math.cuh", "cc_ops.cuh", "cc_body.cuh", "cc_scan.cuh"};
     const std::string dir = source_dir();
     for (const char *n : hdr_names) {
         std::string t;

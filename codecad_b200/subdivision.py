@@ -115,10 +115,9 @@ def subdivision(shape, resolution, overlap_edge_samples=True, grid_size=None, ra
     corners = subdivide_int_corners(program_buffer, box.a, resolution, block_sizes, dimension, rank, world)
     leaf_step_int, leaf_dims = block_sizes[-1]
     leaf_step = leaf_step_int * resolution
-    final_blocks = []
-    for ix, iy, iz in corners.tolist():
-        int_pos = Vector(ix, iy, iz)
-        # subdivision.py:101  pos = int_pos * resolution + origin   (float64)
-        pos = int_pos * resolution + box.a
-        final_blocks.append((leaf_dims, pos, leaf_step, int_pos, leaf_step_int))
+    # subdivision.py:101  pos = int_pos * resolution + origin   (float64, same two IEEE operations
+    # per axis as the reference's Vector arithmetic, vectorised; tuples built with _make)
+    pos = (corners * float(resolution) + np.array([box.a.x, box.a.y, box.a.z], dtype=np.float64)).tolist()
+    mk = Vector._make
+    final_blocks = [(leaf_dims, mk(p), leaf_step, mk(i), leaf_step_int) for p, i in zip(pos, corners.tolist())]
     return program_buffer, leaf_dims, final_blocks

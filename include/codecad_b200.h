@@ -185,6 +185,19 @@ int cc_mass_properties(const cc_program *prog, const double box_a[3], double res
                        const cc_level *levels, uint32_t n_levels,
                        uint32_t rank, uint32_t world, double integrals[10], uint64_t stats[4]);
 
+/* ---- mesh export: replaces the per-block loop of rendering/mesh.py:36-74
+ * (grid_eval_pymcubes launch + blocking device->host copy + mcubes.marching_cubes on the CPU).
+ * For each of the n_blocks equally sized leaf blocks (nx,ny,nz samples, float64 corners[n][3] =
+ * box_corner, rounded to fp32 per block like Vector.as_float4()): evaluate the distance field in
+ * the PyMCubes layout on the device, run marching cubes at isovalue 0 (PyMCubes 0.0.6 conventions,
+ * vertices interpolated in float64) and apply the reference's post-transform (mesh.py:68-72: swap
+ * x/y, negate y, scale by `resolution`, translate by the corner, flip the winding).  Returns a
+ * triangle soup in world coordinates: malloc'ed vertices[n_triangles][3][3] (float64) and the block
+ * index of every triangle, blocks in input order, cells in (i,j,k) order; release with cc_free. */
+int cc_mesh_blocks(const cc_program *prog, const double *corners, double resolution,
+                   uint32_t nx, uint32_t ny, uint32_t nz, uint32_t n_blocks,
+                   double **out_vertices, uint32_t **out_triangle_block, uint64_t *out_triangles);
+
 void cc_free(void *p);
 
 #ifdef __cplusplus

@@ -1,0 +1,85 @@
+"""Mesh export on the GPU (cc_mesh_blocks behind codecad_b200.rendering.triangular_mesh) against the
+CPU restatement of rendering/mesh.py:53-72 (oracle/mc_oracle.py): bit-exact float64 triangles on the
+same blocks, plus the reference's own criterion, watertightness (tests/test_mesh.py:12-29; shapes
+box(10) and sphere(10), grid sizes 2 / 12 / 16)."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import host, mc_oracle as mc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cb():
+    import codecad_b200
+    from codecad_b200 import _lib
+    _lib.init(0)
+    return codecad_b200
+
+
+def _oracle_pieces(scene, grid_size):
+    """The reference's loop with the CPU oracle in place of OpenCL and of mcubes."""
+    res = scene.feature_size / 2
+    if grid_size is None:
+        grid_size = 128
+    dims, blocks = host.subdivision(scene.words, scene.box_a, scene.box_b, scene.dimension, res, True, grid_size)
+    pieces = []
+    for box_size, box_corner, box_resolution, *_ in blocks:
+        corner32 = np.array(box_corner, np.float64).astype(np.float32)
+        field = oracle.grid_eval_pymcubes(scene.words, corner32, np.float32(box_resolution), box_size)
+        # the reference hands mcubes the flat buffer viewed with shape max_box_size (mesh.py:20)
+        block = field.reshape(-1).reshape(tuple(int(d) for d in dims))
+        soup = mc.block_mesh(block, box_corner, box_resolution)
+        if len(soup):
+            pieces.append(soup)
+    return pieces
+
+
+@pytest.mark.parametrize("grid_size", [2, 12, 16])
+@pytest.mark.parametrize("name", ["sub_box10", "dsdf3d_sphere"])
+def test_triangles_bit_exact_and_watertight(cb, scenes, name, grid_size):
+    from codecad_b200.rendering import triangular_mesh
+    s = scenes[name]
+    got = [np.asarray(v, np.float64).reshape(-1, 3, 3) for v, _ in triangular_mesh(s.compiled(), grid_size)]
+    want = _oracle_pieces(s, grid_size)
+    assert len(got) == len(want) and len(got) > 0
+    for g, w in zip(got, want):
+        assert g.shape == w.shape
+        assert np.array_equal(g, w)
+    soup = np.concatenate(got)
+    size = max(b - a for a, b in zip(s.box_a, s.box_b))
+    rep = mc.manifold_report(soup, 1e-6 * size)
+    assert rep["bad_edges"] == 0, rep                       # the reference's test: watertight
+    assert mc.signed_volume(soup) > 0                       # outward normals
+
+
+def test_mesh_volume_matches_mass_properties(cb, scenes):
+    from codecad_b200.rendering import mesh_arrays
+    s = scenes["cfg_csg_example"]
+    vertices, block, boxes = mesh_arrays(s.compiled(), 32)
+    assert len(vertices) > 100 and len(boxes) >= 1 and len(block) == len(vertices)
+    # one block at this resolution: shared vertices are bit-identical, no tolerance needed (the scene
+    # has samples exactly on the surface, i.e. zero-area triangles that a tolerance would tangle up)
+    assert len(boxes) == 1
+    rep = mc.manifold_report(vertices, 0)
+    assert rep["bad_edges"] == 0, rep
+    vol = cb.mass_properties(s.compiled(), 2.0, 32).volume   # the mesh is coarse: feature_size / 2 = 20
+    assert mc.signed_volume(vertices) == pytest.approx(vol, rel=0.15)
+
+
+def test_render_stl(cb, scenes, tmp_path):
+    from codecad_b200.rendering import render_stl
+    path = tmp_path / "box.stl"
+    n = render_stl(scenes["sub_box10"].compiled(), str(path))
+    raw = path.read_bytes()
+    assert n > 0 and len(raw) == 84 + 50 * n
+
+
+def test_debug_boxes_and_dimension_check(cb, scenes):
+    from codecad_b200.rendering import triangular_mesh
+    pieces = list(triangular_mesh(scenes["sub_box10"].compiled(), 4, debug_subdivision_boxes=True))
+    assert len(pieces) >= 1 and all(len(v) == 8 and len(t) == 12 for v, t in pieces)
+    with pytest.raises(AssertionError):
+        list(triangular_mesh(scenes["sub_circle"].compiled()))
