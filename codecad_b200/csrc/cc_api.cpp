@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -984,9 +985,12 @@ int cc_mesh_blocks(const cc_program *prog, const double *corners, double resolut
         if (e) return cuda_fail((cudaError_t)e, "marching-cubes tables");
         tables_uploaded = true;
     }
-    std::vector<double> h_vertices;
-    std::vector<uint32_t> h_blocks;
-    DevBuf field, descs, d_corner, counter, d_vertices, d_tri_block;
+    struct ChunkOut {
+        DevBuf vertices, tri_block;
+        uint32_t n_tri = 0;
+    };
+    std::vector<std::unique_ptr<ChunkOut>> results;  // triangles stay on the device until the end
+    DevBuf field, descs, d_corner, counter;
     int rc;
     if ((rc = counter.reserve(4))) return rc;
     // blocks per chunk: keep the field buffer around 1 GiB
@@ -1033,27 +1037,24 @@ int cc_mesh_blocks(const cc_program *prog, const double *corners, double resolut
         if (n_tri == 0) continue;
         const uint64_t tiles = (uint64_t)m.tiles_per_block * nb;
         if ((rc = ensure_status((size_t)tiles))) return rc;
-        if ((rc = d_vertices.reserve((size_t)n_tri * 9 * sizeof(double)))) return rc;
-        if ((rc = d_tri_block.reserve((size_t)n_tri * 4))) return rc;
+        results.emplace_back(new ChunkOut);
+        ChunkOut &co = *results.back();
+        co.n_tri = n_tri;
+        if ((rc = co.vertices.reserve((size_t)n_tri * 9 * sizeof(double)))) return rc;
+        if ((rc = co.tri_block.reserve((size_t)n_tri * 4))) return rc;
         CU(cudaMemsetAsync(g.d_ticket, 0, 4, g.compute));
         CU(cudaMemsetAsync(g.d_status, 0, (size_t)tiles * sizeof(unsigned long long), g.compute));
         CU(cudaMemsetAsync(counter.p, 0, 4, g.compute));
         m.ticket = g.d_ticket;
         m.tile_status = g.d_status;
-        m.vertices = d_vertices.as<double>();
-        m.tri_block = d_tri_block.as<uint32_t>();
+        m.vertices = co.vertices.as<double>();
+        m.tri_block = co.tri_block.as<uint32_t>();
         e = cc_launch_mesh(m, true, g.compute);
         if (e) return cuda_fail((cudaError_t)e, "marching cubes (emit)");
         g.launches += 1;
-        const size_t old = h_blocks.size();
-        h_vertices.resize((old + n_tri) * 9);
-        h_blocks.resize(old + n_tri);
-        CU(cudaMemcpyAsync(h_vertices.data() + old * 9, d_vertices.p, (size_t)n_tri * 9 * sizeof(double),
-                           cudaMemcpyDeviceToHost, g.compute));
-        CU(cudaMemcpyAsync(h_blocks.data() + old, d_tri_block.p, (size_t)n_tri * 4, cudaMemcpyDeviceToHost, g.compute));
-        CU(cudaStreamSynchronize(g.compute));
     }
-    const size_t n = h_blocks.size();
+    size_t n = 0;
+    for (auto &r : results) n += r->n_tri;
     *out_triangles = n;
     if (n) {
         double *v = (double *)malloc(n * 9 * sizeof(double));
@@ -1063,8 +1064,22 @@ int cc_mesh_blocks(const cc_program *prog, const double *corners, double resolut
             free(b);
             return fail(CC_ERR_INVALID_ARGUMENT, "out of host memory");
         }
-        std::memcpy(v, h_vertices.data(), n * 9 * sizeof(double));
-        std::memcpy(b, h_blocks.data(), n * sizeof(uint32_t));
+        size_t at = 0;
+        cudaError_t ce = cudaSuccess;
+        for (auto &r : results) {  // one copy, straight into the caller's buffers
+            if (ce == cudaSuccess)
+                ce = cudaMemcpyAsync(v + at * 9, r->vertices.p, (size_t)r->n_tri * 9 * sizeof(double), cudaMemcpyDeviceToHost,
+                                     g.compute);
+            if (ce == cudaSuccess)
+                ce = cudaMemcpyAsync(b + at, r->tri_block.p, (size_t)r->n_tri * 4, cudaMemcpyDeviceToHost, g.compute);
+            at += r->n_tri;
+        }
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(g.compute);
+        if (ce != cudaSuccess) {
+            free(v);
+            free(b);
+            return cuda_fail(ce, "triangles D2H");
+        }
         *out_vertices = v;
         *out_triangle_block = b;
     }

@@ -42,12 +42,38 @@ def mesh_blocks(program_buffer, box_size, corners, resolution):
     t = int(n.value)
     if t == 0:
         return np.zeros((0, 3, 3), np.float64), np.zeros((0,), np.uint32)
-    try:
-        return (np.ctypeslib.as_array(out_v, shape=(t, 3, 3)).copy(),
-                np.ctypeslib.as_array(out_b, shape=(t,)).copy())
-    finally:
-        _lib.lib().cc_free(out_v)
-        _lib.lib().cc_free(out_b)
+    # wrap the library's buffers without copying; they are released when the arrays die
+    return _adopt(out_v, (t, 3, 3)), _adopt(out_b, (t,))
+
+
+class _Owner:
+    """Keeps a malloc'ed library buffer alive for the numpy array built on top of it."""
+
+    def __init__(self, pointer):
+        self.pointer = pointer
+
+    def __del__(self):
+        if self.pointer and _lib._lib is not None:
+            _lib._lib.cc_free(self.pointer)
+            self.pointer = None
+
+
+def _adopt(pointer, shape):
+    owner = _Owner(pointer)
+    arr = np.ctypeslib.as_array(pointer, shape=shape)
+    holder = np.ndarray.__new__(_Held, shape=arr.shape, dtype=arr.dtype, buffer=arr)
+    holder._owner = owner
+    return holder
+
+
+class _Held(np.ndarray):
+    """ndarray that carries its buffer's owner (views inherit it through __array_finalize__)."""
+
+    _owner = None
+
+    def __array_finalize__(self, obj):
+        if obj is not None:
+            self._owner = getattr(obj, "_owner", None)
 
 
 def mesh_arrays(obj, subdivision_grid_size=None):
