@@ -14,6 +14,7 @@ What it does (INTEGRATION.md has the file-level view):
         codecad.grid_eval        (grid_eval.py:1-3)
         codecad.subdivision      (subdivision.py)
         codecad.mass_properties  (mass_properties.py)
+        codecad.rendering.mesh, codecad.rendering.stl_renderer   (mesh export)
     are never loaded: the modules of this package take their place under those names.
 
 Everything else of the reference (shapes, nodes, util, assemblies, rendering front ends)
@@ -101,6 +102,9 @@ def install(force_pyopencl=True):
         "codecad.grid_eval": grid_eval,
         "codecad.subdivision": subdivision,
         "codecad.mass_properties": mass_properties,
+        # mesh export (rendering/mesh.py imports mcubes + pyopencl, rendering/stl_renderer.py numpy-stl)
+        "codecad.rendering.mesh": importlib.import_module("codecad_b200.rendering.mesh"),
+        "codecad.rendering.stl_renderer": importlib.import_module("codecad_b200.rendering.stl_renderer"),
     }
     sys.modules.update(aliases)
     return sorted(aliases)

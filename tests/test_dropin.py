@@ -38,8 +38,11 @@ def test_reference_imports_with_our_modules():
         print(type(codecad.cl_util.opencl_manager).__module__, pyopencl.__doc__[:12])
         print(codecad.mass_properties.__module__)
         print(codecad.cl_util.opencl_manager.max_register_count)
+        import codecad.rendering.mesh as m, codecad.rendering.stl_renderer as st
+        print(m.triangular_mesh.__module__, st.render_stl.__module__)
     """)
-    lines = out.strip().splitlines()[-4:]
+    assert out.strip().splitlines()[-1] == "codecad_b200.rendering.mesh codecad_b200.rendering.stl_renderer"
+    lines = out.strip().splitlines()[-5:-1]
     assert lines[0] == "codecad_b200.cl_util codecad_b200.subdivision codecad_b200.grid_eval"
     assert lines[1] == "codecad_b200.cl_util.manager codecad_b200"
     assert lines[2] == "codecad_b200.mass_properties"
