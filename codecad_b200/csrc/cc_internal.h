@@ -22,8 +22,8 @@ struct cc_jit_cfg {
     int pts = 2;         // points per thread
     int threads = 512;   // CTA size
     int min_blocks = 2;  // __launch_bounds__ min CTAs per SM (register cap)
-    int smem_min_len = 16;   // values live for at least this many micro-ops go to shared-memory cells
-    int smem_max_cells = 0;  // budget of cells (0 = keep everything in registers)
+    int smem_min_len = 12;   // values live for at least this many micro-ops go to shared-memory cells
+    int smem_max_cells = 6;  // budget of cells (0 = keep everything in registers)
 };
 struct cc_jit_job;
 
@@ -44,7 +44,7 @@ struct cc_program {
 };
 
 // cc_jit.cpp
-cc_jit_cfg cc_jit_default_cfg(int pts);
+cc_jit_cfg cc_jit_default_cfg(const cc_decoded &dec, int pts);
 int cc_jit_source(const cc_decoded &dec, int pts, unsigned sink_mask, std::string *src, std::string *err);
 int cc_jit_nvrtc(const std::string &src, std::vector<char> *cubin, std::string *err);
 int cc_jit_compile(cc_program *prog, int pts, unsigned sink_mask, double *seconds, std::string *err);

@@ -267,6 +267,13 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
         }
         n_cells = (int)cell_members.size();
     }
+    // experiment: keep the grid coordinates (live through the whole kernel) in one more cell
+    const bool coord_smem = getenv("CODECAD_B200_JIT_COORD_SMEM") != nullptr;
+    const int coord_cell = n_cells;
+    if (coord_smem) ++n_cells;
+    const std::string coord_load = !coord_smem ? std::string() :
+        "          V px[G], py[G], pz[G]; CC_EACH { Val P_; cc_slot_load_opaque(CC_CELL(" + std::to_string(coord_cell) +
+        ", g), P_); px[g] = P_.x; py[g] = P_.y; pz[g] = P_.z; }\n";
     g.n_cells = n_cells;
 
     uint32_t pc = 0;
@@ -286,7 +293,7 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
             } else {  // operand lives in a shared-memory cell: fetch what this op needs
                 B = "B" + std::to_string(op_index) + "[g]";
                 o << "        Val B" << op_index << "[G]; CC_EACH "
-                  << (op == MOP_EXTRUSION ? "cc_slot_load_z(CC_CELL(" : op == MOP_SYM_FROM ? "cc_slot_load_x(CC_CELL(" : "cc_slot_load(CC_CELL(")
+                  << (op == MOP_EXTRUSION ? "cc_slot_load_z_opaque(CC_CELL(" : op == MOP_SYM_FROM ? "cc_slot_load_x_opaque(CC_CELL(" : "cc_slot_load_opaque(CC_CELL(")
                   << iv[u].cell << ", g), " << B << (op == MOP_EXTRUSION ? ".z" : op == MOP_SYM_FROM ? ".x" : "") << ");\n";
             }
         }
@@ -296,10 +303,10 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
         case MOP_LOAD: o << "        CC_EACH L[g] = " << B << ";\n"; break;
         case MOP_PRIM_CIRCLE:
         case MOP_PRIM_RECT:
-            o << "        { const float m[12] = {" << g.args(pc, 1, 12) << "};\n"
+            o << "        { const float m[12] = {" << g.args(pc, 1, 12) << "};\n" << coord_load
               << "          const float mf[12] = {" << g.args(pc, 17, 10) << ", 0.f, 0.f};\n"
               << "          cc_prim_n<" << (op == MOP_PRIM_RECT ? "true" : "false") << ", V, G>(m, mf, " << g.args(pc, 13, 4)
-              << ", gx, gy, gz, L); }\n";
+              << ", " << (coord_smem ? "px, py, pz" : "gx, gy, gz") << ", L); }\n";
             break;
         case MOP_RECTANGLE: o << "        cc_rectangle_n(" << g.args(pc, 1, 2) << ", L);\n"; break;
         case MOP_CIRCLE: o << "        cc_circle_n(" << g.F(pc + 1) << ", L);\n"; break;
@@ -319,8 +326,8 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
         case MOP_REV_TO: o << "        CC_EACH L[g] = cc_op_rev_to(L[g]);\n"; break;
         case MOP_TWIST_TO: o << "        CC_EACH L[g] = cc_op_twist_to(" << g.args(pc, 1, 2) << ", L[g]);\n"; break;
         case MOP_T_INIT:
-            o << "        { const float m[12] = {" << g.args(pc, 1, 12) << "};\n"
-              << "          CC_EACH L[g] = cc_transform(m, gx[g], gy[g], gz[g]); }\n";
+            o << "        { const float m[12] = {" << g.args(pc, 1, 12) << "};\n" << coord_load
+              << "          CC_EACH L[g] = cc_transform(m, " << (coord_smem ? "px[g], py[g], pz[g]" : "gx[g], gy[g], gz[g]") << "); }\n";
             break;
         case MOP_T_TO:
             o << "        { const float m[12] = {" << g.args(pc, 1, 12) << "};\n"
@@ -388,6 +395,8 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
       << g.consts.str() << "struct SceneEval {\n    float4 *sm;  // this thread's column of the value cells\n"
       << "    __device__ __forceinline__ void operator()(const V (&gx)[G], const V (&gy)[G], const V (&gz)[G],\n"
       << "                                               Val (&L)[G]) const\n    {\n";
+    if (coord_smem)
+        s << "        CC_EACH cc_slot_store(CC_CELL(" << coord_cell << ", g), Val{gx[g], gy[g], gz[g], vbc<V>(0.f)});\n";
     s << "        CC_EACH L[g] = Val{vbc<V>(0.f), vbc<V>(0.f), vbc<V>(0.f), vbc<V>(0.f)};\n" << o.str() << "    }\n};\n";
     const char *names[4] = {"float4", "pymcubes", "classify", "mass"};
     const char *sinks[4] = {"CC_SINK_FLOAT4", "CC_SINK_PYMCUBES", "CC_SINK_CLASSIFY", "CC_SINK_MASS"};
@@ -411,10 +420,32 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
 // close together in the straight-line code and share instruction-cache lines), registers capped
 // at 64 so that two CTAs = 32 warps are resident per SM.  Environment overrides for experiments:
 // CODECAD_B200_JIT_PTS / _THREADS / _MINB.
-cc_jit_cfg cc_jit_default_cfg(int pts)
+// Share of a program's work spent in ops that run lane by lane (no packed form: data-dependent
+// loops and early exits).  Such programs gain nothing from a second point per thread but pay its
+// registers: airfoil (two 80-edge polygons) runs 11 % faster with one point per thread.
+static bool lane_by_lane_dominated(const cc_decoded &dec)
+{
+    const std::vector<uint32_t> &c = dec.microcode;
+    uint64_t heavy = 0;
+    for (uint32_t pc = 0; pc < c.size();) {
+        const uint32_t h = c[pc], op = CC_HDR_OP(h);
+        if (op == MOP_RETURN) break;
+        switch (op) {
+        case MOP_POLYGON: heavy += 20ull * (uint32_t)(*reinterpret_cast<const float *>(&c[pc + 1])); break;
+        case MOP_REGPOLY: case MOP_TWIST_FROM: heavy += 60; break;
+        case MOP_TWIST_TO: case MOP_CREP_TO: case MOP_CREP_FROM: heavy += 40; break;
+        case MOP_REPETITION: heavy += 30; break;
+        default: break;
+        }
+        pc += CC_HDR_LEN(h);
+    }
+    return heavy * 2 > dec.info.flops_min;
+}
+
+cc_jit_cfg cc_jit_default_cfg(const cc_decoded &dec, int pts)
 {
     cc_jit_cfg c;
-    c.pts = 2;
+    c.pts = lane_by_lane_dominated(dec) ? 1 : 2;
     c.threads = 512;
     c.min_blocks = 2;
     if (const char *t = getenv("CODECAD_B200_JIT_PTS")) c.pts = atoi(t);
@@ -428,16 +459,20 @@ cc_jit_cfg cc_jit_default_cfg(int pts)
     // the ordered-compaction sinks scan PTS * warps-per-CTA counters with one warp (cc_body.cuh)
     while (c.pts * (c.threads / 32) > 32) c.threads /= 2;
     if (c.min_blocks * c.threads > 2048) c.min_blocks = 2048 / c.threads;
-    // Shared-memory cells for long-lived values (instead of letting ptxas spill what exceeds the
-    // register cap to local memory).  Measured on B200, planetary 512^3, two points per thread:
-    // 0 cells 7.29 Gpts/s, 3 cells 6.87, 6 cells 6.65 (profiles/r1_jit_variants.md) — the L1-cached
-    // spills ptxas places are cheaper than whole-value cells, so the default keeps everything in
-    // registers; CODECAD_B200_JIT_SMEM_CELLS=n opts in (it removes the spill write-back traffic).
+    // Shared-memory cells for long-lived values.  Two points per thread need 8 registers per live
+    // value; what exceeds the 64-register cap ptxas spills to local memory, and with a 344-byte
+    // frame per thread the spill lines do not stay in L2 next to the streaming output: 51.5 GB
+    // of DRAM writes for 17.2 GB of results (planetary 1024^3).  Up to six values that live for
+    // twelve micro-ops or more go to conflict-free shared-memory cells instead (loads through an
+    // opaque asm so that the compiler cannot forward the stored registers and keep them live):
+    // frame 168 B, DRAM writes 17.7 GB, kernel time +0.9 % (profiles/r1_jit_variants.md).
     c.smem_max_cells = 0;
-    if (const char *t = getenv("CODECAD_B200_JIT_SMEM_CELLS")) {
+    c.smem_min_len = 12;
+    if (c.pts >= 2) {
         const int ctas = c.min_blocks > 0 ? c.min_blocks : 1;
         const int fit = (int)((220u * 1024u / ctas - 2048u) / ((size_t)c.pts * c.threads * 16));
-        c.smem_max_cells = std::max(0, std::min(fit, atoi(t)));
+        c.smem_max_cells = std::max(0, std::min(fit, 6));
+        if (const char *t = getenv("CODECAD_B200_JIT_SMEM_CELLS")) c.smem_max_cells = std::max(0, std::min(fit, atoi(t)));
     }
     if (const char *t = getenv("CODECAD_B200_JIT_SMEM_MIN_LEN")) c.smem_min_len = atoi(t);
     return c;
@@ -661,7 +696,7 @@ static void join_job(cc_program *prog, int sink)
 int cc_jit_compile(cc_program *prog, int pts, unsigned sink_mask, double *seconds, std::string *err)
 {
     if ((sink_mask & 15u) == 0) sink_mask = 15u;
-    const cc_jit_cfg cfg = cc_jit_default_cfg(pts);
+    const cc_jit_cfg cfg = cc_jit_default_cfg(prog->dec, pts);
     auto t0 = std::chrono::steady_clock::now();
     for (int k = 0; k < 4; ++k) {
         if (!(sink_mask & (1u << k))) continue;
@@ -682,7 +717,7 @@ void cc_jit_start(cc_program *prog, int sink)
 {
     if (prog->jit_kernel[sink] || prog->jit_job[sink] || prog->jit_failed[sink]) return;
     cc_jit_job *j = new cc_jit_job;
-    j->cfg = cc_jit_default_cfg(0);
+    j->cfg = cc_jit_default_cfg(prog->dec, 0);
     prog->jit_job[sink] = j;
     const cc_decoded *dec = &prog->dec;  // immutable; outlives the thread (destroy joins it)
     j->th = std::thread([j, dec, sink]() {
@@ -738,5 +773,5 @@ int cc_jit_launch(const cc_program *prog, int sink, const cc_eval_args &a, void 
 int cc_jit_source(const cc_decoded &dec, int pts, unsigned sink_mask, std::string *src, std::string *err)
 {
     if ((sink_mask & 15u) == 0) sink_mask = 15u;
-    return generate(dec, cc_jit_default_cfg(pts), sink_mask, src, nullptr, err);
+    return generate(dec, cc_jit_default_cfg(dec, pts), sink_mask, src, nullptr, err);
 }

@@ -621,6 +621,38 @@ CC_DEV void cc_slot_load(const float4 *base, cc_val<float2> &v)
     const float4 a = base[0], b = base[CC_THREADS];
     v = cc_val<float2>{make_float2(a.x, a.y), make_float2(a.z, a.w), make_float2(b.x, b.y), make_float2(b.z, b.w)};
 }
+// opaque 128-bit shared load: the compiler may not forward the stored registers to it
+CC_DEV float4 cc_lds128_opaque(const float4 *p)
+{
+    float4 r;
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a));
+    return r;
+}
+CC_DEV void cc_slot_load_opaque(const float4 *base, cc_val<float> &v)
+{
+    const float4 f = cc_lds128_opaque(base);
+    v = cc_val<float>{f.x, f.y, f.z, f.w};
+}
+CC_DEV void cc_slot_load_opaque(const float4 *base, cc_val<float2> &v)
+{
+    const float4 a = cc_lds128_opaque(base), b = cc_lds128_opaque(base + CC_THREADS);
+    v = cc_val<float2>{make_float2(a.x, a.y), make_float2(a.z, a.w), make_float2(b.x, b.y), make_float2(b.z, b.w)};
+}
+CC_DEV float2 cc_lds64_opaque(const float2 *p)
+{
+    float2 r;
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(a));
+    return r;
+}
+CC_DEV void cc_slot_load_x_opaque(const float4 *base, float &x) { x = cc_lds128_opaque(base).x; }
+CC_DEV void cc_slot_load_x_opaque(const float4 *base, float2 &x) { x = cc_lds64_opaque(reinterpret_cast<const float2 *>(base)); }
+CC_DEV void cc_slot_load_z_opaque(const float4 *base, float &z) { z = cc_lds128_opaque(base).z; }
+CC_DEV void cc_slot_load_z_opaque(const float4 *base, float2 &z)
+{
+    z = cc_lds64_opaque(reinterpret_cast<const float2 *>(base + CC_THREADS));
+}
 CC_DEV void cc_slot_load_x(const float4 *base, float &x) { x = base[0].x; }
 CC_DEV void cc_slot_load_x(const float4 *base, float2 &x) { x = *reinterpret_cast<const float2 *>(base); }
 CC_DEV void cc_slot_load_z(const float4 *base, float &z) { z = base[0].z; }
