@@ -154,6 +154,47 @@ struct Gen {
         for (int i = 0; i < count; ++i) s += (i ? ", " : "") + F(pc + first + i);
         return s;
     }
+    float value(uint32_t idx) const
+    {
+        float f;
+        std::memcpy(&f, &code[idx], 4);
+        return f;
+    }
+    // One matrix row written out term by term with cc-arith's rules (cc_ops.cuh cc_row_to /
+    // cc_row_from): innermost-first (z, y, x), zero coefficients omitted.  Emitting the folded form
+    // here instead of calling the masked templates keeps NVRTC's work small (compile time).
+    std::string row_to(uint32_t m, uint32_t o, const std::string &x, const std::string &y, const std::string &z) const
+    {
+        std::string acc = "vbc<V>(" + F(o) + ")";
+        const std::string v[3] = {x, y, z};
+        for (int k = 2; k >= 0; --k)
+            if (value(m + k) != 0.0f) acc = "vfma(vbc<V>(" + F(m + k) + "), " + v[k] + ", " + acc + ")";
+        return acc;
+    }
+    std::string row_from(uint32_t m, const std::string &x, const std::string &y, const std::string &z) const
+    {
+        std::string acc;
+        const std::string v[3] = {x, y, z};
+        for (int k = 2; k >= 0; --k) {
+            if (value(m + k) == 0.0f) continue;
+            if (acc.empty()) acc = "cc_first_term(" + F(m + k) + ", " + v[k] + ")";
+            else acc = "vfma(vbc<V>(" + F(m + k) + "), " + v[k] + ", " + acc + ")";
+        }
+        return acc.empty() ? std::string("vbc<V>(0.0f)") : acc;
+    }
+    // statements computing `dst` (a Val) = matrix(m..m+8) * (x, y, z) + o(m+9..m+11)
+    std::string transform_to(uint32_t m, const std::string &x, const std::string &y, const std::string &z) const
+    {
+        return "Val{" + row_to(m, m + 9, x, y, z) + ", " + row_to(m + 3, m + 10, x, y, z) + ", " +
+               row_to(m + 6, m + 11, x, y, z) + ", vbc<V>(0.0f)}";
+    }
+    // from-matrix at m..m+8, scale at m+9, applied to the Val named `in`
+    std::string transform_from(uint32_t m, const std::string &in) const
+    {
+        const std::string x = in + ".x", y = in + ".y", z = in + ".z";
+        const std::string w = value(m + 9) == 1.0f ? in + ".w" : "vmul(" + in + ".w, vbc<V>(" + F(m + 9) + "))";
+        return "Val{" + row_from(m, x, y, z) + ", " + row_from(m + 3, x, y, z) + ", " + row_from(m + 6, x, y, z) + ", " + w + "}";
+    }
     std::string C(uint32_t idx) const  // constant-expression literal (for __constant__ initialisers)
     {
         float f;
@@ -303,11 +344,21 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
         case MOP_LOAD: o << "        CC_EACH L[g] = " << B << ";\n"; break;
         case MOP_PRIM_CIRCLE:
         case MOP_PRIM_RECT:
-            o << "        { const float m[12] = {" << g.args(pc, 1, 12) << "};\n" << coord_load
-              << "          const float mf[12] = {" << g.args(pc, 17, 10) << ", 0.f, 0.f};\n"
-              << "          cc_prim_n<" << (op == MOP_PRIM_RECT ? "true" : "false") << ", V, G>(m, mf, " << g.args(pc, 13, 4)
-              << ", " << (coord_smem ? "px, py, pz" : "gx, gy, gz") << ", L); }\n";
+        case MOP_PRIM_CIRCLE_M:
+        case MOP_PRIM_RECT_M: {
+            // words: 1..12 m,o | 13 a | 14 b | 15 h | 16 d | 17..25 m' | 26 scale  (cc_prim_n, unrolled)
+            const bool rect = (op == MOP_PRIM_RECT || op == MOP_PRIM_RECT_M);
+            const std::string X = coord_smem ? "px[g]" : "gx[g]", Y = coord_smem ? "py[g]" : "gy[g]",
+                              Z = coord_smem ? "pz[g]" : "gz[g]";
+            o << "        {\n" << coord_load << "          V pz_[G];\n"
+              << "          CC_EACH { L[g] = " << g.transform_to(pc + 1, X, Y, Z) << "; pz_[g] = L[g].z; }\n";
+            if (rect) o << "          cc_rectangle_n(" << g.args(pc, 13, 2) << ", L);\n";
+            else o << "          cc_circle_n(" << g.F(pc + 13) << ", L);\n";
+            o << "          cc_extrusion_n(" << g.F(pc + 15) << ", L, pz_);\n"
+              << "          CC_EACH { L[g].w = vsub(L[g].w, vbc<V>(" << g.F(pc + 16) << ")); const Val t_ = L[g]; L[g] = "
+              << g.transform_from(pc + 17, "t_") << "; }\n        }\n";
             break;
+        }
         case MOP_RECTANGLE: o << "        cc_rectangle_n(" << g.args(pc, 1, 2) << ", L);\n"; break;
         case MOP_CIRCLE: o << "        cc_circle_n(" << g.F(pc + 1) << ", L);\n"; break;
         case MOP_SPHERE: o << "        cc_sphere_n(" << g.F(pc + 1) << ", L);\n"; break;
@@ -326,16 +377,18 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
         case MOP_REV_TO: o << "        CC_EACH L[g] = cc_op_rev_to(L[g]);\n"; break;
         case MOP_TWIST_TO: o << "        CC_EACH L[g] = cc_op_twist_to(" << g.args(pc, 1, 2) << ", L[g]);\n"; break;
         case MOP_T_INIT:
-            o << "        { const float m[12] = {" << g.args(pc, 1, 12) << "};\n" << coord_load
-              << "          CC_EACH L[g] = cc_transform(m, " << (coord_smem ? "px[g], py[g], pz[g]" : "gx[g], gy[g], gz[g]") << "); }\n";
+        case MOP_T_INIT_M:
+            o << "        {\n" << coord_load << "          CC_EACH L[g] = "
+              << g.transform_to(pc + 1, coord_smem ? "px[g]" : "gx[g]", coord_smem ? "py[g]" : "gy[g]", coord_smem ? "pz[g]" : "gz[g]")
+              << ";\n        }\n";
             break;
         case MOP_T_TO:
-            o << "        { const float m[12] = {" << g.args(pc, 1, 12) << "};\n"
-              << "          CC_EACH L[g] = cc_transform(m, L[g].x, L[g].y, L[g].z); }\n";
+        case MOP_T_TO_M:
+            o << "        CC_EACH { const Val t_ = L[g]; L[g] = " << g.transform_to(pc + 1, "t_.x", "t_.y", "t_.z") << "; }\n";
             break;
         case MOP_T_FROM:
-            o << "        { const float m[12] = {" << g.args(pc, 1, 10) << ", 0.f, 0.f};\n"
-              << "          CC_EACH L[g] = cc_transform_from(m, L[g]); }\n";
+        case MOP_T_FROM_M:
+            o << "        CC_EACH { const Val t_ = L[g]; L[g] = " << g.transform_from(pc + 1, "t_") << "; }\n";
             break;
         case MOP_MIRROR: o << "        CC_EACH L[g].x = vneg(L[g].x);\n"; break;
         case MOP_SYM_TO: o << "        CC_EACH L[g].x = vabs(L[g].x);\n"; break;

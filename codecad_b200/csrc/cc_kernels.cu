@@ -70,7 +70,7 @@ CC_DEV_HEAVY float4 cc_polygon2d(const Prog<MODE> &P, uint32_t pc, float4 co)
 // never leaves registers.  Bit-identical to the unfused sequence (absent offset = 0, absent
 // transformation_from = identity matrix and scale 1).
 // words: 1..12 m,o | 13 a | 14 b | 15 h | 16 d | 17..25 m' | 26 scale
-template <bool RECT, class V, int G, int SMEM>
+template <bool RECT, bool MASKED, class V, int G, int SMEM>
 CC_DEV void cc_prim(const Prog<SMEM> &P, uint32_t pc, const V (&x)[G], const V (&y)[G], const V (&z)[G],
                     cc_val<V> (&L)[G])
 {
@@ -81,7 +81,8 @@ CC_DEV void cc_prim(const Prog<SMEM> &P, uint32_t pc, const V (&x)[G], const V (
     m[6] = b.w; m[7] = c.x; m[8] = c.y; m[9] = c.z; m[10] = c.w; m[11] = d.x;
     mf[0] = e.y; mf[1] = e.z; mf[2] = e.w; mf[3] = f.x; mf[4] = f.y; mf[5] = f.z;
     mf[6] = f.w; mf[7] = g.x; mf[8] = g.y; mf[9] = g.z; mf[10] = 0.f; mf[11] = 0.f;
-    cc_prim_n<RECT, V, G>(m, mf, d.y, d.z, d.w, e.x, x, y, z, L);
+    const uint32_t masks = MASKED ? __float_as_uint(g.w) : 0u;
+    cc_prim_n<RECT, MASKED, V, G>(m, mf, masks & 0x1FFu, (masks >> 9) & 0x1FFu, d.y, d.z, d.w, e.x, x, y, z, L);
 }
 
 template <int PTS, int SMEM>
@@ -117,11 +118,19 @@ CC_DEV void cc_interpret(const Prog<SMEM> P, float4 *__restrict__ regs, const ty
         // uniform datapath (LDCU/UISETP/BRA.U); deriving the increment from a loaded word or
         // advancing before a per-thread branch silently demotes everything to vector code (-11 %).
         case MOP_PRIM_CIRCLE:
-            cc_prim<false, V, G, SMEM>(P, pc, gx, gy, gz, L);
+            cc_prim<false, false, V, G, SMEM>(P, pc, gx, gy, gz, L);
             pc += CC_LEN_PRIM;
             break;
         case MOP_PRIM_RECT:
-            cc_prim<true, V, G, SMEM>(P, pc, gx, gy, gz, L);
+            cc_prim<true, false, V, G, SMEM>(P, pc, gx, gy, gz, L);
+            pc += CC_LEN_PRIM;
+            break;
+        case MOP_PRIM_CIRCLE_M:
+            cc_prim<false, true, V, G, SMEM>(P, pc, gx, gy, gz, L);
+            pc += CC_LEN_PRIM;
+            break;
+        case MOP_PRIM_RECT_M:
+            cc_prim<true, true, V, G, SMEM>(P, pc, gx, gy, gz, L);
             pc += CC_LEN_PRIM;
             break;
         case MOP_RECTANGLE: {
@@ -184,10 +193,27 @@ CC_DEV void cc_interpret(const Prog<SMEM> P, float4 *__restrict__ regs, const ty
             }
             if (op == MOP_T_INIT) {
 #pragma unroll
-                CC_EACH L[g] = cc_transform(m, gx[g], gy[g], gz[g]);
+                CC_EACH L[g] = cc_transform_full(m, gx[g], gy[g], gz[g]);
             } else {
 #pragma unroll
-                CC_EACH L[g] = cc_transform(m, L[g].x, L[g].y, L[g].z);
+                CC_EACH L[g] = cc_transform_full(m, L[g].x, L[g].y, L[g].z);
+            }
+            pc += CC_LEN_T;
+            break;
+        }
+        case MOP_T_INIT_M:
+        case MOP_T_TO_M: {
+            float m[12];
+            const float4 a = P.f4(pc), b = P.f4(pc + 4), c = P.f4(pc + 8), d = P.f4(pc + 12);
+            m[0] = a.y; m[1] = a.z; m[2] = a.w; m[3] = b.x; m[4] = b.y; m[5] = b.z;
+            m[6] = b.w; m[7] = c.x; m[8] = c.y; m[9] = c.z; m[10] = c.w; m[11] = d.x;
+            const uint32_t mask = __float_as_uint(d.y);
+            if (op == MOP_T_INIT_M) {
+#pragma unroll
+                CC_EACH L[g] = cc_transform(m, mask, gx[g], gy[g], gz[g]);
+            } else {
+#pragma unroll
+                CC_EACH L[g] = cc_transform(m, mask, L[g].x, L[g].y, L[g].z);
             }
             pc += CC_LEN_T;
             break;
@@ -200,7 +226,18 @@ CC_DEV void cc_interpret(const Prog<SMEM> P, float4 *__restrict__ regs, const ty
                 m[6] = b.w; m[7] = c.x; m[8] = c.y; m[9] = c.z; m[10] = 0.f; m[11] = 0.f;
             }
 #pragma unroll
-            CC_EACH L[g] = cc_transform_from(m, L[g]);
+            CC_EACH L[g] = cc_transform_from_full(m, L[g]);
+            pc += CC_LEN_T;
+            break;
+        }
+        case MOP_T_FROM_M: {
+            float m[12];
+            const float4 a = P.f4(pc), b = P.f4(pc + 4), c = P.f4(pc + 8);
+            m[0] = a.y; m[1] = a.z; m[2] = a.w; m[3] = b.x; m[4] = b.y; m[5] = b.z;
+            m[6] = b.w; m[7] = c.x; m[8] = c.y; m[9] = c.z; m[10] = 0.f; m[11] = 0.f;
+            const uint32_t mask = __float_as_uint(c.w);
+#pragma unroll
+            CC_EACH L[g] = cc_transform_from(m, mask, L[g]);
             pc += CC_LEN_T;
             break;
         }

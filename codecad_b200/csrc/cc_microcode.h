@@ -57,6 +57,15 @@ enum cc_mop : uint32_t {
     MOP_SUB_R,
     MOP_PRIM_CIRCLE,   // fused T_INIT -> circle -> extrusion -> offset -> T_FROM   (28 words)
     MOP_PRIM_RECT,     // fused T_INIT -> rectangle -> extrusion -> offset -> T_FROM
+    // "_M" variants: some matrix coefficient is exactly zero, and cc-arith omits such terms from
+    // the row sums (cc_ops.cuh).  Same parameter layout plus one word of zero-masks (T_INIT/T_TO:
+    // word 13, T_FROM: word 11, PRIM: word 27 = mask | mask_from << 9).  Separate micro-ops keep
+    // the interpreter's code for full matrices (every primitive of a rotated scene) untouched.
+    MOP_T_INIT_M,
+    MOP_T_TO_M,
+    MOP_T_FROM_M,
+    MOP_PRIM_CIRCLE_M,
+    MOP_PRIM_RECT_M,
     MOP_COUNT
 };
 

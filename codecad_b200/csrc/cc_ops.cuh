@@ -235,24 +235,90 @@ CC_DEV cc_val<V> cc_rounded_union(float r, cc_val<V> o1, cc_val<V> o2)
     return res;
 }
 
-// 3x3 (row-major) * v + o   — common.cl:78-98 in matrix form
+// ---- transformations: 3x3 (row-major) * v [+ o]   — common.cl:78-110 in matrix form ----
+// cc-arith: a row is accumulated innermost-first (z, y, x) and terms whose coefficient is exactly
+// zero are OMITTED (a parameter-only simplification, fixed at load time like the quaternion ->
+// matrix conversion; multiplying by a zero coefficient would only decide the sign of an exactly
+// zero result).  CAD scenes are full of axis-aligned transforms: 44 % of the matrix entries of
+// the planetary scene are zero and 38 % of its matrices are the identity.  `mask` bit k tells
+// whether m[k] != 0; the loader stores it next to the matrix, the specialised kernels compute it
+// from the immediates (and the branches below fold away at compile time).
+#define CC_MASK_FULL 0x1FFu
+CC_DEV unsigned cc_matrix_mask(const float (&m)[12])
+{
+    unsigned k = 0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) k |= (m[i] != 0.0f) ? (1u << i) : 0u;
+    return k;
+}
 template <class V>
-CC_DEV cc_val<V> cc_transform(const float (&m)[12], V x, V y, V z)
+CC_DEV V cc_row_to(unsigned mask3, float m0, float m1, float m2, float o, V x, V y, V z)
+{
+    V acc = vbc<V>(o);
+    if (mask3 & 4u) acc = vfma(vbc<V>(m2), z, acc);
+    if (mask3 & 2u) acc = vfma(vbc<V>(m1), y, acc);
+    if (mask3 & 1u) acc = vfma(vbc<V>(m0), x, acc);
+    return acc;
+}
+// first (innermost) term: a plain product; a coefficient of exactly +-1 returns the operand itself
+// (1 * v == v, -1 * v == -v for every v), which spares the multiply
+template <class V>
+CC_DEV V cc_first_term(float m, V v)
+{
+    if (m == 1.0f) return v;
+    if (m == -1.0f) return vneg(v);
+    return vmul(vbc<V>(m), v);
+}
+template <class V>
+CC_DEV V cc_row_from(unsigned mask3, float m0, float m1, float m2, V x, V y, V z)
+{
+    switch (mask3 & 7u) {
+    case 0u: return vbc<V>(0.0f);
+    case 1u: return cc_first_term(m0, x);
+    case 2u: return cc_first_term(m1, y);
+    case 3u: return vfma(vbc<V>(m0), x, cc_first_term(m1, y));
+    case 4u: return cc_first_term(m2, z);
+    case 5u: return vfma(vbc<V>(m0), x, cc_first_term(m2, z));
+    case 6u: return vfma(vbc<V>(m1), y, cc_first_term(m2, z));
+    default: return vfma(vbc<V>(m0), x, vfma(vbc<V>(m1), y, cc_first_term(m2, z)));
+    }
+}
+// full matrix (no zero coefficient): the straight 9-term form
+template <class V>
+CC_DEV cc_val<V> cc_transform_full(const float (&m)[12], V x, V y, V z)
 {
     return cc_val<V>{vfma(vbc<V>(m[0]), x, vfma(vbc<V>(m[1]), y, vfma(vbc<V>(m[2]), z, vbc<V>(m[9])))),
                      vfma(vbc<V>(m[3]), x, vfma(vbc<V>(m[4]), y, vfma(vbc<V>(m[5]), z, vbc<V>(m[10])))),
                      vfma(vbc<V>(m[6]), x, vfma(vbc<V>(m[7]), y, vfma(vbc<V>(m[8]), z, vbc<V>(m[11])))),
                      vbc<V>(0.0f)};
 }
+// any matrix: `mask` says which coefficients are non-zero (in the specialised kernels it is a
+// compile-time constant and the branches fold; the interpreter runs this for "_M" micro-ops only)
+template <class V>
+CC_DEV cc_val<V> cc_transform(const float (&m)[12], unsigned mask, V x, V y, V z)
+{
+    if (mask == CC_MASK_FULL) return cc_transform_full(m, x, y, z);
+    return cc_val<V>{cc_row_to(mask, m[0], m[1], m[2], m[9], x, y, z), cc_row_to(mask >> 3, m[3], m[4], m[5], m[10], x, y, z),
+                     cc_row_to(mask >> 6, m[6], m[7], m[8], m[11], x, y, z), vbc<V>(0.0f)};
+}
 
 // common.cl:100-110 (matrix already divided by |q|^2; m[9] = |q|^2)
 template <class V>
-CC_DEV cc_val<V> cc_transform_from(const float (&m)[12], cc_val<V> in)
+CC_DEV cc_val<V> cc_transform_from_full(const float (&m)[12], cc_val<V> in)
 {
     return cc_val<V>{vfma(vbc<V>(m[0]), in.x, vfma(vbc<V>(m[1]), in.y, vmul(vbc<V>(m[2]), in.z))),
                      vfma(vbc<V>(m[3]), in.x, vfma(vbc<V>(m[4]), in.y, vmul(vbc<V>(m[5]), in.z))),
                      vfma(vbc<V>(m[6]), in.x, vfma(vbc<V>(m[7]), in.y, vmul(vbc<V>(m[8]), in.z))),
                      vmul(in.w, vbc<V>(m[9]))};
+}
+template <class V>
+CC_DEV cc_val<V> cc_transform_from(const float (&m)[12], unsigned mask, cc_val<V> in)
+{
+    if (mask == CC_MASK_FULL) return cc_transform_from_full(m, in);
+    const V w = (m[9] == 1.0f) ? in.w : vmul(in.w, vbc<V>(m[9]));
+    return cc_val<V>{cc_row_from(mask, m[0], m[1], m[2], in.x, in.y, in.z),
+                     cc_row_from(mask >> 3, m[3], m[4], m[5], in.x, in.y, in.z),
+                     cc_row_from(mask >> 6, m[6], m[7], m[8], in.x, in.y, in.z), w};
 }
 
 // shapes/simple2d.cl:16-46; k = (piOverN, r, r*sin, r*cos, 2*piOverN)
@@ -382,14 +448,14 @@ CC_DEV cc_val<V> cc_revolution_from(cc_val<V> flat, cc_val<V> co)
 
 // Fused primitive (loader pattern initial_transformation_to -> [store p] -> circle|rectangle ->
 // extrusion p -> [offset] -> [transformation_from]); bit-identical to the unfused sequence.
-template <bool RECT, class V, int G>
-CC_DEV void cc_prim_n(const float (&m)[12], const float (&mf)[12], float pa, float pb, float h, float d,
-                      const V (&x)[G], const V (&y)[G], const V (&z)[G], cc_val<V> (&L)[G])
+template <bool RECT, bool MASKED, class V, int G>
+CC_DEV void cc_prim_n(const float (&m)[12], const float (&mf)[12], unsigned mask, unsigned mask_from, float pa, float pb,
+                      float h, float d, const V (&x)[G], const V (&y)[G], const V (&z)[G], cc_val<V> (&L)[G])
 {
     V pz[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-        L[g] = cc_transform(m, x[g], y[g], z[g]);
+        L[g] = MASKED ? cc_transform(m, mask, x[g], y[g], z[g]) : cc_transform_full(m, x[g], y[g], z[g]);
         pz[g] = L[g].z;
     }
     if (RECT) cc_rectangle_n(pa, pb, L);
@@ -398,7 +464,7 @@ CC_DEV void cc_prim_n(const float (&m)[12], const float (&mf)[12], float pa, flo
 #pragma unroll
     for (int g = 0; g < G; ++g) {
         L[g].w = vsub(L[g].w, vbc<V>(d));
-        L[g] = cc_transform_from(mf, L[g]);
+        L[g] = MASKED ? cc_transform_from(mf, mask_from, L[g]) : cc_transform_from_full(mf, L[g]);
     }
 }
 

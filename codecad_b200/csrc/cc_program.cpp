@@ -78,6 +78,27 @@ void quat_matrix(const float *q, bool divide_by_scale, float *m, float *scale)
     if (scale) *scale = (float)s;
 }
 
+// bit k set <=> m[k] != 0 (cc-arith: zero coefficients are omitted from the row sums, cc_ops.cuh)
+uint32_t matrix_mask(const float *m)
+{
+    uint32_t k = 0;
+    for (int i = 0; i < 9; ++i)
+        if (m[i] != 0.0f) k |= 1u << i;
+    return k;
+}
+float mask_word(uint32_t mask)
+{
+    float f;
+    std::memcpy(&f, &mask, 4);
+    return f;
+}
+bool is_identity_from(const float *m, float scale)
+{
+    for (int i = 0; i < 9; ++i)
+        if (m[i] != ((i % 4 == 0) ? 1.0f : 0.0f)) return false;
+    return scale == 1.0f;
+}
+
 struct Emitter {
     std::vector<uint32_t> code;
     size_t last_header = (size_t)-1;  // index of the most recent instruction header
@@ -272,6 +293,14 @@ int cc_decode_program(const float *words, uint32_t n_words, cc_decoded *out, std
                 for (int k = 0; k < 9; ++k) q[16 + k] = (k % 4 == 0) ? 1.0f : 0.0f;
                 q[25] = 1.0f;
             }
+            {
+                const uint32_t mt = matrix_mask(q), mfrom = matrix_mask(q + 16);
+                q[26] = mask_word(mt | (mfrom << 9));
+                if (mt != 0x1FFu || mfrom != 0x1FFu) {  // re-tag as the masked variant
+                    uint32_t &hd = e.code[e.last_header];
+                    hd = CC_HDR(rect ? MOP_PRIM_RECT_M : MOP_PRIM_CIRCLE_M, CC_HDR_SRC(hd), CC_HDR_DST(hd), CC_HDR_LEN(hd));
+                }
+            }
             i += (size_t)fuse_len[i] - 1;
             ++n_micro;
             ++n_p;
@@ -346,13 +375,31 @@ int cc_decode_program(const float *words, uint32_t n_words, cc_decoded *out, std
             q = e.emit(w.op == W_TRANSFORMATION_TO ? MOP_T_TO : MOP_T_INIT, src, CC_LEN_T);
             quat_matrix(p, false, q, nullptr);
             q[9] = p[4]; q[10] = p[5]; q[11] = p[6];
+            q[12] = mask_word(matrix_mask(q));
+            if (matrix_mask(q) != 0x1FFu) {
+                uint32_t &hd = e.code[e.last_header];
+                hd = CC_HDR(w.op == W_TRANSFORMATION_TO ? MOP_T_TO_M : MOP_T_INIT_M, CC_HDR_SRC(hd), CC_HDR_DST(hd), CC_HDR_LEN(hd));
+            }
             cost(42, 42);
             break;
-        case W_TRANSFORMATION_FROM:
-            q = e.emit(MOP_T_FROM, src, CC_LEN_T);
-            quat_matrix(p, true, q, &q[9]);
+        case W_TRANSFORMATION_FROM: {
+            float mf[9], scale;
+            quat_matrix(p, true, mf, &scale);
             cost(50, 50);
+            // identity rotation and unit scale (38 % of the planetary scene's matrices): every row is
+            // 1 * v, the distance is w * 1 — the value does not change, so no micro-op is emitted
+            // (a following _store folds into the instruction that produced the value)
+            if (is_identity_from(mf, scale) && e.last_header != (size_t)-1) continue;
+            q = e.emit(MOP_T_FROM, src, CC_LEN_T);
+            std::memcpy(q, mf, sizeof mf);
+            q[9] = scale;
+            q[10] = mask_word(matrix_mask(q));
+            if (matrix_mask(q) != 0x1FFu) {
+                uint32_t &hd = e.code[e.last_header];
+                hd = CC_HDR(MOP_T_FROM_M, CC_HDR_SRC(hd), CC_HDR_DST(hd), CC_HDR_LEN(hd));
+            }
             break;
+        }
         case W_MIRROR: e.emit(MOP_MIRROR, src, CC_LEN_0); break;
         case W_SYMMETRICAL_TO: e.emit(MOP_SYM_TO, src, CC_LEN_0); break;
         case W_OFFSET:

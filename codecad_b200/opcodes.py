@@ -69,6 +69,8 @@ MICRO_OPS = [
     "REV_TO", "TWIST_TO", "T_INIT", "T_TO", "T_FROM", "MIRROR", "SYM_TO", "OFFSET", "SHELL",
     "REPETITION", "CREP_TO", "CREP_FROM", "GEAR", "EXTRUSION", "REV_FROM", "TWIST_FROM", "SYM_FROM",
     "UNION", "UNION_R", "ISECT", "ISECT_R", "SUB", "SUB_R", "PRIM_CIRCLE", "PRIM_RECT",
+    # "_M": the same op with a matrix that has zero coefficients (omitted from the row sums)
+    "T_INIT_M", "T_TO_M", "T_FROM_M", "PRIM_CIRCLE_M", "PRIM_RECT_M",
 ]
 SLOT_NONE = 0x1FF
 

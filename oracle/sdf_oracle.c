@@ -226,11 +226,30 @@ static inline v4 rounded_union(float r, v4 o1, v4 o2)
     return (o1.w < o2.w) ? o1 : o2;
 }
 
+/* cc-arith: a matrix row is accumulated innermost-first (z, y, x) and terms whose
+ * coefficient is exactly zero are OMITTED — a parameter-only simplification fixed at load time,
+ * like the quaternion -> matrix conversion itself.  (Multiplying by a zero coefficient would only
+ * decide the sign of an exactly-zero result.) */
+static inline float row_to(const float *m, float x, float y, float z, float o)
+{
+    float acc = o;
+    if (m[2] != 0.0f) acc = cc_fma(m[2], z, acc);
+    if (m[1] != 0.0f) acc = cc_fma(m[1], y, acc);
+    if (m[0] != 0.0f) acc = cc_fma(m[0], x, acc);
+    return acc;
+}
+static inline float row_from(const float *m, float x, float y, float z)
+{
+    float acc = 0.0f;
+    int have = 0;
+    if (m[2] != 0.0f) { acc = m[2] * z; have = 1; }
+    if (m[1] != 0.0f) { acc = have ? cc_fma(m[1], y, acc) : m[1] * y; have = 1; }
+    if (m[0] != 0.0f) { acc = have ? cc_fma(m[0], x, acc) : m[0] * x; have = 1; }
+    return acc;
+}
 static inline v4 apply_matrix(const float *m, float x, float y, float z, float ox, float oy, float oz)
 {
-    return mk(cc_fma(m[0], x, cc_fma(m[1], y, cc_fma(m[2], z, ox))),
-              cc_fma(m[3], x, cc_fma(m[4], y, cc_fma(m[5], z, oy))),
-              cc_fma(m[6], x, cc_fma(m[7], y, cc_fma(m[8], z, oz))), 0.0f);
+    return mk(row_to(m, x, y, z, ox), row_to(m + 3, x, y, z, oy), row_to(m + 6, x, y, z, oz), 0.0f);
 }
 
 /* simple2d.cl:16-46 */
@@ -421,9 +440,7 @@ static v4 evaluate(const prog_t *prog, float px, float py, float pz)
         case OP_TRANSFORMATION_FROM: { /* common.cl:100-110 */
             const float *m = I->k;
             float x = last.x, y = last.y, z = last.z;
-            last = mk(cc_fma(m[0], x, cc_fma(m[1], y, m[2] * z)),
-                      cc_fma(m[3], x, cc_fma(m[4], y, m[5] * z)),
-                      cc_fma(m[6], x, cc_fma(m[7], y, m[8] * z)), last.w * I->k[9]);
+            last = mk(row_from(m, x, y, z), row_from(m + 3, x, y, z), row_from(m + 6, x, y, z), last.w * I->k[9]);
             break;
         }
         case OP_MIRROR: last.x = -last.x; break;          /* common.cl:112-114 */

@@ -74,7 +74,7 @@ def test_box_is_one_fused_primitive():
         + ins("extrusion", 0, .5) + ins("_return")
     info, code = _lib.decode_program(words)
     ops = [o[1] for o in disassemble_microcode(code)]
-    assert ops == ["PRIM_RECT", "RETURN"] and info.n_fused == 1 and info.n_slots == 0
+    assert ops == ["PRIM_RECT_M", "RETURN"] and info.n_fused == 1 and info.n_slots == 0   # identity matrices: masked variant
     f = code.view(np.float32)
     assert list(f[1:10]) == [1, 0, 0, 0, 1, 0, 0, 0, 1]            # rotation matrix of the unit quaternion
     assert list(f[13:17]) == [.5, .5, .5, 0]                        # hw, hh, h, offset 0
@@ -87,7 +87,7 @@ def test_point_with_two_readers_is_not_fused():
         + ins("union", 5, -1) + ins("_return")
     info, code = _lib.decode_program(words)
     ops = list(disassemble_microcode(code))
-    assert [o[1] for o in ops] == ["T_INIT", "CIRCLE", "EXTRUSION", "LOAD", "SPHERE", "UNION", "RETURN"]
+    assert [o[1] for o in ops] == ["T_INIT_M", "CIRCLE", "EXTRUSION", "LOAD", "SPHERE", "UNION", "RETURN"]
     assert info.n_fused == 0 and info.n_slots == 2
     assert ops[0][3] == 0 and ops[2][2] == 0 and ops[2][3] == 1 and ops[3][2] == 0 and ops[5][2] == 1
 
@@ -135,3 +135,22 @@ def test_words_after_return_are_ignored():
     words = ins("initial_transformation_to", 0, *IDENT) + ins("sphere", 0, 1) + ins("_return") + [123.0, 456.0]
     info, _ = _lib.decode_program(words)
     assert info.n_words == len(words) - 2 and info.n_instructions == 3
+
+
+def test_matrix_zero_masks_and_identity_elision():
+    """cc-arith omits zero matrix coefficients: the loader tags such transforms "_M" with a mask
+    word, keeps full matrices on the plain micro-ops and drops identity transformation_from ops."""
+    import math
+    q_rot = (0.0, 0.0, math.sin(0.3), math.cos(0.3))            # rotation about z: zeros in the matrix
+    q_gen = (0.1825742, 0.3651484, 0.5477226, 0.7302967)        # general rotation: no zero
+    words = ins("initial_transformation_to", 0, *q_rot, 1.0, 2.0, 3.0) + ins("sphere", 0, 1) \
+        + ins("transformation_from", 0, 0.0, 0.0, 0.0, 1.0) + ins("_store", 1) \
+        + ins("initial_transformation_to", 0, *q_gen, 0.0, 0.0, 0.0) + ins("sphere", 0, 2) \
+        + ins("transformation_from", 0, *q_gen) + ins("union", 1, -1) + ins("_return")
+    info, code = _lib.decode_program(words)
+    ops = list(disassemble_microcode(code))
+    assert [o[1] for o in ops] == ["T_INIT_M", "SPHERE", "T_INIT", "SPHERE", "T_FROM", "UNION", "RETURN"]
+    assert ops[1][3] != 0x1FF                                    # the _store folded into SPHERE (identity T_FROM elided)
+    mask = int(code[ops[0][0] + 13])
+    m = code.view(np.float32)[ops[0][0] + 1: ops[0][0] + 10]
+    assert mask == sum(1 << i for i in range(9) if m[i] != 0) == 0x11B
