@@ -316,7 +316,21 @@ def workload_config(n, world):
 
 # ---- our arm ------------------------------------------------------------------------------------
 
+def _stdout_to_stderr():
+    """Everything libraries print to stdout (NCCL's version banner under torchrun, ...) goes to
+    stderr; the one JSON line is written to the returned descriptor, the original stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return real
+
+
+def _emit(fd, line):
+    os.write(fd, (json.dumps(line) + "\n").encode())
+
+
 def run_ours(args):
+    out_fd = _stdout_to_stderr()
     rank, world, local, torch, dist = dist_setup(args.gpus)
     import importlib
     from codecad_b200 import _lib
@@ -494,7 +508,7 @@ def run_ours(args):
         "tier": tier, "specialize_s": specialize_s, "interpreter_tier": interp, "mass_properties": mass, "subdivision": subdiv, "mesh_export": mesh,
         "device": info.name.decode(),
     }
-    print(json.dumps(line))
+    _emit(out_fd, line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
