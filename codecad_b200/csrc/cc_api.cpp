@@ -31,7 +31,7 @@ struct Context {
     uint64_t launches = 0, points = 0;
     int pts = 0, prog_space = 0;  // tuning overrides, 0 = auto
     int jit_mode = 1;             // 0 never, 1 background (default), 2 compile at first use and wait
-    uint32_t jit_max_ops = 512;   // programs longer than this are not specialised automatically
+    uint32_t jit_max_ops = 4096;  // programs longer than this are not specialised automatically
     uint64_t next_program_id = 1;
     uint64_t constant_program = 0;  // id of the program in the __constant__ window
     // look-back scratch

@@ -24,6 +24,7 @@ struct cc_jit_cfg {
     int min_blocks = 2;  // __launch_bounds__ min CTAs per SM (register cap)
     int smem_min_len = 12;   // values live for at least this many micro-ops go to shared-memory cells
     int smem_max_cells = 6;  // budget of cells (0 = keep everything in registers)
+    int segment_ops = 96;    // programs longer than ~1.5x this are cut into functions of this many micro-ops
 };
 struct cc_jit_job;
 

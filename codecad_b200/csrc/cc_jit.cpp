@@ -136,8 +136,9 @@ bool read_file(const std::string &path, std::string *out)
 
 struct Gen {
     const std::vector<uint32_t> &code;
-    std::ostringstream body, consts;
+    std::ostringstream body, consts, params;
     int n_tables = 0;
+    size_t n_params = 0;  // words in the __constant__ parameter table of the out-of-line ops
     int n_cells = 0;
 
     explicit Gen(const std::vector<uint32_t> &c) : code(c) {}
@@ -317,11 +318,41 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
         ", g), P_); px[g] = P_.x; py[g] = P_.y; pz[g] = P_.z; }\n";
     g.n_cells = n_cells;
 
+    // ---- segments: long programs are cut into __noinline__ functions of seg_ops micro-ops each.
+    // One 1000-op function (the 500-box scene) takes NVRTC/ptxas 5 minutes; compile time grows
+    // faster than linearly with the function size.  Values that cross a segment boundary travel
+    // through a State struct (local memory, L1-resident; a few round trips per hundred micro-ops).
+    const int n_ops_total = (int)op_def.size();
+    int seg_ops = cfg.segment_ops;
+    if (seg_ops <= 0 || n_ops_total <= seg_ops + seg_ops / 2) seg_ops = n_ops_total + 1;
+    const bool segmented = seg_ops <= n_ops_total;
+    auto seg_of = [&](int op) { return op / seg_ops; };
+    const int n_segs = segmented ? seg_of(n_ops_total - 1) + 1 : 1;
+    std::vector<char> crosses(iv.size(), 0);  // register interval read in a later segment than its definition
+    if (segmented)
+        for (size_t k = 0; k < iv.size(); ++k)
+            crosses[k] = iv[k].cell < 0 && iv[k].last_read != iv[k].def && seg_of(iv[k].def) != seg_of(iv[k].last_read);
+    const bool out_of_line = segmented && pts <= 2;  // (the table-driven forms take one lane vector)
+    std::vector<std::string> seg_text((size_t)n_segs);
+    std::vector<std::vector<int>> seg_copy_in((size_t)n_segs);
+    if (segmented)
+        for (int i = 0; i < n_ops_total; ++i) {
+            const int u = op_use[i];
+            if (u >= 0 && crosses[u] && seg_of(i) != seg_of(iv[u].def)) {
+                std::vector<int> &lst = seg_copy_in[(size_t)seg_of(i)];
+                if (std::find(lst.begin(), lst.end(), u) == lst.end()) lst.push_back(u);
+            }
+        }
+
     uint32_t pc = 0;
     for (int op_index = 0;; ++op_index) {
         if (pc >= c.size()) {
             *err = "internal: microcode without RETURN";
             return CC_ERR_INVALID_PROGRAM;
+        }
+        if (segmented && op_index > 0 && op_index % seg_ops == 0) {  // cut: what was emitted so far is one segment
+            seg_text[(size_t)seg_of(op_index - 1)] = o.str();
+            o.str(std::string());
         }
         const uint32_t h = c[pc], op = CC_HDR_OP(h), src_slot = CC_HDR_SRC(h), dst = CC_HDR_DST(h);
         o << "        // pc " << pc << "\n";
@@ -350,6 +381,13 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
             const bool rect = (op == MOP_PRIM_RECT || op == MOP_PRIM_RECT_M);
             const std::string X = coord_smem ? "px[g]" : "gx[g]", Y = coord_smem ? "py[g]" : "gy[g]",
                               Z = coord_smem ? "pz[g]" : "gz[g]";
+            if (out_of_line) {  // large program: call the shared copy with this op's row of the parameter table
+                const size_t off = g.n_params;
+                for (int i = 1; i <= 27; ++i) g.params << (g.n_params++ ? ", " : "") << g.C(pc + i);
+                o << "        {\n" << coord_load << "          CC_EACH L[g] = cc_prim_table<" << (rect ? "true" : "false")
+                  << ", V>(cc_par + " << off << ", " << X << ", " << Y << ", " << Z << ");\n        }\n";
+                break;
+            }
             o << "        {\n" << coord_load << "          V pz_[G];\n"
               << "          CC_EACH { L[g] = " << g.transform_to(pc + 1, X, Y, Z) << "; pz_[g] = L[g].z; }\n";
             if (rect) o << "          cc_rectangle_n(" << g.args(pc, 13, 2) << ", L);\n";
@@ -409,7 +447,10 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
             break;
         case MOP_SYM_FROM: o << "        CC_EACH L[g] = cc_op_sym_from(L[g], " << B << ");\n"; break;
         case MOP_UNION: o << "        CC_EACH L[g] = cc_op_union(L[g], " << B << ");\n"; break;
-        case MOP_UNION_R: o << "        CC_EACH L[g] = cc_rounded_union(" << g.F(pc + 1) << ", L[g], " << B << ");\n"; break;
+        case MOP_UNION_R:
+            o << "        CC_EACH L[g] = " << (out_of_line ? "cc_rounded_union_fn(" : "cc_rounded_union(") << g.F(pc + 1)
+              << ", L[g], " << B << ");\n";
+            break;
         case MOP_ISECT: o << "        CC_EACH L[g] = cc_op_isect(L[g], " << B << ");\n"; break;
         case MOP_ISECT_R: o << "        CC_EACH L[g] = cc_op_isect_r(" << g.F(pc + 1) << ", L[g], " << B << ");\n"; break;
         case MOP_SUB: o << "        CC_EACH L[g] = cc_op_sub(L[g], " << B << ");\n"; break;
@@ -426,6 +467,7 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
                 // never read: nothing to keep
             } else if (iv[d].cell < 0) {
                 o << "        Val I" << d << "[G]; CC_EACH I" << d << "[g] = L[g];\n";
+                if (crosses[d]) o << "        CC_EACH st.I" << d << "[g] = L[g];\n";
             } else if (iv[d].z_only) {
                 o << "        CC_EACH cc_slot_store_z(CC_CELL(" << iv[d].cell << ", g), L[g].z);\n";
             } else {
@@ -445,12 +487,38 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
       << "#define CC_EACH _Pragma(\"unroll\") for (int g = 0; g < G; ++g)\n"
       << "#define CC_CELL(cell, g) (sm + ((cell) * PTS + (g) * cc_lane<V>::N) * CC_THREADS)\n"
       << "#define CC_JIT_SMEM_BYTES " << (size_t)n_cells * pts * cfg.threads * 16 << "\n"
-      << g.consts.str() << "struct SceneEval {\n    float4 *sm;  // this thread's column of the value cells\n"
-      << "    __device__ __forceinline__ void operator()(const V (&gx)[G], const V (&gy)[G], const V (&gz)[G],\n"
-      << "                                               Val (&L)[G]) const\n    {\n";
-    if (coord_smem)
-        s << "        CC_EACH cc_slot_store(CC_CELL(" << coord_cell << ", g), Val{gx[g], gy[g], gz[g], vbc<V>(0.f)});\n";
-    s << "        CC_EACH L[g] = Val{vbc<V>(0.f), vbc<V>(0.f), vbc<V>(0.f), vbc<V>(0.f)};\n" << o.str() << "    }\n};\n";
+      << g.consts.str();
+    if (g.n_params) s << "__constant__ float cc_par[" << g.n_params << "] = {" << g.params.str() << "};\n";
+    if (!segmented) {
+        s << "struct SceneEval {\n    float4 *sm;  // this thread's column of the value cells\n"
+          << "    __device__ __forceinline__ void operator()(const V (&gx)[G], const V (&gy)[G], const V (&gz)[G],\n"
+          << "                                               Val (&L)[G]) const\n    {\n";
+        if (coord_smem)
+            s << "        CC_EACH cc_slot_store(CC_CELL(" << coord_cell << ", g), Val{gx[g], gy[g], gz[g], vbc<V>(0.f)});\n";
+        s << "        CC_EACH L[g] = Val{vbc<V>(0.f), vbc<V>(0.f), vbc<V>(0.f), vbc<V>(0.f)};\n" << o.str() << "    }\n};\n";
+    } else {
+        seg_text[(size_t)n_segs - 1] = o.str();
+        s << "struct State {\n    Val L[G];\n    V gx[G], gy[G], gz[G];\n";
+        for (size_t k = 0; k < iv.size(); ++k)
+            if (crosses[k]) s << "    Val I" << k << "[G];\n";
+        s << "};\n";
+        for (int k = 0; k < n_segs; ++k) {
+            s << "static __device__ __noinline__ void cc_seg_" << k << "(float4 *sm, State &st)\n{\n"
+              << "        Val L[G]; V gx[G], gy[G], gz[G];\n"
+              << "        CC_EACH { L[g] = st.L[g]; gx[g] = st.gx[g]; gy[g] = st.gy[g]; gz[g] = st.gz[g]; }\n";
+            for (int u : seg_copy_in[(size_t)k]) s << "        Val I" << u << "[G]; CC_EACH I" << u << "[g] = st.I" << u << "[g];\n";
+            s << seg_text[(size_t)k] << "        CC_EACH st.L[g] = L[g];\n}\n";
+        }
+        s << "struct SceneEval {\n    float4 *sm;\n"
+          << "    __device__ __forceinline__ void operator()(const V (&gx)[G], const V (&gy)[G], const V (&gz)[G],\n"
+          << "                                               Val (&L)[G]) const\n    {\n        State st;\n";
+        if (coord_smem)
+            s << "        CC_EACH cc_slot_store(CC_CELL(" << coord_cell << ", g), Val{gx[g], gy[g], gz[g], vbc<V>(0.f)});\n";
+        s << "        CC_EACH { st.L[g] = Val{vbc<V>(0.f), vbc<V>(0.f), vbc<V>(0.f), vbc<V>(0.f)}; st.gx[g] = gx[g]; st.gy[g] = gy[g]; "
+             "st.gz[g] = gz[g]; }\n";
+        for (int k = 0; k < n_segs; ++k) s << "        cc_seg_" << k << "(sm, st);\n";
+        s << "        CC_EACH L[g] = st.L[g];\n    }\n};\n";
+    }
     const char *names[4] = {"float4", "pymcubes", "classify", "mass"};
     const char *sinks[4] = {"CC_SINK_FLOAT4", "CC_SINK_PYMCUBES", "CC_SINK_CLASSIFY", "CC_SINK_MASS"};
     // min CTAs per SM: caps the registers so that the wanted number of warps stays resident
@@ -528,6 +596,8 @@ cc_jit_cfg cc_jit_default_cfg(const cc_decoded &dec, int pts)
         if (const char *t = getenv("CODECAD_B200_JIT_SMEM_CELLS")) c.smem_max_cells = std::max(0, std::min(fit, atoi(t)));
     }
     if (const char *t = getenv("CODECAD_B200_JIT_SMEM_MIN_LEN")) c.smem_min_len = atoi(t);
+    c.segment_ops = 320;  // planetary (267 micro-ops) stays one function; the 500-box scene becomes 4
+    if (const char *t = getenv("CODECAD_B200_JIT_SEGMENT_OPS")) c.segment_ops = atoi(t);
     return c;
 }
 

@@ -513,6 +513,32 @@ __device__ __noinline__ float4 cc_polygon2d_table(const float *table, uint32_t n
     return cc_polygon2d_core(cc_table_fetch{table}, n, co);
 }
 
+// ---- out-of-line forms for LARGE programs (specialised kernels of more than a few hundred
+// micro-ops): one copy of the code, parameters read from a __constant__ table through a uniform
+// pointer.  Inlining 500 fused primitives costs NVRTC minutes and produces 880 KB of straight-line
+// code; called like this the kernel compiles in seconds and its body stays in the instruction cache.
+// t = the micro-op's parameter words 1..27 (cc_kernels.cu cc_prim): m,o | a b h d | m' | scale | masks
+template <bool RECT, class V>
+__device__ __noinline__ cc_val<V> cc_prim_table(const float *__restrict__ t, V x, V y, V z)
+{
+    float m[12], mf[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) m[i] = t[i];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) mf[i] = t[16 + i];
+    mf[10] = mf[11] = 0.f;
+    const unsigned masks = __float_as_uint(t[26]);
+    const V xs[1] = {x}, ys[1] = {y}, zs[1] = {z};
+    cc_val<V> L[1];
+    cc_prim_n<RECT, true, V, 1>(m, mf, masks & 0x1FFu, (masks >> 9) & 0x1FFu, t[12], t[13], t[14], t[15], xs, ys, zs, L);
+    return L[0];
+}
+template <class V>
+__device__ __noinline__ cc_val<V> cc_rounded_union_fn(float r, cc_val<V> a, cc_val<V> b)
+{
+    return cc_rounded_union(r, a, b);
+}
+
 // ---- one entry point per micro-op over lane vectors (shared by the interpreter and the
 //      scene-specialised kernels).  Cheap ops are packed; the heavy, rarely dominant ones run
 //      their one-point form lane by lane. ----------------------------------------------------

@@ -105,7 +105,8 @@ int cc_program_use_specialized(cc_program *prog, int enable); /* returns 1 if sp
  * $CODECAD_B200_CACHE or ~/.cache/codecad_b200); launches switch over when it is ready.  Results
  * are bit-identical in both tiers.  mode: 0 = interpreter only, 1 = background (default),
  * 2 = compile at first use and wait.  Environment: CODECAD_B200_JIT.  Programs with more than
- * CODECAD_B200_JIT_MAX_OPS (512) micro-ops are only specialised on request.  Returns the old mode. */
+ * CODECAD_B200_JIT_MAX_OPS (4096) micro-ops are only specialised on request; programs of more than a
+ * few hundred micro-ops are compiled as segments that call shared, table-driven op functions.  Returns the old mode. */
 int cc_set_jit_mode(int mode);
 /* Blocks until the specialised kernels of the sinks in `sink_mask` (0 = all) are compiled and
  * loaded, starting their compilation if necessary; returns how many are ready.  compile_seconds

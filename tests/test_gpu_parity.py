@@ -225,7 +225,7 @@ def test_mass_properties_known_answers(cb, scenes, name):
 
 # ---- scene-specialised (NVRTC) kernels: same op library, same body -> same bits -----------------
 
-JIT_SCENES = ["cfg_csg_example", "cfg_menger_sponge", "cfg_airfoil", "cfg_planetary", "cfg_synthetic32",
+JIT_SCENES = ["cfg_synthetic500", "cfg_csg_example", "cfg_menger_sponge", "cfg_airfoil", "cfg_planetary", "cfg_synthetic32",
               "dsdf3d_extreme_twisted_revolve", "dsdf2d_gear", "dsdf2d_regular_polygon3", "dsdf3d_rotated_pattern_3d",
               "dsdf3d_revolved_pentagon", "x_repetition", "x_smooth_isect", "dsdf2d_polygon2d_non_convex"]
 
