@@ -313,3 +313,29 @@ def test_tiered_execution_modes(cb, scenes):
         assert cb.mass_properties(a.compiled(), 1.0, 32).volume == pytest.approx(vol, rel=1e-12)
     finally:
         _lib.check(L.cc_set_jit_mode(0))
+
+
+@pytest.mark.parametrize("seg", ["7", "40"])
+@pytest.mark.parametrize("name", ["cfg_planetary", "cfg_menger_sponge", "cfg_synthetic32", "x_smooth_isect"])
+def test_specialized_segmented_programs(cb, scenes, name, seg, monkeypatch):
+    """Large programs are generated as __noinline__ segments with table-driven primitives; forcing
+    tiny segments on ordinary scenes exercises every cross-segment value path."""
+    from codecad_b200.cl_util.buffer import ProgramBuffer
+    monkeypatch.setenv("CODECAD_B200_JIT_SEGMENT_OPS", seg)
+    s = scenes[name]
+    prog = ProgramBuffer(s.words)
+    prog.specialize(2, ProgramBuffer.SINK_FLOAT4 | ProgramBuffer.SINK_CLASSIFY)
+    dims = (16, 9, 37) if s.dimension == 3 else (33, 17, 2)
+    corner, step = s.grid(40)
+    assert _same(_f4(cb.grid_eval(prog, corner, step, dims)), oracle.grid_eval(s.words, corner, step, dims))
+    from codecad_b200.cl_util import opencl_manager
+    from codecad_b200.geometry import Vector
+    sdims = (17, 13, 29) if s.dimension == 3 else (40, 37, 1)
+    thr = np.float32(step * np.sqrt(s.dimension) / 2)
+    want = oracle.subdivision_step(s.words, corner, step, thr, sdims)
+    counter, lst = _step_buffers(cb, sdims[0] * sdims[1] * sdims[2])
+    ev = opencl_manager.k.subdivision_step(sdims, None, prog, Vector(*corner).as_float4(), step, thr, counter, lst)
+    n = int(counter.read(wait_for=[ev])[0])
+    got = lst.read()[:n]
+    got = np.stack([got["x"], got["y"], got["z"], got["w"]], axis=-1)
+    assert n == len(want) and _same(got, want)
