@@ -41,25 +41,41 @@ class CompiledScene:
         return self._buffer
 
 
-def make_program(shape):
-    """float32 instruction words of `shape` (nodes/program.py:74-76)."""
+def make_program(shape, random_passes=None):
+    """float32 instruction words of `shape` (nodes/program.py:74-76).
+
+    `random_passes` (not in the reference): the reference's scheduler keeps
+    the best of 2 deterministic + 100 *unseeded* random orderings, each on a deep copy of the node
+    graph (nodes/scheduler.py:146-178) — 2 s for the planetary scene, 28-38 s for 500 boxes, and a
+    different program on every run.  An integer runs that many random passes instead; 0 gives a
+    reproducible program ~50x sooner.  Register pressure, the thing the random passes optimise, is
+    irrelevant here: the loader renames registers by liveness (cc_program.cpp).  The default (None)
+    is the reference's behaviour, unchanged."""
     if isinstance(shape, CompiledScene):
         return shape.words
     if isinstance(shape, np.ndarray):
         return np.ascontiguousarray(shape, dtype=np.float32)
     try:
         from codecad.nodes import program as _ref_program  # the reference's compiler
+        from codecad.nodes import scheduler as _ref_scheduler
     except ImportError as exc:
         raise TypeError(
             "make_program() needs a CompiledScene / word array, or the reference `codecad` "
             "package on sys.path to compile %r" % (shape,)) from exc
-    return _ref_program.make_program(shape)
+    if random_passes is None:
+        return _ref_program.make_program(shape)
+    original = _ref_scheduler.randomized_scheduler
+    _ref_scheduler.randomized_scheduler = lambda node, random_passes=int(random_passes): original(node, random_passes)
+    try:
+        return _ref_program.make_program(shape)
+    finally:
+        _ref_scheduler.randomized_scheduler = original
 
 
-def make_program_buffer(shape):
+def make_program_buffer(shape, random_passes=None):
     """Device-resident program for `shape` (nodes/program.py:79-84)."""
     if isinstance(shape, ProgramBuffer):
         return shape
     if isinstance(shape, CompiledScene):
         return shape.program_buffer()
-    return ProgramBuffer(make_program(shape))
+    return ProgramBuffer(make_program(shape, random_passes))

@@ -91,3 +91,30 @@ def test_compute_without_gpu_fails_loudly():
             print("ok")
     """)
     assert out.strip().splitlines()[-1] in ("ok", "gpu present")
+
+
+def test_opt_in_deterministic_program_build():
+    """make_program(shape, random_passes=0): reproducible, much faster, same geometry."""
+    out = _run("""
+        import time, numpy as np
+        import codecad_b200.dropin as d
+        codecad = d.load()
+        import codecad.shapes as s
+        from codecad_b200.nodes import make_program
+        from codecad_b200 import _lib
+        import oracle
+        parts = [s.box(3, 4, 5).rotated((1, 2, 3), 10 * i).translated(4 * i, 0, 0) for i in range(12)]
+        shape = s.union(parts) - s.sphere(3).translated(6, 1, 0)
+        t0 = time.perf_counter(); w_ref = make_program(shape); t_ref = time.perf_counter() - t0
+        t0 = time.perf_counter(); w0 = make_program(shape, random_passes=0); t_fast = time.perf_counter() - t0
+        assert np.array_equal(w0, make_program(shape, random_passes=0))          # reproducible
+        assert t_fast * 5 < t_ref, (t_fast, t_ref)
+        info, _ = _lib.decode_program(w0)                                          # a valid program
+        assert info.n_instructions > 40
+        corner, step, dims = np.array([-6, -8, -8], np.float32), np.float32(0.9), (60, 18, 18)
+        a = oracle.grid_eval(w_ref, corner, step, dims)
+        b = oracle.grid_eval(w0, corner, step, dims)
+        assert np.allclose(a[..., 3], b[..., 3], rtol=1e-5, atol=1e-5)             # same distances
+        print("ok %.2f s -> %.3f s" % (t_ref, t_fast))
+    """)
+    assert out.strip().splitlines()[-1].startswith("ok")
