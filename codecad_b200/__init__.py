@@ -17,7 +17,7 @@ from . import opcodes  # noqa: F401
 from .geometry import BoundingBox, Vector  # noqa: F401
 from .mass_properties import MassProperties, mass_properties  # noqa: F401
 from .subdivision import calculate_block_sizes, subdivision  # noqa: F401
-from .grid_eval import grid_eval, grid_eval_pymcubes  # noqa: F401
+from .grid_eval import evaluate_points, grid_eval, grid_eval_pymcubes  # noqa: F401
 from .nodes import CompiledScene, make_program, make_program_buffer  # noqa: F401
 
 __all__ = [

@@ -607,6 +607,24 @@ int cc_grid_eval(const cc_program *prog, const float corner[3], float step, uint
     return make_event(ev, g.compute);
 }
 
+int cc_evaluate_points(const cc_program *prog, const float *d_points, uint64_t n, void *d_out, cc_event **ev)
+{
+    NEED_INIT();
+    if (!prog || !d_points || !d_out) return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
+    const uint64_t chunk = 1ull << 30;
+    for (uint64_t i0 = 0; i0 < n; i0 += chunk) {
+        const uint32_t cnt = (uint32_t)std::min<uint64_t>(chunk, n - i0);
+        cc_eval_args a;
+        fill_common(&a, prog);
+        a.nx = cnt; a.ny = 1; a.nz = 1; a.n_blocks = 1;
+        a.points = d_points + 4 * i0;
+        a.out = (char *)d_out + i0 * 16;
+        int rc = launch(CC_SINK_FLOAT4, prog, a, cnt);
+        if (rc) return rc;
+    }
+    return make_event(ev, g.compute);
+}
+
 int cc_grid_eval_to_host(const cc_program *prog, const float corner[3], float step, uint32_t nx, uint32_t ny,
                          uint32_t nz, uint32_t x_offset, int layout, void *h_out)
 {

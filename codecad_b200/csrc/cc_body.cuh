@@ -58,6 +58,10 @@ CC_DEV void cc_kernel_body(const cc_eval_args &a, EVAL &eval)
         gx[j] = cc_fma(a.step, (float)(ix[j] + a.x_offset), cx);
         gy[j] = cc_fma(a.step, (float)iy[j], cy);
         gz[j] = cc_fma(a.step, (float)iz[j], cz);
+        if (a.points) {  // warp-uniform: point list instead of a grid
+            const float4 p = reinterpret_cast<const float4 *>(a.points)[c];
+            gx[j] = p.x; gy[j] = p.y; gz[j] = p.z;
+        }
     }
 
     float4 L[PTS];

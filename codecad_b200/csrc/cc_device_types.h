@@ -45,6 +45,9 @@ struct cc_eval_args {
     // decoupled look-back scratch (ordered compaction)
     uint32_t *ticket;
     unsigned long long *tile_status;
+    // optional: evaluate at these points (x, y, z, unused) instead of grid coordinates; cell c of
+    // the launch reads points[c] (used with nx = number of points, ny = nz = 1)
+    const float *points;  // 16-byte aligned quadruples
 };
 
 #endif

@@ -75,5 +75,31 @@ def grid_eval_pymcubes(shape, corner, step, dims, out=None, device_out=None):
     return _eval(shape, corner, step, dims, _lib.LAYOUT_PYMCUBES_FLOAT, 0, out, True)
 
 
+def evaluate_points(shape, points):
+    """evaluate() at arbitrary points: points [n][3] (or [n][4]) -> float32 [n][4] = (gradient, distance).
+    Host arrays in and out."""
+    program = make_program_buffer(shape)
+    pts = np.asarray(points, dtype=np.float32)
+    n = len(pts)
+    p4 = np.zeros((n, 4), np.float32)
+    p4[:, :3] = pts[:, :3]
+    out = np.empty((n, 4), np.float32)
+    if n == 0:
+        return out
+    L = _lib.lib()
+    d_in, d_out = ctypes.c_void_p(), ctypes.c_void_p()
+    _lib.check(L.cc_buffer_alloc(n * 16, ctypes.byref(d_in)))
+    _lib.check(L.cc_buffer_alloc(n * 16, ctypes.byref(d_out)))
+    try:
+        _lib.check(L.cc_memcpy_h2d_async(d_in, p4.ctypes.data, n * 16, None))
+        _lib.check(L.cc_evaluate_points(program.handle, d_in, n, d_out, None))
+        _lib.check(L.cc_memcpy_d2h_async(out.ctypes.data, d_out, n * 16, None))
+        _lib.check(L.cc_synchronize())
+    finally:
+        L.cc_buffer_free(d_in)
+        L.cc_buffer_free(d_out)
+    return out
+
+
 def synchronize():
     _lib.check(_lib.lib().cc_synchronize())

@@ -143,6 +143,12 @@ int cc_grid_eval(const cc_program *prog, const float corner[3], float step,
                  uint32_t nx, uint32_t ny, uint32_t nz, uint32_t x_offset, int layout,
                  void *d_out, cc_event **ev);
 
+/* evaluate() at arbitrary points: d_points = n x (x, y, z, unused) float4 on the device, d_out = n
+ * float4 (gradient, distance).  This is what the reference's other kernels do around evaluate()
+ * (tests/test_dsdf.cl:7-72 estimate_direction / actual_distance_to_surface, rendering/ray_caster.cl,
+ * rendering/bitmap.cl): the call lets such callers live on the host side of the boundary. */
+int cc_evaluate_points(const cc_program *prog, const float *d_points, uint64_t n, void *d_out, cc_event **ev);
+
 /* Same, result delivered to HOST memory: slabs of the grid are evaluated into a device
  * ring and copied out on the copy stream while the next slab computes.  Blocking.
  * Replaces kernel + Buffer.read()  (rendering/mesh.py:53-61). */

@@ -339,3 +339,29 @@ def test_specialized_segmented_programs(cb, scenes, name, seg, monkeypatch):
     got = lst.read()[:n]
     got = np.stack([got["x"], got["y"], got["z"], got["w"]], axis=-1)
     assert n == len(want) and _same(got, want)
+
+
+# ---- evaluate() at arbitrary points (cc_evaluate_points) ----------------------------------------
+
+@pytest.mark.parametrize("tier", ["interpreter", "specialised"])
+@pytest.mark.parametrize("name", ["cfg_planetary", "cfg_csg_example", "dsdf2d_gear", "dsdf3d_extreme_twisted_revolve",
+                                  "x_repetition", "cfg_synthetic32"])
+def test_evaluate_points_bit_exact(cb, scenes, name, tier):
+    from codecad_b200.cl_util.buffer import ProgramBuffer
+    s = scenes[name]
+    rng = np.random.default_rng(7)
+    a, b = np.asarray(s.box_a, np.float64), np.asarray(s.box_b, np.float64)
+    a, b = np.where(np.isfinite(a), a, -10.0), np.where(np.isfinite(b), b, 10.0)
+    n = 1000 + 37                                           # ragged tail tile
+    pts = (a + (b - a) * (rng.random((n, 3)) * 1.4 - 0.2)).astype(np.float32)
+    if s.dimension == 2:
+        pts[:, 2] = 0
+    pts[:3] = [[0, 0, 0], [np.inf, 0, 0], [np.nan, 1, 2]]   # special operands travel the same paths
+    prog = ProgramBuffer(s.words)
+    if tier == "specialised":
+        prog.specialize(2, ProgramBuffer.SINK_FLOAT4)
+        assert prog.use_specialized(True)
+    want = oracle.evaluate_points(s.words, pts)
+    got = cb.evaluate_points(prog, pts)
+    assert got.shape == (n, 4) and _same(got, want)
+    assert cb.evaluate_points(prog, np.zeros((0, 3), np.float32)).shape == (0, 4)
