@@ -69,6 +69,18 @@ int cc_upload_constant_program(const uint32_t *h_code, uint32_t n_words, void *s
 uint32_t cc_tile_points(const cc_launch_cfg &cfg);
 size_t cc_eval_smem_bytes(const cc_launch_cfg &cfg, uint32_t n_slots, uint32_t code_words);
 
+// image renderers around evaluate() (rendering/ray_caster.cl, rendering/bitmap.cl)
+struct cc_render_launch {
+    const uint32_t *code;
+    uint32_t code_words, n_slots;
+    float origin[3], forward[3], up[3], right[3];
+    float pixel_tolerance, box_radius, min_distance, max_distance, floor_z, step_size;
+    uint32_t options, w, h;
+    uint8_t *out;
+    unsigned long long *eval_count;
+};
+int cc_launch_render(int ray, int prog_space, const cc_render_launch &r, void *stream);
+
 // hierarchy helper kernels
 struct cc_level_geom {
     double ox, oy, oz;      // origin
@@ -92,6 +104,27 @@ int cc_launch_mass_expand_children(const double *d_parent_corners, const uint32_
 int cc_launch_mass_integrals(const double *d_corners, const uint32_t *d_sums, uint32_t n_blocks, double s,
                              double *d_integrals /* [10] accumulated with Kahan, single CTA */,
                              void *stream);
+
+// ---- 2-D outline extraction (cc_polygon.cu, rendering/polygon2d.cl) -----------------------------
+#ifdef __CUDACC__
+#include <vector_types.h>
+#else
+struct float4;
+struct float2;
+#endif
+struct cc_polygon_args {
+    float corner_x, corner_y, step;  // boxCorner, boxStep (single block)
+    const float *block_corners;      // optional: [n_blocks][2] fp32 corners (batched form)
+    uint32_t cx, cy;                 // the OpenCL global size: cells per axis = samples - 1
+    uint32_t n_blocks;
+    const float4 *corners;           // [n_blocks][cx+1][cy+1]
+    float2 *vertices;                // [n_blocks][cx][cy][2]
+    uint32_t *links;                 // same shape
+    uint32_t *starts;                // [n_blocks][max_starts]
+    uint32_t *start_counter;         // [n_blocks], zeroed by the caller
+    uint32_t max_starts;             // <= 1024
+};
+int cc_launch_process_polygon(const cc_polygon_args &a, void *stream);
 
 // ---- marching cubes over leaf blocks (cc_mesh.cu) ---------------------------------------------
 struct cc_mesh_args {

@@ -40,6 +40,25 @@ class Vector(collections.namedtuple("Vector", "x y z")):
     def __abs__(self):
         return math.sqrt(self.x * self.x + self.y * self.y + self.z * self.z)
 
+    def abs_squared(self):
+        return self.dot(self)
+
+    def dot(self, other):
+        return self.x * other.x + self.y * other.y + self.z * other.z
+
+    def cross(self, other):
+        return Vector(self.y * other.z - self.z * other.y, self.z * other.x - self.x * other.z,
+                      self.x * other.y - self.y * other.x)
+
+    def normalized(self):
+        return self / abs(self)
+
+    def elementwise_mul(self, other):
+        return Vector(self.x * other.x, self.y * other.y, self.z * other.z)
+
+    def elementwise_div(self, other):
+        return Vector(self.x / other.x, self.y / other.y, self.z / other.z)
+
     def max(self, other=None):
         if other is None:
             return max(self.x, self.y, self.z)
@@ -55,6 +74,9 @@ class Vector(collections.namedtuple("Vector", "x y z")):
 
     def flattened(self):
         return Vector(self.x, self.y, 0)
+
+    def as_float2(self):
+        return np.array((self.x, self.y), dtype=FLOAT2)
 
     def as_float4(self, w=0):
         """numpy structured float4 scalar, rounded to fp32 (geometry.py:98-99)."""

@@ -149,6 +149,25 @@ int cc_grid_eval(const cc_program *prog, const float corner[3], float step,
  * rendering/bitmap.cl): the call lets such callers live on the host side of the boundary. */
 int cc_evaluate_points(const cc_program *prog, const float *d_points, uint64_t n, void *d_out, cc_event **ev);
 
+/* ---- image renderers around evaluate() --------------------------------
+ * ray_caster  rendering/ray_caster.cl:147-256, launched by rendering/ray_caster.py:55-71 with global
+ * size (width, height): sphere tracing with over-relaxation, soft shadow ray, 4-tap ambient
+ * occlusion and floor shadow.  Arguments are the kernel's own (forward is already scaled by the
+ * focal length, ray_caster.py:39-43); render_options: 1 = false colour, 2 = zebra
+ * (ray_caster.py:13-15).  d_out = width*height*3 bytes in the reference's INDEX2 order
+ * ((y + height*x)*3, cl_util/indexing.h:3), i.e. the numpy array [width][height][3] that
+ * ray_caster.py:89 transposes.  eval_count (may be NULL; makes the call blocking) receives the
+ * number of evaluate() calls the rays made. */
+int cc_ray_caster(const cc_program *prog, const float origin[3], const float forward[3], const float up[3],
+                  const float right[3], float pixel_tolerance, float box_radius, float min_distance,
+                  float max_distance, float floor_z, uint32_t render_options, uint32_t width, uint32_t height,
+                  uint8_t *d_out, uint64_t *eval_count, cc_event **ev);
+
+/* bitmap  rendering/bitmap.cl:1-18 (global size (width, height), rendering/bitmap.py:27-29):
+ * pixel (x, y) shows the sign of the distance at origin + step_size * (x, height - y - 1, 0). */
+int cc_bitmap(const cc_program *prog, const float origin[3], float step_size, uint32_t width, uint32_t height,
+              uint8_t *d_out, cc_event **ev);
+
 /* Same, result delivered to HOST memory: slabs of the grid are evaluated into a device
  * ring and copied out on the copy stream while the next slab computes.  Blocking.
  * Replaces kernel + Buffer.read()  (rendering/mesh.py:53-61). */

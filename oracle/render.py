@@ -37,7 +37,7 @@ def camera_params(box_a, box_b, size, view_angle=None):
     return origin, np.array([0.0, 1.0, 0.0]), np.array([0.0, 0.0, 1.0]), focal
 
 
-def ray_cast(words, box_a, box_b, size, view_angle=None):
+def ray_cast(words, box_a, box_b, size, view_angle=None, options=0):
     """ray_caster.py:30-89 -> uint8 [h][w][3]."""
     a, b = _v(box_a), _v(box_b)
     origin, direction, up, focal = camera_params(a, b, size, view_angle)
@@ -59,7 +59,7 @@ def ray_cast(words, box_a, box_b, size, view_angle=None):
     rc = lib().oracle_ray_caster(w.ctypes.data_as(_fp), len(w), f(origin), f(forward), f(up), f(right),
                                  ctypes.c_float(pixel_tolerance), ctypes.c_float(box_radius),
                                  ctypes.c_float(min_distance), ctypes.c_float(max_distance), ctypes.c_float(floor_z),
-                                 size[0], size[1], out.ctypes.data_as(_u8p))
+                                 ctypes.c_uint(int(options)), size[0], size[1], out.ctypes.data_as(_u8p))
     assert rc == 0
     return out.transpose((1, 0, 2))
 

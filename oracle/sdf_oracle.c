@@ -707,15 +707,16 @@ static void light_no_trace(v3 normal, v3 toLight, v3 toCamera, float *diffuse, f
     sp *= sp; sp *= sp; sp *= sp;
     *specular = sp;
 }
-/* ray_caster.cl:42-99 (false colour not restated) */
-static void light_contribution(const prog_t *prog, v3 point, v3 normal, v3 toLight, v3 toCamera, float minDistance,
-                               float maxDistance, float *diffuse, float *specular)
+/* ray_caster.cl:42-99; returns the step count (what the false-colour mode reports) */
+static unsigned light_contribution(const prog_t *prog, v3 point, v3 normal, v3 toLight, v3 toCamera, float minDistance,
+                                   float maxDistance, float *diffuse, float *specular)
 {
     light_no_trace(normal, toLight, toCamera, diffuse, specular);
-    if (*diffuse <= 0 && *specular <= 0) { *diffuse = *specular = 0; return; }
+    if (*diffuse <= 0 && *specular <= 0) { *diffuse = *specular = 0; return 0; }
     float threshold = (1.0f / 128.0f) / fmaxf(*diffuse, *specular);
     float visibility = 1, distance = minDistance, fallback = distance;
-    for (unsigned step = 0; step < 100; ++step) {
+    unsigned step;
+    for (step = 0; step < 100; ++step) {
         v4 r = eval_at(prog, v3add(point, v3scale(toLight, distance)));
         visibility = fminf(visibility, r.w / distance);
         if (visibility < threshold) break;
@@ -726,6 +727,7 @@ static void light_contribution(const prog_t *prog, v3 point, v3 normal, v3 toLig
     }
     *diffuse *= visibility;
     *specular *= visibility;
+    return step;
 }
 /* ray_caster.cl:101-117 */
 static float ambient_occlusion(const prog_t *prog, v3 point, v3 normal, float distanceStep)
@@ -747,14 +749,16 @@ static inline float smoothstepf(float e0, float e1, float x)
 
 /* ray_caster.cl:147-256, one pixel; out = 3 bytes */
 static void ray_pixel(const prog_t *prog, v3 origin, v3 forward, v3 up, v3 right, float pixelTolerance, float boxRadius,
-                      float minDistance, float maxDistance, float floorZ, int x, int y, int w, int h, unsigned char *out)
+                      float minDistance, float maxDistance, float floorZ, unsigned renderOptions, int x, int y, int w, int h,
+                      unsigned char *out)
 {
     float filmx = x - (w - 1) / 2.0f, filmy = y - (h - 1) / 2.0f;
     v3 direction = v3normalize(v3add(v3add(forward, v3scale(right, filmx)), v3scale(up, -filmy)));
     float distance = minDistance, fallback = minDistance;
     v4 r = {0, 0, 0, 0};
     int hit = 0;
-    for (unsigned step = 0; step < 1000; ++step) {
+    unsigned step;
+    for (step = 0; step < 1000; ++step) {
         r = eval_at(prog, v3add(origin, v3scale(direction, distance)));
         if (distance - fallback > r.w) { distance = fallback; continue; }
         hit = r.w < pixelTolerance * distance;
@@ -768,23 +772,40 @@ static void ray_pixel(const prog_t *prog, v3 origin, v3 forward, v3 up, v3 right
     }
     float cr, cg, cb;
     float localEpsilon = fmaxf(1e-4f, 2 * fabsf(r.w));
-    if (hit) {
+    const v3 light_dir = v3normalize(v3mk(1, 2, -1)), light2_dir = v3normalize(v3mk(-1, 1, 0));
+    if (renderOptions & 1u) { /* RENDER_OPTIONS_FALSE_COLOR, ray_caster.cl:203-221 */
+        v3 point = v3add(origin, v3scale(direction, distance));
+        v3 normal = v3mk(r.x, r.y, r.z);
+        float residual = hit ? fabsf(eval_at(prog, point).w) : 0.0f;
+        float steps = (float)step, d1, s1;
+        steps += (float)light_contribution(prog, point, normal, v3scale(light_dir, -1.0f), v3scale(direction, -1.0f),
+                                           localEpsilon, maxDistance, &d1, &s1);
+        steps += 4;
+        cr = steps; cg = 1000 * residual; cb = 0;
+    } else if (hit) {
         v3 point = v3add(origin, v3scale(direction, distance));
         v3 normal = v3mk(r.x, r.y, r.z);
         float ambient = ambient_occlusion(prog, point, normal, boxRadius / 100);
-        const v3 light_dir = v3normalize(v3mk(1, 2, -1)), light2_dir = v3normalize(v3mk(-1, 1, 0));
         float d1, s1, d2, s2;
         light_contribution(prog, point, normal, v3scale(light_dir, -1.0f), v3scale(direction, -1.0f), localEpsilon, maxDistance,
                            &d1, &s1);
         light_no_trace(normal, v3scale(light2_dir, -1.0f), v3scale(direction, -1.0f), &d2, &s2);
         float diffuse = 0.8f * d1 + 0.2f * d2, specular = 0.8f * s1 + 0.2f * s2;
-        /* map_color, ray_caster.cl:119-132 */
-        float saturation = 0.75f * smoothstepf(0.0f, 0.25f, diffuse);
-        float value = 0.1f + 0.8f * (diffuse + (ambient - diffuse) * 0.3f);
-        float chroma = value * saturation, X = chroma * 0.7f, m = value - chroma;
-        cr = 255 * (X + m) + specular * 128;
-        cg = 255 * (chroma + m) + specular * 128;
-        cb = 255 * m + specular * 128;
+        if (renderOptions & 2u) { /* RENDER_OPTIONS_ZEBRA: map_color_zebra, ray_caster.cl:134-145 */
+            int white = (int)floorf(point.y) & 1;
+            float color = 50 + 150 * white;
+            color *= ambient + diffuse;
+            color += 128 * specular;
+            cr = cg = cb = color;
+        } else {
+            /* map_color, ray_caster.cl:119-132 */
+            float saturation = 0.75f * smoothstepf(0.0f, 0.25f, diffuse);
+            float value = 0.1f + 0.8f * (diffuse + (ambient - diffuse) * 0.3f);
+            float chroma = value * saturation, X = chroma * 0.7f, m = value - chroma;
+            cr = 255 * (X + m) + specular * 128;
+            cg = 255 * (chroma + m) + specular * 128;
+            cb = 255 * m + specular * 128;
+        }
     } else {
         cr = 230; cg = 230; cb = 241;
     }
@@ -805,7 +826,7 @@ static void ray_pixel(const prog_t *prog, v3 origin, v3 forward, v3 up, v3 right
 /* out[x][y][3] with INDEX2 (y fastest), like the reference's output buffer (ray_caster.py:49) */
 int oracle_ray_caster(const float *words, int n_words, const float *origin, const float *forward, const float *up,
                       const float *right, float pixelTolerance, float boxRadius, float minDistance, float maxDistance,
-                      float floorZ, int w, int h, unsigned char *out)
+                      float floorZ, unsigned renderOptions, int w, int h, unsigned char *out)
 {
     prog_t prog;
     int rc = prepare(words, n_words, &prog);
@@ -815,7 +836,7 @@ int oracle_ray_caster(const float *words, int n_words, const float *origin, cons
 #pragma omp parallel for collapse(2) schedule(dynamic, 64)
     for (int x = 0; x < w; ++x)
         for (int y = 0; y < h; ++y)
-            ray_pixel(&prog, o, f, u, r, pixelTolerance, boxRadius, minDistance, maxDistance, floorZ, x, y, w, h,
+            ray_pixel(&prog, o, f, u, r, pixelTolerance, boxRadius, minDistance, maxDistance, floorZ, renderOptions, x, y, w, h,
                       out + 3 * ((size_t)y + (size_t)h * (size_t)x));
     release(&prog);
     return 0;
@@ -836,5 +857,103 @@ int oracle_bitmap(const float *words, int n_words, const float *origin, float st
             else { px[0] = 230; px[1] = 230; px[2] = 241; }
         }
     release(&prog);
+    return 0;
+}
+
+/* ---- 2-D outline extraction: rendering/polygon2d.cl ------------------------------------------------
+ * process_polygon over global size (cx, cy, 2): `corners` is the float4 grid [cx+1][cy+1] that grid_eval
+ * produced (INDEX2 with sizes cx+1, cy+1).  Canonical arithmetic: single IEEE operations in source
+ * order.  `starts` is filled in increasing cell-index order (the reference's atomic_inc order is
+ * arbitrary). */
+
+/* polygon2d.cl:5-35 */
+static uint32_t poly_encode_index(int cx, int cy, uint32_t index, int gs0, int gs1)
+{
+    index &= (1u << 20) - 1u;
+    int is_y, out_c, other_c;
+    if (cx < 0 || cx >= gs0) { is_y = 0; out_c = cx; other_c = cy; }
+    else if (cy < 0 || cy >= gs1) { is_y = 1; out_c = cy; other_c = cx; }
+    else return index;
+    return 0x80000000u | (is_y ? 0x40000000u : 0u) | (out_c < 0 ? 0x20000000u : 0u) | ((uint32_t)other_c << 20) | index;
+}
+
+/* polygon2d.cl:37-80 */
+static void poly_place_vertex(const float pos[3][2], const v4 val[3], float out[2])
+{
+    float ax = 0, ay = 0, weight = 0;
+    for (int i = 0; i < 3; ++i) {
+        float w = 1 / (1 + fabsf(val[i].w));
+        ax += pos[i][0] * w;
+        ay += pos[i][1] * w;
+        weight += w;
+    }
+    ax /= weight;
+    ay /= weight;
+    float px = ax, py = ay;
+    for (int i = 0; i < 8; ++i) {
+        float gx = 0, gy = 0, residualSum = 0;
+        for (int j = 0; j < 3; ++j) {
+            float nx = val[j].x, ny = val[j].y;
+            float tmp = (nx * (px - pos[j][0]) + ny * (py - pos[j][1])) + val[j].w;
+            residualSum += tmp * tmp;
+            gx += nx * tmp;
+            gy += ny * tmp;
+        }
+        if (residualSum < 1e-3f) break;
+        float gl = gx * gx + gy * gy;
+        if (gl < 1e-8f) break;
+        float k = residualSum / gl;
+        px -= gx * k;
+        py -= gy * k;
+    }
+    out[0] = px;
+    out[1] = py;
+}
+
+/* polygon2d.cl:82-175.  vertices: float2 per cell (only written for surface cells), links: uint32 per cell */
+int oracle_process_polygon(const float *box_corner, float box_step, int gs0, int gs1, const float *corners, float *vertices,
+                           uint32_t *links, uint32_t *starts, uint32_t *start_counter)
+{
+    const v4 *c4 = (const v4 *)corners;
+    uint32_t n_starts = 0;
+    for (int x = 0; x < gs0; ++x)
+        for (int y = 0; y < gs1; ++y)
+            for (int t = 0; t < 2; ++t) {
+                const int off[3][2] = {{0, 0}, {1, 1}, {t, 1 - t}};
+                unsigned cellType = 0;
+                for (int i = 0; i < 3; ++i) {
+                    size_t ci = (size_t)(y + off[i][1]) + (size_t)(gs1 + 1) * (size_t)(x + off[i][0]);
+                    cellType = cellType << 1 | (c4[ci].w <= 0 ? 1u : 0u);
+                }
+                const uint32_t index = (uint32_t)t + 2u * ((uint32_t)y + (uint32_t)gs1 * (uint32_t)x);
+                if (cellType == 0 || cellType == 7) { links[index] = 0xFFFFFFFFu; continue; }
+                int backwards = cellType == 3 || cellType == 5 || cellType == 6;
+                if (backwards) cellType = 7 - cellType;
+                const int flip = t == 1;
+                if (flip) backwards = !backwards;
+                int fx = 0, fy = 0, rx = 0, ry = 0;
+                switch (cellType) {
+                case 1: fx = 0; fy = 1; rx = -1; ry = 0; break;
+                case 2: fx = 0; fy = 0; rx = 0; ry = 1; break;
+                case 4: fx = -1; fy = 0; rx = 0; ry = 0; break;
+                }
+                if (backwards) { int a = fx, b = fy; fx = rx; fy = ry; rx = a; ry = b; }
+                if (flip) { int a = fx; fx = fy; fy = a; a = rx; rx = ry; ry = a; }
+                fx += x; fy += y; rx += x; ry += y;
+                links[index] = poly_encode_index(fx, fy, (uint32_t)(1 - t) + 2u * ((uint32_t)fy + (uint32_t)gs1 * (uint32_t)fx),
+                                                 gs0, gs1);
+                uint32_t startIndex = poly_encode_index(rx, ry, index, gs0, gs1);
+                if (startIndex & 0x80000000u) starts[n_starts++] = startIndex ^ 0x20000000u;
+                float pos[3][2];
+                v4 val[3];
+                for (int i = 0; i < 3; ++i) {
+                    int cx = x + off[i][0], cy = y + off[i][1];
+                    pos[i][0] = box_corner[0] + (float)cx * box_step;
+                    pos[i][1] = box_corner[1] + (float)cy * box_step;
+                    val[i] = c4[(size_t)cy + (size_t)(gs1 + 1) * (size_t)cx];
+                }
+                poly_place_vertex((const float(*)[2])pos, val, vertices + 2 * (size_t)index);
+            }
+    *start_counter = n_starts;
     return 0;
 }
