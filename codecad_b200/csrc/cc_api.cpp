@@ -1053,6 +1053,99 @@ int cc_mass_properties(const cc_program *prog, const double box_a[3], double res
 
 extern "C" {
 
+int cc_process_polygon(const float box_corner[2], float box_step, uint32_t cells_x, uint32_t cells_y,
+                       const void *d_corners, void *d_vertices, uint32_t *d_links, uint32_t *d_starts,
+                       uint32_t max_starts, uint32_t *d_start_counter, cc_event **ev)
+{
+    NEED_INIT();
+    if (!box_corner || !d_corners || !d_vertices || !d_links || !d_starts || !d_start_counter)
+        return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
+    if (cells_x == 0 || cells_y == 0) return fail(CC_ERR_INVALID_ARGUMENT, "empty grid");
+    if (cells_x >= 512 || cells_y >= 512)
+        return fail(CC_ERR_INVALID_ARGUMENT, "grid of 512 or more cells overflows the link encoding");  // polygon2d.py:46
+    if (max_starts == 0 || max_starts > 1024) return fail(CC_ERR_INVALID_ARGUMENT, "max_starts must be 1..1024");
+    cc_polygon_args a;
+    std::memset(&a, 0, sizeof(a));
+    a.corner_x = box_corner[0]; a.corner_y = box_corner[1]; a.step = box_step;
+    a.cx = cells_x; a.cy = cells_y; a.n_blocks = 1;
+    a.corners = (const float4 *)d_corners;
+    a.vertices = (float2 *)d_vertices;
+    a.links = d_links; a.starts = d_starts; a.start_counter = d_start_counter; a.max_starts = max_starts;
+    int e = cc_launch_process_polygon(a, g.compute);
+    if (e) return cuda_fail((cudaError_t)e, "process_polygon launch");
+    g.launches += 2;
+    return make_event(ev, g.compute);
+}
+
+int cc_polygon_blocks(const cc_program *prog, const double *corners, double resolution, uint32_t gx, uint32_t gy,
+                      uint32_t n_blocks, float *h_vertices, uint32_t *h_links, uint32_t *h_starts,
+                      uint32_t *h_start_counts)
+{
+    NEED_INIT();
+    if (!prog || !corners || !h_vertices || !h_links || !h_starts || !h_start_counts)
+        return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
+    if (gx < 2 || gy < 2) return fail(CC_ERR_INVALID_ARGUMENT, "outline extraction needs at least 2 samples per axis");
+    if (gx > 512 || gy > 512)
+        return fail(CC_ERR_INVALID_ARGUMENT, "grid of more than 512 samples overflows the link encoding");
+    if (n_blocks == 0) return CC_OK;
+    const uint32_t cx = gx - 1, cy = gy - 1, max_starts = cx + cy;  // polygon2d.py:63-69
+    const uint64_t samples = (uint64_t)gx * gy, cells = 2ull * cx * cy;
+    const uint32_t chunk = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_blocks, (1ull << 26) / samples));
+    DevBuf field, descs, d_corner2, vertices, links, starts, counts;
+    int rc;
+    if ((rc = field.reserve((size_t)chunk * samples * 16))) return rc;
+    if ((rc = descs.reserve((size_t)chunk * sizeof(cc_block_desc)))) return rc;
+    if ((rc = d_corner2.reserve((size_t)chunk * 8))) return rc;
+    if ((rc = vertices.reserve((size_t)chunk * cells * 8))) return rc;
+    if ((rc = links.reserve((size_t)chunk * cells * 4))) return rc;
+    if ((rc = starts.reserve((size_t)chunk * max_starts * 4))) return rc;
+    if ((rc = counts.reserve((size_t)chunk * 4))) return rc;
+    std::vector<cc_block_desc> h_desc(chunk);
+    std::vector<float> h_c2(2 * (size_t)chunk);
+    const float step = (float)resolution;  // numpy.float32(box_resolution), polygon2d.py:96,107
+    for (uint32_t b0 = 0; b0 < n_blocks; b0 += chunk) {
+        const uint32_t nb = std::min(chunk, n_blocks - b0);
+        for (uint32_t b = 0; b < nb; ++b) {  // as_float4() / as_float2(): float64 -> float32 per block
+            const double *c = corners + 3 * (size_t)(b0 + b);
+            h_desc[b] = cc_block_desc{(float)c[0], (float)c[1], (float)c[2], 0u};
+            h_c2[2 * b] = (float)c[0];
+            h_c2[2 * b + 1] = (float)c[1];
+        }
+        CU(cudaMemcpyAsync(descs.p, h_desc.data(), (size_t)nb * sizeof(cc_block_desc), cudaMemcpyHostToDevice, g.compute));
+        CU(cudaMemcpyAsync(d_corner2.p, h_c2.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, g.compute));
+        cc_eval_args a;
+        fill_common(&a, prog);
+        a.step = step;
+        a.nx = gx; a.ny = gy; a.nz = 1; a.n_blocks = nb;
+        a.blocks = descs.as<cc_block_desc>();
+        a.out = field.p;
+        if ((rc = launch(CC_SINK_FLOAT4, prog, a, (uint64_t)nb * samples))) return rc;
+        CU(cudaMemsetAsync(vertices.p, 0, (size_t)nb * cells * 8, g.compute));
+        CU(cudaMemsetAsync(starts.p, 0, (size_t)nb * max_starts * 4, g.compute));
+        CU(cudaMemsetAsync(counts.p, 0, (size_t)nb * 4, g.compute));
+        cc_polygon_args pa;
+        std::memset(&pa, 0, sizeof(pa));
+        pa.step = step;
+        pa.block_corners = d_corner2.as<float>();
+        pa.cx = cx; pa.cy = cy; pa.n_blocks = nb;
+        pa.corners = (const float4 *)field.p;
+        pa.vertices = (float2 *)vertices.p;
+        pa.links = links.as<uint32_t>();
+        pa.starts = starts.as<uint32_t>();
+        pa.start_counter = counts.as<uint32_t>();
+        pa.max_starts = max_starts;
+        int e = cc_launch_process_polygon(pa, g.compute);
+        if (e) return cuda_fail((cudaError_t)e, "process_polygon launch");
+        g.launches += 2;
+        CU(cudaMemcpyAsync(h_vertices + (size_t)b0 * cells * 2, vertices.p, (size_t)nb * cells * 8, cudaMemcpyDeviceToHost, g.compute));
+        CU(cudaMemcpyAsync(h_links + (size_t)b0 * cells, links.p, (size_t)nb * cells * 4, cudaMemcpyDeviceToHost, g.compute));
+        CU(cudaMemcpyAsync(h_starts + (size_t)b0 * max_starts, starts.p, (size_t)nb * max_starts * 4, cudaMemcpyDeviceToHost, g.compute));
+        CU(cudaMemcpyAsync(h_start_counts + b0, counts.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, g.compute));
+        CU(cudaStreamSynchronize(g.compute));  // h_desc / h_c2 are reused by the next chunk
+    }
+    return CC_OK;
+}
+
 int cc_mesh_blocks(const cc_program *prog, const double *corners, double resolution, uint32_t nx, uint32_t ny,
                    uint32_t nz, uint32_t n_blocks, double **out_vertices, uint32_t **out_triangle_block,
                    uint64_t *out_triangles)

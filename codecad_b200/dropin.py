@@ -15,12 +15,12 @@ What it does (INTEGRATION.md has the file-level view):
         codecad.subdivision      (subdivision.py)
         codecad.mass_properties  (mass_properties.py)
         codecad.rendering.mesh, codecad.rendering.stl_renderer   (mesh export)
+        codecad.rendering.ray_caster, .bitmap, .image, .polygon2d (pictures, 2-D outlines)
     are never loaded: the modules of this package take their place under those names.
 
 Everything else of the reference (shapes, nodes, util, assemblies, rendering front ends)
-is imported unchanged.  Rendering kernels other than the four hot-path ones
-(ray_caster, polygon2d, bitmap) raise AttributeError when launched: out of scope, no
-fallback.
+is imported unchanged.  The one remaining OpenCL kernel of the reference without a CUDA
+counterpart (matplotlib_slice) raises AttributeError when launched: out of scope, no fallback.
 """
 import importlib
 import sys
@@ -105,6 +105,11 @@ def install(force_pyopencl=True):
         # mesh export (rendering/mesh.py imports mcubes + pyopencl, rendering/stl_renderer.py numpy-stl)
         "codecad.rendering.mesh": importlib.import_module("codecad_b200.rendering.mesh"),
         "codecad.rendering.stl_renderer": importlib.import_module("codecad_b200.rendering.stl_renderer"),
+        # image renderers and 2-D outlines (their kernels live in libcodecad_b200 too)
+        "codecad.rendering.ray_caster": importlib.import_module("codecad_b200.rendering.ray_caster"),
+        "codecad.rendering.bitmap": importlib.import_module("codecad_b200.rendering.bitmap"),
+        "codecad.rendering.image": importlib.import_module("codecad_b200.rendering.image"),
+        "codecad.rendering.polygon2d": importlib.import_module("codecad_b200.rendering.polygon2d"),
     }
     sys.modules.update(aliases)
     return sorted(aliases)

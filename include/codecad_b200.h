@@ -211,6 +211,27 @@ int cc_mass_properties(const cc_program *prog, const double box_a[3], double res
                        const cc_level *levels, uint32_t n_levels,
                        uint32_t rank, uint32_t world, double integrals[10], uint64_t stats[4]);
 
+/* ---- 2-D outlines: rendering/polygon2d.cl + the device half of
+ * rendering/polygon2d.py:36-173.
+ * process_polygon  polygon2d.cl:82-175 with global size (cells_x, cells_y, 2): d_corners is the
+ * float4 grid [cells_x+1][cells_y+1] grid_eval wrote (INDEX2), d_vertices float2 and d_links uint32
+ * per triangle in INDEX3 order t + 2*(y + cells_y*x), d_starts the encoded starts of open chains and
+ * *d_start_counter (zeroed by the caller, polygon2d.py:100) their number.  Unlike the reference's
+ * atomic_inc order the starts come out ordered by cell index.  max_starts (<= 1024) is the capacity
+ * of d_starts (cells_x + cells_y in the reference, polygon2d.py:63-69). */
+int cc_process_polygon(const float box_corner[2], float box_step, uint32_t cells_x, uint32_t cells_y,
+                       const void *d_corners, void *d_vertices, uint32_t *d_links, uint32_t *d_starts,
+                       uint32_t max_starts, uint32_t *d_start_counter, cc_event **ev);
+
+/* The per-box loop of polygon2d.py:80-117 for n_blocks equally sized boxes in two launches:
+ * grid_eval of every box (gx*gy samples at fp32(corners[b]) + step*(x, y), corners float64 [n][3])
+ * and process_polygon of every box; results land in caller-owned HOST arrays
+ * h_vertices [n][2*(gx-1)*(gy-1)][2] float, h_links [n][2*(gx-1)*(gy-1)], h_starts [n][gx+gy-2],
+ * h_start_counts [n].  Vertices of triangles the outline does not cross are zero.  Blocking. */
+int cc_polygon_blocks(const cc_program *prog, const double *corners, double resolution, uint32_t gx, uint32_t gy,
+                      uint32_t n_blocks, float *h_vertices, uint32_t *h_links, uint32_t *h_starts,
+                      uint32_t *h_start_counts);
+
 /* ---- mesh export: replaces the per-block loop of rendering/mesh.py:36-74
  * (grid_eval_pymcubes launch + blocking device->host copy + mcubes.marching_cubes on the CPU).
  * For each of the n_blocks equally sized leaf blocks (nx,ny,nz samples, float64 corners[n][3] =

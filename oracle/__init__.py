@@ -54,6 +54,7 @@ def lib():
         L.oracle_mass_properties_step.argtypes = (
             [_fp, ctypes.c_int, _fp, ctypes.c_float, ctypes.c_float] + [ctypes.c_int] * 3 + [_u32p, _u32p, _u8p]
         )
+        L.oracle_process_polygon.argtypes = [_fp, ctypes.c_float, ctypes.c_int, ctypes.c_int, _fp, _fp, _u32p, _u32p, _u32p]
         L.oracle_math_probe.argtypes = [ctypes.c_int, _fp, _fp, ctypes.c_long, _fp, _fp]
         L.oracle_num_threads.restype = ctypes.c_int
         L.oracle_set_num_threads.argtypes = [ctypes.c_int]
@@ -140,6 +141,23 @@ def mass_properties_step(words, corner, step, threshold, dims):
     _check(lib().oracle_mass_properties_step(_p(w), len(w), _p(c), np.float32(step), np.float32(threshold),
                                              nx, ny, nz, _p(sums, _u32p), _p(counter, _u32p), _p(lst, _u8p)))
     return sums, lst[: int(counter[0])].copy()
+
+
+def process_polygon(box_corner, step, corners):
+    """rendering/polygon2d.cl process_polygon over the float4 grid corners[gx][gy][4] (grid_eval output
+    with nz = 1 squeezed).  -> (vertices float32 [cells][2], links uint32 [cells], starts uint32 [count])
+    with cells = 2*(gx-1)*(gy-1); vertices of triangles the outline does not cross stay zero."""
+    corners = _f32(corners)
+    gx, gy = corners.shape[0], corners.shape[1]
+    cx, cy = gx - 1, gy - 1
+    c = _f32(box_corner)[:2].copy()
+    vertices = np.zeros((2 * cx * cy, 2), np.float32)
+    links = np.zeros(2 * cx * cy, np.uint32)
+    starts = np.zeros(2 * cx * cy + 1, np.uint32)
+    counter = np.zeros(1, np.uint32)
+    _check(lib().oracle_process_polygon(_p(c), np.float32(step), cx, cy, _p(corners), _p(vertices),
+                                        _p(links, _u32p), _p(starts, _u32p), _p(counter, _u32p)))
+    return vertices, links, starts[: int(counter[0])].copy()
 
 
 def math_probe(which, a, b=None):

@@ -165,3 +165,62 @@ def finish_mass_properties(integrals):
     Ixx, Iyy, Izz = syy + szz, sxx + szz, sxx + syy
     Ixy, Ixz, Iyz = -sxy, -sxz, -syz
     return one, (cx, cy, cz), np.array([[Ixx, Ixy, Ixz], [Ixy, Iyy, Iyz], [Ixz, Iyz, Izz]])
+
+
+# ---- rendering/polygon2d.py:36-173 ---------------------------------------------------------------
+
+_POLY_MASK = 0xFFF00000
+
+
+def polygon(words, box_a, box_b, feature_size, grid_size=128):
+    """Boundary polygons of a 2-D scene: subdivision(feature_size / 2) -> per box grid_eval +
+    process_polygon (polygon2d.py:80-117) -> chains.  Closed chains inside a box are collected like
+    polygon2d.py:165-170.  Pieces that cross box borders are gathered from ALL boxes first and then
+    linked end-key -> begin-key (the keys of polygon2d.py:131,141-144); this is deliberately a
+    different procedure from the product's online joining, and from the reference's, whose
+    bookkeeping does not survive a chain that crosses two borders (see codecad_b200/rendering/
+    polygon2d.py)."""
+    from . import grid_eval, process_polygon
+    max_dims, boxes = subdivision(words, box_a, box_b, 2, feature_size / 2, True, grid_size)
+    assert max_dims[0] < 512 and max_dims[2] == 1
+    closed, pieces = [], {}
+    for dims, corner, step, int_corner, int_step in boxes:
+        c32 = np.array(corner, np.float64).astype(np.float32)
+        field = grid_eval(words, c32, step, (max_dims[0], max_dims[1], 1))[:, :, 0, :]
+        vertices, links, starts = process_polygon(c32, step, field)
+        links = links.tolist()
+        vertices = [tuple(v) for v in vertices.tolist()]
+
+        def collect(i, chain):
+            while not i & _POLY_MASK:
+                chain.append(vertices[i])
+                last = i
+                i = links[i]
+                links[last] = _POLY_MASK
+            return i & _POLY_MASK
+
+        box_step = int_step * (dims[0] - 1)
+        for s in starts.tolist():
+            chain = []
+            spec = collect(s & ~_POLY_MASK & 0xFFFFFFFF, chain)
+            d = -1 if spec & 0x20000000 else 1
+            step_xy = (0, d) if spec & 0x40000000 else (d, 0)
+            begin = (int_corner[0], int_corner[1], s & _POLY_MASK)
+            end = (int_corner[0] + step_xy[0] * box_step, int_corner[1] + step_xy[1] * box_step, spec)
+            assert begin not in pieces
+            pieces[begin] = (chain, end)
+        for i in range(len(links)):
+            if links[i] & _POLY_MASK:
+                continue
+            chain = []
+            collect(i, chain)
+            closed.append(chain)
+    while pieces:
+        begin = min(pieces)
+        chain, end = pieces.pop(begin)
+        chain = list(chain)
+        while end != begin:
+            nxt, end = pieces.pop(end)  # KeyError = an outline that never closes
+            chain.extend(nxt)
+        closed.append(chain)
+    return closed
