@@ -303,6 +303,70 @@ def mesh_export_leg():
             "points_evaluated": int(len(boxes)) * 128 ** 3, "d2h_bytes": int(vertices.nbytes + block.nbytes)}
 
 
+def ray_caster_leg():
+    """rendering.image.render_pil_image of the planetary assembly at the
+    reference's default 1024x768 (what its tests/test_image.py renders per shape): wall clock of the
+    public call (program cached, pixels on the host) and the kernel's own time, beside the CPU
+    oracle's restatement of ray_caster.cl on the box's cores; the two images must be identical."""
+    import numpy as np
+    import oracle
+    from oracle import render as oracle_render
+    from codecad_b200.rendering import ray_caster
+    from scenes import load_scenes
+    s = load_scenes()["cfg_planetary"]
+    scene = s.compiled()
+    size = (1024, 768)
+    cam = ray_caster.get_camera_params(scene.bounding_box(), size, None)
+    from codecad_b200.cl_util.buffer import ProgramBuffer
+    t0 = time.perf_counter()
+    ray_caster.render(scene, size=size, *cam)                        # interpreter tier (compile in background)
+    first_ms = (time.perf_counter() - t0) * 1e3
+    n_ready, _ = scene.program_buffer().wait_specialized(ProgramBuffer.SINK_RAY)
+    times, stats = [], {}
+    for _ in range(5):
+        t0 = time.perf_counter()
+        got = ray_caster.render(scene, size=size, stats=stats, *cam)
+        times.append((time.perf_counter() - t0) * 1e3)
+    t0 = time.perf_counter()
+    want = oracle_render.ray_cast(s.words, s.box_a, s.box_b, size)
+    cpu_ms = (time.perf_counter() - t0) * 1e3
+    return {"workload": "examples/planetary.py render_image 1024x768 (ray caster: primary + shadow rays, AO, floor)",
+            "ms": sorted(times)[len(times) // 2], "ms_best": min(times), "kernel_ms": stats["ms"],
+            "evaluations": stats["evaluations"], "evaluations_per_pixel": stats["evaluations"] / (size[0] * size[1]),
+            "geval_per_s": stats["evaluations"] / stats["ms"] / 1e6, "tier": "specialised" if n_ready else "interpreter",
+            "ms_first_call_interpreter_tier": first_ms,
+            "cpu_ms": cpu_ms, "cpu_cores": oracle.num_threads(), "cpu_kind": "port",
+            "image_identical_to_cpu": bool(np.array_equal(got, want))}
+
+
+def polygon_leg():
+    """rendering.polygon2d.polygon of the involute gear at 1/16 of its feature
+    size with 32x32 boxes (hundreds of boxes, ~10 k outline vertices): device part in two launches,
+    beside the CPU oracle (per-box grid_eval + process_polygon + the same chain following)."""
+    import oracle
+    from oracle import host
+    from codecad_b200 import CompiledScene
+    from codecad_b200.rendering import polygon2d
+    from scenes import load_scenes
+    s = load_scenes()["dsdf2d_gear"]
+    fs = s.feature_size / 16
+    scene = CompiledScene(s.words, 2, s.box_a, s.box_b, fs, "gear@1/16")
+    list(polygon2d.polygon(scene, 32))
+    times = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        got = list(polygon2d.polygon(scene, 32))
+        times.append((time.perf_counter() - t0) * 1e3)
+    t0 = time.perf_counter()
+    want = host.polygon(s.words, s.box_a, s.box_b, fs, 32)
+    cpu_ms = (time.perf_counter() - t0) * 1e3
+    canon = lambda cs: sorted(tuple(c[c.index(min(c)):] + c[:c.index(min(c))]) for c in ([tuple(v) for v in c] for c in cs))
+    return {"workload": "tests/data.py gear: polygon() at feature_size/16, 32x32 boxes",
+            "ms": sorted(times)[len(times) // 2], "ms_best": min(times), "outlines": len(got),
+            "vertices": sum(len(c) for c in got), "cpu_ms": cpu_ms, "cpu_cores": oracle.num_threads(), "cpu_kind": "port",
+            "outlines_identical_to_cpu": canon(got) == canon(want)}
+
+
 def workload_config(n, world):
     return {
         "workload": "examples/planetary.py Planetary(11,60,13,41,18,53).make_assembly().shape(): "
@@ -484,7 +548,7 @@ def run_ours(args):
         r = cpu_sample_run(scene, n, 12.0, 1, "auto")
         cpu = {"value": r["value"], "unit": "Gpts/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
 
-    mass = subdiv = mesh = None
+    mass = subdiv = mesh = rays = outline = None
     if world == 1 and not args.no_cpu:
         try:
             mass = mass_properties_leg()
@@ -498,6 +562,14 @@ def run_ours(args):
             mesh = mesh_export_leg()
         except Exception as exc:  # noqa: BLE001
             mesh = {"error": str(exc)[:200]}
+        try:
+            rays = ray_caster_leg()
+        except Exception as exc:  # noqa: BLE001
+            rays = {"error": str(exc)[:200]}
+        try:
+            outline = polygon_leg()
+        except Exception as exc:  # noqa: BLE001
+            outline = {"error": str(exc)[:200]}
 
     line = {
         "metric": METRIC, "value": value, "unit": "Gpts/s", "n_gpus": world, "steps": args.steps,
@@ -506,6 +578,7 @@ def run_ours(args):
         "config": workload_config(n, world), "clocks": clk, "e2e": e2e,
         "gpu_launches": launches_total, "roofline": roofline, "cpu_baseline": cpu,
         "tier": tier, "specialize_s": specialize_s, "interpreter_tier": interp, "mass_properties": mass, "subdivision": subdiv, "mesh_export": mesh,
+        "ray_caster": rays, "polygon2d": outline,
         "device": info.name.decode(),
     }
     _emit(out_fd, line)

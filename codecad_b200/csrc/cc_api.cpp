@@ -435,7 +435,7 @@ int cc_program_use_specialized(cc_program *prog, int enable)
     if (!prog) return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
     prog->use_jit = enable != 0;
     bool any = false;
-    for (int k = 0; k < 4; ++k) any = any || prog->jit_kernel[k] != nullptr;
+    for (int k = 0; k < CC_N_SINKS; ++k) any = any || prog->jit_kernel[k] != nullptr;
     return (prog->use_jit && any) ? 1 : 0;
 }
 
@@ -451,9 +451,9 @@ int cc_program_specialize_wait(cc_program *prog, unsigned sink_mask, double *com
 {
     NEED_INIT();
     if (!prog) return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
-    if ((sink_mask & 15u) == 0) sink_mask = 15u;
+    if ((sink_mask & CC_SINK_MASK_ALL) == 0) sink_mask = 15u;
     int ready = 0;
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < CC_N_SINKS; ++k) {
         if (!(sink_mask & (1u << k))) continue;
         cc_jit_start(prog, k);
         std::string err;
@@ -634,7 +634,9 @@ int launch_render(bool ray, const cc_program *prog, cc_render_launch &r, uint64_
     const size_t need = cc_eval_smem_bytes(cfg, prog->dec.info.n_slots, prog->dec.info.n_micro_words);
     if (need > (size_t)g.prop.sharedMemPerBlockOptin)
         return fail(CC_ERR_TOO_LARGE, "program needs " + std::to_string(need) + " bytes of shared memory per CTA");
-    int rc = prepare_program(prog, cfg);
+    const int sink = ray ? CC_SINK_RAY : CC_SINK_BITMAP;
+    const bool specialised = jit_ready(const_cast<cc_program *>(prog), sink);
+    int rc = specialised ? CC_OK : prepare_program(prog, cfg);
     if (rc) return rc;
     r.code = prog->d_code;
     r.code_words = prog->dec.info.n_micro_words;
@@ -645,7 +647,7 @@ int launch_render(bool ray, const cc_program *prog, cc_render_launch &r, uint64_
         CU(cudaMemsetAsync(d_count, 0, 8, g.compute));
     }
     r.eval_count = d_count;
-    int e = cc_launch_render(ray ? 1 : 0, cfg.prog_space, r, g.compute);
+    int e = cc_launch_render(ray ? 1 : 0, specialised ? 0 : cfg.prog_space, specialised ? prog : nullptr, r, g.compute);
     if (e) return cuda_fail((cudaError_t)e, "render kernel launch");
     g.launches += 1;
     g.points += (uint64_t)r.w * r.h;

@@ -18,7 +18,11 @@ typedef unsigned long size_t;
 #define CC_THREADS 128  // CTA size of the precompiled kernels; specialised kernels may override it
 #endif
 
-enum cc_sink_kind { CC_SINK_FLOAT4 = 0, CC_SINK_PYMCUBES, CC_SINK_CLASSIFY, CC_SINK_MASS };
+enum cc_sink_kind {
+    CC_SINK_FLOAT4 = 0, CC_SINK_PYMCUBES, CC_SINK_CLASSIFY, CC_SINK_MASS,
+    CC_SINK_RAY, CC_SINK_BITMAP,  // image renderers (cc_render.cuh), one point per thread
+    CC_N_SINKS
+};
 
 struct cc_block_desc {  // one block of a subdivision level (device resident)
     float cx, cy, cz;   // fp32 corner of the first sample (cell centre), reference rounding
@@ -48,6 +52,22 @@ struct cc_eval_args {
     // optional: evaluate at these points (x, y, z, unused) instead of grid coordinates; cell c of
     // the launch reads points[c] (used with nx = number of points, ny = nz = 1)
     const float *points;  // 16-byte aligned quadruples
+};
+
+// arguments of the image renderers (rendering/ray_caster.cl:147-156, rendering/bitmap.cl:1-3)
+struct cc_render_args {
+    const uint32_t *code;
+    uint32_t code_words, n_slots;
+    float ox, oy, oz;        // origin
+    float fx, fy, fz;        // forward * focal length   (ray caster)
+    float ux, uy, uz;        // up
+    float rx, ry, rz;        // right
+    float pixel_tolerance, box_radius, min_distance, max_distance, floor_z;
+    float step_size;         // bitmap
+    uint32_t options;        // 1 = false colour, 2 = zebra
+    uint32_t w, h;
+    uint8_t *out;            // [w][h][3], INDEX2: y fastest (cl_util/indexing.h:3)
+    unsigned long long *eval_count;  // optional: total evaluate() calls of valid lanes
 };
 
 #endif

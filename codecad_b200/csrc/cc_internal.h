@@ -33,12 +33,12 @@ struct cc_program {
     uint32_t *d_code = nullptr;  // device copy of the microcode
     uint64_t id = 0;             // identifies what is currently loaded in the __constant__ window
     // scene-specialised kernels (cc_jit.cpp), one library per sink; null until compiled
-    void *jit_library[4] = {nullptr, nullptr, nullptr, nullptr};
-    void *jit_kernel[4] = {nullptr, nullptr, nullptr, nullptr};
-    cc_jit_cfg jit_cfg[4];
-    size_t jit_smem[4] = {0, 0, 0, 0};  // dynamic shared memory of each specialised kernel
-    cc_jit_job *jit_job[4] = {nullptr, nullptr, nullptr, nullptr};  // background compiles in flight
-    bool jit_failed[4] = {false, false, false, false};
+    void *jit_library[CC_N_SINKS] = {};
+    void *jit_kernel[CC_N_SINKS] = {};
+    cc_jit_cfg jit_cfg[CC_N_SINKS];
+    size_t jit_smem[CC_N_SINKS] = {};  // dynamic shared memory of each specialised kernel
+    cc_jit_job *jit_job[CC_N_SINKS] = {};  // background compiles in flight
+    bool jit_failed[CC_N_SINKS] = {};
     size_t jit_cubin_bytes = 0;
     double jit_seconds = 0;  // background compile time spent so far
     bool use_jit = true;     // per-program switch (cc_program_use_specialized)
@@ -53,6 +53,10 @@ void cc_jit_start(cc_program *prog, int sink);
 int cc_jit_poll(cc_program *prog, int sink, bool wait, std::string *err);
 void cc_jit_release(cc_program *prog);
 int cc_jit_launch(const cc_program *prog, int sink, const cc_eval_args &a, void *stream);
+int cc_jit_launch_render(const cc_program *prog, int sink, const cc_render_args &a, void *stream);
+cc_jit_cfg cc_jit_render_cfg(const cc_decoded &dec);
+#define CC_SINK_MASK_ALL ((1u << CC_N_SINKS) - 1u)
+#define CC_RENDER_THREADS 128  // CTA size of the specialised image renderers
 
 // ---- kernel launch layer (cc_kernels.cu) ------------------------------------------------
 
@@ -79,7 +83,9 @@ struct cc_render_launch {
     uint8_t *out;
     unsigned long long *eval_count;
 };
-int cc_launch_render(int ray, int prog_space, const cc_render_launch &r, void *stream);
+// prog_space 1 = constant bank, 2 = shared copy (interpreter kernels); 0 = the specialised kernel of `prog`
+struct cc_program;
+int cc_launch_render(int ray, int prog_space, const cc_program *prog, const cc_render_launch &r, void *stream);
 
 // hierarchy helper kernels
 struct cc_level_geom {

@@ -481,7 +481,7 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
     s << "// generated by libcodecad_b200 (cc_jit.cpp) from " << dec.info.n_micro_ops << " micro-ops\n"
       << "#define CC_THREADS " << cfg.threads << "\n"
       << (no_pack ? "#define CC_OPT_PACKED 0\n" : "") << extra_defines()
-      << "#include \"cc_ops.cuh\"\n#include \"cc_body.cuh\"\n"
+      << "#include \"cc_ops.cuh\"\n#include \"cc_body.cuh\"\n#include \"cc_render.cuh\"\n"
       << "#define PTS " << pts << "\n"
       << "typedef cc_pts<PTS>::V V;\nconstexpr int G = cc_pts<PTS>::G;\ntypedef cc_val<V> Val;\n"
       << "#define CC_EACH _Pragma(\"unroll\") for (int g = 0; g < G; ++g)\n"
@@ -529,6 +529,18 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
         s << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_" << names[k]
           << "(const cc_eval_args a)\n{\n    extern __shared__ float4 cc_cells[];\n    SceneEval e{cc_cells + threadIdx.x};\n"
           << "    cc_kernel_body<PTS, " << sinks[k] << ">(a, e);\n}\n";
+    // image renderers (cc_render.cuh): one point per thread, their own argument block
+    const char *render_names[2] = {"ray_caster", "bitmap"};
+    for (int k = 0; k < 2; ++k)
+        if (sink_mask & (1u << (CC_SINK_RAY + k))) {
+            if (pts != 1) {
+                *err = "internal: the image renderers are generated with one point per thread";
+                return CC_ERR_INVALID_ARGUMENT;
+            }
+            s << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_" << render_names[k]
+              << "(const cc_render_args a)\n{\n    extern __shared__ float4 cc_cells[];\n    SceneEval e{cc_cells + threadIdx.x};\n"
+              << "    cc_" << render_names[k] << "_body(a, e);\n}\n";
+        }
     *src = s.str();
     if (smem_bytes) *smem_bytes = (size_t)n_cells * pts * cfg.threads * 16;
     return CC_OK;
@@ -608,18 +620,18 @@ int cc_jit_nvrtc(const std::string &src, std::vector<char> *cubin, std::string *
         std::lock_guard<std::mutex> lk(g_nvrtc_mu);  // dlopen + symbol table are set up once
         if (!load_nvrtc(&n, err)) return CC_ERR_CUDA;
     }
-    const char *hdr_names[] = {"cc_device_types.h", "cc_math.cuh", "cc_ops.cuh", "cc_body.cuh", "cc_scan.cuh"};
-    std::string hdr_src[5];
+    const char *hdr_names[] = {"cc_device_types.h", "cc_math.cuh", "cc_ops.cuh", "cc_body.cuh", "cc_scan.cuh", "cc_render.cuh"};
+    std::string hdr_src[6];
     const std::string dir = source_dir();
-    for (int i = 0; i < 5; ++i)
+    for (int i = 0; i < 6; ++i)
         if (!read_file(dir + hdr_names[i], &hdr_src[i])) {
             *err = "cannot read " + dir + hdr_names[i] + " (needed to specialise kernels)";
             return CC_ERR_INVALID_ARGUMENT;
         }
-    const char *hdr_ptrs[5] = {hdr_src[0].c_str(), hdr_src[1].c_str(), hdr_src[2].c_str(), hdr_src[3].c_str(),
-                               hdr_src[4].c_str()};
+    const char *hdr_ptrs[6] = {hdr_src[0].c_str(), hdr_src[1].c_str(), hdr_src[2].c_str(), hdr_src[3].c_str(),
+                               hdr_src[4].c_str(), hdr_src[5].c_str()};
     nvrtcProgram p = nullptr;
-    int e = n.CreateProgram(&p, src.c_str(), "cc_scene.cu", 5, hdr_ptrs, hdr_names);
+    int e = n.CreateProgram(&p, src.c_str(), "cc_scene.cu", 6, hdr_ptrs, hdr_names);
     if (e) {
         *err = std::string("nvrtcCreateProgram: ") + n.GetErrorString(e);
         return CC_ERR_CUDA;
@@ -676,7 +688,7 @@ uint64_t source_key(const std::string &src)
 {
     uint64_t h = 14695981039346656037ull;
     h = fnv1a(h, src);
-    const char *hdr_names[] = {"cc_device_types.h", "cc_math.cuh", "cc_ops.cuh", "cc_body.cuh", "cc_scan.cuh"};
+    const char *hdr_names[] = {"cc_device_types.h", "cc_math.cuh", "cc_ops.cuh", "cc_body.cuh", "cc_scan.cuh", "cc_render.cuh"};
     const std::string dir = source_dir();
     for (const char *n : hdr_names) {
         std::string t;
@@ -762,7 +774,8 @@ static int build_cubin(const cc_decoded &dec, const cc_jit_cfg &cfg, int sink, C
 static int load_cubin(cc_program *prog, int sink, const Cubin &bin, const cc_jit_cfg &cfg, size_t smem_bytes,
                       std::string *err)
 {
-    static const char *names[4] = {"cc_jit_float4", "cc_jit_pymcubes", "cc_jit_classify", "cc_jit_mass"};
+    static const char *names[CC_N_SINKS] = {"cc_jit_float4", "cc_jit_pymcubes", "cc_jit_classify", "cc_jit_mass",
+                                            "cc_jit_ray_caster", "cc_jit_bitmap"};
     cudaLibrary_t lib = nullptr;
     cudaError_t ce = cudaLibraryLoadData(&lib, bin->data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
     if (ce != cudaSuccess) {
@@ -815,15 +828,29 @@ static void join_job(cc_program *prog, int sink)
     prog->jit_job[sink] = nullptr;
 }
 
+// Shape of the specialised image renderers: one ray per thread (the state machine of
+// cc_render.cuh is scalar) and small CTAs, because a CTA lives as long as its slowest ray.
+cc_jit_cfg cc_jit_render_cfg(const cc_decoded &dec)
+{
+    cc_jit_cfg c = cc_jit_default_cfg(dec, 1);
+    c.pts = 1;
+    c.threads = CC_RENDER_THREADS;
+    c.min_blocks = 4;
+    c.smem_max_cells = 0;
+    if (const char *t = getenv("CODECAD_B200_JIT_RENDER_MINB")) c.min_blocks = atoi(t);
+    return c;
+}
+
 // synchronous: build + load every sink of the mask
 int cc_jit_compile(cc_program *prog, int pts, unsigned sink_mask, double *seconds, std::string *err)
 {
-    if ((sink_mask & 15u) == 0) sink_mask = 15u;
-    const cc_jit_cfg cfg = cc_jit_default_cfg(prog->dec, pts);
+    if ((sink_mask & CC_SINK_MASK_ALL) == 0) sink_mask = 15u;  // default: the four grid sinks
+    const cc_jit_cfg grid_cfg = cc_jit_default_cfg(prog->dec, pts), render_cfg = cc_jit_render_cfg(prog->dec);
     auto t0 = std::chrono::steady_clock::now();
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < CC_N_SINKS; ++k) {
         if (!(sink_mask & (1u << k))) continue;
         join_job(prog, k);
+        const cc_jit_cfg &cfg = k >= CC_SINK_RAY ? render_cfg : grid_cfg;
         Cubin bin;
         size_t smem = 0;
         int rc = build_cubin(prog->dec, cfg, k, &bin, &smem, nullptr, err);
@@ -840,7 +867,7 @@ void cc_jit_start(cc_program *prog, int sink)
 {
     if (prog->jit_kernel[sink] || prog->jit_job[sink] || prog->jit_failed[sink]) return;
     cc_jit_job *j = new cc_jit_job;
-    j->cfg = cc_jit_default_cfg(prog->dec, 0);
+    j->cfg = sink >= CC_SINK_RAY ? cc_jit_render_cfg(prog->dec) : cc_jit_default_cfg(prog->dec, 0);
     prog->jit_job[sink] = j;
     const cc_decoded *dec = &prog->dec;  // immutable; outlives the thread (destroy joins it)
     j->th = std::thread([j, dec, sink]() {
@@ -875,7 +902,7 @@ int cc_jit_poll(cc_program *prog, int sink, bool wait, std::string *err)
 
 void cc_jit_release(cc_program *prog)
 {
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < CC_N_SINKS; ++k) {
         join_job(prog, k);
         if (prog->jit_library[k]) cudaLibraryUnload((cudaLibrary_t)prog->jit_library[k]);
         prog->jit_library[k] = nullptr;
@@ -895,6 +922,18 @@ int cc_jit_launch(const cc_program *prog, int sink, const cc_eval_args &a, void 
 
 int cc_jit_source(const cc_decoded &dec, int pts, unsigned sink_mask, std::string *src, std::string *err)
 {
-    if ((sink_mask & 15u) == 0) sink_mask = 15u;
+    if ((sink_mask & CC_SINK_MASK_ALL) == 0) sink_mask = 15u;
+    if (sink_mask >> CC_SINK_RAY) return generate(dec, cc_jit_render_cfg(dec), sink_mask, src, nullptr, err);
     return generate(dec, cc_jit_default_cfg(dec, pts), sink_mask, src, nullptr, err);
+}
+
+int cc_jit_launch_render(const cc_program *prog, int sink, const cc_render_args &a, void *stream)
+{
+    const uint32_t threads = (uint32_t)prog->jit_cfg[sink].threads;
+    const uint32_t tiles = ((a.w + 7) / 8) * ((a.h + 3) / 4);  // one warp each (cc_render.cuh)
+    const uint32_t grid = (tiles + threads / 32 - 1) / (threads / 32);
+    if (grid == 0) return 0;
+    void *args[] = {(void *)&a};
+    return (int)cudaLaunchKernel((const void *)prog->jit_kernel[sink], dim3(grid), dim3(threads), args,
+                                 prog->jit_smem[sink], (cudaStream_t)stream);
 }

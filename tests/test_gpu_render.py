@@ -77,3 +77,58 @@ def test_view_angle_and_large_program(cb, scenes):
     got = image.render_pixels(s.compiled(), size, view_angle=30)
     want = oracle_render.ray_cast(s.words, s.box_a, s.box_b, size, view_angle=30)
     assert np.array_equal(got, want)
+
+
+# ---- scene-specialised renderers (NVRTC): same render body, same op library -> same bytes -------
+
+@pytest.mark.parametrize("name", NAMES + ["cfg_planetary", "cfg_menger_sponge"])
+def test_specialised_renderers_bit_exact(cb, scenes, name):
+    from codecad_b200 import CompiledScene
+    from codecad_b200.cl_util.buffer import ProgramBuffer
+    from codecad_b200.rendering import image
+    s = scenes[name]
+    scene = s.compiled()
+    prog = scene.program_buffer()
+    sink = ProgramBuffer.SINK_BITMAP if s.dimension == 2 else ProgramBuffer.SINK_RAY
+    assert prog.specialize(1, sink) > 0 and prog.use_specialized(True)
+    size = (333, 251)
+    from codecad_b200 import _lib
+    launches0, _ = _lib.counters()
+    got = image.render_pixels(scene, size)
+    assert _lib.counters()[0] == launches0 + 1
+    assert np.array_equal(got, oracle_render.render(s.words, s.dimension, s.box_a, s.box_b, size))
+    # back on the interpreter: same picture
+    assert not prog.use_specialized(False)
+    assert np.array_equal(image.render_pixels(scene, size), got)
+
+
+def test_specialised_segmented_ray_caster(cb, scenes):
+    """The 500-box scene is generated as several functions; one ray per thread goes through them too."""
+    from codecad_b200.cl_util.buffer import ProgramBuffer
+    from codecad_b200.rendering import image
+    s = scenes["cfg_synthetic500"]
+    scene = s.compiled()
+    scene.program_buffer().specialize(1, ProgramBuffer.SINK_RAY)
+    size = (96, 64)
+    assert np.array_equal(image.render_pixels(scene, size), oracle_render.ray_cast(s.words, s.box_a, s.box_b, size))
+
+
+def test_tiered_rendering(cb, scenes):
+    """Default mode: the first picture comes from the interpreter while the specialised kernel
+    compiles in the background; later pictures use it.  Identical bytes."""
+    from codecad_b200 import _lib
+    from codecad_b200.cl_util.buffer import ProgramBuffer
+    from codecad_b200.rendering import image
+    L = _lib.lib()
+    s = scenes["dsdf3d_csg_thing"]
+    scene = s.compiled()
+    size = (160, 120)
+    want = oracle_render.render(s.words, 3, s.box_a, s.box_b, size)
+    try:
+        _lib.check(L.cc_set_jit_mode(1))
+        assert np.array_equal(image.render_pixels(scene, size), want)
+        ready, _ = scene.program_buffer().wait_specialized(ProgramBuffer.SINK_RAY)
+        assert ready == 1
+        assert np.array_equal(image.render_pixels(scene, size), want)
+    finally:
+        _lib.check(L.cc_set_jit_mode(0))
