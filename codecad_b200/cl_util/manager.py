@@ -82,7 +82,7 @@ def _dims(global_size):
 
 
 class _Kernels:
-    """`opencl_manager.k`: the four hot-path kernels with the .cl argument lists."""
+    """`opencl_manager.k`: the hot-path kernels and the renderers around evaluate(), with the .cl argument lists."""
 
     def __init__(self, manager):
         self.manager = manager
@@ -130,10 +130,54 @@ class _Kernels:
                                                       ctypes.byref(ev)))
         return Event(ev)
 
+    # rendering/bitmap.cl:1-3   bitmap(scene, float4 origin, float stepSize, uchar* output)
+    def bitmap(self, global_size, local_size, program, origin, step_size, output, wait_for=None):
+        w, h, _ = _dims(global_size)
+        if output.size < w * h * 3:
+            raise RuntimeError("Output buffer too small for the launch")
+        ev = _new_event_ref()
+        _lib.check(_lib.lib().cc_bitmap(program.handle, _lib.f3(origin), float(np.float32(step_size)), w, h,
+                                        output.device_ptr, ctypes.byref(ev)))
+        return Event(ev)
+
+    # rendering/ray_caster.cl:147-156 (the AssertBuffer argument is accepted and ignored)
+    def ray_caster(self, global_size, local_size, program, origin, forward, up, right, pixel_tolerance, box_radius,
+                   min_distance, max_distance, floor_z, render_options, output, assert_buffer=None, wait_for=None):
+        w, h, _ = _dims(global_size)
+        if output.size < w * h * 3:
+            raise RuntimeError("Output buffer too small for the launch")
+        ev = _new_event_ref()
+        f = lambda x: float(np.float32(x))  # noqa: E731
+        _lib.check(_lib.lib().cc_ray_caster(program.handle, _lib.f3(origin), _lib.f3(forward), _lib.f3(up), _lib.f3(right),
+                                            f(pixel_tolerance), f(box_radius), f(min_distance), f(max_distance),
+                                            f(floor_z), int(render_options), w, h, output.device_ptr, None,
+                                            ctypes.byref(ev)))
+        return Event(ev)
+
+    # rendering/polygon2d.cl:82-90   process_polygon(float2 boxCorner, float boxStep, corners, vertices, links,
+    #                                                starts, startCounter)
+    def process_polygon(self, global_size, local_size, box_corner, box_step, corners, vertices, links, starts,
+                        start_counter, wait_for=None):
+        cx, cy, two = _dims(global_size)
+        if two != 2:
+            raise RuntimeError("process_polygon runs over (cells_x, cells_y, 2)")
+        c = np.asarray(box_corner)
+        c2 = (ctypes.c_float * 2)(float(c["x"]), float(c["y"])) if c.dtype.names else (ctypes.c_float * 2)(
+            *[float(np.float32(v)) for v in np.asarray(c, dtype=np.float64).ravel()[:2]])
+        corners_ptr = corners.device_ptr if hasattr(corners, "device_ptr") else corners
+        if vertices.size < cx * cy * 2 * 8 or links.size < cx * cy * 2 * 4:
+            raise RuntimeError("Output buffer too small for the launch")
+        max_starts = min(int(starts.size) // 4, 1024)
+        ev = _new_event_ref()
+        _lib.check(_lib.lib().cc_process_polygon(c2, float(np.float32(box_step)), cx, cy, corners_ptr,
+                                                 vertices.device_ptr, links.device_ptr, starts.device_ptr, max_starts,
+                                                 start_counter.device_ptr, ctypes.byref(ev)))
+        return Event(ev)
+
     def __getattr__(self, name):
         raise AttributeError(
-            "kernel %r is not part of the CUDA hot path (grid_eval, grid_eval_pymcubes, "
-            "subdivision_step, mass_properties); there is no OpenCL fallback" % name)
+            "kernel %r has no CUDA counterpart (available: grid_eval, grid_eval_pymcubes, subdivision_step, "
+            "mass_properties, bitmap, ray_caster, process_polygon); there is no OpenCL fallback" % name)
 
 
 class OpenCLManager:

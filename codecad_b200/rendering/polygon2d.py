@@ -124,12 +124,21 @@ def polygon(obj, subdivision_grid_size=None):
     vertices, links, starts, counts = polygon_blocks(program_buffer, (grid_size[0], grid_size[1]), corners,
                                                      boxes[0][2])
     open_chains = _OpenChains()
+    # only the triangles the outline crosses matter to the host: pull them out of the dense
+    # per-box arrays in one pass (links of untouched triangles are 0xFFFFFFFF)
+    hit_box, hit_index = np.nonzero(links != 0xFFFFFFFF)
+    first = np.searchsorted(hit_box, np.arange(len(boxes) + 1))
+    hit_links = links[hit_box, hit_index].tolist()
+    hit_vertices = list(map(tuple, vertices[hit_box, hit_index].tolist()))
+    hit_index = hit_index.tolist()
+    counts = counts.tolist()
     for b, (box_size, _, _, int_corner, int_resolution) in enumerate(boxes):
-        surface = np.flatnonzero((links[b] & _LINK_OVERFLOW_MASK) == 0)
-        if len(surface) == 0 and counts[b] == 0:
+        lo, hi = int(first[b]), int(first[b + 1])
+        if lo == hi:
             continue
-        box_links = links[b].tolist()
-        box_vertices = list(map(tuple, vertices[b].tolist()))
+        surface = hit_index[lo:hi]
+        box_links = dict(zip(surface, hit_links[lo:hi]))
+        box_vertices = dict(zip(surface, hit_vertices[lo:hi]))
         assert counts[b] <= starts.shape[1]
         if counts[b]:
             int_step = int_resolution * (box_size[0] - 1)  # boxes share their border samples
@@ -142,7 +151,7 @@ def polygon(obj, subdivision_grid_size=None):
                 closed = open_chains.add(chain, begin, end)
                 if closed is not None:
                     yield closed
-        for index in surface.tolist():  # what is left belongs to chains closed inside the box
+        for index in surface:  # what is left belongs to chains closed inside the box
             if box_links[index] & _LINK_OVERFLOW_MASK:
                 continue
             chain = []

@@ -19,6 +19,9 @@
  *
  * Pinning: no OpenCL runtime exists in the build container or on the GPU box, so
  * bit-level parity with a vendor OpenCL build is UNPINNED.  The oracle is pinned
+ * (0) against the reference's 32 golden pictures (tests/baseline/rendered_*.png, copied to
+ * tests/golden/reference_renders): the renderers restated at the end of this file reproduce every one
+ * within the reference's own tolerance (tests/test_oracle_golden_images.py),
  * (a) against every known-answer test the reference holds for this path
  * (tests/test_oracle_known_answers.py: tests/test_mass_properties.py:16-108,
  * tests/test_subdivision.py:110-161, tests/test_dsdf.py:113-192 of the reference) and

@@ -132,3 +132,68 @@ def test_tiered_rendering(cb, scenes):
         assert np.array_equal(image.render_pixels(scene, size), want)
     finally:
         _lib.check(L.cc_set_jit_mode(0))
+
+
+# ---- the operator boundary: opencl_manager.k.<kernel> with cl_util.Buffer, the way the reference's
+#      rendering/ray_caster.py:55-75, bitmap.py:27-30 and polygon2d.py:88-117 launch them --------------
+
+def test_kernel_proxy_ray_caster_and_bitmap(cb, scenes):
+    from codecad_b200 import cl_util
+    from codecad_b200.cl_util import opencl_manager
+    from codecad_b200.geometry import BoundingBox, Vector
+    from codecad_b200.nodes import make_program_buffer
+    from codecad_b200.rendering import ray_caster
+    s = scenes["dsdf3d_csg_thing"]
+    scene = s.compiled()
+    size = (120, 90)
+    box = scene.bounding_box()
+    origin, direction, up, focal = ray_caster.get_camera_params(box, size, None)
+    origin, forward, up, right, tol, radius, dmin, dmax, floor_z = ray_caster.kernel_arguments(box, origin, direction, up, focal)
+    out = cl_util.Buffer(np.uint8, [size[0], size[1], 3])
+    ev = opencl_manager.k.ray_caster(size, None, make_program_buffer(scene), origin.as_float4(), forward.as_float4(),
+                                     up.as_float4(), right.as_float4(), np.float32(tol), np.float32(radius),
+                                     np.float32(dmin), np.float32(dmax), np.float32(floor_z), np.uint32(0), out, None)
+    got = out.read(wait_for=[ev]).transpose((1, 0, 2))
+    assert np.array_equal(got, oracle_render.ray_cast(s.words, s.box_a, s.box_b, size))
+
+    s2 = scenes["dsdf2d_gear"]
+    scene2 = s2.compiled()
+    box2 = scene2.bounding_box().flattened()
+    resolution = Vector(size[0], size[1], 1)
+    step = box2.size().elementwise_div(resolution).max()
+    o2 = box2.midpoint() - resolution * step / 2
+    out2 = cl_util.Buffer(np.uint8, [size[0], size[1], 3])
+    ev = opencl_manager.k.bitmap(size, None, make_program_buffer(scene2), o2.as_float4(), np.float32(step), out2)
+    got2 = out2.read(wait_for=[ev]).reshape((size[0], size[1], 3)).transpose((1, 0, 2))
+    assert np.array_equal(got2, oracle_render.bitmap(s2.words, s2.box_a, s2.box_b, size))
+
+
+def test_kernel_proxy_process_polygon(cb, scenes):
+    import oracle
+    from codecad_b200 import cl_util
+    from codecad_b200.cl_util import opencl_manager
+    from codecad_b200.geometry import FLOAT4, Vector
+    from codecad_b200.nodes import make_program_buffer
+    s = scenes["dsdf2d_gear"]
+    gx = gy = 40
+    corner, step = s.grid(40)
+    c = Vector(float(corner[0]), float(corner[1]), float(corner[2]))
+    corners = cl_util.Buffer(FLOAT4, [gx, gy])
+    tri = (gx - 1, gy - 1, 2)
+    vertices = cl_util.Buffer(cl_util.Buffer.dual_dtype(np.float32), tri[0] * tri[1] * tri[2])
+    links = cl_util.Buffer(np.uint32, tri[0] * tri[1] * tri[2])
+    starts = cl_util.Buffer(np.uint32, tri[0] + tri[1])
+    counter = cl_util.Buffer(np.uint32, 1)
+    prog = make_program_buffer(s.compiled())
+    ev1 = opencl_manager.k.grid_eval((gx, gy), None, prog, c.as_float4(), np.float32(step), corners)
+    ev2 = counter.enqueue_write(np.zeros(1, np.uint32))
+    ev3 = vertices.enqueue_write(np.zeros(tri[0] * tri[1] * tri[2], vertices.dtype))
+    ev = opencl_manager.k.process_polygon(tri, None, c.as_float2(), np.float32(step), corners, vertices, links, starts,
+                                          counter, wait_for=[ev1, ev2, ev3])
+    field = oracle.grid_eval(s.words, corner, step, (gx, gy, 1))[:, :, 0, :]
+    want_v, want_l, want_s = oracle.process_polygon(corner[:2], step, field)
+    got_v = vertices.read(wait_for=[ev])
+    assert np.array_equal(np.stack([got_v["x"], got_v["y"]], -1), want_v)
+    assert np.array_equal(links.read(wait_for=[ev]), want_l)
+    assert int(counter.read(wait_for=[ev])[0]) == len(want_s)
+    assert np.array_equal(starts.read(wait_for=[ev])[:len(want_s)], want_s)

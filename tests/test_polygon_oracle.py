@@ -89,3 +89,40 @@ def test_process_polygon_link_encoding():
     assert np.allclose(vertices[out][:, 0], 1.5, atol=1e-6)
     start = int(starts[0])
     assert start & 0x80000000 and (start & 0xFFFFF) in out
+
+
+@pytest.mark.parametrize("grid", [128, 24, 9, 5])
+@pytest.mark.parametrize("name", ["dsdf2d_gear", "dsdf2d_nonconvex_shell1", "dsdf2d_bin_counter_11", "dsdf2d_circle"])
+def test_product_host_logic_on_oracle_data(scenes, name, grid, monkeypatch):
+    """The product's chain following / piece joining (codecad_b200/rendering/polygon2d.py), fed with the
+    oracle's per-box outputs instead of the device's: same polygons as the oracle's own procedure."""
+    from codecad_b200.rendering import polygon2d
+    s = scenes[name]
+
+    def fake_subdivision(obj, resolution, grid_size=None):
+        max_dims, boxes = host.subdivision(s.words, s.box_a, s.box_b, 2, resolution, True, grid_size)
+        return None, max_dims, boxes
+
+    def fake_polygon_blocks(program_buffer, grid_xy, corners, resolution):
+        gx, gy = grid_xy
+        cells = 2 * (gx - 1) * (gy - 1)
+        n = len(corners)
+        vertices = np.zeros((n, cells, 2), np.float32)
+        links = np.zeros((n, cells), np.uint32)
+        starts = np.zeros((n, gx + gy - 2), np.uint32)
+        counts = np.zeros(n, np.uint32)
+        for b, c in enumerate(corners):
+            c32 = np.asarray(c, np.float64).astype(np.float32)
+            field = oracle.grid_eval(s.words, c32, resolution, (gx, gy, 1))[:, :, 0, :]
+            vertices[b], links[b], st = oracle.process_polygon(c32, resolution, field)
+            starts[b, :len(st)] = st
+            counts[b] = len(st)
+        return vertices, links, starts, counts
+
+    monkeypatch.setattr(polygon2d, "subdivision", fake_subdivision)
+    monkeypatch.setattr(polygon2d, "polygon_blocks", fake_polygon_blocks)
+    got = list(polygon2d.polygon(s.compiled(), grid))
+    want = host.polygon(s.words, s.box_a, s.box_b, s.feature_size, grid)
+    assert canonical(got) == canonical(want)
+    if grid == 128:
+        assert [[tuple(v) for v in c] for c in got] == [[tuple(v) for v in c] for c in want]
