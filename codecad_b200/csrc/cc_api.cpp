@@ -183,8 +183,10 @@ bool jit_ready(cc_program *p, int sink)
     return r == 1;
 }
 
-int launch(int sink, const cc_program *prog, cc_eval_args &a, uint64_t points)
+int launch(int sink_kind, const cc_program *prog, cc_eval_args &a, uint64_t points)
 {
+    // which specialised kernel serves the launch: point lists have their own (cc_jit_points)
+    const int sink = a.points ? (int)CC_SINK_POINTS : sink_kind;
     if (jit_ready(const_cast<cc_program *>(prog), sink)) {
         // scene-specialised kernel: slots are registers, parameters immediates
         const uint32_t tile = (uint32_t)(prog->jit_cfg[sink].threads * prog->jit_cfg[sink].pts);
@@ -209,6 +211,10 @@ int launch(int sink, const cc_program *prog, cc_eval_args &a, uint64_t points)
     cc_launch_cfg cfg;
     int rc = choose_cfg(prog, points, &cfg);
     if (rc) return rc;
+    if (a.points) {  // the point-list kernels exist for 1 / 2 points per thread, constant or shared program
+        if (cfg.pts > 2) cfg.pts = 2;
+        if (cfg.prog_space == 3) cfg.prog_space = 1;
+    }
     rc = prepare_program(prog, cfg);
     if (rc) return rc;
     const uint32_t tile = cc_tile_points(cfg);
@@ -224,7 +230,7 @@ int launch(int sink, const cc_program *prog, cc_eval_args &a, uint64_t points)
         a.ticket = g.d_ticket;
         a.tile_status = g.d_status;
     }
-    int e = cc_launch_eval(sink, cfg, a, g.compute);
+    int e = cc_launch_eval(sink_kind, cfg, a, g.compute);
     if (e) return cuda_fail((cudaError_t)e, "cc_eval_kernel launch");
     g.launches += 1;
     g.points += points;

@@ -21,6 +21,7 @@ typedef unsigned long size_t;
 enum cc_sink_kind {
     CC_SINK_FLOAT4 = 0, CC_SINK_PYMCUBES, CC_SINK_CLASSIFY, CC_SINK_MASS,
     CC_SINK_RAY, CC_SINK_BITMAP,  // image renderers (cc_render.cuh), one point per thread
+    CC_SINK_POINTS,               // FLOAT4 sink fed from a point list (cc_evaluate_points)
     CC_N_SINKS
 };
 

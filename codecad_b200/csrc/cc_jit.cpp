@@ -529,6 +529,10 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
         s << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_" << names[k]
           << "(const cc_eval_args a)\n{\n    extern __shared__ float4 cc_cells[];\n    SceneEval e{cc_cells + threadIdx.x};\n"
           << "    cc_kernel_body<PTS, " << sinks[k] << ">(a, e);\n}\n";
+    if (sink_mask & (1u << CC_SINK_POINTS))
+        s << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_points"
+          << "(const cc_eval_args a)\n{\n    extern __shared__ float4 cc_cells[];\n    SceneEval e{cc_cells + threadIdx.x};\n"
+          << "    cc_kernel_body<PTS, CC_SINK_FLOAT4, SceneEval, true>(a, e);\n}\n";
     // image renderers (cc_render.cuh): one point per thread, their own argument block
     const char *render_names[2] = {"ray_caster", "bitmap"};
     for (int k = 0; k < 2; ++k)
@@ -775,7 +779,7 @@ static int load_cubin(cc_program *prog, int sink, const Cubin &bin, const cc_jit
                       std::string *err)
 {
     static const char *names[CC_N_SINKS] = {"cc_jit_float4", "cc_jit_pymcubes", "cc_jit_classify", "cc_jit_mass",
-                                            "cc_jit_ray_caster", "cc_jit_bitmap"};
+                                            "cc_jit_ray_caster", "cc_jit_bitmap", "cc_jit_points"};
     cudaLibrary_t lib = nullptr;
     cudaError_t ce = cudaLibraryLoadData(&lib, bin->data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
     if (ce != cudaSuccess) {
@@ -850,7 +854,7 @@ int cc_jit_compile(cc_program *prog, int pts, unsigned sink_mask, double *second
     for (int k = 0; k < CC_N_SINKS; ++k) {
         if (!(sink_mask & (1u << k))) continue;
         join_job(prog, k);
-        const cc_jit_cfg &cfg = k >= CC_SINK_RAY ? render_cfg : grid_cfg;
+        const cc_jit_cfg &cfg = (k == CC_SINK_RAY || k == CC_SINK_BITMAP) ? render_cfg : grid_cfg;
         Cubin bin;
         size_t smem = 0;
         int rc = build_cubin(prog->dec, cfg, k, &bin, &smem, nullptr, err);
@@ -867,7 +871,7 @@ void cc_jit_start(cc_program *prog, int sink)
 {
     if (prog->jit_kernel[sink] || prog->jit_job[sink] || prog->jit_failed[sink]) return;
     cc_jit_job *j = new cc_jit_job;
-    j->cfg = sink >= CC_SINK_RAY ? cc_jit_render_cfg(prog->dec) : cc_jit_default_cfg(prog->dec, 0);
+    j->cfg = (sink == CC_SINK_RAY || sink == CC_SINK_BITMAP) ? cc_jit_render_cfg(prog->dec) : cc_jit_default_cfg(prog->dec, 0);
     prog->jit_job[sink] = j;
     const cc_decoded *dec = &prog->dec;  // immutable; outlives the thread (destroy joins it)
     j->th = std::thread([j, dec, sink]() {
@@ -923,7 +927,8 @@ int cc_jit_launch(const cc_program *prog, int sink, const cc_eval_args &a, void 
 int cc_jit_source(const cc_decoded &dec, int pts, unsigned sink_mask, std::string *src, std::string *err)
 {
     if ((sink_mask & CC_SINK_MASK_ALL) == 0) sink_mask = 15u;
-    if (sink_mask >> CC_SINK_RAY) return generate(dec, cc_jit_render_cfg(dec), sink_mask, src, nullptr, err);
+    if (sink_mask & ((1u << CC_SINK_RAY) | (1u << CC_SINK_BITMAP)))
+        return generate(dec, cc_jit_render_cfg(dec), sink_mask, src, nullptr, err);
     return generate(dec, cc_jit_default_cfg(dec, pts), sink_mask, src, nullptr, err);
 }
 

@@ -421,7 +421,7 @@ struct InterpEval {
     }
 };
 
-template <int PTS, int SMEM, int SINK>
+template <int PTS, int SMEM, int SINK, bool POINTS = false>
 __global__ void __launch_bounds__(CC_THREADS) cc_eval_kernel(const cc_eval_args a)
 {
     extern __shared__ float4 smem4[];
@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(CC_THREADS) cc_eval_kernel(const cc_eval_args 
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
     InterpEval<PTS, SMEM> eval{Prog<SMEM>{s_code}, regs};
-    cc_kernel_body<PTS, SINK>(a, eval);
+    cc_kernel_body<PTS, SINK, InterpEval<PTS, SMEM>, POINTS>(a, eval);
 }
 
 // ---- host-side launch ---------------------------------------------------------------------------
@@ -457,10 +457,10 @@ int cc_upload_constant_program(const uint32_t *h_code, uint32_t n_words, void *s
                                         (cudaStream_t)stream);
 }
 
-template <int PTS, int SMEM, int SINK>
+template <int PTS, int SMEM, int SINK, bool POINTS = false>
 static int launch_one(const cc_eval_args &a, size_t smem, uint32_t grid, cudaStream_t st)
 {
-    auto k = cc_eval_kernel<PTS, SMEM, SINK>;
+    auto k = cc_eval_kernel<PTS, SMEM, SINK, POINTS>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     k<<<grid, CC_THREADS, smem, st>>>(a);
@@ -493,6 +493,15 @@ int cc_launch_eval(int sink, const cc_launch_cfg &cfg, const cc_eval_args &a, vo
     const size_t smem = cc_eval_smem_bytes(cfg, a.n_slots, a.code_words);
     const uint32_t grid = a.n_blocks * a.tiles_per_block;
     if (grid == 0) return 0;
+    if (a.points) {
+        // point lists: FLOAT4 sink, 1 or 2 points per thread, constant bank or shared copy
+        if (sink != CC_SINK_FLOAT4 || cfg.pts > 2 || cfg.prog_space > 2) return (int)cudaErrorInvalidValue;
+        if (cfg.pts == 1)
+            return cfg.prog_space == 1 ? launch_one<1, 0, CC_SINK_FLOAT4, true>(a, smem, grid, st)
+                                       : launch_one<1, 1, CC_SINK_FLOAT4, true>(a, smem, grid, st);
+        return cfg.prog_space == 1 ? launch_one<2, 0, CC_SINK_FLOAT4, true>(a, smem, grid, st)
+                                   : launch_one<2, 1, CC_SINK_FLOAT4, true>(a, smem, grid, st);
+    }
     switch (sink) {
     case CC_SINK_FLOAT4: return launch_sink<CC_SINK_FLOAT4>(cfg, a, smem, grid, st);
     case CC_SINK_PYMCUBES: return launch_sink<CC_SINK_PYMCUBES>(cfg, a, smem, grid, st);

@@ -359,7 +359,7 @@ def test_evaluate_points_bit_exact(cb, scenes, name, tier):
     pts[:3] = [[0, 0, 0], [np.inf, 0, 0], [np.nan, 1, 2]]   # special operands travel the same paths
     prog = ProgramBuffer(s.words)
     if tier == "specialised":
-        prog.specialize(2, ProgramBuffer.SINK_FLOAT4)
+        prog.specialize(2, ProgramBuffer.SINK_POINTS)
         assert prog.use_specialized(True)
     want = oracle.evaluate_points(s.words, pts)
     got = cb.evaluate_points(prog, pts)
