@@ -19,7 +19,7 @@ import numpy as np
 from . import _compat  # noqa: F401  (kept tiny: shape protocol helpers)
 from .. import _lib
 from ..geometry import Vector
-from ..subdivision import subdivision
+from ..subdivision import block_corners, subdivision
 
 
 def _check_3d(obj):
@@ -80,9 +80,9 @@ def mesh_arrays(obj, subdivision_grid_size=None):
     """All triangles of the shape at once: (vertices float64 [t][3][3], block index [t], boxes)."""
     _check_3d(obj)
     program_buffer, max_box_size, boxes = subdivision(obj, obj.feature_size() / 2, grid_size=subdivision_grid_size)
-    if not boxes:
+    if not len(boxes):
         return np.zeros((0, 3, 3), np.float64), np.zeros((0,), np.uint32), boxes
-    corners = np.array([[b[1].x, b[1].y, b[1].z] for b in boxes], dtype=np.float64)
+    corners = block_corners(boxes)
     # every leaf block has the same size and resolution (subdivision.py:97-111)
     vertices, block = mesh_blocks(program_buffer, max_box_size, corners, boxes[0][2])
     return vertices, block, boxes

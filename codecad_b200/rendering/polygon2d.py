@@ -22,7 +22,7 @@ import numpy as np
 
 from .. import _lib
 from ..geometry import Vector
-from ..subdivision import subdivision
+from ..subdivision import LeafBlocks, block_corners, subdivision
 
 _LINK_OVERFLOW_MASK = 0xFFF00000   # polygon2d.cl:5-35: flags (bits 29-31) + row / column (bits 20-28)
 _INDEX_MASK = 0x000FFFFF
@@ -114,15 +114,14 @@ def polygon(obj, subdivision_grid_size=None):
 
     assert grid_size[0] < 512, "Larger grid size would overflow the index encoding"
     assert grid_size[2] == 1
-    if not boxes:
+    if not len(boxes):
         return
-    for box_size, _, _, _, _ in boxes:
-        if len(boxes) > 1:
+    if len(boxes) > 1:
+        for box_size in ([boxes.dims] if isinstance(boxes, LeafBlocks) else [b[0] for b in boxes]):
             assert box_size[0] == box_size[1]
 
-    corners = np.array([[c[0], c[1], c[2]] for _, c, _, _, _ in boxes], dtype=np.float64)
-    vertices, links, starts, counts = polygon_blocks(program_buffer, (grid_size[0], grid_size[1]), corners,
-                                                     boxes[0][2])
+    vertices, links, starts, counts = polygon_blocks(program_buffer, (grid_size[0], grid_size[1]),
+                                                     block_corners(boxes), boxes[0][2])
     open_chains = _OpenChains()
     # only the triangles the outline crosses matter to the host: pull them out of the dense
     # per-box arrays in one pass (links of untouched triangles are 0xFFFFFFFF)
@@ -132,10 +131,11 @@ def polygon(obj, subdivision_grid_size=None):
     hit_vertices = list(map(tuple, vertices[hit_box, hit_index].tolist()))
     hit_index = hit_index.tolist()
     counts = counts.tolist()
-    for b, (box_size, _, _, int_corner, int_resolution) in enumerate(boxes):
+    for b in range(len(boxes)):
         lo, hi = int(first[b]), int(first[b + 1])
         if lo == hi:
             continue
+        box_size, _, _, int_corner, int_resolution = boxes[b]
         surface = hit_index[lo:hi]
         box_links = dict(zip(surface, hit_links[lo:hi]))
         box_vertices = dict(zip(surface, hit_vertices[lo:hi]))

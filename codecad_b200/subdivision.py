@@ -3,7 +3,9 @@
 :169-253); the per-block `_Helper` launch/readback loop (:14-113) is replaced by one
 device-resident pass per level inside libcodecad_b200 (cc_subdivide).
 """
+import collections.abc
 import ctypes
+import itertools
 import math
 
 import numpy as np
@@ -84,6 +86,56 @@ def subdivide_int_corners(program, origin, resolution, block_sizes, dimension, r
         _lib.lib().cc_free(out)
 
 
+class LeafBlocks(collections.abc.Sequence):
+    """The third element of subdivision()'s result: a read-only sequence of
+    (grid_dims, corner Vector(float64), step, int_corner Vector(int), int_step) tuples, exactly the
+    reference's list (subdivision.py:97-111), built on demand from two arrays.  12 000 leaf blocks
+    are 36 000 Python objects; callers that hand all blocks to the device in one go
+    (rendering.mesh, rendering.polygon2d) read `.corners` / `.int_corners` and never create them."""
+
+    def __init__(self, dims, corners, step, int_corners, int_step):
+        self.dims, self.step, self.int_step = dims, step, int_step
+        self.corners = corners          # float64 [n][3]: int_pos * resolution + origin
+        self.int_corners = int_corners  # int64 [n][3]
+        self._items = None
+
+    def _materialise(self):
+        if self._items is None:
+            new, vec = tuple.__new__, itertools.repeat(Vector)
+            self._items = list(zip(itertools.repeat(self.dims), map(new, vec, self.corners.tolist()),
+                                   itertools.repeat(self.step), map(new, vec, self.int_corners.tolist()),
+                                   itertools.repeat(self.int_step)))
+        return self._items
+
+    def __len__(self):
+        return len(self.int_corners)
+
+    def __getitem__(self, i):
+        if self._items is None and isinstance(i, (int, np.integer)):
+            i = int(i)
+            if not -len(self) <= i < len(self):
+                raise IndexError("block index out of range")
+            return (self.dims, Vector._make(self.corners[i].tolist()), self.step,
+                    Vector._make(self.int_corners[i].tolist()), self.int_step)
+        return self._materialise()[i]
+
+    def __iter__(self):
+        return iter(self._materialise())
+
+    def __eq__(self, other):
+        return list(self) == list(other)
+
+    def __repr__(self):
+        return "LeafBlocks(%d blocks of %s)" % (len(self), tuple(self.dims))
+
+
+def block_corners(blocks):
+    """float64 [n][3] box corners of a subdivision() block list (without building the tuples)."""
+    if isinstance(blocks, LeafBlocks):
+        return blocks.corners
+    return np.array([[b[1][0], b[1][1], b[1][2]] for b in blocks], dtype=np.float64).reshape(-1, 3)
+
+
 def subdivision(shape, resolution, overlap_edge_samples=True, grid_size=None, rank=0, world=1):
     """subdivision.py:169-253.  Returns (program_buffer, max_grid_dims,
     [(grid_dims, corner, step, int_corner, int_step), ...]) for the leaf blocks.
@@ -117,7 +169,5 @@ def subdivision(shape, resolution, overlap_edge_samples=True, grid_size=None, ra
     leaf_step = leaf_step_int * resolution
     # subdivision.py:101  pos = int_pos * resolution + origin   (float64, same two IEEE operations
     # per axis as the reference's Vector arithmetic, vectorised; tuples built with _make)
-    pos = (corners * float(resolution) + np.array([box.a.x, box.a.y, box.a.z], dtype=np.float64)).tolist()
-    mk = Vector._make
-    final_blocks = [(leaf_dims, mk(p), leaf_step, mk(i), leaf_step_int) for p, i in zip(pos, corners.tolist())]
-    return program_buffer, leaf_dims, final_blocks
+    pos = corners * float(resolution) + np.array([box.a.x, box.a.y, box.a.z], dtype=np.float64)
+    return program_buffer, leaf_dims, LeafBlocks(leaf_dims, pos, leaf_step, corners, leaf_step_int)

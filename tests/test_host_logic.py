@@ -204,3 +204,28 @@ def test_vector_matches_reference_semantics():
     assert (Vector(1, 2, 3) * 2 + Vector(1, 1, 1)) == (3, 5, 7)
     f4 = Vector(0.1, 0.2, 0.3).as_float4()
     assert f4.dtype.names == ("x", "y", "z", "w") and f4["x"] == np.float32(0.1) and f4["w"] == 0
+
+
+def test_leaf_blocks_sequence_is_the_reference_list():
+    """subdivision()'s block list is built on demand; it must behave like the reference's list of
+    (dims, corner Vector, step, int_corner Vector, int_step) tuples (subdivision.py:97-111)."""
+    import numpy as np
+    from codecad_b200.geometry import Vector
+    from codecad_b200.subdivision import LeafBlocks, block_corners
+    ints = np.array([[0, 15, 30], [45, 0, 15], [15, 15, 15]], dtype=np.int64)
+    pos = ints * 0.25 + np.array([-1.0, -2.0, -3.0])
+    dims = Vector(16, 16, 16)
+    blocks = LeafBlocks(dims, pos, 0.25, ints, 1)
+    want = [(dims, Vector(*p), 0.25, Vector(*i), 1) for p, i in zip(pos.tolist(), ints.tolist())]
+    assert len(blocks) == 3 and blocks[1] == want[1] and blocks[-1] == want[-1]     # before materialising
+    assert isinstance(blocks[0][1], Vector) and isinstance(blocks[0][3].x, int)
+    assert list(blocks) == want and blocks == want and blocks[0:2] == want[0:2]
+    acc = []
+    acc += blocks
+    assert acc == want and sorted(tuple(b[3]) for b in blocks) == sorted(tuple(i) for i in ints.tolist())
+    for size, corner, step, int_corner, int_step in blocks:
+        assert size == dims and step == 0.25 and int_step == 1
+    with __import__("pytest").raises(IndexError):
+        blocks[3]
+    assert np.array_equal(block_corners(blocks), pos) and np.array_equal(block_corners(want), pos)
+    assert len(LeafBlocks(dims, pos[:0], 0.25, ints[:0], 1)) == 0 and not list(LeafBlocks(dims, pos[:0], 0.25, ints[:0], 1))
