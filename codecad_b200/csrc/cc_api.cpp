@@ -709,78 +709,6 @@ int cc_evaluate_points(const cc_program *prog, const float *d_points, uint64_t n
     return make_event(ev, g.compute);
 }
 
-namespace {
-int launch_render(bool ray, const cc_program *prog, cc_render_launch &r, uint64_t *eval_count)
-{
-    if (r.w == 0 || r.h == 0) return fail(CC_ERR_INVALID_ARGUMENT, "empty image");
-    if ((uint64_t)r.w * r.h > (1ull << 31)) return fail(CC_ERR_INVALID_ARGUMENT, "more than 2^31 pixels");
-    cc_launch_cfg cfg{1, prog->dec.info.n_micro_words <= CC_CONST_WORDS && g.prog_space != 2 ? 1 : 2};
-    const size_t need = cc_eval_smem_bytes(cfg, prog->dec.info.n_slots, prog->dec.info.n_micro_words);
-    if (need > (size_t)g.prop.sharedMemPerBlockOptin)
-        return fail(CC_ERR_TOO_LARGE, "program needs " + std::to_string(need) + " bytes of shared memory per CTA");
-    const int sink = ray ? CC_SINK_RAY : CC_SINK_BITMAP;
-    const bool specialised = jit_ready(const_cast<cc_program *>(prog), sink);
-    int rc = specialised ? CC_OK : prepare_program(prog, cfg);
-    if (rc) return rc;
-    r.code = prog->d_code;
-    r.code_words = prog->dec.info.n_micro_words;
-    r.n_slots = prog->dec.info.n_slots;
-    unsigned long long *d_count = nullptr;
-    if (eval_count) {
-        CU(cudaMallocAsync((void **)&d_count, 8, g.compute));
-        CU(cudaMemsetAsync(d_count, 0, 8, g.compute));
-    }
-    r.eval_count = d_count;
-    int e = cc_launch_render(ray ? 1 : 0, specialised ? 0 : cfg.prog_space, specialised ? prog : nullptr, r, g.compute);
-    if (e) return cuda_fail((cudaError_t)e, "render kernel launch");
-    g.launches += 1;
-    g.points += (uint64_t)r.w * r.h;
-    if (eval_count) {
-        unsigned long long h = 0;
-        CU(cudaMemcpyAsync(&h, d_count, 8, cudaMemcpyDeviceToHost, g.compute));
-        CU(cudaStreamSynchronize(g.compute));
-        CU(cudaFreeAsync(d_count, g.compute));
-        *eval_count = h;
-    }
-    return CC_OK;
-}
-}  // namespace
-
-int cc_ray_caster(const cc_program *prog, const float origin[3], const float forward[3], const float up[3],
-                  const float right[3], float pixel_tolerance, float box_radius, float min_distance,
-                  float max_distance, float floor_z, uint32_t render_options, uint32_t width, uint32_t height,
-                  uint8_t *d_out, uint64_t *eval_count, cc_event **ev)
-{
-    NEED_INIT();
-    if (!prog || !origin || !forward || !up || !right || !d_out) return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
-    if (render_options & ~3u) return fail(CC_ERR_INVALID_ARGUMENT, "unknown render option");
-    cc_render_launch r;
-    std::memset(&r, 0, sizeof(r));
-    for (int i = 0; i < 3; ++i) {
-        r.origin[i] = origin[i]; r.forward[i] = forward[i]; r.up[i] = up[i]; r.right[i] = right[i];
-    }
-    r.pixel_tolerance = pixel_tolerance; r.box_radius = box_radius; r.min_distance = min_distance;
-    r.max_distance = max_distance; r.floor_z = floor_z; r.options = render_options;
-    r.w = width; r.h = height; r.out = d_out;
-    int rc = launch_render(true, prog, r, eval_count);
-    if (rc) return rc;
-    return make_event(ev, g.compute);
-}
-
-int cc_bitmap(const cc_program *prog, const float origin[3], float step_size, uint32_t width, uint32_t height,
-              uint8_t *d_out, cc_event **ev)
-{
-    NEED_INIT();
-    if (!prog || !origin || !d_out) return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
-    cc_render_launch r;
-    std::memset(&r, 0, sizeof(r));
-    for (int i = 0; i < 3; ++i) r.origin[i] = origin[i];
-    r.step_size = step_size; r.w = width; r.h = height; r.out = d_out;
-    int rc = launch_render(false, prog, r, nullptr);
-    if (rc) return rc;
-    return make_event(ev, g.compute);
-}
-
 int cc_grid_eval_to_host(const cc_program *prog, const float corner[3], float step, uint32_t nx, uint32_t ny,
                          uint32_t nz, uint32_t x_offset, int layout, void *h_out)
 {
@@ -1137,7 +1065,81 @@ int cc_mass_properties(const cc_program *prog, const double box_a[3], double res
 
 // ---- mesh export: marching cubes over leaf blocks --------------------------------------------------------
 
+namespace {
+int launch_render(bool ray, const cc_program *prog, cc_render_launch &r, uint64_t *eval_count)
+{
+    if (r.w == 0 || r.h == 0) return fail(CC_ERR_INVALID_ARGUMENT, "empty image");
+    if ((uint64_t)r.w * r.h > (1ull << 31)) return fail(CC_ERR_INVALID_ARGUMENT, "more than 2^31 pixels");
+    const int sink = ray ? CC_SINK_RAY : CC_SINK_BITMAP;
+    const bool specialised = jit_ready(const_cast<cc_program *>(prog), sink);
+    cc_launch_cfg cfg{1, prog->dec.info.n_micro_words <= CC_CONST_WORDS && g.prog_space != 2 ? 1 : 2};
+    if (!specialised) {
+        const size_t need = cc_eval_smem_bytes(cfg, prog->dec.info.n_slots, prog->dec.info.n_micro_words);
+        if (need > (size_t)g.prop.sharedMemPerBlockOptin)
+            return fail(CC_ERR_TOO_LARGE, "program needs " + std::to_string(need) + " bytes of shared memory per CTA");
+        int rc = prepare_program(prog, cfg);
+        if (rc) return rc;
+    }
+    r.code = prog->d_code;
+    r.code_words = prog->dec.info.n_micro_words;
+    r.n_slots = prog->dec.info.n_slots;
+    DevBuf count;  // released on every path
+    if (eval_count) {
+        int rc = count.reserve(8);
+        if (rc) return rc;
+        CU(cudaMemsetAsync(count.p, 0, 8, g.compute));
+    }
+    r.eval_count = count.as<unsigned long long>();
+    int e = cc_launch_render(ray ? 1 : 0, specialised ? 0 : cfg.prog_space, specialised ? prog : nullptr, r, g.compute);
+    if (e) return cuda_fail((cudaError_t)e, "render kernel launch");
+    g.launches += 1;
+    g.points += (uint64_t)r.w * r.h;
+    if (eval_count) {
+        unsigned long long h = 0;
+        CU(cudaMemcpyAsync(&h, count.p, 8, cudaMemcpyDeviceToHost, g.compute));
+        CU(cudaStreamSynchronize(g.compute));
+        *eval_count = h;
+    }
+    return CC_OK;
+}
+}  // namespace
+
 extern "C" {
+
+int cc_ray_caster(const cc_program *prog, const float origin[3], const float forward[3], const float up[3],
+                  const float right[3], float pixel_tolerance, float box_radius, float min_distance,
+                  float max_distance, float floor_z, uint32_t render_options, uint32_t width, uint32_t height,
+                  uint8_t *d_out, uint64_t *eval_count, cc_event **ev)
+{
+    NEED_INIT();
+    if (!prog || !origin || !forward || !up || !right || !d_out) return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
+    if (render_options & ~3u) return fail(CC_ERR_INVALID_ARGUMENT, "unknown render option");
+    cc_render_launch r;
+    std::memset(&r, 0, sizeof(r));
+    for (int i = 0; i < 3; ++i) {
+        r.origin[i] = origin[i]; r.forward[i] = forward[i]; r.up[i] = up[i]; r.right[i] = right[i];
+    }
+    r.pixel_tolerance = pixel_tolerance; r.box_radius = box_radius; r.min_distance = min_distance;
+    r.max_distance = max_distance; r.floor_z = floor_z; r.options = render_options;
+    r.w = width; r.h = height; r.out = d_out;
+    int rc = launch_render(true, prog, r, eval_count);
+    if (rc) return rc;
+    return make_event(ev, g.compute);
+}
+
+int cc_bitmap(const cc_program *prog, const float origin[3], float step_size, uint32_t width, uint32_t height,
+              uint8_t *d_out, cc_event **ev)
+{
+    NEED_INIT();
+    if (!prog || !origin || !d_out) return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
+    cc_render_launch r;
+    std::memset(&r, 0, sizeof(r));
+    for (int i = 0; i < 3; ++i) r.origin[i] = origin[i];
+    r.step_size = step_size; r.w = width; r.h = height; r.out = d_out;
+    int rc = launch_render(false, prog, r, nullptr);
+    if (rc) return rc;
+    return make_event(ev, g.compute);
+}
 
 int cc_process_polygon(const float box_corner[2], float box_step, uint32_t cells_x, uint32_t cells_y,
                        const void *d_corners, void *d_vertices, uint32_t *d_links, uint32_t *d_starts,
