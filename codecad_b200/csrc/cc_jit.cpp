@@ -559,7 +559,7 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
 // CODECAD_B200_JIT_PTS / _THREADS / _MINB.
 // Share of a program's work spent in ops that run lane by lane (no packed form: data-dependent
 // loops and early exits).  Such programs gain nothing from a second point per thread but pay its
-// registers: airfoil (two 80-edge polygons) runs 11 % faster with one point per thread.
+// registers.
 static bool lane_by_lane_dominated(const cc_decoded &dec)
 {
     const std::vector<uint32_t> &c = dec.microcode;
@@ -568,7 +568,7 @@ static bool lane_by_lane_dominated(const cc_decoded &dec)
         const uint32_t h = c[pc], op = CC_HDR_OP(h);
         if (op == MOP_RETURN) break;
         switch (op) {
-        case MOP_POLYGON: heavy += 20ull * (uint32_t)(*reinterpret_cast<const float *>(&c[pc + 1])); break;
+        // (polygon2d is no longer in this list: its edge loop is branch-free lane-vector code)
         case MOP_REGPOLY: case MOP_TWIST_FROM: heavy += 60; break;
         case MOP_TWIST_TO: case MOP_CREP_TO: case MOP_CREP_FROM: heavy += 40; break;
         case MOP_REPETITION: heavy += 30; break;

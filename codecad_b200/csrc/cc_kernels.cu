@@ -59,10 +59,10 @@ struct ProgFetch {
     CC_DEV float operator()(uint32_t i) const { return P.f(base + i); }
 };
 // polygons2d.cl:1-74; the edge table lives after the RETURN instruction, word 2 = its offset
-template <int MODE>
-CC_DEV_HEAVY float4 cc_polygon2d(const Prog<MODE> &P, uint32_t pc, float4 co)
+template <class V, int MODE>
+CC_DEV_HEAVY cc_val<V> cc_polygon2d(const Prog<MODE> &P, uint32_t pc, cc_val<V> co)
 {
-    return cc_polygon2d_core(ProgFetch<MODE>{P, P.u(pc + 2)}, (uint32_t)P.f(pc + 1), co);
+    return cc_polygon2d_v<V>(ProgFetch<MODE>{P, P.u(pc + 2)}, (uint32_t)P.f(pc + 1), co);
 }
 
 // ---- the interpreter ------------------------------------------------------------------------
@@ -157,7 +157,7 @@ CC_DEV void cc_interpret(const Prog<SMEM> P, float4 *__restrict__ regs, const ty
         }
         case MOP_POLYGON: {
 #pragma unroll
-            CC_EACH L[g] = cc_map1(L[g], [&](float4 p) { return cc_polygon2d<SMEM>(P, pc, p); });
+            CC_EACH L[g] = cc_polygon2d<V, SMEM>(P, pc, L[g]);
             pc += CC_LEN_0;
             break;
         }

@@ -471,47 +471,82 @@ CC_DEV void cc_prim_n(const float (&m)[12], const float (&mf)[12], unsigned mask
 // shapes/polygons2d.cl:1-74 over a precomputed edge table (px, py, dx, dy, 1/|d|^2, cy) per
 // edge; FETCH(i) returns table word i (the interpreter reads it from the microcode, the
 // specialised kernels from a __constant__ array).
+//
+// The edge loop is branch-free and works on lane vectors: per edge the candidate squared distance
+// is selected (segment interior / start vertex / none when t > 1) and only two running values are
+// kept per point, the smallest squared distance and the index of the edge that produced it (as a
+// float: exact below 2^24 edges).  Which kind of feature won and its normal are recomputed once,
+// after the loop, from that edge — the same operations on the same operands, hence the same bits
+// as the reference's running (normal, isVertex) pair with its strict `<` update.  The crossing
+// test reuses the previous edge's end-point comparison (cy of edge i is py of edge i+1).
 template <class FETCH>
-CC_DEV float4 cc_polygon2d_core(const FETCH &fetch, uint32_t n, float4 co)
+CC_DEV float4 cc_polygon2d_finish(const FETCH &fetch, float best, float x, float y, float nearest, float outside)
 {
-    float nnx = 0.0f, nny = 0.0f, nearest = __int_as_float(0x7f800000), outside = 1.0f;
+    float nnx = 0.0f, nny = 0.0f;
     bool nearest_is_vertex = false;
-    uint32_t e = 0;
-    for (uint32_t i = 0; i < n; ++i, e += 6) {
-        float px = fetch(e), py = fetch(e + 1), dx = fetch(e + 2), dy = fetch(e + 3), inv = fetch(e + 4),
-              cy = fetch(e + 5);
-        float tqx = co.x - px, tqy = co.y - py;
-        float snx = -dy, sny = dx;
-        if (((py < co.y) != (cy < co.y)) && (dy * cc_fma(snx, tqx, sny * tqy) > 0.0f)) outside = -outside;
-        float t = cc_fma(dx, tqx, dy * tqy) * inv;
-        if (t > 1.0f) continue;
-        float cnx, cny, cd;
-        bool civ;
-        if (t >= 0.0f) {
-            float tcx = cc_fma(-t, dx, tqx), tcy = cc_fma(-t, dy, tqy);
-            cd = cc_fma(tcx, tcx, tcy * tcy);
-            cnx = snx; cny = sny; civ = false;
-        } else {
-            cnx = tqx; cny = tqy;
-            cd = cc_fma(cnx, cnx, cny * cny);
-            civ = cd > 1.1920928955078125e-7f;
-            if (!civ) { cnx = snx; cny = sny; }
+    if (best >= 0.0f) {
+        const uint32_t e = 6u * (uint32_t)best;
+        const float px = fetch(e), py = fetch(e + 1), dx = fetch(e + 2), dy = fetch(e + 3), inv = fetch(e + 4);
+        const float tqx = x - px, tqy = y - py;
+        const float t = cc_fma(dx, tqx, dy * tqy) * inv;
+        nnx = -dy; nny = dx;  // segment normal
+        if (!(t >= 0.0f)) {
+            const float cd = cc_fma(tqx, tqx, tqy * tqy);
+            nearest_is_vertex = cd > 1.1920928955078125e-7f;  // too close to the vertex: keep the segment normal
+            if (nearest_is_vertex) { nnx = tqx; nny = tqy; }
         }
-        if (cd < nearest) { nearest = cd; nnx = cnx; nny = cny; nearest_is_vertex = civ; }
     }
-    float distance = outside * cc_sqrt(nearest);
-    float inv = nearest_is_vertex ? cc_rcp(distance) : cc_rcp(cc_len2(nnx, nny));
+    const float distance = outside * cc_sqrt(nearest);
+    const float inv = nearest_is_vertex ? cc_rcp(distance) : cc_rcp(cc_len2(nnx, nny));
     return make_float4(nnx * inv, nny * inv, 0.0f, distance);
+}
+
+template <class V, class FETCH>
+CC_DEV cc_val<V> cc_polygon2d_v(const FETCH &fetch, uint32_t n, cc_val<V> co)
+{
+    typedef typename cc_lane<V>::mask M;
+    const V zero = vbc<V>(0.0f), one = vbc<V>(1.0f);
+    V nearest = vbc<V>(__int_as_float(0x7f800000)), best = vbc<V>(-1.0f), outside = one;
+    M prev_below = vlt(vbc<V>(n ? fetch(1) : 0.0f), co.y);  // previousPoint.y < coords.y of edge 0
+    uint32_t e = 0;
+#pragma unroll 2
+    for (uint32_t i = 0; i < n; ++i, e += 6) {
+        const float px = fetch(e), py = fetch(e + 1), dx = fetch(e + 2), dy = fetch(e + 3), inv = fetch(e + 4),
+                    cy = fetch(e + 5);
+        const V tqx = vsub(co.x, vbc<V>(px)), tqy = vsub(co.y, vbc<V>(py));
+        // polygons2d.cl:24-26: even-odd crossing test
+        const M cur_below = vlt(vbc<V>(cy), co.y);
+        const V side = vmul(vbc<V>(dy), vfma(vbc<V>(-dy), tqx, vmul(vbc<V>(dx), tqy)));
+        outside = vsel(mand(mxor(prev_below, cur_below), vgt(side, zero)), vneg(outside), outside);
+        prev_below = cur_below;
+        // :28-52: nearest point of the edge, t > 1 belongs to the next edge's start vertex
+        // For t < 0 (or NaN) the candidate is the start vertex, |toQuery|^2.  Clamping t at zero
+        // gives exactly that through the segment formula: fma(-0, d, tq) == tq up to the sign of a
+        // zero, which the squares erase; fmaxf returns 0 for a NaN t, the branch the reference's
+        // `t >= 0` test takes as well.
+        const V t = vmul(vfma(vbc<V>(dx), tqx, vmul(vbc<V>(dy), tqy)), vbc<V>(inv));
+        const V tc = vmax(t, zero);
+        const V tcx = vfma(vneg(tc), vbc<V>(dx), tqx), tcy = vfma(vneg(tc), vbc<V>(dy), tqy);
+        const V cd = vfma(tcx, tcx, vmul(tcy, tcy));
+        // :55-60
+        const M better = mand(mnot(vgt(t, one)), vlt(cd, nearest));
+        nearest = vsel(better, cd, nearest);
+        best = vsel(better, vbc<V>((float)i), best);
+        (void)py;
+    }
+    cc_val<V> r;
+#pragma unroll
+    for (int l = 0; l < cc_lane<V>::N; ++l)
+        cc_lane_put(r, l, cc_polygon2d_finish(fetch, cc_lane_scalar(best, l), cc_lane_scalar(co.x, l), cc_lane_scalar(co.y, l),
+                                              cc_lane_scalar(nearest, l), cc_lane_scalar(outside, l)));
+    return r;
 }
 
 struct cc_table_fetch {
     const float *t;
     CC_DEV float operator()(uint32_t i) const { return t[i]; }
 };
-__device__ __noinline__ float4 cc_polygon2d_table(const float *table, uint32_t n, float4 co)
-{
-    return cc_polygon2d_core(cc_table_fetch{table}, n, co);
-}
+
 
 // ---- out-of-line forms for LARGE programs (specialised kernels of more than a few hundred
 // micro-ops): one copy of the code, parameters read from a __constant__ table through a uniform
@@ -689,9 +724,11 @@ template <class V> CC_DEV cc_val<V> cc_op_crep_from(float a0, float a1, cc_val<V
 {
     return cc_map2(a, point, [&](float4 p, float4 q) { return cc_circular_repetition_from(a0, a1, p, q); });
 }
+// inlined on purpose: `table` is then a known __constant__ array and the loop counter is uniform, so
+// the six edge parameters are constant-bank operands of the arithmetic instead of loads
 template <class V> CC_DEV cc_val<V> cc_op_polygon_table(const float *table, uint32_t n, cc_val<V> a)
 {
-    return cc_map1(a, [&](float4 p) { return cc_polygon2d_table(table, n, p); });
+    return cc_polygon2d_v<V>(cc_table_fetch{table}, n, a);
 }
 
 // ---- shared-memory value slots (interpreter) / value cells (specialised kernels) ----

@@ -129,3 +129,21 @@ def test_menger_256_against_oracle_planes(cb, scenes):
     for x in (0, 77, 128, 255):
         want = oracle.grid_eval(s.words, corner, step, (1, n, n), x_offset=x)[0]
         assert np.array_equal(got[x], want, equal_nan=True)
+
+
+@pytest.mark.parametrize("name", ["cfg_planetary", "cfg_menger_sponge", "cfg_airfoil", "cfg_csg_example"])
+def test_config_scenes_rendered_at_the_reference_size(cb, scenes, name):
+    """The reference's default picture, 1024x768 (rendering/image.py:7), of the BASELINE scenes: both
+    tiers byte-identical to the oracle's restatement of the ray caster (~11 M evaluate() calls)."""
+    from oracle import render as oracle_render
+    from codecad_b200.cl_util.buffer import ProgramBuffer
+    from codecad_b200.rendering import image
+    s = scenes[name]
+    scene = s.compiled()
+    size = (1024, 768)
+    want = oracle_render.ray_cast(s.words, s.box_a, s.box_b, size)
+    assert np.array_equal(image.render_pixels(scene, size), want)
+    scene.program_buffer().specialize(1, ProgramBuffer.SINK_RAY)
+    assert scene.program_buffer().use_specialized(True)
+    assert np.array_equal(image.render_pixels(scene, size), want)
+    assert (want != want[0, 0]).any()          # not a blank picture
