@@ -315,6 +315,53 @@ static inline v4 polygon2d(const ins_t *I, v4 co)
     return mk(nnx * inv, nny * inv, 0, distance);
 }
 
+/* The PRODUCT's formulation of the same op (codecad_b200/csrc/cc_ops.cuh cc_polygon2d_v), restated
+ * here only so that tests/test_oracle_known_answers.py can compare the two formulations on millions
+ * of points on the CPU: branch-free edge loop keeping the smallest squared distance and the index of
+ * the edge that produced it, t clamped at zero instead of a separate start-vertex candidate, crossing
+ * test reusing the previous end-point comparison; feature kind and normal recomputed after the loop. */
+static int g_polygon_alt = 0;
+static inline v4 polygon2d_alt(const ins_t *I, v4 co)
+{
+    float nearest = INFINITY, best = -1.0f, outside = 1.0f;
+    int prev_below = I->n ? (I->edges[1] < co.y) : 0;
+    for (int i = 0; i < I->n; ++i) {
+        const float *e = I->edges + 5 * i;
+        float px = e[0], py = e[1], dx = e[2], dy = e[3], cy = I->p[2 + 2 * i];
+        float tqx = co.x - px, tqy = co.y - py;
+        int cur_below = cy < co.y;
+        float side = dy * cc_fma(-dy, tqx, dx * tqy);
+        if ((prev_below != cur_below) && side > 0.0f) outside = -outside;
+        prev_below = cur_below;
+        float t = cc_fma(dx, tqx, dy * tqy) * e[4];
+        float tc = fmaxf(t, 0.0f);
+        float tcx = cc_fma(-tc, dx, tqx), tcy = cc_fma(-tc, dy, tqy);
+        float cd = cc_fma(tcx, tcx, tcy * tcy);
+        int better = !(t > 1.0f) && (cd < nearest);
+        nearest = better ? cd : nearest;
+        best = better ? (float)i : best;
+        (void)py;
+    }
+    float nnx = 0.0f, nny = 0.0f;
+    int nearest_is_vertex = 0;
+    if (best >= 0.0f) {
+        const float *e = I->edges + 5 * (int)best;
+        float px = e[0], py = e[1], dx = e[2], dy = e[3];
+        float tqx = co.x - px, tqy = co.y - py;
+        float t = cc_fma(dx, tqx, dy * tqy) * e[4];
+        nnx = -dy; nny = dx;
+        if (!(t >= 0.0f)) {
+            float cd = cc_fma(tqx, tqx, tqy * tqy);
+            nearest_is_vertex = cd > 1.1920928955078125e-7f;
+            if (nearest_is_vertex) { nnx = tqx; nny = tqy; }
+        }
+    }
+    float distance = outside * cc_sqrt(nearest);
+    float inv = nearest_is_vertex ? cc_rcp(distance) : cc_rcp(cc_len2(nnx, nny));
+    return mk(nnx * inv, nny * inv, 0, distance);
+}
+void oracle_set_polygon_formulation(int alt) { g_polygon_alt = alt; }
+
 /* gears.cl:1-42 */
 static inline v4 involute_gear(const ins_t *I, v4 co)
 {
@@ -424,7 +471,7 @@ static v4 evaluate(const prog_t *prog, float px, float py, float pz)
             break;
         }
         case OP_REGULAR_POLYGON2D: last = regular_polygon2d(I, last); break;
-        case OP_POLYGON2D: last = polygon2d(I, last); break;
+        case OP_POLYGON2D: last = g_polygon_alt ? polygon2d_alt(I, last) : polygon2d(I, last); break;
         case OP_SPHERE: { /* simple3d.cl:1-12 */
             float len = cc_len3(last.x, last.y, last.z);
             if (len == 0.0f) last = mk(1, 0, 0, len - p[0]);

@@ -345,7 +345,8 @@ def test_specialized_segmented_programs(cb, scenes, name, seg, monkeypatch):
 
 @pytest.mark.parametrize("tier", ["interpreter", "specialised"])
 @pytest.mark.parametrize("name", ["cfg_planetary", "cfg_csg_example", "dsdf2d_gear", "dsdf3d_extreme_twisted_revolve",
-                                  "x_repetition", "cfg_synthetic32"])
+                                  "x_repetition", "cfg_synthetic32", "cfg_airfoil", "dsdf2d_polygon2d_non_convex",
+                                  "dsdf2d_polygon2d_collinear_consecutive_edges"])
 def test_evaluate_points_bit_exact(cb, scenes, name, tier):
     from codecad_b200.cl_util.buffer import ProgramBuffer
     s = scenes[name]
@@ -356,7 +357,9 @@ def test_evaluate_points_bit_exact(cb, scenes, name, tier):
     pts = (a + (b - a) * (rng.random((n, 3)) * 1.4 - 0.2)).astype(np.float32)
     if s.dimension == 2:
         pts[:, 2] = 0
-    pts[:3] = [[0, 0, 0], [np.inf, 0, 0], [np.nan, 1, 2]]   # special operands travel the same paths
+    pts[:6] = [[0, 0, 0], [np.inf, 0, 0], [np.nan, 1, 2], [1, -np.inf, 0], [3e38, 3e38, 0], [1e-40, -1e-42, 0]]
+    if s.words.size > 8:                                    # and points exactly on polygon vertices / edges
+        pts[6:10] = [[0, 0, 0], [3, 3, 0], [1.5, 0, 0], [4, 0, 0]]
     prog = ProgramBuffer(s.words)
     if tier == "specialised":
         prog.specialize(2, ProgramBuffer.SINK_POINTS)
