@@ -516,8 +516,13 @@ CC_DEV cc_val<V> cc_polygon2d_v(const FETCH &fetch, uint32_t n, cc_val<V> co)
         const V tqx = vsub(co.x, vbc<V>(px)), tqy = vsub(co.y, vbc<V>(py));
         // polygons2d.cl:24-26: even-odd crossing test
         const M cur_below = vlt(vbc<V>(cy), co.y);
-        const V side = vmul(vbc<V>(dy), vfma(vbc<V>(-dy), tqx, vmul(vbc<V>(dx), tqy)));
-        outside = vsel(mand(mxor(prev_below, cur_below), vgt(side, zero)), vneg(outside), outside);
+        const M straddle = mxor(prev_below, cur_below);
+        // few edges straddle a point's y, and the points of a warp are neighbours: skip the side
+        // test when no lane needs it (warp-uniform branch; `outside` is unchanged in that case)
+        if (__any_sync(0xffffffffu, many(straddle))) {
+            const V side = vmul(vbc<V>(dy), vfma(vbc<V>(-dy), tqx, vmul(vbc<V>(dx), tqy)));
+            outside = vsel(mand(straddle, vgt(side, zero)), vneg(outside), outside);
+        }
         prev_below = cur_below;
         // :28-52: nearest point of the edge, t > 1 belongs to the next edge's start vertex
         // For t < 0 (or NaN) the candidate is the start vertex, |toQuery|^2.  Clamping t at zero
