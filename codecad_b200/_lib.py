@@ -88,6 +88,7 @@ SIGNATURES = {
     "cc_ray_caster": (_I, [_V, c_float_p, c_float_p, c_float_p, c_float_p, _F, _F, _F, _F, _F, _U, _U, _U, _V,
                            ctypes.POINTER(ctypes.c_uint64), c_void_pp]),
     "cc_bitmap": (_I, [_V, c_float_p, _F, _U, _U, _V, c_void_pp]),
+    "cc_matplotlib_slice": (_I, [_V, c_float_p, _F, _U, _U, _V, c_void_pp]),
     "cc_process_polygon": (_I, [c_float_p, _F, _U, _U, _V, _V, _V, _V, _U, _V, c_void_pp]),
     "cc_polygon_blocks": (_I, [_V, ctypes.POINTER(ctypes.c_double), ctypes.c_double, _U, _U, _U, _V, _V, _V, _V]),
     "cc_mesh_blocks": (_I, [_V, ctypes.POINTER(ctypes.c_double), ctypes.c_double, _U, _U, _U, _U,

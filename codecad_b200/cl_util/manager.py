@@ -154,6 +154,16 @@ class _Kernels:
                                             ctypes.byref(ev)))
         return Event(ev)
 
+    # rendering/matplotlib_slice.cl:1-4   matplotlib_slice(scene, float4 boxCorner, float boxStep, float* output)
+    def matplotlib_slice(self, global_size, local_size, program, corner, step, output, wait_for=None):
+        w, h, _ = _dims(global_size)
+        if output.size < w * h * 12:
+            raise RuntimeError("Output buffer too small for the launch")
+        ev = _new_event_ref()
+        _lib.check(_lib.lib().cc_matplotlib_slice(program.handle, _lib.f3(corner), float(np.float32(step)), w, h,
+                                                  output.device_ptr, ctypes.byref(ev)))
+        return Event(ev)
+
     # rendering/polygon2d.cl:82-90   process_polygon(float2 boxCorner, float boxStep, corners, vertices, links,
     #                                                starts, startCounter)
     def process_polygon(self, global_size, local_size, box_corner, box_step, corners, vertices, links, starts,
@@ -177,7 +187,7 @@ class _Kernels:
     def __getattr__(self, name):
         raise AttributeError(
             "kernel %r has no CUDA counterpart (available: grid_eval, grid_eval_pymcubes, subdivision_step, "
-            "mass_properties, bitmap, ray_caster, process_polygon); there is no OpenCL fallback" % name)
+            "mass_properties, bitmap, ray_caster, process_polygon, matplotlib_slice); there is no OpenCL fallback" % name)
 
 
 class OpenCLManager:

@@ -1141,6 +1141,27 @@ int cc_bitmap(const cc_program *prog, const float origin[3], float step_size, ui
     return make_event(ev, g.compute);
 }
 
+int cc_matplotlib_slice(const cc_program *prog, const float corner[3], float step, uint32_t width, uint32_t height,
+                        float *d_out, cc_event **ev)
+{
+    NEED_INIT();
+    if (!prog || !corner || !d_out) return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
+    int rc = check_dims(width, height, 1);
+    if (rc) return rc;
+    DevBuf field;
+    if ((rc = field.reserve((size_t)width * height * 16))) return rc;
+    cc_eval_args a;
+    fill_common(&a, prog);
+    a.cx = corner[0]; a.cy = corner[1]; a.cz = corner[2]; a.step = step;
+    a.nx = width; a.ny = height; a.nz = 1; a.n_blocks = 1;
+    a.out = field.p;
+    if ((rc = launch(CC_SINK_FLOAT4, prog, a, (uint64_t)width * height))) return rc;
+    int e = cc_launch_slice_repack(field.p, width, height, d_out, g.compute);
+    if (e) return cuda_fail((cudaError_t)e, "slice repack launch");
+    g.launches += 1;
+    return make_event(ev, g.compute);
+}
+
 int cc_process_polygon(const float box_corner[2], float box_step, uint32_t cells_x, uint32_t cells_y,
                        const void *d_corners, void *d_vertices, uint32_t *d_links, uint32_t *d_starts,
                        uint32_t max_starts, uint32_t *d_start_counter, cc_event **ev)

@@ -131,6 +131,7 @@ struct cc_polygon_args {
     uint32_t max_starts;             // <= 1024
 };
 int cc_launch_process_polygon(const cc_polygon_args &a, void *stream);
+int cc_launch_slice_repack(const void *d_field, uint32_t w, uint32_t h, float *d_out, void *stream);
 
 // ---- marching cubes over leaf blocks (cc_mesh.cu) ---------------------------------------------
 struct cc_mesh_args {

@@ -146,7 +146,29 @@ __global__ void __launch_bounds__(1024) cc_sort_starts_kernel(uint32_t *starts, 
     if (i < n) mine[i] = s[i];
 }
 
+// matplotlib_slice  /root/reference/codecad/rendering/matplotlib_slice.cl:1-20: the viewer's layout
+// (distance, gradient x, gradient y) at (x + y*w)*3, from the float4 grid [w][h] grid_eval wrote
+__global__ void __launch_bounds__(256) cc_slice_repack_kernel(const float4 *__restrict__ field, uint32_t w, uint32_t h,
+                                                             float *__restrict__ out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * 256u + threadIdx.x;  // output pixel, x fastest
+    if (i >= (uint64_t)w * h) return;
+    const uint32_t y = (uint32_t)(i / w), x = (uint32_t)(i - (uint64_t)y * w);
+    const float4 v = field[(size_t)y + (size_t)h * x];
+    out[3 * i + 0] = v.w;
+    out[3 * i + 1] = v.x;
+    out[3 * i + 2] = v.y;
+}
+
 }  // namespace
+
+int cc_launch_slice_repack(const void *d_field, uint32_t w, uint32_t h, float *d_out, void *stream)
+{
+    const uint64_t n = (uint64_t)w * h;
+    if (n == 0) return 0;
+    cc_slice_repack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float4 *)d_field, w, h, d_out);
+    return (int)cudaGetLastError();
+}
 
 int cc_launch_process_polygon(const cc_polygon_args &a, void *stream)
 {

@@ -19,8 +19,8 @@ What it does (INTEGRATION.md has the file-level view):
     are never loaded: the modules of this package take their place under those names.
 
 Everything else of the reference (shapes, nodes, util, assemblies, rendering front ends)
-is imported unchanged.  The one remaining OpenCL kernel of the reference without a CUDA
-counterpart (matplotlib_slice) raises AttributeError when launched: out of scope, no fallback.
+is imported unchanged.  All eight production kernels of the reference have CUDA counterparts behind
+`opencl_manager.k`; any other kernel name raises AttributeError (no OpenCL fallback).
 """
 import importlib
 import sys
@@ -110,6 +110,7 @@ def install(force_pyopencl=True):
         "codecad.rendering.bitmap": importlib.import_module("codecad_b200.rendering.bitmap"),
         "codecad.rendering.image": importlib.import_module("codecad_b200.rendering.image"),
         "codecad.rendering.polygon2d": importlib.import_module("codecad_b200.rendering.polygon2d"),
+        "codecad.rendering.matplotlib_slice": importlib.import_module("codecad_b200.rendering.matplotlib_slice"),
     }
     sys.modules.update(aliases)
     return sorted(aliases)

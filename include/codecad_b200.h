@@ -211,6 +211,12 @@ int cc_mass_properties(const cc_program *prog, const double box_a[3], double res
                        const cc_level *levels, uint32_t n_levels,
                        uint32_t rank, uint32_t world, double integrals[10], uint64_t stats[4]);
 
+/* matplotlib_slice  rendering/matplotlib_slice.cl:1-20 (global size (width, height),
+ * rendering/matplotlib_slice.py:44-52): d_out[(x + y*width)*3 + 0..2] = distance, gradient x,
+ * gradient y at corner + step * (x, y, 0) — the numpy array [height][width][3] the viewer plots. */
+int cc_matplotlib_slice(const cc_program *prog, const float corner[3], float step, uint32_t width, uint32_t height,
+                        float *d_out, cc_event **ev);
+
 /* ---- 2-D outlines: rendering/polygon2d.cl + the device half of
  * rendering/polygon2d.py:36-173.
  * process_polygon  polygon2d.cl:82-175 with global size (cells_x, cells_y, 2): d_corners is the

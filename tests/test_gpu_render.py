@@ -197,3 +197,24 @@ def test_kernel_proxy_process_polygon(cb, scenes):
     assert np.array_equal(links.read(wait_for=[ev]), want_l)
     assert int(counter.read(wait_for=[ev])[0]) == len(want_s)
     assert np.array_equal(starts.read(wait_for=[ev])[:len(want_s)], want_s)
+
+
+@pytest.mark.parametrize("name", ["dsdf2d_gear", "dsdf2d_nonconvex_shell1", "dsdf3d_csg_thing"])
+def test_matplotlib_slice_field(cb, scenes, name):
+    """matplotlib_slice.cl:1-20 through rendering.matplotlib_slice.slice_values and through k.matplotlib_slice."""
+    import oracle
+    from codecad_b200 import cl_util
+    from codecad_b200.cl_util import opencl_manager
+    from codecad_b200.rendering import matplotlib_slice
+    s = scenes[name]
+    scene = s.compiled()
+    values, corner, resolution, _ = matplotlib_slice.slice_values(scene)
+    h, w, three = values.shape
+    assert three == 3
+    c32 = np.array([corner.x, corner.y, corner.z], np.float64).astype(np.float32)
+    field = oracle.grid_eval(s.words, c32, np.float32(resolution), (w, h, 1))[:, :, 0, :]      # [x][y][4]
+    want = np.stack([field[..., 3], field[..., 0], field[..., 1]], -1).transpose((1, 0, 2))      # [y][x][3]
+    assert np.array_equal(values, want, equal_nan=True)
+    out = cl_util.Buffer(np.float32, [h, w, 3])
+    ev = opencl_manager.k.matplotlib_slice((w, h), None, scene.program_buffer(), corner.as_float4(), np.float32(resolution), out)
+    assert np.array_equal(out.read(wait_for=[ev]).reshape(h, w, 3), want, equal_nan=True)
