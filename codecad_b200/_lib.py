@@ -91,6 +91,8 @@ SIGNATURES = {
     "cc_matplotlib_slice": (_I, [_V, c_float_p, _F, _U, _U, _V, c_void_pp]),
     "cc_process_polygon": (_I, [c_float_p, _F, _U, _U, _V, _V, _V, _V, _U, _V, c_void_pp]),
     "cc_polygon_blocks": (_I, [_V, ctypes.POINTER(ctypes.c_double), ctypes.c_double, _U, _U, _U, _V, _V, _V, _V]),
+    "cc_polygon_assemble": (_I, [_V, _V, _V, _V, _V, ctypes.c_int64, _U, _U, _U, ctypes.POINTER(ctypes.POINTER(ctypes.c_float)),
+                                 ctypes.POINTER(ctypes.POINTER(ctypes.c_uint64)), ctypes.POINTER(ctypes.c_uint64)]),
     "cc_mesh_blocks": (_I, [_V, ctypes.POINTER(ctypes.c_double), ctypes.c_double, _U, _U, _U, _U,
                             ctypes.POINTER(ctypes.POINTER(ctypes.c_double)),
                             ctypes.POINTER(ctypes.POINTER(ctypes.c_uint32)), ctypes.POINTER(ctypes.c_uint64)]),

@@ -591,14 +591,16 @@ int cc_buffer_free(void *dptr)
 int cc_host_alloc(size_t bytes, void **hptr)
 {
     NEED_INIT();
-    CU(cudaMallocHost(hptr, bytes ? bytes : 1));
+    if (!hptr) return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
+    *hptr = g_pinned.get(bytes);  // pooled: page-locking costs ~0.3 ms per MB
+    if (!*hptr) return fail(CC_ERR_CUDA, "cudaHostAlloc failed for " + std::to_string(bytes) + " bytes");
     return CC_OK;
 }
 
 int cc_host_free(void *hptr)
 {
     NEED_INIT();
-    if (hptr) CU(cudaFreeHost(hptr));
+    if (hptr && !g_pinned.put(hptr)) CU(cudaFreeHost(hptr));
     return CC_OK;
 }
 
@@ -1103,6 +1105,143 @@ int launch_render(bool ray, const cc_program *prog, cc_render_launch &r, uint64_
     return CC_OK;
 }
 }  // namespace
+
+// ---- host half of polygon(): follow the links of process_polygon into closed outlines -------------
+// (rendering/polygon2d.py:15-31 _collect_polygon / _step_from_overflow_spec, :119-170).  No device
+// work: usable without cc_init.
+namespace {
+constexpr uint32_t kLinkOverflowMask = 0xFFF00000u;  // flags (bits 29-31) + row / column (bits 20-28)
+constexpr uint32_t kLinkIndexMask = 0x000FFFFFu;
+
+struct PieceKey {
+    int64_t x, y;
+    uint32_t spec;
+    bool operator==(const PieceKey &o) const { return x == o.x && y == o.y && spec == o.spec; }
+};
+struct PieceKeyHash {
+    size_t operator()(const PieceKey &k) const
+    {
+        uint64_t h = (uint64_t)k.x * 0x9E3779B97F4A7C15ull;
+        h ^= ((uint64_t)k.y + 0x7F4A7C15ull + (h << 6) + (h >> 2));
+        h ^= ((uint64_t)k.spec * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2));
+        return (size_t)h;
+    }
+};
+struct Piece {
+    std::vector<float> v;  // x0, y0, x1, y1, ...
+    PieceKey begin, end;
+};
+// Outline pieces that cross box borders, joinable at either end.
+struct OpenChains {
+    std::unordered_map<PieceKey, Piece *, PieceKeyHash> by_begin, by_end;
+    std::vector<std::unique_ptr<Piece>> store;
+    // returns the piece if this addition closed it
+    Piece *add(std::vector<float> &&chain, const PieceKey &begin, const PieceKey &end)
+    {
+        Piece *piece;
+        auto it = by_end.find(begin);
+        if (it == by_end.end()) {
+            store.emplace_back(new Piece{std::move(chain), begin, end});
+            piece = store.back().get();
+            by_begin[begin] = piece;
+        } else {  // continues a chain that ended on this box's border
+            piece = it->second;
+            by_end.erase(it);
+            piece->v.insert(piece->v.end(), chain.begin(), chain.end());
+            piece->end = end;
+        }
+        auto jt = by_begin.find(end);
+        if (jt == by_begin.end()) {
+            by_end[end] = piece;
+            return nullptr;
+        }
+        Piece *next = jt->second;
+        by_begin.erase(jt);
+        if (next == piece) return piece;
+        piece->v.insert(piece->v.end(), next->v.begin(), next->v.end());
+        piece->end = next->end;
+        std::vector<float>().swap(next->v);
+        by_end[piece->end] = piece;
+        return nullptr;
+    }
+};
+
+// appends the vertices from `index` on; visited links are overwritten with the mask; returns the
+// flags of the terminating link, or 0xFFFFFFFF on a link that points outside the box's arrays
+uint32_t follow_links(uint32_t *links, const float *vertices, uint32_t cells, uint32_t index, std::vector<float> *chain)
+{
+    while (!(index & kLinkOverflowMask)) {
+        if (index >= cells) return 0xFFFFFFFFu;
+        chain->push_back(vertices[2 * (size_t)index]);
+        chain->push_back(vertices[2 * (size_t)index + 1]);
+        const uint32_t next = links[index];
+        links[index] = kLinkOverflowMask;
+        index = next;
+    }
+    return index & kLinkOverflowMask;
+}
+}  // namespace
+
+extern "C" int cc_polygon_assemble(const float *vertices, uint32_t *links, const uint32_t *starts,
+                                   const uint32_t *start_counts, const int64_t *int_corners, int64_t int_step,
+                                   uint32_t cells, uint32_t max_starts, uint32_t n_blocks, float **out_vertices,
+                                   uint64_t **out_offsets, uint64_t *out_chains)
+{
+    if (!vertices || !links || !starts || !start_counts || !int_corners || !out_vertices || !out_offsets || !out_chains)
+        return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
+    *out_vertices = nullptr;
+    *out_offsets = nullptr;
+    *out_chains = 0;
+    std::vector<float> all;            // vertices of the finished outlines, in the order they close
+    std::vector<uint64_t> offsets{0};  // in vertices
+    OpenChains open;
+    for (uint32_t b = 0; b < n_blocks; ++b) {
+        uint32_t *bl = links + (size_t)b * cells;
+        const float *bv = vertices + 2 * (size_t)b * cells;
+        const int64_t cx = int_corners[3 * (size_t)b], cy = int_corners[3 * (size_t)b + 1];
+        const uint32_t ns = start_counts[b];
+        if (ns > max_starts) return fail(CC_ERR_INVALID_ARGUMENT, "more open chains than the start list holds");
+        for (uint32_t k = 0; k < ns; ++k) {  // chains that enter through the box border (polygon2d.py:121-163)
+            const uint32_t start = starts[(size_t)b * max_starts + k];
+            std::vector<float> chain;
+            const uint32_t spec = follow_links(bl, bv, cells, start & kLinkIndexMask, &chain);
+            if (spec == 0xFFFFFFFFu) return fail(CC_ERR_INVALID_ARGUMENT, "corrupt link");
+            const int64_t d = (spec & 0x20000000u) ? -1 : 1;  // polygon2d.py:26-31
+            const bool along_y = (spec & 0x40000000u) != 0;
+            const PieceKey begin{cx, cy, start & kLinkOverflowMask};
+            const PieceKey end{cx + (along_y ? 0 : d * int_step), cy + (along_y ? d * int_step : 0), spec};
+            if (Piece *closed = open.add(std::move(chain), begin, end)) {
+                all.insert(all.end(), closed->v.begin(), closed->v.end());
+                offsets.push_back(all.size() / 2);
+                std::vector<float>().swap(closed->v);
+            }
+        }
+        for (uint32_t i = 0; i < cells; ++i) {  // what is left are chains closed inside the box (:165-170)
+            if (bl[i] & kLinkOverflowMask) continue;
+            const size_t before = all.size();
+            const uint32_t spec = follow_links(bl, bv, cells, i, &all);
+            if (spec == 0xFFFFFFFFu) return fail(CC_ERR_INVALID_ARGUMENT, "corrupt link");
+            (void)before;
+            offsets.push_back(all.size() / 2);
+        }
+    }
+    if (!open.by_begin.empty() || !open.by_end.empty())
+        return fail(CC_ERR_OPEN_OUTLINE, "an outline left the subdivided region");
+    const size_t n_chains = offsets.size() - 1;
+    float *v = (float *)malloc(std::max<size_t>(all.size(), 1) * sizeof(float));
+    uint64_t *o = (uint64_t *)malloc(offsets.size() * sizeof(uint64_t));
+    if (!v || !o) {
+        free(v);
+        free(o);
+        return fail(CC_ERR_INVALID_ARGUMENT, "out of host memory");
+    }
+    if (!all.empty()) std::memcpy(v, all.data(), all.size() * sizeof(float));
+    std::memcpy(o, offsets.data(), offsets.size() * sizeof(uint64_t));
+    *out_vertices = v;
+    *out_offsets = o;
+    *out_chains = n_chains;
+    return CC_OK;
+}
 
 extern "C" {
 

@@ -5,7 +5,8 @@ a generator of closed vertex chains [(x, y), ...].
 The reference walks the leaf boxes of `subdivision(obj, feature_size / 2)` one at a time: a
 grid_eval launch, a process_polygon launch and five blocking reads per box (polygon2d.py:88-117).
 Here `cc_polygon_blocks` evaluates and processes every box in two launches and one round of
-copies; the host then follows the links exactly as the reference does:
+copies; `cc_polygon_assemble` (native host code, no device work) then follows the links exactly as
+the reference's Python does:
 
   * closed chains inside a box come out in increasing order of their first triangle
     (polygon2d.py:165-170) — for a shape that fits one box (the default grid of 128 and
@@ -14,18 +15,15 @@ copies; the host then follows the links exactly as the reference does:
     the pieces of the neighbouring boxes, in whatever order the boxes arrive, until they close.
     (The reference's bookkeeping for this case, polygon2d.py:131-163, leaves stale entries behind
     as soon as a chain crosses more than one box boundary and then trips its own assertion; the
-    piece table below implements what it is meant to do.)
+    piece table of the native code implements what it is meant to do.)
 """
 import ctypes
 
 import numpy as np
 
 from .. import _lib
-from ..geometry import Vector
+from ..cl_util.buffer import _Pinned
 from ..subdivision import LeafBlocks, block_corners, subdivision
-
-_LINK_OVERFLOW_MASK = 0xFFF00000   # polygon2d.cl:5-35: flags (bits 29-31) + row / column (bits 20-28)
-_INDEX_MASK = 0x000FFFFF
 
 
 def polygon_blocks(program_buffer, grid, corners, resolution):
@@ -36,10 +34,14 @@ def polygon_blocks(program_buffer, grid, corners, resolution):
     corners = np.ascontiguousarray(corners, dtype=np.float64).reshape(-1, 3)
     n = len(corners)
     cells = 2 * (gx - 1) * (gy - 1)
-    vertices = np.zeros((n, cells, 2), np.float32)
-    links = np.full((n, cells), 0xFFFFFFFF, np.uint32)
-    starts = np.zeros((n, gx + gy - 2), np.uint32)
-    counts = np.zeros((n,), np.uint32)
+    if n == 0:
+        return (np.zeros((0, cells, 2), np.float32), np.zeros((0, cells), np.uint32),
+                np.zeros((0, gx + gy - 2), np.uint32), np.zeros((0,), np.uint32))
+    # page-locked (pooled) result arrays: every element is written by the copies
+    vertices = _Pinned(n * cells * 8).array(np.float32, (n, cells, 2))
+    links = _Pinned(n * cells * 4).array(np.uint32, (n, cells))
+    starts = _Pinned(n * (gx + gy - 2) * 4).array(np.uint32, (n, gx + gy - 2))
+    counts = _Pinned(n * 4).array(np.uint32, (n,))
     if n:
         _lib.check(_lib.lib().cc_polygon_blocks(
             program_buffer.handle, corners.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), float(resolution),
@@ -47,60 +49,39 @@ def polygon_blocks(program_buffer, grid, corners, resolution):
     return vertices, links, starts, counts
 
 
-def _follow(links, vertices, index, chain):
-    """Append the vertices from `index` on until a link leaves the box or reaches a visited
-    triangle; visited links are overwritten with the mask.  Returns the terminating link's flags."""
-    while not index & _LINK_OVERFLOW_MASK:
-        chain.append(vertices[index])
-        nxt = links[index]
-        links[index] = _LINK_OVERFLOW_MASK
-        index = nxt
-    return index & _LINK_OVERFLOW_MASK
+ERR_OPEN_OUTLINE = -6  # CC_ERR_OPEN_OUTLINE (include/codecad_b200.h)
 
 
-def _neighbour_step(spec):
-    """Which neighbouring box a link with flags `spec` leads into (polygon2d.py:26-31)."""
-    d = -1 if spec & 0x20000000 else 1
-    return (0, d) if spec & 0x40000000 else (d, 0)
-
-
-class _Piece:
-    __slots__ = ("chain", "begin", "end")
-
-    def __init__(self, chain, begin, end):
-        self.chain, self.begin, self.end = chain, begin, end
-
-
-class _OpenChains:
-    """Pieces of outlines that cross box boundaries, joinable at either end."""
-
-    def __init__(self):
-        self.by_begin = {}
-        self.by_end = {}
-
-    def add(self, chain, begin, end):
-        """Returns a closed chain if this piece completed one, else None."""
-        prev = self.by_end.pop(begin, None)
-        if prev is None:
-            piece = _Piece(chain, begin, end)
-            self.by_begin[begin] = piece
-        else:  # continues a chain that ended on this box's border
-            prev.chain.extend(chain)
-            prev.end = end
-            piece = prev
-        nxt = self.by_begin.pop(end, None)
-        if nxt is None:
-            self.by_end[end] = piece
-            return None
-        if nxt is piece:
-            return piece.chain
-        piece.chain.extend(nxt.chain)
-        piece.end = nxt.end
-        self.by_end[nxt.end] = piece
-        return None
-
-    def __len__(self):
-        return len(self.by_begin) + len(self.by_end)
+def assemble(vertices, links, starts, counts, int_corners, int_step):
+    """Host half (native, no device work): dense per-box arrays of polygon_blocks() -> list of
+    closed chains [(x, y), ...] in the order they close.  `links` is consumed (visit marks)."""
+    n, cells = links.shape
+    int_corners = np.ascontiguousarray(int_corners, dtype=np.int64).reshape(-1, 3)
+    assert len(int_corners) == n and vertices.shape == (n, cells, 2) and starts.shape[0] == n
+    vertices = np.ascontiguousarray(vertices, dtype=np.float32)
+    links = np.ascontiguousarray(links, dtype=np.uint32)
+    starts = np.ascontiguousarray(starts, dtype=np.uint32)
+    counts = np.ascontiguousarray(counts, dtype=np.uint32)
+    out_v = ctypes.POINTER(ctypes.c_float)()
+    out_o = ctypes.POINTER(ctypes.c_uint64)()
+    n_chains = ctypes.c_uint64()
+    L = _lib.load()
+    rc = L.cc_polygon_assemble(vertices.ctypes.data, links.ctypes.data, starts.ctypes.data, counts.ctypes.data,
+                               int_corners.ctypes.data, int(int_step), cells, starts.shape[1], n,
+                               ctypes.byref(out_v), ctypes.byref(out_o), ctypes.byref(n_chains))
+    if rc == ERR_OPEN_OUTLINE:
+        # the reference ends with `assert len(open_chain_beginnings) == 0` (polygon2d.py:172-173)
+        raise AssertionError("an outline left the subdivided region")
+    _lib.check(rc)
+    try:
+        k = int(n_chains.value)
+        offsets = np.ctypeslib.as_array(out_o, shape=(k + 1,)).tolist()
+        total = offsets[-1]
+        flat = np.ctypeslib.as_array(out_v, shape=(max(total, 1), 2))[:total].tolist()
+        return [list(map(tuple, flat[offsets[i]:offsets[i + 1]])) for i in range(k)]
+    finally:
+        L.cc_free(out_v)
+        L.cc_free(out_o)
 
 
 def polygon(obj, subdivision_grid_size=None):
@@ -122,39 +103,9 @@ def polygon(obj, subdivision_grid_size=None):
 
     vertices, links, starts, counts = polygon_blocks(program_buffer, (grid_size[0], grid_size[1]),
                                                      block_corners(boxes), boxes[0][2])
-    open_chains = _OpenChains()
-    # only the triangles the outline crosses matter to the host: pull them out of the dense
-    # per-box arrays in one pass (links of untouched triangles are 0xFFFFFFFF)
-    hit_box, hit_index = np.nonzero(links != 0xFFFFFFFF)
-    first = np.searchsorted(hit_box, np.arange(len(boxes) + 1))
-    hit_links = links[hit_box, hit_index].tolist()
-    hit_vertices = list(map(tuple, vertices[hit_box, hit_index].tolist()))
-    hit_index = hit_index.tolist()
-    counts = counts.tolist()
-    for b in range(len(boxes)):
-        lo, hi = int(first[b]), int(first[b + 1])
-        if lo == hi:
-            continue
-        box_size, _, _, int_corner, int_resolution = boxes[b]
-        surface = hit_index[lo:hi]
-        box_links = dict(zip(surface, hit_links[lo:hi]))
-        box_vertices = dict(zip(surface, hit_vertices[lo:hi]))
-        assert counts[b] <= starts.shape[1]
-        if counts[b]:
-            int_step = int_resolution * (box_size[0] - 1)  # boxes share their border samples
-            for start in starts[b, :counts[b]].tolist():
-                begin = (int_corner[0], int_corner[1], start & _LINK_OVERFLOW_MASK)
-                chain = []
-                spec = _follow(box_links, box_vertices, start & _INDEX_MASK, chain)
-                dx, dy = _neighbour_step(spec)
-                end = (int_corner[0] + dx * int_step, int_corner[1] + dy * int_step, spec)
-                closed = open_chains.add(chain, begin, end)
-                if closed is not None:
-                    yield closed
-        for index in surface:  # what is left belongs to chains closed inside the box
-            if box_links[index] & _LINK_OVERFLOW_MASK:
-                continue
-            chain = []
-            _follow(box_links, box_vertices, index, chain)
-            yield chain
-    assert len(open_chains) == 0, "an outline left the subdivided region"
+    if isinstance(boxes, LeafBlocks):
+        int_corners, int_step = boxes.int_corners, boxes.int_step * (boxes.dims[0] - 1)
+    else:
+        int_corners = np.array([[b[3][0], b[3][1], b[3][2]] for b in boxes], dtype=np.int64)
+        int_step = boxes[0][4] * (boxes[0][0][0] - 1)  # boxes share their border samples
+    yield from assemble(vertices, links, starts, counts, int_corners, int_step)

@@ -30,7 +30,9 @@ typedef enum cc_status {
     CC_ERR_NOT_INITIALIZED = -2,
     CC_ERR_INVALID_PROGRAM = -3, /* malformed word stream (bad opcode / truncated)      */
     CC_ERR_INVALID_ARGUMENT = -4,
-    CC_ERR_TOO_LARGE = -5      /* program or register demand exceeds device limits      */
+    CC_ERR_TOO_LARGE = -5,     /* program or register demand exceeds device limits      */
+    CC_ERR_OPEN_OUTLINE = -6   /* polygon(): an outline leaves the subdivided region (the
+                                  reference's final assertion, rendering/polygon2d.py:172-173) */
 } cc_status;
 
 typedef struct cc_program cc_program; /* decoded node program resident on the device */
@@ -237,6 +239,19 @@ int cc_process_polygon(const float box_corner[2], float box_step, uint32_t cells
 int cc_polygon_blocks(const cc_program *prog, const double *corners, double resolution, uint32_t gx, uint32_t gy,
                       uint32_t n_blocks, float *h_vertices, uint32_t *h_links, uint32_t *h_starts,
                       uint32_t *h_start_counts);
+
+/* Host half of polygon() (no device work, usable without cc_init): follows the links that
+ * process_polygon wrote for n_blocks boxes (arrays as returned by cc_polygon_blocks; `links` is
+ * overwritten with visit marks) into closed outlines — rendering/polygon2d.py:15-31 and :119-170.
+ * Chains closed inside a box come out in increasing order of their first triangle; chains that cross
+ * box borders are joined through the (box corner, side + row) keys of polygon2d.py:131,141-144, with
+ * int_corners [n][3] and int_step = int_resolution * (box_size - 1).  Results: malloc'ed
+ * out_vertices float[total][2] and out_offsets uint64[chains + 1] (release with cc_free).
+ * CC_ERR_OPEN_OUTLINE if a chain never closes. */
+int cc_polygon_assemble(const float *vertices, uint32_t *links, const uint32_t *starts,
+                        const uint32_t *start_counts, const int64_t *int_corners, int64_t int_step,
+                        uint32_t cells, uint32_t max_starts, uint32_t n_blocks, float **out_vertices,
+                        uint64_t **out_offsets, uint64_t *out_chains);
 
 /* ---- mesh export: replaces the per-block loop of rendering/mesh.py:36-74
  * (grid_eval_pymcubes launch + blocking device->host copy + mcubes.marching_cubes on the CPU).

@@ -126,3 +126,30 @@ def test_product_host_logic_on_oracle_data(scenes, name, grid, monkeypatch):
     assert canonical(got) == canonical(want)
     if grid == 128:
         assert [[tuple(v) for v in c] for c in got] == [[tuple(v) for v in c] for c in want]
+
+
+def test_open_outline_raises_like_the_reference():
+    """A surface that leaves the only box: the reference ends on `assert len(open_chain_beginnings) == 0`
+    (polygon2d.py:172-173); the native assembly reports CC_ERR_OPEN_OUTLINE -> AssertionError."""
+    from codecad_b200.rendering import polygon2d
+    gx = gy = 4
+    xs = np.arange(gx, dtype=np.float32)
+    field = np.zeros((gx, gy, 4), np.float32)
+    field[..., 0] = 1.0
+    field[..., 3] = (xs - 1.5)[:, None]
+    vertices, links, starts = oracle.process_polygon((0.0, 0.0), 1.0, field)
+    st = np.zeros((1, gx + gy - 2), np.uint32)
+    st[0, :len(starts)] = starts
+    with pytest.raises(AssertionError):
+        polygon2d.assemble(vertices[None], links[None].copy(), st, np.array([len(starts)], np.uint32), [[0, 0, 0]], 3)
+    # a closed square inside one box assembles without a device
+    d = np.maximum(np.abs(xs[:, None] - 1.5), np.abs(xs[None, :] - 1.5)) - 1.0
+    field2 = np.zeros((gx, gy, 4), np.float32)
+    field2[..., 3] = d
+    field2[..., 0] = np.where(np.abs(xs[:, None] - 1.5) >= np.abs(xs[None, :] - 1.5), np.sign(xs[:, None] - 1.5), 0)
+    field2[..., 1] = np.where(np.abs(xs[:, None] - 1.5) < np.abs(xs[None, :] - 1.5), np.sign(xs[None, :] - 1.5), 0)
+    v2, l2, s2 = oracle.process_polygon((0.0, 0.0), 1.0, field2)
+    assert len(s2) == 0
+    chains = polygon2d.assemble(v2[None], l2[None].copy(), np.zeros((1, 6), np.uint32), np.zeros(1, np.uint32), [[0, 0, 0]], 3)
+    assert len(chains) == 1 and len(chains[0]) >= 4
+    assert abs(signed_area(chains[0])) == pytest.approx(4.0, rel=0.2)
