@@ -1419,7 +1419,7 @@ int cc_mesh_blocks(const cc_program *prog, const double *corners, double resolut
         uint32_t n_tri = 0;
     };
     std::vector<std::unique_ptr<ChunkOut>> results;  // triangles stay on the device until the end
-    DevBuf field, descs, d_corner, counter;
+    DevBuf field, descs, d_corner, counter, tile_offsets;
     int rc;
     if ((rc = counter.reserve(4))) return rc;
     // blocks per chunk: keep the field buffer around 1 GiB
@@ -1457,25 +1457,21 @@ int cc_mesh_blocks(const cc_program *prog, const double *corners, double resolut
         m.resolution = resolution;
         m.counter = counter.as<uint32_t>();
         m.first_block = b0;
-        CU(cudaMemsetAsync(counter.p, 0, 4, g.compute));
-        int e = cc_launch_mesh(m, false, g.compute);
+        const uint64_t tiles = (uint64_t)m.tiles_per_block * nb;
+        if (tiles >= (1ull << 31)) return fail(CC_ERR_INVALID_ARGUMENT, "too many tiles in one launch");
+        if ((rc = tile_offsets.reserve(((size_t)tiles + tiles / 4096 + 1) * 4))) return rc;
+        m.tile_offsets = tile_offsets.as<uint32_t>();
+        int e = cc_launch_mesh(m, false, g.compute);  // count per tile + exclusive scan + total
         if (e) return cuda_fail((cudaError_t)e, "marching cubes (count)");
-        g.launches += 1;
+        g.launches += 4;
         uint32_t n_tri = 0;
         if ((rc = read_counter(counter.as<uint32_t>(), &n_tri))) return rc;
         if (n_tri == 0) continue;
-        const uint64_t tiles = (uint64_t)m.tiles_per_block * nb;
-        if ((rc = ensure_status((size_t)tiles))) return rc;
         results.emplace_back(new ChunkOut);
         ChunkOut &co = *results.back();
         co.n_tri = n_tri;
         if ((rc = co.vertices.reserve((size_t)n_tri * 9 * sizeof(double)))) return rc;
         if ((rc = co.tri_block.reserve((size_t)n_tri * 4))) return rc;
-        CU(cudaMemsetAsync(g.d_ticket, 0, 4, g.compute));
-        CU(cudaMemsetAsync(g.d_status, 0, (size_t)tiles * sizeof(unsigned long long), g.compute));
-        CU(cudaMemsetAsync(counter.p, 0, 4, g.compute));
-        m.ticket = g.d_ticket;
-        m.tile_status = g.d_status;
         m.vertices = co.vertices.as<double>();
         m.tri_block = co.tri_block.as<uint32_t>();
         e = cc_launch_mesh(m, true, g.compute);

@@ -141,12 +141,11 @@ struct cc_mesh_args {
     uint32_t tiles_per_block;
     const double *corner;  // [n_blocks][3] box_corner (float64)
     double resolution;     // box_resolution (float64)
-    uint32_t *counter;     // running number of triangles
+    uint32_t *counter;     // total number of triangles (written by the scan after the count pass)
     double *vertices;      // [n_triangles][3 vertices][3]  (emit pass)
     uint32_t *tri_block;   // [n_triangles] block of every triangle (emit pass)
     uint32_t first_block;  // added to the block index written to tri_block
-    uint32_t *ticket;
-    unsigned long long *tile_status;
+    uint32_t *tile_offsets; // [tiles + ceil(tiles / 4096)]: triangle counts (count pass) -> exclusive offsets; scan partials
 };
 
 int cc_mesh_upload_tables(void *stream);

@@ -16,7 +16,6 @@
 #include <stdint.h>
 
 #include "cc_internal.h"
-#include "cc_scan.cuh"
 #include "cc_mc_table.h"
 
 __constant__ unsigned char c_mc_count[256];
@@ -47,18 +46,17 @@ __device__ __forceinline__ uint32_t cc_mesh_case(const cc_mesh_args &a, const fl
     return c;
 }
 
+// Two passes share this kernel.  COUNT writes every tile's number of triangles to tile_offsets[tile];
+// cc_mesh_scan_kernel turns them into exclusive offsets (+ the total in *counter); EMIT reads its base
+// from there.  (The first version ordered the tiles with a ticket and a decoupled look-back inside the
+// emit pass: with 896 k tiles of which 95 % are empty, every CTA sat ~7 us at the barrier behind its
+// look-back warp — 11.6 ms for csg_example at 512^3, stall_barrier 30 per issue; profiles/r1_mesh.md.)
 template <bool EMIT>
 __global__ void __launch_bounds__(CC_MESH_THREADS) cc_mesh_kernel(const cc_mesh_args a)
 {
-    __shared__ uint32_t s_tile, s_base;
     __shared__ uint32_t s_warp[CC_MESH_THREADS / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint32_t tile = blockIdx.x;
-    if (EMIT) {  // ticket order: look-back never waits on a tile that is not running yet
-        if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
-        __syncthreads();
-        tile = s_tile;
-    }
+    const uint32_t tile = blockIdx.x;
     const uint32_t block = tile / a.tiles_per_block;
     const uint32_t tile_in_block = tile - block * a.tiles_per_block;
     const uint32_t c0 = a.d0 - 1, c1 = a.d1 - 1, c2 = a.d2 - 1;
@@ -95,20 +93,12 @@ __global__ void __launch_bounds__(CC_MESH_THREADS) cc_mesh_kernel(const cc_mesh_
         }
         const uint32_t total = __shfl_sync(0xffffffffu, wi, 31);
         if (lane < CC_MESH_THREADS / 32) s_warp[lane] = wi - w;
-        if (EMIT) {
-            const uint32_t base = cc_lookback(a.tile_status, tile, total, a.counter);
-            if (lane == 0) {
-                s_base = base;
-                if (tile == gridDim.x - 1) *a.counter = base + total;
-            }
-        } else if (lane == 0 && total) {
-            atomicAdd(a.counter, total);
-        }
+        if (!EMIT && lane == 0) a.tile_offsets[tile] = total;
     }
     if (!EMIT) return;
     __syncthreads();
     if (n == 0) return;
-    uint32_t pos = s_base + s_warp[warp] + (incl - n);
+    uint32_t pos = a.tile_offsets[tile] + s_warp[warp] + (incl - n);
     const double cx = a.corner[3 * (size_t)block + 0], cy = a.corner[3 * (size_t)block + 1], cz = a.corner[3 * (size_t)block + 2];
     const double base_idx[3] = {(double)i, (double)j, (double)k};
     for (uint32_t t = 0; t < n; ++t, ++pos) {
@@ -147,6 +137,82 @@ __global__ void __launch_bounds__(CC_MESH_THREADS) cc_mesh_kernel(const cc_mesh_
     }
 }
 
+// In-place exclusive scan of the n tile counts (n ~ 10^6), three small launches:
+//   cc_scan_local_kernel  4096 elements per CTA: exclusive scan inside the CTA, CTA total -> part[cta]
+//   cc_scan_parts_kernel  one CTA: exclusive scan of part[] (chunk per thread), grand total -> *counter
+//   cc_scan_add_kernel    adds part[cta] to the CTA's elements
+#define CC_SCAN_PER_CTA 4096u
+__global__ void __launch_bounds__(1024) cc_scan_local_kernel(uint32_t *__restrict__ v, uint32_t n, uint32_t *__restrict__ part)
+{
+    __shared__ uint32_t s_warp[32];
+    const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const uint32_t i0 = blockIdx.x * CC_SCAN_PER_CTA + 4u * t;
+    uint32_t x[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) x[k] = (i0 + k < n) ? v[i0 + k] : 0u;
+    const uint32_t mine = x[0] + x[1] + x[2] + x[3];
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += up;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t w = s_warp[lane];
+        uint32_t wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += up;
+        }
+        s_warp[lane] = wi - w;
+        if (lane == 31) part[blockIdx.x] = wi;
+    }
+    __syncthreads();
+    uint32_t run = s_warp[warp] + (incl - mine);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (i0 + k < n) v[i0 + k] = run;
+        run += x[k];
+    }
+}
+
+__global__ void __launch_bounds__(1024) cc_scan_parts_kernel(uint32_t *__restrict__ v, uint32_t n, uint32_t *__restrict__ counter)
+{
+    __shared__ uint32_t s_part[1024];
+    const uint32_t t = threadIdx.x;
+    const uint32_t per = (n + 1023u) / 1024u;
+    const uint32_t lo = min(n, t * per), hi = min(n, lo + per);
+    uint32_t sum = 0;
+    for (uint32_t i = lo; i < hi; ++i) sum += v[i];
+    s_part[t] = sum;
+    __syncthreads();
+    for (uint32_t d = 1; d < 1024u; d <<= 1) {  // Hillis-Steele inclusive scan of the 1024 partial sums
+        const uint32_t add = t >= d ? s_part[t - d] : 0u;
+        __syncthreads();
+        s_part[t] += add;
+        __syncthreads();
+    }
+    uint32_t run = s_part[t] - sum;
+    for (uint32_t i = lo; i < hi; ++i) {
+        const uint32_t c = v[i];
+        v[i] = run;
+        run += c;
+    }
+    if (t == 1023u) *counter = s_part[1023];
+}
+
+__global__ void __launch_bounds__(1024) cc_scan_add_kernel(uint32_t *__restrict__ v, uint32_t n, const uint32_t *__restrict__ part)
+{
+    const uint32_t base = part[blockIdx.x];
+    const uint32_t i0 = blockIdx.x * CC_SCAN_PER_CTA + 4u * threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (i0 + k < n) v[i0 + k] += base;
+}
+
 // ---- host side ------------------------------------------------------------------------------------
 
 int cc_mesh_upload_tables(void *stream)
@@ -171,7 +237,16 @@ int cc_launch_mesh(const cc_mesh_args &a, bool emit, void *stream)
 {
     const uint32_t grid = a.n_blocks * a.tiles_per_block;
     if (grid == 0) return 0;
-    if (emit) cc_mesh_kernel<true><<<grid, CC_MESH_THREADS, 0, (cudaStream_t)stream>>>(a);
-    else cc_mesh_kernel<false><<<grid, CC_MESH_THREADS, 0, (cudaStream_t)stream>>>(a);
+    if (emit) {
+        cc_mesh_kernel<true><<<grid, CC_MESH_THREADS, 0, (cudaStream_t)stream>>>(a);
+    } else {
+        cc_mesh_kernel<false><<<grid, CC_MESH_THREADS, 0, (cudaStream_t)stream>>>(a);
+        // exclusive offsets per tile + total; the CTA partials live right behind the tile counts
+        const uint32_t ctas = (grid + CC_SCAN_PER_CTA - 1) / CC_SCAN_PER_CTA;
+        uint32_t *part = a.tile_offsets + grid;
+        cc_scan_local_kernel<<<ctas, 1024, 0, (cudaStream_t)stream>>>(a.tile_offsets, grid, part);
+        cc_scan_parts_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(part, ctas, a.counter);
+        cc_scan_add_kernel<<<ctas, 1024, 0, (cudaStream_t)stream>>>(a.tile_offsets, grid, part);
+    }
     return (int)cudaGetLastError();
 }

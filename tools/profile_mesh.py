@@ -1,0 +1,23 @@
+#!/usr/bin/env python3
+"""mesh_arrays of csg_example at 512^3 effective resolution, 128^3 blocks, a few times (for ncu)."""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from codecad_b200 import CompiledScene, _lib  # noqa: E402
+from codecad_b200.cl_util.buffer import ProgramBuffer  # noqa: E402
+from codecad_b200.rendering import mesh_arrays  # noqa: E402
+from scenes import load_scenes  # noqa: E402
+
+_lib.init(0)
+c = load_scenes()["cfg_csg_example"]
+scene = CompiledScene(c.words, 3, c.box_a, c.box_b, 2 * 100.0 / 512, "csg_example@512")
+mesh_arrays(scene, 128)
+scene.program_buffer().wait_specialized(ProgramBuffer.SINK_PYMCUBES | ProgramBuffer.SINK_CLASSIFY)
+for _ in range(3):
+    t0 = time.perf_counter()
+    vertices, block, boxes = mesh_arrays(scene, 128)
+    print("mesh_arrays %.3f ms, %d triangles, %d blocks" % ((time.perf_counter() - t0) * 1e3, len(vertices), len(boxes)))
