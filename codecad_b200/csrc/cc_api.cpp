@@ -571,10 +571,14 @@ int cc_specialize_source(const float *words, uint32_t n_words, int points_per_th
 
 // ---- buffers / events ---------------------------------------------------------------------------------
 
+// Stream-ordered allocations from the device's default pool on the compute stream (every kernel
+// and copy that touches a caller's buffer is issued on that stream; cc_init keeps the pool warm):
+// a cl_util.Buffer costs microseconds instead of a cudaMalloc + a device-wide cudaFree.
 int cc_buffer_alloc(size_t bytes, void **dptr)
 {
     NEED_INIT();
-    CU(cudaMalloc(dptr, bytes ? bytes : 1));
+    if (!dptr) return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
+    CU(cudaMallocAsync(dptr, bytes ? bytes : 1, g.compute));
     return CC_OK;
 }
 
@@ -582,9 +586,8 @@ int cc_buffer_free(void *dptr)
 {
     NEED_INIT();
     if (!dptr) return CC_OK;
-    CU(cudaStreamSynchronize(g.compute));
-    CU(cudaStreamSynchronize(g.copy));
-    CU(cudaFree(dptr));
+    CU(cudaStreamSynchronize(g.copy));  // the slab pipeline may still be reading from it
+    CU(cudaFreeAsync(dptr, g.compute));
     return CC_OK;
 }
 

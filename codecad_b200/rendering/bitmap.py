@@ -6,6 +6,7 @@ import ctypes
 import numpy as np
 
 from .. import _lib
+from ..cl_util.buffer import _Pinned
 from ..geometry import Vector
 from ..nodes import make_program_buffer
 
@@ -23,7 +24,7 @@ def render(obj, size):
 
     program = make_program_buffer(obj)
     w, h = int(size[0]), int(size[1])
-    out = np.empty((w, h, 3), np.uint8)
+    out = _Pinned(w * h * 3).array(np.uint8, (w, h, 3))  # pooled page-locked memory: the copy-out runs at PCIe speed
     L = _lib.lib()
     d_out = ctypes.c_void_p()
     _lib.check(L.cc_buffer_alloc(out.nbytes, ctypes.byref(d_out)))
