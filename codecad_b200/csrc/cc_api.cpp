@@ -1424,7 +1424,7 @@ int cc_mesh_blocks(const cc_program *prog, const double *corners, double resolut
     std::vector<std::unique_ptr<ChunkOut>> results;  // triangles stay on the device until the end
     DevBuf field, descs, d_corner, counter, tile_offsets;
     int rc;
-    if ((rc = counter.reserve(4))) return rc;
+    if ((rc = counter.reserve(8))) return rc;
     // blocks per chunk: keep the field buffer around 1 GiB
     const uint32_t chunk = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_blocks, (1ull << 28) / cells));
     std::vector<cc_block_desc> h_desc(chunk);
@@ -1462,13 +1462,20 @@ int cc_mesh_blocks(const cc_program *prog, const double *corners, double resolut
         m.first_block = b0;
         const uint64_t tiles = (uint64_t)m.tiles_per_block * nb;
         if (tiles >= (1ull << 31)) return fail(CC_ERR_INVALID_ARGUMENT, "too many tiles in one launch");
-        if ((rc = tile_offsets.reserve(((size_t)tiles + tiles / 4096 + 1) * 4))) return rc;
+        if ((rc = tile_offsets.reserve(cc_mesh_scratch_words((uint32_t)tiles) * 4))) return rc;
         m.tile_offsets = tile_offsets.as<uint32_t>();
-        int e = cc_launch_mesh(m, false, g.compute);  // count per tile + exclusive scan + total
+        m.tile_list = m.tile_offsets + (cc_mesh_scratch_words((uint32_t)tiles) - tiles);
+        int e = cc_launch_mesh(m, false, 0, g.compute);  // count per tile + scan + list of non-empty tiles
         if (e) return cuda_fail((cudaError_t)e, "marching cubes (count)");
         g.launches += 4;
-        uint32_t n_tri = 0;
-        if ((rc = read_counter(counter.as<uint32_t>(), &n_tri))) return rc;
+        uint32_t n_tri = 0, n_tiles = 0;
+        {
+            uint32_t h2[2] = {0, 0};
+            CU(cudaMemcpyAsync(h2, counter.p, 8, cudaMemcpyDeviceToHost, g.compute));
+            CU(cudaStreamSynchronize(g.compute));
+            n_tri = h2[0];
+            n_tiles = h2[1];
+        }
         if (n_tri == 0) continue;
         results.emplace_back(new ChunkOut);
         ChunkOut &co = *results.back();
@@ -1477,7 +1484,7 @@ int cc_mesh_blocks(const cc_program *prog, const double *corners, double resolut
         if ((rc = co.tri_block.reserve((size_t)n_tri * 4))) return rc;
         m.vertices = co.vertices.as<double>();
         m.tri_block = co.tri_block.as<uint32_t>();
-        e = cc_launch_mesh(m, true, g.compute);
+        e = cc_launch_mesh(m, true, n_tiles, g.compute);
         if (e) return cuda_fail((cudaError_t)e, "marching cubes (emit)");
         g.launches += 1;
     }

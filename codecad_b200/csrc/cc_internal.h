@@ -141,15 +141,17 @@ struct cc_mesh_args {
     uint32_t tiles_per_block;
     const double *corner;  // [n_blocks][3] box_corner (float64)
     double resolution;     // box_resolution (float64)
-    uint32_t *counter;     // total number of triangles (written by the scan after the count pass)
+    uint32_t *counter;     // [2]: total triangles, non-empty tiles (written by the scan after the count pass)
     double *vertices;      // [n_triangles][3 vertices][3]  (emit pass)
     uint32_t *tri_block;   // [n_triangles] block of every triangle (emit pass)
     uint32_t first_block;  // added to the block index written to tri_block
-    uint32_t *tile_offsets; // [tiles + ceil(tiles / 4096)]: triangle counts (count pass) -> exclusive offsets; scan partials
+    uint32_t *tile_offsets; // cc_mesh_scratch_words(tiles) words: triangle counts (count pass) -> exclusive offsets; scan scratch
+    uint32_t *tile_list;    // ids of the tiles that hold triangles, increasing (inside the same scratch)
 };
 
 int cc_mesh_upload_tables(void *stream);
 uint32_t cc_mesh_tiles_per_block(uint32_t d0, uint32_t d1, uint32_t d2);
-int cc_launch_mesh(const cc_mesh_args &a, bool emit, void *stream);
+int cc_launch_mesh(const cc_mesh_args &a, bool emit, uint32_t emit_tiles, void *stream);
+size_t cc_mesh_scratch_words(uint32_t tiles);
 
 #endif
