@@ -1417,107 +1417,146 @@ int cc_mesh_blocks(const cc_program *prog, const double *corners, double resolut
         if (e) return cuda_fail((cudaError_t)e, "marching-cubes tables");
         tables_uploaded = true;
     }
-    struct ChunkOut {
-        DevBuf vertices, tri_block;
-        uint32_t n_tri = 0;
+    // Phase A per chunk of blocks: evaluate the field, count triangles per tile, scan.  Phase B per
+    // chunk: emit the triangles.  When every chunk's field fits the budget at once (the usual
+    // case), all of phase A runs first, the page-locked result is sized from the totals, and each
+    // chunk's triangles start crossing PCIe on the copy stream as soon as its emit pass is done,
+    // while the next chunk emits.  Larger meshes keep one field buffer, run A + B chunk by chunk
+    // and copy at the end.
+    struct Chunk {
+        uint32_t b0 = 0, nb = 0, n_tri = 0, n_tiles = 0;
+        DevBuf field, descs, corner, scratch, vertices, tri_block;
+        cc_mesh_args m;
     };
-    std::vector<std::unique_ptr<ChunkOut>> results;  // triangles stay on the device until the end
-    DevBuf field, descs, d_corner, counter, tile_offsets;
+    // (both sizes can be overridden for tests: CODECAD_B200_MESH_FIELD_BUDGET / _MESH_CHUNK_BYTES)
+    uint64_t field_budget = 4ull << 30;
+    if (const char *t = getenv("CODECAD_B200_MESH_FIELD_BUDGET")) field_budget = strtoull(t, nullptr, 10);
+    const bool resident = (uint64_t)n_blocks * cells * 4 <= field_budget;
+    // blocks per chunk: ~256 MiB of field when the copies are pipelined (several chunks to overlap),
+    // ~1 GiB otherwise
+    uint64_t chunk_bytes = resident ? (1ull << 28) : (1ull << 30);
+    if (const char *t = getenv("CODECAD_B200_MESH_CHUNK_BYTES")) chunk_bytes = std::max<uint64_t>(1, strtoull(t, nullptr, 10));
+    const uint32_t chunk = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_blocks, chunk_bytes / (cells * 4)));
+    std::vector<std::unique_ptr<Chunk>> chunks;
+    DevBuf counter, shared_field;
     int rc;
     if ((rc = counter.reserve(8))) return rc;
-    // blocks per chunk: keep the field buffer around 1 GiB
-    const uint32_t chunk = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_blocks, (1ull << 28) / cells));
+    if (!resident && (rc = shared_field.reserve((size_t)chunk * cells * 4))) return rc;
     std::vector<cc_block_desc> h_desc(chunk);
     const float step = (float)resolution;  // numpy.float32(box_resolution), rendering/mesh.py:58
-    for (uint32_t b0 = 0; b0 < n_blocks; b0 += chunk) {
-        const uint32_t nb = std::min(chunk, n_blocks - b0);
-        if ((rc = field.reserve((size_t)nb * cells * 4))) return rc;
-        if ((rc = descs.reserve((size_t)nb * sizeof(cc_block_desc)))) return rc;
-        if ((rc = d_corner.reserve((size_t)nb * 3 * sizeof(double)))) return rc;
+
+    auto phase_a = [&](Chunk &c) -> int {
+        int rc2;
+        const uint32_t nb = c.nb;
+        if (resident && (rc2 = c.field.reserve((size_t)nb * cells * 4))) return rc2;
+        if ((rc2 = c.descs.reserve((size_t)nb * sizeof(cc_block_desc)))) return rc2;
+        if ((rc2 = c.corner.reserve((size_t)nb * 3 * sizeof(double)))) return rc2;
         for (uint32_t b = 0; b < nb; ++b) {  // Vector.as_float4(): float64 -> float32 per block
-            const double *c = corners + 3 * (size_t)(b0 + b);
-            h_desc[b] = cc_block_desc{(float)c[0], (float)c[1], (float)c[2], 0u};
+            const double *p = corners + 3 * (size_t)(c.b0 + b);
+            h_desc[b] = cc_block_desc{(float)p[0], (float)p[1], (float)p[2], 0u};
         }
-        CU(cudaMemcpyAsync(descs.p, h_desc.data(), (size_t)nb * sizeof(cc_block_desc), cudaMemcpyHostToDevice, g.compute));
-        CU(cudaMemcpyAsync(d_corner.p, corners + 3 * (size_t)b0, (size_t)nb * 3 * sizeof(double), cudaMemcpyHostToDevice,
+        CU(cudaMemcpyAsync(c.descs.p, h_desc.data(), (size_t)nb * sizeof(cc_block_desc), cudaMemcpyHostToDevice, g.compute));
+        CU(cudaMemcpyAsync(c.corner.p, corners + 3 * (size_t)c.b0, (size_t)nb * 3 * sizeof(double), cudaMemcpyHostToDevice,
                            g.compute));
-        CU(cudaStreamSynchronize(g.compute));  // h_desc is reused by the next chunk
+        void *field = resident ? c.field.p : shared_field.p;
         cc_eval_args a;
         fill_common(&a, prog);
         a.step = step;
         a.nx = nx; a.ny = ny; a.nz = nz; a.n_blocks = nb;
-        a.blocks = descs.as<cc_block_desc>();
-        a.out = field.p;
-        if ((rc = launch(CC_SINK_PYMCUBES, prog, a, (uint64_t)nb * cells))) return rc;
+        a.blocks = c.descs.as<cc_block_desc>();
+        a.out = field;
+        if ((rc2 = launch(CC_SINK_PYMCUBES, prog, a, (uint64_t)nb * cells))) return rc2;
 
-        cc_mesh_args m;
+        cc_mesh_args &m = c.m;
         std::memset(&m, 0, sizeof(m));
-        m.field = field.as<float>();
+        m.field = (const float *)field;
         m.d0 = nx; m.d1 = ny; m.d2 = nz;  // numpy.empty(max_box_size): the array shape mcubes sees
         m.n_blocks = nb;
         m.tiles_per_block = cc_mesh_tiles_per_block(nx, ny, nz);
-        m.corner = d_corner.as<double>();
+        m.corner = c.corner.as<double>();
         m.resolution = resolution;
         m.counter = counter.as<uint32_t>();
-        m.first_block = b0;
+        m.first_block = c.b0;
         const uint64_t tiles = (uint64_t)m.tiles_per_block * nb;
         if (tiles >= (1ull << 31)) return fail(CC_ERR_INVALID_ARGUMENT, "too many tiles in one launch");
-        if ((rc = tile_offsets.reserve(cc_mesh_scratch_words((uint32_t)tiles) * 4))) return rc;
-        m.tile_offsets = tile_offsets.as<uint32_t>();
-        m.tile_list = m.tile_offsets + (cc_mesh_scratch_words((uint32_t)tiles) - tiles);
+        const size_t words = cc_mesh_scratch_words((uint32_t)tiles);
+        if ((rc2 = c.scratch.reserve(words * 4))) return rc2;
+        m.tile_offsets = c.scratch.as<uint32_t>();
+        m.tile_list = m.tile_offsets + (words - tiles);
         int e = cc_launch_mesh(m, false, 0, g.compute);  // count per tile + scan + list of non-empty tiles
         if (e) return cuda_fail((cudaError_t)e, "marching cubes (count)");
         g.launches += 4;
-        uint32_t n_tri = 0, n_tiles = 0;
-        {
-            uint32_t h2[2] = {0, 0};
-            CU(cudaMemcpyAsync(h2, counter.p, 8, cudaMemcpyDeviceToHost, g.compute));
-            CU(cudaStreamSynchronize(g.compute));
-            n_tri = h2[0];
-            n_tiles = h2[1];
-        }
-        if (n_tri == 0) continue;
-        results.emplace_back(new ChunkOut);
-        ChunkOut &co = *results.back();
-        co.n_tri = n_tri;
-        if ((rc = co.vertices.reserve((size_t)n_tri * 9 * sizeof(double)))) return rc;
-        if ((rc = co.tri_block.reserve((size_t)n_tri * 4))) return rc;
-        m.vertices = co.vertices.as<double>();
-        m.tri_block = co.tri_block.as<uint32_t>();
-        e = cc_launch_mesh(m, true, n_tiles, g.compute);
+        uint32_t h2[2] = {0, 0};
+        CU(cudaMemcpyAsync(h2, counter.p, 8, cudaMemcpyDeviceToHost, g.compute));
+        CU(cudaStreamSynchronize(g.compute));  // also: h_desc is reused by the next chunk
+        c.n_tri = h2[0];
+        c.n_tiles = h2[1];
+        return CC_OK;
+    };
+    auto phase_b = [&](Chunk &c) -> int {
+        if (c.n_tri == 0) return CC_OK;
+        int rc2;
+        if ((rc2 = c.vertices.reserve((size_t)c.n_tri * 9 * sizeof(double)))) return rc2;
+        if ((rc2 = c.tri_block.reserve((size_t)c.n_tri * 4))) return rc2;
+        c.m.vertices = c.vertices.as<double>();
+        c.m.tri_block = c.tri_block.as<uint32_t>();
+        int e = cc_launch_mesh(c.m, true, c.n_tiles, g.compute);
         if (e) return cuda_fail((cudaError_t)e, "marching cubes (emit)");
         g.launches += 1;
+        return CC_OK;
+    };
+
+    for (uint32_t b0 = 0; b0 < n_blocks; b0 += chunk) {
+        chunks.emplace_back(new Chunk);
+        Chunk &c = *chunks.back();
+        c.b0 = b0;
+        c.nb = std::min(chunk, n_blocks - b0);
+        if ((rc = phase_a(c))) return rc;
+        if (!resident && (rc = phase_b(c))) return rc;  // the shared field is overwritten by the next chunk
     }
     size_t n = 0;
-    for (auto &r : results) n += r->n_tri;
+    for (auto &c : chunks) n += c->n_tri;
     *out_triangles = n;
-    if (n) {
-        double *v = (double *)g_pinned.get(n * 9 * sizeof(double));  // page-locked: the copy runs at PCIe speed
-        uint32_t *b = (uint32_t *)g_pinned.get(n * sizeof(uint32_t));
-        if (!v || !b) {
-            cc_free(v);
-            cc_free(b);
-            return fail(CC_ERR_INVALID_ARGUMENT, "out of host memory");
-        }
-        size_t at = 0;
-        cudaError_t ce = cudaSuccess;
-        for (auto &r : results) {  // one copy, straight into the caller's buffers
-            if (ce == cudaSuccess)
-                ce = cudaMemcpyAsync(v + at * 9, r->vertices.p, (size_t)r->n_tri * 9 * sizeof(double), cudaMemcpyDeviceToHost,
-                                     g.compute);
-            if (ce == cudaSuccess)
-                ce = cudaMemcpyAsync(b + at, r->tri_block.p, (size_t)r->n_tri * 4, cudaMemcpyDeviceToHost, g.compute);
-            at += r->n_tri;
-        }
-        if (ce == cudaSuccess) ce = cudaStreamSynchronize(g.compute);
-        if (ce != cudaSuccess) {
-            cc_free(v);
-            cc_free(b);
-            return cuda_fail(ce, "triangles D2H");
-        }
-        *out_vertices = v;
-        *out_triangle_block = b;
+    if (n == 0) return CC_OK;
+    double *v = (double *)g_pinned.get(n * 9 * sizeof(double));  // page-locked: the copy runs at PCIe speed
+    uint32_t *b = (uint32_t *)g_pinned.get(n * sizeof(uint32_t));
+    if (!v || !b) {
+        cc_free(v);
+        cc_free(b);
+        return fail(CC_ERR_INVALID_ARGUMENT, "out of host memory");
     }
+    size_t at = 0;
+    cudaError_t ce = cudaSuccess;
+    rc = CC_OK;
+    cudaEvent_t emitted = nullptr;
+    if (resident) ce = cudaEventCreateWithFlags(&emitted, cudaEventDisableTiming);
+    for (auto &cp : chunks) {
+        Chunk &c = *cp;
+        if (c.n_tri == 0) continue;
+        cudaStream_t copy_on = g.compute;
+        if (resident && ce == cudaSuccess) {
+            if ((rc = phase_b(c))) break;
+            ce = cudaEventRecord(emitted, g.compute);
+            if (ce == cudaSuccess) ce = cudaStreamWaitEvent(g.copy, emitted, 0);
+            copy_on = g.copy;  // this chunk's triangles cross PCIe while the next chunk emits
+        }
+        if (ce == cudaSuccess)
+            ce = cudaMemcpyAsync(v + at * 9, c.vertices.p, (size_t)c.n_tri * 9 * sizeof(double), cudaMemcpyDeviceToHost, copy_on);
+        if (ce == cudaSuccess)
+            ce = cudaMemcpyAsync(b + at, c.tri_block.p, (size_t)c.n_tri * 4, cudaMemcpyDeviceToHost, copy_on);
+        at += c.n_tri;
+    }
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(g.compute);
+    cudaError_t ce2 = cudaStreamSynchronize(g.copy);  // before the chunks' device buffers are released
+    if (ce == cudaSuccess) ce = ce2;
+    if (emitted) cudaEventDestroy(emitted);
+    if (rc != CC_OK || ce != cudaSuccess) {
+        cc_free(v);
+        cc_free(b);
+        return rc != CC_OK ? rc : cuda_fail(ce, "triangles D2H");
+    }
+    *out_vertices = v;
+    *out_triangle_block = b;
     return CC_OK;
 }
 

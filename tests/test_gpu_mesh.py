@@ -83,3 +83,23 @@ def test_debug_boxes_and_dimension_check(cb, scenes):
     assert len(pieces) >= 1 and all(len(v) == 8 and len(t) == 12 for v, t in pieces)
     with pytest.raises(AssertionError):
         list(triangular_mesh(scenes["sub_circle"].compiled()))
+
+
+@pytest.mark.parametrize("mode", ["pipelined chunks", "one field buffer"])
+def test_chunked_paths_give_the_same_triangles(cb, scenes, mode, monkeypatch):
+    """cc_mesh_blocks works through the blocks in chunks: with all fields resident the copy of one
+    chunk overlaps the emit pass of the next, larger meshes reuse one field buffer.  Tiny budgets
+    force both paths on a small mesh; triangles and their order must not change."""
+    from codecad_b200 import CompiledScene
+    from codecad_b200.rendering import mesh_arrays
+    s = scenes["cfg_csg_example"]
+    scene = CompiledScene(s.words, 3, s.box_a, s.box_b, 2 * 100.0 / 128, "csg@128")
+    want_v, want_b, boxes = mesh_arrays(scene, 16)
+    assert len(boxes) > 40 and len(want_v) > 10000
+    want_v, want_b = want_v.copy(), want_b.copy()
+    block_bytes = 16 ** 3 * 4
+    monkeypatch.setenv("CODECAD_B200_MESH_CHUNK_BYTES", str(7 * block_bytes))          # 7 blocks per chunk
+    if mode == "one field buffer":
+        monkeypatch.setenv("CODECAD_B200_MESH_FIELD_BUDGET", str(20 * block_bytes))    # fewer than the mesh has
+    got_v, got_b, _ = mesh_arrays(scene, 16)
+    assert np.array_equal(got_b, want_b) and np.array_equal(got_v, want_v)
