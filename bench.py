@@ -113,6 +113,14 @@ def dist_setup(n_gpus):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # one process per GPU: keep this rank's host buffers on the NUMA node next to its GPU (N = 1
+    # keeps every core: the CPU baseline legs run there)
+    if world > 1:
+        try:
+            from codecad_b200 import _lib as _cc
+            _cc.bind_host_to_device(local)
+        except Exception:  # noqa: BLE001
+            pass
     import torch
     torch.cuda.set_device(local)
     dist = None

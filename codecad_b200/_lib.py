@@ -51,6 +51,7 @@ SIGNATURES = {
     "cc_device_count": (_I, []),
     "cc_last_error": (ctypes.c_char_p, []),
     "cc_get_device_info": (_I, [ctypes.POINTER(DeviceInfo)]),
+    "cc_device_pci_bus_id": (_I, [_I, ctypes.c_char_p, _I]),
     "cc_synchronize": (_I, []),
     "cc_get_counters": (_I, [ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
     "cc_reset_counters": (None, []),
@@ -124,6 +125,38 @@ def check(rc):
     if rc < 0:
         raise CodecadB200Error("libcodecad_b200: %s (code %d)" % (load().cc_last_error().decode(), rc))
     return rc
+
+
+def bind_host_to_device(device):
+    """Pin the calling process to the CPU cores (hence the NUMA node) next to CUDA device `device`,
+    so that page-locked host buffers allocated afterwards sit on the memory the GPU's PCIe root
+    reaches directly.  With one process per GPU and results delivered to host memory this decides
+    whether eight ranks share one socket's memory controllers.  Uses the PCI address from sysfs;
+    returns the CPU list applied, or None when the topology cannot be read (nothing is changed)."""
+    try:
+        info = DeviceInfo()
+        L = load()
+        bus = ctypes.create_string_buffer(32)
+        if not hasattr(L, "cc_device_pci_bus_id") or L.cc_device_pci_bus_id(int(device), bus, 32) != 0:
+            return None
+        path = "/sys/bus/pci/devices/%s/local_cpulist" % bus.value.decode().lower()
+        with open(path) as f:
+            text = f.read().strip()
+        cpus = set()
+        for part in text.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:  # noqa: BLE001 - an optimisation, never a failure
+        return None
 
 
 def init(device=None):

@@ -390,6 +390,14 @@ void cc_shutdown(void)
     g = Context();
 }
 
+int cc_device_pci_bus_id(int device, char *out, int capacity)
+{
+    if (!out || capacity < 13) return fail(CC_ERR_INVALID_ARGUMENT, "buffer too small for a PCI bus id");
+    cudaError_t e = cudaDeviceGetPCIBusId(out, capacity, device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetPCIBusId");
+    return CC_OK;
+}
+
 int cc_get_device_info(cc_device_info *out)
 {
     NEED_INIT();

@@ -52,6 +52,9 @@ typedef struct cc_device_info {
     size_t total_mem;
     char name[64];
 } cc_device_info;
+/* PCI address ("0000:17:00.0") of CUDA device `device`, without creating a context on it: lets
+ * the host side place its page-locked buffers on the NUMA node next to the GPU. */
+int cc_device_pci_bus_id(int device, char *out, int capacity);
 int cc_get_device_info(cc_device_info *out);
 int cc_synchronize(void);
 /* counters since cc_init / the last reset: kernels launched by this library and grid
