@@ -128,10 +128,13 @@ __global__ void __launch_bounds__(1024) cc_sort_starts_kernel(uint32_t *starts, 
     __shared__ uint32_t s[1024];
     uint32_t *mine = starts + (size_t)blockIdx.x * max_starts;
     const uint32_t n = min(counter[blockIdx.x], max_starts);
+    if (n <= 1) return;  // uniform: most boxes have no open chain at all
+    uint32_t m = 2;      // bitonic network over the next power of two only (typically 2-4 starts)
+    while (m < n) m <<= 1;
     const uint32_t i = threadIdx.x;
     s[i] = i < n ? mine[i] : 0xFFFFFFFFu;
     __syncthreads();
-    for (uint32_t k = 2; k <= 1024; k <<= 1)
+    for (uint32_t k = 2; k <= m; k <<= 1)
         for (uint32_t j = k >> 1; j > 0; j >>= 1) {
             const uint32_t p = i ^ j;
             if (p > i) {
