@@ -145,6 +145,23 @@ def max_over_ranks(torch, dist, value):
     return float(t.item())
 
 
+def min_over_ranks(torch, dist, value):
+    if dist is None:
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return float(t.item())
+
+
+def gather_over_ranks(torch, dist, value):
+    if dist is None:
+        return [value]
+    t = torch.tensor([value], dtype=torch.float64, device="cuda")
+    parts = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(parts, t)
+    return [float(p.item()) for p in parts]
+
+
 def sum_over_ranks(torch, dist, value):
     if dist is None:
         return value
@@ -194,7 +211,10 @@ def cpu_sample_run(scene, n, target_seconds, steps=1, impl="auto"):
         "value": pts / mean / 1e9, "unit": "Gpts/s", "cores": threads, "kind": kind,
         "sample": "%d x-planes (%d x %d x %d = %.3g points) of the %d^3 planetary grid per step, "
                   "%d step(s), mean %.2f s/step (best %.2f s)" % (planes, planes, n, n, pts, n, steps, mean, best),
-        "ms_per_step": mean * 1e3, "points_per_step": pts,
+        "ms_per_step": mean * 1e3, "points_per_step": pts, "sample_fraction": pts / float(n) ** 3,
+        "compile_flags": ("g++ -std=c++17 -O2 -mavx2 -mfma -ffp-contract=off -fno-fast-math -fopenmp (oracle/build_ref.py: the "
+                          "reference's own .cl sources, one work-item at a time)" if kind == "reference" else
+                          "gcc -O3 -mavx2 -mfma -ffp-contract=off -fno-fast-math -fopenmp (oracle/sdf_oracle.c)"),
     }
 
 
@@ -216,7 +236,7 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.grid, 1),
         "cpu_baseline": {"value": r["value"], "unit": "Gpts/s", "cores": r["cores"], "kind": r["kind"],
-                         "sample": r["sample"]},
+                         "sample": r["sample"], "sample_fraction": r["sample_fraction"], "compile_flags": r["compile_flags"]},
         "e2e": {"value": r["value"], "unit": "Gpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -378,6 +398,242 @@ def polygon_leg():
             "outlines_identical_to_cpu": canon(got) == canon(want)}
 
 
+def _timed_events(L, _lib, fn, steps):
+    e0, e1 = ctypes.c_void_p(), ctypes.c_void_p()
+    _lib.check(L.cc_event_record(ctypes.byref(e0)))
+    for _ in range(steps):
+        fn()
+    _lib.check(L.cc_event_record(ctypes.byref(e1)))
+    _lib.check(L.cc_event_wait(e1))
+    ms = ctypes.c_float()
+    _lib.check(L.cc_event_elapsed_ms(e0, e1, ctypes.byref(ms)))
+    L.cc_event_destroy(e0)
+    L.cc_event_destroy(e1)
+    return ms.value
+
+
+def config_grid_leg(name, label, n, slab_planes, rank, world, torch, dist, info, sm_max_mhz, hbm_peak, steps, out_buffer):
+    """Dense grid_eval of one BASELINE.json scene on an n^3 grid cut into x-slabs (one per rank):
+    kernel time by CUDA events, max over ranks; FP32 and HBM-store roofline fractions of the launch.
+    slab_planes: x-planes per rank (None = n / world)."""
+    import importlib
+    from codecad_b200 import _lib
+    from codecad_b200.cl_util.buffer import ProgramBuffer
+    from scenes import load_scenes
+    ge = importlib.import_module("codecad_b200.grid_eval")
+    L = _lib.lib()
+    scene = load_scenes()[name]
+    corner, step = scene.grid(n)
+    if slab_planes is None:
+        x0, x1 = ge.slab_range(n, rank, world)
+    else:
+        x0, x1 = rank * slab_planes, (rank + 1) * slab_planes
+    nx = x1 - x0
+    prog = ProgramBuffer(scene.words)
+    pinfo = prog.info
+    n_ready, spec_s = prog.wait_specialized(ProgramBuffer.SINK_FLOAT4)
+    c3 = _lib.f3(corner)
+    assert nx * n * n * 16 <= out_buffer.size
+
+    def step_fn():
+        _lib.check(L.cc_grid_eval(prog.handle, c3, float(step), nx, n, n, x0, 0, out_buffer.device_ptr, None))
+
+    for _ in range(2):
+        step_fn()
+    _lib.check(L.cc_synchronize())
+    barrier(torch, dist)
+    ms = max_over_ranks(torch, dist, _timed_events(L, _lib, step_fn, steps)) / steps
+    barrier(torch, dist)
+    tier = prog.tier(ProgramBuffer.SINK_FLOAT4) if hasattr(prog, "tier") else ("specialised" if n_ready else "interpreter")
+    prog.release()
+    pts_rank = float(nx) * n * n
+    pts_all = pts_rank * world
+    peak = info.sm_count * 128 * 2 * sm_max_mhz * 1e6 / 1e12
+    tflops = pts_rank * int(pinfo.flops_min) / (ms * 1e-3) / 1e12
+    gbs = pts_rank * 16 / (ms * 1e-3) / 1e9
+    return {"workload": label, "scene": name, "grid": [nx * world, n, n], "x_planes_per_rank": nx,
+            "value": pts_all / (ms * 1e-3) / 1e9, "unit": "Gpts/s", "ms_per_step": ms, "steps": steps,
+            "tier": tier, "specialize_s": spec_s, "micro_ops": int(pinfo.n_micro_ops),
+            "flop_per_point": int(pinfo.flops_min),
+            "roofline": {"fp32_tflops": tflops, "fp32_frac": tflops / peak, "hbm_gbs": gbs, "hbm_frac": gbs / hbm_peak,
+                         "bound": "fp32" if tflops / peak >= gbs / hbm_peak else "hbm"}}
+
+
+def sharded_hierarchy_legs(rank, world, torch, dist):
+    """SURVEY.md 8(e) in front of the driver: mass_properties (configs[2], airfoil, resolution 0.25,
+    64^3 blocks) and subdivision (configs[1], csg_example at 100/512 with 16^3 blocks) sharded over
+    the ranks.  The hits of the level that feeds the most expensive level are dealt round-robin; the
+    only data that crosses NVLink is the 40-int64 exact accumulator of the ten integrals (one NCCL
+    all-reduce).  Every rank then also computes the UNSHARDED result on its own GPU: the sharded
+    one must be bit-identical."""
+    import importlib
+    import codecad_b200
+    from codecad_b200.cl_util.buffer import ProgramBuffer
+    from scenes import load_scenes
+    mpm = importlib.import_module("codecad_b200.mass_properties")
+    sub = importlib.import_module("codecad_b200.subdivision")
+    S = load_scenes()
+    out = {}
+
+    # ---- mass_properties ----
+    a = S["cfg_airfoil"]
+    scene = a.compiled()
+    res, grid = 0.25, 64
+    st = {}
+    codecad_b200.mass_properties(scene, res, grid, group=True if dist else None)
+    scene.program_buffer().wait_specialized(ProgramBuffer.SINK_MASS)
+    codecad_b200.mass_properties(scene, res, grid, group=True if dist else None)
+    times = []
+    for _ in range(5):
+        barrier(torch, dist)
+        t0 = time.perf_counter()
+        got = codecad_b200.mass_properties(scene, res, grid, group=True if dist else None, stats=st)
+        times.append(max_over_ranks(torch, dist, (time.perf_counter() - t0) * 1e3))
+    # the all-reduce alone (40 int64 on the GPU, the same call the leg makes)
+    ar_us = None
+    if dist:
+        limbs = np.arange(40, dtype=np.int64)
+        mpm.allreduce_limbs(limbs)
+        barrier(torch, dist)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            mpm.allreduce_limbs(limbs)
+        ar_us = max_over_ranks(torch, dist, (time.perf_counter() - t0) / 20 * 1e6)
+    whole = codecad_b200.mass_properties(scene, res, grid)          # unsharded, this rank's GPU
+    same = (got.volume == whole.volume and tuple(got.centroid) == tuple(whole.centroid)
+            and np.array_equal(got.inertia_tensor, whole.inertia_tensor))
+    cells = gather_over_ranks(torch, dist, float(st["cells"]))
+    dealt = gather_over_ranks(torch, dist, float(st["dealt_blocks"]))
+    out["mass_properties"] = {
+        "workload": "examples/airfoil.py mass_properties(resolution=0.25, grid_size=64), sharded over %d rank(s)" % world,
+        "ms": sorted(times)[len(times) // 2], "ms_best": min(times), "nccl_allreduce_us": ar_us,
+        "allreduce_bytes": 320 if dist else 0,
+        "cells_per_rank": [int(c) for c in cells], "dealt_blocks_per_rank": [int(d) for d in dealt],
+        "imbalance_max_over_mean": max(cells) / (sum(cells) / len(cells)),
+        "volume": got.volume, "identical_to_unsharded": bool(min_over_ranks(torch, dist, 1.0 if same else 0.0) == 1.0)}
+
+    # ---- subdivision ----
+    c = S["cfg_csg_example"]
+    scene = c.compiled()
+    res, grid = 100.0 / 512, 16
+    codecad_b200.subdivision(scene, res, True, grid, rank=rank, world=world)
+    scene.program_buffer().wait_specialized(ProgramBuffer.SINK_CLASSIFY)
+    times = []
+    for _ in range(5):
+        barrier(torch, dist)
+        t0 = time.perf_counter()
+        mine = codecad_b200.subdivision(scene, res, True, grid, rank=rank, world=world)[2]
+        times.append(max_over_ranks(torch, dist, (time.perf_counter() - t0) * 1e3))
+    whole = codecad_b200.subdivision(scene, res, True, grid)[2]
+    counts = gather_over_ranks(torch, dist, float(len(mine)))
+    # union over the ranks, put back into the order one GPU lists the blocks
+    if dist:
+        cap = int(max(counts))
+        pad = np.full((cap, 3), -1, dtype=np.int64)
+        pad[:len(mine)] = mine.int_corners
+        t = torch.from_numpy(pad).cuda()
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        union = np.concatenate([p.cpu().numpy()[:int(n)] for p, n in zip(parts, counts)])
+    else:
+        union = mine.int_corners
+    from codecad_b200.geometry import BoundingBox, as_vector
+    box = BoundingBox(as_vector(c.box_a), as_vector(c.box_b)).expanded_additive(res / 2)
+    plan = sub.calculate_block_sizes(box, 3, res, grid, True)
+    merged = sub.sort_leaf_corners(union, plan)
+    same = np.array_equal(merged, whole.int_corners)
+    out["subdivision"] = {
+        "workload": "examples/csg_example.py subdivision(resolution=100/512, grid_size=16), sharded over %d rank(s)" % world,
+        "ms": sorted(times)[len(times) // 2], "ms_best": min(times), "leaf_blocks": int(len(merged)),
+        "leaf_blocks_per_rank": [int(n) for n in counts],
+        "imbalance_max_over_mean": max(counts) / max(1e-9, sum(counts) / len(counts)),
+        "identical_to_unsharded": bool(min_over_ranks(torch, dist, 1.0 if same else 0.0) == 1.0)}
+    return out
+
+
+def d2h_probe(L, _lib, device_ptr, host_array, nbytes, torch, dist):
+    """Bare cudaMemcpyAsync of the rank's result slab into its pinned host buffer, all ranks at once:
+    what the PCIe / host-memory path delivers without any kernel in the way (attributes the e2e leg)."""
+    _lib.check(L.cc_memcpy_d2h_async(host_array.ctypes.data, device_ptr, nbytes, None))
+    _lib.check(L.cc_synchronize())
+    barrier(torch, dist)
+    t0 = time.perf_counter()
+    _lib.check(L.cc_memcpy_d2h_async(host_array.ctypes.data, device_ptr, nbytes, None))
+    _lib.check(L.cc_synchronize())
+    dt = time.perf_counter() - t0
+    barrier(torch, dist)
+    return nbytes / dt / 1e9, nbytes / max_over_ranks(torch, dist, dt) / 1e9
+
+
+def single_process_leg(n_devices):
+    """One process, n GPUs (cc_init_devices): the unmodified module calls — the reference's user is a
+    single Python script — fan out inside the library.  Prints one JSON object."""
+    import importlib
+    import codecad_b200
+    from codecad_b200 import _lib
+    from codecad_b200.cl_util.buffer import ProgramBuffer, _Pinned
+    from codecad_b200.geometry import FLOAT4
+    from scenes import load_scenes
+    S = load_scenes()
+    _lib.init(0)
+    a = S["cfg_airfoil"].compiled()
+    res, grid = 0.25, 64
+    codecad_b200.mass_properties(a, res, grid)
+    a.program_buffer().wait_specialized(ProgramBuffer.SINK_MASS)
+    one = codecad_b200.mass_properties(a, res, grid)
+    t1 = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        codecad_b200.mass_properties(a, res, grid)
+        t1.append((time.perf_counter() - t0) * 1e3)
+    c = S["cfg_csg_example"].compiled()
+    one_sub = codecad_b200.subdivision(c, 100.0 / 512, True, 16)[2]
+    # dense grid into host memory: 512 x-planes of the 1024^3 planetary grid
+    p = S["cfg_planetary"]
+    corner, step = p.grid(1024)
+    planes = 256
+    pin = _Pinned(planes * 1024 * 1024 * 16)
+    host = pin.array(FLOAT4, (planes, 1024, 1024))
+    pc = p.compiled()
+    ge = importlib.import_module("codecad_b200.grid_eval")
+    ge.grid_eval(pc, corner, step, (planes, 1024, 1024), out=host)
+    pc.program_buffer().wait_specialized(ProgramBuffer.SINK_FLOAT4)
+    t0 = time.perf_counter()
+    ge.grid_eval(pc, corner, step, (planes, 1024, 1024), out=host)
+    g1 = time.perf_counter() - t0
+    check1 = host[::37, ::129, ::257].copy()
+
+    _lib.init_devices(list(range(n_devices)))
+    st = {}
+    codecad_b200.mass_properties(a, res, grid)
+    alln = codecad_b200.mass_properties(a, res, grid, stats=st)
+    tn = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        codecad_b200.mass_properties(a, res, grid)
+        tn.append((time.perf_counter() - t0) * 1e3)
+    all_sub = codecad_b200.subdivision(c, 100.0 / 512, True, 16)[2]
+    ge.grid_eval(pc, corner, step, (planes, 1024, 1024), out=host)
+    t0 = time.perf_counter()
+    ge.grid_eval(pc, corner, step, (planes, 1024, 1024), out=host)
+    gn = time.perf_counter() - t0
+    same_grid = bool(np.array_equal(host[::37, ::129, ::257], check1))
+    same_mp = (alln.volume == one.volume and tuple(alln.centroid) == tuple(one.centroid)
+               and np.array_equal(alln.inertia_tensor, one.inertia_tensor))
+    pts = planes * 1024.0 * 1024.0
+    print(json.dumps({
+        "devices": _lib.active_devices(),
+        "mass_properties": {"ms_1gpu": sorted(t1)[2], "ms": sorted(tn)[2], "identical_to_1gpu": bool(same_mp),
+                            "cells_busiest_device": st.get("cells_busiest_device"),
+                            "cells_idlest_device": st.get("cells_idlest_device")},
+        "subdivision": {"leaf_blocks": len(all_sub),
+                        "identical_to_1gpu": bool(np.array_equal(all_sub.int_corners, one_sub.int_corners))},
+        "grid_eval_to_host": {"grid": [planes, 1024, 1024], "gpts_1gpu": pts / g1 / 1e9, "gpts": pts / gn / 1e9,
+                              "identical_to_1gpu": same_grid},
+    }))
+    return 0
+
+
 def workload_config(n, world):
     return {
         "workload": "examples/planetary.py Planetary(11,60,13,41,18,53).make_assembly().shape(): "
@@ -507,11 +763,80 @@ def run_ours(args):
                "d2h_bytes_per_step": int(total_points * 16),
                "ms_per_step": dt * 1e3, "steps": e2e_steps,
                "api": "codecad_b200 cc_grid_eval_to_host: program upload + slab-pipelined kernel/D2H into pinned host memory"}
-        # spot-check the delivered result against the device-resident one
+        # the same bytes with no kernel in the way: what the PCIe / host-memory path alone delivers
+        try:
+            mine_gbs, agg_gbs = d2h_probe(L, _lib, out.device_ptr, host, my_points * 16, torch, dist)
+            e2e["d2h_probe"] = {"gbs_this_rank": mine_gbs, "gbs_all_ranks": agg_gbs * world,
+                                "e2e_gbs_all_ranks": total_points * 16 / dt / 1e9,
+                                "note": "bare cudaMemcpyAsync of every rank's slab into its pinned buffer, all ranks "
+                                        "at once, same job: e2e is bound by this path when the two agree"}
+        except Exception as exc:  # noqa: BLE001
+            e2e["d2h_probe"] = {"error": str(exc)[:200]}
         del host, pin
     except Exception as exc:  # noqa: BLE001
         e2e = {"value": None, "unit": "Gpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                "error": str(exc)[:200]}
+
+    # ---- the other BASELINE.json configs as dense grids, and the sharded hierarchy paths: every
+    #      rank takes part (slabs / shares), rank 0 reports ----
+    sm_max_all = max_over_ranks(torch, dist, float((clk or {}).get("sm_max_mhz") or info.sm_clock_khz / 1e3))
+    try:
+        hbm_peak_all = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0)
+    except Exception:  # noqa: BLE001
+        hbm_peak_all = 6650.0
+    configs = {}
+    if not args.no_configs:
+        out.release()
+        big = Buffer(FLOAT4, (256, 2048, 2048))   # 17.2 GB: the slab one GPU of eight owns at 2048^3
+        plan = [
+            ("C1_menger_256", "cfg_menger_sponge", "examples/menger_sponge.py dense grid_eval 256^3 (BASELINE configs[0])", 256, None, 20),
+            ("C2_csg_dense_1024", "cfg_csg_example", "examples/csg_example.py dense grid_eval 1024^3 (store-bandwidth probe)", 1024, None, 5),
+            ("C3_airfoil_dense_1024", "cfg_airfoil", "examples/airfoil.py dense grid_eval 1024^3", 1024, None, 2),
+            ("C5_synthetic500_2048", "cfg_synthetic500",
+             "synthetic deep-CSG scene (500 rounded boxes, smooth unions) grid_eval at 2048^3, 256 x-planes per GPU "
+             "(the slab each of 8 GPUs owns; the full 2048^3 grid at N = 8) (BASELINE configs[4])", 2048, 256, 2),
+        ]
+        for key, name, label, n_c, slab, k in plan:
+            try:
+                configs[key] = config_grid_leg(name, label, n_c, slab, rank, world, torch, dist, info, sm_max_all,
+                                               hbm_peak_all, k, big)
+            except Exception as exc:  # noqa: BLE001
+                configs[key] = {"error": str(exc)[:300]}
+        if "value" in configs.get("C5_synthetic500_2048", {}):
+            configs["C5_synthetic500_2048"]["full_2048_cubed"] = bool(world == 8)
+        big.release()
+    sharded = None
+    try:
+        sharded = sharded_hierarchy_legs(rank, world, torch, dist)
+    except Exception as exc:  # noqa: BLE001
+        sharded = {"error": str(exc)[:300]}
+
+    # ---- one process driving all N GPUs (rank 0 spawns it while the other ranks wait on the store) ----
+    single = None
+    if world > 1 and not args.no_configs:
+        store = None
+        try:
+            import torch.distributed.distributed_c10d as c10d
+            store = c10d._get_default_store()
+        except Exception:  # noqa: BLE001
+            store = None
+        _lib.check(L.cc_synchronize())
+        barrier(torch, dist)
+        if rank == 0:
+            try:
+                env = {k: v for k, v in os.environ.items()
+                       if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "OMP_NUM_THREADS")}
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--single-process-leg", str(world)],
+                                   capture_output=True, text=True, timeout=600, env=env)
+                lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+                single = json.loads(lines[-1]) if (r.returncode == 0 and lines) else {"error": (r.stderr or r.stdout)[-300:]}
+            except Exception as exc:  # noqa: BLE001
+                single = {"error": str(exc)[:300]}
+            if store is not None:
+                store.set("single_process_leg_done", "1")
+        elif store is not None:
+            store.wait(["single_process_leg_done"])
+        barrier(torch, dist)
 
     if rank != 0:
         if dist is not None:
@@ -542,6 +867,8 @@ def run_ours(args):
     roofline = {
         "bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
         "frac": achieved / peak_tflops, "traffic": traffic,
+        "traffic_source": "replayed from profiles/bench_traffic.json (one ncu --set full capture of this kernel at this "
+                          "grid size, dram__bytes_read.sum + dram__bytes_write.sum per launch); not measured in this run",
         "kernel": "cc_jit_float4 (scene-specialised, packed FFMA2 lanes)" if n_ready else "cc_eval_kernel<PTS,const,FLOAT4>",
         "flop_per_point": flops_pt,
         "peak_source": "derived: %d SMs x 128 FP32 lanes x 2 x %.0f MHz (no FP32 figure in MEASURED_PEAKS.json)"
@@ -557,7 +884,8 @@ def run_ours(args):
     cpu = None
     if world == 1 and not args.no_cpu:
         r = cpu_sample_run(scene, n, 12.0, 1, "auto")
-        cpu = {"value": r["value"], "unit": "Gpts/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+        cpu = {"value": r["value"], "unit": "Gpts/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+               "sample_fraction": r["sample_fraction"], "compile_flags": r["compile_flags"]}
 
     mass = subdiv = mesh = rays = outline = None
     if world == 1 and not args.no_cpu:
@@ -590,6 +918,7 @@ def run_ours(args):
         "gpu_launches": launches_total, "roofline": roofline, "cpu_baseline": cpu,
         "tier": tier, "specialize_s": specialize_s, "interpreter_tier": interp, "mass_properties": mass, "subdivision": subdiv, "mesh_export": mesh,
         "ray_caster": rays, "polygon2d": outline,
+        "configs": configs, "sharded": sharded, "single_process_multi_gpu": single,
         "device": info.name.decode(),
     }
     _emit(out_fd, line)
@@ -606,7 +935,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, default=1024)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config dense grids and the single-process leg")
+    ap.add_argument("--single-process-leg", type=int, default=0, help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.single_process_leg:
+        return single_process_leg(args.single_process_leg)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

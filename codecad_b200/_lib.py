@@ -47,6 +47,8 @@ _U = ctypes.c_uint32
 _F = ctypes.c_float
 SIGNATURES = {
     "cc_init": (_I, [_I]),
+    "cc_init_devices": (_I, [ctypes.POINTER(ctypes.c_int), _I]),
+    "cc_active_devices": (_I, []),
     "cc_shutdown": (None, []),
     "cc_device_count": (_I, []),
     "cc_last_error": (ctypes.c_char_p, []),
@@ -85,6 +87,12 @@ SIGNATURES = {
                           _U, _U, ctypes.POINTER(ctypes.POINTER(ctypes.c_int64)), ctypes.POINTER(ctypes.c_uint64)]),
     "cc_mass_properties": (_I, [_V, ctypes.POINTER(ctypes.c_double), ctypes.c_double, ctypes.POINTER(Level), _U,
                                 _U, _U, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]),
+    "cc_mass_properties_exact": (_I, [_V, ctypes.POINTER(ctypes.c_double), ctypes.c_double, ctypes.POINTER(Level), _U,
+                                      _U, _U, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int32),
+                                      ctypes.POINTER(ctypes.c_uint64)]),
+    "cc_mass_limbs_to_integrals": (_I, [ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int32),
+                                        ctypes.POINTER(ctypes.c_double)]),
+    "cc_sort_leaf_corners": (_I, [ctypes.POINTER(ctypes.c_int64), ctypes.c_uint64, ctypes.POINTER(Level), _U]),
     "cc_evaluate_points": (_I, [_V, _V, ctypes.c_uint64, _V, c_void_pp]),
     "cc_ray_caster": (_I, [_V, c_float_p, c_float_p, c_float_p, c_float_p, _F, _F, _F, _F, _F, _U, _U, _U, _V,
                            ctypes.POINTER(ctypes.c_uint64), c_void_pp]),
@@ -159,11 +167,27 @@ def bind_host_to_device(device):
         return None
 
 
+def _devices_from_env():
+    """CODECAD_B200_DEVICES: "all", or a comma separated list of CUDA device indices that one
+    process should drive (the first one is the primary device)."""
+    spec = os.environ.get("CODECAD_B200_DEVICES", "").strip()
+    if not spec:
+        return None
+    if spec.lower() == "all":
+        return list(range(load().cc_device_count()))
+    return [int(x) for x in spec.split(",") if x.strip()]
+
+
 def init(device=None):
-    """Create the CUDA context on `device` (default: LOCAL_RANK, else 0)."""
+    """Create the CUDA context on `device` (default: LOCAL_RANK, else 0).  Outside torchrun,
+    CODECAD_B200_DEVICES=all (or "0,1,2,3") makes this one process drive several GPUs: the calls
+    that shard (mass_properties, subdivision, grid_eval to host) then use all of them."""
     global _initialized_device
     L = load()
     if device is None:
+        devices = _devices_from_env() if "LOCAL_RANK" not in os.environ else None
+        if devices:
+            return init_devices(devices)
         device = int(os.environ.get("LOCAL_RANK", "0"))
     if _initialized_device is None:
         check(L.cc_init(int(device)))
@@ -171,6 +195,28 @@ def init(device=None):
     elif _initialized_device != int(device):
         raise CodecadB200Error("already initialised on device %d" % _initialized_device)
     return L
+
+
+def init_devices(devices=None):
+    """One process, several GPUs (cc_init_devices): `devices` is a list of CUDA device indices
+    (default: all).  devices[0] is the primary device; may follow init(devices[0])."""
+    global _initialized_device
+    L = load()
+    if devices is None:
+        devices = list(range(L.cc_device_count()))
+    devices = [int(d) for d in devices]
+    if not devices:
+        raise CodecadB200Error("no CUDA device available; libcodecad_b200 has no CPU fallback")
+    if _initialized_device is not None and _initialized_device != devices[0]:
+        raise CodecadB200Error("already initialised on device %d" % _initialized_device)
+    arr = (ctypes.c_int * len(devices))(*devices)
+    check(L.cc_init_devices(arr, len(devices)))
+    _initialized_device = devices[0]
+    return L
+
+
+def active_devices():
+    return int(load().cc_active_devices())
 
 
 def lib():

@@ -17,14 +17,13 @@ SOURCES = ["cc_kernels.cu", "cc_mesh.cu", "cc_polygon.cu", "cc_program.cpp", "cc
 HEADERS = ["cc_internal.h", "cc_microcode.h", "cc_math.cuh", "cc_ops.cuh", "cc_body.cuh", "cc_render.cuh", "cc_device_types.h", "cc_mc_table.h", "cc_scan.cuh",
            os.path.join("..", "..", "include", "codecad_b200.h")]
 
-NVCC_FLAGS = [
+COMPILE_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false",
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math",
-    "-shared",
-    "-ldl",
 ]
+OBJ_DIR = os.path.join(HERE, "build")
 
 
 def find_nvcc():
@@ -34,22 +33,38 @@ def find_nvcc():
     raise RuntimeError("nvcc not found")
 
 
+def _deps():
+    return [os.path.join(CSRC, f) for f in HEADERS] + [os.path.abspath(__file__)]
+
+
 def needs_build():
     if not os.path.exists(SO):
         return True
     t = os.path.getmtime(SO)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    deps = [os.path.join(CSRC, f) for f in SOURCES] + _deps()
     return any(os.path.getmtime(d) > t for d in deps)
 
 
 def build(force=False, verbose=False):
+    """One object per source, compiled in parallel and only when stale (objects live in the
+    git-ignored codecad_b200/build/), then linked into the in-tree shared library."""
     if not force and not needs_build():
         return SO
-    cmd = [find_nvcc()] + NVCC_FLAGS
-    if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", SO] + [os.path.join(CSRC, f) for f in SOURCES]
-    subprocess.run(cmd, check=True)
+    nvcc = find_nvcc()
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    newest_header = max(os.path.getmtime(d) for d in _deps())
+    jobs, objs = [], []
+    for f in SOURCES:
+        src = os.path.join(CSRC, f)
+        obj = os.path.join(OBJ_DIR, os.path.splitext(f)[0] + ".o")
+        objs.append(obj)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), newest_header):
+            cmd = [nvcc] + COMPILE_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            jobs.append((f, subprocess.Popen(cmd)))
+    failed = [f for f, p in jobs if p.wait() != 0]
+    if failed:
+        raise RuntimeError("nvcc failed for " + ", ".join(failed))
+    subprocess.run([nvcc, "-shared", "-o", SO] + objs + ["-ldl"], check=True)
     return SO
 
 

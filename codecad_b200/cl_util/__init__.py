@@ -15,25 +15,3 @@ from .buffer import AssertBuffer, Buffer, BufferList, OpenClAssertionError, Prog
 from .manager import Event, instance as opencl_manager  # noqa: F401
 from .pipeline import interleave, interleave2  # noqa: F401
 from . import parallel_sum  # noqa: F401
-
-
-def format_c_string_literal(s):
-    """cl_util/codegen.py:7-30 — kept because tests/test_clutil.py imports it."""
-
-    def inner(s):
-        yield '"'
-        for c in s:
-            o = ord(c)
-            if c in '\\"':
-                yield "\\" + c
-            elif 0x20 <= o < 0x7F:
-                yield c
-            elif o < 0x80:
-                yield "\\{:03o}".format(o)
-            elif 0x80 <= o < 0xA0 or 0xD800 <= o < 0xE000:
-                raise ValueError("codepoint cannot be escaped in a C string")
-            else:
-                yield "\\U{:08x}".format(o)
-        yield '"'
-
-    return "".join(inner(s))

@@ -4,6 +4,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -34,8 +37,9 @@ struct Context {
     int pts = 0, prog_space = 0;  // tuning overrides, 0 = auto
     int jit_mode = 1;             // 0 never, 1 background (default), 2 compile at first use and wait
     uint32_t jit_max_ops = 4096;  // programs longer than this are not specialised automatically
-    uint64_t next_program_id = 1;
-    uint64_t constant_program = 0;  // id of the program in the __constant__ window
+    uint64_t constant_program = 0;  // id of the program in this device's __constant__ window
+    int index = 0;                  // position in g_ctx
+    bool mesh_tables = false;       // marching-cubes tables uploaded to this device
     // look-back scratch
     uint32_t *d_ticket = nullptr;
     unsigned long long *d_status = nullptr;
@@ -48,8 +52,17 @@ struct Context {
     size_t ring_bytes = 0;
     cudaEvent_t ring_computed[kRing] = {}, ring_copied[kRing] = {};
 };
-Context g;
-std::mutex g_mu;
+// One context per device the process drives (cc_init: one; cc_init_devices: several).  Every
+// function body below works on "the current context" `g`: contexts[0] on the caller's thread, and
+// contexts[i] on the worker thread that serves device i while a call is fanned out over the
+// devices (for_each_device).
+Context g_ctx[CC_MAX_DEVICES];
+int g_n_ctx = 0;
+thread_local Context *tl_ctx = &g_ctx[0];
+thread_local int tl_device = -1;  // device this thread last made current through the library
+#define g (*tl_ctx)
+std::mutex g_mu, g_jit_mu;
+std::atomic<uint64_t> g_next_program_id{1};
 
 int fail(int code, const std::string &msg)
 {
@@ -69,9 +82,15 @@ int cuda_fail(cudaError_t e, const char *what)
         if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
     } while (0)
 
+// (the CUDA current device is per thread: a caller's thread other than the one that ran cc_init
+// would otherwise talk to device 0)
 #define NEED_INIT()                                                             \
     do {                                                                        \
         if (!g.ready) return fail(CC_ERR_NOT_INITIALIZED, "cc_init() has not succeeded"); \
+        if (tl_device != g.device) {                                            \
+            CU(cudaSetDevice(g.device));                                        \
+            tl_device = g.device;                                               \
+        }                                                                       \
     } while (0)
 
 int make_event(cc_event **ev, cudaStream_t st)
@@ -223,13 +242,40 @@ struct PinnedPool {
 };
 PinnedPool g_pinned;
 
-void fill_common(cc_eval_args *a, const cc_program *prog)
+// the program's microcode on the current device (replicated on first use)
+int program_on_device(const cc_program *prog, const uint32_t **out)
+{
+    cc_program *p = const_cast<cc_program *>(prog);
+    uint32_t *&d = p->d_code[g.index];
+    if (!d) {
+        const size_t bytes = p->dec.microcode.size() * 4;
+        cudaError_t e = cudaMalloc(&d, bytes);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d, p->dec.microcode.data(), bytes, cudaMemcpyHostToDevice, g.compute);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(g.compute);
+        if (e != cudaSuccess) {
+            if (d) cudaFree(d);
+            d = nullptr;
+            return cuda_fail(e, "program upload");
+        }
+    }
+    *out = d;
+    return CC_OK;
+}
+
+int fill_common(cc_eval_args *a, const cc_program *prog)
 {
     std::memset(a, 0, sizeof(*a));
-    a->code = prog->d_code;
+    int rc = program_on_device(prog, &a->code);
+    if (rc) return rc;
     a->code_words = prog->dec.info.n_micro_words;
     a->n_slots = prog->dec.info.n_slots;
+    return CC_OK;
 }
+#define FILL_COMMON(a, prog)                 \
+    do {                                     \
+        int rc_ = fill_common(&(a), (prog)); \
+        if (rc_) return rc_;                 \
+    } while (0)
 
 int check_dims(uint32_t nx, uint32_t ny, uint32_t nz)
 {
@@ -244,6 +290,7 @@ int check_dims(uint32_t nx, uint32_t ny, uint32_t nz)
 // as it is ready.  Both tiers produce identical bits (same op library, same -fmad=false contract).
 bool jit_ready(cc_program *p, int sink)
 {
+    std::lock_guard<std::mutex> lk(g_jit_mu);  // device threads of a fanned-out call share the program
     if (!p->use_jit) return false;
     if (p->jit_kernel[sink]) return true;
     if (g.jit_mode == 0 || p->jit_failed[sink]) return false;
@@ -276,7 +323,7 @@ int launch(int sink_kind, const cc_program *prog, cc_eval_args &a, uint64_t poin
             a.ticket = g.d_ticket;
             a.tile_status = g.d_status;
         }
-        int e = cc_jit_launch(prog, sink, a, g.compute);
+        int e = cc_jit_launch(prog, sink, a, g.compute, g.index);
         if (e) return cuda_fail((cudaError_t)e, "specialised kernel launch");
         g.launches += 1;
         g.points += points;
@@ -311,6 +358,137 @@ int launch(int sink_kind, const cc_program *prog, cc_eval_args &a, uint64_t poin
     return CC_OK;
 }
 
+
+int init_context(Context &c, int device, int index)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(CC_ERR_CUDA, "no CUDA device available; libcodecad_b200 has no CPU fallback");
+    }
+    if (device < 0 || device >= n) return fail(CC_ERR_INVALID_ARGUMENT, "no such device");
+    CU(cudaSetDevice(device));
+    tl_device = device;
+    CU(cudaGetDeviceProperties(&c.prop, device));
+    if (c.prop.major < 10)
+        return fail(CC_ERR_CUDA, std::string("device ") + c.prop.name + " is not sm_100 (built for sm_100a only)");
+    CU(cudaStreamCreateWithFlags(&c.compute, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c.copy, cudaStreamNonBlocking));
+    CU(cudaMallocHost(&c.h_word, 64));
+    {
+        // keep freed work-list memory in the pool instead of returning it to the driver at every sync
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        } else {
+            cudaGetLastError();
+        }
+    }
+    c.device = device;
+    c.index = index;
+    const char *p = getenv("CODECAD_B200_PTS");
+    if (p) c.pts = atoi(p);
+    p = getenv("CODECAD_B200_PROG_SPACE");
+    if (p) c.prog_space = atoi(p);
+    p = getenv("CODECAD_B200_JIT");
+    if (p) c.jit_mode = std::max(0, std::min(2, atoi(p)));
+    p = getenv("CODECAD_B200_JIT_MAX_OPS");
+    if (p) c.jit_max_ops = (uint32_t)atoi(p);
+    c.ready = true;
+    return CC_OK;
+}
+
+// ---- one worker thread per additional device ----------------------------------------------------
+// A call that shards (cc_mass_properties, cc_subdivide, cc_grid_eval_to_host) runs its single-device
+// body once per device: device 0 on the caller's thread, device i on worker i, whose current
+// context is g_ctx[i].  Workers are created on first use and live until cc_shutdown.
+struct Worker {
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::function<void()> task;
+    bool has_task = false, stop = false;
+};
+Worker *g_workers[CC_MAX_DEVICES] = {};
+
+void worker_main(Worker *w, int index)
+{
+    tl_ctx = &g_ctx[index];
+    cudaSetDevice(g_ctx[index].device);
+    tl_device = g_ctx[index].device;
+    for (;;) {
+        std::function<void()> task;
+        {
+            std::unique_lock<std::mutex> lk(w->mu);
+            w->cv.wait(lk, [&] { return w->has_task || w->stop; });
+            if (w->stop) return;
+            task.swap(w->task);
+            w->has_task = false;
+        }
+        task();
+    }
+}
+
+void stop_workers()
+{
+    for (int i = 0; i < CC_MAX_DEVICES; ++i) {
+        Worker *w = g_workers[i];
+        if (!w) continue;
+        {
+            std::lock_guard<std::mutex> lk(w->mu);
+            w->stop = true;
+        }
+        w->cv.notify_all();
+        if (w->th.joinable()) w->th.join();
+        delete w;
+        g_workers[i] = nullptr;
+    }
+}
+
+// fn(device index) -> status, once per initialised device, concurrently; returns the first failure
+template <class F>
+int for_each_device(F fn)
+{
+    const int n = g_n_ctx;
+    if (n <= 1 || tl_ctx != &g_ctx[0]) return fn(g.index);
+    std::vector<int> rc((size_t)n, CC_OK);
+    std::vector<std::string> errs((size_t)n);
+    std::mutex done_mu;
+    std::condition_variable done_cv;
+    int pending = n - 1;
+    for (int i = 1; i < n; ++i) {
+        if (!g_workers[i]) {
+            g_workers[i] = new Worker;
+            g_workers[i]->th = std::thread(worker_main, g_workers[i], i);
+        }
+        Worker *w = g_workers[i];
+        {
+            std::lock_guard<std::mutex> lk(w->mu);
+            w->task = [&, i] {
+                rc[(size_t)i] = fn(i);
+                if (rc[(size_t)i]) errs[(size_t)i] = g_err;
+                std::lock_guard<std::mutex> dl(done_mu);
+                if (--pending == 0) done_cv.notify_one();
+            };
+            w->has_task = true;
+        }
+        w->cv.notify_one();
+    }
+    rc[0] = fn(0);
+    {
+        std::unique_lock<std::mutex> lk(done_mu);
+        done_cv.wait(lk, [&] { return pending == 0; });
+    }
+    for (int i = 0; i < n; ++i)
+        if (rc[(size_t)i]) {
+            if (i) g_err = "device " + std::to_string(g_ctx[i].device) + ": " + errs[(size_t)i];
+            return rc[(size_t)i];
+        }
+    return CC_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -330,64 +508,72 @@ int cc_device_count(void)
 int cc_init(int device)
 {
     std::lock_guard<std::mutex> lk(g_mu);
-    if (g.ready) {
-        if (g.device == device) return CC_OK;
+    Context &c = g_ctx[0];
+    if (c.ready) {
+        if (c.device == device) return CC_OK;
         return fail(CC_ERR_INVALID_ARGUMENT, "already initialised on another device");
     }
-    int n = 0;
-    cudaError_t e = cudaGetDeviceCount(&n);
-    if (e != cudaSuccess || n == 0) {
-        cudaGetLastError();
-        return fail(CC_ERR_CUDA, "no CUDA device available; libcodecad_b200 has no CPU fallback");
-    }
-    if (device < 0 || device >= n) return fail(CC_ERR_INVALID_ARGUMENT, "no such device");
-    CU(cudaSetDevice(device));
-    CU(cudaGetDeviceProperties(&g.prop, device));
-    if (g.prop.major < 10)
-        return fail(CC_ERR_CUDA, std::string("device ") + g.prop.name + " is not sm_100 (built for sm_100a only)");
-    CU(cudaStreamCreateWithFlags(&g.compute, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&g.copy, cudaStreamNonBlocking));
-    CU(cudaMallocHost(&g.h_word, 64));
-    {
-        // keep freed work-list memory in the pool instead of returning it to the driver at every sync
-        cudaMemPool_t pool = nullptr;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-            uint64_t keep = UINT64_MAX;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        } else {
-            cudaGetLastError();
-        }
-    }
-    g.device = device;
-    g.ready = true;
-    const char *p = getenv("CODECAD_B200_PTS");
-    if (p) g.pts = atoi(p);
-    p = getenv("CODECAD_B200_PROG_SPACE");
-    if (p) g.prog_space = atoi(p);
-    p = getenv("CODECAD_B200_JIT");
-    if (p) g.jit_mode = std::max(0, std::min(2, atoi(p)));
-    p = getenv("CODECAD_B200_JIT_MAX_OPS");
-    if (p) g.jit_max_ops = (uint32_t)atoi(p);
+    int rc = init_context(c, device, 0);
+    if (rc) return rc;
+    g_n_ctx = 1;
+    tl_ctx = &g_ctx[0];
     return CC_OK;
 }
+
+int cc_init_devices(const int *devices, int n)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!devices || n < 1 || n > CC_MAX_DEVICES) return fail(CC_ERR_INVALID_ARGUMENT, "1.." + std::to_string(CC_MAX_DEVICES) + " devices");
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < i; ++j)
+            if (devices[i] == devices[j]) return fail(CC_ERR_INVALID_ARGUMENT, "a device is listed twice");
+    if (g_ctx[0].ready && g_ctx[0].device != devices[0])
+        return fail(CC_ERR_INVALID_ARGUMENT, "already initialised with another first device");
+    if (g_n_ctx > n) return fail(CC_ERR_INVALID_ARGUMENT, "already initialised with more devices");
+    for (int i = 0; i < n; ++i) {
+        Context &c = g_ctx[i];
+        if (c.ready) {
+            if (c.device != devices[i]) return fail(CC_ERR_INVALID_ARGUMENT, "already initialised with other devices");
+            continue;
+        }
+        int rc = init_context(c, devices[i], i);
+        if (rc) return rc;
+        g_n_ctx = std::max(g_n_ctx, i + 1);
+    }
+    // the caller's thread keeps driving the first device
+    tl_ctx = &g_ctx[0];
+    CU(cudaSetDevice(g_ctx[0].device));
+    tl_device = g_ctx[0].device;
+    return CC_OK;
+}
+
+int cc_active_devices(void) { return g_n_ctx; }
 
 void cc_shutdown(void)
 {
     std::lock_guard<std::mutex> lk(g_mu);
-    if (!g.ready) return;
-    cudaDeviceSynchronize();
-    if (g.d_ticket) cudaFree(g.d_ticket);
-    if (g.d_status) cudaFree(g.d_status);
-    if (g.h_word) cudaFreeHost(g.h_word);
+    stop_workers();
     g_pinned.trim(0);
-    for (int i = 0; i < Context::kRing; ++i) {
-        if (g.ring[i]) cudaFree(g.ring[i]);
-        if (g.ring_computed[i]) cudaEventDestroy(g.ring_computed[i]);
-        if (g.ring_copied[i]) cudaEventDestroy(g.ring_copied[i]);
+    for (int k = 0; k < g_n_ctx; ++k) {
+        Context &c = g_ctx[k];
+        if (!c.ready) continue;
+        cudaSetDevice(c.device);
+        cudaDeviceSynchronize();
+        if (c.d_ticket) cudaFree(c.d_ticket);
+        if (c.d_status) cudaFree(c.d_status);
+        if (c.h_word) cudaFreeHost(c.h_word);
+        for (int i = 0; i < Context::kRing; ++i) {
+            if (c.ring[i]) cudaFree(c.ring[i]);
+            if (c.ring_computed[i]) cudaEventDestroy(c.ring_computed[i]);
+            if (c.ring_copied[i]) cudaEventDestroy(c.ring_copied[i]);
+        }
+        cudaStreamDestroy(c.compute);
+        cudaStreamDestroy(c.copy);
+        c = Context();
     }
-    cudaStreamDestroy(g.compute);
-    cudaStreamDestroy(g.copy);
-    g = Context();
+    g_n_ctx = 0;
+    tl_ctx = &g_ctx[0];
+    tl_device = -1;
 }
 
 int cc_device_pci_bus_id(int device, char *out, int capacity)
@@ -423,20 +609,30 @@ int cc_synchronize(void)
 
 int cc_get_counters(uint64_t *kernel_launches, uint64_t *points_evaluated)
 {
-    if (kernel_launches) *kernel_launches = g.launches;
-    if (points_evaluated) *points_evaluated = g.points;
+    uint64_t l = 0, p = 0;
+    for (int i = 0; i < std::max(g_n_ctx, 1); ++i) {
+        l += g_ctx[i].launches;
+        p += g_ctx[i].points;
+    }
+    if (kernel_launches) *kernel_launches = l;
+    if (points_evaluated) *points_evaluated = p;
     return CC_OK;
 }
 
-void cc_reset_counters(void) { g.launches = g.points = 0; }
+void cc_reset_counters(void)
+{
+    for (int i = 0; i < CC_MAX_DEVICES; ++i) g_ctx[i].launches = g_ctx[i].points = 0;
+}
 
 int cc_set_tuning(int points_per_thread, int program_space)
 {
     if (points_per_thread != 0 && points_per_thread != 1 && points_per_thread != 2 && points_per_thread != 4)
         return fail(CC_ERR_INVALID_ARGUMENT, "points_per_thread must be 0, 1, 2 or 4");
     if (program_space < 0 || program_space > 3) return fail(CC_ERR_INVALID_ARGUMENT, "program_space must be 0..3");
-    g.pts = points_per_thread;
-    g.prog_space = program_space;
+    for (int i = 0; i < CC_MAX_DEVICES; ++i) {
+        g_ctx[i].pts = points_per_thread;
+        g_ctx[i].prog_space = program_space;
+    }
     return CC_OK;
 }
 
@@ -453,16 +649,13 @@ int cc_program_create(const float *words, uint32_t n_words, cc_program **out)
         delete p;
         return fail(rc, err);
     }
-    size_t bytes = p->dec.microcode.size() * 4;
-    cudaError_t e = cudaMalloc(&p->d_code, bytes);
-    if (e == cudaSuccess)
-        e = cudaMemcpyAsync(p->d_code, p->dec.microcode.data(), bytes, cudaMemcpyHostToDevice, g.compute);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(g.compute);
-    if (e != cudaSuccess) {
+    const uint32_t *d = nullptr;
+    rc = program_on_device(p, &d);  // the caller's device now; other devices on first use
+    if (rc != CC_OK) {
         delete p;
-        return cuda_fail(e, "program upload");
+        return rc;
     }
-    p->id = g.next_program_id++;
+    p->id = g_next_program_id++;
     *out = p;
     return CC_OK;
 }
@@ -471,10 +664,17 @@ void cc_program_destroy(cc_program *prog)
 {
     if (!prog) return;
     if (g.ready) {
-        cudaStreamSynchronize(g.compute);
+        for (int i = 0; i < g_n_ctx; ++i) {
+            Context &c = g_ctx[i];
+            if (!c.ready) continue;
+            cudaSetDevice(c.device);
+            cudaStreamSynchronize(c.compute);
+            if (prog->d_code[i]) cudaFree(prog->d_code[i]);
+            if (c.constant_program == prog->id) c.constant_program = 0;
+        }
+        cudaSetDevice(g.device);
+        tl_device = g.device;
         cc_jit_release(prog);
-        cudaFree(prog->d_code);
-        if (g.constant_program == prog->id) g.constant_program = 0;
     }
     delete prog;
 }
@@ -532,7 +732,7 @@ int cc_set_jit_mode(int mode)
 {
     const int old = g.jit_mode;
     if (mode < 0 || mode > 2) return fail(CC_ERR_INVALID_ARGUMENT, "jit mode must be 0, 1 or 2");
-    g.jit_mode = mode;
+    for (int i = 0; i < CC_MAX_DEVICES; ++i) g_ctx[i].jit_mode = mode;
     return old;
 }
 
@@ -611,7 +811,11 @@ int cc_host_alloc(size_t bytes, void **hptr)
 int cc_host_free(void *hptr)
 {
     NEED_INIT();
-    if (hptr && !g_pinned.put(hptr)) CU(cudaFreeHost(hptr));
+    if (!hptr) return CC_OK;
+    // an asynchronous copy into the block may still be in flight
+    CU(cudaStreamSynchronize(g.compute));
+    CU(cudaStreamSynchronize(g.copy));
+    if (!g_pinned.put(hptr)) CU(cudaFreeHost(hptr));
     return CC_OK;
 }
 
@@ -692,7 +896,7 @@ int cc_grid_eval(const cc_program *prog, const float corner[3], float step, uint
     for (uint32_t x0 = 0; x0 < nx; x0 += max_x) {
         uint32_t cnt = std::min(max_x, nx - x0);
         cc_eval_args a;
-        fill_common(&a, prog);
+        FILL_COMMON(a, prog);
         a.cx = corner[0]; a.cy = corner[1]; a.cz = corner[2]; a.step = step;
         a.nx = cnt; a.ny = ny; a.nz = nz; a.x_offset = x_offset + x0;
         a.n_blocks = 1;
@@ -712,7 +916,7 @@ int cc_evaluate_points(const cc_program *prog, const float *d_points, uint64_t n
     for (uint64_t i0 = 0; i0 < n; i0 += chunk) {
         const uint32_t cnt = (uint32_t)std::min<uint64_t>(chunk, n - i0);
         cc_eval_args a;
-        fill_common(&a, prog);
+        FILL_COMMON(a, prog);
         a.nx = cnt; a.ny = 1; a.nz = 1; a.n_blocks = 1;
         a.points = d_points + 4 * i0;
         a.out = (char *)d_out + i0 * 16;
@@ -722,29 +926,16 @@ int cc_evaluate_points(const cc_program *prog, const float *d_points, uint64_t n
     return make_event(ev, g.compute);
 }
 
-int cc_grid_eval_to_host(const cc_program *prog, const float corner[3], float step, uint32_t nx, uint32_t ny,
-                         uint32_t nz, uint32_t x_offset, int layout, void *h_out)
+// Dense float4 grid into host memory on the current device: slabs of ~64 MiB are computed on the
+// compute stream into a device ring (kept between calls) and copied out on the copy stream; a ring
+// entry is re-used only after its copy has finished.
+static int grid_to_host_share(const cc_program *prog, const float corner[3], float step, uint32_t nx, uint32_t ny,
+                              uint32_t nz, uint32_t x_offset, void *h_out)
 {
-    NEED_INIT();
-    if (!prog || !corner || !h_out) return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
-    if (nx == 0 || ny == 0 || nz == 0) return fail(CC_ERR_INVALID_ARGUMENT, "empty grid");
+    if (nx == 0) return CC_OK;
     const uint64_t plane = (uint64_t)ny * nz;
-    const size_t elem = layout == CC_LAYOUT_INDEX3_FLOAT4 ? 16 : 4;
-    if (layout == CC_LAYOUT_PYMCUBES_FLOAT) {
-        // y-flipped layout is not x-separable: evaluate whole, then one copy
-        void *d = nullptr;
-        CU(cudaMalloc(&d, (size_t)nx * plane * elem));
-        int rc = cc_grid_eval(prog, corner, step, nx, ny, nz, x_offset, layout, d, nullptr);
-        if (rc == CC_OK) {
-            cudaError_t e = cudaMemcpyAsync(h_out, d, (size_t)nx * plane * elem, cudaMemcpyDeviceToHost, g.compute);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(g.compute);
-            if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync D2H");
-        }
-        cudaFree(d);
-        return rc;
-    }
-    // slabs of ~64 MiB: compute on the compute stream into a device ring (kept between calls),
-    // copy out on the copy stream; a ring entry is re-used only after its copy has finished.
+    const size_t elem = 16;
+    const int layout = CC_LAYOUT_INDEX3_FLOAT4;
     const int RING = Context::kRing;
     uint32_t slab_x = (uint32_t)std::max<uint64_t>(1, (64ull << 20) / (plane * elem));
     slab_x = std::min(slab_x, nx);
@@ -782,6 +973,46 @@ int cc_grid_eval_to_host(const cc_program *prog, const float corner[3], float st
     return rc;
 }
 
+int cc_grid_eval_to_host(const cc_program *prog, const float corner[3], float step, uint32_t nx, uint32_t ny,
+                         uint32_t nz, uint32_t x_offset, int layout, void *h_out)
+{
+    NEED_INIT();
+    if (!prog || !corner || !h_out) return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
+    if (nx == 0 || ny == 0 || nz == 0) return fail(CC_ERR_INVALID_ARGUMENT, "empty grid");
+    if (layout != CC_LAYOUT_INDEX3_FLOAT4 && layout != CC_LAYOUT_PYMCUBES_FLOAT)
+        return fail(CC_ERR_INVALID_ARGUMENT, "unknown layout");
+    const uint64_t plane = (uint64_t)ny * nz;
+    if (layout == CC_LAYOUT_PYMCUBES_FLOAT) {
+        // y-flipped layout [ny][nx][nz] is not x-separable: evaluate whole (pooled device memory),
+        // then copy in pieces so that the first bytes cross PCIe while the driver maps the rest
+        const size_t bytes = (size_t)nx * plane * 4;
+        void *d = nullptr;
+        CU(cudaMallocAsync(&d, bytes, g.compute));
+        int rc = cc_grid_eval(prog, corner, step, nx, ny, nz, x_offset, layout, d, nullptr);
+        if (rc == CC_OK) {
+            const size_t piece = 64ull << 20;
+            cudaError_t e = cudaSuccess;
+            for (size_t o = 0; o < bytes && e == cudaSuccess; o += piece)
+                e = cudaMemcpyAsync((char *)h_out + o, (char *)d + o, std::min(piece, bytes - o), cudaMemcpyDeviceToHost,
+                                    g.compute);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(g.compute);
+            if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync D2H");
+        }
+        cudaFreeAsync(d, g.compute);
+        return rc;
+    }
+    // x-slabs over the initialised devices (the INDEX3 layout is contiguous in x), each with its
+    // own compute/copy pipeline; coordinates stay corner + step * global index
+    const uint32_t nd = (uint32_t)std::max(1, g_n_ctx);
+    if (nd == 1 || nx < nd) return grid_to_host_share(prog, corner, step, nx, ny, nz, x_offset, h_out);
+    return for_each_device([&](int i) {
+        const uint32_t base = nx / nd, rem = nx % nd;
+        const uint32_t x0 = (uint32_t)i * base + std::min<uint32_t>((uint32_t)i, rem);
+        const uint32_t cnt = base + ((uint32_t)i < rem ? 1u : 0u);
+        return grid_to_host_share(prog, corner, step, cnt, ny, nz, x_offset + x0, (char *)h_out + (size_t)x0 * plane * 16);
+    });
+}
+
 int cc_subdivision_step(const cc_program *prog, const float corner[3], float step, float threshold,
                         uint32_t nx, uint32_t ny, uint32_t nz, uint32_t *d_counter, uint8_t *d_list,
                         cc_event **ev)
@@ -793,7 +1024,7 @@ int cc_subdivision_step(const cc_program *prog, const float corner[3], float ste
     if (nx > 256 || ny > 256 || nz > 256)
         return fail(CC_ERR_INVALID_ARGUMENT, "grid dimension > 256 overflows the uchar4 index list");
     cc_eval_args a;
-    fill_common(&a, prog);
+    FILL_COMMON(a, prog);
     a.cx = corner[0]; a.cy = corner[1]; a.cz = corner[2]; a.step = step;
     a.nx = nx; a.ny = ny; a.nz = nz; a.n_blocks = 1;
     a.threshold = threshold; a.counter = d_counter; a.list = d_list;
@@ -813,7 +1044,7 @@ int cc_mass_properties_step(const cc_program *prog, const float corner[3], float
     if (nx > 256 || ny > 256 || nz > 256)
         return fail(CC_ERR_INVALID_ARGUMENT, "grid dimension > 256 overflows the uchar4 index list");
     cc_eval_args a;
-    fill_common(&a, prog);
+    FILL_COMMON(a, prog);
     a.cx = corner[0]; a.cy = corner[1]; a.cz = corner[2]; a.step = step;
     a.nx = nx; a.ny = ny; a.nz = nz; a.n_blocks = 1;
     a.threshold = threshold; a.counter = d_counter; a.list = d_list; a.sums = d_sums;
@@ -860,25 +1091,30 @@ int read_counter(uint32_t *d_counter, uint32_t *out)
 // a chunk evaluates at most `kChunkCells` cells and can emit at most that many hits.
 const uint64_t kChunkCells = 1ull << 27;
 
-}  // namespace
+// Which level's hits are dealt to the shares (ranks x devices): the one that feeds the most
+// expensive level, so that the unit of distribution is as fine as it gets.  Levels up to and
+// including it are evaluated by every share (they are a few thousand cells), everything below is
+// evaluated by the share that owns the block.  Hit h of a launch goes to share h % n_shares.
+//   subdivision: levels 0 .. n-2 are classified, n-2 is the big one -> deal the hits of n-3
+//   mass properties: the leaf level n-1 is the big one           -> deal the hits of n-2
+uint32_t deal_level_subdiv(uint32_t n_levels) { return n_levels >= 3 ? n_levels - 3 : 0; }
+uint32_t deal_level_mass(uint32_t n_levels) { return n_levels >= 2 ? n_levels - 2 : 0; }
 
-extern "C" {
-
-int cc_subdivide(const cc_program *prog, const double origin[3], double resolution, const cc_level *levels,
-                 uint32_t n_levels, int dimension, uint32_t rank, uint32_t world, int64_t **out_corners,
-                 uint64_t *out_count)
+int check_levels(const cc_level *levels, uint32_t n_levels)
 {
-    NEED_INIT();
-    if (!prog || !origin || !levels || !out_corners || !out_count)
-        return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
-    if (n_levels < 2) return fail(CC_ERR_INVALID_ARGUMENT, "cc_subdivide needs at least two levels");
-    if (dimension != 2 && dimension != 3) return fail(CC_ERR_INVALID_ARGUMENT, "dimension must be 2 or 3");
-    if (world == 0 || rank >= world) return fail(CC_ERR_INVALID_ARGUMENT, "bad rank/world");
     for (uint32_t l = 0; l < n_levels; ++l)
         if (levels[l].nx > 256 || levels[l].ny > 256 || levels[l].nz > 256 || !levels[l].nx || !levels[l].ny ||
-            !levels[l].nz)
+            !levels[l].nz || levels[l].cell_size < 1)
             return fail(CC_ERR_INVALID_ARGUMENT, "level grid dimensions must be in 1..256");
+    return CC_OK;
+}
 
+// subdivision() on the current device for share `rank` of `world`: appends the int corners of the
+// share's leaf blocks to *out (host), in the order the levels produce them
+int subdivide_share(const cc_program *prog, const double origin[3], double resolution, const cc_level *levels,
+                    uint32_t n_levels, int dimension, uint32_t rank, uint32_t world, std::vector<int64_t> *out,
+                    uint64_t *dealt_blocks)
+{
     DevBuf corners_a, corners_b, blocks, hit_xyz, hit_block, counter;
     int rc;
     if ((rc = counter.reserve(4))) return rc;
@@ -888,6 +1124,8 @@ int cc_subdivide(const cc_program *prog, const double origin[3], double resoluti
     if ((rc = corners_a.reserve(3 * sizeof(int64_t)))) return rc;
     CU(cudaMemcpyAsync(corners_a.p, cur_host.data(), 3 * sizeof(int64_t), cudaMemcpyHostToDevice, g.compute));
     DevBuf *cur = &corners_a, *nxt = &corners_b;
+    const uint32_t deal = deal_level_subdiv(n_levels);
+    if (dealt_blocks) *dealt_blocks = 0;
 
     for (uint32_t l = 0; l + 1 < n_levels; ++l) {
         const cc_level &L = levels[l];
@@ -899,7 +1137,7 @@ int cc_subdivide(const cc_program *prog, const double origin[3], double resoluti
         // children of this level, gathered chunk by chunk
         uint64_t n_next = 0;
         size_t next_cap = 0;
-        const uint32_t w = (l == 0) ? world : 1u, r = (l == 0) ? rank : 0u;
+        const uint32_t w = (l == deal) ? world : 1u, r = (l == deal) ? rank : 0u;
         for (uint64_t b0 = 0; b0 < n_cur; b0 += chunk_blocks) {
             const uint32_t nb = (uint32_t)std::min<uint64_t>(chunk_blocks, n_cur - b0);
             if ((rc = blocks.reserve((size_t)nb * sizeof(cc_block_desc)))) return rc;
@@ -909,7 +1147,7 @@ int cc_subdivide(const cc_program *prog, const double origin[3], double resoluti
             if (e) return cuda_fail((cudaError_t)e, "make_blocks");
             CU(cudaMemsetAsync(counter.p, 0, 4, g.compute));
             cc_eval_args a;
-            fill_common(&a, prog);
+            FILL_COMMON(a, prog);
             a.step = (float)box_step;
             a.nx = L.nx; a.ny = L.ny; a.nz = L.nz; a.n_blocks = nb;
             a.blocks = blocks.as<cc_block_desc>();
@@ -946,48 +1184,91 @@ int cc_subdivide(const cc_program *prog, const double origin[3], double resoluti
         }
         std::swap(cur, nxt);
         n_cur = n_next;
+        if (l == deal && dealt_blocks) *dealt_blocks = n_cur;
         if (n_cur == 0) break;
     }
-    // `cur` now holds the int corners of the leaf blocks
-    *out_count = n_cur;
-    *out_corners = nullptr;
+    // `cur` now holds the int corners of the share's leaf blocks
     if (n_cur) {
-        int64_t *h = (int64_t *)malloc((size_t)n_cur * 3 * sizeof(int64_t));
-        if (!h) return fail(CC_ERR_INVALID_ARGUMENT, "out of host memory");
-        cudaError_t e = cudaMemcpyAsync(h, cur->p, (size_t)n_cur * 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, g.compute);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(g.compute);
-        if (e != cudaSuccess) {
-            free(h);
-            return cuda_fail(e, "leaf list D2H");
-        }
-        *out_corners = h;
+        const size_t at = out->size();
+        out->resize(at + (size_t)n_cur * 3);
+        CU(cudaMemcpyAsync(out->data() + at, cur->p, (size_t)n_cur * 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, g.compute));
+        CU(cudaStreamSynchronize(g.compute));
     }
     return CC_OK;
 }
 
-int cc_mass_properties(const cc_program *prog, const double box_a[3], double resolution, const cc_level *levels,
-                       uint32_t n_levels, uint32_t rank, uint32_t world, double integrals[10], uint64_t stats[4])
+// The order in which one GPU lists the leaf blocks: level by level the hits come out by parent
+// block and, inside a block, in INDEX3 cell order (x slowest) — i.e. lexicographic in the per-level
+// cell coordinates (x0,y0,z0, x1,y1,z1, ...), which can be read off a leaf corner because
+// cell_size[l-1] is a multiple of cell_size[l] that exceeds any offset inside the level.
+void hierarchy_order(int64_t *corners, uint64_t n, const cc_level *levels, uint32_t n_levels)
 {
-    NEED_INIT();
-    if (!prog || !box_a || !levels || !integrals) return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
-    if (n_levels < 1) return fail(CC_ERR_INVALID_ARGUMENT, "no levels");
-    if (world == 0 || rank >= world) return fail(CC_ERR_INVALID_ARGUMENT, "bad rank/world");
-    for (uint32_t l = 0; l < n_levels; ++l)
-        if (levels[l].nx > 256 || levels[l].ny > 256 || levels[l].nz > 256 || !levels[l].nx || !levels[l].ny ||
-            !levels[l].nz)
-            return fail(CC_ERR_INVALID_ARGUMENT, "level grid dimensions must be in 1..256");
+    const uint32_t nd = n_levels - 1;  // classified levels
+    std::vector<uint32_t> key((size_t)n * nd * 3);
+    for (uint64_t i = 0; i < n; ++i)
+        for (int ax = 0; ax < 3; ++ax) {
+            int64_t rest = corners[3 * i + ax];
+            for (uint32_t l = 0; l < nd; ++l) {
+                const int64_t cs = levels[l].cell_size;
+                key[((size_t)i * nd + l) * 3 + ax] = (uint32_t)(rest / cs);
+                rest %= cs;
+            }
+        }
+    std::vector<uint64_t> order((size_t)n);
+    for (uint64_t i = 0; i < n; ++i) order[(size_t)i] = i;
+    const size_t kl = (size_t)nd * 3;
+    std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) {
+        return std::lexicographical_compare(key.begin() + (ptrdiff_t)(a * kl), key.begin() + (ptrdiff_t)((a + 1) * kl),
+                                            key.begin() + (ptrdiff_t)(b * kl), key.begin() + (ptrdiff_t)((b + 1) * kl));
+    });
+    std::vector<int64_t> sorted((size_t)n * 3);
+    for (uint64_t i = 0; i < n; ++i)
+        for (int ax = 0; ax < 3; ++ax) sorted[3 * (size_t)i + ax] = corners[3 * order[(size_t)i] + ax];
+    std::memcpy(corners, sorted.data(), sorted.size() * sizeof(int64_t));
+}
 
+// Exponents of the accumulator quanta of the ten integrals (one,x,y,z,xx,yy,zz,xy,xz,yz): the
+// hierarchy lives inside the top-level block, so |integral| and every block's contribution are
+// bounded by V, V*M_k, V*M_j*M_k with V its volume and M_k the largest |coordinate| along axis k.
+// Depends on the arguments only, hence identical on every device and rank.
+cc_mass_quanta mass_quanta(const double box_a[3], double resolution, const cc_level &top)
+{
+    const double s0 = resolution * (double)top.cell_size;
+    const double ext[3] = {top.nx * s0, top.ny * s0, top.nz * s0};
+    double M[3], V = 1.0;
+    for (int k = 0; k < 3; ++k) {
+        M[k] = std::max(std::fabs(box_a[k]), std::fabs(box_a[k] + ext[k])) + s0;
+        V *= ext[k];
+    }
+    const double bound[10] = {V, V * M[0], V * M[1], V * M[2], V * M[0] * M[0], V * M[1] * M[1], V * M[2] * M[2],
+                              V * M[0] * M[1], V * M[0] * M[2], V * M[1] * M[2]};
+    cc_mass_quanta q;
+    for (int i = 0; i < 10; ++i) {
+        int e = 0;
+        std::frexp(bound[i], &e);  // bound < 2^e
+        q.e[i] = e + 3 - 100;      // 8x head room; a value is < 2^100 quanta
+    }
+    return q;
+}
+
+// mass_properties() on the current device for share `rank` of `world`: limb sums of the share's
+// contribution (limbs[10][4] + overflow count), stats = launches, cells, blocks, blocks of the dealt level
+int mass_share(const cc_program *prog, const double box_a[3], double resolution, const cc_level *levels,
+               uint32_t n_levels, uint32_t rank, uint32_t world, const cc_mass_quanta &quanta, int64_t limbs[41],
+               uint64_t stats[4])
+{
     DevBuf corners_a, corners_b, blocks, hit_xyz, hit_block, counter, sums, acc;
     int rc;
     if ((rc = counter.reserve(4))) return rc;
-    if ((rc = acc.reserve(20 * sizeof(double)))) return rc;
-    CU(cudaMemsetAsync(acc.p, 0, 20 * sizeof(double), g.compute));
+    if ((rc = acc.reserve(41 * sizeof(unsigned long long)))) return rc;
+    CU(cudaMemsetAsync(acc.p, 0, 41 * sizeof(unsigned long long), g.compute));
     double root[3] = {box_a[0], box_a[1], box_a[2]};
     if ((rc = corners_a.reserve(3 * sizeof(double)))) return rc;
     CU(cudaMemcpyAsync(corners_a.p, root, sizeof(root), cudaMemcpyHostToDevice, g.compute));
     CU(cudaStreamSynchronize(g.compute));
     DevBuf *cur = &corners_a, *nxt = &corners_b;
-    uint64_t n_cur = 1, n_launch = 0, n_cells = 0, n_blocks_total = 0;
+    uint64_t n_cur = 1, n_launch = 0, n_cells = 0, n_blocks_total = 0, n_dealt = 0;
+    const uint32_t deal = deal_level_mass(n_levels);
 
     for (uint32_t l = 0; l < n_levels && n_cur; ++l) {
         const cc_level &L = levels[l];
@@ -996,7 +1277,7 @@ int cc_mass_properties(const cc_program *prog, const double box_a[3], double res
         const uint64_t chunk_blocks = std::max<uint64_t>(1, kChunkCells / cells);
         const double s = resolution * (double)L.cell_size;                       // mass_properties.py:51-53
         const float thr = leaf ? 0.0f : (float)(s * std::sqrt(3.0) / 2);         // :87-90
-        const uint32_t w = (l == 0) ? world : 1u, r = (l == 0) ? rank : 0u;
+        const uint32_t w = (l == deal) ? world : 1u, r = (l == deal) ? rank : 0u;
         uint64_t n_next = 0;
         size_t next_cap = 0;
         for (uint64_t b0 = 0; b0 < n_cur; b0 += chunk_blocks) {
@@ -1015,7 +1296,7 @@ int cc_mass_properties(const cc_program *prog, const double box_a[3], double res
             CU(cudaMemsetAsync(counter.p, 0, 4, g.compute));
             CU(cudaMemsetAsync(sums.p, 0, (size_t)nb * 10 * 4, g.compute));
             cc_eval_args a;
-            fill_common(&a, prog);
+            FILL_COMMON(a, prog);
             a.step = (float)s;
             a.nx = L.nx; a.ny = L.ny; a.nz = L.nz; a.n_blocks = nb;
             a.blocks = blocks.as<cc_block_desc>();
@@ -1028,11 +1309,14 @@ int cc_mass_properties(const cc_program *prog, const double box_a[3], double res
             n_launch += 1;
             n_cells += (uint64_t)nb * cells;
             n_blocks_total += nb;
-            // every rank evaluates level 0, but only rank 0 counts its inside cells
-            if (l > 0 || rank == 0) {
-                e = cc_launch_mass_integrals(cur->as<double>() + 3 * b0, sums.as<uint32_t>(), nb, s, acc.as<double>(), g.compute);
+            // levels up to the dealt one are evaluated by every share; share 0 alone counts their
+            // inside cells
+            if (l > deal || rank == 0 || world == 1) {
+                e = cc_launch_mass_integrals(cur->as<double>() + 3 * b0, sums.as<uint32_t>(), nb, s, quanta,
+                                             acc.as<unsigned long long>(), g.compute);
                 if (e) return cuda_fail((cudaError_t)e, "mass integrals");
             }
+            g.launches += 2;  // make_blocks, integrals
             if (leaf) continue;
             uint32_t hits = 0;
             if ((rc = read_counter(counter.as<uint32_t>(), &hits))) return rc;
@@ -1054,24 +1338,142 @@ int cc_mass_properties(const cc_program *prog, const double box_a[3], double res
                                                    hit_xyz.as<uint8_t>(), hits, s, r, w,
                                                    nxt->as<double>() + 3 * n_next, g.compute);
                 if (e) return cuda_fail((cudaError_t)e, "mass expand_children");
+                g.launches += 1;
                 n_next += mine;
             }
         }
-        g.launches += 3;
         std::swap(cur, nxt);
         n_cur = n_next;
+        if (l == deal) n_dealt = n_cur;
     }
-    double h_acc[20];
+    unsigned long long h_acc[41];
     CU(cudaMemcpyAsync(h_acc, acc.p, sizeof(h_acc), cudaMemcpyDeviceToHost, g.compute));
     CU(cudaStreamSynchronize(g.compute));
-    for (int i = 0; i < 10; ++i) integrals[i] = h_acc[i];
+    for (int i = 0; i < 41; ++i) limbs[i] = (int64_t)h_acc[i];
+    stats[0] = n_launch;
+    stats[1] = n_cells;
+    stats[2] = n_blocks_total;
+    stats[3] = n_dealt;
+    return CC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cc_sort_leaf_corners(int64_t *corners, uint64_t n, const cc_level *levels, uint32_t n_levels)
+{
+    if ((!corners && n) || !levels || n_levels < 2) return fail(CC_ERR_INVALID_ARGUMENT, "bad argument");
+    int rc = check_levels(levels, n_levels);
+    if (rc) return rc;
+    if (n > 1) hierarchy_order(corners, n, levels, n_levels);
+    return CC_OK;
+}
+
+int cc_subdivide(const cc_program *prog, const double origin[3], double resolution, const cc_level *levels,
+                 uint32_t n_levels, int dimension, uint32_t rank, uint32_t world, int64_t **out_corners,
+                 uint64_t *out_count)
+{
+    NEED_INIT();
+    if (!prog || !origin || !levels || !out_corners || !out_count)
+        return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
+    if (n_levels < 2) return fail(CC_ERR_INVALID_ARGUMENT, "cc_subdivide needs at least two levels");
+    if (dimension != 2 && dimension != 3) return fail(CC_ERR_INVALID_ARGUMENT, "dimension must be 2 or 3");
+    if (world == 0 || rank >= world) return fail(CC_ERR_INVALID_ARGUMENT, "bad rank/world");
+    int rc = check_levels(levels, n_levels);
+    if (rc) return rc;
+    *out_count = 0;
+    *out_corners = nullptr;
+    // every initialised device takes a share of this rank's share
+    const uint32_t nd = (uint32_t)std::max(1, g_n_ctx);
+    std::vector<std::vector<int64_t>> part(nd);
+    rc = for_each_device([&](int i) {
+        return subdivide_share(prog, origin, resolution, levels, n_levels, dimension, rank * nd + (uint32_t)i, world * nd,
+                               &part[(size_t)i], nullptr);
+    });
+    if (rc) return rc;
+    size_t total = 0;
+    for (auto &v : part) total += v.size();
+    if (!total) return CC_OK;
+    int64_t *h = (int64_t *)malloc(total * sizeof(int64_t));
+    if (!h) return fail(CC_ERR_INVALID_ARGUMENT, "out of host memory");
+    size_t at = 0;
+    for (auto &v : part) {
+        if (!v.empty()) std::memcpy(h + at, v.data(), v.size() * sizeof(int64_t));
+        at += v.size();
+    }
+    if (nd > 1) hierarchy_order(h, total / 3, levels, n_levels);  // the order one GPU produces
+    *out_corners = h;
+    *out_count = total / 3;
+    return CC_OK;
+}
+
+int cc_mass_properties_exact(const cc_program *prog, const double box_a[3], double resolution, const cc_level *levels,
+                             uint32_t n_levels, uint32_t rank, uint32_t world, int64_t limbs[40], int32_t exponents[10],
+                             uint64_t stats[8])
+{
+    NEED_INIT();
+    if (!prog || !box_a || !levels || !limbs || !exponents) return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
+    if (n_levels < 1) return fail(CC_ERR_INVALID_ARGUMENT, "no levels");
+    if (world == 0 || rank >= world) return fail(CC_ERR_INVALID_ARGUMENT, "bad rank/world");
+    int rc = check_levels(levels, n_levels);
+    if (rc) return rc;
+    if (!(resolution > 0)) return fail(CC_ERR_INVALID_ARGUMENT, "resolution must be positive");
+    const cc_mass_quanta quanta = mass_quanta(box_a, resolution, levels[0]);
+    const uint32_t nd = (uint32_t)std::max(1, g_n_ctx);
+    std::vector<int64_t> part((size_t)nd * 41, 0);
+    std::vector<uint64_t> st((size_t)nd * 4, 0);
+    rc = for_each_device([&](int i) {
+        return mass_share(prog, box_a, resolution, levels, n_levels, rank * nd + (uint32_t)i, world * nd, quanta,
+                          part.data() + (size_t)i * 41, st.data() + (size_t)i * 4);
+    });
+    if (rc) return rc;
+    for (int k = 0; k < 40; ++k) limbs[k] = 0;
+    int64_t overflow = 0;
+    uint64_t s4[4] = {0, 0, 0, 0}, max_cells = 0, min_cells = UINT64_MAX;
+    for (uint32_t i = 0; i < nd; ++i) {
+        for (int k = 0; k < 40; ++k) limbs[k] += part[(size_t)i * 41 + k];
+        overflow += part[(size_t)i * 41 + 40];
+        for (int k = 0; k < 4; ++k) s4[k] += st[(size_t)i * 4 + k];
+        max_cells = std::max(max_cells, st[(size_t)i * 4 + 1]);
+        min_cells = std::min(min_cells, st[(size_t)i * 4 + 1]);
+    }
+    if (overflow) return fail(CC_ERR_INVALID_ARGUMENT, "mass integrals left the range of the exact accumulator");
+    for (int i = 0; i < 10; ++i) exponents[i] = quanta.e[i];
     if (stats) {
-        stats[0] = n_launch;
-        stats[1] = n_cells;
-        stats[2] = n_blocks_total;
-        stats[3] = n_levels;
+        stats[0] = s4[0]; stats[1] = s4[1]; stats[2] = s4[2]; stats[3] = n_levels;
+        stats[4] = s4[3];      // blocks of the dealt level owned by this call's devices
+        stats[5] = nd;         // devices used
+        stats[6] = max_cells;  // cells evaluated by the busiest / the least busy device
+        stats[7] = min_cells;
     }
     return CC_OK;
+}
+
+int cc_mass_limbs_to_integrals(const int64_t limbs[40], const int32_t exponents[10], double integrals[10])
+{
+    if (!limbs || !exponents || !integrals) return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
+    for (int i = 0; i < 10; ++i) {
+        __int128 t = 0;
+        for (int k = 3; k >= 0; --k) t = t * ((__int128)1 << 32) + (__int128)limbs[4 * i + k];
+        // (double)__int128 rounds to nearest even; ldexp is exact here
+        integrals[i] = std::ldexp((double)t, exponents[i]);
+    }
+    return CC_OK;
+}
+
+int cc_mass_properties(const cc_program *prog, const double box_a[3], double resolution, const cc_level *levels,
+                       uint32_t n_levels, uint32_t rank, uint32_t world, double integrals[10], uint64_t stats[4])
+{
+    if (!integrals) return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
+    int64_t limbs[40];
+    int32_t ex[10];
+    uint64_t st[8];
+    int rc = cc_mass_properties_exact(prog, box_a, resolution, levels, n_levels, rank, world, limbs, ex, st);
+    if (rc) return rc;
+    if (stats)
+        for (int k = 0; k < 4; ++k) stats[k] = st[k];
+    return cc_mass_limbs_to_integrals(limbs, ex, integrals);
 }
 
 }  // extern "C"
@@ -1093,7 +1495,10 @@ int launch_render(bool ray, const cc_program *prog, cc_render_launch &r, uint64_
         int rc = prepare_program(prog, cfg);
         if (rc) return rc;
     }
-    r.code = prog->d_code;
+    {
+        int rc = program_on_device(prog, &r.code);
+        if (rc) return rc;
+    }
     r.code_words = prog->dec.info.n_micro_words;
     r.n_slots = prog->dec.info.n_slots;
     DevBuf count;  // released on every path
@@ -1103,7 +1508,7 @@ int launch_render(bool ray, const cc_program *prog, cc_render_launch &r, uint64_
         CU(cudaMemsetAsync(count.p, 0, 8, g.compute));
     }
     r.eval_count = count.as<unsigned long long>();
-    int e = cc_launch_render(ray ? 1 : 0, specialised ? 0 : cfg.prog_space, specialised ? prog : nullptr, r, g.compute);
+    int e = cc_launch_render(ray ? 1 : 0, specialised ? 0 : cfg.prog_space, specialised ? prog : nullptr, r, g.compute, g.index);
     if (e) return cuda_fail((cudaError_t)e, "render kernel launch");
     g.launches += 1;
     g.points += (uint64_t)r.w * r.h;
@@ -1301,7 +1706,7 @@ int cc_matplotlib_slice(const cc_program *prog, const float corner[3], float ste
     DevBuf field;
     if ((rc = field.reserve((size_t)width * height * 16))) return rc;
     cc_eval_args a;
-    fill_common(&a, prog);
+    FILL_COMMON(a, prog);
     a.cx = corner[0]; a.cy = corner[1]; a.cz = corner[2]; a.step = step;
     a.nx = width; a.ny = height; a.nz = 1; a.n_blocks = 1;
     a.out = field.p;
@@ -1373,7 +1778,7 @@ int cc_polygon_blocks(const cc_program *prog, const double *corners, double reso
         CU(cudaMemcpyAsync(descs.p, h_desc.data(), (size_t)nb * sizeof(cc_block_desc), cudaMemcpyHostToDevice, g.compute));
         CU(cudaMemcpyAsync(d_corner2.p, h_c2.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, g.compute));
         cc_eval_args a;
-        fill_common(&a, prog);
+        FILL_COMMON(a, prog);
         a.step = step;
         a.nx = gx; a.ny = gy; a.nz = 1; a.n_blocks = nb;
         a.blocks = descs.as<cc_block_desc>();
@@ -1419,11 +1824,10 @@ int cc_mesh_blocks(const cc_program *prog, const double *corners, double resolut
     *out_triangle_block = nullptr;
     *out_triangles = 0;
     if (n_blocks == 0) return CC_OK;
-    static bool tables_uploaded = false;
-    if (!tables_uploaded) {
+    if (!g.mesh_tables) {  // __constant__ tables are per device (and gone after cc_shutdown)
         int e = cc_mesh_upload_tables(g.compute);
         if (e) return cuda_fail((cudaError_t)e, "marching-cubes tables");
-        tables_uploaded = true;
+        g.mesh_tables = true;
     }
     // Phase A per chunk of blocks: evaluate the field, count triangles per tile, scan.  Phase B per
     // chunk: emit the triangles.  When every chunk's field fits the budget at once (the usual
@@ -1468,7 +1872,7 @@ int cc_mesh_blocks(const cc_program *prog, const double *corners, double resolut
                            g.compute));
         void *field = resident ? c.field.p : shared_field.p;
         cc_eval_args a;
-        fill_common(&a, prog);
+        FILL_COMMON(a, prog);
         a.step = step;
         a.nx = nx; a.ny = ny; a.nz = nz; a.n_blocks = nb;
         a.blocks = c.descs.as<cc_block_desc>();

@@ -28,15 +28,18 @@ struct cc_jit_cfg {
 };
 struct cc_jit_job;
 
+#define CC_MAX_DEVICES 16  // devices one process can drive (cc_init_devices)
+
 struct cc_program {
     cc_decoded dec;
-    uint32_t *d_code = nullptr;  // device copy of the microcode
-    uint64_t id = 0;             // identifies what is currently loaded in the __constant__ window
+    uint32_t *d_code[CC_MAX_DEVICES] = {};  // device copies of the microcode, one per initialised device (made on first use)
+    uint64_t id = 0;             // identifies what is currently loaded in a device's __constant__ window
     // scene-specialised kernels (cc_jit.cpp), one library per sink; null until compiled
     void *jit_library[CC_N_SINKS] = {};
     void *jit_kernel[CC_N_SINKS] = {};
     cc_jit_cfg jit_cfg[CC_N_SINKS];
     size_t jit_smem[CC_N_SINKS] = {};  // dynamic shared memory of each specialised kernel
+    bool jit_attr_done[CC_N_SINKS][CC_MAX_DEVICES] = {};  // MaxDynamicSharedMemorySize is a per-device attribute
     cc_jit_job *jit_job[CC_N_SINKS] = {};  // background compiles in flight
     bool jit_failed[CC_N_SINKS] = {};
     size_t jit_cubin_bytes = 0;
@@ -52,8 +55,9 @@ int cc_jit_compile(cc_program *prog, int pts, unsigned sink_mask, double *second
 void cc_jit_start(cc_program *prog, int sink);
 int cc_jit_poll(cc_program *prog, int sink, bool wait, std::string *err);
 void cc_jit_release(cc_program *prog);
-int cc_jit_launch(const cc_program *prog, int sink, const cc_eval_args &a, void *stream);
-int cc_jit_launch_render(const cc_program *prog, int sink, const cc_render_args &a, void *stream);
+// dev_index = index of the library context (device) the launch goes to
+int cc_jit_launch(const cc_program *prog, int sink, const cc_eval_args &a, void *stream, int dev_index);
+int cc_jit_launch_render(const cc_program *prog, int sink, const cc_render_args &a, void *stream, int dev_index);
 cc_jit_cfg cc_jit_render_cfg(const cc_decoded &dec);
 #define CC_SINK_MASK_ALL ((1u << CC_N_SINKS) - 1u)
 #define CC_RENDER_THREADS 128  // CTA size of the specialised image renderers
@@ -85,7 +89,7 @@ struct cc_render_launch {
 };
 // prog_space 1 = constant bank, 2 = shared copy (interpreter kernels); 0 = the specialised kernel of `prog`
 struct cc_program;
-int cc_launch_render(int ray, int prog_space, const cc_program *prog, const cc_render_launch &r, void *stream);
+int cc_launch_render(int ray, int prog_space, const cc_program *prog, const cc_render_launch &r, void *stream, int dev_index);
 
 // hierarchy helper kernels
 struct cc_level_geom {
@@ -107,9 +111,12 @@ int cc_launch_mass_make_blocks(const double *d_corners, uint32_t n, double s, cc
 int cc_launch_mass_expand_children(const double *d_parent_corners, const uint32_t *d_hit_block,
                                    const uint8_t *d_hit_xyz, uint32_t n_hits, double s,
                                    uint32_t rank, uint32_t world, double *d_child_corners, void *stream);
+// per-block integrals (mass_properties.py:139-148, float64) added to an exact fixed-point accumulator:
+// d_limbs[10][4] signed 64-bit sums of the 32-bit limbs of trunc(value / 2^quantum_exp[i]); d_limbs[40]
+// counts values outside the accumulator's range (must stay 0)
+struct cc_mass_quanta { int e[10]; };
 int cc_launch_mass_integrals(const double *d_corners, const uint32_t *d_sums, uint32_t n_blocks, double s,
-                             double *d_integrals /* [10] accumulated with Kahan, single CTA */,
-                             void *stream);
+                             cc_mass_quanta q, unsigned long long *d_limbs /* [41] */, void *stream);
 
 // ---- 2-D outline extraction (cc_polygon.cu, rendering/polygon2d.cl) -----------------------------
 #ifdef __CUDACC__

@@ -51,7 +51,9 @@ struct Nvrtc {
     int (*Version)(int *, int *);
 };
 
-std::mutex g_nvrtc_mu;
+// Leaked on purpose (like the caches below): a background compile thread may still be running when
+// the process exits, and must not find these destroyed by static destruction.
+std::mutex &g_nvrtc_mu = *new std::mutex;
 
 bool load_nvrtc(Nvrtc *n, std::string *err)
 {
@@ -676,8 +678,24 @@ int cc_jit_nvrtc(const std::string &src, std::vector<char> *cubin, std::string *
 namespace {
 
 typedef std::shared_ptr<const std::vector<char>> Cubin;
-std::mutex g_cache_mu;
-std::map<uint64_t, Cubin> g_cache;
+std::mutex &g_cache_mu = *new std::mutex;
+std::map<uint64_t, Cubin> &g_cache = *new std::map<uint64_t, Cubin>;
+
+// On-disk entries carry a header so that a stale, truncated or foreign file with the right name is
+// never loaded as a kernel: magic, the source key, the payload length and its FNV-1a checksum.
+struct CacheHeader {
+    char magic[8];  // "CCB2CUB1"
+    uint64_t key, bytes, checksum;
+};
+uint64_t fnv1a_bytes(const char *p, size_t n)
+{
+    uint64_t h = 14695981039346656037ull;
+    for (size_t i = 0; i < n; ++i) {
+        h ^= (unsigned char)p[i];
+        h *= 1099511628211ull;
+    }
+    return h;
+}
 
 uint64_t fnv1a(uint64_t h, const std::string &s)
 {
@@ -727,7 +745,7 @@ std::string cache_path(uint64_t key)
 void mkdirs(const std::string &d)
 {
     for (size_t i = 1; i <= d.size(); ++i)
-        if (i == d.size() || d[i] == '/') mkdir(d.substr(0, i).c_str(), 0755);
+        if (i == d.size() || d[i] == '/') mkdir(d.substr(0, i).c_str(), 0700);
 }
 
 }  // namespace
@@ -752,9 +770,18 @@ static int build_cubin(const cc_decoded &dec, const cc_jit_cfg &cfg, int sink, C
     auto bin = std::make_shared<std::vector<char>>();
     const std::string path = cache_path(key);
     std::string blob;
-    if (!path.empty() && read_file(path, &blob) && blob.size() > 64) {
-        bin->assign(blob.begin(), blob.end());
-    } else {
+    bool from_disk = false;
+    if (!path.empty() && read_file(path, &blob) && blob.size() > sizeof(CacheHeader)) {
+        CacheHeader hd;
+        std::memcpy(&hd, blob.data(), sizeof hd);
+        const size_t n = blob.size() - sizeof hd;
+        if (std::memcmp(hd.magic, "CCB2CUB1", 8) == 0 && hd.key == key && hd.bytes == n &&
+            hd.checksum == fnv1a_bytes(blob.data() + sizeof hd, n)) {
+            bin->assign(blob.begin() + sizeof hd, blob.end());
+            from_disk = true;
+        }
+    }
+    if (!from_disk) {
         if (cached) *cached = false;
         rc = cc_jit_nvrtc(src, bin.get(), err);
         if (rc) return rc;
@@ -763,6 +790,12 @@ static int build_cubin(const cc_decoded &dec, const cc_jit_cfg &cfg, int sink, C
             const std::string tmp = path + ".tmp" + std::to_string((long)getpid());
             std::ofstream f(tmp.c_str(), std::ios::binary);
             if (f) {
+                CacheHeader hd;
+                std::memcpy(hd.magic, "CCB2CUB1", 8);
+                hd.key = key;
+                hd.bytes = bin->size();
+                hd.checksum = fnv1a_bytes(bin->data(), bin->size());
+                f.write(reinterpret_cast<const char *>(&hd), sizeof hd);
                 f.write(bin->data(), (std::streamsize)bin->size());
                 f.close();
                 if (!f || rename(tmp.c_str(), path.c_str()) != 0) remove(tmp.c_str());
@@ -793,16 +826,9 @@ static int load_cubin(cc_program *prog, int sink, const Cubin &bin, const cc_jit
         cudaLibraryUnload(lib);
         return CC_ERR_CUDA;
     }
-    if (smem_bytes > 0) {
-        ce = cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        if (ce != cudaSuccess) {
-            *err = std::string("cudaFuncSetAttribute(MaxDynamicSharedMemorySize): ") + cudaGetErrorString(ce);
-            cudaLibraryUnload(lib);
-            return CC_ERR_CUDA;
-        }
-    }
     if (prog->jit_library[sink]) cudaLibraryUnload((cudaLibrary_t)prog->jit_library[sink]);
     prog->jit_smem[sink] = smem_bytes;
+    for (int d = 0; d < CC_MAX_DEVICES; ++d) prog->jit_attr_done[sink][d] = false;
     prog->jit_library[sink] = (void *)lib;
     prog->jit_kernel[sink] = (void *)kern;
     prog->jit_cfg[sink] = cfg;
@@ -915,10 +941,23 @@ void cc_jit_release(cc_program *prog)
     prog->jit_cubin_bytes = 0;
 }
 
-int cc_jit_launch(const cc_program *prog, int sink, const cc_eval_args &a, void *stream)
+// MaxDynamicSharedMemorySize is kept per device: set it the first time a device launches the kernel
+static int ensure_smem_attr(const cc_program *prog, int sink, int dev_index)
+{
+    cc_program *p = const_cast<cc_program *>(prog);
+    if (p->jit_attr_done[sink][dev_index] || p->jit_smem[sink] == 0) return 0;
+    cudaError_t ce = cudaFuncSetAttribute((const void *)p->jit_kernel[sink], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)p->jit_smem[sink]);
+    if (ce != cudaSuccess) return (int)ce;
+    p->jit_attr_done[sink][dev_index] = true;
+    return 0;
+}
+
+int cc_jit_launch(const cc_program *prog, int sink, const cc_eval_args &a, void *stream, int dev_index)
 {
     const uint32_t grid = a.n_blocks * a.tiles_per_block;
     if (grid == 0) return 0;
+    if (int e = ensure_smem_attr(prog, sink, dev_index)) return e;
     void *args[] = {(void *)&a};
     return (int)cudaLaunchKernel((const void *)prog->jit_kernel[sink], dim3(grid), dim3(prog->jit_cfg[sink].threads),
                                  args, prog->jit_smem[sink], (cudaStream_t)stream);
@@ -932,8 +971,9 @@ int cc_jit_source(const cc_decoded &dec, int pts, unsigned sink_mask, std::strin
     return generate(dec, cc_jit_default_cfg(dec, pts), sink_mask, src, nullptr, err);
 }
 
-int cc_jit_launch_render(const cc_program *prog, int sink, const cc_render_args &a, void *stream)
+int cc_jit_launch_render(const cc_program *prog, int sink, const cc_render_args &a, void *stream, int dev_index)
 {
+    if (int e = ensure_smem_attr(prog, sink, dev_index)) return e;
     const uint32_t threads = (uint32_t)prog->jit_cfg[sink].threads;
     const uint32_t tiles = ((a.w + 7) / 8) * ((a.h + 3) / 4);  // one warp each (cc_render.cuh)
     const uint32_t grid = (tiles + threads / 32 - 1) / (threads / 32);

@@ -576,7 +576,7 @@ static int launch_render(bool ray, const cc_render_args &a, size_t smem, cudaStr
 
 // prog_space 1 = constant bank (program already uploaded by the caller), 2 = shared copy,
 // 0 = scene-specialised kernel of `prog`
-int cc_launch_render(int ray, int prog_space, const cc_program *prog, const cc_render_launch &r, void *stream)
+int cc_launch_render(int ray, int prog_space, const cc_program *prog, const cc_render_launch &r, void *stream, int dev_index)
 {
     cc_render_args a;
     a.code = r.code; a.code_words = r.code_words; a.n_slots = r.n_slots;
@@ -588,7 +588,7 @@ int cc_launch_render(int ray, int prog_space, const cc_program *prog, const cc_r
     a.min_distance = r.min_distance; a.max_distance = r.max_distance; a.floor_z = r.floor_z;
     a.step_size = r.step_size; a.options = r.options; a.w = r.w; a.h = r.h; a.out = r.out;
     a.eval_count = r.eval_count;
-    if (prog_space == 0) return cc_jit_launch_render(prog, ray ? CC_SINK_RAY : CC_SINK_BITMAP, a, stream);
+    if (prog_space == 0) return cc_jit_launch_render(prog, ray ? CC_SINK_RAY : CC_SINK_BITMAP, a, stream, dev_index);
     cc_launch_cfg cfg{1, prog_space};
     const size_t smem = cc_eval_smem_bytes(cfg, a.n_slots, a.code_words);
     return prog_space == 1 ? launch_render<0>(ray != 0, a, smem, (cudaStream_t)stream)
@@ -662,34 +662,57 @@ __global__ void cc_mass_expand_children_kernel(const double *__restrict__ parent
 }
 
 // mass_properties.py:119-148: per block, index sums -> the ten integrals, in float64 with the
-// reference's expression order; blocks are then combined by a fixed-shape (deterministic)
-// reduction: strided Kahan partials per thread, pairwise tree across the CTA, Kahan into the
-// running totals acc[0..9] (+ compensation acc[10..19]).
+// reference's expression order.  The reference then adds the blocks up with a Kahan sum in job
+// order; here every block's ten values go into an EXACT accumulator instead, so that the total
+// does not depend on the order of the blocks, on how a level is chunked, or on how the hierarchy
+// is dealt to GPUs and ranks: value i is truncated to a multiple of 2^q.e[i] (a quantum ~2^-97 of
+// a bound on the integral, cc_api.cpp mass_quanta()), the 128-bit integer is cut into four 32-bit
+// limbs, limbs are summed as signed 64-bit integers (warp shuffle tree, one atomic per warp and
+// limb).  Integer addition is associative, so one GPU, eight GPUs in one process and eight ranks
+// with an int64 all-reduce produce the same bits.
+__device__ __forceinline__ void cc_to_limbs(double v, int quantum_exp, long long (&limb)[4], unsigned &overflow)
+{
+    const long long bits = __double_as_longlong(v);
+    int ex = (int)((bits >> 52) & 0x7ff);
+    unsigned long long m = (unsigned long long)bits & ((1ull << 52) - 1);
+    if (ex == 0) ex = 1; else m |= 1ull << 52;  // value = m * 2^(ex - 1075)
+    const int sh = (ex - 1075) - quantum_exp;
+    unsigned __int128 t = 0;
+    if (ex == 0x7ff || sh > 70) {  // inf / nan / beyond the stated bound
+        if (m != 0 || ex == 0x7ff) overflow = 1u;
+    } else if (sh >= 0) {
+        t = (unsigned __int128)m << sh;
+    } else if (sh > -64) {
+        t = (unsigned __int128)(m >> (-sh));
+    }
+    const long long sign = bits < 0 ? -1 : 1;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) limb[k] = sign * (long long)((unsigned long long)(t >> (32 * k)) & 0xffffffffull);
+}
+
 __global__ void __launch_bounds__(256) cc_mass_integrals_kernel(const double *__restrict__ corners,
                                                                 const uint32_t *__restrict__ sums,
-                                                                uint32_t n_blocks, double s,
-                                                                double *__restrict__ acc)
+                                                                uint32_t n_blocks, double s, cc_mass_quanta qe,
+                                                                unsigned long long *__restrict__ acc)
 {
-    __shared__ double red[256];
+    const uint32_t b = blockIdx.x * 256u + threadIdx.x;
     const double s2 = __dmul_rn(s, s);
     const double s3 = __dmul_rn(s, s2);
     const double half = __ddiv_rn(s, 2.0);
     const double s2_12 = __ddiv_rn(s2, 12.0);
-    double part[10], comp[10];
+    double v[10];
 #pragma unroll
-    for (int i = 0; i < 10; ++i) { part[i] = 0.0; comp[i] = 0.0; }
-    for (uint32_t b = threadIdx.x; b < n_blocks; b += 256) {
+    for (int i = 0; i < 10; ++i) v[i] = 0.0;
+    if (b < n_blocks && sums[(size_t)b * 10 + 9] != 0) {
         const uint32_t *q = sums + (size_t)b * 10;
         const double sxx = q[0], sxy = q[1], sxz = q[2], sx = q[3], syy = q[4], syz = q[5], sy = q[6],
                      szz = q[7], sz = q[8], n = q[9];
-        if (q[9] == 0) continue;
         const double bx = __dadd_rn(corners[3 * b + 0], half);
         const double by = __dadd_rn(corners[3 * b + 1], half);
         const double bz = __dadd_rn(corners[3 * b + 2], half);
         const double tx = s * sx, ty = s * sy, tz = s * sz;
         const double txx = s2 * sxx, tyy = s2 * syy, tzz = s2 * szz;
         const double txy = s2 * sxy, txz = s2 * sxz, tyz = s2 * syz;
-        double v[10];
         v[0] = s3 * n;
         v[1] = s3 * (n * bx + tx);
         v[2] = s3 * (n * by + ty);
@@ -700,29 +723,22 @@ __global__ void __launch_bounds__(256) cc_mass_integrals_kernel(const double *__
         v[7] = s3 * (n * bx * by + bx * ty + by * tx + txy);
         v[8] = s3 * (n * bx * bz + bx * tz + bz * tx + txz);
         v[9] = s3 * (n * by * bz + by * tz + bz * ty + tyz);
+    }
+    unsigned overflow = 0;
+    const uint32_t lane = threadIdx.x & 31;
 #pragma unroll
-        for (int i = 0; i < 10; ++i) {  // util/math.py:12-17
-            double y = v[i] - comp[i];
-            double t = part[i] + y;
-            comp[i] = (t - part[i]) - y;
-            part[i] = t;
-        }
-    }
     for (int i = 0; i < 10; ++i) {
-        red[threadIdx.x] = part[i];
-        __syncthreads();
-        for (int d = 128; d > 0; d >>= 1) {
-            if (threadIdx.x < d) red[threadIdx.x] = red[threadIdx.x] + red[threadIdx.x + d];
-            __syncthreads();
+        long long limb[4];
+        cc_to_limbs(v[i], qe.e[i], limb, overflow);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            long long x = limb[k];
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) x += __shfl_down_sync(0xffffffffu, x, d);
+            if (lane == 0 && x != 0) atomicAdd(acc + 4 * i + k, (unsigned long long)x);
         }
-        if (threadIdx.x == 0) {
-            double y = red[0] - acc[10 + i];
-            double t = acc[i] + y;
-            acc[10 + i] = (t - acc[i]) - y;
-            acc[i] = t;
-        }
-        __syncthreads();
     }
+    if (__any_sync(0xffffffffu, overflow != 0) && lane == 0) atomicAdd(acc + 40, 1ull);
 }
 
 int cc_launch_make_blocks_subdiv(const int64_t *d_int_corners, uint32_t n, cc_level_geom g,
@@ -764,9 +780,10 @@ int cc_launch_mass_expand_children(const double *d_parent_corners, const uint32_
 }
 
 int cc_launch_mass_integrals(const double *d_corners, const uint32_t *d_sums, uint32_t n_blocks, double s,
-                             double *d_integrals, void *stream)
+                             cc_mass_quanta q, unsigned long long *d_limbs, void *stream)
 {
     if (!n_blocks) return 0;
-    cc_mass_integrals_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d_corners, d_sums, n_blocks, s, d_integrals);
+    cc_mass_integrals_kernel<<<(n_blocks + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_corners, d_sums, n_blocks, s, q,
+                                                                                      d_limbs);
     return (int)cudaGetLastError();
 }

@@ -30,12 +30,10 @@ def _eval(shape, corner, step, dims, layout, x_offset, out, to_host):
         else:
             want_shape, dtype = (ny, nx, nz), np.float32
         if out is None:
-            holder = Buffer.__new__(Buffer)  # pinned host array without a device twin
+            # pinned host array without a device twin; the array's buffer owns the allocation and
+            # returns it to the library's page-locked pool when the last view is collected
             from .cl_util.buffer import _Pinned
-            pin = _Pinned(nx * ny * nz * np.dtype(dtype).itemsize)
-            out = pin.array(dtype, want_shape)
-            _PINS[id(out)] = pin
-            del holder
+            out = _Pinned(nx * ny * nz * np.dtype(dtype).itemsize).array(dtype, want_shape)
         if out.nbytes < nx * ny * nz * np.dtype(dtype).itemsize:
             raise RuntimeError("Not enough space to store the grid")
         _lib.check(_lib.lib().cc_grid_eval_to_host(program.handle, _lib.f3(corner), float(np.float32(step)),
@@ -48,12 +46,9 @@ def _eval(shape, corner, step, dims, layout, x_offset, out, to_host):
     return out
 
 
-_PINS = {}
-
-
 def release_host_grid(arr):
-    """Free the pinned memory behind an array returned by grid_eval(out=None)."""
-    _PINS.pop(id(arr), None)
+    """Deprecated no-op: an array returned by grid_eval(out=None) owns its page-locked memory and
+    gives it back when it is garbage collected."""
 
 
 def grid_eval(shape, corner, step, dims, x_offset=0, out=None, device_out=None):

@@ -22,14 +22,38 @@ class MassProperties(collections.namedtuple("MassProperties", "volume centroid i
     __slots__ = ()
 
 
-def mass_integrals(program, box_a, resolution, block_sizes, rank=0, world=1):
-    """The ten integrals (one,x,y,z,xx,yy,zz,xy,xz,yz) over this rank's share, + stats."""
-    integrals = (ctypes.c_double * 10)()
-    stats = (ctypes.c_uint64 * 4)()
+STAT_NAMES = ("launches", "cells", "blocks", "levels", "dealt_blocks", "devices", "cells_busiest_device",
+              "cells_idlest_device")
+
+
+def mass_limbs(program, box_a, resolution, block_sizes, rank=0, world=1):
+    """This rank's share of the ten integrals as the library's exact accumulator: (limbs int64[40],
+    exponents int32[10], stats dict).  Limbs of different ranks add up exactly (integers);
+    limbs_to_integrals() converts the total."""
+    limbs = (ctypes.c_int64 * 40)()
+    exps = (ctypes.c_int32 * 10)()
+    stats = (ctypes.c_uint64 * 8)()
     a = (ctypes.c_double * 3)(float(box_a[0]), float(box_a[1]), float(box_a[2]))
-    _lib.check(_lib.lib().cc_mass_properties(program.handle, a, float(resolution), _levels(block_sizes),
-                                             len(block_sizes), int(rank), int(world), integrals, stats))
-    return np.array(integrals[:], dtype=np.float64), tuple(int(s) for s in stats)
+    _lib.check(_lib.lib().cc_mass_properties_exact(program.handle, a, float(resolution), _levels(block_sizes),
+                                                   len(block_sizes), int(rank), int(world), limbs, exps, stats))
+    return (np.array(limbs[:], dtype=np.int64), np.array(exps[:], dtype=np.int32),
+            dict(zip(STAT_NAMES, (int(v) for v in stats))))
+
+
+def limbs_to_integrals(limbs, exponents):
+    """Exact accumulator -> the ten float64 integrals (one rounding each)."""
+    l = (ctypes.c_int64 * 40)(*[int(v) for v in limbs])
+    e = (ctypes.c_int32 * 10)(*[int(v) for v in exponents])
+    out = (ctypes.c_double * 10)()
+    _lib.check(_lib.load().cc_mass_limbs_to_integrals(l, e, out))
+    return np.array(out[:], dtype=np.float64)
+
+
+def mass_integrals(program, box_a, resolution, block_sizes, rank=0, world=1):
+    """The ten integrals (one,x,y,z,xx,yy,zz,xy,xz,yz) over this rank's share, + stats
+    (launches, cells, blocks, levels)."""
+    limbs, exps, stats = mass_limbs(program, box_a, resolution, block_sizes, rank, world)
+    return limbs_to_integrals(limbs, exps), tuple(stats[k] for k in STAT_NAMES[:4])
 
 
 def finish(integrals):
@@ -54,10 +78,13 @@ def finish(integrals):
     return MassProperties(volume, centroid, inertia_tensor)
 
 
-def mass_properties(shape, resolution, grid_size=None, group=None):
+def mass_properties(shape, resolution, grid_size=None, group=None, stats=None):
     """mass_properties.py:30.  With `group` (a torch.distributed process group, or True
-    for the default group) the hierarchy is sharded over its ranks and the ten integrals
-    are all-reduced; every rank returns the same result."""
+    for the default group) the hierarchy is sharded over its ranks and the exact accumulator
+    of the ten integrals is all-reduced (40 int64): every rank returns the same result, and it
+    is bit-identical to the unsharded one.  One process that drives several GPUs
+    (_lib.init_devices / CODECAD_B200_DEVICES) shards inside the library with no argument here.
+    `stats` (a dict) receives this rank's counters."""
     if grid_size is None:
         grid_size = 64
 
@@ -77,10 +104,25 @@ def mass_properties(shape, resolution, grid_size=None, group=None):
         pg = None if group is True else group
         rank, world = dist.get_rank(pg), dist.get_world_size(pg)
 
-    integrals, _ = mass_integrals(program_buffer, box_a, resolution, block_sizes, rank, world)
+    limbs, exps, st = mass_limbs(program_buffer, box_a, resolution, block_sizes, rank, world)
+    if stats is not None:
+        stats.update(st)
     if world > 1:
-        integrals = allreduce_integrals(integrals, None if group is True else group)
-    return finish(integrals)
+        limbs = allreduce_limbs(limbs, None if group is True else group)
+    return finish(limbs_to_integrals(limbs, exps))
+
+
+def allreduce_limbs(limbs, group=None):
+    """Sum the exact accumulators (40 int64) over the ranks — the only data that crosses NVLink on
+    this path.  Integer sums are exact and order-independent, so every rank converts the same total.
+    NCCL needs the tensor on the GPU; gloo (CPU tests) does not."""
+    import torch
+    import torch.distributed as dist
+    t = torch.from_numpy(np.ascontiguousarray(limbs, dtype=np.int64))
+    if dist.get_backend(group) == "nccl":
+        t = t.cuda()
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy()
 
 
 def allreduce_integrals(integrals, group=None):

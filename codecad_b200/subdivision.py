@@ -15,49 +15,36 @@ from .geometry import BoundingBox, Vector, as_vector
 from .nodes import make_program_buffer
 
 
-def _round_up_to(x, y):
-    return ((x + y - 1) // y) * y
-
-
-def _clamp(v, lower, upper):
-    return max(lower, min(v, upper))
-
-
 def calculate_block_sizes(box, dimension, resolution, grid_size, overlap, level_size_multiplier=1):
-    """subdivision.py:116-166 — top..leaf list of (cell_size, Vector level_dims)."""
-    if grid_size % level_size_multiplier != 0:
+    """Level plan of the hierarchy, top level first: [(cell size in leaf cells, Vector grid dims), ...].
+    Same contract as the reference's planner (subdivision.py:116-166; its 80 property cases are
+    tests/test_host_logic.py): the leaf level has cell size 1; each level above multiplies the
+    cell size by grid_size, except that with `overlap` a leaf block advances by grid_size - 1
+    cells (neighbouring leaf blocks share a layer of samples); every level below the top is a
+    full grid (flat in z for 2-D shapes); the top level is only as large as the box needs,
+    rounded up to level_size_multiplier."""
+    if grid_size % level_size_multiplier:
         raise ValueError("Grid size must be divisible by level_size_multiplier")
-
-    block_sizes = []
+    assert dimension in (2, 3)
+    lo, hi = as_vector(box[0]), as_vector(box[1])
+    full = (grid_size, grid_size, grid_size)
     if dimension == 2:
-        level_size = Vector(grid_size, grid_size, 1)
-        box = BoundingBox(as_vector(box[0]).flattened(), as_vector(box[1]).flattened())
-    elif dimension == 3:
-        level_size = Vector.splat(grid_size)
-    else:
-        assert False
-
-    box_int_size = ((as_vector(box[1]) - as_vector(box[0])) / resolution).applyfunc(math.ceil)
-    box_max_int_size = box_int_size.max()
-    cell_size = 1
-
-    while True:
-        block_sizes.append((cell_size, level_size))
-        overlap_delta = 1 if overlap and len(block_sizes) == 1 else 0
-        next_cell_size = cell_size * (grid_size - overlap_delta)
-        if next_cell_size >= box_max_int_size:
-            break
-        cell_size = next_cell_size
-
-    block_sizes[-1] = (
-        cell_size,
-        Vector(*(
-            _clamp(_round_up_to(math.ceil(x) + overlap_delta, level_size_multiplier), 1, s)
-            for x, s in zip(box_int_size / cell_size, level_size)
-        )),
-    )
-    block_sizes.reverse()
-    return block_sizes
+        lo, hi = lo.flattened(), hi.flattened()
+        full = (grid_size, grid_size, 1)
+    samples = [math.ceil(extent / resolution) for extent in (hi - lo)]  # leaf cells per axis
+    # cell sizes from the leaf upwards, until one block of the level spans the longest axis
+    cells, factor = [1], (grid_size - 1 if overlap else grid_size)
+    while cells[-1] * factor < max(samples):
+        cells.append(cells[-1] * factor)
+        factor = grid_size
+    top = cells.pop()
+    shared_layer = 1 if (overlap and not cells) else 0  # a single-level plan keeps the extra sample layer
+    top_dims = []
+    for n, limit in zip(samples, full):
+        want = math.ceil(n / top) + shared_layer
+        want = -(-want // level_size_multiplier) * level_size_multiplier
+        top_dims.append(min(max(want, 1), limit))
+    return [(top, Vector(*top_dims))] + [(c, Vector(*full)) for c in reversed(cells)]
 
 
 def _levels(block_sizes):
@@ -84,6 +71,16 @@ def subdivide_int_corners(program, origin, resolution, block_sizes, dimension, r
         return np.ctypeslib.as_array(out, shape=(n, 3)).copy()
     finally:
         _lib.lib().cc_free(out)
+
+
+def sort_leaf_corners(corners, block_sizes):
+    """Put int corners gathered from several ranks into the order one GPU lists them (level by
+    level: parent block order, then INDEX3 cell order); returns a new int64 [n][3] array."""
+    c = np.ascontiguousarray(corners, dtype=np.int64).reshape(-1, 3).copy()
+    if len(c) > 1 and len(block_sizes) >= 2:
+        _lib.check(_lib.load().cc_sort_leaf_corners(c.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), len(c),
+                                                    _levels(block_sizes), len(block_sizes)))
+    return c
 
 
 class LeafBlocks(collections.abc.Sequence):

@@ -8,9 +8,9 @@
  *
  * Conventions: plain pointers and sizes only.  Every function returning `int` returns
  * 0 on success and a negative cc_status on failure; cc_last_error() then returns a
- * thread-local message.  One process drives one GPU (one rank per GPU under
- * torchrun); the library owns one CUDA context, one compute stream and one copy
- * stream.  Host pointers are caller-owned; device pointers and handles are
+ * thread-local message.  One process drives one GPU (cc_init; one rank per GPU under
+ * torchrun) or several (cc_init_devices); per device the library owns one compute stream and
+ * one copy stream.  Host pointers are caller-owned; device pointers and handles are
  * library-owned until the matching *_free / *_destroy.  There is NO CPU fallback: with
  * no usable CUDA device cc_init() fails and every other call fails after it.
  */
@@ -44,6 +44,15 @@ typedef struct cc_event cc_event;     /* completion marker on a library stream  
 
 /* ---- context: replaces OpenCLManager.__init__  cl_util/opencl_manager.py:87-98 ------- */
 int cc_init(int device);            /* idempotent for the same device */
+/* Several GPUs driven by ONE process (the reference's user is a single Python script with one
+ * context and one queue, cl_util/opencl_manager.py:89-98; SURVEY.md 8(b) asks for exactly this
+ * entry point).  devices[0] is the primary device: buffers, events and every per-launch kernel
+ * call live there, as after cc_init(devices[0]).  The calls that shard — cc_grid_eval_to_host
+ * (x-slabs), cc_subdivide and cc_mass_properties (blocks of the hierarchy) — then use all n
+ * devices, one worker thread, compute stream and copy stream per device, programs replicated on
+ * first use, and return exactly what one device returns.  May be called after cc_init(devices[0]). */
+int cc_init_devices(const int *devices, int n);
+int cc_active_devices(void);        /* devices initialised in this process (0 before cc_init)  */
 void cc_shutdown(void);
 int cc_device_count(void);          /* 0 when no CUDA device/driver is usable */
 const char *cc_last_error(void);
@@ -201,20 +210,38 @@ typedef struct cc_level {
 
 /* subdivision()  subdivision.py:169-253 for n_levels >= 2.  origin = expanded bbox.a,
  * float64 like the reference's host math.  Returns the int corners (resolution units)
- * of the leaf blocks owned by `rank` of `world` (blocks of the first refined level are
- * dealt round-robin; every rank evaluates the tiny top level).  *out_corners is a
- * malloc'ed int64[n][3] released with cc_free. */
+ * of the leaf blocks owned by `rank` of `world`: the hits of the level that feeds the last
+ * classified level are dealt round-robin, the (tiny) levels above it are evaluated by everyone.
+ * With several devices (cc_init_devices) the rank's share is dealt on over them and merged back
+ * into the order one device produces.  *out_corners is a malloc'ed int64[n][3] released with
+ * cc_free.  cc_sort_leaf_corners puts a union of per-rank lists into that same order (level by
+ * level: parent block order, then INDEX3 cell order), so that results can be compared as arrays. */
 int cc_subdivide(const cc_program *prog, const double origin[3], double resolution,
                  const cc_level *levels, uint32_t n_levels, int dimension,
                  uint32_t rank, uint32_t world, int64_t **out_corners, uint64_t *out_count);
+int cc_sort_leaf_corners(int64_t *corners, uint64_t n, const cc_level *levels, uint32_t n_levels);
 
-/* mass_properties()  mass_properties.py:30-177: returns the ten integrals
- * (one,x,y,z,xx,yy,zz,xy,xz,yz) over the part of the hierarchy owned by `rank`; the
- * caller sums them over ranks (NCCL all-reduce of 10 doubles) and finishes with
- * mass_properties.py:179-229.  stats[0..3] = launches, evaluated cells, blocks, levels. */
+/* mass_properties()  mass_properties.py:30-177: the ten integrals (one,x,y,z,xx,yy,zz,xy,xz,yz)
+ * over the part of the hierarchy owned by `rank` of `world` (all of it for world = 1), shared out
+ * over the devices of cc_init_devices; finish with mass_properties.py:179-229.
+ * stats[0..3] = launches, evaluated cells, blocks, levels.
+ *
+ * Exactness.  Each block's ten float64 values (mass_properties.py:139-148, the reference's
+ * expression order) are added in an exact fixed-point accumulator instead of the reference's
+ * Kahan sum in job order (util/math.py:4-21), so the result does not depend on the order of the
+ * blocks nor on how they are dealt to devices and ranks: 1, 2, 4 and 8 GPUs return the same bits.
+ * cc_mass_properties_exact returns the accumulator itself: limbs[10][4] = signed sums of the
+ * 32-bit limbs of trunc(value / 2^exponents[i]); ranks add their limbs (an int64 all-reduce, NCCL
+ * or gloo) and convert once with cc_mass_limbs_to_integrals.  exponents depend on the arguments
+ * only.  stats[4..7] = blocks of the dealt level owned, devices used, cells evaluated by the
+ * busiest and by the least busy device. */
 int cc_mass_properties(const cc_program *prog, const double box_a[3], double resolution,
                        const cc_level *levels, uint32_t n_levels,
                        uint32_t rank, uint32_t world, double integrals[10], uint64_t stats[4]);
+int cc_mass_properties_exact(const cc_program *prog, const double box_a[3], double resolution,
+                             const cc_level *levels, uint32_t n_levels, uint32_t rank, uint32_t world,
+                             int64_t limbs[40], int32_t exponents[10], uint64_t stats[8]);
+int cc_mass_limbs_to_integrals(const int64_t limbs[40], const int32_t exponents[10], double integrals[10]);
 
 /* matplotlib_slice  rendering/matplotlib_slice.cl:1-20 (global size (width, height),
  * rendering/matplotlib_slice.py:44-52): d_out[(x + y*width)*3 + 0..2] = distance, gradient x,

@@ -72,8 +72,50 @@ def test_two_gpu_sharding(tmp_path):
     want = np.concatenate([[single.volume], list(single.centroid), single.inertia_tensor.ravel()])
     r0, r1 = np.load(tmp_path / "mp_r0.npy"), np.load(tmp_path / "mp_r1.npy")
     assert np.array_equal(r0, r1)
-    assert np.allclose(r0, want, rtol=1e-12, atol=0)
+    assert np.array_equal(r0, want), "the int64 all-reduce of the exact accumulator is bit-identical to one GPU"
 
     whole = codecad_b200.subdivision(S["cfg_csg_example"].compiled(), 100 / 128, True, 16)[2]
     got = np.concatenate([np.load(tmp_path / ("sub_r%d.npy" % r)) for r in range(2)])
     assert sorted(map(tuple, got.tolist())) == sorted(tuple(b[3]) for b in whole)
+
+
+SINGLE_PROCESS = r"""
+import sys, numpy as np
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(root)r + "/tests")
+import codecad_b200
+from codecad_b200 import _lib
+from scenes import load_scenes
+S = load_scenes()
+air, csg, plan = S["cfg_airfoil"].compiled(), S["cfg_csg_example"].compiled(), S["cfg_planetary"]
+_lib.init(0)
+one_mp = codecad_b200.mass_properties(air, 0.5, 64)
+one_sub = codecad_b200.subdivision(csg, 100 / 512, True, 16)[2]
+corner, step = plan.grid(48)
+one_grid = np.array(codecad_b200.grid_eval(plan.compiled(), corner, step, (45, 16, 32)))
+_lib.init_devices(list(range(%(n)d)))          # the same process now drives every GPU
+assert _lib.active_devices() == %(n)d
+st = {}
+all_mp = codecad_b200.mass_properties(air, 0.5, 64, stats=st)
+all_sub = codecad_b200.subdivision(csg, 100 / 512, True, 16)[2]
+all_grid = np.array(codecad_b200.grid_eval(plan.compiled(), corner, step, (45, 16, 32)))
+assert st["devices"] == %(n)d and st["cells_idlest_device"] > 0, st
+assert all_mp.volume == one_mp.volume and tuple(all_mp.centroid) == tuple(one_mp.centroid)
+assert np.array_equal(all_mp.inertia_tensor, one_mp.inertia_tensor)
+assert np.array_equal(all_sub.int_corners, one_sub.int_corners) and np.array_equal(all_sub.corners, one_sub.corners)
+assert all_grid.tobytes() == one_grid.tobytes()
+print("single-process ok", st)
+"""
+
+
+def test_one_process_drives_all_gpus(tmp_path):
+    """cc_init_devices: the unmodified module calls use every GPU of the box from ONE process and
+    return what one GPU returns, bit for bit."""
+    import subprocess
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs two GPUs")
+    r = subprocess.run([sys.executable, "-c", SINGLE_PROCESS % {"root": ROOT, "n": n}], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "single-process ok" in r.stdout

@@ -229,3 +229,63 @@ def test_leaf_blocks_sequence_is_the_reference_list():
         blocks[3]
     assert np.array_equal(block_corners(blocks), pos) and np.array_equal(block_corners(want), pos)
     assert len(LeafBlocks(dims, pos[:0], 0.25, ints[:0], 1)) == 0 and not list(LeafBlocks(dims, pos[:0], 0.25, ints[:0], 1))
+
+
+# ---- exact accumulator of the mass integrals and the canonical leaf order (host-only entry points) ----
+
+def _to_limbs(value, exponent):
+    """trunc(value / 2^exponent) cut into four signed 32-bit limbs (what cc_mass_integrals_kernel adds up)."""
+    from fractions import Fraction
+    t = int(Fraction(value) / Fraction(2) ** exponent)        # int() truncates toward zero
+    sign, mag = (-1 if t < 0 else 1), abs(t)
+    return [sign * ((mag >> (32 * k)) & 0xFFFFFFFF) for k in range(4)]
+
+
+def test_limb_sums_convert_exactly_and_order_independently():
+    import random
+    from fractions import Fraction
+    import importlib
+    mpm = importlib.import_module("codecad_b200.mass_properties")
+    rng = random.Random(7)
+    exps = np.array([-60, -55, -55, -55, -50, -50, -50, -50, -50, -50], dtype=np.int32)
+    values = [[rng.uniform(-1, 1) * 10 ** rng.uniform(-6, 6) for _ in range(10)] for _ in range(300)]
+    def total(rows):
+        limbs = np.zeros(40, dtype=np.int64)
+        for row in rows:
+            for i, v in enumerate(row):
+                limbs[4 * i:4 * i + 4] += np.array(_to_limbs(v, int(exps[i])), dtype=np.int64)
+        return limbs
+    a = total(values)
+    rng.shuffle(values)
+    b = total(values[:100]) + total(values[100:])            # another order, another partition
+    assert np.array_equal(a, b)
+    got = mpm.limbs_to_integrals(a, exps)
+    for i in range(10):
+        exact = sum(Fraction(int(Fraction(row[i]) / Fraction(2) ** int(exps[i]))) for row in values) * Fraction(2) ** int(exps[i])
+        assert got[i] == float(exact)                          # one correctly rounded conversion
+        assert abs(got[i] - sum(row[i] for row in values)) <= 1e-9 * sum(abs(row[i]) for row in values)
+
+
+def test_sort_leaf_corners_restores_the_single_device_order():
+    import random
+    from codecad_b200.geometry import Vector
+    from codecad_b200.subdivision import sort_leaf_corners
+    rng = random.Random(3)
+    for grid, overlap in ((16, True), (8, False), (5, True)):
+        leaf_factor = grid - 1 if overlap else grid
+        plan = [(leaf_factor * grid, Vector(3, 2, 3)), (leaf_factor, Vector.splat(grid)), (1, Vector.splat(grid))]
+        # breadth-first production: level-0 hits in INDEX3 order, then per parent the level-1 hits in INDEX3 order
+        def hits(dims, frac):
+            cells = [(x, y, z) for x in range(dims[0]) for y in range(dims[1]) for z in range(dims[2])]
+            return [c for c in cells if rng.random() < frac]
+        corners = []
+        for c0 in hits((3, 2, 3), 0.6):
+            for c1 in hits((grid,) * 3, 0.05):
+                corners.append([c0[k] * plan[0][0] + c1[k] * plan[1][0] for k in range(3)])
+        want = np.array(corners, dtype=np.int64)
+        order = list(range(len(want)))
+        rng.shuffle(order)
+        shuffled = want[order]
+        # dealing to ranks permutes the list; the sort must undo any permutation
+        assert np.array_equal(sort_leaf_corners(shuffled, plan), want)
+        assert np.array_equal(sort_leaf_corners(want[::-1], plan), want)
