@@ -36,6 +36,7 @@ struct Context {
     uint64_t launches = 0, points = 0;
     int pts = 0, prog_space = 0;  // tuning overrides, 0 = auto
     int jit_mode = 1;             // 0 never, 1 background (default), 2 compile at first use and wait
+    int forest_mode = 1;          // 1: dense grids of union-forest programs use the culling kernel (cc_forest.cu)
     uint32_t jit_max_ops = 4096;  // programs longer than this are not specialised automatically
     uint64_t constant_program = 0;  // id of the program in this device's __constant__ window
     int index = 0;                  // position in g_ctx
@@ -304,8 +305,61 @@ bool jit_ready(cc_program *p, int sink)
     return r == 1;
 }
 
+// tables of a union-forest program on the current device (replicated on first use)
+int forest_on_device(const cc_program *prog, cc_forest_launch *out)
+{
+    cc_program *p = const_cast<cc_program *>(prog);
+    const cc_forest &f = p->dec.forest;
+    void *&d = p->d_forest[g.index];
+    const size_t nb = f.bounds.size() * 4, ne = f.events.size() * 4;
+    if (!d) {
+        cudaError_t e = cudaMalloc(&d, nb + ne);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d, f.bounds.data(), nb, cudaMemcpyHostToDevice, g.compute);
+        if (e == cudaSuccess) e = cudaMemcpyAsync((char *)d + nb, f.events.data(), ne, cudaMemcpyHostToDevice, g.compute);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(g.compute);
+        if (e != cudaSuccess) {
+            if (d) cudaFree(d);
+            d = nullptr;
+            return cuda_fail(e, "forest table upload");
+        }
+    }
+    out->bounds = (const float *)d;
+    out->events = (const uint32_t *)((char *)d + nb);
+    out->n_leaves = f.n_leaves;
+    out->n_events = f.n_events;
+    out->max_depth = f.max_depth;
+    out->rmax = f.rmax;
+    return CC_OK;
+}
+
+bool forest_applies(int sink_kind, const cc_program *prog, const cc_eval_args &a)
+{
+    if (!g.forest_mode || sink_kind != CC_SINK_FLOAT4 || a.points || a.blocks) return false;
+    const cc_forest &f = prog->dec.forest;
+    return f.enabled && cc_forest_smem_bytes(f) <= (size_t)g.prop.sharedMemPerBlockOptin && f.n_events <= 8192;
+}
+
+int launch_forest(const cc_program *prog, cc_eval_args &a, uint64_t points)
+{
+    cc_forest_launch f;
+    int rc = forest_on_device(prog, &f);
+    if (rc) return rc;
+    // error budget of the primitives' bounds: 2^-16 of the magnitudes that enter their arithmetic
+    const double ext[3] = {std::fabs((double)a.step) * (double)(a.nx + a.x_offset), std::fabs((double)a.step) * a.ny,
+                           std::fabs((double)a.step) * a.nz};
+    const double pmax = std::max(std::fabs((double)a.cx) + ext[0], std::max(std::fabs((double)a.cy) + ext[1], std::fabs((double)a.cz) + ext[2]));
+    f.slack = (float)(((double)prog->dec.forest.err_a + (double)prog->dec.forest.err_b * pmax) / 65536.0);
+    if (!std::isfinite(f.slack)) return fail(CC_ERR_INVALID_ARGUMENT, "grid coordinates out of range");
+    int e = cc_launch_forest(a, f, g.compute);
+    if (e) return cuda_fail((cudaError_t)e, "cc_forest_kernel launch");
+    g.launches += 1;
+    g.points += points;
+    return CC_OK;
+}
+
 int launch(int sink_kind, const cc_program *prog, cc_eval_args &a, uint64_t points)
 {
+    if (forest_applies(sink_kind, prog, a)) return launch_forest(prog, a, points);
     // which specialised kernel serves the launch: point lists have their own (cc_jit_points)
     const int sink = a.points ? (int)CC_SINK_POINTS : sink_kind;
     if (jit_ready(const_cast<cc_program *>(prog), sink)) {
@@ -396,6 +450,8 @@ int init_context(Context &c, int device, int index)
     if (p) c.jit_mode = std::max(0, std::min(2, atoi(p)));
     p = getenv("CODECAD_B200_JIT_MAX_OPS");
     if (p) c.jit_max_ops = (uint32_t)atoi(p);
+    p = getenv("CODECAD_B200_FOREST");
+    if (p) c.forest_mode = atoi(p) != 0;
     c.ready = true;
     return CC_OK;
 }
@@ -670,6 +726,7 @@ void cc_program_destroy(cc_program *prog)
             cudaSetDevice(c.device);
             cudaStreamSynchronize(c.compute);
             if (prog->d_code[i]) cudaFree(prog->d_code[i]);
+            if (prog->d_forest[i]) cudaFree(prog->d_forest[i]);
             if (c.constant_program == prog->id) c.constant_program = 0;
         }
         cudaSetDevice(g.device);
@@ -734,6 +791,25 @@ int cc_set_jit_mode(int mode)
     if (mode < 0 || mode > 2) return fail(CC_ERR_INVALID_ARGUMENT, "jit mode must be 0, 1 or 2");
     for (int i = 0; i < CC_MAX_DEVICES; ++i) g_ctx[i].jit_mode = mode;
     return old;
+}
+
+int cc_set_forest_mode(int mode)
+{
+    const int old = g.forest_mode;
+    if (mode != 0 && mode != 1) return fail(CC_ERR_INVALID_ARGUMENT, "forest mode must be 0 or 1");
+    for (int i = 0; i < CC_MAX_DEVICES; ++i) g_ctx[i].forest_mode = mode;
+    return old;
+}
+
+int cc_program_get_forest_info(const cc_program *prog, uint32_t out[4])
+{
+    if (!prog || !out) return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
+    const cc_forest &f = prog->dec.forest;
+    out[0] = f.enabled ? f.n_leaves : 0;
+    out[1] = f.enabled ? f.n_unions : 0;
+    out[2] = f.enabled ? f.max_depth : 0;
+    out[3] = f.enabled ? f.n_events : 0;
+    return f.enabled ? 1 : 0;
 }
 
 int cc_program_specialize_wait(cc_program *prog, unsigned sink_mask, double *compile_seconds)

@@ -10,9 +10,27 @@
 #include "cc_device_types.h"
 #include "cc_microcode.h"
 
+// A program that is one tree of unions over fused primitives ("union forest"): what the loader
+// proves about it (cc_program.cpp analyse_forest) so that cc_forest.cu may skip, per tile of the
+// grid, every primitive that provably cannot influence a single bit of the tile's results.
+struct cc_forest {
+    bool enabled = false;
+    uint32_t n_leaves = 0, n_unions = 0, n_events = 0, max_depth = 0;
+    float rmax = 0.0f;             // largest blend radius of its rounded unions (0: sharp unions only)
+    float err_a = 0.0f, err_b = 0.0f;  // |computed - exact| of a primitive's distance <= 2^-16 (err_a + err_b * max|p|)
+    std::vector<float> bounds;     // [n_leaves][8]: centre x,y,z, g_lo, r_lb, g_hi, r_ub, depth  (cc_forest.cu)
+    std::vector<uint32_t> events;  // [n_events][4]: PUSH / PRIM / COMBINE in evaluation order
+};
+#define CC_FOREST_PUSH 0u
+#define CC_FOREST_PRIM 1u
+#define CC_FOREST_COMBINE 2u
+#define CC_FOREST_EVENT(type, kind, pc) ((uint32_t)(type) | ((uint32_t)(kind) << 2) | ((uint32_t)(pc) << 8))
+#define CC_FOREST_MIN_LEAVES 8u
+
 struct cc_decoded {
     std::vector<uint32_t> microcode;
     cc_program_info info;
+    cc_forest forest;
 };
 
 // cc_program.cpp
@@ -33,6 +51,7 @@ struct cc_jit_job;
 struct cc_program {
     cc_decoded dec;
     uint32_t *d_code[CC_MAX_DEVICES] = {};  // device copies of the microcode, one per initialised device (made on first use)
+    void *d_forest[CC_MAX_DEVICES] = {};    // device copies of the forest tables (bounds, then events)
     uint64_t id = 0;             // identifies what is currently loaded in a device's __constant__ window
     // scene-specialised kernels (cc_jit.cpp), one library per sink; null until compiled
     void *jit_library[CC_N_SINKS] = {};
@@ -90,6 +109,16 @@ struct cc_render_launch {
 // prog_space 1 = constant bank, 2 = shared copy (interpreter kernels); 0 = the specialised kernel of `prog`
 struct cc_program;
 int cc_launch_render(int ray, int prog_space, const cc_program *prog, const cc_render_launch &r, void *stream, int dev_index);
+
+// union-forest kernel (cc_forest.cu): dense float4 grids with per-tile culling
+struct cc_forest_launch {
+    const float *bounds;     // device, [n_leaves][8]
+    const uint32_t *events;  // device, [n_events][4]
+    uint32_t n_leaves, n_events, max_depth;
+    float rmax, slack;
+};
+size_t cc_forest_smem_bytes(const cc_forest &f);
+int cc_launch_forest(const cc_eval_args &a, const cc_forest_launch &f, void *stream);
 
 // hierarchy helper kernels
 struct cc_level_geom {

@@ -17,7 +17,7 @@
 #define CC_OPT_NOINLINE_HEAVY 1
 #endif
 #if CC_OPT_NOINLINE_HEAVY
-#define CC_DEV_HEAVY __device__ __noinline__
+#define CC_DEV_HEAVY static __device__ __noinline__
 #else
 #define CC_DEV_HEAVY __device__ __forceinline__
 #endif
@@ -86,10 +86,10 @@ CC_DEV float4 cc_sphere(float r, float4 p)
 // Results are identical to the per-point forms above (which remain the slow path and the
 // reference for the oracle): in the fast path every sqrt/rcp operand is in the exact range of
 // cc_sqrt_fast / cc_rcp_fast, and a length in that range is never zero.
-__device__ __noinline__ float4 cc_rectangle_slow(float hw, float hh, float4 p) { return cc_rectangle(hw, hh, p); }
-__device__ __noinline__ float4 cc_circle_slow(float r, float4 p) { return cc_circle(r, p); }
-__device__ __noinline__ float4 cc_sphere_slow(float r, float4 p) { return cc_sphere(r, p); }
-__device__ __noinline__ float4 cc_extrusion_slow(float h, float4 in, float cz) { return cc_extrusion(h, in, cz); }
+static __device__ __noinline__ float4 cc_rectangle_slow(float hw, float hh, float4 p) { return cc_rectangle(hw, hh, p); }
+static __device__ __noinline__ float4 cc_circle_slow(float r, float4 p) { return cc_circle(r, p); }
+static __device__ __noinline__ float4 cc_sphere_slow(float r, float4 p) { return cc_sphere(r, p); }
+static __device__ __noinline__ float4 cc_extrusion_slow(float h, float4 in, float cz) { return cc_extrusion(h, in, cz); }
 
 // apply a one-point function to every lane of every vector
 template <class V, int G, class F>
@@ -217,6 +217,13 @@ CC_DEV void cc_extrusion_n(float h, cc_val<V> (&L)[G], const V (&cz)[G])
 }
 
 // shapes/common.cl:45-64
+// cc-arith pins down two cases that the formula leaves to rounding noise (both are no-ops in exact
+// arithmetic, where |c| <= 1): (1) the blend is taken only if at least one operand is closer than
+// r — with both farther away it would need c > 1, which only a dot product of two unit normals
+// rounded ABOVE one can deliver; (2) the radicand is clamped at zero, so the blend value is never
+// NaN.  With (1) a union of operands that are all farther than r away is exactly the nearest
+// operand, which is what lets whole subtrees be skipped without changing a bit (cc_forest.cu).
+// Both tests sit in the rare path.
 template <class V>
 CC_DEV cc_val<V> cc_rounded_union(float r, cc_val<V> o1, cc_val<V> o2)
 {
@@ -226,11 +233,12 @@ CC_DEV cc_val<V> cc_rounded_union(float r, cc_val<V> o1, cc_val<V> o2)
     const V x1 = vsub(vbc<V>(r), o1.w), x2 = vsub(vbc<V>(r), o2.w);
     const M blend = mand(vlt(vmul(c, x1), x2), vlt(vmul(c, x2), x1));
     if (many(blend)) {  // rare: only within r of both surfaces
+        const V zero = vbc<V>(0.0f);
+        const M near = mor(vgt(x1, zero), vgt(x2, zero));
         const V num = vfma(vneg(vmul(vmul(vbc<V>(2.0f), c), x1)), x2, vfma(x1, x1, vmul(x2, x2)));
         const V den = vfma(vneg(c), c, vbc<V>(1.0f));
-        const V zero = vbc<V>(0.0f);
-        const cc_val<V> b{zero, zero, zero, vsub(vbc<V>(r), vsqrt(vdiv(num, den)))};
-        res = cc_val_sel(blend, b, res);
+        const cc_val<V> b{zero, zero, zero, vsub(vbc<V>(r), vsqrt(vmax(vdiv(num, den), zero)))};
+        res = cc_val_sel(mand(blend, near), b, res);
     }
     return res;
 }
@@ -659,7 +667,7 @@ CC_DEV cc_val<float> cc_op_gear(float k0, float k1, float k2, float k3, float k4
 #if CC_OPT_GEAR_INLINE
 CC_DEV
 #else
-__device__ __noinline__
+static __device__ __noinline__
 #endif
 cc_val<float2> cc_involute_gear2(float k0, float k1, float k2, float k3, float k4, cc_val<float2> co)
 {

@@ -7,6 +7,7 @@
 // canonical arithmetic (DESIGN.md "cc-arith") and must not be fused.
 #include "cc_internal.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <string>
@@ -122,6 +123,184 @@ struct Emitter {
         code[last_header] = CC_HDR(CC_HDR_OP(h), CC_HDR_SRC(h), dst, CC_HDR_LEN(h));
     }
 };
+
+}  // namespace
+
+
+// ---- union forests ------------------------------------------------------------------------------
+// Recognises microcode that is ONE tree of (rounded) unions over fused primitives — the shape of a
+// scene assembled from many boxes and cylinders, BASELINE config 5 — and tabulates what
+// cc_forest.cu needs to cull primitives per tile: for every primitive a bounding ball of its
+// distance function, for every union the leaf ranges of its two operands, and the evaluation order
+// as a stack program (PUSH / PRIM / COMBINE).
+//
+// Bounds.  A fused primitive computes  w = scale * (solid(M p + o) - d)  with M = s * rotation,
+// solid = the signed distance of a box (half extents a, b, h) or cylinder (radius a, half height h).
+// With c = -M^-1 o, rho the circumradius and r_in the inradius of the solid:
+//     scale * (smin |p - c| - rho - d)  <=  w  <=  scale * (smax |p - c| - r_in - d),   w >= -scale * (r_in + d)
+// (circumscribed / inscribed ball, centre value), where smin, smax bound the singular values of M.
+// The computed fp32 value differs from the exact one by a few ulps of the magnitudes involved;
+// err_a + err_b * max|p| bounds those magnitudes, and the kernel allows 2^-16 of it (>100 ulps).
+namespace {
+
+bool invert3(const double *m, double *inv)
+{
+    const double c0 = m[4] * m[8] - m[5] * m[7], c1 = m[5] * m[6] - m[3] * m[8], c2 = m[3] * m[7] - m[4] * m[6];
+    const double det = m[0] * c0 + m[1] * c1 + m[2] * c2;
+    if (!(std::fabs(det) > 1e-30) || !std::isfinite(det)) return false;
+    inv[0] = c0 / det; inv[1] = (m[2] * m[7] - m[1] * m[8]) / det; inv[2] = (m[1] * m[5] - m[2] * m[4]) / det;
+    inv[3] = c1 / det; inv[4] = (m[0] * m[8] - m[2] * m[6]) / det; inv[5] = (m[2] * m[3] - m[0] * m[5]) / det;
+    inv[6] = c2 / det; inv[7] = (m[1] * m[6] - m[0] * m[7]) / det; inv[8] = (m[0] * m[4] - m[1] * m[3]) / det;
+    return true;
+}
+
+bool prim_bounds(const uint32_t *op_words, bool rect, float *out8, double *err_a, double *err_b)
+{
+    float q[27];
+    std::memcpy(q, op_words + 1, sizeof q);
+    double M[9], inv[9];
+    for (int i = 0; i < 9; ++i) M[i] = q[i];
+    for (int i = 0; i < 27; ++i)
+        if (i != 26 && !std::isfinite(q[i])) return false;
+    if (!invert3(M, inv)) return false;
+    double c[3];
+    for (int i = 0; i < 3; ++i) c[i] = -(inv[3 * i] * q[9] + inv[3 * i + 1] * q[10] + inv[3 * i + 2] * q[11]);
+    // M^T M = s^2 (I + E): singular values of M lie in s * sqrt(1 -+ |E|_F)
+    double g[9], s2 = 0;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) g[3 * i + j] = M[i] * M[j] + M[3 + i] * M[3 + j] + M[6 + i] * M[6 + j];
+    s2 = (g[0] + g[4] + g[8]) / 3;
+    if (!(s2 > 1e-30)) return false;
+    double ef = 0;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            const double e = g[3 * i + j] / s2 - (i == j ? 1.0 : 0.0);
+            ef += e * e;
+        }
+    ef = std::sqrt(ef);
+    if (!(ef < 0.25)) return false;  // not a similarity transform: no forest
+    const double s = std::sqrt(s2), smin = s * std::sqrt(1 - ef) * (1 - 1e-6), smax = s * std::sqrt(1 + ef) * (1 + 1e-6);
+    const double a = q[12], b = q[13], h = q[14], d = q[15], scale = q[25];
+    if (!(scale > 0) || !(a >= 0) || !(h >= 0) || (rect && !(b >= 0))) return false;
+    const double rho = rect ? std::sqrt(a * a + b * b + h * h) : std::sqrt(a * a + h * h);
+    const double rin = rect ? std::min(a, std::min(b, h)) : std::min(a, h);
+    const double tiny = 1e-6 * (rho + std::fabs(d));
+    out8[0] = (float)c[0]; out8[1] = (float)c[1]; out8[2] = (float)c[2];
+    // rounding the centre to fp32 moves it by < 2^-23 |c|; covered by the error budget below
+    out8[3] = (float)(scale * smin * (1 - 1e-6));                 // g_lo
+    out8[4] = (float)(scale * (rho + d + tiny) * (1 + 1e-6) + 1e-30);   // r_lb   (w >= g_lo |p-c| - r_lb)
+    out8[5] = (float)(scale * smax * (1 + 1e-6));                 // g_hi
+    out8[6] = (float)(scale * (rin + d - tiny) - 1e-6 * std::fabs(scale * (rin + d)));  // r_ub   (w <= g_hi |p-c| - r_ub)
+    out8[7] = (float)std::max(0.0, scale * (rin + d + tiny) * (1 + 1e-6));               // depth  (w >= -depth)
+    for (int i = 3; i < 8; ++i)
+        if (!std::isfinite(out8[i])) return false;
+    // magnitudes that enter the computed value: |M| |p| + |o|, the solid's size, the offset
+    const double cn = std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+    *err_a = std::max(*err_a, scale * (smax * cn + std::fabs((double)q[9]) + std::fabs((double)q[10]) + std::fabs((double)q[11]) + rho + std::fabs(d)));
+    *err_b = std::max(*err_b, scale * smax * 3.0);
+    return true;
+}
+
+void analyse_forest(const std::vector<uint32_t> &code, cc_forest *f)
+{
+    *f = cc_forest();
+    struct Node { uint32_t lo, hi; };
+    struct Union { uint32_t lo, mid, hi, pc, kind; float r; };
+    std::vector<Node> nodes;
+    std::vector<Union> unions;
+    std::vector<uint32_t> leaf_pc, leaf_kind;
+    std::vector<int> slot_node(CC_SLOT_NONE + 1, -1);
+    int L = -1;
+    bool L_stored = true;
+    // pass 1: the tree
+    std::vector<std::pair<uint32_t, int>> order;  // (pc, union index or -1 - leaf) in microcode order
+    for (uint32_t pc = 0;;) {
+        if (pc >= code.size()) return;
+        const uint32_t hd = code[pc], op = CC_HDR_OP(hd), src = CC_HDR_SRC(hd), dst = CC_HDR_DST(hd);
+        if (op == MOP_RETURN) break;
+        int made = -1;
+        if (op == MOP_PRIM_CIRCLE || op == MOP_PRIM_RECT || op == MOP_PRIM_CIRCLE_M || op == MOP_PRIM_RECT_M) {
+            if (L >= 0 && !L_stored) return;  // a value would be lost
+            const uint32_t k = (uint32_t)leaf_pc.size();
+            leaf_pc.push_back(pc);
+            leaf_kind.push_back(op);
+            nodes.push_back(Node{k, k + 1});
+            made = (int)nodes.size() - 1;
+            order.emplace_back(pc, -1 - (int)k);
+        } else if (op == MOP_UNION || op == MOP_UNION_R) {
+            if (src == CC_SLOT_NONE || slot_node[src] < 0 || L < 0 || L_stored) return;
+            const Node A = nodes[(size_t)slot_node[src]], B = nodes[(size_t)L];
+            slot_node[src] = -1;
+            if (A.hi != B.lo) return;  // operands must be adjacent subtrees, stored one first
+            float r = 0.0f;
+            std::memcpy(&r, &code[pc + 1], 4);
+            if (op == MOP_UNION_R && !(r >= 0.0f && std::isfinite(r))) return;
+            unions.push_back(Union{A.lo, A.hi, B.hi, pc, op, op == MOP_UNION_R ? r : 0.0f});
+            nodes.push_back(Node{A.lo, B.hi});
+            made = (int)nodes.size() - 1;
+            order.emplace_back(pc, (int)unions.size() - 1);
+        } else {
+            return;  // any other micro-op: not a pure union forest
+        }
+        L = made;
+        L_stored = false;
+        if (dst != CC_SLOT_NONE) {
+            if (slot_node[dst] >= 0) return;  // overwrites a value nobody consumed
+            slot_node[dst] = made;
+            L_stored = true;
+        }
+        pc += CC_HDR_LEN(hd);
+    }
+    const uint32_t n = (uint32_t)leaf_pc.size();
+    if (n < CC_FOREST_MIN_LEAVES || n > 60000u || L < 0 || L_stored) return;
+    if (nodes[(size_t)L].lo != 0 || nodes[(size_t)L].hi != n) return;
+    for (int v : slot_node)
+        if (v >= 0) return;
+    // pass 2: events in evaluation order; a union's PUSH sits just before the first leaf of its second operand
+    std::vector<int> mid_of(n, -1);
+    for (size_t u = 0; u < unions.size(); ++u) mid_of[unions[u].mid] = (int)u;
+    auto push_event = [&](uint32_t w0, uint32_t w1, uint32_t w2, float r) {
+        uint32_t rb;
+        std::memcpy(&rb, &r, 4);
+        f->events.insert(f->events.end(), {w0, w1, w2, rb});
+    };
+    uint32_t depth = 0, max_depth = 0;
+    for (auto &o : order) {
+        if (o.second < 0) {
+            const uint32_t k = (uint32_t)(-1 - o.second);
+            if (mid_of[k] >= 0) {
+                const Union &u = unions[(size_t)mid_of[k]];
+                push_event(CC_FOREST_EVENT(CC_FOREST_PUSH, u.kind, u.pc), u.lo | (u.mid << 16), u.hi, u.r);
+                max_depth = std::max(max_depth, ++depth);
+            }
+            push_event(CC_FOREST_EVENT(CC_FOREST_PRIM, leaf_kind[k], leaf_pc[k]), k, 0, 0.0f);
+        } else {
+            const Union &u = unions[(size_t)o.second];
+            push_event(CC_FOREST_EVENT(CC_FOREST_COMBINE, u.kind, u.pc), u.lo | (u.mid << 16), u.hi, u.r);
+            --depth;
+        }
+    }
+    if (code.size() >= (1u << 24)) return;
+    f->bounds.resize((size_t)n * 8);
+    double ea = 0, eb = 0;
+    for (uint32_t k = 0; k < n; ++k) {
+        const bool rect = leaf_kind[k] == MOP_PRIM_RECT || leaf_kind[k] == MOP_PRIM_RECT_M;
+        if (!prim_bounds(&code[leaf_pc[k]], rect, &f->bounds[(size_t)k * 8], &ea, &eb)) {
+            *f = cc_forest();
+            return;
+        }
+    }
+    float rmax = 0.0f;
+    for (const Union &u : unions) rmax = std::max(rmax, u.r);
+    f->n_leaves = n;
+    f->n_unions = (uint32_t)unions.size();
+    f->n_events = (uint32_t)(f->events.size() / 4);
+    f->max_depth = std::max(1u, max_depth);
+    f->rmax = rmax;
+    f->err_a = (float)(ea * 1.01 + rmax);
+    f->err_b = (float)(eb * 1.01);
+    f->enabled = true;
+}
 
 }  // namespace
 
@@ -477,6 +656,7 @@ int cc_decode_program(const float *words, uint32_t n_words, cc_decoded *out, std
         std::memcpy(&e.code[off], tab.data(), tab.size() * sizeof(float));
     }
     out->microcode.swap(e.code);
+    analyse_forest(out->microcode, &out->forest);
     out->info.n_words = pc;
     out->info.n_instructions = (uint32_t)ins.size();
     out->info.n_micro_ops = n_micro;
@@ -486,5 +666,7 @@ int cc_decode_program(const float *words, uint32_t n_words, cc_decoded *out, std
     out->info.n_fused = n_p;
     out->info.flops_min = fmin;
     out->info.flops_max = fmax;
+    out->info.n_forest_leaves = out->forest.enabled ? out->forest.n_leaves : 0;
+    out->info.forest_depth = out->forest.enabled ? out->forest.max_depth : 0;
     return CC_OK;
 }

@@ -91,6 +91,8 @@ typedef struct cc_program_info {
     uint32_t n_fused;        /* fused primitive micro-ops (MOP_PRIM_*)               */
     uint32_t flops_min;      /* static algorithmic flop/point, SURVEY.md 8(a3) rules */
     uint32_t flops_max;
+    uint32_t n_forest_leaves; /* primitives of a union forest (cc_set_forest_mode), 0 = not one */
+    uint32_t forest_depth;    /* its evaluation stack depth                                    */
 } cc_program_info;
 int cc_program_get_info(const cc_program *prog, cc_program_info *out);
 /* copies the decoded microcode (for tests / disassembly); returns the microcode length */
@@ -122,6 +124,17 @@ int cc_program_use_specialized(cc_program *prog, int enable); /* returns 1 if sp
  * CODECAD_B200_JIT_MAX_OPS (4096) micro-ops are only specialised on request; programs of more than a
  * few hundred micro-ops are compiled as segments that call shared, table-driven op functions.  Returns the old mode. */
 int cc_set_jit_mode(int mode);
+/* Union forests.  A program that is one tree of (rounded) unions over fused boxes / cylinders
+ * (500 rounded boxes) is recognised at load time; its dense float4 grids
+ * (cc_grid_eval, cc_grid_eval_to_host) are then evaluated tile by tile, skipping in each tile the
+ * primitives that provably cannot change a bit of its results (csrc/cc_forest.cu; the reference
+ * walks the whole program for every point, nodes/codegen.py:17-63).  Bit-identical to the full
+ * evaluation; needs no compilation and has no size limit short of 60 000 primitives.  mode 1 = on
+ * (default; environment CODECAD_B200_FOREST), 0 = always evaluate everything.  Returns the old mode.
+ * cc_program_get_forest_info: returns 1 and fills {primitives, unions, stack depth, events} if the
+ * program is a union forest, else 0. */
+int cc_set_forest_mode(int mode);
+int cc_program_get_forest_info(const cc_program *prog, uint32_t out[4]);
 /* Blocks until the specialised kernels of the sinks in `sink_mask` (0 = all) are compiled and
  * loaded, starting their compilation if necessary; returns how many are ready.  compile_seconds
  * receives the background compile time spent on this program so far. */

@@ -213,16 +213,18 @@ static inline v4 slab_x(float h, v4 p) { return mk(copysignf(1.0f, p.x), 0, 0, f
 static inline v4 slab_y(float h, v4 p) { return mk(0, copysignf(1.0f, p.y), 0, fabsf(p.y) - h); }
 static inline v4 slab_z(float h, v4 p) { return mk(0, 0, copysignf(1.0f, p.z), fabsf(p.z) - h); }
 
-/* common.cl:45-64 */
+/* common.cl:45-64.  cc-arith pins down two cases the formula leaves to rounding noise,
+ * both no-ops in exact arithmetic where |c| <= 1: the blend needs at least one operand closer than r
+ * (with both farther it would take c > 1), and the radicand is clamped at zero (never NaN). */
 static inline v4 rounded_union(float r, v4 o1, v4 o2)
 {
     if (r >= 0.0f) {
         float c = cc_dot3(o1.x, o1.y, o1.z, o2.x, o2.y, o2.z);
         float x1 = r - o1.w, x2 = r - o2.w;
-        if (c * x1 < x2 && c * x2 < x1) {
+        if (c * x1 < x2 && c * x2 < x1 && (x1 > 0.0f || x2 > 0.0f)) {
             float num = cc_fma(-((2.0f * c) * x1), x2, cc_fma(x1, x1, x2 * x2));
             float den = cc_fma(-c, c, 1.0f);
-            float d = r - cc_sqrt(cc_div(num, den));
+            float d = r - cc_sqrt(fmaxf(cc_div(num, den), 0.0f));
             return mk(0, 0, 0, d);
         }
     }

@@ -29,10 +29,17 @@ class Scene:
         return np.array(corner, np.float64).astype(np.float32), np.float32(step)
 
 
+FILES = ("scenes.npz", "forest_scenes.npz")  # tools/make_fixtures.py, tools/make_fixtures.py --forests
+
+
 def load_scenes():
-    z = np.load(os.path.join(GOLDEN, "scenes.npz"))
-    names = sorted(k[:-6] for k in z.files if k.endswith(".words"))
-    return {n: Scene(n, z[n + ".words"], z[n + ".meta"]) for n in names}
+    out = {}
+    for f in FILES:
+        z = np.load(os.path.join(GOLDEN, f))
+        for n in sorted(k[:-6] for k in z.files if k.endswith(".words")):
+            out[n] = Scene(n, z[n + ".words"], z[n + ".meta"])
+    return out
 
 
-ALL_NAMES = sorted(k[:-6] for k in np.load(os.path.join(GOLDEN, "scenes.npz")).files if k.endswith(".words"))
+ALL_NAMES = sorted(load_scenes())
+FOREST_NAMES = [n for n in ALL_NAMES if n.startswith("forest_") or n.startswith("cfg_synthetic")]

@@ -154,3 +154,20 @@ def test_matrix_zero_masks_and_identity_elision():
     mask = int(code[ops[0][0] + 13])
     m = code.view(np.float32)[ops[0][0] + 1: ops[0][0] + 10]
     assert mask == sum(1 << i for i in range(9) if m[i] != 0) == 0x11B
+
+
+def test_union_forests_are_recognised_and_nothing_else(scenes):
+    """cc_program.cpp analyse_forest: one tree of unions over fused primitives -> forest tables."""
+    from scenes import FOREST_NAMES
+    from codecad_b200 import _lib
+    want = {"cfg_synthetic500": (500, 9), "cfg_synthetic32": (32, 5), "forest_dense64": (64, None)}
+    for name, s in scenes.items():
+        info, _ = _lib.decode_program(s.words)
+        if name in FOREST_NAMES:
+            assert info.n_forest_leaves == info.n_fused > 0, name
+            assert 1 <= info.forest_depth <= info.n_forest_leaves
+            if name in want:
+                assert info.n_forest_leaves == want[name][0]
+                assert want[name][1] in (None, info.forest_depth)
+        else:
+            assert info.n_forest_leaves == 0 and info.forest_depth == 0, name

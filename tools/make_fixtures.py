@@ -64,6 +64,44 @@ def synthetic_deep_csg(n=500, seed=1234):
     return parts[0]
 
 
+def forest_scenes():
+    """Union forests for csrc/cc_forest.cu beyond config C5: cylinders as well as boxes, axis-aligned
+    and scaled placements, sharp and rounded unions of several radii in one tree, a left-deep chain
+    (an n-ary union), and a dense cluster in which most primitives overlap."""
+    out = {}
+    rng = random.Random(99)
+
+    def prim(spread, allow_scale=True):
+        kind = rng.random()
+        if kind < 0.5:
+            p = s.box(rng.uniform(1, 6), rng.uniform(1, 6), rng.uniform(1, 6))
+        else:
+            p = s.cylinder(h=rng.uniform(1, 6), r=rng.uniform(0.5, 3))
+        if rng.random() < 0.6:
+            p = p.offset(rng.uniform(0.05, 0.6))
+        if allow_scale and rng.random() < 0.25:
+            p = p.scaled(rng.uniform(0.5, 2.0))
+        if rng.random() < 0.7:
+            p = p.rotated((rng.uniform(-1, 1), rng.uniform(-1, 1), rng.uniform(-1, 1)), rng.uniform(0, 360))
+        elif rng.random() < 0.5:
+            p = p.rotated((0, 0, 1), 90)
+        return p.translated(rng.uniform(-spread, spread), rng.uniform(-spread, spread), rng.uniform(-spread, spread))
+
+    def tree(parts, radii):
+        parts = list(parts)
+        while len(parts) > 1:
+            i = rng.randrange(len(parts) - 1)
+            parts[i:i + 2] = [s.union([parts[i], parts[i + 1]], r=rng.choice(radii))]
+        return parts[0]
+
+    out["forest_mixed40"] = tree([prim(20) for _ in range(40)], [0.5, 0.2, -1, 1.0])
+    out["forest_sharp24"] = tree([prim(12) for _ in range(24)], [-1])
+    out["forest_dense64"] = tree([prim(6) for _ in range(64)], [0.5, 0.3])
+    out["forest_chain12"] = s.union([prim(10) for _ in range(12)], r=0.3)
+    out["forest_big_r16"] = tree([prim(15, False) for _ in range(16)], [3.0, 0.1])
+    return out
+
+
 def collect():
     scenes = {}
 
@@ -118,7 +156,8 @@ def collect():
 
 def main():
     out = {}
-    scenes = collect()
+    forests = "--forests" in sys.argv   # the extra file tests/golden/forest_scenes.npz
+    scenes = forest_scenes() if forests else collect()
     for name, shape in scenes.items():
         random.seed(0)
         words = codecad.nodes.make_program(shape)
@@ -135,7 +174,7 @@ def main():
         out[name + ".words"] = words
         out[name + ".meta"] = meta
         print("%-46s dim %d  %5d words  bbox %s .. %s" % (name, shape.dimension(), len(words), box.a, box.b))
-    path = os.path.join(REPO, "tests", "golden", "scenes.npz")
+    path = os.path.join(REPO, "tests", "golden", "forest_scenes.npz" if forests else "scenes.npz")
     numpy.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")
 
