@@ -26,8 +26,8 @@ class _Pinned:
     def array(self, dtype, shape):
         buf = (ctypes.c_uint8 * max(self.nbytes, 1)).from_address(self.ptr.value)
         buf._pinned_owner = self  # the array keeps the allocation alive through its buffer
-        arr = np.frombuffer(buf, dtype=np.uint8, count=self.nbytes).view(dtype).reshape(shape)
-        return arr
+        # (like numpy.empty(shape, dtype): a sub-array dtype such as (float4, (2,)) adds its own axes)
+        return np.ndarray(shape=shape, dtype=dtype, buffer=buf)
 
     def __del__(self):
         try:

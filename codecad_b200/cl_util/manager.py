@@ -185,6 +185,9 @@ class _Kernels:
         return Event(ev)
 
     def __getattr__(self, name):
+        extra = self.__dict__.get("manager")._extra_kernels if "manager" in self.__dict__ else {}
+        if name in extra:
+            return extra[name]
         raise AttributeError(
             "kernel %r has no CUDA counterpart (available: grid_eval, grid_eval_pymcubes, subdivision_step, "
             "mass_properties, bitmap, ray_caster, process_polygon, matplotlib_slice); there is no OpenCL fallback" % name)
@@ -196,8 +199,15 @@ class OpenCLManager:
         self.queue = _Queue(self.context)
         self._compile_units = []
         self.common_header = CompileUnit()
+        self._extra_kernels = {}
         self.k = _Kernels(self)
         self.max_register_count = 512  # EVAL_REGISTER_COUNT, nodes/__init__.py:6
+
+    def register_kernel(self, name, fn):
+        """Make `k.<name>(global_size, local_size, *args, wait_for=None)` call fn.  For callers that
+        bring their own kernels built around evaluate() — the reference's tests do (tests/test_dsdf.cl)
+        — and express them on the host side of the boundary with codecad_b200.evaluate_points."""
+        self._extra_kernels[name] = fn
 
     def add_compile_unit(self, *args, **kwargs):
         cu = CompileUnit(*args, **kwargs)

@@ -32,7 +32,7 @@ struct Context {
     bool ready = false;
     int device = -1;
     cudaDeviceProp prop;
-    cudaStream_t compute = nullptr, copy = nullptr;
+    cudaStream_t compute = nullptr, copy = nullptr, copy2 = nullptr;
     uint64_t launches = 0, points = 0;
     int pts = 0, prog_space = 0;  // tuning overrides, 0 = auto
     int jit_mode = 1;             // 0 never, 1 background (default), 2 compile at first use and wait
@@ -42,6 +42,8 @@ struct Context {
     int index = 0;                  // position in g_ctx
     bool mesh_tables = false;       // marching-cubes tables uploaded to this device
     // look-back scratch
+    uint32_t *d_forest_scratch = nullptr;  // deferred super-tiles of the union-forest kernel
+    size_t forest_scratch_words = 0;
     uint32_t *d_ticket = nullptr;
     unsigned long long *d_status = nullptr;
     size_t status_cap = 0;
@@ -336,7 +338,8 @@ bool forest_applies(int sink_kind, const cc_program *prog, const cc_eval_args &a
 {
     if (!g.forest_mode || sink_kind != CC_SINK_FLOAT4 || a.points || a.blocks) return false;
     const cc_forest &f = prog->dec.forest;
-    return f.enabled && cc_forest_smem_bytes(f) <= (size_t)g.prop.sharedMemPerBlockOptin && f.n_events <= 8192;
+    return f.enabled && cc_forest_smem_bytes(f) <= (size_t)g.prop.sharedMemPerBlockOptin && f.n_events <= 8192 &&
+           f.n_leaves <= 8192;
 }
 
 int launch_forest(const cc_program *prog, cc_eval_args &a, uint64_t points)
@@ -350,7 +353,15 @@ int launch_forest(const cc_program *prog, cc_eval_args &a, uint64_t points)
     const double pmax = std::max(std::fabs((double)a.cx) + ext[0], std::max(std::fabs((double)a.cy) + ext[1], std::fabs((double)a.cz) + ext[2]));
     f.slack = (float)(((double)prog->dec.forest.err_a + (double)prog->dec.forest.err_b * pmax) / 65536.0);
     if (!std::isfinite(f.slack)) return fail(CC_ERR_INVALID_ARGUMENT, "grid coordinates out of range");
-    int e = cc_launch_forest(a, f, g.compute);
+    const size_t ow = cc_forest_overflow_words(a);
+    if (ow > g.forest_scratch_words) {
+        if (g.d_forest_scratch) CU(cudaFree(g.d_forest_scratch));
+        g.d_forest_scratch = nullptr;
+        g.forest_scratch_words = 0;
+        CU(cudaMalloc(&g.d_forest_scratch, ow * 4));
+        g.forest_scratch_words = ow;
+    }
+    int e = cc_launch_forest(a, f, g.d_forest_scratch, g.prop.multiProcessorCount, g.compute);
     if (e) return cuda_fail((cudaError_t)e, "cc_forest_kernel launch");
     g.launches += 1;
     g.points += points;
@@ -429,6 +440,7 @@ int init_context(Context &c, int device, int index)
         return fail(CC_ERR_CUDA, std::string("device ") + c.prop.name + " is not sm_100 (built for sm_100a only)");
     CU(cudaStreamCreateWithFlags(&c.compute, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c.copy, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c.copy2, cudaStreamNonBlocking));
     CU(cudaMallocHost(&c.h_word, 64));
     {
         // keep freed work-list memory in the pool instead of returning it to the driver at every sync
@@ -617,6 +629,7 @@ void cc_shutdown(void)
         cudaDeviceSynchronize();
         if (c.d_ticket) cudaFree(c.d_ticket);
         if (c.d_status) cudaFree(c.d_status);
+        if (c.d_forest_scratch) cudaFree(c.d_forest_scratch);
         if (c.h_word) cudaFreeHost(c.h_word);
         for (int i = 0; i < Context::kRing; ++i) {
             if (c.ring[i]) cudaFree(c.ring[i]);
@@ -625,6 +638,7 @@ void cc_shutdown(void)
         }
         cudaStreamDestroy(c.compute);
         cudaStreamDestroy(c.copy);
+        cudaStreamDestroy(c.copy2);
         c = Context();
     }
     g_n_ctx = 0;
@@ -660,6 +674,7 @@ int cc_synchronize(void)
     NEED_INIT();
     CU(cudaStreamSynchronize(g.compute));
     CU(cudaStreamSynchronize(g.copy));
+    CU(cudaStreamSynchronize(g.copy2));
     return CC_OK;
 }
 
@@ -871,6 +886,7 @@ int cc_buffer_free(void *dptr)
     NEED_INIT();
     if (!dptr) return CC_OK;
     CU(cudaStreamSynchronize(g.copy));  // the slab pipeline may still be reading from it
+    CU(cudaStreamSynchronize(g.copy2));
     CU(cudaFreeAsync(dptr, g.compute));
     return CC_OK;
 }
@@ -1013,7 +1029,14 @@ static int grid_to_host_share(const cc_program *prog, const float corner[3], flo
     const size_t elem = 16;
     const int layout = CC_LAYOUT_INDEX3_FLOAT4;
     const int RING = Context::kRing;
-    uint32_t slab_x = (uint32_t)std::max<uint64_t>(1, (64ull << 20) / (plane * elem));
+    // slab size: large enough that the per-copy overhead vanishes (64 MiB slabs reached 46 of the
+    // 57 GB/s one big copy gets on the test box), small enough that the ring stays modest
+    static const uint64_t slab_mib = [] {
+        const char *t = getenv("CODECAD_B200_SLAB_MIB");
+        const long v = t ? atol(t) : 0;
+        return (uint64_t)(v > 0 ? v : 64);
+    }();
+    uint32_t slab_x = (uint32_t)std::max<uint64_t>(1, (slab_mib << 20) / (plane * elem));
     slab_x = std::min(slab_x, nx);
     const size_t slab_bytes = (size_t)slab_x * plane * elem;
     if (slab_bytes > g.ring_bytes) {
@@ -1038,13 +1061,18 @@ static int grid_to_host_share(const cc_program *prog, const float corner[3], flo
         rc = cc_grid_eval(prog, corner, step, cnt, ny, nz, x_offset + x0, layout, g.ring[slot], nullptr);
         if (rc) break;
         CU(cudaEventRecord(g.ring_computed[slot], g.compute));
-        CU(cudaStreamWaitEvent(g.copy, g.ring_computed[slot], 0));
+        // two copy streams take the slabs in turn, so that the next transfer is already queued on the
+        // copy engine when one ends
+        cudaStream_t cs = (slot & 1) ? g.copy2 : g.copy;
+        CU(cudaStreamWaitEvent(cs, g.ring_computed[slot], 0));
         CU(cudaMemcpyAsync((char *)h_out + (size_t)x0 * plane * elem, g.ring[slot], (size_t)cnt * plane * elem,
-                           cudaMemcpyDeviceToHost, g.copy));
-        CU(cudaEventRecord(g.ring_copied[slot], g.copy));
+                           cudaMemcpyDeviceToHost, cs));
+        CU(cudaEventRecord(g.ring_copied[slot], cs));
     }
     cudaStreamSynchronize(g.compute);
     cudaError_t e = cudaStreamSynchronize(g.copy);
+    cudaError_t e2 = cudaStreamSynchronize(g.copy2);
+    if (e == cudaSuccess) e = e2;
     if (rc == CC_OK && e != cudaSuccess) rc = cuda_fail(e, "grid_eval_to_host");
     return rc;
 }

@@ -117,8 +117,9 @@ struct cc_forest_launch {
     uint32_t n_leaves, n_events, max_depth;
     float rmax, slack;
 };
-size_t cc_forest_smem_bytes(const cc_forest &f);
-int cc_launch_forest(const cc_eval_args &a, const cc_forest_launch &f, void *stream);
+size_t cc_forest_smem_bytes(const cc_forest &f);          // of the (rare) second launch, the larger one
+uint32_t cc_forest_overflow_words(const cc_eval_args &a);  // scratch the launch needs: deferred super-tiles
+int cc_launch_forest(const cc_eval_args &a, const cc_forest_launch &f, uint32_t *d_overflow, int sm_count, void *stream);
 
 // hierarchy helper kernels
 struct cc_level_geom {

@@ -67,10 +67,24 @@ def _make_pyopencl():
     cl.enqueue_map_buffer = _no_opencl
 
     ct = types.ModuleType("pyopencl.cltypes")
-    ct.float = np.float32
-    ct.uint = np.uint32
-    ct.int = np.int32
-    ct.uchar = np.uint8
+    # scalar and vector types with pyopencl's layouts: field names x,y,z,w then s4.., a 3-vector
+    # occupies the space of a 4-vector
+    scalars = {"char": np.int8, "uchar": np.uint8, "short": np.int16, "ushort": np.uint16, "int": np.int32,
+               "uint": np.uint32, "long": np.int64, "ulong": np.uint64, "half": np.float16, "float": np.float32,
+               "double": np.float64}
+    field_names = ["x", "y", "z", "w"] + ["s%d" % i for i in range(4, 16)]
+    for sname, stype in scalars.items():
+        setattr(ct, sname, stype)
+        for count in (2, 3, 4, 8, 16):
+            padded = 4 if count == 3 else count
+            names = field_names[:count] if count <= 4 else ["s%d" % i for i in range(count)]
+            names = names + ["padding%d" % i for i in range(padded - count)]
+            dt = np.dtype([(n, stype) for n in names])
+            setattr(ct, "%s%d" % (sname, count), dt)
+
+            def filled(value, dt=dt):
+                return np.array(tuple([value] * len(dt.names)), dtype=dt)
+            setattr(ct, "filled_%s%d" % (sname, count), filled)
     ct.float2 = FLOAT2
     ct.float3 = FLOAT4  # an OpenCL float3 occupies 16 bytes
     ct.float4 = FLOAT4
