@@ -92,6 +92,23 @@ __device__ __forceinline__ void ccf_prim(const uint32_t *__restrict__ code, uint
     cc_prim_n<RECT, MASKED, V, G>(m, mf, masks & 0x1FFu, (masks >> 9) & 0x1FFu, d.y, d.z, d.w, e.x, x, y, z, L);
 }
 
+// one point, parameters that differ from lane to lane (the masked form covers full matrices too)
+template <bool RECT>
+__device__ __forceinline__ void ccf_prim_lane(const uint32_t *__restrict__ code, uint32_t pc, const float (&x)[1],
+                                              const float (&y)[1], const float (&z)[1], cc_val<float> (&L)[1])
+{
+    const float4 *q = reinterpret_cast<const float4 *>(code + pc);
+    const float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3), e = __ldg(q + 4), f = __ldg(q + 5),
+                 g = __ldg(q + 6);
+    float m[12], mf[12];
+    m[0] = a.y; m[1] = a.z; m[2] = a.w; m[3] = b.x; m[4] = b.y; m[5] = b.z;
+    m[6] = b.w; m[7] = c.x; m[8] = c.y; m[9] = c.z; m[10] = c.w; m[11] = d.x;
+    mf[0] = e.y; mf[1] = e.z; mf[2] = e.w; mf[3] = f.x; mf[4] = f.y; mf[5] = f.z;
+    mf[6] = f.w; mf[7] = g.x; mf[8] = g.y; mf[9] = g.z; mf[10] = 0.f; mf[11] = 0.f;
+    const uint32_t masks = __float_as_uint(g.w);  // word 27 is written for every fused primitive
+    cc_prim_n<RECT, true, float, 1>(m, mf, masks & 0x1FFu, (masks >> 9) & 0x1FFu, d.y, d.z, d.w, e.x, x, y, z, L);
+}
+
 // lb <= w_k(p) <= ub for every point p within `rad` of centre (mx, my, mz)   (cc_program.cpp prim_bounds)
 __device__ __forceinline__ void ccf_bounds(const float4 *__restrict__ bounds, uint32_t k, float mx, float my, float mz,
                                            float rad, float slack, float *lb, float *ub, float *depth)
@@ -124,6 +141,7 @@ __global__ void __launch_bounds__(CCF_THREADS) cc_forest_kernel(const cc_forest_
     uint2 *s_ev = reinterpret_cast<uint2 *>(smem4 + A.region0_f4);
     uint32_t *s_wlist = reinterpret_cast<uint32_t *>(s_ev + A.ev_cap);
     uint32_t *s_leaf = s_wlist + (size_t)(CCF_THREADS / 32) * A.ev_cap;
+    uint32_t *s_leafw = s_leaf + CCF_LEAF_CAP;  // the PRIM event word (pc, kind) of every kept leaf
     __shared__ uint32_t s_warp[CCF_THREADS / 32];
     __shared__ float s_red[2][CCF_THREADS / 32];
     __shared__ uint32_t s_info[2];  // events kept, stack depth they need
@@ -223,8 +241,10 @@ __global__ void __launch_bounds__(CCF_THREADS) cc_forest_kernel(const cc_forest_
                 if (keep & (1u << (e - e0))) {
                     const uint4 ev = __ldg(events + e);
                     uint32_t where;
-                    if ((ev.x & 3u) == CC_FOREST_PRIM) where = s_prefix[ev.y];
-                    else where = (s_prefix[ev.y & 0xffffu] & 0xffu) | ((s_prefix[ev.y >> 16] & 0xffu) << 8) | ((s_prefix[ev.z] & 0xffu) << 16);
+                    if ((ev.x & 3u) == CC_FOREST_PRIM) {
+                        where = s_prefix[ev.y];
+                        if (where < CCF_LEAF_CAP) s_leafw[where] = ev.x;
+                    } else where = (s_prefix[ev.y & 0xffffu] & 0xffu) | ((s_prefix[ev.y >> 16] & 0xffu) << 8) | ((s_prefix[ev.z] & 0xffu) << 16);
                     s_ev[at++] = make_uint2(ev.x, where);
                 }
         __syncthreads();
@@ -262,24 +282,51 @@ __global__ void __launch_bounds__(CCF_THREADS) cc_forest_kernel(const cc_forest_
                 const float uy = cc_fma(a.step, (float)ty0 + h2, cy);
                 const float uz = cc_fma(a.step, (float)tz0 + h2, cz);
                 const float r2 = fabsf(a.step) * (h2 * 1.7320509f * 1.0001f);
-                float lb0 = 0.f, lb1 = 0.f, ub, depth, u2 = __int_as_float(0x7f800000), d2 = 0.0f;
+                // Bounds of a kept primitive over the tile from its OWN computed value at the tile centre:
+                // the solid's distance is 1-Lipschitz, so |w(p) - w(centre)| <= g_hi |p - centre| (+ rounding,
+                // inside the slack) — far tighter than the ball bound of the super-tile pass.  Lane i (and
+                // i + 32) evaluates kept leaf i at the centre with the scalar form of the same op code.
+                float lb0 = 0.f, lb1 = 0.f, u2 = __int_as_float(0x7f800000), d2 = 0.0f;
                 const bool v0 = lane < m, v1 = lane + 32 < m;
-                if (v0) {
-                    ccf_bounds(bounds, s_leaf[lane], ux, uy, uz, r2, slack, &lb0, &ub, &depth);
-                    u2 = ub;
-                    if (lb0 < A.f.rmax) d2 = depth;
-                }
-                if (v1) {
-                    ccf_bounds(bounds, s_leaf[lane + 32], ux, uy, uz, r2, slack, &lb1, &ub, &depth);
-                    u2 = fminf(u2, ub);
-                    if (lb1 < A.f.rmax) d2 = fmaxf(d2, depth);
+                {
+                    const float px[1] = {ux}, py[1] = {uy}, pz[1] = {uz};
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const bool v = hh ? v1 : v0;
+                        if (hh && !__any_sync(0xffffffffu, v1)) break;  // uniform
+                        const uint32_t i = v ? lane + 32 * hh : 0u;
+                        const uint32_t lw = s_leafw[i], kind = (lw >> 2) & 63u, pc = lw >> 8;
+                        const bool rect = kind == MOP_PRIM_RECT || kind == MOP_PRIM_RECT_M;
+                        float wc = 0.0f;
+                        // (the op library votes across the warp: both forms run converged, each lane keeps its own)
+                        if (__any_sync(0xffffffffu, rect)) {
+                            cc_val<float> Lc[1];
+                            ccf_prim_lane<true>(a.code, pc, px, py, pz, Lc);
+                            if (rect) wc = Lc[0].w;
+                        }
+                        if (__any_sync(0xffffffffu, !rect)) {
+                            cc_val<float> Lc[1];
+                            ccf_prim_lane<false>(a.code, pc, px, py, pz, Lc);
+                            if (!rect) wc = Lc[0].w;
+                        }
+                        const float4 b1 = __ldg(bounds + 2 * s_leaf[i] + 1);
+                        const float spread = b1.y * r2 + 2.0f * slack;
+                        const float lb = wc - spread, ub = wc + spread;
+                        if (v) {
+                            u2 = fminf(u2, ub);
+                            if (lb < A.f.rmax) d2 = fmaxf(d2, b1.w);
+                        }
+                        if (hh) lb1 = lb; else lb0 = lb;
+                    }
                 }
 #pragma unroll
                 for (int d = 16; d > 0; d >>= 1) {
                     u2 = fminf(u2, __shfl_xor_sync(0xffffffffu, u2, d));
                     d2 = fmaxf(d2, __shfl_xor_sync(0xffffffffu, d2, d));
                 }
-                const float tau2 = fmaxf(u2, A.f.rmax + 1.01f * (A.f.rmax + d2 + slack)) + 2.0f * slack;
+                // (never above the super-tile's threshold, which holds for all of its points: what the
+                // super-tile dropped, lb > tau, then stays dropped)
+                const float tau2 = fminf(tau, fmaxf(u2, A.f.rmax + 1.01f * (A.f.rmax + d2 + slack)) + 2.0f * slack);
                 const unsigned long long mask = (unsigned long long)__ballot_sync(0xffffffffu, v0 && lb0 <= tau2) |
                                                 ((unsigned long long)__ballot_sync(0xffffffffu, v1 && lb1 <= tau2) << 32);
                 count = 0;
@@ -356,7 +403,7 @@ static size_t ccf_region0(uint32_t stack_cap, uint32_t n_leaves)
 static size_t ccf_smem(uint32_t stack_cap, uint32_t ev_cap, uint32_t n_leaves)
 {
     return ccf_region0(stack_cap, n_leaves) + (size_t)ev_cap * sizeof(uint2) + (size_t)(CCF_THREADS / 32) * ev_cap * 4 +
-           CCF_LEAF_CAP * 4;
+           2 * CCF_LEAF_CAP * 4;
 }
 
 size_t cc_forest_smem_bytes(const cc_forest &f) { return ccf_smem(std::max(f.max_depth, 1u), f.n_events, f.n_leaves); }

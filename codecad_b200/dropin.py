@@ -135,9 +135,13 @@ def load():
     as attributes of it (the import system only does that for modules it loaded itself)."""
     names = install()
     codecad = importlib.import_module("codecad")
+    rendering = importlib.import_module("codecad.rendering")
     for full in names:
         parent, _, child = full.rpartition(".")
         mod = sys.modules[full]
+        if parent == "codecad.rendering":
+            setattr(rendering, child, mod)  # `import codecad.rendering.mesh; codecad.rendering.mesh.f()`
+            continue
         if parent != "codecad":
             continue  # cl_util.opencl_manager must stay the *instance* (cl_util/__init__.py:4)
         if child == "mass_properties":
