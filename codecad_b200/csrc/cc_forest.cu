@@ -129,7 +129,10 @@ __device__ __forceinline__ uint32_t ccf_count(unsigned long long mask, uint32_t 
     return (uint32_t)__popcll(mask & below_b & ~below_a);
 }
 
-__global__ void __launch_bounds__(CCF_THREADS) cc_forest_kernel(const cc_forest_args A)
+#ifndef CCF_MIN_CTAS
+#define CCF_MIN_CTAS 4  // 64 registers: four CTAs = 32 warps per SM
+#endif
+__global__ void __launch_bounds__(CCF_THREADS, CCF_MIN_CTAS) cc_forest_kernel(const cc_forest_args A)
 {
     typedef float2 V;
     typedef cc_val<V> Val;
@@ -347,21 +350,27 @@ __global__ void __launch_bounds__(CCF_THREADS) cc_forest_kernel(const cc_forest_
                 }
                 __syncwarp();
             }
+            // the thread's first cell of the tile; bricks and the second point are constant offsets from it
+            const uint32_t *const lst = refine ? wlist : reinterpret_cast<const uint32_t *>(s_ev);
+            const uint32_t lstride = refine ? 1u : 2u;
+            const bool inside = tx0 + CCF_TILE <= a.nx && ty0 + CCF_TILE <= a.ny && tz0 + CCF_TILE <= a.nz;  // uniform
+            const size_t plane = (size_t)a.ny * a.nz;
+            float4 *const out_t = out + ((size_t)(tx0 + lx) * a.ny + (ty0 + ly)) * a.nz + (tz0 + lz);
             for (uint32_t sb = 0; sb < 8; ++sb) {
-                const uint32_t bx = tx0 + ((sb >> 2) & 1) * 8, by = ty0 + ((sb >> 1) & 1) * 8, bz = tz0 + (sb & 1) * 8;
-                if (bx >= a.nx || by >= a.ny || bz >= a.nz) continue;  // uniform
-                const uint32_t ix0 = bx + lx, ix1 = bx + lx + 4, iy = by + ly, iz = bz + lz;
+                const uint32_t ox = ((sb >> 2) & 1) * 8, oy = ((sb >> 1) & 1) * 8, oz = (sb & 1) * 8;
+                if (!inside && (tx0 + ox >= a.nx || ty0 + oy >= a.ny || tz0 + oz >= a.nz)) continue;  // uniform
+                const uint32_t ix0 = tx0 + ox + lx, iy = ty0 + oy + ly, iz = tz0 + oz + lz;
                 // grid_eval.cl:13,31: corner + step * convert_float(id), one FMA per axis (cc_body.cuh)
                 const float gy = cc_fma(a.step, (float)iy, cy), gz = cc_fma(a.step, (float)iz, cz);
                 V vx[1], vy[1], vz[1];
-                vx[0] = make_float2(cc_fma(a.step, (float)(ix0 + a.x_offset), cx), cc_fma(a.step, (float)(ix1 + a.x_offset), cx));
+                vx[0] = make_float2(cc_fma(a.step, (float)(ix0 + a.x_offset), cx), cc_fma(a.step, (float)(ix0 + 4 + a.x_offset), cx));
                 vy[0] = make_float2(gy, gy);
                 vz[0] = make_float2(gz, gz);
                 Val L[1];
                 L[0] = Val{vbc<V>(0.f), vbc<V>(0.f), vbc<V>(0.f), vbc<V>(0.f)};
                 uint32_t sp = 0;
                 for (uint32_t i = 0; i < count; ++i) {
-                    const uint32_t w0 = refine ? wlist[i] : s_ev[i].x;
+                    const uint32_t w0 = lst[i * lstride];
                     const uint32_t type = w0 & 3u, kind = (w0 >> 2) & 63u, pc = w0 >> 8;
                     if (type == CC_FOREST_PRIM) {
                         switch (kind) {
@@ -385,10 +394,11 @@ __global__ void __launch_bounds__(CCF_THREADS) cc_forest_kernel(const cc_forest_
                         else L[0] = cc_op_union(L[0], B);
                     }
                 }
-                if (iy < a.ny && iz < a.nz) {
-                    // INDEX3: z + nz * (y + ny * x); a warp writes four 128-byte runs
-                    if (ix0 < a.nx) __stcs(out + ((size_t)ix0 * a.ny + iy) * a.nz + iz, cc_lane_get(L[0], 0));
-                    if (ix1 < a.nx) __stcs(out + ((size_t)ix1 * a.ny + iy) * a.nz + iz, cc_lane_get(L[0], 1));
+                // INDEX3: z + nz * (y + ny * x); a warp writes four 128-byte runs
+                float4 *const o = out_t + (size_t)ox * plane + (size_t)oy * a.nz + oz;
+                if (inside || (iy < a.ny && iz < a.nz)) {
+                    if (inside || ix0 < a.nx) __stcs(o, cc_lane_get(L[0], 0));
+                    if (inside || ix0 + 4 < a.nx) __stcs(o + 4 * plane, cc_lane_get(L[0], 1));
                 }
             }
             __syncwarp();  // the warp's tile program is rewritten next
