@@ -34,7 +34,11 @@ REF = os.environ.get("CODECAD_REFERENCE", "/root/reference")
 
 KEEP = {"util.h", "indexing.h", "util.cl", "common.h", "common.cl", "simple2d.cl", "simple3d.cl",
         "polygons2d.cl", "unsafe.cl", "gears.cl", "codegen.py", "grid_eval.cl", "subdivision.cl",
-        "mass_properties.cl"}
+        "mass_properties.cl",
+        # the renderers around evaluate(): pin the oracle's restatements of them
+        "assert.h", "opencl_manager.py", "ray_caster.cl", "bitmap.cl", "polygon2d.cl", "matplotlib_slice.cl"}
+# read straight from the tree: its Python module needs matplotlib to import, so the unit is never registered
+EXTRA_FILES = ["codecad/rendering/matplotlib_slice.cl"]
 
 DRIVER = r'''
 thread_local ndrange g_nd;
@@ -97,6 +101,58 @@ void ref_mass_properties(const float *scene, const float *corner, float step, fl
             }
 }
 
+// ---- the renderers around evaluate() ----
+void ref_process_polygon(const float *corner2, float step, int cx, int cy, const float *corners, float *vertices,
+                         unsigned *links, unsigned *starts, unsigned *counter)
+{
+    clref::float2 c(corner2[0], corner2[1]);
+    // sequential: the order of `starts` is then x, y, triangle (the reference's atomic_inc order is arbitrary)
+    for (int x = 0; x < cx; ++x)
+        for (int y = 0; y < cy; ++y)
+            for (int t = 0; t < 2; ++t) {
+                g_nd = ndrange{{(uint)x, (uint)y, (uint)t}, {(uint)cx, (uint)cy, 2u}};
+                process_polygon(c, step, reinterpret_cast<clref::float4 *>(const_cast<float *>(corners)),
+                                reinterpret_cast<clref::float2 *>(vertices), links, starts, counter);
+            }
+}
+
+void ref_bitmap(const float *scene, const float *origin, float step, int w, int h, unsigned char *out)
+{
+    clref::float4 o(origin[0], origin[1], origin[2], 0.0f);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int x = 0; x < w; ++x)
+        for (int y = 0; y < h; ++y) {
+            g_nd = ndrange{{(uint)x, (uint)y, 0u}, {(uint)w, (uint)h, 1u}};
+            bitmap(scene, o, step, out);
+        }
+}
+
+void ref_matplotlib_slice(const float *scene, const float *corner, float step, int w, int h, float *out)
+{
+    clref::float4 c(corner[0], corner[1], corner[2], 0.0f);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int x = 0; x < w; ++x)
+        for (int y = 0; y < h; ++y) {
+            g_nd = ndrange{{(uint)x, (uint)y, 0u}, {(uint)w, (uint)h, 1u}};
+            matplotlib_slice(scene, c, step, out);
+        }
+}
+
+void ref_ray_caster(const float *scene, const float *origin, const float *forward, const float *up, const float *right,
+                    float pixelTolerance, float boxRadius, float minDistance, float maxDistance, float floorZ,
+                    unsigned renderOptions, int w, int h, unsigned char *out)
+{
+    clref::float4 o(origin[0], origin[1], origin[2], 0.0f), f(forward[0], forward[1], forward[2], 0.0f),
+        u(up[0], up[1], up[2], 0.0f), r(right[0], right[1], right[2], 0.0f);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int x = 0; x < w; ++x)
+        for (int y = 0; y < h; ++y) {
+            g_nd = ndrange{{(uint)x, (uint)y, 0u}, {(uint)w, (uint)h, 1u}};
+            ray_caster(scene, o, f, u, r, pixelTolerance, boxRadius, minDistance, maxDistance, floorZ, renderOptions, out,
+                       nullptr);
+        }
+}
+
 }  // extern "C"
 '''
 
@@ -124,18 +180,25 @@ def collect_reference_program():
             origin = os.path.basename(m.group(1).encode().decode("unicode_escape"))
             continue
         units.append((origin, p))
+    have = {o for o, _ in units}
+    for rel in EXTRA_FILES:
+        if os.path.basename(rel) not in have:
+            with open(os.path.join(REF, rel)) as f:
+                units.append((os.path.basename(rel), f.read()))
     return units
 
 
-_VEC = re.compile(r"\(\s*(float2|float3|float4|uint3|uchar4)\s*\)\s*\(")
+_VEC = re.compile(r"\(\s*(float2|float3|float4|uint2|uint3|int2|uchar4)\s*\)\s*\(")
 _FLT = re.compile(r"(?<![\w.])((?:\d+\.\d*|\.\d+)(?:[eE][+-]?\d+)?)(?![\w.])")
 
 
 def translate(units):
-    out = ['#include "../opencl_shim.hpp"', "#include <omp.h>", "namespace clref {"]
+    out = ['#include "../opencl_shim.hpp"', "#include <omp.h>", "namespace clref {",
+           "#define ASSERT_BUFFER_SIZE 1024  /* cl_util/cl_assert.py; asserts themselves stay disabled */"]
     for origin, text in units:
         if origin not in KEEP:
             continue
+        text = text.replace("const __constant", "__constant")
         text = _VEC.sub(lambda m: "mk_%s(" % m.group(1), text)
         text = _FLT.sub(lambda m: m.group(1) + "f", text)
         out.append("// ---- from the reference: %s ----" % origin)

@@ -31,8 +31,9 @@ struct swz {
 };
 
 struct float2 {
-    union { float d[2]; struct { float x, y; }; };
+    union { float d[2]; struct { float x, y; }; struct { float s0, s1; }; };
     float2() : x(0), y(0) {}
+    float2(float a) : x(a), y(a) {}  // OpenCL widens scalars implicitly
     float2(float a, float b) : x(a), y(b) {}
 };
 struct float3 {
@@ -43,6 +44,7 @@ struct float3 {
         swz<float2, 2, 0, 2> xz;
     };
     float3() : x(0), y(0), z(0) {}
+    explicit float3(float a) : x(a), y(a), z(a) {}  // (float3)scalar
     float3(float a, float b, float c) : x(a), y(b), z(c) {}
 };
 struct float4 {
@@ -59,6 +61,21 @@ struct float4 {
 };
 struct uint3 { uint x, y, z; };
 struct uchar4 { uchar x, y, z, w; };
+struct uint2 { uint x, y; };
+struct int2;
+struct int2_yx {  // the .yx swizzle of an int2 (rendering/polygon2d.cl)
+    int d[2];
+    operator int2() const;
+};
+struct int2 {
+    union { int d[2]; struct { int x, y; }; int2_yx yx; };
+    int2() : x(0), y(0) {}
+    int2(int a, int b) : x(a), y(b) {}
+};
+inline int2_yx::operator int2() const { return int2(d[1], d[0]); }
+inline int2 operator+(int2 a, int2 b) { return int2(a.x + b.x, a.y + b.y); }
+inline int2 &operator+=(int2 &a, int2 b) { a.x += b.x; a.y += b.y; return a; }
+inline uint2 operator+(uint2 a, uint2 b) { uint2 r = {a.x + b.x, a.y + b.y}; return r; }
 
 // ---- vector literals: (float4)(a, b, c, d) is rewritten to mk_float4(a, b, c, d) ----
 inline float2 mk_float2(float a, float b) { return float2(a, b); }
@@ -68,6 +85,9 @@ inline float4 mk_float4(float2 a, float c, float d) { return float4(a.x, a.y, c,
 inline float4 mk_float4(float3 a, float d) { return float4(a.x, a.y, a.z, d); }
 inline float4 mk_float4(float a, float3 b) { return float4(a, b.x, b.y, b.z); }
 inline uint3 mk_uint3(uint a, uint b, uint c) { uint3 r = {a, b, c}; return r; }
+inline uint2 mk_uint2(uint a, uint b) { uint2 r = {a, b}; return r; }
+inline int2 mk_int2(int a, int b) { return int2(a, b); }
+inline float3 mk_float3(float a) { return float3(a, a, a); }
 inline uchar4 mk_uchar4(uint a, uint b, uint c, uint d) { uchar4 r = {(uchar)a, (uchar)b, (uchar)c, (uchar)d}; return r; }
 
 // ---- arithmetic ----
@@ -90,6 +110,9 @@ CLREF_OPS(float4, 4)
 inline float3 as_float3(float4 v) { return float3(v.x, v.y, v.z); }
 inline float4 as_float4(float3 v) { return float4(v.x, v.y, v.z, 0.0f); }
 inline float3 convert_float3(uint3 v) { return float3((float)v.x, (float)v.y, (float)v.z); }
+inline float2 convert_float2(uint2 v) { return float2((float)v.x, (float)v.y); }
+inline float3 operator+(float3 a, float s) { return float3(a.x + s, a.y + s, a.z + s); }
+inline float3 operator*(int s, float3 a) { return float3(s * a.x, s * a.y, s * a.z); }
 
 // ---- built-in math (fp32 glibc, no contraction) ----
 inline float dot(float2 a, float2 b) { return a.x * b.x + a.y * b.y; }
@@ -116,9 +139,35 @@ inline float fmod(float a, float b) { return ::fmodf(a, b); }
 inline float remainder(float a, float b) { return ::remainderf(a, b); }
 inline float sincos(float x, float *c) { *c = ::cosf(x); return ::sinf(x); }
 inline float sign(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : (x == 0.0f ? x : 0.0f)); }
-inline float min(float a, float b) { return a < b ? a : b; }
-inline float max(float a, float b) { return a > b ? a : b; }
+// OpenCL leaves min/max of a NaN undefined; GPU implementations map them to the hardware's
+// NaN-ignoring min/max instructions (PTX min.f32 / max.f32), which is fminf/fmaxf.  It matters in
+// one place: the false-colour picture, where rays that miss everything carry a NaN normal.
+inline float min(float a, float b) { return ::fminf(a, b); }
+inline float max(float a, float b) { return ::fmaxf(a, b); }
 inline float2 vload2(size_t i, const float *p) { return float2(p[2 * i], p[2 * i + 1]); }
+inline float3 normalize(float3 v) { return v / length(v); }
+inline float clamp(float x, float lo, float hi) { return min(max(x, lo), hi); }
+inline float mix(float a, float b, float t) { return a + (b - a) * t; }
+inline float3 mix(float3 a, float3 b, float t) { return a + (b - a) * t; }
+inline float step(float edge, float x) { return x < edge ? 0.0f : 1.0f; }
+inline float smoothstep(float e0, float e1, float x)
+{
+    const float t = clamp((x - e0) / (e1 - e0), 0.0f, 1.0f);
+    return t * t * (3.0f - 2.0f * t);
+}
+inline float3 fract(float3 v, float3 *ip)
+{
+    float3 r;
+    for (int i = 0; i < 3; ++i) {
+        ip->d[i] = ::floorf(v.d[i]);
+        r.d[i] = ::fminf(v.d[i] - ip->d[i], 0x1.fffffep-1f);
+    }
+    return r;
+}
+inline float pow(float a, float b) { return ::powf(a, b); }
+inline float exp(float a) { return ::expf(a); }
+inline float fmin(float a, float b) { return ::fminf(a, b); }
+inline float fmax(float a, float b) { return ::fmaxf(a, b); }
 
 #define M_PI_F 3.14159274101257324f
 #define M_PI_2_F 1.57079637050628662f

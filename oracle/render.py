@@ -37,6 +37,32 @@ def camera_params(box_a, box_b, size, view_angle=None):
     return origin, np.array([0.0, 1.0, 0.0]), np.array([0.0, 0.0, 1.0]), focal
 
 
+def ray_cast_args(box_a, box_b, size, view_angle=None):
+    """The kernel arguments ray_caster.py:30-71 computes for a picture of the box: origin, forward (scaled
+    by the focal length), up, right, pixel_tolerance, box_radius, min_distance, max_distance, floor_z."""
+    a, b = _v(box_a), _v(box_b)
+    origin, direction, up, focal = camera_params(a, b, size, view_angle)
+    forward = _norm(direction)
+    up = up - forward * float(up @ forward)
+    up = _norm(up)
+    right = np.cross(forward, up)
+    forward = forward * focal
+    mid = (a + b) / 2
+    origin_to_mid = math.sqrt(float((origin - mid) @ (origin - mid)))
+    box_radius = math.sqrt(float((b - a) @ (b - a))) / 2
+    return (origin, forward, up, right, 0.5 / focal, box_radius, max(0, origin_to_mid - box_radius),
+            origin_to_mid + box_radius, a[2] - (b[2] - a[2]) / 20)
+
+
+def bitmap_args(box_a, box_b, size):
+    """origin and step of bitmap.py:12-30."""
+    a, b = _v(box_a).copy(), _v(box_b).copy()
+    a[2] = b[2] = 0
+    resolution = np.array([size[0], size[1], 1.0])
+    step = float(((b - a) / resolution).max())
+    return (a + b) / 2 - resolution * step / 2, step
+
+
 def ray_cast(words, box_a, box_b, size, view_angle=None, options=0):
     """ray_caster.py:30-89 -> uint8 [h][w][3]."""
     a, b = _v(box_a), _v(box_b)

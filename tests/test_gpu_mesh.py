@@ -103,3 +103,53 @@ def test_chunked_paths_give_the_same_triangles(cb, scenes, mode, monkeypatch):
         monkeypatch.setenv("CODECAD_B200_MESH_FIELD_BUDGET", str(20 * block_bytes))    # fewer than the mesh has
     got_v, got_b, _ = mesh_arrays(scene, 16)
     assert np.array_equal(got_b, want_b) and np.array_equal(got_v, want_v)
+
+
+# ---- pins that do not depend on PyMCubes' exact triangulation (absent from the image) ----------
+# Whatever table a marching-cubes implementation uses, its vertices lie on cell edges where the field
+# changes sign, so they must be ON the surface to interpolation accuracy, and volume / area of the
+# mesh must converge to the solid's as the resolution grows.
+
+
+
+@pytest.mark.parametrize("name", ["sub_box10", "dsdf3d_sphere", "cfg_csg_example", "dsdf3d_torus", "mp_drunk_box"])
+def test_every_vertex_lies_on_the_surface(cb, scenes, name):
+    from codecad_b200 import CompiledScene
+    from codecad_b200.rendering import mesh_arrays
+    s = scenes[name]
+    size = max(b - a for a, b in zip(s.box_a, s.box_b))
+    res = size / 96
+    scene = CompiledScene(s.words, 3, s.box_a, s.box_b, 2 * res, name + "@96")
+    vertices, _, _ = mesh_arrays(scene, 32)
+    pts = np.asarray(vertices, np.float64).reshape(-1, 3)
+    assert len(pts) > 1000
+    d = cb.evaluate_points(scene, pts.astype(np.float32))[:, 3]
+    # linear interpolation along a cell edge of a 1-Lipschitz field: the error is second order in the
+    # cell size where the field is smooth and at most one cell near creases
+    assert np.abs(d).max() <= 1.0 * res, np.abs(d).max() / res
+    assert np.mean(np.abs(d)) <= 0.05 * res, np.mean(np.abs(d)) / res
+
+
+def _area(soup):
+    a, b, c = soup[:, 0], soup[:, 1], soup[:, 2]
+    return 0.5 * np.linalg.norm(np.cross(b - a, c - a), axis=1).sum()
+
+
+def test_volume_and_area_converge_to_the_analytic_solid(cb, scenes):
+    from codecad_b200 import CompiledScene
+    from codecad_b200.rendering import mesh_arrays
+    # box(10): volume 1000, area 600.  sphere: radius from its bounding box.
+    for name, volume, area in (("sub_box10", 1000.0, 600.0), ("dsdf3d_sphere", None, None)):
+        s = scenes[name]
+        size = max(b - a for a, b in zip(s.box_a, s.box_b))
+        if volume is None:
+            r = size / 2
+            volume, area = 4 / 3 * np.pi * r ** 3, 4 * np.pi * r ** 2
+        errs = []
+        for n in (24, 48, 96, 192):
+            scene = CompiledScene(s.words, 3, s.box_a, s.box_b, 2 * size / n, "%s@%d" % (name, n))
+            soup = np.asarray(mesh_arrays(scene, 32)[0], np.float64).reshape(-1, 3, 3)
+            errs.append((abs(mc.signed_volume(soup) - volume) / volume, abs(_area(soup) - area) / area))
+        v_err, a_err = zip(*errs)
+        assert v_err[-1] <= 2e-3 and a_err[-1] <= 2e-2, (name, errs)
+        assert v_err[-1] <= v_err[0] and a_err[-1] <= a_err[0] * 1.01, (name, errs)
