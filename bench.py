@@ -452,6 +452,7 @@ def config_grid_leg(name, label, n, slab_planes, rank, world, torch, dist, info,
     peak = info.sm_count * 128 * 2 * sm_max_mhz * 1e6 / 1e12
     tflops = pts_rank * int(pinfo.flops_min) / (ms * 1e-3) / 1e12
     gbs = pts_rank * 16 / (ms * 1e-3) / 1e9
+    f_exec = load_executed_flops().get(name)
     roof = {"fp32_tflops": tflops, "fp32_frac": tflops / peak, "hbm_gbs": gbs, "hbm_frac": gbs / hbm_peak,
             "bound": "fp32" if tflops / peak >= gbs / hbm_peak else "hbm"}
     if forest:
@@ -464,7 +465,9 @@ def config_grid_leg(name, label, n, slab_planes, rank, world, torch, dist, info,
     return {"workload": label, "scene": name, "grid": [nx * world, n, n], "x_planes_per_rank": nx,
             "value": pts_all / (ms * 1e-3) / 1e9, "unit": "Gpts/s", "ms_per_step": ms, "steps": steps,
             "tier": tier, "specialize_s": spec_s, "micro_ops": int(pinfo.n_micro_ops),
-            "flop_per_point": int(pinfo.flops_min), "roofline": roof}
+            "flop_per_point": int(pinfo.flops_min), "flop_per_point_executed": f_exec,
+            "fp32_frac_executed_branch": (None if f_exec is None or forest else pts_rank * f_exec / (ms * 1e-3) / 1e12 / peak),
+            "roofline": roof}
 
 
 def sharded_hierarchy_legs(rank, world, torch, dist):
@@ -640,6 +643,26 @@ def single_process_leg(n_devices):
                               "identical_to_1gpu": same_grid},
     }))
     return 0
+
+
+def load_executed_flops():
+    """scene -> executed-branch algorithmic flop/point (profiles/executed_flops.json)."""
+    try:
+        data = json.load(open(os.path.join(ROOT, "profiles", "executed_flops.json")))["scenes"]
+        return {k: float(v["flop_per_point_executed"]) for k, v in data.items()}
+    except Exception:  # noqa: BLE001
+        return {}
+
+
+def load_issued_flops(tier, n):
+    """FP32 operations the kernel actually ISSUED per point (FFMA = 2), from one ncu capture of this kernel at
+    this grid size (profiles/bench_issued.json; smsp__sass_thread_inst_executed_op_{ffma,fmul,fadd}_pred_on):
+    the kernel's own cheaper formulation (matrices instead of quaternions, zero coefficients dropped),
+    hence less than the algorithmic count.  Replayed, not measured in this run."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "bench_issued.json"))).get("%s_%d" % (tier, n))
+    except Exception:  # noqa: BLE001
+        return None
 
 
 def workload_config(n, world):
@@ -872,6 +895,7 @@ def run_ours(args):
     except Exception:  # noqa: BLE001
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    executed = load_executed_flops()
     roofline = {
         "bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
         "frac": achieved / peak_tflops, "traffic": traffic,
@@ -879,6 +903,14 @@ def run_ours(args):
                           "grid size, dram__bytes_read.sum + dram__bytes_write.sum per launch); not measured in this run",
         "kernel": "cc_jit_float4 (scene-specialised, packed FFMA2 lanes)" if n_ready else "cc_eval_kernel<PTS,const,FLOAT4>",
         "flop_per_point": flops_pt,
+        "flop_per_point_executed": executed.get(SCENE),
+        "achieved_executed_branch": (None if SCENE not in executed else
+                                     (total_points / world) * executed[SCENE] / (ms_step * 1e-3) / 1e12),
+        "frac_executed_branch": (None if SCENE not in executed else
+                                 (total_points / world) * executed[SCENE] / (ms_step * 1e-3) / 1e12 / peak_tflops),
+        "executed_source": "profiles/executed_flops.json (instrumented CPU oracle, 64^3 stratified subsample of this grid, "
+                           "tools/measure_executed_flops.py; SURVEY.md 8(d)); `achieved`/`frac` use the static minimum",
+        "issued": load_issued_flops(tier, n),
         "peak_source": "derived: %d SMs x 128 FP32 lanes x 2 x %.0f MHz (no FP32 figure in MEASURED_PEAKS.json)"
                        % (info.sm_count, sm_max_mhz),
         "note": "algorithmic flop/point = static minimum over data-dependent branches with the "

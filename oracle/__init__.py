@@ -55,6 +55,8 @@ def lib():
             [_fp, ctypes.c_int, _fp, ctypes.c_float, ctypes.c_float] + [ctypes.c_int] * 3 + [_u32p, _u32p, _u8p]
         )
         L.oracle_process_polygon.argtypes = [_fp, ctypes.c_float, ctypes.c_int, ctypes.c_int, _fp, _fp, _u32p, _u32p, _u32p]
+        L.oracle_executed_flops.argtypes = [_fp, ctypes.c_int, _fp, ctypes.c_float] + [ctypes.c_int] * 5 + [
+            ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]
         L.oracle_math_probe.argtypes = [ctypes.c_int, _fp, _fp, ctypes.c_long, _fp, _fp]
         L.oracle_num_threads.restype = ctypes.c_int
         L.oracle_set_num_threads.argtypes = [ctypes.c_int]
@@ -158,6 +160,18 @@ def process_polygon(box_corner, step, corners):
     _check(lib().oracle_process_polygon(_p(c), np.float32(step), cx, cy, _p(corners), _p(vertices),
                                         _p(links, _u32p), _p(starts, _u32p), _p(counter, _u32p)))
     return vertices, links, starts[: int(counter[0])].copy()
+
+
+def executed_flops(words, corner, step, dims, stride=16, x_offset=0):
+    """Mean executed-branch algorithmic flop/point (SURVEY.md 8(a3) counting rules, the reference's
+    formulation of every op) over every `stride`-th point per axis of the grid -> (mean, points)."""
+    w = _f32(words)
+    c = _f32(corner)[:3].copy()
+    nx, ny, nz = (int(d) for d in dims)
+    mean, pts = ctypes.c_double(), ctypes.c_longlong()
+    _check(lib().oracle_executed_flops(_p(w), len(w), _p(c), np.float32(step), nx, ny, nz, int(x_offset), int(stride),
+                                       ctypes.byref(mean), ctypes.byref(pts)))
+    return float(mean.value), int(pts.value)
 
 
 def math_probe(which, a, b=None):

@@ -190,6 +190,21 @@ static void release(prog_t *prog)
     prog->ins = NULL;
 }
 
+/* ---- executed-branch algorithmic flop counter ---------------------------------
+ * Counting rules of SURVEY.md 8(a3): add/sub/mul/div/sqrt = 1, FMA = 2, compare/select/abs/neg free,
+ * libm-class calls not counted; costs are those of the REFERENCE's formulation of each op (the
+ * static minimum per op is the table the device loader uses for cc_program_info.flops_min).  The
+ * counter adds, per evaluation, the cost of the branches that were actually taken. */
+static __thread unsigned long long t_flops;
+#define FL(n) (t_flops += (unsigned long long)(n))
+static const unsigned char BASE_FLOPS[OP_COUNT] = {
+    /* return store load */ 0, 0, 0, /* rectangle */ 2, /* circle */ 7, /* regular_polygon2d */ 25, /* polygon2d */ 10,
+    /* sphere */ 11, /* half_space */ 0, /* revolution_to */ 4, /* twist_revolution_to */ 16,
+    /* initial_transformation_to */ 42, /* transformation_to */ 42, /* transformation_from */ 50, /* mirror */ 0,
+    /* symmetrical_to */ 0, /* offset */ 1, /* shell */ 1, /* repetition */ 3, /* circular_repetition_to */ 14,
+    /* circular_repetition_from */ 14, /* involute_gear */ 20, /* extrusion */ 1, /* revolution_from */ 7,
+    /* twist_revolution_from */ 15, /* symmetrical_from */ 0, /* union isect sub: 9 when rounded */ 0, 0, 0};
+
 /* ---- op library ----------------------------------------------------------------- */
 
 static inline v4 mk(float x, float y, float z, float w) { v4 r = {x, y, z, w}; return r; }
@@ -199,6 +214,7 @@ static inline v4 neg(v4 a) { return mk(-a.x, -a.y, -a.z, -a.w); }
 static inline v4 perpendicular_intersection(v4 a, v4 b)
 {
     if (a.w > 0.0f && b.w > 0.0f) {
+        FL(15);
         float dist = cc_len2(a.w, b.w);
         float inv = cc_rcp(dist);
         float m1 = a.w * inv, m2 = b.w * inv;
@@ -221,7 +237,9 @@ static inline v4 rounded_union(float r, v4 o1, v4 o2)
     if (r >= 0.0f) {
         float c = cc_dot3(o1.x, o1.y, o1.z, o2.x, o2.y, o2.z);
         float x1 = r - o1.w, x2 = r - o2.w;
+        FL(9);
         if (c * x1 < x2 && c * x2 < x1 && (x1 > 0.0f || x2 > 0.0f)) {
+            FL(12);
             float num = cc_fma(-((2.0f * c) * x1), x2, cc_fma(x1, x1, x2 * x2));
             float den = cc_fma(-c, c, 1.0f);
             float d = r - cc_sqrt(fmaxf(cc_div(num, den), 0.0f));
@@ -269,6 +287,7 @@ static inline v4 regular_polygon2d(const ins_t *I, v4 co)
     float s, c;
     cc_sincos(modAlpha, &s, &c);
     if (fabsf(s * len) > I->k[0]) {
+        FL(15);
         float ny, nx;
         cc_sincos(cc_fma(cc_sign(s), piOverN, t), &ny, &nx);
         float dx = co.x - nx * r, dy = co.y - ny * r;
@@ -297,6 +316,7 @@ static inline v4 polygon2d(const ins_t *I, v4 co)
         if (((py < co.y) != (cy < co.y)) && (dy * cc_fma(snx, tqx, sny * tqy) > 0.0f))
             outside = -outside;
         float t = cc_fma(dx, tqx, dy * tqy) * e[4];
+        FL(15 + (t > 1.0f ? 0 : (t >= 0.0f ? 7 : 5)));
         if (t > 1.0f) continue;
         float cnx, cny, cd;
         int civ;
@@ -336,6 +356,7 @@ static inline v4 polygon2d_alt(const ins_t *I, v4 co)
         if ((prev_below != cur_below) && side > 0.0f) outside = -outside;
         prev_below = cur_below;
         float t = cc_fma(dx, tqx, dy * tqy) * e[4];
+        FL(15 + (t > 1.0f ? 0 : (t >= 0.0f ? 7 : 5)));
         float tc = fmaxf(t, 0.0f);
         float tcx = cc_fma(-tc, dx, tqx), tcy = cc_fma(-tc, dy, tqy);
         float cd = cc_fma(tcx, tcx, tcy * tcy);
@@ -379,6 +400,7 @@ static inline v4 involute_gear(const ins_t *I, v4 co)
         if (wrapped > toothAngle) { nx = -nx; ny = -ny; }
         return mk(nx, ny, 0, (d - halfTooth) * len);
     }
+    FL(10);
     float phi = involuteAlpha + cc_acos(cc_div(baseRadius, len));
     float base = alpha - involuteAlpha;
     float normalAngle = (wrapped < toothAngle) ? (CC_PI_F - phi) - base : phi - base;
@@ -410,6 +432,7 @@ static inline v4 twist_revolution_from(const ins_t *I, v4 inPlane, v4 co)
     float wd = icd - minorR;
     float bound, dx, dy;
     if (ad == 0.0f) return mk(1, 0, 0, r - minorR);
+    if (!(wd > I->k[1])) FL(25);
     if (wd > I->k[1]) {
         float inv = cc_rcp(icd);
         bound = wd; dx = ipx * inv; dy = ipy * inv;
@@ -458,6 +481,7 @@ static v4 evaluate(const prog_t *prog, float px, float py, float pz)
     const ins_t *I = prog->ins;
     for (;; ++I) {
         const float *p = I->p;
+        FL(BASE_FLOPS[I->op]);
 #define in2 (registers[I->reg]) /* second operand of arity-2 ops / source of _load */
         switch (I->op) {
         case OP_RETURN: return last;
@@ -605,6 +629,35 @@ int oracle_grid_eval(const float *words, int n_words, const float *corner, float
             }
         }
     release(&prog);
+    return 0;
+}
+
+/* Mean executed-branch algorithmic flop/point over every `stride`-th point per axis of the grid
+ * (a stratified subsample; SURVEY.md 8(d): 64^3 of the config grid). */
+int oracle_executed_flops(const float *words, int n_words, const float *corner, float step,
+                          int nx, int ny, int nz, int x_offset, int stride, double *mean, long long *points)
+{
+    prog_t prog;
+    int rc = prepare(words, n_words, &prog);
+    if (rc < 0) return rc;
+    if (stride < 1) stride = 1;
+    unsigned long long total = 0;
+    long long count = 0;
+#pragma omp parallel for collapse(2) schedule(dynamic, 4) reduction(+ : total, count)
+    for (int x = stride / 2; x < nx; x += stride)
+        for (int y = stride / 2; y < ny; y += stride) {
+            float px = grid_coord(corner[0], step, (unsigned)(x + x_offset));
+            float py = grid_coord(corner[1], step, (unsigned)y);
+            for (int z = stride / 2; z < nz; z += stride) {
+                t_flops = 0;
+                (void)evaluate(&prog, px, py, grid_coord(corner[2], step, (unsigned)z));
+                total += t_flops;
+                ++count;
+            }
+        }
+    release(&prog);
+    *mean = count ? (double)total / (double)count : 0.0;
+    *points = count;
     return 0;
 }
 

@@ -3,6 +3,8 @@ mass-property post-processing."""
 import itertools
 import math
 import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 import sys
 
 import numpy as np
@@ -289,3 +291,21 @@ def test_sort_leaf_corners_restores_the_single_device_order():
         # dealing to ranks permutes the list; the sort must undo any permutation
         assert np.array_equal(sort_leaf_corners(shuffled, plan), want)
         assert np.array_equal(sort_leaf_corners(want[::-1], plan), want)
+
+
+def test_executed_flops_file_matches_the_instrumented_oracle(scenes):
+    """profiles/executed_flops.json (what bench.py reports as flop_per_point_executed) is the oracle's
+    executed-branch count; re-measured here on a coarser subsample, and bracketed by the loader's
+    static minimum / maximum."""
+    import json
+    import oracle
+    from codecad_b200 import _lib
+    data = json.load(open(os.path.join(ROOT, "profiles", "executed_flops.json")))["scenes"]
+    for name in ("cfg_csg_example", "cfg_menger_sponge", "cfg_airfoil", "cfg_planetary"):
+        s = scenes[name]
+        n = data[name]["grid"]
+        corner, step = s.grid(n)
+        mean, pts = oracle.executed_flops(s.words, corner, step, (n, n, n), stride=n // 32)
+        info, _ = _lib.decode_program(s.words)
+        assert info.flops_min <= data[name]["flop_per_point_executed"] <= info.flops_max
+        assert mean == pytest.approx(data[name]["flop_per_point_executed"], rel=0.02)
