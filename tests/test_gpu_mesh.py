@@ -120,9 +120,14 @@ def test_every_vertex_lies_on_the_surface(cb, scenes, name):
     size = max(b - a for a, b in zip(s.box_a, s.box_b))
     res = size / 96
     scene = CompiledScene(s.words, 3, s.box_a, s.box_b, 2 * res, name + "@96")
-    vertices, _, _ = mesh_arrays(scene, 32)
-    pts = np.asarray(vertices, np.float64).reshape(-1, 3)
+    vertices, _, boxes = mesh_arrays(scene, 32)
+    pts = np.asarray(vertices, np.float64).reshape(-1, 3).copy()
     assert len(pts) > 1000
+    # The reference's post-transform (rendering/mesh.py:68-72) undoes the y flip of grid_eval_pymcubes
+    # by negating the flipped row index, which leaves every block — hence the whole mesh — translated
+    # by -(ny - 1) * resolution along y.  Reproduced faithfully (STL consumers see the reference's
+    # coordinates); undone here to compare with the field.
+    pts[:, 1] += (int(boxes.dims[1]) - 1) * res
     d = cb.evaluate_points(scene, pts.astype(np.float32))[:, 3]
     # linear interpolation along a cell edge of a 1-Lipschitz field: the error is second order in the
     # cell size where the field is smooth and at most one cell near creases
@@ -148,7 +153,7 @@ def test_volume_and_area_converge_to_the_analytic_solid(cb, scenes):
         errs = []
         for n in (24, 48, 96, 192):
             scene = CompiledScene(s.words, 3, s.box_a, s.box_b, 2 * size / n, "%s@%d" % (name, n))
-            soup = np.asarray(mesh_arrays(scene, 32)[0], np.float64).reshape(-1, 3, 3)
+            soup = np.asarray(mesh_arrays(scene, 32)[0], np.float64).reshape(-1, 3, 3)   # (translated along y: no effect here)
             errs.append((abs(mc.signed_volume(soup) - volume) / volume, abs(_area(soup) - area) / area))
         v_err, a_err = zip(*errs)
         assert v_err[-1] <= 2e-3 and a_err[-1] <= 2e-2, (name, errs)
