@@ -18,6 +18,16 @@ typedef unsigned long size_t;
 #define CC_THREADS 128  // CTA size of the precompiled kernels; specialised kernels may override it
 #endif
 
+// polygon2d edge table (microcode, after RETURN; __constant__ array in the specialised kernels):
+// n edges of (px, py, dx, dy, 1/|d|^2, cy), then
+#define CC_POLY_EDGE_WORDS 6
+// after the n edges: one entry per group of CC_POLY_GROUP consecutive edges, (xmin, xmax, ymin, ymax of
+// the group's vertices, x and y of its first vertex) — lets the edge loop skip whole groups exactly
+#define CC_POLY_GROUP 8
+#define CC_POLY_GROUP_WORDS 6
+#define CC_POLY_TABLE_WORDS(n) (CC_POLY_EDGE_WORDS * (n) + CC_POLY_GROUP_WORDS * (((n) + CC_POLY_GROUP - 1) / CC_POLY_GROUP))
+
+
 enum cc_sink_kind {
     CC_SINK_FLOAT4 = 0, CC_SINK_PYMCUBES, CC_SINK_CLASSIFY, CC_SINK_MASS,
     CC_SINK_RAY, CC_SINK_BITMAP,  // image renderers (cc_render.cuh), one point per thread

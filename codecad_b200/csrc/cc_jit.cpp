@@ -407,8 +407,9 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
             const uint32_t n = (uint32_t)(*reinterpret_cast<const float *>(&c[pc + 1]));
             const uint32_t off = c[pc + 2];
             const int k = g.n_tables++;
-            g.consts << "__constant__ float cc_poly_" << k << "[" << 6 * n << "] = {";
-            for (uint32_t i = 0; i < 6 * n; ++i) g.consts << (i ? ", " : "") << g.C(off + i);
+            const uint32_t words = CC_POLY_TABLE_WORDS(n);
+            g.consts << "__constant__ float cc_poly_" << k << "[" << words << "] = {";
+            for (uint32_t i = 0; i < words; ++i) g.consts << (i ? ", " : "") << g.C(off + i);
             g.consts << "};\n";
             o << "        CC_EACH L[g] = cc_op_polygon_table(cc_poly_" << k << ", " << n << "u, L[g]);\n";
             break;

@@ -29,7 +29,7 @@ enum cc_mop : uint32_t {
     MOP_RECTANGLE,     // hw, hh
     MOP_CIRCLE,        // r
     MOP_REGPOLY,       // piOverN, r, r*sin, r*cos, 2*piOverN
-    MOP_POLYGON,       // n, word offset of its edge table: n * (px, py, dx, dy, 1/|d|^2, cy), stored after RETURN
+    MOP_POLYGON,       // n, word offset of its edge table: n * (px, py, dx, dy, 1/|d|^2, cy) + group entries, stored after RETURN
     MOP_SPHERE,        // r
     MOP_HALF_SPACE,
     MOP_REV_TO,
@@ -84,8 +84,6 @@ enum cc_mop : uint32_t {
 #define CC_LEN_7 8   // up to 7 parameters
 #define CC_LEN_T 16  // 12 parameters (+3 spare)
 #define CC_LEN_PRIM 28
-#define CC_POLY_EDGE_WORDS 6
-
 #define CC_CONST_WORDS 16128  // microcode words that fit the 63 KB __constant__ window
 
 #endif

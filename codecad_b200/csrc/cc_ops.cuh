@@ -10,6 +10,7 @@
 #define CC_OPS_CUH
 
 #include "cc_math.cuh"
+#include "cc_device_types.h"
 
 // heavy, rarely dominant ops are real functions: inlining them PTS times per kernel variant
 // would push the interpreter out of the instruction cache
@@ -509,6 +510,16 @@ CC_DEV float4 cc_polygon2d_finish(const FETCH &fetch, float best, float x, float
     return make_float4(nnx * inv, nny * inv, 0.0f, distance);
 }
 
+// Edge groups.  The table continues with one entry per group of CC_POLY_GROUP consecutive edges:
+// the bounding interval of the group's vertices and its first vertex.  A group is skipped when
+// (a) no lane can improve on the nearest distance there: the squared distance to the group's
+//     bounding box exceeds B, an upper bound of the FINAL nearest value (the squared distance to the
+//     first vertex of some group: the candidate chain that starts at a vertex only ever gets closer);
+//     every candidate of the group then loses the strict `<` whatever the running value is, and
+// (b) no lane's y lies inside the group's y range, so no edge of it can flip the crossing parity.
+// Both tests carry a 2e-5 relative margin against the rounding of the candidate distances; the
+// skipped work could not have changed a bit.  The points of a warp are neighbours (often they share
+// x and y exactly: the extrusion axis is the fastest grid axis), so the votes rarely split.
 template <class V, class FETCH>
 CC_DEV cc_val<V> cc_polygon2d_v(const FETCH &fetch, uint32_t n, cc_val<V> co)
 {
@@ -516,36 +527,57 @@ CC_DEV cc_val<V> cc_polygon2d_v(const FETCH &fetch, uint32_t n, cc_val<V> co)
     const V zero = vbc<V>(0.0f), one = vbc<V>(1.0f);
     V nearest = vbc<V>(__int_as_float(0x7f800000)), best = vbc<V>(-1.0f), outside = one;
     M prev_below = vlt(vbc<V>(n ? fetch(1) : 0.0f), co.y);  // previousPoint.y < coords.y of edge 0
-    uint32_t e = 0;
-#pragma unroll 2
-    for (uint32_t i = 0; i < n; ++i, e += 6) {
-        const float px = fetch(e), py = fetch(e + 1), dx = fetch(e + 2), dy = fetch(e + 3), inv = fetch(e + 4),
-                    cy = fetch(e + 5);
-        const V tqx = vsub(co.x, vbc<V>(px)), tqy = vsub(co.y, vbc<V>(py));
-        // polygons2d.cl:24-26: even-odd crossing test
-        const M cur_below = vlt(vbc<V>(cy), co.y);
-        const M straddle = mxor(prev_below, cur_below);
-        // few edges straddle a point's y, and the points of a warp are neighbours: skip the side
-        // test when no lane needs it (warp-uniform branch; `outside` is unchanged in that case)
-        if (__any_sync(0xffffffffu, many(straddle))) {
-            const V side = vmul(vbc<V>(dy), vfma(vbc<V>(-dy), tqx, vmul(vbc<V>(dx), tqy)));
-            outside = vsel(mand(straddle, vgt(side, zero)), vneg(outside), outside);
+    const uint32_t gt = CC_POLY_EDGE_WORDS * n, ng = (n + CC_POLY_GROUP - 1) / CC_POLY_GROUP;
+    V bound = vbc<V>(__int_as_float(0x7f800000));
+    for (uint32_t g = 0; g < ng; ++g) {
+        const V qx = vsub(co.x, vbc<V>(fetch(gt + 6 * g + 4))), qy = vsub(co.y, vbc<V>(fetch(gt + 6 * g + 5)));
+        bound = vmin(bound, vfma(qx, qx, vmul(qy, qy)));
+    }
+    bound = vmul(bound, vbc<V>(1.00002f));
+    for (uint32_t g = 0; g < ng; ++g) {
+        const float xmin = fetch(gt + 6 * g), xmax = fetch(gt + 6 * g + 1), ymin = fetch(gt + 6 * g + 2), ymax = fetch(gt + 6 * g + 3);
+        const V ex = vmax(vmax(vsub(vbc<V>(xmin), co.x), vsub(co.x, vbc<V>(xmax))), zero);
+        const V ey = vmax(vmax(vsub(vbc<V>(ymin), co.y), vsub(co.y, vbc<V>(ymax))), zero);
+        const V lb = vmul(vfma(ex, ex, vmul(ey, ey)), vbc<V>(0.99998f));
+        const M above = vgt(co.y, vbc<V>(ymax));                      // every vertex of the group is below the point
+        const M may_cross = mand(vgt(co.y, vbc<V>(ymin)), mnot(above));
+        const M may_win = mnot(vgt(lb, bound));                       // (NaN coordinates: never skipped)
+        if (!__any_sync(0xffffffffu, many(mor(may_cross, may_win)))) {
+            prev_below = above;  // = (y of the group's last vertex < coords.y)
+            continue;
         }
-        prev_below = cur_below;
-        // :28-52: nearest point of the edge, t > 1 belongs to the next edge's start vertex
-        // For t < 0 (or NaN) the candidate is the start vertex, |toQuery|^2.  Clamping t at zero
-        // gives exactly that through the segment formula: fma(-0, d, tq) == tq up to the sign of a
-        // zero, which the squares erase; fmaxf returns 0 for a NaN t, the branch the reference's
-        // `t >= 0` test takes as well.
-        const V t = vmul(vfma(vbc<V>(dx), tqx, vmul(vbc<V>(dy), tqy)), vbc<V>(inv));
-        const V tc = vmax(t, zero);
-        const V tcx = vfma(vneg(tc), vbc<V>(dx), tqx), tcy = vfma(vneg(tc), vbc<V>(dy), tqy);
-        const V cd = vfma(tcx, tcx, vmul(tcy, tcy));
-        // :55-60
-        const M better = mand(mnot(vgt(t, one)), vlt(cd, nearest));
-        nearest = vsel(better, cd, nearest);
-        best = vsel(better, vbc<V>((float)i), best);
-        (void)py;
+        const uint32_t i1 = min(n, (g + 1) * CC_POLY_GROUP);
+        uint32_t e = CC_POLY_EDGE_WORDS * g * CC_POLY_GROUP;
+#pragma unroll 2
+        for (uint32_t i = g * CC_POLY_GROUP; i < i1; ++i, e += 6) {
+            const float px = fetch(e), py = fetch(e + 1), dx = fetch(e + 2), dy = fetch(e + 3), inv = fetch(e + 4),
+                        cy = fetch(e + 5);
+            const V tqx = vsub(co.x, vbc<V>(px)), tqy = vsub(co.y, vbc<V>(py));
+            // polygons2d.cl:24-26: even-odd crossing test
+            const M cur_below = vlt(vbc<V>(cy), co.y);
+            const M straddle = mxor(prev_below, cur_below);
+            // few edges straddle a point's y, and the points of a warp are neighbours: skip the side
+            // test when no lane needs it (warp-uniform branch; `outside` is unchanged in that case)
+            if (__any_sync(0xffffffffu, many(straddle))) {
+                const V side = vmul(vbc<V>(dy), vfma(vbc<V>(-dy), tqx, vmul(vbc<V>(dx), tqy)));
+                outside = vsel(mand(straddle, vgt(side, zero)), vneg(outside), outside);
+            }
+            prev_below = cur_below;
+            // :28-52: nearest point of the edge, t > 1 belongs to the next edge's start vertex
+            // For t < 0 (or NaN) the candidate is the start vertex, |toQuery|^2.  Clamping t at zero
+            // gives exactly that through the segment formula: fma(-0, d, tq) == tq up to the sign of a
+            // zero, which the squares erase; fmaxf returns 0 for a NaN t, the branch the reference's
+            // `t >= 0` test takes as well.
+            const V t = vmul(vfma(vbc<V>(dx), tqx, vmul(vbc<V>(dy), tqy)), vbc<V>(inv));
+            const V tc = vmax(t, zero);
+            const V tcx = vfma(vneg(tc), vbc<V>(dx), tqx), tcy = vfma(vneg(tc), vbc<V>(dy), tqy);
+            const V cd = vfma(tcx, tcx, vmul(tcy, tcy));
+            // :55-60
+            const M better = mand(mnot(vgt(t, one)), vlt(cd, nearest));
+            nearest = vsel(better, cd, nearest);
+            best = vsel(better, vbc<V>((float)i), best);
+            (void)py;
+        }
     }
     cc_val<V> r;
 #pragma unroll

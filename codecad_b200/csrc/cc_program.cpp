@@ -522,7 +522,7 @@ int cc_decode_program(const float *words, uint32_t n_words, cc_decoded *out, std
             q = e.emit(MOP_POLYGON, src, CC_LEN_0);
             q[0] = (float)n;
             poly_fixups.push_back(e.last_header);  // word 2 <- offset of the edge table
-            std::vector<float> &tab = poly_tables.emplace_back((size_t)CC_POLY_EDGE_WORDS * n);
+            std::vector<float> &tab = poly_tables.emplace_back((size_t)CC_POLY_TABLE_WORDS(n));
             float *eg = tab.data();
             for (int k = 0; k < n; ++k) {
                 int j = (k + n - 1) % n;  // previous vertex, polygons2d.cl:13,17-18
@@ -533,6 +533,17 @@ int cc_decode_program(const float *words, uint32_t n_words, cc_decoded *out, std
                 eg[4] = 1.0f / std::fmaf(dx, dx, dy * dy);
                 eg[5] = cy;
                 eg += CC_POLY_EDGE_WORDS;
+            }
+            for (int g0 = 0; g0 < n; g0 += CC_POLY_GROUP) {  // bounding interval + first vertex of every edge group
+                const int j = (g0 + n - 1) % n;
+                float xmin = p[1 + 2 * j], xmax = xmin, ymin = p[2 + 2 * j], ymax = ymin;
+                for (int k = g0; k < std::min(n, g0 + CC_POLY_GROUP); ++k) {
+                    xmin = std::fmin(xmin, p[1 + 2 * k]); xmax = std::fmax(xmax, p[1 + 2 * k]);
+                    ymin = std::fmin(ymin, p[2 + 2 * k]); ymax = std::fmax(ymax, p[2 + 2 * k]);
+                }
+                eg[0] = xmin; eg[1] = xmax; eg[2] = ymin; eg[3] = ymax;
+                eg[4] = p[1 + 2 * j]; eg[5] = p[2 + 2 * j];
+                eg += CC_POLY_GROUP_WORDS;
             }
             cost(10 + 15u * (uint32_t)n, 10 + 22u * (uint32_t)n);
             break;

@@ -62,6 +62,7 @@ typedef struct {
     const float *p; /* parameters inside the caller's word array */
     float k[16];    /* per-instruction constants derived from the parameters */
     float *edges;   /* polygon2d: 5 floats per edge (px, py, dx, dy, 1/|d|^2) */
+    float *groups;  /* polygon2d, product formulation only: per 8 edges (xmin, xmax, ymin, ymax, first vertex x, y) */
     int n;
 } ins_t;
 
@@ -170,6 +171,17 @@ static int prepare(const float *words, int n_words, prog_t *prog)
                 e[0] = px; e[1] = py; e[2] = dx; e[3] = dy;
                 e[4] = cc_rcp(cc_fma(dx, dx, dy * dy));
             }
+            I->groups = (float *)malloc(sizeof(float) * 6 * (size_t)((n + 7) / 8 + 1));
+            for (int g0 = 0, g = 0; g0 < n; g0 += 8, ++g) {
+                int j = (g0 + n - 1) % n;
+                float xmin = p[1 + 2 * j], xmax = xmin, ymin = p[2 + 2 * j], ymax = ymin;
+                for (int k = g0; k < n && k < g0 + 8; ++k) {
+                    xmin = fminf(xmin, p[1 + 2 * k]); xmax = fmaxf(xmax, p[1 + 2 * k]);
+                    ymin = fminf(ymin, p[2 + 2 * k]); ymax = fmaxf(ymax, p[2 + 2 * k]);
+                }
+                float *q = I->groups + 6 * g;
+                q[0] = xmin; q[1] = xmax; q[2] = ymin; q[3] = ymax; q[4] = p[1 + 2 * j]; q[5] = p[2 + 2 * j];
+            }
             break;
         }
         default:
@@ -185,7 +197,7 @@ static int prepare(const float *words, int n_words, prog_t *prog)
 
 static void release(prog_t *prog)
 {
-    for (int i = 0; i < prog->count; ++i) free(prog->ins[i].edges);
+    for (int i = 0; i < prog->count; ++i) { free(prog->ins[i].edges); free(prog->ins[i].groups); }
     free(prog->ins);
     prog->ins = NULL;
 }
@@ -347,7 +359,24 @@ static inline v4 polygon2d_alt(const ins_t *I, v4 co)
 {
     float nearest = INFINITY, best = -1.0f, outside = 1.0f;
     int prev_below = I->n ? (I->edges[1] < co.y) : 0;
-    for (int i = 0; i < I->n; ++i) {
+    /* edge groups (cc_ops.cuh): B bounds the final nearest value from above; a group whose bounding box
+     * is farther than B, and whose y range does not contain the point, cannot change a bit */
+    const int ng = (I->n + 7) / 8;
+    float bound = INFINITY;
+    for (int g = 0; g < ng; ++g) {
+        float qx = co.x - I->groups[6 * g + 4], qy = co.y - I->groups[6 * g + 5];
+        bound = fminf(bound, cc_fma(qx, qx, qy * qy));
+    }
+    bound = bound * 1.00002f;
+    for (int g = 0; g < ng; ++g) {
+        const float *q = I->groups + 6 * g;
+        float ex = fmaxf(fmaxf(q[0] - co.x, co.x - q[1]), 0.0f), ey = fmaxf(fmaxf(q[2] - co.y, co.y - q[3]), 0.0f);
+        float lb = cc_fma(ex, ex, ey * ey) * 0.99998f;
+        int above = co.y > q[3];
+        int may_cross = (co.y > q[2]) && !above;
+        int may_win = !(lb > bound);
+        if (!may_cross && !may_win) { prev_below = above; continue; }
+    for (int i = 8 * g; i < I->n && i < 8 * g + 8; ++i) {
         const float *e = I->edges + 5 * i;
         float px = e[0], py = e[1], dx = e[2], dy = e[3], cy = I->p[2 + 2 * i];
         float tqx = co.x - px, tqy = co.y - py;
@@ -364,6 +393,7 @@ static inline v4 polygon2d_alt(const ins_t *I, v4 co)
         nearest = better ? cd : nearest;
         best = better ? (float)i : best;
         (void)py;
+    }
     }
     float nnx = 0.0f, nny = 0.0f;
     int nearest_is_vertex = 0;
