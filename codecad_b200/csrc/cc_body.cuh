@@ -130,6 +130,11 @@ CC_DEV void cc_kernel_body(const cc_eval_args &a, EVAL &eval)
                 if (lane == 0 && w) atomicAdd(dst + i, w);
             }
         }
+        // The leaf level of mass_properties runs with threshold 0 (mass_properties.py:87-90): `inside` is
+        // v <= -0 and a hit would need v < 0 on top of !inside — no cell can qualify, the list stays
+        // empty, and the tile neither ranks nor waits for its predecessors.  (Warp-uniform: a launch
+        // argument.)  The leaf launch is 98 % of a mass_properties call.
+        if (SINK == CC_SINK_MASS && a.threshold == 0.0f) return;
         // ranks inside the tile, in cell order (j major, then warp, then lane)
         uint32_t ballot[PTS];
 #pragma unroll

@@ -22,9 +22,9 @@ typedef unsigned long size_t;
 // n edges of (px, py, dx, dy, 1/|d|^2, cy), then
 #define CC_POLY_EDGE_WORDS 6
 // after the n edges: one entry per group of CC_POLY_GROUP consecutive edges, (xmin, xmax, ymin, ymax of
-// the group's vertices, x and y of its first vertex) — lets the edge loop skip whole groups exactly
+// the group's vertices) — lets the edge loop skip whole groups exactly
 #define CC_POLY_GROUP 8
-#define CC_POLY_GROUP_WORDS 6
+#define CC_POLY_GROUP_WORDS 4
 #define CC_POLY_TABLE_WORDS(n) (CC_POLY_EDGE_WORDS * (n) + CC_POLY_GROUP_WORDS * (((n) + CC_POLY_GROUP - 1) / CC_POLY_GROUP))
 
 

@@ -534,7 +534,7 @@ int cc_decode_program(const float *words, uint32_t n_words, cc_decoded *out, std
                 eg[5] = cy;
                 eg += CC_POLY_EDGE_WORDS;
             }
-            for (int g0 = 0; g0 < n; g0 += CC_POLY_GROUP) {  // bounding interval + first vertex of every edge group
+            for (int g0 = 0; g0 < n; g0 += CC_POLY_GROUP) {  // bounding interval of every edge group
                 const int j = (g0 + n - 1) % n;
                 float xmin = p[1 + 2 * j], xmax = xmin, ymin = p[2 + 2 * j], ymax = ymin;
                 for (int k = g0; k < std::min(n, g0 + CC_POLY_GROUP); ++k) {
@@ -542,7 +542,6 @@ int cc_decode_program(const float *words, uint32_t n_words, cc_decoded *out, std
                     ymin = std::fmin(ymin, p[2 + 2 * k]); ymax = std::fmax(ymax, p[2 + 2 * k]);
                 }
                 eg[0] = xmin; eg[1] = xmax; eg[2] = ymin; eg[3] = ymax;
-                eg[4] = p[1 + 2 * j]; eg[5] = p[2 + 2 * j];
                 eg += CC_POLY_GROUP_WORDS;
             }
             cost(10 + 15u * (uint32_t)n, 10 + 22u * (uint32_t)n);

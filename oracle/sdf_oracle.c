@@ -62,7 +62,7 @@ typedef struct {
     const float *p; /* parameters inside the caller's word array */
     float k[16];    /* per-instruction constants derived from the parameters */
     float *edges;   /* polygon2d: 5 floats per edge (px, py, dx, dy, 1/|d|^2) */
-    float *groups;  /* polygon2d, product formulation only: per 8 edges (xmin, xmax, ymin, ymax, first vertex x, y) */
+    float *groups;  /* polygon2d, product formulation only: per 8 edges (xmin, xmax, ymin, ymax) + 2 spare */
     int n;
 } ins_t;
 
@@ -355,6 +355,11 @@ static inline v4 polygon2d(const ins_t *I, v4 co)
  * the edge that produced it, t clamped at zero instead of a separate start-vertex candidate, crossing
  * test reusing the previous end-point comparison; feature kind and normal recomputed after the loop. */
 static int g_polygon_alt = 0;
+static unsigned long long g_polygon_groups[3]; /* product formulation: edge groups seen / run for crossing only / run for distance */
+void oracle_polygon_group_counters(unsigned long long out[3], int reset)
+{
+    for (int i = 0; i < 3; ++i) { out[i] = g_polygon_groups[i]; if (reset) g_polygon_groups[i] = 0; }
+}
 static inline v4 polygon2d_alt(const ins_t *I, v4 co)
 {
     float nearest = INFINITY, best = -1.0f, outside = 1.0f;
@@ -363,8 +368,8 @@ static inline v4 polygon2d_alt(const ins_t *I, v4 co)
      * is farther than B, and whose y range does not contain the point, cannot change a bit */
     const int ng = (I->n + 7) / 8;
     float bound = INFINITY;
-    for (int g = 0; g < ng; ++g) {
-        float qx = co.x - I->groups[6 * g + 4], qy = co.y - I->groups[6 * g + 5];
+    for (int i = 0; i < I->n; i += 4) { /* CC_POLY_BOUND_STRIDE */
+        float qx = co.x - I->edges[5 * i], qy = co.y - I->edges[5 * i + 1];
         bound = fminf(bound, cc_fma(qx, qx, qy * qy));
     }
     bound = bound * 1.00002f;
@@ -375,7 +380,23 @@ static inline v4 polygon2d_alt(const ins_t *I, v4 co)
         int above = co.y > q[3];
         int may_cross = (co.y > q[2]) && !above;
         int may_win = !(lb > bound);
+        __atomic_fetch_add(&g_polygon_groups[0], 1ull, __ATOMIC_RELAXED);
         if (!may_cross && !may_win) { prev_below = above; continue; }
+        __atomic_fetch_add(&g_polygon_groups[1 + (may_win ? 1 : 0)], 1ull, __ATOMIC_RELAXED);
+        if (!may_win) { /* crossing parity only */
+            for (int i = 8 * g; i < I->n && i < 8 * g + 8; ++i) {
+                const float *e = I->edges + 5 * i;
+                float cy = I->p[2 + 2 * i];
+                int cur_below = cy < co.y;
+                if (prev_below != cur_below) {
+                    float tqx = co.x - e[0], tqy = co.y - e[1];
+                    float side = e[3] * cc_fma(-e[3], tqx, e[2] * tqy);
+                    if (side > 0.0f) outside = -outside;
+                }
+                prev_below = cur_below;
+            }
+            continue;
+        }
     for (int i = 8 * g; i < I->n && i < 8 * g + 8; ++i) {
         const float *e = I->edges + 5 * i;
         float px = e[0], py = e[1], dx = e[2], dy = e[3], cy = I->p[2 + 2 * i];
