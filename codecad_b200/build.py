@@ -49,6 +49,10 @@ def build(force=False, verbose=False):
     """One object per source, compiled in parallel and only when stale (objects live in the
     git-ignored codecad_b200/build/), then linked into the in-tree shared library."""
     if not force and not needs_build():
+        try:
+            build_pylist()
+        except Exception:  # noqa: BLE001
+            pass
         return SO
     nvcc = find_nvcc()
     os.makedirs(OBJ_DIR, exist_ok=True)
@@ -65,8 +69,24 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("nvcc failed for " + ", ".join(failed))
     subprocess.run([nvcc, "-shared", "-o", SO] + objs + ["-ldl"], check=True)
+    try:
+        build_pylist(force)
+    except Exception as exc:  # noqa: BLE001 - optional accelerator of a Python-side conversion
+        print("codecad_b200/_cc_pylist.so not built:", exc)
     return SO
+
+
+def build_pylist(force=False):
+    """The small CPython helper (csrc/cc_pylist.c): host-only, plain gcc."""
+    import sysconfig
+    src = os.path.join(CSRC, "cc_pylist.c")
+    so = os.path.join(HERE, "_cc_pylist.so")
+    if not force and os.path.exists(so) and os.path.getmtime(so) >= os.path.getmtime(src):
+        return so
+    subprocess.run(["gcc", "-O2", "-shared", "-fPIC", "-I", sysconfig.get_paths()["include"], "-o", so, src], check=True)
+    return so
 
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build_pylist(force="--force" in sys.argv))

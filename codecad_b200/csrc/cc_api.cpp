@@ -1029,12 +1029,13 @@ static int grid_to_host_share(const cc_program *prog, const float corner[3], flo
     const size_t elem = 16;
     const int layout = CC_LAYOUT_INDEX3_FLOAT4;
     const int RING = Context::kRing;
-    // slab size: large enough that the per-copy overhead vanishes (64 MiB slabs reached 46 of the
-    // 57 GB/s one big copy gets on the test box), small enough that the ring stays modest
+    // slab size, measured on the test box against 51.9 GB/s for one bare copy of the whole grid:
+    // 16 MiB slabs 50.6 GB/s, 32 MiB 49.2, 64 MiB 44.7, 128 MiB 37.9, 256 MiB 33.9 — a slab that the
+    // copy engine still finds in the 126 MB L2 is read there instead of in HBM
     static const uint64_t slab_mib = [] {
         const char *t = getenv("CODECAD_B200_SLAB_MIB");
         const long v = t ? atol(t) : 0;
-        return (uint64_t)(v > 0 ? v : 64);
+        return (uint64_t)(v > 0 ? v : 16);
     }();
     uint32_t slab_x = (uint32_t)std::max<uint64_t>(1, (slab_mib << 20) / (plane * elem));
     slab_x = std::min(slab_x, nx);

@@ -47,6 +47,12 @@ def calculate_block_sizes(box, dimension, resolution, grid_size, overlap, level_
     return [(top, Vector(*top_dims))] + [(c, Vector(*full)) for c in reversed(cells)]
 
 
+try:  # optional C helper (csrc/cc_pylist.c) that builds the list of block tuples
+    from . import _cc_pylist as _pylist
+except ImportError:
+    _pylist = None
+
+
 def _levels(block_sizes):
     arr = (_lib.Level * len(block_sizes))()
     for i, (cell, dims) in enumerate(block_sizes):
@@ -97,6 +103,10 @@ class LeafBlocks(collections.abc.Sequence):
         self._items = None
 
     def _materialise(self):
+        if self._items is None and _pylist is not None:
+            self._items = _pylist.leaf_blocks(Vector, self.dims, np.ascontiguousarray(self.corners, dtype=np.float64),
+                                              self.step, np.ascontiguousarray(self.int_corners, dtype=np.int64),
+                                              self.int_step)
         if self._items is None:
             new, vec = tuple.__new__, itertools.repeat(Vector)
             self._items = list(zip(itertools.repeat(self.dims), map(new, vec, self.corners.tolist()),

@@ -309,3 +309,26 @@ def test_executed_flops_file_matches_the_instrumented_oracle(scenes):
         info, _ = _lib.decode_program(s.words)
         assert info.flops_min <= data[name]["flop_per_point_executed"] <= info.flops_max
         assert mean == pytest.approx(data[name]["flop_per_point_executed"], rel=0.02)
+
+
+def test_leaf_block_list_built_in_c_equals_the_python_form():
+    """csrc/cc_pylist.c builds subdivision()'s list of block tuples; same objects as the Python form."""
+    import importlib
+    sub = importlib.import_module("codecad_b200.subdivision")
+    if sub._pylist is None:
+        pytest.skip("codecad_b200/_cc_pylist.so not built")
+    rng = np.random.default_rng(2)
+    ic = rng.integers(-5000, 5000, (777, 3)).astype(np.int64)
+    c = ic * 0.195 + (-50.1)
+    dims = Vector(16, 16, 16)
+    fast = list(sub.LeafBlocks(dims, c, 0.195, ic, 15))
+    saved, sub._pylist = sub._pylist, None
+    try:
+        slow = list(sub.LeafBlocks(dims, c, 0.195, ic, 15))
+    finally:
+        sub._pylist = saved
+    assert fast == slow and len(fast) == 777
+    b = fast[3]
+    assert type(b) is tuple and type(b[1]) is Vector and type(b[3]) is Vector
+    assert type(b[1].x) is float and type(b[3].z) is int and b[0] is dims and b[4] == 15
+    assert sub.LeafBlocks(dims, c[:0], 0.195, ic[:0], 15)._materialise() == []
