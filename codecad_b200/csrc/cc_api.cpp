@@ -37,6 +37,9 @@ struct Context {
     int pts = 0, prog_space = 0;  // tuning overrides, 0 = auto
     int jit_mode = 1;             // 0 never, 1 background (default), 2 compile at first use and wait
     int forest_mode = 1;          // 1: dense grids of union-forest programs use the culling kernel (cc_forest.cu)
+    int parts_mode = 1;           // 1: dense grids of assemblies skip, per brick, the parts that cannot be nearest
+    uint32_t *d_part_masks = nullptr;
+    size_t part_masks_cap = 0;
     uint32_t jit_max_ops = 4096;  // programs longer than this are not specialised automatically
     uint64_t constant_program = 0;  // id of the program in this device's __constant__ window
     int index = 0;                  // position in g_ctx
@@ -368,9 +371,46 @@ int launch_forest(const cc_program *prog, cc_eval_args &a, uint64_t points)
     return CC_OK;
 }
 
+// Dense float4 grid of an assembly through the part-culling kernels; the caller checked
+// that the specialised kernels of CC_SINK_PARTS are loaded.
+int launch_parts(const cc_program *prog, cc_eval_args &a, uint64_t points)
+{
+    const uint64_t nb = (uint64_t)((a.nx + CC_BRICK_X - 1) / CC_BRICK_X) * ((a.ny + CC_BRICK_Y - 1) / CC_BRICK_Y) *
+                        ((a.nz + CC_BRICK_Z - 1) / CC_BRICK_Z);
+    if (nb >= (1ull << 31)) return fail(CC_ERR_INVALID_ARGUMENT, "too many bricks in one launch");
+    if (nb > g.part_masks_cap) {
+        if (g.d_part_masks) CU(cudaFree(g.d_part_masks));
+        g.d_part_masks = nullptr;
+        g.part_masks_cap = 0;
+        CU(cudaMalloc(&g.d_part_masks, (size_t)nb * 4));
+        g.part_masks_cap = (size_t)nb;
+    }
+    // rounding budget of a part's value: 2^-13 of the magnitudes that enter its arithmetic (a part is at
+    // most a few hundred fp32 operations deep: ~1e-5 relative; this allows 1.2e-4)
+    const double ext[3] = {std::fabs((double)a.step) * (double)(a.nx + a.x_offset), std::fabs((double)a.step) * a.ny,
+                           std::fabs((double)a.step) * a.nz};
+    const double pmax = std::max(std::fabs((double)a.cx) + ext[0], std::max(std::fabs((double)a.cy) + ext[1], std::fabs((double)a.cz) + ext[2]));
+    a.part_slack = (float)(((double)prog->dec.parts.magnitude_a + (double)prog->dec.parts.magnitude_b * pmax) / 8192.0);
+    if (!std::isfinite(a.part_slack)) return fail(CC_ERR_INVALID_ARGUMENT, "grid coordinates out of range");
+    a.part_masks = g.d_part_masks;
+    int e = cc_jit_launch_parts(prog, a, (uint32_t)nb, g.compute, g.index);
+    if (e) return cuda_fail((cudaError_t)e, "part-culling kernel launch");
+    g.launches += 2;
+    g.points += points;
+    return CC_OK;
+}
+
+bool parts_apply(int sink_kind, const cc_program *prog, const cc_eval_args &a)
+{
+    return g.parts_mode && sink_kind == CC_SINK_FLOAT4 && !a.points && !a.blocks && prog->dec.parts.enabled &&
+           (uint64_t)a.nx * a.ny * a.nz >= 4096;
+}
+
 int launch(int sink_kind, const cc_program *prog, cc_eval_args &a, uint64_t points)
 {
     if (forest_applies(sink_kind, prog, a)) return launch_forest(prog, a, points);
+    if (parts_apply(sink_kind, prog, a) && jit_ready(const_cast<cc_program *>(prog), CC_SINK_PARTS))
+        return launch_parts(prog, a, points);
     // which specialised kernel serves the launch: point lists have their own (cc_jit_points)
     const int sink = a.points ? (int)CC_SINK_POINTS : sink_kind;
     if (jit_ready(const_cast<cc_program *>(prog), sink)) {
@@ -464,6 +504,8 @@ int init_context(Context &c, int device, int index)
     if (p) c.jit_max_ops = (uint32_t)atoi(p);
     p = getenv("CODECAD_B200_FOREST");
     if (p) c.forest_mode = atoi(p) != 0;
+    p = getenv("CODECAD_B200_PARTS");
+    if (p) c.parts_mode = atoi(p) != 0;
     c.ready = true;
     return CC_OK;
 }
@@ -630,6 +672,7 @@ void cc_shutdown(void)
         if (c.d_ticket) cudaFree(c.d_ticket);
         if (c.d_status) cudaFree(c.d_status);
         if (c.d_forest_scratch) cudaFree(c.d_forest_scratch);
+        if (c.d_part_masks) cudaFree(c.d_part_masks);
         if (c.h_word) cudaFreeHost(c.h_word);
         for (int i = 0; i < Context::kRing; ++i) {
             if (c.ring[i]) cudaFree(c.ring[i]);
@@ -816,6 +859,14 @@ int cc_set_forest_mode(int mode)
     return old;
 }
 
+int cc_set_parts_mode(int mode)
+{
+    const int old = g.parts_mode;
+    if (mode != 0 && mode != 1) return fail(CC_ERR_INVALID_ARGUMENT, "parts mode must be 0 or 1");
+    for (int i = 0; i < CC_MAX_DEVICES; ++i) g_ctx[i].parts_mode = mode;
+    return old;
+}
+
 int cc_program_get_forest_info(const cc_program *prog, uint32_t out[4])
 {
     if (!prog || !out) return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
@@ -832,6 +883,8 @@ int cc_program_specialize_wait(cc_program *prog, unsigned sink_mask, double *com
     NEED_INIT();
     if (!prog) return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
     if ((sink_mask & CC_SINK_MASK_ALL) == 0) sink_mask = 15u;
+    // dense float4 grids of an assembly run on the part-culling kernels: "ready" includes them
+    if ((sink_mask & (1u << CC_SINK_FLOAT4)) && prog->dec.parts.enabled && g.parts_mode) sink_mask |= 1u << CC_SINK_PARTS;
     int ready = 0;
     for (int k = 0; k < CC_N_SINKS; ++k) {
         if (!(sink_mask & (1u << k))) continue;

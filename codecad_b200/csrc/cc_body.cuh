@@ -176,5 +176,96 @@ CC_DEV void cc_kernel_body(const cc_eval_args &a, EVAL &eval)
     }
 }
 
+// ---- part culling: the dense float4 grid in bricks of 8 x 8 x 16 cells ------------------
+// One CTA of 512 threads x 2 points per brick (z fastest inside the brick: a warp's store is two 256-byte
+// runs); bricks in z-fastest order.  EVAL carries the brick's part mask.
+CC_DEV void cc_brick_of(const cc_eval_args &a, uint32_t brick, uint32_t &x0, uint32_t &y0, uint32_t &z0)
+{
+    const uint32_t nbz = (a.nz + CC_BRICK_Z - 1) / CC_BRICK_Z, nby = (a.ny + CC_BRICK_Y - 1) / CC_BRICK_Y;
+    const uint32_t bz = brick % nbz, t = brick / nbz;
+    z0 = bz * CC_BRICK_Z;
+    y0 = (t % nby) * CC_BRICK_Y;
+    x0 = (t / nby) * CC_BRICK_X;
+}
+
+template <int PTS, class EVAL>
+CC_DEV void cc_kernel_body_bricks(const cc_eval_args &a, EVAL &eval)
+{
+    static_assert(PTS == 2 && CC_THREADS * PTS == CC_BRICK_X * CC_BRICK_Y * CC_BRICK_Z, "one brick per CTA");
+    typedef typename cc_pts<PTS>::V V;
+    uint32_t x0, y0, z0;
+    cc_brick_of(a, blockIdx.x, x0, y0, z0);
+    const uint32_t tid = threadIdx.x;
+    uint32_t ix[PTS], iy[PTS], iz[PTS];
+    float gx[PTS], gy[PTS], gz[PTS];
+#pragma unroll
+    for (int j = 0; j < PTS; ++j) {
+        const uint32_t c = (uint32_t)j * CC_THREADS + tid;  // cell of the brick: z fastest, then y, then x
+        ix[j] = x0 + (c >> 7);
+        iy[j] = y0 + ((c >> 4) & 7u);
+        iz[j] = z0 + (c & 15u);
+        // grid_eval.cl:13,31: corner + step * convert_float(id), one FMA per axis (same as cc_kernel_body)
+        gx[j] = cc_fma(a.step, (float)(ix[j] + a.x_offset), a.cx);
+        gy[j] = cc_fma(a.step, (float)iy[j], a.cy);
+        gz[j] = cc_fma(a.step, (float)iz[j], a.cz);
+    }
+    V vx[1], vy[1], vz[1];
+    cc_val<V> LV[1];
+    vx[0] = cc_pack<V>(gx);
+    vy[0] = cc_pack<V>(gy);
+    vz[0] = cc_pack<V>(gz);
+    eval(vx, vy, vz, LV);
+    float4 *out = reinterpret_cast<float4 *>(a.out);
+#pragma unroll
+    for (int j = 0; j < PTS; ++j)
+        if (ix[j] < a.nx && iy[j] < a.ny && iz[j] < a.nz)
+            __stcs(out + ((size_t)ix[j] * a.ny + iy[j]) * a.nz + iz[j], cc_lane_get(LV[0], j));  // INDEX3
+}
+
+// Brick-centre pass.  Thread t evaluates every part at the centres of bricks 2t and 2t + 1 (one packed
+// pair; `pw` receives the parts' values) and derives the bricks' masks: with |w_k(p) - w_k(centre)| <=
+// lip_k * radius + slack for every point p of the brick, part k can be the nearest somewhere in the brick
+// only if  w_k(centre) - lip_k r - slack  <=  min_j (w_j(centre) + lip_j r + slack).  Written with negated
+// comparisons so that a NaN keeps a part alive.
+template <int P, class EVAL, class V>
+CC_DEV void cc_part_centers_body(const cc_eval_args &a, EVAL &eval, V *pw, const float *lip)
+{
+    const uint32_t nbx = (a.nx + CC_BRICK_X - 1) / CC_BRICK_X, nby = (a.ny + CC_BRICK_Y - 1) / CC_BRICK_Y,
+                   nbz = (a.nz + CC_BRICK_Z - 1) / CC_BRICK_Z;
+    const uint32_t n_bricks = nbx * nby * nbz;
+    const uint32_t b0 = 2u * (blockIdx.x * CC_THREADS + threadIdx.x);
+    float gx[2], gy[2], gz[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        uint32_t x0, y0, z0;
+        cc_brick_of(a, min(b0 + (uint32_t)j, n_bricks - 1u), x0, y0, z0);
+        gx[j] = cc_fma(a.step, (float)(x0 + a.x_offset) + 0.5f * (CC_BRICK_X - 1), a.cx);
+        gy[j] = cc_fma(a.step, (float)y0 + 0.5f * (CC_BRICK_Y - 1), a.cy);
+        gz[j] = cc_fma(a.step, (float)z0 + 0.5f * (CC_BRICK_Z - 1), a.cz);
+    }
+    V vx[1], vy[1], vz[1];
+    cc_val<V> LV[1];
+    vx[0] = cc_pack<V>(gx);
+    vy[0] = cc_pack<V>(gy);
+    vz[0] = cc_pack<V>(gz);
+#pragma unroll
+    for (int k = 0; k < P; ++k) pw[k] = vbc<V>(__int_as_float(0x7fc00000));  // NaN: "unknown" keeps a part alive
+    eval(vx, vy, vz, LV);
+    // half diagonal of the brick's cell centres, with head room for the rounding of the coordinates
+    const float r = fabsf(a.step) * (0.5f * 1.0001f) *
+                    sqrtf((float)((CC_BRICK_X - 1) * (CC_BRICK_X - 1) + (CC_BRICK_Y - 1) * (CC_BRICK_Y - 1) + (CC_BRICK_Z - 1) * (CC_BRICK_Z - 1)));
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        if (b0 + (uint32_t)j >= n_bricks) break;
+        float upper = __int_as_float(0x7f800000);
+#pragma unroll
+        for (int k = 0; k < P; ++k) upper = fminf(upper, cc_lane_scalar(pw[k], j) + (lip[k] * r + a.part_slack));  // (NaN, inf ignored)
+        uint32_t mask = 0;
+#pragma unroll
+        for (int k = 0; k < P; ++k)
+            if (!(cc_lane_scalar(pw[k], j) - (lip[k] * r + a.part_slack) > upper)) mask |= 1u << k;
+        a.part_masks[b0 + (uint32_t)j] = mask;
+    }
+}
 
 #endif

@@ -32,6 +32,7 @@ enum cc_sink_kind {
     CC_SINK_FLOAT4 = 0, CC_SINK_PYMCUBES, CC_SINK_CLASSIFY, CC_SINK_MASS,
     CC_SINK_RAY, CC_SINK_BITMAP,  // image renderers (cc_render.cuh), one point per thread
     CC_SINK_POINTS,               // FLOAT4 sink fed from a point list (cc_evaluate_points)
+    CC_SINK_PARTS,                // FLOAT4 sink over 8 x 8 x 16 bricks with per-brick part masks (cc_jit.cpp)
     CC_N_SINKS
 };
 
@@ -63,7 +64,15 @@ struct cc_eval_args {
     // optional: evaluate at these points (x, y, z, unused) instead of grid coordinates; cell c of
     // the launch reads points[c] (used with nx = number of points, ny = nz = 1)
     const float *points;  // 16-byte aligned quadruples
+    // part culling (CC_SINK_PARTS): one mask per brick, bit k = part k can matter there
+    uint32_t *part_masks;
+    float part_slack;     // bound on |computed - exact| of a part's value over the launch
 };
+
+// bricks of the part-culling kernels: a CTA of 512 threads x 2 points
+#define CC_BRICK_X 8
+#define CC_BRICK_Y 8
+#define CC_BRICK_Z 16
 
 // arguments of the image renderers (rendering/ray_caster.cl:147-156, rendering/bitmap.cl:1-3)
 struct cc_render_args {

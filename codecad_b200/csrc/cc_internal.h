@@ -27,10 +27,24 @@ struct cc_forest {
 #define CC_FOREST_EVENT(type, kind, pc) ((uint32_t)(type) | ((uint32_t)(kind) << 2) | ((uint32_t)(pc) << 8))
 #define CC_FOREST_MIN_LEAVES 8u
 
+// A program whose value is a tree of sharp unions over self-contained sub-programs ("parts": the
+// components of an assembly), possibly under a chain of distance-monotone ops.  A part whose value
+// over a brick provably exceeds another part's cannot be selected there, so its code is skipped
+// (cc_program.cpp analyse_parts, cc_jit.cpp).
+struct cc_parts {
+    bool enabled = false;
+    uint32_t n_parts = 0;                 // <= 32
+    std::vector<int> part_of_op;          // micro-op index -> part, -1 = outside every part
+    std::vector<uint32_t> union_a, union_b;  // micro-op index of a union of the tree -> bit masks of the parts below its two operands (0 elsewhere)
+    std::vector<float> lipschitz;         // per part: |w(p) - w(q)| <= lipschitz |p - q|   (inf: never culled)
+    float magnitude_a = 0.0f, magnitude_b = 0.0f;  // rounding budget: 2^-13 (a + b max|p|)
+};
+
 struct cc_decoded {
     std::vector<uint32_t> microcode;
     cc_program_info info;
     cc_forest forest;
+    cc_parts parts;
 };
 
 // cc_program.cpp
@@ -56,6 +70,7 @@ struct cc_program {
     // scene-specialised kernels (cc_jit.cpp), one library per sink; null until compiled
     void *jit_library[CC_N_SINKS] = {};
     void *jit_kernel[CC_N_SINKS] = {};
+    void *jit_kernel_centers = nullptr;  // CC_SINK_PARTS: the brick-centre pass of the same library
     cc_jit_cfg jit_cfg[CC_N_SINKS];
     size_t jit_smem[CC_N_SINKS] = {};  // dynamic shared memory of each specialised kernel
     bool jit_attr_done[CC_N_SINKS][CC_MAX_DEVICES] = {};  // MaxDynamicSharedMemorySize is a per-device attribute
@@ -76,6 +91,8 @@ int cc_jit_poll(cc_program *prog, int sink, bool wait, std::string *err);
 void cc_jit_release(cc_program *prog);
 // dev_index = index of the library context (device) the launch goes to
 int cc_jit_launch(const cc_program *prog, int sink, const cc_eval_args &a, void *stream, int dev_index);
+// part culling: the centre pass over `n_bricks` bricks, then one CTA per brick
+int cc_jit_launch_parts(const cc_program *prog, const cc_eval_args &a, uint32_t n_bricks, void *stream, int dev_index);
 int cc_jit_launch_render(const cc_program *prog, int sink, const cc_render_args &a, void *stream, int dev_index);
 cc_jit_cfg cc_jit_render_cfg(const cc_decoded &dec);
 #define CC_SINK_MASK_ALL ((1u << CC_N_SINKS) - 1u)

@@ -238,6 +238,15 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
     Gen g(dec.microcode);
     const std::vector<uint32_t> &c = dec.microcode;
     std::ostringstream &o = g.body;
+    // part culling: the run of micro-ops of part k is wrapped in `if (mask & (1 << k))`,
+    // a union of the tree is taken only if both operands keep a part; generated for CC_SINK_PARTS only
+    const bool parts_mode = (sink_mask & (1u << CC_SINK_PARTS)) != 0;
+    const cc_parts &parts = dec.parts;
+    if (parts_mode && (!parts.enabled || pts != 2 || cfg.threads * pts != CC_BRICK_X * CC_BRICK_Y * CC_BRICK_Z)) {
+        *err = "part culling needs a program with parts and 512 threads x 2 points";
+        return CC_ERR_INVALID_ARGUMENT;
+    }
+    std::ostringstream hoisted;  // parts mode: value variables are declared ahead of the conditional blocks
 
     // ---- value intervals: one per slot definition, from the storing micro-op to its last reader.
     // Each interval becomes its own variable (the microcode is straight-line, so this is SSA).
@@ -328,6 +337,10 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
     int seg_ops = cfg.segment_ops;
     if (seg_ops <= 0 || n_ops_total <= seg_ops + seg_ops / 2) seg_ops = n_ops_total + 1;
     const bool segmented = seg_ops <= n_ops_total;
+    if (segmented && parts_mode) {
+        *err = "part culling is not generated for segmented programs";
+        return CC_ERR_INVALID_ARGUMENT;
+    }
     auto seg_of = [&](int op) { return op / seg_ops; };
     const int n_segs = segmented ? seg_of(n_ops_total - 1) + 1 : 1;
     std::vector<char> crosses(iv.size(), 0);  // register interval read in a later segment than its definition
@@ -358,6 +371,14 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
         }
         const uint32_t h = c[pc], op = CC_HDR_OP(h), src_slot = CC_HDR_SRC(h), dst = CC_HDR_DST(h);
         o << "        // pc " << pc << "\n";
+        const int my_part = (parts_mode && op != MOP_RETURN && (size_t)op_index < parts.part_of_op.size()) ? parts.part_of_op[(size_t)op_index] : -1;
+        const bool tree_union = parts_mode && op == MOP_UNION && (size_t)op_index < parts.union_a.size() &&
+                                parts.union_a[(size_t)op_index] != 0;
+        if (my_part >= 0 && (op_index == 0 || parts.part_of_op[(size_t)op_index - 1] != my_part))
+            o << "        if (mask & " << (1u << my_part) << "u) {  // part " << my_part << "\n";
+        if (tree_union)
+            o << "        if ((mask & " << parts.union_a[(size_t)op_index] << "u) && (mask & " << parts.union_b[(size_t)op_index]
+              << "u)) {  // both operands keep a part; otherwise the survivor is already in L\n";
         std::string B = "?";
         if (op_use[op_index] >= 0) {
             const int u = op_use[op_index];
@@ -464,12 +485,18 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
         }
         if (op == MOP_RETURN) break;
         if (stop_after >= 0 && ++n_emitted > stop_after) break;
+        if (tree_union) o << "        }\n";
         if (op_def[op_index] >= 0) {
             const int d = op_def[op_index];
             if (iv[d].last_read == iv[d].def) {
                 // never read: nothing to keep
             } else if (iv[d].cell < 0) {
-                o << "        Val I" << d << "[G]; CC_EACH I" << d << "[g] = L[g];\n";
+                if (parts_mode) {
+                    hoisted << "        Val I" << d << "[G];\n";
+                    o << "        CC_EACH I" << d << "[g] = L[g];\n";
+                } else {
+                    o << "        Val I" << d << "[G]; CC_EACH I" << d << "[g] = L[g];\n";
+                }
                 if (crosses[d]) o << "        CC_EACH st.I" << d << "[g] = L[g];\n";
             } else if (iv[d].z_only) {
                 o << "        CC_EACH cc_slot_store_z(CC_CELL(" << iv[d].cell << ", g), L[g].z);\n";
@@ -477,6 +504,8 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
                 o << "        CC_EACH cc_slot_store(CC_CELL(" << iv[d].cell << ", g), L[g]);\n";
             }
         }
+        if (my_part >= 0 && ((size_t)op_index + 1 >= parts.part_of_op.size() || parts.part_of_op[(size_t)op_index + 1] != my_part))
+            o << "          if (pw) pw[" << my_part << "] = L[0].w;  // the part's value (brick centres)\n        }\n";
         pc += CC_HDR_LEN(h);
     }
 
@@ -493,9 +522,10 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
       << g.consts.str();
     if (g.n_params) s << "__constant__ float cc_par[" << g.n_params << "] = {" << g.params.str() << "};\n";
     if (!segmented) {
-        s << "struct SceneEval {\n    float4 *sm;  // this thread's column of the value cells\n"
-          << "    __device__ __forceinline__ void operator()(const V (&gx)[G], const V (&gy)[G], const V (&gz)[G],\n"
-          << "                                               Val (&L)[G]) const\n    {\n";
+        s << "struct SceneEval {\n    float4 *sm;  // this thread's column of the value cells\n";
+        if (parts_mode) s << "    unsigned mask;  // bit k: part k can matter in this brick\n    V *pw;  // brick-centre pass: receives every part's value\n";
+        s << "    __device__ __forceinline__ void operator()(const V (&gx)[G], const V (&gy)[G], const V (&gz)[G],\n"
+          << "                                               Val (&L)[G]) const\n    {\n" << hoisted.str();
         if (coord_smem)
             s << "        CC_EACH cc_slot_store(CC_CELL(" << coord_cell << ", g), Val{gx[g], gy[g], gz[g], vbc<V>(0.f)});\n";
         s << "        CC_EACH L[g] = Val{vbc<V>(0.f), vbc<V>(0.f), vbc<V>(0.f), vbc<V>(0.f)};\n" << o.str() << "    }\n};\n";
@@ -532,6 +562,26 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
         s << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_" << names[k]
           << "(const cc_eval_args a)\n{\n    extern __shared__ float4 cc_cells[];\n    SceneEval e{cc_cells + threadIdx.x};\n"
           << "    cc_kernel_body<PTS, " << sinks[k] << ">(a, e);\n}\n";
+    if (parts_mode) {
+        // main kernel: one 8 x 8 x 16 brick per CTA, its mask decides which parts run; centre pass: a
+        // thread evaluates the centres of two bricks (one packed pair), derives the bricks' masks from
+        // the parts' values there and their Lipschitz constants, and writes them for the main kernel
+        s << "__constant__ float cc_part_lipschitz[" << parts.n_parts << "] = {";
+        for (uint32_t k = 0; k < parts.n_parts; ++k) {
+            const float l = parts.lipschitz[k];
+            s << (k ? ", " : "");
+            if (l - l != 0.0f) s << "__builtin_huge_valf()";
+            else { char buf[48]; std::snprintf(buf, sizeof buf, "%af", (double)l); s << buf; }
+        }
+        s << "};\n"
+          << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_parts(const cc_eval_args a)\n{\n"
+          << "    extern __shared__ float4 cc_cells[];\n    SceneEval e{cc_cells + threadIdx.x, a.part_masks[blockIdx.x], nullptr};\n"
+          << "    cc_kernel_body_bricks<PTS>(a, e);\n}\n"
+          << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_part_centers(const cc_eval_args a)\n{\n"
+          << "    extern __shared__ float4 cc_cells[];\n    V pw[" << parts.n_parts << "];\n"
+          << "    SceneEval e{cc_cells + threadIdx.x, 0xffffffffu, pw};\n"
+          << "    cc_part_centers_body<" << parts.n_parts << ">(a, e, pw, cc_part_lipschitz);\n}\n";
+    }
     if (sink_mask & (1u << CC_SINK_POINTS))
         s << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_points"
           << "(const cc_eval_args a)\n{\n    extern __shared__ float4 cc_cells[];\n    SceneEval e{cc_cells + threadIdx.x};\n"
@@ -813,7 +863,7 @@ static int load_cubin(cc_program *prog, int sink, const Cubin &bin, const cc_jit
                       std::string *err)
 {
     static const char *names[CC_N_SINKS] = {"cc_jit_float4", "cc_jit_pymcubes", "cc_jit_classify", "cc_jit_mass",
-                                            "cc_jit_ray_caster", "cc_jit_bitmap", "cc_jit_points"};
+                                            "cc_jit_ray_caster", "cc_jit_bitmap", "cc_jit_points", "cc_jit_parts"};
     cudaLibrary_t lib = nullptr;
     cudaError_t ce = cudaLibraryLoadData(&lib, bin->data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
     if (ce != cudaSuccess) {
@@ -826,6 +876,16 @@ static int load_cubin(cc_program *prog, int sink, const Cubin &bin, const cc_jit
         *err = std::string("cudaLibraryGetKernel: ") + cudaGetErrorString(ce);
         cudaLibraryUnload(lib);
         return CC_ERR_CUDA;
+    }
+    cudaKernel_t centers = nullptr;
+    if (sink == CC_SINK_PARTS) {
+        ce = cudaLibraryGetKernel(&centers, lib, "cc_jit_part_centers");
+        if (ce != cudaSuccess) {
+            *err = std::string("cudaLibraryGetKernel(cc_jit_part_centers): ") + cudaGetErrorString(ce);
+            cudaLibraryUnload(lib);
+            return CC_ERR_CUDA;
+        }
+        prog->jit_kernel_centers = (void *)centers;
     }
     if (prog->jit_library[sink]) cudaLibraryUnload((cudaLibrary_t)prog->jit_library[sink]);
     prog->jit_smem[sink] = smem_bytes;
@@ -962,6 +1022,25 @@ int cc_jit_launch(const cc_program *prog, int sink, const cc_eval_args &a, void 
     void *args[] = {(void *)&a};
     return (int)cudaLaunchKernel((const void *)prog->jit_kernel[sink], dim3(grid), dim3(prog->jit_cfg[sink].threads),
                                  args, prog->jit_smem[sink], (cudaStream_t)stream);
+}
+
+int cc_jit_launch_parts(const cc_program *prog, const cc_eval_args &a, uint32_t n_bricks, void *stream, int dev_index)
+{
+    if (n_bricks == 0) return 0;
+    const int sink = CC_SINK_PARTS;
+    if (int e = ensure_smem_attr(prog, sink, dev_index)) return e;
+    const size_t smem = prog->jit_smem[sink];
+    if (smem) {  // the centre pass shares the value cells' layout (per device, like the main kernel's attribute)
+        cudaError_t ce = cudaFuncSetAttribute((const void *)prog->jit_kernel_centers, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (ce != cudaSuccess) return (int)ce;
+    }
+    const uint32_t threads = (uint32_t)prog->jit_cfg[sink].threads;
+    void *args[] = {(void *)&a};
+    cudaError_t ce = cudaLaunchKernel((const void *)prog->jit_kernel_centers, dim3((n_bricks + 2 * threads - 1) / (2 * threads)),
+                                      dim3(threads), args, smem, (cudaStream_t)stream);
+    if (ce != cudaSuccess) return (int)ce;
+    return (int)cudaLaunchKernel((const void *)prog->jit_kernel[sink], dim3(n_bricks), dim3(threads), args, smem,
+                                 (cudaStream_t)stream);
 }
 
 int cc_jit_source(const cc_decoded &dec, int pts, unsigned sink_mask, std::string *src, std::string *err)

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <vector>
 
@@ -300,6 +301,246 @@ void analyse_forest(const std::vector<uint32_t> &code, cc_forest *f)
     f->err_a = (float)(ea * 1.01 + rmax);
     f->err_b = (float)(eb * 1.01);
     f->enabled = true;
+}
+
+}  // namespace
+
+
+// ---- parts of an assembly --------------------------------------------------------------------------
+// Finds the shape  post-ops( union( union(part, part), part ... ) )  with sharp unions: the result at a
+// point is the part with the smallest distance, passed through whole.  A part that is provably farther
+// than some other part over a whole brick is never selected there.  The proof needs a Lipschitz bound
+// of every part's value, derived op by op:
+//   coordinates: transformation M -> largest singular value of M; mirror / |x| / revolution keep it;
+//   distances of exact primitives (circle, sphere, rectangle, polygon, half-space): that of the coordinates;
+//   extrusion: sqrt(a^2 + b^2) or max(a, b) of a distance in x, y and a slab in z — orthogonal
+//   arguments of the same coordinates, so the maximum of the two constants;
+//   involute gear: sqrt(1 + g^2) with g the largest angle that scales the radius (gears.cl:24);
+//   offset, shell, sharp union / intersection / subtraction: maximum of the operands'; inverse
+//   transformation: times its scale.  Anything else (twists, repetitions, regular polygons, rounded
+//   combinators) yields no bound and the part is always evaluated.
+namespace {
+
+bool sigma_max(const float *m, double *out)
+{
+    double g[9], s2;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) g[3 * i + j] = (double)m[i] * m[j] + (double)m[3 + i] * m[3 + j] + (double)m[6 + i] * m[6 + j];
+    s2 = (g[0] + g[4] + g[8]) / 3;
+    if (!(s2 > 1e-30) || !std::isfinite(s2)) return false;
+    double ef = 0;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            const double e = g[3 * i + j] / s2 - (i == j ? 1.0 : 0.0);
+            ef += e * e;
+        }
+    *out = std::sqrt(s2) * std::sqrt(1 + std::sqrt(ef)) * (1 + 1e-6);
+    return std::isfinite(*out);
+}
+
+void analyse_parts(const std::vector<uint32_t> &code, cc_parts *out)
+{
+    *out = cc_parts();
+    struct Op { uint32_t pc, op, src, dst; int in_l, in_s; };  // producers of the two inputs (op index), -1 = none
+    std::vector<Op> ops;
+    std::vector<int> slot_prod(CC_SLOT_NONE + 1, -1);
+    int L = -1, root = -1;
+    for (uint32_t pc = 0;;) {
+        if (pc >= code.size()) return;
+        const uint32_t hd = code[pc], op = CC_HDR_OP(hd), src = CC_HDR_SRC(hd), dst = CC_HDR_DST(hd);
+        if (op == MOP_RETURN) { root = L; break; }
+        Op o{pc, op, src, dst, -1, -1};
+        const bool from_point = op == MOP_T_INIT || op == MOP_T_INIT_M || op == MOP_PRIM_CIRCLE || op == MOP_PRIM_RECT ||
+                                op == MOP_PRIM_CIRCLE_M || op == MOP_PRIM_RECT_M;
+        if (!from_point && op != MOP_LOAD) {
+            if (L < 0) return;
+            o.in_l = L;
+        }
+        if (src != CC_SLOT_NONE) {
+            if (slot_prod[src] < 0) return;
+            o.in_s = slot_prod[src];
+        }
+        ops.push_back(o);
+        L = (int)ops.size() - 1;  // (NOP and LOAD are nodes too: they move a value)
+        if (dst != CC_SLOT_NONE) slot_prod[dst] = L;
+        pc += CC_HDR_LEN(hd);
+    }
+    const int n = (int)ops.size();
+    if (root < 0 || n < 8) return;
+    std::vector<int> uses((size_t)n, 0);
+    for (const Op &o : ops) {
+        if (o.in_l >= 0) ++uses[(size_t)o.in_l];
+        if (o.in_s >= 0) ++uses[(size_t)o.in_s];
+    }
+    auto fl = [&](uint32_t pc, int k) { float f; std::memcpy(&f, &code[pc + 1 + (uint32_t)k], 4); return f; };
+    // the chain above the union tree: ops that map the winner's distance monotonically
+    int top = root;
+    std::vector<char> in_chain((size_t)n, 0);
+    for (;;) {
+        const Op &o = ops[(size_t)top];
+        const bool t_from = (o.op == MOP_T_FROM || o.op == MOP_T_FROM_M) && fl(o.pc, 9) > 0.0f;
+        if (!(t_from || o.op == MOP_OFFSET || o.op == MOP_NOP) || o.in_l < 0 || uses[(size_t)o.in_l] != 1) break;
+        in_chain[(size_t)top] = 1;
+        top = o.in_l;
+    }
+    if (ops[(size_t)top].op != MOP_UNION) return;
+    // flatten the tree of sharp unions below `top`
+    std::vector<int> part_root;
+    std::vector<char> is_tree_union((size_t)n, 0);
+    struct Item { int node; };
+    std::vector<int> stack{top};
+    while (!stack.empty()) {
+        const int u = stack.back();
+        stack.pop_back();
+        const Op &o = ops[(size_t)u];
+        if (o.op == MOP_UNION && (u == top || uses[(size_t)u] == 1) && o.in_l >= 0 && o.in_s >= 0) {
+            is_tree_union[(size_t)u] = 1;
+            stack.push_back(o.in_l);
+            stack.push_back(o.in_s);
+        } else {
+            if (uses[(size_t)u] != 1) return;  // a value shared between parts
+            part_root.push_back(u);
+        }
+    }
+    std::sort(part_root.begin(), part_root.end());
+    const int P = (int)part_root.size();
+    if (P < 2 || P > 32) return;
+    // every part = the closure of its root, which must be a contiguous run of micro-ops
+    std::vector<int> part_of((size_t)n, -1);
+    for (int k = 0; k < P; ++k) {
+        std::vector<int> todo{part_root[(size_t)k]};
+        int lo = part_root[(size_t)k];
+        while (!todo.empty()) {
+            const int v = todo.back();
+            todo.pop_back();
+            if (part_of[(size_t)v] == k) continue;
+            if (part_of[(size_t)v] >= 0 || is_tree_union[(size_t)v] || in_chain[(size_t)v]) return;  // shared with another part
+            part_of[(size_t)v] = k;
+            lo = std::min(lo, v);
+            if (ops[(size_t)v].in_l >= 0) todo.push_back(ops[(size_t)v].in_l);
+            if (ops[(size_t)v].in_s >= 0) todo.push_back(ops[(size_t)v].in_s);
+        }
+        for (int v = lo; v <= part_root[(size_t)k]; ++v)
+            if (part_of[(size_t)v] != k) return;  // foreign op inside the run
+    }
+    for (int v = 0; v < n; ++v) {
+        if (part_of[(size_t)v] < 0 && !is_tree_union[(size_t)v] && !in_chain[(size_t)v]) return;  // dead or stray code
+        // nothing but the part itself (and, for its root, the tree) may read a part's values
+        const Op &o = ops[(size_t)v];
+        for (int in : {o.in_l, o.in_s})
+            if (in >= 0 && part_of[(size_t)in] >= 0 && part_of[(size_t)in] != part_of[(size_t)v] &&
+                !(is_tree_union[(size_t)v] && in == part_root[(size_t)part_of[(size_t)in]]))
+                return;
+    }
+    // post-order layout: a union's stored operand ends where its running operand begins, and the union
+    // follows its running operand at once — then "skip a part's run" leaves the survivor in L
+    std::vector<int> first((size_t)n, 0);
+    std::vector<uint32_t> below((size_t)n, 0u);
+    for (int v = 0; v < n; ++v) {
+        if (part_of[(size_t)v] >= 0 && part_root[(size_t)part_of[(size_t)v]] == v) {
+            int lo = v;
+            while (lo > 0 && part_of[(size_t)lo - 1] == part_of[(size_t)v]) --lo;
+            first[(size_t)v] = lo;
+            below[(size_t)v] = 1u << part_of[(size_t)v];
+        } else if (is_tree_union[(size_t)v]) {
+            const int a = ops[(size_t)v].in_s, b = ops[(size_t)v].in_l;  // stored operand, running operand
+            if (b != v - 1 || first[(size_t)b] != a + 1) return;
+            first[(size_t)v] = first[(size_t)a];
+            below[(size_t)v] = below[(size_t)a] | below[(size_t)b];
+        }
+    }
+    if (first[(size_t)top] != 0) return;
+    // Lipschitz bounds, op by op
+    const double INF = std::numeric_limits<double>::infinity();
+    std::vector<double> lip((size_t)n, INF);     // of the node's distance (or of its coordinates)
+    std::vector<int> coords_of((size_t)n, -1);   // the coordinate node a 2-D distance was computed from
+    double mag_a = 0, mag_b = 0;
+    for (int v = 0; v < n; ++v) {
+        if (part_of[(size_t)v] < 0) continue;
+        const Op &o = ops[(size_t)v];
+        const double li = o.in_l >= 0 ? lip[(size_t)o.in_l] : INF, ls = o.in_s >= 0 ? lip[(size_t)o.in_s] : INF;
+        double r = INF;
+        switch (o.op) {
+        case MOP_T_INIT: case MOP_T_INIT_M: case MOP_T_TO: case MOP_T_TO_M: {
+            float m[9];
+            for (int i = 0; i < 9; ++i) m[i] = fl(o.pc, i);
+            double sm;
+            if (!sigma_max(m, &sm)) break;
+            const bool init = o.op == MOP_T_INIT || o.op == MOP_T_INIT_M;
+            r = init ? sm : sm * li;
+            mag_a = std::max(mag_a, (double)std::fabs(fl(o.pc, 9)) + std::fabs(fl(o.pc, 10)) + std::fabs(fl(o.pc, 11)));
+            mag_b = std::max(mag_b, 3.0 * (init ? sm : r));
+            break;
+        }
+        case MOP_PRIM_CIRCLE: case MOP_PRIM_RECT: case MOP_PRIM_CIRCLE_M: case MOP_PRIM_RECT_M: {
+            float m[9];
+            for (int i = 0; i < 9; ++i) m[i] = fl(o.pc, i);
+            double sm;
+            const double scale = fl(o.pc, 25);
+            if (!sigma_max(m, &sm) || !(scale > 0)) break;
+            r = sm * scale;
+            mag_a = std::max(mag_a, scale * ((double)std::fabs(fl(o.pc, 9)) + std::fabs(fl(o.pc, 10)) + std::fabs(fl(o.pc, 11)) +
+                                             std::fabs(fl(o.pc, 12)) + std::fabs(fl(o.pc, 13)) + std::fabs(fl(o.pc, 14)) + std::fabs(fl(o.pc, 15))));
+            mag_b = std::max(mag_b, 3.0 * r);
+            break;
+        }
+        case MOP_LOAD: r = ls; coords_of[(size_t)v] = o.in_s >= 0 ? coords_of[(size_t)o.in_s] : -1; break;
+        case MOP_NOP: r = li; coords_of[(size_t)v] = o.in_l >= 0 ? coords_of[(size_t)o.in_l] : -1; break;
+        case MOP_MIRROR: case MOP_SYM_TO: case MOP_REV_TO: r = li; break;
+        case MOP_CIRCLE: case MOP_RECTANGLE: case MOP_POLYGON:
+            r = li;
+            coords_of[(size_t)v] = o.in_l;
+            mag_a = std::max(mag_a, (double)std::fabs(fl(o.pc, 0)) + std::fabs(fl(o.pc, 1)));
+            break;
+        case MOP_SPHERE: case MOP_HALF_SPACE: r = li; mag_a = std::max(mag_a, (double)std::fabs(fl(o.pc, 0))); break;
+        case MOP_GEAR: {
+            const double tooth = fl(o.pc, 1), half = fl(o.pc, 2);
+            const double gmax = std::max(std::fabs(half), std::fabs(tooth - half));
+            r = li * std::sqrt(1 + gmax * gmax) * (1 + 1e-5);
+            coords_of[(size_t)v] = o.in_l;
+            mag_a = std::max(mag_a, 8.0);  // angles up to 4 pi enter the arithmetic
+            break;
+        }
+        case MOP_OFFSET: case MOP_SHELL:
+            r = li;
+            coords_of[(size_t)v] = o.in_l >= 0 ? coords_of[(size_t)o.in_l] : -1;
+            mag_a = std::max(mag_a, (double)std::fabs(fl(o.pc, 0)));
+            break;
+        case MOP_EXTRUSION:
+            // distance in (x, y) of the coordinates in the slot, slab in their z: orthogonal arguments
+            r = (o.in_l >= 0 && coords_of[(size_t)o.in_l] == o.in_s) ? std::max(li, ls) : std::sqrt(li * li + ls * ls);
+            mag_a = std::max(mag_a, (double)std::fabs(fl(o.pc, 0)));
+            break;
+        case MOP_REV_FROM: case MOP_SYM_FROM: r = li; break;
+        case MOP_T_FROM: case MOP_T_FROM_M: {
+            const double scale = fl(o.pc, 9);
+            r = scale > 0 ? li * scale * (1 + 1e-6) : INF;
+            break;
+        }
+        case MOP_UNION: case MOP_ISECT: case MOP_SUB: r = std::max(li, ls); break;
+        default: break;  // no bound: the part is never culled
+        }
+        lip[(size_t)v] = r;
+    }
+    out->n_parts = (uint32_t)P;
+    out->part_of_op = part_of;
+    out->union_a.assign((size_t)n, 0u);
+    out->union_b.assign((size_t)n, 0u);
+    for (int v = 0; v < n; ++v)
+        if (is_tree_union[(size_t)v]) {
+            out->union_a[(size_t)v] = below[(size_t)ops[(size_t)v].in_s];
+            out->union_b[(size_t)v] = below[(size_t)ops[(size_t)v].in_l];
+        }
+    out->lipschitz.resize((size_t)P);
+    int bounded = 0;
+    for (int k = 0; k < P; ++k) {
+        const double l = lip[(size_t)part_root[(size_t)k]];
+        out->lipschitz[(size_t)k] = std::isfinite(l) ? (float)(l * (1 + 1e-5)) : std::numeric_limits<float>::infinity();
+        bounded += std::isfinite(l) ? 1 : 0;
+    }
+    out->magnitude_a = (float)(mag_a + 1.0);
+    out->magnitude_b = (float)std::max(mag_b, 3.0);
+    out->enabled = bounded >= 1;  // (at least one part can ever be dropped)
 }
 
 }  // namespace
@@ -667,6 +908,7 @@ int cc_decode_program(const float *words, uint32_t n_words, cc_decoded *out, std
     }
     out->microcode.swap(e.code);
     analyse_forest(out->microcode, &out->forest);
+    analyse_parts(out->microcode, &out->parts);
     out->info.n_words = pc;
     out->info.n_instructions = (uint32_t)ins.size();
     out->info.n_micro_ops = n_micro;
@@ -678,5 +920,9 @@ int cc_decode_program(const float *words, uint32_t n_words, cc_decoded *out, std
     out->info.flops_max = fmax;
     out->info.n_forest_leaves = out->forest.enabled ? out->forest.n_leaves : 0;
     out->info.forest_depth = out->forest.enabled ? out->forest.max_depth : 0;
+    out->info.n_parts = out->parts.enabled ? out->parts.n_parts : 0;
+    out->info.n_parts_bounded = 0;
+    if (out->parts.enabled)
+        for (float l : out->parts.lipschitz) out->info.n_parts_bounded += std::isfinite(l) ? 1u : 0u;
     return CC_OK;
 }

@@ -93,6 +93,8 @@ typedef struct cc_program_info {
     uint32_t flops_max;
     uint32_t n_forest_leaves; /* primitives of a union forest (cc_set_forest_mode), 0 = not one */
     uint32_t forest_depth;    /* its evaluation stack depth                                    */
+    uint32_t n_parts;         /* parts of an assembly (cc_set_parts_mode), 0 = none            */
+    uint32_t n_parts_bounded; /* of them: with a Lipschitz bound, i.e. cullable                */
 } cc_program_info;
 int cc_program_get_info(const cc_program *prog, cc_program_info *out);
 /* copies the decoded microcode (for tests / disassembly); returns the microcode length */
@@ -134,6 +136,12 @@ int cc_set_jit_mode(int mode);
  * cc_program_get_forest_info: returns 1 and fills {primitives, unions, stack depth, events} if the
  * program is a union forest, else 0. */
 int cc_set_forest_mode(int mode);
+/* Parts.  A program whose value is a tree of sharp unions over self-contained sub-programs — the
+ * components of an assembly, SURVEY.md 8(d) config C4 — gets, next to its specialised kernels, a pair
+ * that evaluates dense float4 grids brick by brick and skips in every brick the parts that provably
+ * cannot be the nearest there (Lipschitz bound of every part from the brick centre; csrc/cc_body.cuh).
+ * Bit-identical to the full evaluation.  mode 1 = on (default; CODECAD_B200_PARTS), 0 = off. */
+int cc_set_parts_mode(int mode);
 int cc_program_get_forest_info(const cc_program *prog, uint32_t out[4]);
 /* Blocks until the specialised kernels of the sinks in `sink_mask` (0 = all) are compiled and
  * loaded, starting their compilation if necessary; returns how many are ready.  compile_seconds

@@ -1,0 +1,85 @@
+"""Part culling: dense float4 grids of an assembly — a tree of sharp unions over
+self-contained sub-programs — skip, brick by brick, the parts that provably cannot be the nearest.
+Must not change a bit: against the CPU oracle on windows of several scales, and against the same
+library with the culling switched off on larger grids."""
+import numpy as np
+import pytest
+
+import oracle
+from scenes import ALL_NAMES
+
+pytestmark = pytest.mark.gpu
+PART_SCENES = ["cfg_planetary", "cfg_menger_sponge", "dsdf3d_mirror_3d", "dsdf2d_mirror_2d", "dsdf2d_rotated_pattern_2d"]
+
+
+@pytest.fixture(scope="module")
+def cb():
+    import codecad_b200
+    from codecad_b200 import _lib
+    _lib.init(0)
+    L = _lib.lib()
+    old_jit = _lib.check(L.cc_set_jit_mode(2))     # compile at first use and wait: the part kernels are NVRTC kernels
+    old_forest = _lib.check(L.cc_set_forest_mode(0))
+    yield codecad_b200
+    _lib.check(L.cc_set_parts_mode(1))
+    _lib.check(L.cc_set_forest_mode(old_forest))
+    _lib.check(L.cc_set_jit_mode(old_jit))
+
+
+def _f4(arr):
+    return np.stack([arr["x"], arr["y"], arr["z"], arr["w"]], axis=-1)
+
+
+def test_which_scenes_have_parts(scenes):
+    from codecad_b200 import _lib
+    with_parts = sorted(n for n in ALL_NAMES if _lib.decode_program(scenes[n].words)[0].n_parts)
+    assert set(PART_SCENES) <= set(with_parts)
+    info = _lib.decode_program(scenes["cfg_planetary"].words)[0]
+    assert info.n_parts == 7 and info.n_parts_bounded == 7
+
+
+@pytest.mark.parametrize("name", PART_SCENES)
+def test_parts_bit_exact_vs_oracle(cb, scenes, name):
+    from codecad_b200 import _lib
+    _lib.check(_lib.lib().cc_set_parts_mode(1))
+    s = scenes[name]
+    scene = s.compiled()
+    rng = np.random.default_rng(3)
+    a, b = np.array(s.box_a), np.array(s.box_b)
+    if s.dimension == 2:
+        a[2], b[2] = -1.0, 1.0
+    size = float(max(b - a))
+    corner, step = s.grid(48)
+    windows = [(corner, step, (48, 40, 33))]
+    for frac, dims in ((0.3, (40, 33, 48)), (0.05, (33, 48, 40)), (0.01, (24, 40, 64))):
+        for _ in range(2):
+            centre = a + (b - a) * rng.uniform(0.2, 0.8, 3)
+            st = np.float32(size * frac / 32)
+            windows.append(((centre - st * np.array(dims) / 2).astype(np.float32), st, dims))
+    for corner, step, dims in windows:
+        want = oracle.grid_eval(s.words, corner, step, dims)
+        got = _f4(cb.grid_eval(scene, corner, step, dims))
+        assert np.array_equal(got, want, equal_nan=True), "%s step %g: %d values differ" % (name, step, int((got != want).sum()))
+
+
+@pytest.mark.parametrize("name", PART_SCENES)
+def test_parts_equal_the_unculled_kernels(cb, scenes, name):
+    from codecad_b200 import _lib
+    L = _lib.lib()
+    s = scenes[name]
+    scene = s.compiled()
+    rng = np.random.default_rng(17)
+    a, b = np.array(s.box_a), np.array(s.box_b)
+    if s.dimension == 2:
+        a[2], b[2] = -1.0, 1.0
+    size = float(max(b - a))
+    for frac, dims, x_offset in ((1.05, (128, 128, 128), 0), (0.3, (130, 70, 90), 5), (0.04, (64, 136, 100), 0)):
+        centre = a + (b - a) * rng.uniform(0.3, 0.7, 3)
+        st = np.float32(size * frac / max(dims))
+        corner = (centre - st * np.array(dims) / 2).astype(np.float32)
+        _lib.check(L.cc_set_parts_mode(1))
+        got = np.array(cb.grid_eval(scene, corner, st, dims, x_offset=x_offset))
+        _lib.check(L.cc_set_parts_mode(0))
+        want = np.array(cb.grid_eval(scene, corner, st, dims, x_offset=x_offset))
+        _lib.check(L.cc_set_parts_mode(1))
+        assert got.tobytes() == want.tobytes(), "%s frac %g" % (name, frac)
