@@ -859,22 +859,70 @@ static int build_cubin(const cc_decoded &dec, const cc_jit_cfg &cfg, int sink, C
     return CC_OK;
 }
 
+// loaded libraries, shared between programs with the same cubin; unreferenced ones are kept (the most
+// recent 16) so that re-creating a program for the same scene does not load its code again
+namespace {
+struct Loaded {
+    cudaLibrary_t lib;
+    int refs;
+    uint64_t stamp;
+    Cubin bin;  // keeps the key (the cubin's address) alive
+};
+std::map<const void *, Loaded> &g_loaded = *new std::map<const void *, Loaded>;
+uint64_t g_loaded_clock = 0;
+
+void release_library(cudaLibrary_t lib)
+{
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    size_t idle = 0;
+    for (auto &kv : g_loaded) {
+        if (kv.second.lib == lib && kv.second.refs > 0) kv.second.refs -= 1;
+        if (kv.second.refs == 0) ++idle;
+    }
+    while (idle > 16) {
+        auto oldest = g_loaded.end();
+        for (auto it = g_loaded.begin(); it != g_loaded.end(); ++it)
+            if (it->second.refs == 0 && (oldest == g_loaded.end() || it->second.stamp < oldest->second.stamp)) oldest = it;
+        if (oldest == g_loaded.end()) break;
+        cudaLibraryUnload(oldest->second.lib);
+        g_loaded.erase(oldest);
+        --idle;
+    }
+}
+}  // namespace
+
 static int load_cubin(cc_program *prog, int sink, const Cubin &bin, const cc_jit_cfg &cfg, size_t smem_bytes,
                       std::string *err)
 {
     static const char *names[CC_N_SINKS] = {"cc_jit_float4", "cc_jit_pymcubes", "cc_jit_classify", "cc_jit_mass",
                                             "cc_jit_ray_caster", "cc_jit_bitmap", "cc_jit_points", "cc_jit_parts"};
+    // A cubin is loaded once per process: programs with the same specialised source (the same scene
+    // uploaded again) share the loaded library.  Loading costs milliseconds per megabyte of code.
     cudaLibrary_t lib = nullptr;
-    cudaError_t ce = cudaLibraryLoadData(&lib, bin->data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
-    if (ce != cudaSuccess) {
-        *err = std::string("cudaLibraryLoadData: ") + cudaGetErrorString(ce);
-        return CC_ERR_CUDA;
+    cudaError_t ce = cudaSuccess;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        auto it = g_loaded.find(bin.get());
+        if (it != g_loaded.end()) {
+            lib = it->second.lib;
+            it->second.refs += 1;
+            it->second.stamp = ++g_loaded_clock;
+        }
+    }
+    if (!lib) {
+        ce = cudaLibraryLoadData(&lib, bin->data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+        if (ce != cudaSuccess) {
+            *err = std::string("cudaLibraryLoadData: ") + cudaGetErrorString(ce);
+            return CC_ERR_CUDA;
+        }
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        g_loaded[bin.get()] = Loaded{lib, 1, ++g_loaded_clock, bin};
     }
     cudaKernel_t kern = nullptr;
     ce = cudaLibraryGetKernel(&kern, lib, names[sink]);
     if (ce != cudaSuccess) {
         *err = std::string("cudaLibraryGetKernel: ") + cudaGetErrorString(ce);
-        cudaLibraryUnload(lib);
+        release_library(lib);
         return CC_ERR_CUDA;
     }
     cudaKernel_t centers = nullptr;
@@ -882,12 +930,12 @@ static int load_cubin(cc_program *prog, int sink, const Cubin &bin, const cc_jit
         ce = cudaLibraryGetKernel(&centers, lib, "cc_jit_part_centers");
         if (ce != cudaSuccess) {
             *err = std::string("cudaLibraryGetKernel(cc_jit_part_centers): ") + cudaGetErrorString(ce);
-            cudaLibraryUnload(lib);
+            release_library(lib);
             return CC_ERR_CUDA;
         }
         prog->jit_kernel_centers = (void *)centers;
     }
-    if (prog->jit_library[sink]) cudaLibraryUnload((cudaLibrary_t)prog->jit_library[sink]);
+    if (prog->jit_library[sink]) release_library((cudaLibrary_t)prog->jit_library[sink]);
     prog->jit_smem[sink] = smem_bytes;
     for (int d = 0; d < CC_MAX_DEVICES; ++d) prog->jit_attr_done[sink][d] = false;
     prog->jit_library[sink] = (void *)lib;
@@ -995,7 +1043,7 @@ void cc_jit_release(cc_program *prog)
 {
     for (int k = 0; k < CC_N_SINKS; ++k) {
         join_job(prog, k);
-        if (prog->jit_library[k]) cudaLibraryUnload((cudaLibrary_t)prog->jit_library[k]);
+        if (prog->jit_library[k]) release_library((cudaLibrary_t)prog->jit_library[k]);
         prog->jit_library[k] = nullptr;
         prog->jit_kernel[k] = nullptr;
     }
