@@ -469,7 +469,7 @@ void analyse_parts(const std::vector<uint32_t> &code, cc_parts *out)
             const bool init = o.op == MOP_T_INIT || o.op == MOP_T_INIT_M;
             r = init ? sm : sm * li;
             mag_a = std::max(mag_a, (double)std::fabs(fl(o.pc, 9)) + std::fabs(fl(o.pc, 10)) + std::fabs(fl(o.pc, 11)));
-            mag_b = std::max(mag_b, 3.0 * (init ? sm : r));
+            if (std::isfinite(r)) mag_b = std::max(mag_b, 3.0 * r);  // (no bound: the part is never culled, its rounding is moot)
             break;
         }
         case MOP_PRIM_CIRCLE: case MOP_PRIM_RECT: case MOP_PRIM_CIRCLE_M: case MOP_PRIM_RECT_M: {
@@ -481,7 +481,7 @@ void analyse_parts(const std::vector<uint32_t> &code, cc_parts *out)
             r = sm * scale;
             mag_a = std::max(mag_a, scale * ((double)std::fabs(fl(o.pc, 9)) + std::fabs(fl(o.pc, 10)) + std::fabs(fl(o.pc, 11)) +
                                              std::fabs(fl(o.pc, 12)) + std::fabs(fl(o.pc, 13)) + std::fabs(fl(o.pc, 14)) + std::fabs(fl(o.pc, 15))));
-            mag_b = std::max(mag_b, 3.0 * r);
+            if (std::isfinite(r)) mag_b = std::max(mag_b, 3.0 * r);
             break;
         }
         case MOP_LOAD: r = ls; coords_of[(size_t)v] = o.in_s >= 0 ? coords_of[(size_t)o.in_s] : -1; break;
@@ -538,6 +538,7 @@ void analyse_parts(const std::vector<uint32_t> &code, cc_parts *out)
         out->lipschitz[(size_t)k] = std::isfinite(l) ? (float)(l * (1 + 1e-5)) : std::numeric_limits<float>::infinity();
         bounded += std::isfinite(l) ? 1 : 0;
     }
+    if (!std::isfinite(mag_a) || !std::isfinite(mag_b)) return;
     out->magnitude_a = (float)(mag_a + 1.0);
     out->magnitude_b = (float)std::max(mag_b, 3.0);
     out->enabled = bounded >= 1;  // (at least one part can ever be dropped)
