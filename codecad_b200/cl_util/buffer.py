@@ -23,11 +23,11 @@ class _Pinned:
         _lib.check(_lib.lib().cc_host_alloc(max(int(nbytes), 1), ctypes.byref(self.ptr)))
         self.nbytes = int(nbytes)
 
-    def array(self, dtype, shape):
+    def array(self, dtype, shape, offset=0):
         buf = (ctypes.c_uint8 * max(self.nbytes, 1)).from_address(self.ptr.value)
         buf._pinned_owner = self  # the array keeps the allocation alive through its buffer
         # (like numpy.empty(shape, dtype): a sub-array dtype such as (float4, (2,)) adds its own axes)
-        return np.ndarray(shape=shape, dtype=dtype, buffer=buf)
+        return np.ndarray(shape=shape, dtype=dtype, buffer=buf, offset=offset)
 
     def __del__(self):
         try:
@@ -126,16 +126,40 @@ class Buffer:
 
     @contextlib.contextmanager
     def map(self, map_flags=None, offset=None, shape=None, wait_for=None):
-        """Maps the buffer as a numpy array: read on entry, written back on exit."""
-        arr = self.read()
-        if offset is None:
-            offset = 0
-        view = arr.reshape(-1)[offset:] if offset else arr
-        if shape is not None:
-            n = int(np.prod(shape))
-            view = arr.reshape(-1)[offset:offset + n].reshape(shape)
-        yield view
-        self.enqueue_write().wait()
+        """Maps (part of) the buffer as a numpy array, like cl_buffer.py:101-122 /
+        pyopencl.enqueue_map_buffer: `offset` is in BYTES, `shape` defaults to the whole buffer.  A map
+        with READ (or no flags) sees the device contents; the mapped range is written back on exit — also
+        when the body raises — only if WRITE or WRITE_INVALIDATE_REGION was asked for (bits 2 and 4 of
+        the stand-in map_flags of dropin.py; None = read and write)."""
+        flags = 3 if map_flags is None else int(map_flags)
+        offset = int(offset or 0)
+        if shape is None:
+            shape = self.shape
+        try:
+            shape = tuple(int(v) for v in shape)
+        except TypeError:
+            shape = (int(shape),)
+        if offset % self.dtype.itemsize:
+            raise RuntimeError("map offset must be a multiple of the item size")
+        first = offset // self.dtype.itemsize
+        count = int(np.prod(shape)) if shape else 1
+        if first + count > self.nitems:
+            raise RuntimeError("mapped range exceeds the buffer")
+        writes = bool(flags & 6)
+        invalidate = bool(flags & 4) and not (flags & 1)
+        self._process_array(None)            # the page-locked mirror (.array)
+        if not invalidate:
+            self.read()                      # READ / WRITE: the current device contents
+        view = self._pinned.array(self.dtype, shape, offset)
+        try:
+            yield view
+        finally:
+            if writes:
+                nbytes = count * self.dtype.itemsize
+                ev = _new_event_ref()
+                _lib.check(_lib.lib().cc_memcpy_h2d_async(ctypes.c_void_p(self.device_ptr.value + offset),
+                                                          view.ctypes.data, nbytes, ctypes.byref(ev)))
+                Event(ev).wait()
 
     def __getitem__(self, key):
         return self.array[key]
