@@ -769,9 +769,22 @@ def run_ours(args):
         i_steps = max(1, min(args.steps, 2))
         i_ms = max_over_ranks(torch, dist, timed(kernel_step, i_steps)) / i_steps
         barrier(torch, dist)
-        prog.use_specialized(True)
         interp = {"value": total_points / (i_ms * 1e-3) / 1e9, "unit": "Gpts/s", "ms_per_step": i_ms,
                   "steps": i_steps, "kernel": "cc_eval_kernel<PTS,const,FLOAT4>"}
+        if parts_active:
+            # the interpreter walks the loader's segment table with the same per-brick masks (csrc/cc_parts.cu);
+            # the full walk (every micro-op at every point) is timed beside it
+            interp["kernel"] = "cc_parts_eval_kernel + cc_parts_centers_kernel (interpreter, per-brick part culling)"
+            old_parts = _lib.check(L.cc_set_parts_mode(0))
+            kernel_step()
+            _lib.check(L.cc_synchronize())
+            barrier(torch, dist)
+            f_ms = max_over_ranks(torch, dist, timed(kernel_step, 1))
+            barrier(torch, dist)
+            _lib.check(L.cc_set_parts_mode(old_parts))
+            interp["full_walk"] = {"value": total_points / (f_ms * 1e-3) / 1e9, "unit": "Gpts/s", "ms_per_step": f_ms,
+                                   "kernel": "cc_eval_kernel<PTS,const,FLOAT4>"}
+        prog.use_specialized(True)
 
     # ---- end to end: fresh program upload + result into pinned host memory ----
     e2e = None
@@ -885,6 +898,9 @@ def run_ours(args):
     achieved = (total_points / world) * flops_pt / (ms_step * 1e-3) / 1e12
     if interp:
         interp["roofline_frac"] = (total_points / world) * flops_pt / (interp["ms_per_step"] * 1e-3) / 1e12 / peak_tflops
+        if "full_walk" in interp:
+            interp["full_walk"]["roofline_frac"] = ((total_points / world) * flops_pt / (interp["full_walk"]["ms_per_step"] * 1e-3)
+                                                    / 1e12 / peak_tflops)
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "bench_traffic.json")
     if os.path.exists(tpath):

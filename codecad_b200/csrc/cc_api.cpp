@@ -373,7 +373,28 @@ int launch_forest(const cc_program *prog, cc_eval_args &a, uint64_t points)
 
 // Dense float4 grid of an assembly through the part-culling kernels; the caller checked
 // that the specialised kernels of CC_SINK_PARTS are loaded.
-int launch_parts(const cc_program *prog, cc_eval_args &a, uint64_t points)
+// cc_parts::table on the current device (replicated on first use)
+int parts_on_device(const cc_program *prog, const uint32_t **out)
+{
+    cc_program *p = const_cast<cc_program *>(prog);
+    uint32_t *&d = p->d_parts[g.index];
+    if (!d) {
+        const size_t bytes = p->dec.parts.table.size() * 4;
+        cudaError_t e = cudaMalloc(&d, bytes);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d, p->dec.parts.table.data(), bytes, cudaMemcpyHostToDevice, g.compute);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(g.compute);
+        if (e != cudaSuccess) {
+            if (d) cudaFree(d);
+            d = nullptr;
+            return cuda_fail(e, "part table upload");
+        }
+    }
+    *out = d;
+    return CC_OK;
+}
+
+// `specialised`: the NVRTC pair is loaded; otherwise the interpreter-tier pair of cc_parts.cu
+int launch_parts(const cc_program *prog, cc_eval_args &a, uint64_t points, bool specialised)
 {
     const uint64_t nb = (uint64_t)((a.nx + CC_BRICK_X - 1) / CC_BRICK_X) * ((a.ny + CC_BRICK_Y - 1) / CC_BRICK_Y) *
                         ((a.nz + CC_BRICK_Z - 1) / CC_BRICK_Z);
@@ -393,7 +414,15 @@ int launch_parts(const cc_program *prog, cc_eval_args &a, uint64_t points)
     a.part_slack = (float)(((double)prog->dec.parts.magnitude_a + (double)prog->dec.parts.magnitude_b * pmax) / 8192.0);
     if (!std::isfinite(a.part_slack)) return fail(CC_ERR_INVALID_ARGUMENT, "grid coordinates out of range");
     a.part_masks = g.d_part_masks;
-    int e = cc_jit_launch_parts(prog, a, (uint32_t)nb, g.compute, g.index);
+    int e;
+    if (specialised) {
+        e = cc_jit_launch_parts(prog, a, (uint32_t)nb, g.compute, g.index);
+    } else {
+        const uint32_t *table = nullptr;
+        int rc = parts_on_device(prog, &table);
+        if (rc) return rc;
+        e = cc_launch_parts_interp(a, table, (uint32_t)nb, g.compute);
+    }
     if (e) return cuda_fail((cudaError_t)e, "part-culling kernel launch");
     g.launches += 2;
     g.points += points;
@@ -409,8 +438,13 @@ bool parts_apply(int sink_kind, const cc_program *prog, const cc_eval_args &a)
 int launch(int sink_kind, const cc_program *prog, cc_eval_args &a, uint64_t points)
 {
     if (forest_applies(sink_kind, prog, a)) return launch_forest(prog, a, points);
-    if (parts_apply(sink_kind, prog, a) && jit_ready(const_cast<cc_program *>(prog), CC_SINK_PARTS))
-        return launch_parts(prog, a, points);
+    if (parts_apply(sink_kind, prog, a)) {
+        if (jit_ready(const_cast<cc_program *>(prog), CC_SINK_PARTS)) return launch_parts(prog, a, points, true);
+        // interpreter tier: the same culling by walking the segment table (needs the microcode in shared memory)
+        if (!prog->dec.parts.table.empty() && prog->dec.parts.n_parts <= 32 &&
+            cc_parts_smem_bytes(prog->dec.info.n_slots, prog->dec.info.n_micro_words, 2) * 2 <= (size_t)g.prop.sharedMemPerMultiprocessor)
+            return launch_parts(prog, a, points, false);
+    }
     // which specialised kernel serves the launch: point lists have their own (cc_jit_points)
     const int sink = a.points ? (int)CC_SINK_POINTS : sink_kind;
     if (jit_ready(const_cast<cc_program *>(prog), sink)) {
@@ -785,6 +819,7 @@ void cc_program_destroy(cc_program *prog)
             cudaStreamSynchronize(c.compute);
             if (prog->d_code[i]) cudaFree(prog->d_code[i]);
             if (prog->d_forest[i]) cudaFree(prog->d_forest[i]);
+            if (prog->d_parts[i]) cudaFree(prog->d_parts[i]);
             if (c.constant_program == prog->id) c.constant_program = 0;
         }
         cudaSetDevice(g.device);

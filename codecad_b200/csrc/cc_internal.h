@@ -38,7 +38,16 @@ struct cc_parts {
     std::vector<uint32_t> union_a, union_b;  // micro-op index of a union of the tree -> bit masks of the parts below its two operands (0 elsewhere)
     std::vector<float> lipschitz;         // per part: |w(p) - w(q)| <= lipschitz |p - q|   (inf: never culled)
     float magnitude_a = 0.0f, magnitude_b = 0.0f;  // rounding budget: 2^-13 (a + b max|p|)
+    // The same structure for the interpreter tier (cc_parts.cu), device table:
+    //   [0] n_parts  [1] n_segments  [2 .. 2+P) Lipschitz constants (float bits)  then P x (pc begin, pc end)
+    //   then n_segments x 4 words: (kind, a, b, c)
+    //     kind 0: micro-ops [a, b) always        kind 1: micro-ops [a, b) if mask & c (a part's run)
+    //     kind 2: the union at pc a if (mask & b) && (mask & c), else kind 3's effect with its dst slot
+    std::vector<uint32_t> table;
 };
+#define CC_SEG_ALWAYS 0u
+#define CC_SEG_PART 1u
+#define CC_SEG_UNION 2u
 
 struct cc_decoded {
     std::vector<uint32_t> microcode;
@@ -66,6 +75,7 @@ struct cc_program {
     cc_decoded dec;
     uint32_t *d_code[CC_MAX_DEVICES] = {};  // device copies of the microcode, one per initialised device (made on first use)
     void *d_forest[CC_MAX_DEVICES] = {};    // device copies of the forest tables (bounds, then events)
+    uint32_t *d_parts[CC_MAX_DEVICES] = {};  // device copies of cc_parts::table
     uint64_t id = 0;             // identifies what is currently loaded in a device's __constant__ window
     // scene-specialised kernels (cc_jit.cpp), one library per sink; null until compiled
     void *jit_library[CC_N_SINKS] = {};
@@ -137,6 +147,10 @@ struct cc_forest_launch {
 size_t cc_forest_smem_bytes(const cc_forest &f);          // of the (rare) second launch, the larger one
 uint32_t cc_forest_overflow_words(const cc_eval_args &a);  // scratch the launch needs: deferred super-tiles
 int cc_launch_forest(const cc_eval_args &a, const cc_forest_launch &f, uint32_t *d_overflow, int sm_count, void *stream);
+
+// part culling on the interpreter tier (cc_parts.cu): brick-centre pass + one CTA per quarter brick
+size_t cc_parts_smem_bytes(uint32_t n_slots, uint32_t code_words, int pts);
+int cc_launch_parts_interp(const cc_eval_args &a, const uint32_t *d_table, uint32_t n_bricks, void *stream);
 
 // hierarchy helper kernels
 struct cc_level_geom {

@@ -539,6 +539,38 @@ void analyse_parts(const std::vector<uint32_t> &code, cc_parts *out)
         bounded += std::isfinite(l) ? 1 : 0;
     }
     if (!std::isfinite(mag_a) || !std::isfinite(mag_b)) return;
+    {  // the table the interpreter tier walks (cc_internal.h)
+        std::vector<uint32_t> &t = out->table;
+        t.assign(2, 0u);
+        t[0] = (uint32_t)P;
+        for (int k = 0; k < P; ++k) {
+            uint32_t bits;
+            std::memcpy(&bits, &out->lipschitz[(size_t)k], 4);
+            t.push_back(bits);
+        }
+        auto end_pc = [&](int v) { return ops[(size_t)v].pc + CC_HDR_LEN(code[ops[(size_t)v].pc]); };
+        for (int k = 0; k < P; ++k) {
+            int lo = part_root[(size_t)k];
+            while (lo > 0 && part_of[(size_t)lo - 1] == k) --lo;
+            t.push_back(ops[(size_t)lo].pc);
+            t.push_back(end_pc(part_root[(size_t)k]));
+        }
+        uint32_t n_seg = 0;
+        for (int v = 0; v < n;) {
+            if (is_tree_union[(size_t)v]) {
+                t.insert(t.end(), {CC_SEG_UNION, ops[(size_t)v].pc, out->union_a[(size_t)v], out->union_b[(size_t)v]});
+                ++v;
+            } else {
+                const int k = part_of[(size_t)v];
+                int w = v;
+                while (w + 1 < n && part_of[(size_t)w + 1] == k && !is_tree_union[(size_t)w + 1]) ++w;
+                t.insert(t.end(), {k >= 0 ? CC_SEG_PART : CC_SEG_ALWAYS, ops[(size_t)v].pc, end_pc(w), k >= 0 ? (1u << k) : 0u});
+                v = w + 1;
+            }
+            ++n_seg;
+        }
+        t[1] = n_seg;
+    }
     out->magnitude_a = (float)(mag_a + 1.0);
     out->magnitude_b = (float)std::max(mag_b, 3.0);
     out->enabled = bounded >= 1;  // (at least one part can ever be dropped)

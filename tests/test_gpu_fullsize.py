@@ -67,6 +67,29 @@ def test_planetary_1024_cubed(cb, scenes):
     t2 = _planes(L, out, n, sample)
     crc2 = zlib.crc32(b"".join(np.uint32(zlib.crc32(t2[x].tobytes())).tobytes() for x in sample))
     assert crc1 == crc2
+    # tier 3 (the part-culling pair, what dense grids of this assembly use in steady state): the same planes,
+    # and every byte of a 128-plane slab through the middle of the gearbox against tier 2
+    mid = Buffer(FLOAT4, (128, n, n))
+    cb.grid_eval(prog, corner, step, (128, n, n), x_offset=448, device_out=mid)
+    want_mid = np.empty((128, n, n, 4), np.float32)
+    _lib.check(L.cc_memcpy_d2h_async(want_mid.ctypes.data, mid.device_ptr, want_mid.nbytes, None))
+    _lib.check(L.cc_synchronize())
+    prog.specialize(0, ProgramBuffer.SINK_PARTS)
+    launches0, _ = _lib.counters()
+    _lib.check(L.cc_memset_async(out.device_ptr, 0, n * n * n * 16, None))
+    cb.grid_eval(prog, corner, step, (n, n, n), device_out=out)
+    assert _lib.counters()[0] == launches0 + 2, "the part-culling kernels did not run"
+    t3 = _planes(L, out, n, sample)
+    crc3 = zlib.crc32(b"".join(np.uint32(zlib.crc32(t3[x].tobytes())).tobytes() for x in sample))
+    assert crc1 == crc3
+    _lib.check(L.cc_memset_async(mid.device_ptr, 0, want_mid.nbytes, None))
+    cb.grid_eval(prog, corner, step, (128, n, n), x_offset=448, device_out=mid)
+    got_mid = np.empty_like(want_mid)
+    _lib.check(L.cc_memcpy_d2h_async(got_mid.ctypes.data, mid.device_ptr, got_mid.nbytes, None))
+    _lib.check(L.cc_synchronize())
+    assert got_mid.tobytes() == want_mid.tobytes()
+    mid.release()
+    del got_mid, want_mid
     # z-slab sharding as on 8 GPUs: rank 5 of 8 evaluates x in [640, 768) with an offset
     x0, x1 = cb.grid_eval.__globals__["slab_range"](n, 5, 8)
     slab = Buffer(FLOAT4, (x1 - x0, n, n))
@@ -93,6 +116,26 @@ def test_synthetic500_2048_slab(cb, scenes):
     got = np.stack([got["x"], got["y"], got["z"], got["w"]], axis=-1)
     want = oracle.grid_eval(s.words, corner, step, dims, x_offset=x0 + 100)
     assert np.array_equal(got, want, equal_nan=True)
+
+
+def test_synthetic500_culled_slab_equals_the_full_walk(cb, scenes):
+    """64 x-planes of the 2048^3 grid (2.7e8 points) of the 500-box scene: the union-forest kernel against
+    the interpreter, which evaluates all 500 boxes at every point — every byte."""
+    from codecad_b200 import _lib
+    L = _lib.lib()
+    s = scenes["cfg_synthetic500"]
+    n = 2048
+    corner, step = s.grid(n)
+    scene = s.compiled()
+    dims = (64, n, n)
+    _lib.check(L.cc_set_forest_mode(1))
+    got = np.array(cb.grid_eval(scene, corner, step, dims, x_offset=1000))
+    try:
+        _lib.check(L.cc_set_forest_mode(0))
+        want = np.array(cb.grid_eval(scene, corner, step, dims, x_offset=1000))
+    finally:
+        _lib.check(L.cc_set_forest_mode(1))
+    assert got.tobytes() == want.tobytes()
 
 
 def test_airfoil_mass_properties_config(cb, scenes):

@@ -83,3 +83,62 @@ def test_parts_equal_the_unculled_kernels(cb, scenes, name):
         want = np.array(cb.grid_eval(scene, corner, st, dims, x_offset=x_offset))
         _lib.check(L.cc_set_parts_mode(1))
         assert got.tobytes() == want.tobytes(), "%s frac %g" % (name, frac)
+
+
+# ---- the same culling on the interpreter tier (cc_parts.cu): what runs before NVRTC has delivered ----
+
+@pytest.fixture()
+def interpreter_only(cb):
+    from codecad_b200 import _lib
+    L = _lib.lib()
+    old = _lib.check(L.cc_set_jit_mode(0))
+    yield
+    _lib.check(L.cc_set_jit_mode(old))
+
+
+@pytest.mark.parametrize("name", PART_SCENES)
+def test_interpreter_parts_bit_exact_vs_oracle(cb, interpreter_only, scenes, name):
+    from codecad_b200 import _lib
+    _lib.check(_lib.lib().cc_set_parts_mode(1))
+    s = scenes[name]
+    scene = s.compiled()
+    rng = np.random.default_rng(5)
+    a, b = np.array(s.box_a), np.array(s.box_b)
+    if s.dimension == 2:
+        a[2], b[2] = -1.0, 1.0
+    size = float(max(b - a))
+    corner, step = s.grid(48)
+    windows = [(corner, step, (48, 40, 33))]
+    for frac, dims in ((0.3, (40, 33, 48)), (0.05, (33, 48, 40)), (0.01, (24, 40, 64))):
+        centre = a + (b - a) * rng.uniform(0.2, 0.8, 3)
+        st = np.float32(size * frac / 32)
+        windows.append(((centre - st * np.array(dims) / 2).astype(np.float32), st, dims))
+    for corner, step, dims in windows:
+        want = oracle.grid_eval(s.words, corner, step, dims)
+        got = _f4(cb.grid_eval(scene, corner, step, dims))
+        assert np.array_equal(got, want, equal_nan=True), "%s step %g: %d values differ" % (name, step, int((got != want).sum()))
+
+
+@pytest.mark.parametrize("name", PART_SCENES)
+def test_interpreter_parts_equal_the_full_walk(cb, interpreter_only, scenes, name):
+    from codecad_b200 import _lib
+    L = _lib.lib()
+    s = scenes[name]
+    scene = s.compiled()
+    rng = np.random.default_rng(19)
+    a, b = np.array(s.box_a), np.array(s.box_b)
+    if s.dimension == 2:
+        a[2], b[2] = -1.0, 1.0
+    size = float(max(b - a))
+    for frac, dims, x_offset in ((1.05, (128, 128, 128), 0), (0.3, (130, 70, 90), 5), (0.04, (64, 136, 100), 0)):
+        centre = a + (b - a) * rng.uniform(0.3, 0.7, 3)
+        st = np.float32(size * frac / max(dims))
+        corner = (centre - st * np.array(dims) / 2).astype(np.float32)
+        _lib.check(L.cc_set_parts_mode(1))
+        n0 = _lib.counters()[0]
+        got = np.array(cb.grid_eval(scene, corner, st, dims, x_offset=x_offset))
+        assert (_lib.counters()[0] - n0) % 2 == 0 and _lib.counters()[0] > n0   # brick centres + the culled walk, per chunk
+        _lib.check(L.cc_set_parts_mode(0))
+        want = np.array(cb.grid_eval(scene, corner, st, dims, x_offset=x_offset))
+        _lib.check(L.cc_set_parts_mode(1))
+        assert got.tobytes() == want.tobytes(), "%s frac %g" % (name, frac)

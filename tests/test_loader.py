@@ -171,3 +171,18 @@ def test_union_forests_are_recognised_and_nothing_else(scenes):
                 assert want[name][1] in (None, info.forest_depth)
         else:
             assert info.n_forest_leaves == 0 and info.forest_depth == 0, name
+
+
+def test_assemblies_are_cut_into_parts(scenes):
+    """cc_program.cpp analyse_parts: sharp unions over self-contained sub-programs, each with a Lipschitz
+    bound unless it contains an op that has none."""
+    from codecad_b200 import _lib
+    want = {"cfg_planetary": (7, 7), "cfg_menger_sponge": (2, 1), "dsdf3d_mirror_3d": (5, 5), "dsdf2d_mirror_2d": (4, 4),
+            "dsdf2d_rotated_pattern_2d": (3, 3)}
+    for name, s in scenes.items():
+        info, _ = _lib.decode_program(s.words)
+        if name in want:
+            assert (info.n_parts, info.n_parts_bounded) == want[name], name
+        assert info.n_parts_bounded <= info.n_parts <= 32
+        if name in ("cfg_csg_example", "cfg_airfoil", "mp_sphere", "x_smooth_isect"):
+            assert info.n_parts == 0, name        # one component, or a rounded combinator at the root
