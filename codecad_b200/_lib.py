@@ -32,7 +32,8 @@ class DeviceInfo(ctypes.Structure):
 class ProgramInfo(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint32) for n in (
         "n_words", "n_instructions", "n_micro_ops", "n_micro_words", "n_wire_registers",
-        "n_slots", "n_fused", "flops_min", "flops_max", "n_forest_leaves", "forest_depth", "n_parts", "n_parts_bounded")]
+        "n_slots", "n_fused", "flops_min", "flops_max", "n_forest_leaves", "forest_depth", "n_parts", "n_parts_bounded",
+        "column_invariant_percent")]
 
 
 class Level(ctypes.Structure):
@@ -68,6 +69,7 @@ SIGNATURES = {
     "cc_set_jit_mode": (_I, [_I]),
     "cc_set_forest_mode": (_I, [_I]),
     "cc_set_parts_mode": (_I, [_I]),
+    "cc_set_columns_mode": (_I, [_I]),
     "cc_program_get_forest_info": (_I, [_V, c_u32_p]),
     "cc_program_specialize_wait": (_I, [_V, _U, ctypes.POINTER(ctypes.c_double)]),
     "cc_specialize_source": (_I, [c_float_p, _U, _I, _U, ctypes.c_char_p, _U, _I, ctypes.POINTER(ctypes.c_uint64)]),

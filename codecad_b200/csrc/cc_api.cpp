@@ -38,6 +38,9 @@ struct Context {
     int jit_mode = 1;             // 0 never, 1 background (default), 2 compile at first use and wait
     int forest_mode = 1;          // 1: dense grids of union-forest programs use the culling kernel (cc_forest.cu)
     int parts_mode = 1;           // 1: dense grids of assemblies skip, per brick, the parts that cannot be nearest
+    int columns_mode = 1;         // 1: dense grids evaluate what cannot see z once per z-column
+    void *d_columns = nullptr;    // column buffer of the column kernels (values, flags, brick list)
+    size_t columns_cap = 0;
     uint32_t *d_part_masks = nullptr;
     size_t part_masks_cap = 0;
     uint32_t jit_max_ops = 4096;  // programs longer than this are not specialised automatically
@@ -393,12 +396,9 @@ int parts_on_device(const cc_program *prog, const uint32_t **out)
     return CC_OK;
 }
 
-// `specialised`: the NVRTC pair is loaded; otherwise the interpreter-tier pair of cc_parts.cu
-int launch_parts(const cc_program *prog, cc_eval_args &a, uint64_t points, bool specialised)
+// the brick masks' buffer and the rounding budget of the parts' values
+int prepare_part_masks(const cc_program *prog, cc_eval_args &a, uint64_t nb)
 {
-    const uint64_t nb = (uint64_t)((a.nx + CC_BRICK_X - 1) / CC_BRICK_X) * ((a.ny + CC_BRICK_Y - 1) / CC_BRICK_Y) *
-                        ((a.nz + CC_BRICK_Z - 1) / CC_BRICK_Z);
-    if (nb >= (1ull << 31)) return fail(CC_ERR_INVALID_ARGUMENT, "too many bricks in one launch");
     if (nb > g.part_masks_cap) {
         if (g.d_part_masks) CU(cudaFree(g.d_part_masks));
         g.d_part_masks = nullptr;
@@ -414,6 +414,17 @@ int launch_parts(const cc_program *prog, cc_eval_args &a, uint64_t points, bool 
     a.part_slack = (float)(((double)prog->dec.parts.magnitude_a + (double)prog->dec.parts.magnitude_b * pmax) / 8192.0);
     if (!std::isfinite(a.part_slack)) return fail(CC_ERR_INVALID_ARGUMENT, "grid coordinates out of range");
     a.part_masks = g.d_part_masks;
+    return CC_OK;
+}
+
+// `specialised`: the NVRTC pair is loaded; otherwise the interpreter-tier pair of cc_parts.cu
+int launch_parts(const cc_program *prog, cc_eval_args &a, uint64_t points, bool specialised)
+{
+    const uint64_t nb = (uint64_t)((a.nx + CC_BRICK_X - 1) / CC_BRICK_X) * ((a.ny + CC_BRICK_Y - 1) / CC_BRICK_Y) *
+                        ((a.nz + CC_BRICK_Z - 1) / CC_BRICK_Z);
+    if (nb >= (1ull << 31)) return fail(CC_ERR_INVALID_ARGUMENT, "too many bricks in one launch");
+    int prc = prepare_part_masks(prog, a, nb);
+    if (prc) return prc;
     int e;
     if (specialised) {
         e = cc_jit_launch_parts(prog, a, (uint32_t)nb, g.compute, g.index);
@@ -429,6 +440,54 @@ int launch_parts(const cc_program *prog, cc_eval_args &a, uint64_t points, bool 
     return CC_OK;
 }
 
+// Dense float4 grid through the column kernel: one warp per 8 x 8 x 16 brick, what does not
+// depend on z evaluated once per column; with the parts' masks when the scene is an assembly.
+int launch_columns(const cc_program *prog, cc_eval_args &a, uint64_t points, bool with_parts)
+{
+    const uint64_t nb = (uint64_t)((a.nx + CC_BRICK_X - 1) / CC_BRICK_X) * ((a.ny + CC_BRICK_Y - 1) / CC_BRICK_Y) *
+                        ((a.nz + CC_BRICK_Z - 1) / CC_BRICK_Z);
+    if (nb >= (1ull << 31)) return fail(CC_ERR_INVALID_ARGUMENT, "too many bricks in one launch");
+    const cc_columns_meta &meta = prog->jit_columns;
+    const uint64_t ncol = (uint64_t)a.nx * a.ny;
+    // column buffer (+ flags, brick list, counter behind it when some transform row is checked per column)
+    const size_t values = (size_t)ncol * 4 * std::max(1u, meta.n_values) * sizeof(float);
+    const size_t flags_at = (values + 255) & ~(size_t)255, list_at = (flags_at + ncol + 255) & ~(size_t)255;
+    const size_t bytes = meta.checks ? list_at + ((size_t)nb + 1) * 4 : values;
+    if (bytes > g.columns_cap) {
+        if (g.d_columns) CU(cudaFree(g.d_columns));
+        g.d_columns = nullptr;
+        g.columns_cap = 0;
+        CU(cudaMalloc(&g.d_columns, bytes));
+        g.columns_cap = bytes;
+    }
+    a.columns = reinterpret_cast<float *>(g.d_columns);
+    a.column_flags = nullptr;
+    a.brick_list = a.brick_count = nullptr;
+    if (meta.checks) {
+        a.column_flags = reinterpret_cast<unsigned char *>(g.d_columns) + flags_at;
+        a.brick_count = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(g.d_columns) + list_at);
+        a.brick_list = a.brick_count + 1;
+        CU(cudaMemsetAsync(a.brick_count, 0, 4, g.compute));
+    }
+    a.part_masks = nullptr;
+    if (with_parts) {
+        int rc = prepare_part_masks(prog, a, nb);
+        if (rc) return rc;
+    }
+    int n_launches = 0;
+    int e = cc_jit_launch_columns(prog, a, (uint32_t)nb, g.prop.multiProcessorCount, g.compute, g.index, &n_launches);
+    if (e) return cuda_fail((cudaError_t)e, "column kernel launch");
+    g.launches += (uint64_t)n_launches;
+    g.points += points;
+    return CC_OK;
+}
+
+bool columns_apply(int sink_kind, const cc_program *prog, const cc_eval_args &a)
+{
+    return g.columns_mode && sink_kind == CC_SINK_FLOAT4 && !a.points && !a.blocks && prog->dec.columns.enabled &&
+           a.nz >= 8 && (uint64_t)a.nx * a.ny * a.nz >= 4096;
+}
+
 bool parts_apply(int sink_kind, const cc_program *prog, const cc_eval_args &a)
 {
     return g.parts_mode && sink_kind == CC_SINK_FLOAT4 && !a.points && !a.blocks && prog->dec.parts.enabled &&
@@ -438,6 +497,13 @@ bool parts_apply(int sink_kind, const cc_program *prog, const cc_eval_args &a)
 int launch(int sink_kind, const cc_program *prog, cc_eval_args &a, uint64_t points)
 {
     if (forest_applies(sink_kind, prog, a)) return launch_forest(prog, a, points);
+    if (columns_apply(sink_kind, prog, a)) {
+        cc_program *p = const_cast<cc_program *>(prog);
+        const bool with_parts = parts_apply(sink_kind, prog, a);
+        // (the specialised column kernels or nothing: until they are loaded the other paths serve the launch)
+        if (jit_ready(p, CC_SINK_COLUMNS) && (uint64_t)a.nx * a.ny * 16 * std::max(1u, p->jit_columns.n_values) <= (8ull << 30))
+            return launch_columns(prog, a, points, with_parts);
+    }
     if (parts_apply(sink_kind, prog, a)) {
         if (jit_ready(const_cast<cc_program *>(prog), CC_SINK_PARTS)) return launch_parts(prog, a, points, true);
         // interpreter tier: the same culling by walking the segment table (needs the microcode in shared memory)
@@ -540,6 +606,8 @@ int init_context(Context &c, int device, int index)
     if (p) c.forest_mode = atoi(p) != 0;
     p = getenv("CODECAD_B200_PARTS");
     if (p) c.parts_mode = atoi(p) != 0;
+    p = getenv("CODECAD_B200_COLUMNS");
+    if (p) c.columns_mode = atoi(p) != 0;
     c.ready = true;
     return CC_OK;
 }
@@ -707,6 +775,7 @@ void cc_shutdown(void)
         if (c.d_status) cudaFree(c.d_status);
         if (c.d_forest_scratch) cudaFree(c.d_forest_scratch);
         if (c.d_part_masks) cudaFree(c.d_part_masks);
+        if (c.d_columns) cudaFree(c.d_columns);
         if (c.h_word) cudaFreeHost(c.h_word);
         for (int i = 0; i < Context::kRing; ++i) {
             if (c.ring[i]) cudaFree(c.ring[i]);
@@ -894,6 +963,14 @@ int cc_set_forest_mode(int mode)
     return old;
 }
 
+int cc_set_columns_mode(int mode)
+{
+    const int old = g.columns_mode;
+    if (mode != 0 && mode != 1) return fail(CC_ERR_INVALID_ARGUMENT, "columns mode must be 0 or 1");
+    for (int i = 0; i < CC_MAX_DEVICES; ++i) g_ctx[i].columns_mode = mode;
+    return old;
+}
+
 int cc_set_parts_mode(int mode)
 {
     const int old = g.parts_mode;
@@ -920,6 +997,7 @@ int cc_program_specialize_wait(cc_program *prog, unsigned sink_mask, double *com
     if ((sink_mask & CC_SINK_MASK_ALL) == 0) sink_mask = 15u;
     // dense float4 grids of an assembly run on the part-culling kernels: "ready" includes them
     if ((sink_mask & (1u << CC_SINK_FLOAT4)) && prog->dec.parts.enabled && g.parts_mode) sink_mask |= 1u << CC_SINK_PARTS;
+    if ((sink_mask & (1u << CC_SINK_FLOAT4)) && prog->dec.columns.enabled && g.columns_mode) sink_mask |= 1u << CC_SINK_COLUMNS;
     int ready = 0;
     for (int k = 0; k < CC_N_SINKS; ++k) {
         if (!(sink_mask & (1u << k))) continue;

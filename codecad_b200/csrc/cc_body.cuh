@@ -189,12 +189,12 @@ CC_DEV void cc_brick_of(const cc_eval_args &a, uint32_t brick, uint32_t &x0, uin
 }
 
 template <int PTS, class EVAL>
-CC_DEV void cc_kernel_body_bricks(const cc_eval_args &a, EVAL &eval)
+CC_DEV void cc_kernel_body_bricks_at(const cc_eval_args &a, EVAL &eval, uint32_t brick)
 {
     static_assert(PTS == 2 && CC_THREADS * PTS == CC_BRICK_X * CC_BRICK_Y * CC_BRICK_Z, "one brick per CTA");
     typedef typename cc_pts<PTS>::V V;
     uint32_t x0, y0, z0;
-    cc_brick_of(a, blockIdx.x, x0, y0, z0);
+    cc_brick_of(a, brick, x0, y0, z0);
     const uint32_t tid = threadIdx.x;
     uint32_t ix[PTS], iy[PTS], iz[PTS];
     float gx[PTS], gy[PTS], gz[PTS];
@@ -220,6 +220,122 @@ CC_DEV void cc_kernel_body_bricks(const cc_eval_args &a, EVAL &eval)
     for (int j = 0; j < PTS; ++j)
         if (ix[j] < a.nx && iy[j] < a.ny && iz[j] < a.nz)
             __stcs(out + ((size_t)ix[j] * a.ny + iy[j]) * a.nz + iz[j], cc_lane_get(LV[0], j));  // INDEX3
+}
+
+// ---- columns: what cannot see the grid's z is evaluated once per z-column -----------------
+// Three kernels around two generated functors.  AHEAD runs, for every (x, y) column of the launch, the
+// micro-ops that cannot depend on z and writes the values the rest of the program reads from them into the
+// column buffer  float4 columns[nx * ny][CC_COL_VALUES];  LOOP is the rest of the program, run per
+// cell by the brick kernel, which reads those values instead of computing them.  A column for which the
+// run-time check of AHEAD::invariant() fails (cc_jit.cpp) flags its bricks; they are evaluated by the full
+// walk in a third launch.
+#ifndef CC_COL_VALUES
+#define CC_COL_VALUES 1  // values per column record (the generated source defines it)
+#endif
+struct cc_col_ref {
+    float4 *rec[2];  // the column record of each point of the thread's pair: float4 rec[CC_COL_VALUES]
+    bool ok[2];
+};
+template <class V> CC_DEV void cc_col_store(const cc_col_ref &r, uint32_t k, const cc_val<V> &v)
+{
+#pragma unroll
+    for (int l = 0; l < cc_lane<V>::N; ++l)
+        if (r.ok[l]) r.rec[l][k] = cc_lane_get(v, l);
+}
+template <class V> CC_DEV cc_val<V> cc_col_load(const cc_col_ref &r, uint32_t k)
+{
+    cc_val<V> v;
+#pragma unroll
+    for (int l = 0; l < cc_lane<V>::N; ++l) cc_lane_put(v, l, __ldg(r.rec[l] + k));
+    return v;
+}
+CC_DEV bool cc_same_bits(float a, float b) { return __float_as_uint(a) == __float_as_uint(b) && a == a; }
+CC_DEV bool cc_same_bits(float2 a, float2 b) { return cc_same_bits(a.x, b.x) && cc_same_bits(a.y, b.y); }
+
+// one thread per pair of columns 2t, 2t + 1 (column = ix * ny + iy)
+template <int PTS, class AHEAD>
+CC_DEV void cc_column_profiles_body(const cc_eval_args &a, AHEAD &ahead)
+{
+    static_assert(PTS == 2, "two columns per thread");
+    typedef typename cc_pts<PTS>::V V;
+    const uint32_t ncol = a.nx * a.ny, t = blockIdx.x * CC_THREADS + threadIdx.x;
+    float gx[PTS], gy[PTS], gz[PTS], gl[PTS];
+    uint32_t col[PTS];
+#pragma unroll
+    for (int j = 0; j < PTS; ++j) {
+        const uint32_t c = 2u * t + (uint32_t)j;
+        ahead.cr.ok[j] = c < ncol;
+        col[j] = min(c, ncol - 1u);  // (every thread evaluates: the ops vote across the warp)
+        ahead.cr.rec[j] = reinterpret_cast<float4 *>(a.columns) + (size_t)col[j] * CC_COL_VALUES;
+        const uint32_t ix = col[j] / a.ny, iy = col[j] - ix * a.ny;
+        gx[j] = cc_fma(a.step, (float)(ix + a.x_offset), a.cx);
+        gy[j] = cc_fma(a.step, (float)iy, a.cy);
+        gz[j] = cc_fma(a.step, 0.0f, a.cz);
+        gl[j] = cc_fma(a.step, (float)(a.nz - 1u), a.cz);
+    }
+    V vx[1], vy[1], vz[1], vl[1];
+    vx[0] = cc_pack<V>(gx);
+    vy[0] = cc_pack<V>(gy);
+    vz[0] = cc_pack<V>(gz);
+    vl[0] = cc_pack<V>(gl);
+    if (a.column_flags) {
+        const unsigned char bad = ahead.invariant(vx, vy, vz, vl) ? 0 : 1;
+#pragma unroll
+        for (int j = 0; j < PTS; ++j)
+            if (ahead.cr.ok[j]) a.column_flags[col[j]] = bad;
+    }
+    ahead(vx, vy, vz);
+}
+
+// the brick kernel of cc_kernel_body_bricks with the thread's two columns at hand
+template <int PTS, class EVAL>
+CC_DEV void cc_kernel_body_brick_columns(const cc_eval_args &a, EVAL &eval)
+{
+    static_assert(PTS == 2 && CC_THREADS * PTS == CC_BRICK_X * CC_BRICK_Y * CC_BRICK_Z, "one brick per CTA");
+    typedef typename cc_pts<PTS>::V V;
+    uint32_t x0, y0, z0;
+    cc_brick_of(a, blockIdx.x, x0, y0, z0);
+    const uint32_t tid = threadIdx.x;
+    uint32_t ix[PTS], iy[PTS], iz[PTS], col[PTS];
+    float gx[PTS], gy[PTS], gz[PTS];
+#pragma unroll
+    for (int j = 0; j < PTS; ++j) {
+        const uint32_t c = (uint32_t)j * CC_THREADS + tid;
+        ix[j] = x0 + (c >> 7);
+        iy[j] = y0 + ((c >> 4) & 7u);
+        iz[j] = z0 + (c & 15u);
+        gx[j] = cc_fma(a.step, (float)(ix[j] + a.x_offset), a.cx);
+        gy[j] = cc_fma(a.step, (float)iy[j], a.cy);
+        gz[j] = cc_fma(a.step, (float)iz[j], a.cz);
+        col[j] = min(ix[j], a.nx - 1u) * a.ny + min(iy[j], a.ny - 1u);  // (cells past the edge read a neighbour's column)
+        eval.cr.rec[j] = reinterpret_cast<float4 *>(a.columns) + (size_t)col[j] * CC_COL_VALUES;
+        eval.cr.ok[j] = true;
+    }
+    if (a.column_flags) {
+        // a column whose "invariant" micro-ops do see z in some bit: the whole brick takes the full walk
+        const int flagged = __syncthreads_or((int)(a.column_flags[col[0]] | a.column_flags[col[1]]));
+        if (flagged) {
+            if (tid == 0) a.brick_list[atomicAdd(a.brick_count, 1u)] = blockIdx.x;
+            return;
+        }
+    }
+    V vx[1], vy[1], vz[1];
+    cc_val<V> LV[1];
+    vx[0] = cc_pack<V>(gx);
+    vy[0] = cc_pack<V>(gy);
+    vz[0] = cc_pack<V>(gz);
+    eval(vx, vy, vz, LV);
+    float4 *out = reinterpret_cast<float4 *>(a.out);
+#pragma unroll
+    for (int j = 0; j < PTS; ++j)
+        if (ix[j] < a.nx && iy[j] < a.ny && iz[j] < a.nz)
+            __stcs(out + ((size_t)ix[j] * a.ny + iy[j]) * a.nz + iz[j], cc_lane_get(LV[0], j));  // INDEX3
+}
+
+template <int PTS, class EVAL>
+CC_DEV void cc_kernel_body_bricks(const cc_eval_args &a, EVAL &eval)
+{
+    cc_kernel_body_bricks_at<PTS>(a, eval, blockIdx.x);
 }
 
 // Brick-centre pass.  Thread t evaluates every part at the centres of bricks 2t and 2t + 1 (one packed

@@ -33,6 +33,7 @@ enum cc_sink_kind {
     CC_SINK_RAY, CC_SINK_BITMAP,  // image renderers (cc_render.cuh), one point per thread
     CC_SINK_POINTS,               // FLOAT4 sink fed from a point list (cc_evaluate_points)
     CC_SINK_PARTS,                // FLOAT4 sink over 8 x 8 x 16 bricks with per-brick part masks (cc_jit.cpp)
+    CC_SINK_COLUMNS,              // FLOAT4 sink, one z-column of a brick per lane: what does not depend on z is evaluated once
     CC_N_SINKS
 };
 
@@ -67,6 +68,11 @@ struct cc_eval_args {
     // part culling (CC_SINK_PARTS): one mask per brick, bit k = part k can matter there
     uint32_t *part_masks;
     float part_slack;     // bound on |computed - exact| of a part's value over the launch
+    // columns (CC_SINK_COLUMNS, cc_body.cuh): per-column values of the z-invariant micro-ops, columns that
+    // failed the run-time check (null: the program has nothing to check), the bricks those send to the full walk
+    float *columns;
+    unsigned char *column_flags;
+    uint32_t *brick_list, *brick_count;
 };
 
 // bricks of the part-culling kernels: a CTA of 512 threads x 2 points

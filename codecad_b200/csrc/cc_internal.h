@@ -49,11 +49,27 @@ struct cc_parts {
 #define CC_SEG_PART 1u
 #define CC_SEG_UNION 2u
 
+// Columns.  On a dense grid the z axis of the grid is the z axis of the program's point;
+// a 2-D profile under an extrusion — transform, polygon, gear, their unions — sees x and y only, so its
+// value is the same for every cell of a z-column.  The loader tracks, op by op and component by component,
+// what can depend on the grid's z, and splits the micro-ops into those that run once per column (before
+// the z loop) and those that run per cell (cc_program.cpp analyse_columns, cc_jit.cpp).
+struct cc_columns {
+    bool enabled = false;
+    std::vector<uint8_t> phase;        // per micro-op: bit 0 = runs before the z loop, bit 1 = runs inside it
+    std::vector<int> restore_from;     // per micro-op of the loop: the op (outside the loop) whose result is its running value, else -1
+    std::vector<uint8_t> save_l;       // per micro-op: its result is carried into the loop as a running value
+    int root_restore = -1;             // the program's result itself is column-invariant: op index, else -1
+    std::vector<uint32_t> checked_rows;  // (micro-op index * 4 + row) of T_INIT rows whose z coefficient is rounding residue: verified per column
+    float invariant_share = 0.0f;      // estimated share of the arithmetic that leaves the loop
+};
+
 struct cc_decoded {
     std::vector<uint32_t> microcode;
     cc_program_info info;
     cc_forest forest;
     cc_parts parts;
+    cc_columns columns;
 };
 
 // cc_program.cpp
@@ -68,6 +84,12 @@ struct cc_jit_cfg {
     int segment_ops = 96;    // programs longer than ~1.5x this are cut into functions of this many micro-ops
 };
 struct cc_jit_job;
+// what the column kernels of a program need from the host (filled by the code generator)
+struct cc_columns_meta {
+    uint32_t n_values = 0;  // carried values: the column buffer holds 4 * n_values floats per column
+    bool checks = false;    // some transform row is verified per column: flags, brick list and the full-walk kernel exist
+    bool centers = false;   // the program has parts: the library has its own brick-centre kernel
+};
 
 #define CC_MAX_DEVICES 16  // devices one process can drive (cc_init_devices)
 
@@ -81,6 +103,8 @@ struct cc_program {
     void *jit_library[CC_N_SINKS] = {};
     void *jit_kernel[CC_N_SINKS] = {};
     void *jit_kernel_centers = nullptr;  // CC_SINK_PARTS: the brick-centre pass of the same library
+    void *jit_columns_kernels[3] = {};   // CC_SINK_COLUMNS: centres, profiles, full walk (jit_kernel[] holds the brick kernel)
+    cc_columns_meta jit_columns;
     cc_jit_cfg jit_cfg[CC_N_SINKS];
     size_t jit_smem[CC_N_SINKS] = {};  // dynamic shared memory of each specialised kernel
     bool jit_attr_done[CC_N_SINKS][CC_MAX_DEVICES] = {};  // MaxDynamicSharedMemorySize is a per-device attribute
@@ -102,7 +126,10 @@ void cc_jit_release(cc_program *prog);
 // dev_index = index of the library context (device) the launch goes to
 int cc_jit_launch(const cc_program *prog, int sink, const cc_eval_args &a, void *stream, int dev_index);
 // part culling: the centre pass over `n_bricks` bricks, then one CTA per brick
-int cc_jit_launch_parts(const cc_program *prog, const cc_eval_args &a, uint32_t n_bricks, void *stream, int dev_index);
+int cc_jit_launch_parts(const cc_program *prog, const cc_eval_args &a, uint32_t n_bricks, void *stream, int dev_index,
+                        bool centers_only = false);
+int cc_jit_launch_columns(const cc_program *prog, const cc_eval_args &a, uint32_t n_bricks, int sm_count, void *stream, int dev_index,
+                          int *n_launches);
 int cc_jit_launch_render(const cc_program *prog, int sink, const cc_render_args &a, void *stream, int dev_index);
 cc_jit_cfg cc_jit_render_cfg(const cc_decoded &dec);
 #define CC_SINK_MASK_ALL ((1u << CC_N_SINKS) - 1u)

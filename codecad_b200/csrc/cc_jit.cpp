@@ -227,7 +227,7 @@ std::string extra_defines()
 }
 
 int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, std::string *src, size_t *smem_bytes,
-             std::string *err)
+             std::string *err, cc_columns_meta *columns_meta = nullptr)
 {
     const int pts = cfg.pts;
     // debugging aids: stop after N micro-ops (bisecting a mismatch), force scalar lanes
@@ -240,13 +240,27 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
     std::ostringstream &o = g.body;
     // part culling: the run of micro-ops of part k is wrapped in `if (mask & (1 << k))`,
     // a union of the tree is taken only if both operands keep a part; generated for CC_SINK_PARTS only
-    const bool parts_mode = (sink_mask & (1u << CC_SINK_PARTS)) != 0;
+    // columns: the micro-ops that cannot see the grid's z (cc_program.cpp analyse_columns) become
+    // one functor that runs once per (x, y) column and leaves its results in the column buffer, the rest another
+    // that runs per cell and reads them there; a third is the full walk (brick centres, flagged bricks).
+    const bool columns_mode = (sink_mask & (1u << CC_SINK_COLUMNS)) != 0;
+    const cc_columns &cols = dec.columns;
     const cc_parts &parts = dec.parts;
-    if (parts_mode && (!parts.enabled || pts != 2 || cfg.threads * pts != CC_BRICK_X * CC_BRICK_Y * CC_BRICK_Z)) {
+    const bool parts_mode = (sink_mask & (1u << CC_SINK_PARTS)) != 0 || (columns_mode && parts.enabled);
+    if (columns_mode && (!cols.enabled || pts != 2 || cfg.threads * pts != CC_BRICK_X * CC_BRICK_Y * CC_BRICK_Z)) {
+        *err = "column kernels need a program with column-invariant micro-ops and 512 threads x 2 points";
+        return CC_ERR_INVALID_ARGUMENT;
+    }
+    if (parts_mode && !columns_mode && (!parts.enabled || pts != 2 || cfg.threads * pts != CC_BRICK_X * CC_BRICK_Y * CC_BRICK_Z)) {
         *err = "part culling needs a program with parts and 512 threads x 2 points";
         return CC_ERR_INVALID_ARGUMENT;
     }
     std::ostringstream hoisted;  // parts mode: value variables are declared ahead of the conditional blocks
+    std::ostringstream ahead, in_loop, full;  // columns mode: the three bodies
+    int full_open = -1, loop_open = -1;       // the part whose `if` is open in each body
+    uint32_t n_carried = 0;                   // values in the column buffer
+    std::vector<int> carried_interval, carried_l;  // interval / micro-op -> its place there, -1 = none
+    auto col_phase = [&](int op) { return columns_mode && (size_t)op < cols.phase.size() ? cols.phase[(size_t)op] : (uint8_t)3; };
 
     // ---- value intervals: one per slot definition, from the storing micro-op to its last reader.
     // Each interval becomes its own variable (the microcode is straight-line, so this is SSA).
@@ -256,6 +270,7 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
     struct Interval {
         int def, last_read, cell;
         bool z_only;  // every reader is an extrusion (needs the point's z only)
+        bool carried; // columns mode: defined ahead of the z loop only, read inside it (lives through the loop: a register)
     };
     std::vector<Interval> iv;
     std::vector<int> op_def, op_use;  // per micro-op: interval defined / interval read (-1 = none)
@@ -277,12 +292,13 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
                 }
                 iv[use].last_read = i;
                 if (op != MOP_EXTRUSION) iv[use].z_only = false;
+                if ((col_phase(i) & 2) && !(col_phase(iv[use].def) & 2)) iv[use].carried = true;
             }
             op_use.push_back(use);
             int def = -1;
             if (dst != CC_SLOT_NONE && op != MOP_RETURN) {
                 def = (int)iv.size();
-                iv.push_back(Interval{i, i, -1, true});
+                iv.push_back(Interval{i, i, -1, true, false});
                 cur[dst] = def;
             }
             op_def.push_back(def);
@@ -296,7 +312,7 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
         const int min_len = cfg.smem_min_len, max_cells = cfg.smem_max_cells;
         std::vector<int> order;
         for (int k = 0; k < (int)iv.size(); ++k)
-            if (max_cells > 0 && iv[k].last_read - iv[k].def >= min_len) order.push_back(k);
+            if (max_cells > 0 && iv[k].last_read - iv[k].def >= min_len && !iv[k].carried) order.push_back(k);
         std::sort(order.begin(), order.end(), [&](int a, int b) {
             return iv[a].last_read - iv[a].def > iv[b].last_read - iv[b].def;
         });
@@ -337,8 +353,8 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
     int seg_ops = cfg.segment_ops;
     if (seg_ops <= 0 || n_ops_total <= seg_ops + seg_ops / 2) seg_ops = n_ops_total + 1;
     const bool segmented = seg_ops <= n_ops_total;
-    if (segmented && parts_mode) {
-        *err = "part culling is not generated for segmented programs";
+    if (segmented && (parts_mode || columns_mode)) {
+        *err = "part culling and column kernels are not generated for segmented programs";
         return CC_ERR_INVALID_ARGUMENT;
     }
     auto seg_of = [&](int op) { return op / seg_ops; };
@@ -370,15 +386,17 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
             o.str(std::string());
         }
         const uint32_t h = c[pc], op = CC_HDR_OP(h), src_slot = CC_HDR_SRC(h), dst = CC_HDR_DST(h);
+        if (columns_mode) o.str(std::string());  // one micro-op at a time: its text goes to one body or both
         o << "        // pc " << pc << "\n";
         const int my_part = (parts_mode && op != MOP_RETURN && (size_t)op_index < parts.part_of_op.size()) ? parts.part_of_op[(size_t)op_index] : -1;
         const bool tree_union = parts_mode && op == MOP_UNION && (size_t)op_index < parts.union_a.size() &&
                                 parts.union_a[(size_t)op_index] != 0;
-        if (my_part >= 0 && (op_index == 0 || parts.part_of_op[(size_t)op_index - 1] != my_part))
+        if (!columns_mode && my_part >= 0 && (op_index == 0 || parts.part_of_op[(size_t)op_index - 1] != my_part))
             o << "        if (mask & " << (1u << my_part) << "u) {  // part " << my_part << "\n";
-        if (tree_union)
-            o << "        if ((mask & " << parts.union_a[(size_t)op_index] << "u) && (mask & " << parts.union_b[(size_t)op_index]
-              << "u)) {  // both operands keep a part; otherwise the survivor is already in L\n";
+        const std::string tree_union_open = !tree_union ? std::string() :
+            "        if ((mask & " + std::to_string(parts.union_a[(size_t)op_index]) + "u) && (mask & " +
+            std::to_string(parts.union_b[(size_t)op_index]) + "u)) {  // both operands keep a part; otherwise the survivor is already in L\n";
+        if (!columns_mode) o << tree_union_open;
         std::string B = "?";
         if (op_use[op_index] >= 0) {
             const int u = op_use[op_index];
@@ -392,6 +410,7 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
                   << iv[u].cell << ", g), " << B << (op == MOP_EXTRUSION ? ".z" : op == MOP_SYM_FROM ? ".x" : "") << ");\n";
             }
         }
+        if (columns_mode) o << tree_union_open;  // (after the operand fetch: the other branch needs it too)
         switch (op) {
         case MOP_RETURN: break;
         case MOP_NOP: break;
@@ -485,13 +504,17 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
         }
         if (op == MOP_RETURN) break;
         if (stop_after >= 0 && ++n_emitted > stop_after) break;
-        if (tree_union) o << "        }\n";
+        if (tree_union && columns_mode)
+            // the two operands may have run in different bodies (one ahead of the loop, one inside): L holds
+            // the running operand's value whenever that one keeps a part, never the slot operand's
+            o << "        } else if (!(mask & " << parts.union_b[(size_t)op_index] << "u)) {\n        CC_EACH L[g] = " << B << ";\n        }\n";
+        else if (tree_union) o << "        }\n";
         if (op_def[op_index] >= 0) {
             const int d = op_def[op_index];
             if (iv[d].last_read == iv[d].def) {
                 // never read: nothing to keep
             } else if (iv[d].cell < 0) {
-                if (parts_mode) {
+                if (parts_mode || columns_mode) {
                     hoisted << "        Val I" << d << "[G];\n";
                     o << "        CC_EACH I" << d << "[g] = L[g];\n";
                 } else {
@@ -504,8 +527,54 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
                 o << "        CC_EACH cc_slot_store(CC_CELL(" << iv[d].cell << ", g), L[g]);\n";
             }
         }
-        if (my_part >= 0 && ((size_t)op_index + 1 >= parts.part_of_op.size() || parts.part_of_op[(size_t)op_index + 1] != my_part))
+        if (!columns_mode && my_part >= 0 &&
+            ((size_t)op_index + 1 >= parts.part_of_op.size() || parts.part_of_op[(size_t)op_index + 1] != my_part))
             o << "          if (pw) pw[" << my_part << "] = L[0].w;  // the part's value (brick centres)\n        }\n";
+        if (columns_mode) {
+            // every micro-op in its own block, under its part's bit (warp-uniform; neighbours with the same
+            // condition fuse); what the loop reads from the column pass travels through the column buffer
+            // (one `if` per run of micro-ops with the same condition; -2 = nothing open, -1 = unconditional)
+            auto put = [&](std::ostringstream &os, int &open, int part, const std::string &t) {
+                if (open != part) {
+                    if (open >= 0) os << "        }\n";
+                    if (part >= 0) os << "        if (mask & " << (1u << part) << "u) {\n";
+                    open = part;
+                }
+                os << "        {\n" << t << "        }\n";
+            };
+            const uint8_t ph = col_phase(op_index);
+            const std::string text = o.str();
+            put(full, full_open, my_part, text);
+            if (my_part >= 0 && ((size_t)op_index + 1 >= parts.part_of_op.size() || parts.part_of_op[(size_t)op_index + 1] != my_part))
+                put(full, full_open, my_part, "        if (pw) pw[" + std::to_string(my_part) + "] = L[0].w;  // the part's value (brick centres)\n");
+            if (carried_l.empty()) { carried_l.assign(cols.phase.size(), -1); carried_interval.assign(iv.size(), -1); }
+            if (ph & 1) {
+                ahead << "        {\n" << text;
+                if (cols.save_l[(size_t)op_index]) {
+                    carried_l[(size_t)op_index] = (int)n_carried;
+                    ahead << "        CC_EACH cc_col_store(cr, " << n_carried++ << "u, L[g]);\n";
+                }
+                const int d = op_def[op_index];
+                if (d >= 0 && iv[d].carried && !(ph & 2)) {
+                    carried_interval[(size_t)d] = (int)n_carried;
+                    ahead << "        CC_EACH cc_col_store(cr, " << n_carried++ << "u, L[g]);\n";
+                }
+                ahead << "        }\n";
+            }
+            if (ph & 2) {
+                const int from = cols.restore_from[(size_t)op_index];
+                if (from >= 0) {
+                    const int from_part = (size_t)from < parts.part_of_op.size() && parts_mode ? parts.part_of_op[(size_t)from] : -1;
+                    put(in_loop, loop_open, from_part, "        CC_EACH L[g] = cc_col_load<V>(cr, " + std::to_string(carried_l[(size_t)from]) + "u);\n");
+                }
+                std::string fetch;
+                const int u = op_use[op_index];
+                if (u >= 0 && iv[u].carried)  // (shadows the register of the same name: this body never defines it)
+                    fetch = "        Val I" + std::to_string(u) + "[G]; CC_EACH I" + std::to_string(u) + "[g] = cc_col_load<V>(cr, " +
+                            std::to_string(carried_interval[(size_t)u]) + "u);\n";
+                put(in_loop, loop_open, my_part, fetch + text);
+            }
+        }
         pc += CC_HDR_LEN(h);
     }
 
@@ -513,6 +582,7 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
     s << "// generated by libcodecad_b200 (cc_jit.cpp) from " << dec.info.n_micro_ops << " micro-ops\n"
       << "#define CC_THREADS " << cfg.threads << "\n"
       << (no_pack ? "#define CC_OPT_PACKED 0\n" : "") << extra_defines()
+      << (columns_mode ? "#define CC_COL_VALUES " + std::to_string(std::max(1u, n_carried)) + "\n" : std::string())
       << "#include \"cc_ops.cuh\"\n#include \"cc_body.cuh\"\n#include \"cc_render.cuh\"\n"
       << "#define PTS " << pts << "\n"
       << "typedef cc_pts<PTS>::V V;\nconstexpr int G = cc_pts<PTS>::G;\ntypedef cc_val<V> Val;\n"
@@ -521,7 +591,50 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
       << "#define CC_JIT_SMEM_BYTES " << (size_t)n_cells * pts * cfg.threads * 16 << "\n"
       << g.consts.str();
     if (g.n_params) s << "__constant__ float cc_par[" << g.n_params << "] = {" << g.params.str() << "};\n";
-    if (!segmented) {
+    if (columns_mode) {
+        // rows of initial transforms whose z coefficient is rounding residue: equal bits at both ends of the column
+        // prove the row constant along it (monotone in z); otherwise the column is evaluated cell by cell in full
+        std::ostringstream chk;
+        {
+            std::vector<uint32_t> pcs;  // micro-op index -> pc
+            for (uint32_t q = 0; q < c.size() && CC_HDR_OP(c[q]) != MOP_RETURN; q += CC_HDR_LEN(c[q])) pcs.push_back(q);
+            for (uint32_t cr : cols.checked_rows) {
+                const uint32_t opi = cr / 4, r = cr % 4;
+                if (opi >= pcs.size() || !(col_phase((int)opi) & 1)) continue;
+                const int part = parts_mode && opi < parts.part_of_op.size() ? parts.part_of_op[opi] : -1;
+                const uint32_t m = pcs[opi] + 1;
+                chk << "        " << (part >= 0 ? "if (mask & " + std::to_string(1u << part) + "u) " : std::string())
+                    << "CC_EACH ok = ok && cc_same_bits(" << g.row_to(m + 3 * r, m + 9 + r, "gx[g]", "gy[g]", "gz[g]") << ", "
+                    << g.row_to(m + 3 * r, m + 9 + r, "gx[g]", "gy[g]", "gz_last[g]") << ");\n";
+            }
+        }
+        if (full_open >= 0) full << "        }\n";
+        if (loop_open >= 0) in_loop << "        }\n";
+        const std::string zero_l = "        CC_EACH L[g] = Val{vbc<V>(0.f), vbc<V>(0.f), vbc<V>(0.f), vbc<V>(0.f)};\n";
+        const std::string sig = "(const V (&gx)[G], const V (&gy)[G], const V (&gz)[G]";
+        s << "// the full walk: brick centres, bricks with a column that failed the check\n"
+          << "struct SceneFull {\n    float4 *sm;\n    unsigned mask;\n    V *pw;\n"
+          << "    __device__ __forceinline__ void operator()" << sig << ", Val (&L)[G]) const\n    {\n" << hoisted.str() << zero_l
+          << full.str() << "    }\n};\n"
+          << "// once per (x, y) column: what cannot see the grid's z; every part (a column crosses many bricks)\n"
+          << "struct SceneAhead {\n    float4 *sm;\n    cc_col_ref cr;\n    static constexpr unsigned mask = 0xffffffffu;\n"
+          << "    // may one evaluation stand for the whole column gz .. gz_last?\n"
+          << "    __device__ __forceinline__ bool invariant" << sig << ", const V (&gz_last)[G]) const\n    {\n"
+          << "        bool ok = true;\n" << chk.str() << "        return ok;\n    }\n"
+          << "    __device__ __forceinline__ void operator()" << sig << ") const\n    {\n" << hoisted.str() << "        Val L[G];\n" << zero_l
+          << ahead.str() << "    }\n};\n"
+          << "// per cell: the rest, reading the column's values\n"
+          << "struct SceneEval {\n    float4 *sm;\n    unsigned mask;\n    cc_col_ref cr;\n"
+          << "    __device__ __forceinline__ void operator()" << sig << ", Val (&L)[G]) const\n    {\n" << hoisted.str() << zero_l
+          << in_loop.str();
+        if (cols.root_restore >= 0) s << "        CC_EACH L[g] = cc_col_load<V>(cr, " << carried_l[(size_t)cols.root_restore] << "u);\n";
+        s << "    }\n};\n";
+        if (columns_meta) {
+            columns_meta->n_values = n_carried;
+            columns_meta->checks = !chk.str().empty();
+            columns_meta->centers = parts_mode;
+        }
+    } else if (!segmented) {
         s << "struct SceneEval {\n    float4 *sm;  // this thread's column of the value cells\n";
         if (parts_mode) s << "    unsigned mask;  // bit k: part k can matter in this brick\n    V *pw;  // brick-centre pass: receives every part's value\n";
         s << "    __device__ __forceinline__ void operator()(const V (&gx)[G], const V (&gy)[G], const V (&gz)[G],\n"
@@ -562,7 +675,33 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
         s << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_" << names[k]
           << "(const cc_eval_args a)\n{\n    extern __shared__ float4 cc_cells[];\n    SceneEval e{cc_cells + threadIdx.x};\n"
           << "    cc_kernel_body<PTS, " << sinks[k] << ">(a, e);\n}\n";
-    if (parts_mode) {
+    if (columns_mode) {
+        const std::string head = "(const cc_eval_args a)\n{\n    extern __shared__ float4 cc_cells[];\n";
+        s << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_columns_profiles" << head
+          << "    SceneAhead e;\n    e.sm = cc_cells + threadIdx.x;\n"
+          << "    cc_column_profiles_body<PTS>(a, e);\n}\n"
+          << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_columns" << head
+          << "    SceneEval e;\n    e.sm = cc_cells + threadIdx.x;\n    e.mask = a.part_masks ? a.part_masks[blockIdx.x] : 0xffffffffu;\n"
+          << "    cc_kernel_body_brick_columns<PTS>(a, e);\n}\n"
+          << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_columns_full" << head
+          << "    const unsigned n = *a.brick_count;\n    for (unsigned i = blockIdx.x; i < n; i += gridDim.x) {\n"
+          << "        const unsigned b = a.brick_list[i];\n"
+          << "        SceneFull e{cc_cells + threadIdx.x, a.part_masks ? a.part_masks[b] : 0xffffffffu, nullptr};\n"
+          << "        cc_kernel_body_bricks_at<PTS>(a, e, b);\n    }\n}\n";
+        if (parts_mode) {
+            s << "__constant__ float cc_part_lipschitz[" << parts.n_parts << "] = {";
+            for (uint32_t k = 0; k < parts.n_parts; ++k) {
+                const float l = parts.lipschitz[k];
+                s << (k ? ", " : "");
+                if (l - l != 0.0f || l > 1e30f) s << "1e30f";
+                else { char buf[48]; std::snprintf(buf, sizeof buf, "%af", (double)l); s << buf; }
+            }
+            s << "};\nextern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_columns_centers" << head
+              << "    V pw[" << parts.n_parts << "];\n    SceneFull e{cc_cells + threadIdx.x, 0xffffffffu, pw};\n"
+              << "    cc_part_centers_body<" << parts.n_parts << ">(a, e, pw, cc_part_lipschitz);\n}\n";
+        }
+    }
+    if (parts_mode && !columns_mode) {
         // main kernel: one 8 x 8 x 16 brick per CTA, its mask decides which parts run; centre pass: a
         // thread evaluates the centres of two bricks (one packed pair), derives the bricks' masks from
         // the parts' values there and their Lipschitz constants, and writes them for the main kernel
@@ -895,7 +1034,7 @@ static int load_cubin(cc_program *prog, int sink, const Cubin &bin, const cc_jit
                       std::string *err)
 {
     static const char *names[CC_N_SINKS] = {"cc_jit_float4", "cc_jit_pymcubes", "cc_jit_classify", "cc_jit_mass",
-                                            "cc_jit_ray_caster", "cc_jit_bitmap", "cc_jit_points", "cc_jit_parts"};
+                                            "cc_jit_ray_caster", "cc_jit_bitmap", "cc_jit_points", "cc_jit_parts", "cc_jit_columns"};
     // A cubin is loaded once per process: programs with the same specialised source (the same scene
     // uploaded again) share the loaded library.  Loading costs milliseconds per megabyte of code.
     cudaLibrary_t lib = nullptr;
@@ -934,6 +1073,27 @@ static int load_cubin(cc_program *prog, int sink, const Cubin &bin, const cc_jit
             return CC_ERR_CUDA;
         }
         prog->jit_kernel_centers = (void *)centers;
+    }
+    if (sink == CC_SINK_COLUMNS) {
+        // what the kernels need from the host: the generator's own bookkeeping (a second, source-only pass)
+        std::string src;
+        size_t sm = 0;
+        cc_columns_meta meta;
+        if (generate(prog->dec, cfg, 1u << sink, &src, &sm, err, &meta) != CC_OK) {
+            release_library(lib);
+            return CC_ERR_CUDA;
+        }
+        const char *extra[3] = {meta.centers ? "cc_jit_columns_centers" : nullptr, "cc_jit_columns_profiles", "cc_jit_columns_full"};
+        for (int k = 0; k < 3; ++k) {
+            cudaKernel_t kk = nullptr;
+            if (extra[k] && (ce = cudaLibraryGetKernel(&kk, lib, extra[k])) != cudaSuccess) {
+                *err = std::string("cudaLibraryGetKernel(") + extra[k] + "): " + cudaGetErrorString(ce);
+                release_library(lib);
+                return CC_ERR_CUDA;
+            }
+            prog->jit_columns_kernels[k] = (void *)kk;
+        }
+        prog->jit_columns = meta;
     }
     if (prog->jit_library[sink]) release_library((cudaLibrary_t)prog->jit_library[sink]);
     prog->jit_smem[sink] = smem_bytes;
@@ -1072,7 +1232,7 @@ int cc_jit_launch(const cc_program *prog, int sink, const cc_eval_args &a, void 
                                  args, prog->jit_smem[sink], (cudaStream_t)stream);
 }
 
-int cc_jit_launch_parts(const cc_program *prog, const cc_eval_args &a, uint32_t n_bricks, void *stream, int dev_index)
+int cc_jit_launch_parts(const cc_program *prog, const cc_eval_args &a, uint32_t n_bricks, void *stream, int dev_index, bool centers_only)
 {
     if (n_bricks == 0) return 0;
     const int sink = CC_SINK_PARTS;
@@ -1086,9 +1246,48 @@ int cc_jit_launch_parts(const cc_program *prog, const cc_eval_args &a, uint32_t 
     void *args[] = {(void *)&a};
     cudaError_t ce = cudaLaunchKernel((const void *)prog->jit_kernel_centers, dim3((n_bricks + 2 * threads - 1) / (2 * threads)),
                                       dim3(threads), args, smem, (cudaStream_t)stream);
-    if (ce != cudaSuccess) return (int)ce;
+    if (ce != cudaSuccess || centers_only) return (int)ce;
     return (int)cudaLaunchKernel((const void *)prog->jit_kernel[sink], dim3(n_bricks), dim3(threads), args, smem,
                                  (cudaStream_t)stream);
+}
+
+// CC_SINK_COLUMNS: [brick centres ->] column pass -> brick kernel [-> full walk of the flagged bricks]; the caller
+// prepared a.columns (and a.part_masks / a.column_flags + a.brick_list + a.brick_count as the program needs)
+int cc_jit_launch_columns(const cc_program *prog, const cc_eval_args &a, uint32_t n_bricks, int sm_count, void *stream, int dev_index,
+                          int *n_launches)
+{
+    if (n_bricks == 0) return 0;
+    const int sink = CC_SINK_COLUMNS;
+    const size_t smem = prog->jit_smem[sink];
+    if (int e = ensure_smem_attr(prog, sink, dev_index)) return e;
+    if (smem)
+        for (void *k : prog->jit_columns_kernels)
+            if (k) {
+                cudaError_t ce = cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (ce != cudaSuccess) return (int)ce;
+            }
+    const uint32_t threads = (uint32_t)prog->jit_cfg[sink].threads;
+    cudaStream_t st = (cudaStream_t)stream;
+    void *args[] = {(void *)&a};
+    cudaError_t ce = cudaSuccess;
+    *n_launches = 0;
+    if (a.part_masks) {
+        ce = cudaLaunchKernel((const void *)prog->jit_columns_kernels[0], dim3((n_bricks + 2 * threads - 1) / (2 * threads)), dim3(threads), args, smem, st);
+        if (ce != cudaSuccess) return (int)ce;
+        ++*n_launches;
+    }
+    const uint32_t ncol = a.nx * a.ny;
+    ce = cudaLaunchKernel((const void *)prog->jit_columns_kernels[1], dim3((ncol + 2 * threads - 1) / (2 * threads)), dim3(threads), args, smem, st);
+    if (ce != cudaSuccess) return (int)ce;
+    ce = cudaLaunchKernel((const void *)prog->jit_kernel[sink], dim3(n_bricks), dim3(threads), args, smem, st);
+    if (ce != cudaSuccess) return (int)ce;
+    *n_launches += 2;
+    if (a.column_flags) {
+        ce = cudaLaunchKernel((const void *)prog->jit_columns_kernels[2], dim3((unsigned)std::max(1, 2 * sm_count)), dim3(threads), args, smem, st);
+        if (ce != cudaSuccess) return (int)ce;
+        ++*n_launches;
+    }
+    return 0;
 }
 
 int cc_jit_source(const cc_decoded &dec, int pts, unsigned sink_mask, std::string *src, std::string *err)

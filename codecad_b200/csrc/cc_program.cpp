@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -336,6 +337,139 @@ bool sigma_max(const float *m, double *out)
         }
     *out = std::sqrt(s2) * std::sqrt(1 + std::sqrt(ef)) * (1 + 1e-6);
     return std::isfinite(*out);
+}
+
+// ---- columns: which micro-ops can see the grid's z (cc_internal.h cc_columns) ---------------------
+// Forward data flow over the straight-line microcode with one bit per component (x, y, z, w) of the
+// running value and of every slot: "may differ between two cells of one z-column".  The rules below
+// follow the op library (cc_ops.cuh) and cc-arith's matrix form, where a zero coefficient is not a
+// multiplication by zero but an omitted term — the remaining terms never see that operand:
+//   transforms          row r depends on what its non-zero coefficients read
+//   2-D primitives      read x, y; write (nx, ny, 0, d)
+//   mirror/offset/nop   component-wise
+//   everything else     any dependent input makes every output component dependent
+void analyse_columns(const std::vector<uint32_t> &code, cc_columns *out)
+{
+    *out = cc_columns();
+    enum { X = 1, Y = 2, Z = 4, W = 8, ALL = 15 };
+    struct Op { uint32_t pc, op; int in_l, in_s; uint8_t dep; uint32_t cost; };
+    std::vector<Op> ops;
+    std::vector<int> slot_prod(CC_SLOT_NONE + 1, -1);
+    int L = -1, root = -1;
+    auto fl = [&](uint32_t pc, int k) { float f; std::memcpy(&f, &code[pc + 1 + (uint32_t)k], 4); return f; };
+    for (uint32_t pc = 0;;) {
+        if (pc >= code.size()) return;
+        const uint32_t hd = code[pc], op = CC_HDR_OP(hd), src = CC_HDR_SRC(hd), dst = CC_HDR_DST(hd);
+        if (op == MOP_RETURN) { root = L; break; }
+        Op o{pc, op, -1, -1, 0, 4};
+        const bool from_point = op == MOP_T_INIT || op == MOP_T_INIT_M || op == MOP_PRIM_CIRCLE || op == MOP_PRIM_RECT ||
+                                op == MOP_PRIM_CIRCLE_M || op == MOP_PRIM_RECT_M;
+        if (!from_point && op != MOP_LOAD) {
+            if (L < 0) return;
+            o.in_l = L;
+        }
+        if (src != CC_SLOT_NONE) {
+            if (slot_prod[src] < 0) return;
+            o.in_s = slot_prod[src];
+        }
+        const uint8_t dl = o.in_l >= 0 ? ops[(size_t)o.in_l].dep : 0, ds = o.in_s >= 0 ? ops[(size_t)o.in_s].dep : 0;
+        auto rows = [&](uint8_t in, bool carries_w) {  // a 3 x 3 matrix at words 1..9 applied to (x, y, z)
+            uint8_t d = 0;
+            for (int r = 0; r < 3; ++r)
+                for (int k = 0; k < 3; ++k)
+                    if (fl(pc, 3 * r + k) != 0.0f && (in & (1 << k))) d |= (uint8_t)(1 << r);
+            if (carries_w && (in & W)) d |= W;
+            return d;
+        };
+        switch (op) {
+        case MOP_T_INIT: case MOP_T_INIT_M: {  // the grid point: only its z varies
+            // A coefficient of z that is rounding residue (a half turn written as a quaternion leaves
+            // cos(pi/2) = 6e-17 behind) is not omitted by cc-arith, so the row does see z — in the last bits of
+            // a value near zero, if at all.  Such rows count as invariant here and are CHECKED per column at run
+            // time: each row is a monotone function of z (a chain of correctly rounded FMAs), so equal bits at
+            // both ends of the column mean equal bits at every cell between them (cc_jit.cpp `invariant`).
+            uint8_t d = 0;
+            for (int r = 0; r < 3; ++r) {
+                const float big = std::max(std::fabs(fl(pc, 3 * r)), std::fabs(fl(pc, 3 * r + 1)));
+                const float mz = std::fabs(fl(pc, 3 * r + 2));
+                if (mz != 0.0f && !(mz <= big * 9.313225746154785e-10f)) d |= (uint8_t)(1 << r);  // 2^-30
+                else if (mz != 0.0f) out->checked_rows.push_back((uint32_t)ops.size() * 4u + (uint32_t)r);
+            }
+            o.dep = d;
+            o.cost = 18;
+            break;
+        }
+        case MOP_T_TO: case MOP_T_TO_M: o.dep = rows(dl, false); o.cost = 18; break;
+        case MOP_T_FROM: case MOP_T_FROM_M: o.dep = rows(dl, true); o.cost = 18; break;
+        case MOP_MIRROR: case MOP_SYM_TO: case MOP_OFFSET: case MOP_NOP: o.dep = dl; o.cost = 1; break;
+        case MOP_LOAD: o.dep = ds; o.cost = 0; break;
+        case MOP_CIRCLE: o.dep = (dl & (X | Y)) ? (X | Y | W) : 0; o.cost = 10; break;
+        case MOP_RECTANGLE: o.dep = (dl & (X | Y)) ? (X | Y | W) : 0; o.cost = 17; break;
+        case MOP_REGPOLY: o.dep = (dl & (X | Y)) ? (X | Y | W) : 0; o.cost = 120; break;
+        case MOP_GEAR: o.dep = (dl & (X | Y)) ? (X | Y | W) : 0; o.cost = 200; break;
+        case MOP_POLYGON: o.dep = (dl & (X | Y)) ? (X | Y | W) : 0; o.cost = 12u * (uint32_t)fl(pc, 0) + 30u; break;
+        case MOP_SYM_FROM: o.dep = (uint8_t)(dl | ((ds & X) ? X : 0)); o.cost = 2; break;
+        case MOP_PRIM_CIRCLE: case MOP_PRIM_RECT: case MOP_PRIM_CIRCLE_M: case MOP_PRIM_RECT_M: o.dep = ALL; o.cost = 100; break;
+        default:
+            o.dep = (dl | ds) ? ALL : 0;
+            o.cost = (op == MOP_UNION || op == MOP_ISECT || op == MOP_SUB) ? 5 : 30;
+            break;
+        }
+        ops.push_back(o);
+        L = (int)ops.size() - 1;
+        if (dst != CC_SLOT_NONE) slot_prod[dst] = L;
+        pc += CC_HDR_LEN(hd);
+    }
+    const int n = (int)ops.size();
+    if (root < 0 || n < 3) return;
+    // what the loop needs (dependent ops, from the result backwards) and what must run ahead of it
+    // (invariant ops that feed the loop, and whatever feeds those — possibly dependent ops again, whose
+    // invariant components are what is read)
+    std::vector<char> in_loop((size_t)n, 0), ahead((size_t)n, 0);
+    std::vector<int> todo;
+    auto want = [&](int v) {
+        if (v < 0) return;
+        std::vector<char> &set = ops[(size_t)v].dep ? in_loop : ahead;
+        if (!set[(size_t)v]) { set[(size_t)v] = 1; todo.push_back(v); }
+    };
+    want(root);
+    while (!todo.empty()) {
+        const int v = todo.back();
+        todo.pop_back();
+        if (ops[(size_t)v].dep && in_loop[(size_t)v]) { want(ops[(size_t)v].in_l); want(ops[(size_t)v].in_s); }
+    }
+    for (int v = n - 1; v >= 0; --v) {  // inputs precede their readers: one backward sweep closes `ahead`
+        if (!ahead[(size_t)v]) continue;
+        for (int p : {ops[(size_t)v].in_l, ops[(size_t)v].in_s})
+            if (p >= 0) ahead[(size_t)p] = 1;
+    }
+    out->phase.assign((size_t)n, 0);
+    out->restore_from.assign((size_t)n, -1);
+    out->save_l.assign((size_t)n, 0);
+    uint64_t total = 0, hoisted = 0, repeated = 0;
+    for (int v = 0; v < n; ++v) {
+        out->phase[(size_t)v] = (uint8_t)((ahead[(size_t)v] ? 1 : 0) | (in_loop[(size_t)v] ? 2 : 0));
+        if (ahead[(size_t)v] || in_loop[(size_t)v]) total += ops[(size_t)v].cost;
+        if (ahead[(size_t)v] && !in_loop[(size_t)v]) hoisted += ops[(size_t)v].cost;
+        if (ahead[(size_t)v] && in_loop[(size_t)v]) repeated += ops[(size_t)v].cost;
+        const int p = ops[(size_t)v].in_l;
+        if (in_loop[(size_t)v] && p >= 0 && !in_loop[(size_t)p]) {
+            out->restore_from[(size_t)v] = p;
+            out->save_l[(size_t)p] = 1;
+        }
+    }
+    if (!in_loop[(size_t)root]) {
+        out->root_restore = root;
+        out->save_l[(size_t)root] = 1;
+    }
+    if (getenv("CODECAD_B200_COLUMNS_DEBUG"))
+        for (int v = 0; v < n; ++v)
+            std::fprintf(stderr, "op %3d  mop %2u  in_l %3d in_s %3d  dep %x  phase %u  save %u restore %d cost %u\n", v, ops[(size_t)v].op,
+                         ops[(size_t)v].in_l, ops[(size_t)v].in_s, ops[(size_t)v].dep, out->phase[(size_t)v], out->save_l[(size_t)v],
+                         out->restore_from[(size_t)v], ops[(size_t)v].cost);
+    (void)repeated;
+    out->invariant_share = total ? (float)((double)hoisted / (double)total) : 0.0f;
+    out->enabled = out->invariant_share >= 0.25f;
 }
 
 void analyse_parts(const std::vector<uint32_t> &code, cc_parts *out)
@@ -942,6 +1076,7 @@ int cc_decode_program(const float *words, uint32_t n_words, cc_decoded *out, std
     out->microcode.swap(e.code);
     analyse_forest(out->microcode, &out->forest);
     analyse_parts(out->microcode, &out->parts);
+    analyse_columns(out->microcode, &out->columns);
     out->info.n_words = pc;
     out->info.n_instructions = (uint32_t)ins.size();
     out->info.n_micro_ops = n_micro;
@@ -957,5 +1092,6 @@ int cc_decode_program(const float *words, uint32_t n_words, cc_decoded *out, std
     out->info.n_parts_bounded = 0;
     if (out->parts.enabled)
         for (float l : out->parts.lipschitz) out->info.n_parts_bounded += std::isfinite(l) ? 1u : 0u;
+    out->info.column_invariant_percent = out->columns.enabled ? (uint32_t)(out->columns.invariant_share * 100.0f) : 0u;
     return CC_OK;
 }

@@ -95,6 +95,9 @@ typedef struct cc_program_info {
     uint32_t forest_depth;    /* its evaluation stack depth                                    */
     uint32_t n_parts;         /* parts of an assembly (cc_set_parts_mode), 0 = none            */
     uint32_t n_parts_bounded; /* of them: with a Lipschitz bound, i.e. cullable                */
+    uint32_t column_invariant_percent; /* estimated share of the arithmetic that does not depend on the grid's z
+                                          (2-D profiles under extrusions); evaluated once per z-column of a dense
+                                          grid when >= 25 (cc_set_columns_mode), 0 = nothing to gain          */
 } cc_program_info;
 int cc_program_get_info(const cc_program *prog, cc_program_info *out);
 /* copies the decoded microcode (for tests / disassembly); returns the microcode length */
@@ -142,6 +145,14 @@ int cc_set_forest_mode(int mode);
  * cannot be the nearest there (Lipschitz bound of every part from the brick centre; csrc/cc_body.cuh).
  * Bit-identical to the full evaluation.  mode 1 = on (default; CODECAD_B200_PARTS), 0 = off. */
 int cc_set_parts_mode(int mode);
+/* Columns.  On a dense grid the grid's z axis is the z axis of the program's point, and a 2-D profile
+ * under an extrusion (transform, polygon2d, involute gear, their CSG: shapes/simple2d.cl, polygons2d.cl,
+ * gears.cl before simple3d.cl extrusion) reads x and y only: its value is the same in every cell of a
+ * z-column.  The loader proves, micro-op by micro-op and component by component, what cannot depend on
+ * the grid's z (cc_program_info.column_invariant_percent); the column kernel evaluates that once per
+ * column and only the rest per cell.  Same arithmetic on the same operands: bit-identical.  Combines with
+ * the parts' masks.  mode 1 = on (default; CODECAD_B200_COLUMNS), 0 = off.  Returns the old mode. */
+int cc_set_columns_mode(int mode);
 int cc_program_get_forest_info(const cc_program *prog, uint32_t out[4]);
 /* Blocks until the specialised kernels of the sinks in `sink_mask` (0 = all) are compiled and
  * loaded, starting their compilation if necessary; returns how many are ready.  compile_seconds

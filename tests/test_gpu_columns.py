@@ -1,0 +1,119 @@
+"""Columns: dense float4 grids evaluate the micro-ops that cannot see the grid's z — the
+2-D profile under an extrusion — once per z-column.  Must not change a bit: against the CPU oracle on
+windows of several scales, against the same library with the column kernel switched off on larger grids,
+and on grids with cell centres exactly on the coordinate planes, where a transform whose z coefficient is
+rounding residue does depend on z and the per-column check has to send the column down the full path."""
+import numpy as np
+import pytest
+
+import oracle
+from scenes import ALL_NAMES
+
+pytestmark = pytest.mark.gpu
+COLUMN_SCENES = ["cfg_planetary", "x_gear3d", "dsdf2d_gear", "dsdf2d_mirror_2d", "dsdf2d_rotated_pattern_2d", "dsdf2d_bin_counter_11"]
+
+
+@pytest.fixture(scope="module")
+def cb():
+    import codecad_b200
+    from codecad_b200 import _lib
+    _lib.init(0)
+    L = _lib.lib()
+    old_jit = _lib.check(L.cc_set_jit_mode(2))     # compile at first use and wait: the column kernel is an NVRTC kernel
+    yield codecad_b200
+    _lib.check(L.cc_set_columns_mode(1))
+    _lib.check(L.cc_set_jit_mode(old_jit))
+
+
+def _f4(arr):
+    return np.stack([arr["x"], arr["y"], arr["z"], arr["w"]], axis=-1)
+
+
+def _box(s):
+    a, b = np.array(s.box_a, dtype=np.float64), np.array(s.box_b, dtype=np.float64)
+    if s.dimension == 2:
+        a[2], b[2] = -1.0, 1.0
+    return a, b
+
+
+def test_which_scenes_have_columns(scenes):
+    from codecad_b200 import _lib
+    have = sorted(n for n in ALL_NAMES if _lib.decode_program(scenes[n].words)[0].column_invariant_percent)
+    assert set(COLUMN_SCENES) <= set(have)
+    assert _lib.decode_program(scenes["cfg_planetary"].words)[0].column_invariant_percent >= 40
+    assert _lib.decode_program(scenes["cfg_csg_example"].words)[0].column_invariant_percent == 0
+
+
+@pytest.mark.parametrize("name", COLUMN_SCENES)
+def test_columns_bit_exact_vs_oracle(cb, scenes, name):
+    from codecad_b200 import _lib
+    _lib.check(_lib.lib().cc_set_columns_mode(1))
+    s = scenes[name]
+    scene = s.compiled()
+    rng = np.random.default_rng(11)
+    a, b = _box(s)
+    size = float(max(b - a))
+    corner, step = s.grid(48)
+    windows = [(corner, step, (48, 40, 33))]
+    for frac, dims in ((0.3, (40, 33, 48)), (0.05, (33, 48, 40)), (0.01, (24, 40, 64))):
+        for _ in range(2):
+            centre = a + (b - a) * rng.uniform(0.2, 0.8, 3)
+            st = np.float32(size * frac / 32)
+            windows.append(((centre - st * np.array(dims) / 2).astype(np.float32), st, dims))
+    # cell centres exactly on x = 0, y = 0 and z = 0 (a power-of-two step, the corner a multiple of it)
+    st = np.float32(2.0 ** np.floor(np.log2(size / 40)))
+    windows.append((np.array([-20 * st, -16 * st, -24 * st], np.float32), st, (40, 32, 48)))
+    launches0 = _lib.counters()[0]
+    for corner, step, dims in windows:
+        want = oracle.grid_eval(s.words, corner, step, dims)
+        got = _f4(cb.grid_eval(scene, corner, step, dims))
+        assert np.array_equal(got, want, equal_nan=True), "%s step %g: %d values differ" % (name, step, int((got != want).sum()))
+    assert _lib.counters()[0] - launches0 >= len(windows)
+
+
+@pytest.mark.parametrize("name", COLUMN_SCENES)
+def test_columns_equal_the_other_kernels(cb, scenes, name):
+    from codecad_b200 import _lib
+    L = _lib.lib()
+    s = scenes[name]
+    scene = s.compiled()
+    rng = np.random.default_rng(23)
+    a, b = _box(s)
+    size = float(max(b - a))
+    cases = [(1.05, (128, 128, 128), 0, None), (0.3, (130, 70, 90), 5, None), (0.04, (64, 136, 100), 0, None)]
+    st0 = np.float32(2.0 ** np.floor(np.log2(size / 120)))
+    cases.append((None, (128, 120, 136), 0, (np.array([-64 * st0, -60 * st0, -68 * st0], np.float32), st0)))   # on the coordinate planes
+    for frac, dims, x_offset, fixed in cases:
+        if fixed is None:
+            centre = a + (b - a) * rng.uniform(0.3, 0.7, 3)
+            st = np.float32(size * frac / max(dims))
+            corner = (centre - st * np.array(dims) / 2).astype(np.float32)
+        else:
+            corner, st = fixed
+        _lib.check(L.cc_set_columns_mode(1))
+        got = np.array(cb.grid_eval(scene, corner, st, dims, x_offset=x_offset))
+        _lib.check(L.cc_set_columns_mode(0))
+        want = np.array(cb.grid_eval(scene, corner, st, dims, x_offset=x_offset))
+        _lib.check(L.cc_set_columns_mode(1))
+        assert got.tobytes() == want.tobytes(), "%s %s" % (name, frac)
+
+
+def test_columns_serve_the_launch(cb, scenes):
+    """The column kernels are what runs: the column pass and the brick kernel, the brick centres ahead of them for
+    an assembly, the full walk of flagged bricks behind them when a transform row needs the per-column check."""
+    from codecad_b200 import _lib
+    L = _lib.lib()
+    for name, n_launches in (("cfg_planetary", (3, 4)), ("x_gear3d", (2, 3))):
+        s = scenes[name]
+        prog = s.compiled()
+        corner, step = s.grid(64)
+        cb.grid_eval(prog, corner, step, (64, 64, 64))
+        assert _lib.decode_program(s.words)[0].column_invariant_percent > 0
+        n0 = _lib.counters()[0]
+        cb.grid_eval(prog, corner, step, (64, 64, 64))
+        assert _lib.counters()[0] - n0 in n_launches
+        _lib.check(L.cc_set_columns_mode(0))
+        n0 = _lib.counters()[0]
+        cb.grid_eval(prog, corner, step, (64, 64, 64))
+        assert _lib.counters()[0] - n0 < n_launches[0]
+        _lib.check(L.cc_set_columns_mode(1))
