@@ -446,6 +446,10 @@ def config_grid_leg(name, label, n, slab_planes, rank, world, torch, dist, info,
     ms = max_over_ranks(torch, dist, _timed_events(L, _lib, step_fn, steps)) / steps
     barrier(torch, dist)
     tier = "forest (per-tile exact culling, csrc/cc_forest.cu)" if forest else ("specialised" if n_ready else "interpreter")
+    if (n_ready and not forest and int(pinfo.column_invariant_percent) > 0 and os.environ.get("CODECAD_B200_COLUMNS", "1") != "0"
+            and (nx if int(pinfo.column_axis) == 0 else n) >= 8):
+        tier = ("specialised, column kernels (%d %% of the arithmetic once per %s-column, csrc/cc_body.cuh)"
+                % (int(pinfo.column_invariant_percent), "xyz"[int(pinfo.column_axis)]))
     prog.release()
     pts_rank = float(nx) * n * n
     pts_all = pts_rank * world
@@ -721,7 +725,10 @@ def run_ours(args):
     tier = "specialised" if n_ready else "interpreter"
     # assemblies: the specialised kernels of dense grids skip, per brick, the parts that cannot be nearest
     parts_active = bool(n_ready) and int(pinfo.n_parts_bounded) > 0 and os.environ.get("CODECAD_B200_PARTS", "1") != "0"
-    kernel_key = "parts" if parts_active else tier
+    # extrusions: what cannot see the grid coordinate along the extrusion axis is evaluated once per column
+    columns_active = (bool(n_ready) and int(pinfo.column_invariant_percent) > 0 and os.environ.get("CODECAD_B200_COLUMNS", "1") != "0"
+                      and (nx if int(pinfo.column_axis) == 0 else n) >= 8)
+    kernel_key = "columns" if columns_active else "parts" if parts_active else tier
 
     def kernel_step():
         _lib.check(L.cc_grid_eval(prog.handle, c3, float(step), nx, n, n, x0, 0, out.device_ptr, None))
@@ -920,13 +927,22 @@ def run_ours(args):
         "frac": achieved / peak_tflops, "traffic": traffic,
         "traffic_source": "replayed from profiles/bench_traffic.json (one ncu --set full capture of this kernel at this "
                           "grid size, dram__bytes_read.sum + dram__bytes_write.sum per launch); not measured in this run",
-        "kernel": ("cc_jit_parts + cc_jit_part_centers (scene-specialised, packed FFMA2 lanes, per-brick part culling)" if parts_active
+        "kernel": ("cc_jit_columns + cc_jit_columns_profiles%s (scene-specialised, packed FFMA2 lanes; the 2-D profiles under the "
+                   "extrusions once per %s-column, the rest per cell%s)"
+                   % (" + cc_jit_columns_centers" if parts_active else "", "xyz"[int(pinfo.column_axis)],
+                      ", per-brick part culling" if parts_active else "") if columns_active
+                   else "cc_jit_parts + cc_jit_part_centers (scene-specialised, packed FFMA2 lanes, per-brick part culling)" if parts_active
                    else "cc_jit_float4 (scene-specialised, packed FFMA2 lanes)" if n_ready else "cc_eval_kernel<PTS,const,FLOAT4>"),
         "culling": (None if not parts_active else
                     "the scene is an assembly of %d parts under sharp unions; per 8x8x16 brick the kernel evaluates every part at the "
                     "brick centre, bounds it over the brick by its Lipschitz constant and skips the parts that cannot be the nearest "
                     "anywhere in the brick (bit-identical results, tests/test_gpu_parts.py).  `achieved` counts the flops of the full "
                     "walk the reference does, so `frac` exceeds 1; `issued` is what the kernel executes" % int(pinfo.n_parts)),
+        "columns": (None if not columns_active else
+                    "%d %% of the program's arithmetic (loader estimate) cannot depend on the grid's %s: 2-D profiles under extrusions.  "
+                    "One kernel evaluates those micro-ops once per column and writes the values the rest reads into a column buffer, "
+                    "the brick kernel evaluates only the rest per cell (bit-identical, tests/test_gpu_columns.py; DESIGN.md 4.10)"
+                    % (int(pinfo.column_invariant_percent), "xyz"[int(pinfo.column_axis)])),
         "flop_per_point": flops_pt,
         "flop_per_point_executed": executed.get(SCENE),
         "achieved_executed_branch": (None if SCENE not in executed else

@@ -33,7 +33,7 @@ class ProgramInfo(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint32) for n in (
         "n_words", "n_instructions", "n_micro_ops", "n_micro_words", "n_wire_registers",
         "n_slots", "n_fused", "flops_min", "flops_max", "n_forest_leaves", "forest_depth", "n_parts", "n_parts_bounded",
-        "column_invariant_percent")]
+        "column_invariant_percent", "column_axis")]
 
 
 class Level(ctypes.Structure):

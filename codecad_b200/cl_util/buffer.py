@@ -198,7 +198,8 @@ class ProgramBuffer:
     SINK_FLOAT4, SINK_PYMCUBES, SINK_CLASSIFY, SINK_MASS = 1, 2, 4, 8
     SINK_RAY, SINK_BITMAP = 16, 32  # image renderers (one ray / pixel per thread)
     SINK_POINTS = 64                # evaluate_points()
-    SINK_PARTS = 128                # dense float4 grids of an assembly: the part-culling pair of kernels
+    SINK_PARTS = 128                  # dense float4 grids of an assembly: the part-culling pair of kernels
+    SINK_COLUMNS = 256                # dense float4 grids of extrusions: the column kernels
 
     def specialize(self, points_per_thread=0, sinks=0):
         """Compile scene-specialised kernels for this program (NVRTC, seconds per sink); later

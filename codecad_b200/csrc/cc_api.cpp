@@ -448,7 +448,8 @@ int launch_columns(const cc_program *prog, cc_eval_args &a, uint64_t points, boo
                         ((a.nz + CC_BRICK_Z - 1) / CC_BRICK_Z);
     if (nb >= (1ull << 31)) return fail(CC_ERR_INVALID_ARGUMENT, "too many bricks in one launch");
     const cc_columns_meta &meta = prog->jit_columns;
-    const uint64_t ncol = (uint64_t)a.nx * a.ny;
+    const int axis = meta.axis;
+    const uint64_t ncol = axis == 2 ? (uint64_t)a.nx * a.ny : axis == 1 ? (uint64_t)a.nx * a.nz : (uint64_t)a.ny * a.nz;
     // column buffer (+ flags, brick list, counter behind it when some transform row is checked per column)
     const size_t values = (size_t)ncol * 4 * std::max(1u, meta.n_values) * sizeof(float);
     const size_t flags_at = (values + 255) & ~(size_t)255, list_at = (flags_at + ncol + 255) & ~(size_t)255;
@@ -482,10 +483,17 @@ int launch_columns(const cc_program *prog, cc_eval_args &a, uint64_t points, boo
     return CC_OK;
 }
 
+uint64_t axis_len(const cc_program *prog, const cc_eval_args &a)
+{
+    const int axis = prog->dec.columns.axis;
+    return std::max(1u, axis == 0 ? a.nx : axis == 1 ? a.ny : a.nz);
+}
+
 bool columns_apply(int sink_kind, const cc_program *prog, const cc_eval_args &a)
 {
+    const int axis = prog->dec.columns.axis;
     return g.columns_mode && sink_kind == CC_SINK_FLOAT4 && !a.points && !a.blocks && prog->dec.columns.enabled &&
-           a.nz >= 8 && (uint64_t)a.nx * a.ny * a.nz >= 4096;
+           (axis == 0 ? a.nx : axis == 1 ? a.ny : a.nz) >= 8 && (uint64_t)a.nx * a.ny * a.nz >= 4096;
 }
 
 bool parts_apply(int sink_kind, const cc_program *prog, const cc_eval_args &a)
@@ -501,7 +509,7 @@ int launch(int sink_kind, const cc_program *prog, cc_eval_args &a, uint64_t poin
         cc_program *p = const_cast<cc_program *>(prog);
         const bool with_parts = parts_apply(sink_kind, prog, a);
         // (the specialised column kernels or nothing: until they are loaded the other paths serve the launch)
-        if (jit_ready(p, CC_SINK_COLUMNS) && (uint64_t)a.nx * a.ny * 16 * std::max(1u, p->jit_columns.n_values) <= (8ull << 30))
+        if (jit_ready(p, CC_SINK_COLUMNS) && (uint64_t)a.nx * a.ny * a.nz / (axis_len(prog, a)) * 16 * std::max(1u, p->jit_columns.n_values) <= (8ull << 30))
             return launch_columns(prog, a, points, with_parts);
     }
     if (parts_apply(sink_kind, prog, a)) {

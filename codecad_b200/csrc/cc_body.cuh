@@ -232,6 +232,13 @@ CC_DEV void cc_kernel_body_bricks_at(const cc_eval_args &a, EVAL &eval, uint32_t
 #ifndef CC_COL_VALUES
 #define CC_COL_VALUES 1  // values per column record (the generated source defines it)
 #endif
+#ifndef CC_COL_AXIS
+#define CC_COL_AXIS 2    // the grid axis the columns run along: the program is (mostly) invariant along it
+#endif
+// columns are numbered over the two other axes (u slow, v fast): z-columns by (x, y), y-columns by (x, z), x-columns by (y, z)
+CC_DEV uint32_t cc_col_dim_u(const cc_eval_args &a) { return CC_COL_AXIS == 0 ? a.ny : a.nx; }
+CC_DEV uint32_t cc_col_dim_v(const cc_eval_args &a) { return CC_COL_AXIS == 2 ? a.ny : a.nz; }
+CC_DEV uint32_t cc_col_len(const cc_eval_args &a) { return CC_COL_AXIS == 0 ? a.nx : CC_COL_AXIS == 1 ? a.ny : a.nz; }
 struct cc_col_ref {
     float4 *rec[2];  // the column record of each point of the thread's pair: float4 rec[CC_COL_VALUES]
     bool ok[2];
@@ -252,13 +259,14 @@ template <class V> CC_DEV cc_val<V> cc_col_load(const cc_col_ref &r, uint32_t k)
 CC_DEV bool cc_same_bits(float a, float b) { return __float_as_uint(a) == __float_as_uint(b) && a == a; }
 CC_DEV bool cc_same_bits(float2 a, float2 b) { return cc_same_bits(a.x, b.x) && cc_same_bits(a.y, b.y); }
 
-// one thread per pair of columns 2t, 2t + 1 (column = ix * ny + iy)
+// one thread per pair of columns 2t, 2t + 1
 template <int PTS, class AHEAD>
 CC_DEV void cc_column_profiles_body(const cc_eval_args &a, AHEAD &ahead)
 {
     static_assert(PTS == 2, "two columns per thread");
     typedef typename cc_pts<PTS>::V V;
-    const uint32_t ncol = a.nx * a.ny, t = blockIdx.x * CC_THREADS + threadIdx.x;
+    const uint32_t dim_v = cc_col_dim_v(a), ncol = cc_col_dim_u(a) * dim_v, t = blockIdx.x * CC_THREADS + threadIdx.x;
+    const uint32_t last = cc_col_len(a) - 1u;
     float gx[PTS], gy[PTS], gz[PTS], gl[PTS];
     uint32_t col[PTS];
 #pragma unroll
@@ -267,11 +275,13 @@ CC_DEV void cc_column_profiles_body(const cc_eval_args &a, AHEAD &ahead)
         ahead.cr.ok[j] = c < ncol;
         col[j] = min(c, ncol - 1u);  // (every thread evaluates: the ops vote across the warp)
         ahead.cr.rec[j] = reinterpret_cast<float4 *>(a.columns) + (size_t)col[j] * CC_COL_VALUES;
-        const uint32_t ix = col[j] / a.ny, iy = col[j] - ix * a.ny;
+        const uint32_t u = col[j] / dim_v, v = col[j] - u * dim_v;
+        const uint32_t ix = CC_COL_AXIS == 0 ? 0u : u, iy = CC_COL_AXIS == 0 ? u : CC_COL_AXIS == 1 ? 0u : v, iz = CC_COL_AXIS == 2 ? 0u : v;
         gx[j] = cc_fma(a.step, (float)(ix + a.x_offset), a.cx);
         gy[j] = cc_fma(a.step, (float)iy, a.cy);
-        gz[j] = cc_fma(a.step, 0.0f, a.cz);
-        gl[j] = cc_fma(a.step, (float)(a.nz - 1u), a.cz);
+        gz[j] = cc_fma(a.step, (float)iz, a.cz);
+        gl[j] = CC_COL_AXIS == 0 ? cc_fma(a.step, (float)(last + a.x_offset), a.cx)
+                                 : cc_fma(a.step, (float)last, CC_COL_AXIS == 1 ? a.cy : a.cz);
     }
     V vx[1], vy[1], vz[1], vl[1];
     vx[0] = cc_pack<V>(gx);
@@ -307,7 +317,8 @@ CC_DEV void cc_kernel_body_brick_columns(const cc_eval_args &a, EVAL &eval)
         gx[j] = cc_fma(a.step, (float)(ix[j] + a.x_offset), a.cx);
         gy[j] = cc_fma(a.step, (float)iy[j], a.cy);
         gz[j] = cc_fma(a.step, (float)iz[j], a.cz);
-        col[j] = min(ix[j], a.nx - 1u) * a.ny + min(iy[j], a.ny - 1u);  // (cells past the edge read a neighbour's column)
+        const uint32_t u = CC_COL_AXIS == 0 ? iy[j] : ix[j], v = CC_COL_AXIS == 2 ? iy[j] : iz[j];
+        col[j] = min(u, cc_col_dim_u(a) - 1u) * cc_col_dim_v(a) + min(v, cc_col_dim_v(a) - 1u);  // (cells past the edge read a neighbour's column)
         eval.cr.rec[j] = reinterpret_cast<float4 *>(a.columns) + (size_t)col[j] * CC_COL_VALUES;
         eval.cr.ok[j] = true;
     }

@@ -56,6 +56,7 @@ struct cc_parts {
 // the z loop) and those that run per cell (cc_program.cpp analyse_columns, cc_jit.cpp).
 struct cc_columns {
     bool enabled = false;
+    int axis = 2;                      // the grid axis of the columns: 0 = x, 1 = y, 2 = z
     std::vector<uint8_t> phase;        // per micro-op: bit 0 = runs before the z loop, bit 1 = runs inside it
     std::vector<int> restore_from;     // per micro-op of the loop: the op (outside the loop) whose result is its running value, else -1
     std::vector<uint8_t> save_l;       // per micro-op: its result is carried into the loop as a running value
@@ -89,6 +90,7 @@ struct cc_columns_meta {
     uint32_t n_values = 0;  // carried values: the column buffer holds 4 * n_values floats per column
     bool checks = false;    // some transform row is verified per column: flags, brick list and the full-walk kernel exist
     bool centers = false;   // the program has parts: the library has its own brick-centre kernel
+    int axis = 2;           // the grid axis of the columns
 };
 
 #define CC_MAX_DEVICES 16  // devices one process can drive (cc_init_devices)

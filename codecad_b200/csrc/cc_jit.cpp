@@ -582,7 +582,8 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
     s << "// generated by libcodecad_b200 (cc_jit.cpp) from " << dec.info.n_micro_ops << " micro-ops\n"
       << "#define CC_THREADS " << cfg.threads << "\n"
       << (no_pack ? "#define CC_OPT_PACKED 0\n" : "") << extra_defines()
-      << (columns_mode ? "#define CC_COL_VALUES " + std::to_string(std::max(1u, n_carried)) + "\n" : std::string())
+      << (columns_mode ? "#define CC_COL_VALUES " + std::to_string(std::max(1u, n_carried)) + "\n#define CC_COL_AXIS " + std::to_string(cols.axis) + "\n"
+                       : std::string())
       << "#include \"cc_ops.cuh\"\n#include \"cc_body.cuh\"\n#include \"cc_render.cuh\"\n"
       << "#define PTS " << pts << "\n"
       << "typedef cc_pts<PTS>::V V;\nconstexpr int G = cc_pts<PTS>::G;\ntypedef cc_val<V> Val;\n"
@@ -605,7 +606,8 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
                 const uint32_t m = pcs[opi] + 1;
                 chk << "        " << (part >= 0 ? "if (mask & " + std::to_string(1u << part) + "u) " : std::string())
                     << "CC_EACH ok = ok && cc_same_bits(" << g.row_to(m + 3 * r, m + 9 + r, "gx[g]", "gy[g]", "gz[g]") << ", "
-                    << g.row_to(m + 3 * r, m + 9 + r, "gx[g]", "gy[g]", "gz_last[g]") << ");\n";
+                    << g.row_to(m + 3 * r, m + 9 + r, cols.axis == 0 ? "g_last[g]" : "gx[g]", cols.axis == 1 ? "g_last[g]" : "gy[g]",
+                                cols.axis == 2 ? "g_last[g]" : "gz[g]") << ");\n";
             }
         }
         if (full_open >= 0) full << "        }\n";
@@ -618,8 +620,8 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
           << full.str() << "    }\n};\n"
           << "// once per (x, y) column: what cannot see the grid's z; every part (a column crosses many bricks)\n"
           << "struct SceneAhead {\n    float4 *sm;\n    cc_col_ref cr;\n    static constexpr unsigned mask = 0xffffffffu;\n"
-          << "    // may one evaluation stand for the whole column gz .. gz_last?\n"
-          << "    __device__ __forceinline__ bool invariant" << sig << ", const V (&gz_last)[G]) const\n    {\n"
+          << "    // may one evaluation stand for the whole column?  (g_last: the coordinate along the columns' axis at its far end)\n"
+          << "    __device__ __forceinline__ bool invariant" << sig << ", const V (&g_last)[G]) const\n    {\n"
           << "        bool ok = true;\n" << chk.str() << "        return ok;\n    }\n"
           << "    __device__ __forceinline__ void operator()" << sig << ") const\n    {\n" << hoisted.str() << "        Val L[G];\n" << zero_l
           << ahead.str() << "    }\n};\n"
@@ -633,6 +635,7 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
             columns_meta->n_values = n_carried;
             columns_meta->checks = !chk.str().empty();
             columns_meta->centers = parts_mode;
+            columns_meta->axis = cols.axis;
         }
     } else if (!segmented) {
         s << "struct SceneEval {\n    float4 *sm;  // this thread's column of the value cells\n";
@@ -1276,7 +1279,7 @@ int cc_jit_launch_columns(const cc_program *prog, const cc_eval_args &a, uint32_
         if (ce != cudaSuccess) return (int)ce;
         ++*n_launches;
     }
-    const uint32_t ncol = a.nx * a.ny;
+    const uint32_t ncol = prog->jit_columns.axis == 2 ? a.nx * a.ny : prog->jit_columns.axis == 1 ? a.nx * a.nz : a.ny * a.nz;
     ce = cudaLaunchKernel((const void *)prog->jit_columns_kernels[1], dim3((ncol + 2 * threads - 1) / (2 * threads)), dim3(threads), args, smem, st);
     if (ce != cudaSuccess) return (int)ce;
     ce = cudaLaunchKernel((const void *)prog->jit_kernel[sink], dim3(n_bricks), dim3(threads), args, smem, st);

@@ -348,9 +348,10 @@ bool sigma_max(const float *m, double *out)
 //   2-D primitives      read x, y; write (nx, ny, 0, d)
 //   mirror/offset/nop   component-wise
 //   everything else     any dependent input makes every output component dependent
-void analyse_columns(const std::vector<uint32_t> &code, cc_columns *out)
+static void analyse_columns_along(const std::vector<uint32_t> &code, int axis, cc_columns *out)
 {
     *out = cc_columns();
+    out->axis = axis;
     enum { X = 1, Y = 2, Z = 4, W = 8, ALL = 15 };
     struct Op { uint32_t pc, op; int in_l, in_s; uint8_t dep; uint32_t cost; };
     std::vector<Op> ops;
@@ -382,7 +383,7 @@ void analyse_columns(const std::vector<uint32_t> &code, cc_columns *out)
             return d;
         };
         switch (op) {
-        case MOP_T_INIT: case MOP_T_INIT_M: {  // the grid point: only its z varies
+        case MOP_T_INIT: case MOP_T_INIT_M: {  // the grid point: only its coordinate along the axis varies
             // A coefficient of z that is rounding residue (a half turn written as a quaternion leaves
             // cos(pi/2) = 6e-17 behind) is not omitted by cc-arith, so the row does see z — in the last bits of
             // a value near zero, if at all.  Such rows count as invariant here and are CHECKED per column at run
@@ -390,8 +391,8 @@ void analyse_columns(const std::vector<uint32_t> &code, cc_columns *out)
             // both ends of the column mean equal bits at every cell between them (cc_jit.cpp `invariant`).
             uint8_t d = 0;
             for (int r = 0; r < 3; ++r) {
-                const float big = std::max(std::fabs(fl(pc, 3 * r)), std::fabs(fl(pc, 3 * r + 1)));
-                const float mz = std::fabs(fl(pc, 3 * r + 2));
+                const float big = std::max(std::fabs(fl(pc, 3 * r + (axis + 1) % 3)), std::fabs(fl(pc, 3 * r + (axis + 2) % 3)));
+                const float mz = std::fabs(fl(pc, 3 * r + axis));
                 if (mz != 0.0f && !(mz <= big * 9.313225746154785e-10f)) d |= (uint8_t)(1 << r);  // 2^-30
                 else if (mz != 0.0f) out->checked_rows.push_back((uint32_t)ops.size() * 4u + (uint32_t)r);
             }
@@ -470,6 +471,17 @@ void analyse_columns(const std::vector<uint32_t> &code, cc_columns *out)
     (void)repeated;
     out->invariant_share = total ? (float)((double)hoisted / (double)total) : 0.0f;
     out->enabled = out->invariant_share >= 0.25f;
+}
+
+// the grid axis along which most of the program is invariant (z, the fastest index of the output, on ties)
+void analyse_columns(const std::vector<uint32_t> &code, cc_columns *out)
+{
+    analyse_columns_along(code, 2, out);
+    for (int axis = 1; axis >= 0; --axis) {
+        cc_columns c;
+        analyse_columns_along(code, axis, &c);
+        if (c.invariant_share > out->invariant_share + 0.05f) *out = c;
+    }
 }
 
 void analyse_parts(const std::vector<uint32_t> &code, cc_parts *out)
@@ -1093,5 +1105,6 @@ int cc_decode_program(const float *words, uint32_t n_words, cc_decoded *out, std
     if (out->parts.enabled)
         for (float l : out->parts.lipschitz) out->info.n_parts_bounded += std::isfinite(l) ? 1u : 0u;
     out->info.column_invariant_percent = out->columns.enabled ? (uint32_t)(out->columns.invariant_share * 100.0f) : 0u;
+    out->info.column_axis = (uint32_t)out->columns.axis;
     return CC_OK;
 }

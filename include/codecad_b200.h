@@ -98,6 +98,7 @@ typedef struct cc_program_info {
     uint32_t column_invariant_percent; /* estimated share of the arithmetic that does not depend on the grid's z
                                           (2-D profiles under extrusions); evaluated once per z-column of a dense
                                           grid when >= 25 (cc_set_columns_mode), 0 = nothing to gain          */
+    uint32_t column_axis;     /* the grid axis those columns run along: 0 = x, 1 = y, 2 = z                */
 } cc_program_info;
 int cc_program_get_info(const cc_program *prog, cc_program_info *out);
 /* copies the decoded microcode (for tests / disassembly); returns the microcode length */
@@ -149,8 +150,9 @@ int cc_set_parts_mode(int mode);
  * under an extrusion (transform, polygon2d, involute gear, their CSG: shapes/simple2d.cl, polygons2d.cl,
  * gears.cl before simple3d.cl extrusion) reads x and y only: its value is the same in every cell of a
  * z-column.  The loader proves, micro-op by micro-op and component by component, what cannot depend on
- * the grid's z (cc_program_info.column_invariant_percent); the column kernel evaluates that once per
- * column and only the rest per cell.  Same arithmetic on the same operands: bit-identical.  Combines with
+ * the grid's z — or x, or y: the axis with the largest invariant share is taken — (cc_program_info.
+ * column_invariant_percent, column_axis); the column kernels evaluate that once per column and only the
+ * rest per cell.  Same arithmetic on the same operands: bit-identical.  Combines with
  * the parts' masks.  mode 1 = on (default; CODECAD_B200_COLUMNS), 0 = off.  Returns the old mode. */
 int cc_set_columns_mode(int mode);
 int cc_program_get_forest_info(const cc_program *prog, uint32_t out[4]);

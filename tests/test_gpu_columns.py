@@ -10,7 +10,7 @@ import oracle
 from scenes import ALL_NAMES
 
 pytestmark = pytest.mark.gpu
-COLUMN_SCENES = ["cfg_planetary", "x_gear3d", "dsdf2d_gear", "dsdf2d_mirror_2d", "dsdf2d_rotated_pattern_2d", "dsdf2d_bin_counter_11"]
+COLUMN_SCENES = ["cfg_planetary", "cfg_airfoil", "x_gear3d", "dsdf2d_gear", "dsdf2d_mirror_2d", "dsdf2d_rotated_pattern_2d", "dsdf2d_bin_counter_11"]
 
 
 @pytest.fixture(scope="module")
@@ -42,6 +42,8 @@ def test_which_scenes_have_columns(scenes):
     assert set(COLUMN_SCENES) <= set(have)
     assert _lib.decode_program(scenes["cfg_planetary"].words)[0].column_invariant_percent >= 40
     assert _lib.decode_program(scenes["cfg_csg_example"].words)[0].column_invariant_percent == 0
+    assert _lib.decode_program(scenes["cfg_planetary"].words)[0].column_axis == 2       # gears extruded along z
+    assert _lib.decode_program(scenes["cfg_airfoil"].words)[0].column_axis != 2         # the wing's span is not the grid's z
 
 
 @pytest.mark.parametrize("name", COLUMN_SCENES)
