@@ -73,9 +73,10 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append(line.strip())
+            self.samples.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, window=None):
+        """window = (t0, t1) host times: only the samples taken inside it count."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -85,7 +86,9 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        for t, s in self.samples:
+            if window is not None and not (window[0] <= t <= window[1]):
+                continue
             parts = [p.strip() for p in s.split(",")]
             if len(parts) < 7:
                 continue
@@ -747,19 +750,32 @@ def run_ours(args):
         return ms.value
 
     # ---- kernel-only throughput ----
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
     for _ in range(max(args.warmup, 3)):
         kernel_step()
     _lib.check(L.cc_synchronize())
     barrier(torch, dist)
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     L.cc_reset_counters()
+    t_begin = time.time()
     ms_total = timed(kernel_step, args.steps)
     _lib.check(L.cc_synchronize())
+    t_end = time.time()
     barrier(torch, dist)
     launches, _ = _lib.counters()
-    clk = clocks.stop() if rank == 0 else None
+    clk = None
+    if rank == 0:
+        # nvidia-smi samples every 100 ms (started ahead of the warm-up: its first line takes longer than that); the K
+        # timed steps may last no longer than one period, so the same step keeps running, untimed, until the load
+        # window holds a handful of samples — the window reported is then the timed region plus that continuation
+        t_load = t_end
+        while len([1 for t, _s in clocks.samples if t_begin <= t <= t_load]) < 5 and t_load - t_end < 2.0:
+            kernel_step()
+            _lib.check(L.cc_synchronize())
+            t_load = time.time()
+        clk = clocks.stop((t_begin, t_load))
+        clk["window_s"] = {"timed_region": t_end - t_begin, "same_steps_continued_untimed": t_load - t_end}
     ms_total = max_over_ranks(torch, dist, ms_total)
     ms_step = ms_total / args.steps
     total_points = float(n) ** 3

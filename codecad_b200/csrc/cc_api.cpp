@@ -483,6 +483,44 @@ int launch_columns(const cc_program *prog, cc_eval_args &a, uint64_t points, boo
     return CC_OK;
 }
 
+// The hierarchy sinks (ordered hit lists, mass sums) through the column kernels: the column pass covers the
+// columns of every block of the launch, the tile kernel is cc_kernel_body with the per-cell body.
+int launch_columns_tiles(int sink_kind, const cc_program *prog, cc_eval_args &a, uint64_t points)
+{
+    const cc_columns_meta &meta = prog->jit_columns;
+    const int sink = CC_SINK_COLUMNS;
+    const uint32_t tile = (uint32_t)(prog->jit_cfg[sink].threads * prog->jit_cfg[sink].pts);
+    const uint64_t cells = (uint64_t)a.nx * a.ny * a.nz;
+    a.tiles_per_block = (uint32_t)((cells + tile - 1) / tile);
+    const uint64_t tiles = (uint64_t)a.tiles_per_block * a.n_blocks;
+    if (tiles >= (1ull << 31)) return fail(CC_ERR_INVALID_ARGUMENT, "too many tiles in one launch");
+    int rc = ensure_status((size_t)tiles);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(g.d_ticket, 0, 4, g.compute));
+    CU(cudaMemsetAsync(g.d_status, 0, (size_t)tiles * sizeof(unsigned long long), g.compute));
+    a.ticket = g.d_ticket;
+    a.tile_status = g.d_status;
+    const int axis = meta.axis;
+    const uint64_t ncol = (uint64_t)a.n_blocks * (axis == 2 ? (uint64_t)a.nx * a.ny : axis == 1 ? (uint64_t)a.nx * a.nz : (uint64_t)a.ny * a.nz);
+    const size_t values = (size_t)ncol * 4 * std::max(1u, meta.n_values) * sizeof(float);
+    const size_t flags_at = (values + 255) & ~(size_t)255;
+    const size_t bytes = meta.checks ? flags_at + ncol : values;
+    if (bytes > g.columns_cap) {
+        if (g.d_columns) CU(cudaFree(g.d_columns));
+        g.d_columns = nullptr;
+        g.columns_cap = 0;
+        CU(cudaMalloc(&g.d_columns, bytes));
+        g.columns_cap = bytes;
+    }
+    a.columns = reinterpret_cast<float *>(g.d_columns);
+    a.column_flags = meta.checks ? reinterpret_cast<unsigned char *>(g.d_columns) + flags_at : nullptr;
+    int e = cc_jit_launch_columns_tiles(prog, sink_kind, a, g.compute, g.index);
+    if (e) return cuda_fail((cudaError_t)e, "column tile kernel launch");
+    g.launches += 2;
+    g.points += points;
+    return CC_OK;
+}
+
 uint64_t axis_len(const cc_program *prog, const cc_eval_args &a)
 {
     const int axis = prog->dec.columns.axis;
@@ -511,6 +549,13 @@ int launch(int sink_kind, const cc_program *prog, cc_eval_args &a, uint64_t poin
         // (the specialised column kernels or nothing: until they are loaded the other paths serve the launch)
         if (jit_ready(p, CC_SINK_COLUMNS) && (uint64_t)a.nx * a.ny * a.nz / (axis_len(prog, a)) * 16 * std::max(1u, p->jit_columns.n_values) <= (8ull << 30))
             return launch_columns(prog, a, points, with_parts);
+    }
+    if ((sink_kind == CC_SINK_CLASSIFY || sink_kind == CC_SINK_MASS) && g.columns_mode && !a.points && prog->dec.columns.enabled &&
+        axis_len(prog, a) >= 8 && (uint64_t)a.nx * a.ny * a.nz >= 512) {
+        cc_program *p = const_cast<cc_program *>(prog);
+        if (jit_ready(p, CC_SINK_COLUMNS) &&
+            (uint64_t)a.n_blocks * a.nx * a.ny * a.nz / axis_len(prog, a) * 16 * std::max(1u, p->jit_columns.n_values) <= (8ull << 30))
+            return launch_columns_tiles(sink_kind, prog, a, points);
     }
     if (parts_apply(sink_kind, prog, a)) {
         if (jit_ready(const_cast<cc_program *>(prog), CC_SINK_PARTS)) return launch_parts(prog, a, points, true);
@@ -1005,7 +1050,8 @@ int cc_program_specialize_wait(cc_program *prog, unsigned sink_mask, double *com
     if ((sink_mask & CC_SINK_MASK_ALL) == 0) sink_mask = 15u;
     // dense float4 grids of an assembly run on the part-culling kernels: "ready" includes them
     if ((sink_mask & (1u << CC_SINK_FLOAT4)) && prog->dec.parts.enabled && g.parts_mode) sink_mask |= 1u << CC_SINK_PARTS;
-    if ((sink_mask & (1u << CC_SINK_FLOAT4)) && prog->dec.columns.enabled && g.columns_mode) sink_mask |= 1u << CC_SINK_COLUMNS;
+    if ((sink_mask & ((1u << CC_SINK_FLOAT4) | (1u << CC_SINK_CLASSIFY) | (1u << CC_SINK_MASS))) && prog->dec.columns.enabled && g.columns_mode)
+        sink_mask |= 1u << CC_SINK_COLUMNS;
     int ready = 0;
     for (int k = 0; k < CC_N_SINKS; ++k) {
         if (!(sink_mask & (1u << k))) continue;

@@ -17,6 +17,15 @@
 // POINTS: the launch evaluates a list of points (a.points) instead of grid coordinates; a
 // compile-time switch so that the grid kernels carry nothing for it (a run-time branch cost the
 // 64-register specialised kernel 3.5 % more instructions).
+// optional hook: a functor with locate(a, block, ix, iy, iz) is told, before it is called, which cells of which
+// block the thread evaluates (the column kernels look up their columns there, cc_col_locate)
+template <class EVAL, class... T> CC_DEV void cc_eval_locate_(long, EVAL &, const T &...) {}
+template <class EVAL, class... T>
+CC_DEV auto cc_eval_locate_(int, EVAL &e, const T &...t) -> decltype(e.locate(t...), void())
+{
+    e.locate(t...);
+}
+
 template <int PTS, int SINK, class EVAL, bool POINTS = false>
 CC_DEV void cc_kernel_body(const cc_eval_args &a, EVAL &eval)
 {
@@ -67,6 +76,7 @@ CC_DEV void cc_kernel_body(const cc_eval_args &a, EVAL &eval)
         }
     }
 
+    if (!POINTS) cc_eval_locate_(0, eval, a, block, ix, iy, iz);
     float4 L[PTS];
     {
         V vx[G], vy[G], vz[G];
@@ -265,7 +275,8 @@ CC_DEV void cc_column_profiles_body(const cc_eval_args &a, AHEAD &ahead)
 {
     static_assert(PTS == 2, "two columns per thread");
     typedef typename cc_pts<PTS>::V V;
-    const uint32_t dim_v = cc_col_dim_v(a), ncol = cc_col_dim_u(a) * dim_v, t = blockIdx.x * CC_THREADS + threadIdx.x;
+    const uint32_t dim_v = cc_col_dim_v(a), per_block = cc_col_dim_u(a) * dim_v, ncol = per_block * max(a.n_blocks, 1u),
+                   t = blockIdx.x * CC_THREADS + threadIdx.x;
     const uint32_t last = cc_col_len(a) - 1u;
     float gx[PTS], gy[PTS], gz[PTS], gl[PTS];
     uint32_t col[PTS];
@@ -275,13 +286,19 @@ CC_DEV void cc_column_profiles_body(const cc_eval_args &a, AHEAD &ahead)
         ahead.cr.ok[j] = c < ncol;
         col[j] = min(c, ncol - 1u);  // (every thread evaluates: the ops vote across the warp)
         ahead.cr.rec[j] = reinterpret_cast<float4 *>(a.columns) + (size_t)col[j] * CC_COL_VALUES;
-        const uint32_t u = col[j] / dim_v, v = col[j] - u * dim_v;
+        const uint32_t block = col[j] / per_block, in_block = col[j] - block * per_block;
+        const uint32_t u = in_block / dim_v, v = in_block - u * dim_v;
         const uint32_t ix = CC_COL_AXIS == 0 ? 0u : u, iy = CC_COL_AXIS == 0 ? u : CC_COL_AXIS == 1 ? 0u : v, iz = CC_COL_AXIS == 2 ? 0u : v;
-        gx[j] = cc_fma(a.step, (float)(ix + a.x_offset), a.cx);
-        gy[j] = cc_fma(a.step, (float)iy, a.cy);
-        gz[j] = cc_fma(a.step, (float)iz, a.cz);
-        gl[j] = CC_COL_AXIS == 0 ? cc_fma(a.step, (float)(last + a.x_offset), a.cx)
-                                 : cc_fma(a.step, (float)last, CC_COL_AXIS == 1 ? a.cy : a.cz);
+        float cx = a.cx, cy = a.cy, cz = a.cz;
+        if (a.blocks) {  // the block's own corner, as in cc_kernel_body
+            const cc_block_desc bd = a.blocks[block];
+            cx = bd.cx; cy = bd.cy; cz = bd.cz;
+        }
+        gx[j] = cc_fma(a.step, (float)(ix + a.x_offset), cx);
+        gy[j] = cc_fma(a.step, (float)iy, cy);
+        gz[j] = cc_fma(a.step, (float)iz, cz);
+        gl[j] = CC_COL_AXIS == 0 ? cc_fma(a.step, (float)(last + a.x_offset), cx)
+                                 : cc_fma(a.step, (float)last, CC_COL_AXIS == 1 ? cy : cz);
     }
     V vx[1], vy[1], vz[1], vl[1];
     vx[0] = cc_pack<V>(gx);
@@ -295,6 +312,26 @@ CC_DEV void cc_column_profiles_body(const cc_eval_args &a, AHEAD &ahead)
             if (ahead.cr.ok[j]) a.column_flags[col[j]] = bad;
     }
     ahead(vx, vy, vz);
+}
+
+// the columns of the cells a thread of cc_kernel_body evaluates (blocks x linear tiles); returns whether any column
+// of the CTA's tile failed the run-time check (CTA-uniform: every thread calls it)
+template <int PTS>
+CC_DEV bool cc_col_locate(const cc_eval_args &a, uint32_t block, const uint32_t (&ix)[PTS], const uint32_t (&iy)[PTS],
+                          const uint32_t (&iz)[PTS], cc_col_ref &cr)
+{
+    static_assert(PTS == 2, "two points per thread");
+    const uint32_t dim_v = cc_col_dim_v(a), per_block = cc_col_dim_u(a) * dim_v;
+    int flagged = 0;
+#pragma unroll
+    for (int j = 0; j < PTS; ++j) {
+        const uint32_t u = CC_COL_AXIS == 0 ? iy[j] : ix[j], v = CC_COL_AXIS == 2 ? iy[j] : iz[j];
+        const uint32_t col = block * per_block + u * dim_v + v;
+        cr.rec[j] = reinterpret_cast<float4 *>(a.columns) + (size_t)col * CC_COL_VALUES;
+        cr.ok[j] = true;
+        if (a.column_flags) flagged |= a.column_flags[col];
+    }
+    return a.column_flags ? __syncthreads_or(flagged) != 0 : false;
 }
 
 // the brick kernel of cc_kernel_body_bricks with the thread's two columns at hand

@@ -631,6 +631,12 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
           << in_loop.str();
         if (cols.root_restore >= 0) s << "        CC_EACH L[g] = cc_col_load<V>(cr, " << carried_l[(size_t)cols.root_restore] << "u);\n";
         s << "    }\n};\n";
+        s << "// the hierarchy sinks (blocks x linear tiles): the rest per cell, or the full walk for a tile with a flagged column\n"
+          << "struct SceneTile {\n    SceneEval loop;\n    SceneFull full;\n    bool use_full;\n"
+          << "    __device__ __forceinline__ void locate(const cc_eval_args &a, unsigned block, const unsigned (&ix)[PTS], const unsigned (&iy)[PTS],\n"
+          << "                                           const unsigned (&iz)[PTS])\n    {\n        use_full = cc_col_locate<PTS>(a, block, ix, iy, iz, loop.cr);\n    }\n"
+          << "    __device__ __forceinline__ void operator()" << sig << ", Val (&L)[G]) const\n    {\n"
+          << "        if (use_full) full(gx, gy, gz, L);\n        else loop(gx, gy, gz, L);\n    }\n};\n";
         if (columns_meta) {
             columns_meta->n_values = n_carried;
             columns_meta->checks = !chk.str().empty();
@@ -691,6 +697,11 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
           << "        const unsigned b = a.brick_list[i];\n"
           << "        SceneFull e{cc_cells + threadIdx.x, a.part_masks ? a.part_masks[b] : 0xffffffffu, nullptr};\n"
           << "        cc_kernel_body_bricks_at<PTS>(a, e, b);\n    }\n}\n";
+        const char *tile_sinks[2][2] = {{"classify", "CC_SINK_CLASSIFY"}, {"mass", "CC_SINK_MASS"}};
+        for (auto &ts : tile_sinks)
+            s << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_columns_" << ts[0] << head
+              << "    SceneTile e;\n    e.loop.sm = e.full.sm = cc_cells + threadIdx.x;\n    e.loop.mask = e.full.mask = 0xffffffffu;\n"
+              << "    e.full.pw = nullptr;\n    cc_kernel_body<PTS, " << ts[1] << ">(a, e);\n}\n";
         if (parts_mode) {
             s << "__constant__ float cc_part_lipschitz[" << parts.n_parts << "] = {";
             for (uint32_t k = 0; k < parts.n_parts; ++k) {
@@ -1086,8 +1097,9 @@ static int load_cubin(cc_program *prog, int sink, const Cubin &bin, const cc_jit
             release_library(lib);
             return CC_ERR_CUDA;
         }
-        const char *extra[3] = {meta.centers ? "cc_jit_columns_centers" : nullptr, "cc_jit_columns_profiles", "cc_jit_columns_full"};
-        for (int k = 0; k < 3; ++k) {
+        const char *extra[5] = {meta.centers ? "cc_jit_columns_centers" : nullptr, "cc_jit_columns_profiles", "cc_jit_columns_full",
+                                "cc_jit_columns_classify", "cc_jit_columns_mass"};
+        for (int k = 0; k < 5; ++k) {
             cudaKernel_t kk = nullptr;
             if (extra[k] && (ce = cudaLibraryGetKernel(&kk, lib, extra[k])) != cudaSuccess) {
                 *err = std::string("cudaLibraryGetKernel(") + extra[k] + "): " + cudaGetErrorString(ce);
@@ -1252,6 +1264,32 @@ int cc_jit_launch_parts(const cc_program *prog, const cc_eval_args &a, uint32_t 
     if (ce != cudaSuccess || centers_only) return (int)ce;
     return (int)cudaLaunchKernel((const void *)prog->jit_kernel[sink], dim3(n_bricks), dim3(threads), args, smem,
                                  (cudaStream_t)stream);
+}
+
+// the hierarchy sinks through the column kernels: column pass over every block's columns, then the ordered tile kernel
+// (the caller prepared tickets, tile status, a.columns and a.column_flags like cc_jit_launch / cc_jit_launch_columns)
+int cc_jit_launch_columns_tiles(const cc_program *prog, int sink_kind, const cc_eval_args &a, void *stream, int dev_index)
+{
+    const int sink = CC_SINK_COLUMNS;
+    const size_t smem = prog->jit_smem[sink];
+    if (int e = ensure_smem_attr(prog, sink, dev_index)) return e;
+    if (smem)
+        for (void *k : prog->jit_columns_kernels)
+            if (k) {
+                cudaError_t ce = cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (ce != cudaSuccess) return (int)ce;
+            }
+    const uint32_t threads = (uint32_t)prog->jit_cfg[sink].threads;
+    const int axis = prog->jit_columns.axis;
+    const uint64_t ncol = (uint64_t)std::max(1u, a.n_blocks) * (axis == 2 ? (uint64_t)a.nx * a.ny : axis == 1 ? (uint64_t)a.nx * a.nz : (uint64_t)a.ny * a.nz);
+    const uint64_t tiles = (uint64_t)a.tiles_per_block * a.n_blocks;
+    if (tiles == 0) return 0;
+    void *args[] = {(void *)&a};
+    cudaError_t ce = cudaLaunchKernel((const void *)prog->jit_columns_kernels[1], dim3((unsigned)((ncol + 2 * threads - 1) / (2 * threads))),
+                                      dim3(threads), args, smem, (cudaStream_t)stream);
+    if (ce != cudaSuccess) return (int)ce;
+    return (int)cudaLaunchKernel((const void *)prog->jit_columns_kernels[sink_kind == CC_SINK_CLASSIFY ? 3 : 4], dim3((unsigned)tiles), dim3(threads),
+                                 args, smem, (cudaStream_t)stream);
 }
 
 // CC_SINK_COLUMNS: [brick centres ->] column pass -> brick kernel [-> full walk of the flagged bricks]; the caller

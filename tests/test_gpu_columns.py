@@ -119,3 +119,61 @@ def test_columns_serve_the_launch(cb, scenes):
         cb.grid_eval(prog, corner, step, (64, 64, 64))
         assert _lib.counters()[0] - n0 < n_launches[0]
         _lib.check(L.cc_set_columns_mode(1))
+
+
+# ---- the hierarchy sinks through the column kernels (blocks x linear tiles) ----
+
+HIERARCHY_SCENES = ["cfg_airfoil", "cfg_planetary", "x_gear3d"]
+
+
+@pytest.mark.parametrize("name", HIERARCHY_SCENES)
+def test_mass_properties_through_columns_is_identical(cb, scenes, name):
+    """mass_properties sums are integers: with and without the column kernels they must be the same numbers, and
+    the oracle's."""
+    import codecad_b200
+    from codecad_b200 import _lib
+    from codecad_b200.cl_util.buffer import ProgramBuffer
+    from oracle import host
+    L = _lib.lib()
+    s = scenes[name]
+    scene = s.compiled()
+    a, b = _box(s)
+    res = float(max(b - a)) / 150.0
+    scene.program_buffer().wait_specialized(ProgramBuffer.SINK_MASS)
+    _lib.check(L.cc_set_columns_mode(1))
+    n0 = _lib.counters()[0]
+    got = codecad_b200.mass_properties(scene, res, 32)
+    with_columns = _lib.counters()[0] - n0
+    _lib.check(L.cc_set_columns_mode(0))
+    n0 = _lib.counters()[0]
+    want = codecad_b200.mass_properties(scene, res, 32)
+    without = _lib.counters()[0] - n0
+    _lib.check(L.cc_set_columns_mode(1))
+    assert with_columns > without                       # the column pass is an extra launch per level chunk: it ran
+    assert got.volume == want.volume and tuple(got.centroid) == tuple(want.centroid)
+    assert np.array_equal(np.array(got.inertia_tensor), np.array(want.inertia_tensor))
+    vol, cen, _ = host.mass_properties(s.words, s.box_a, s.box_b, res, 32)   # (Kahan sums on the host: last-digit differences allowed)
+    assert abs(got.volume - vol) <= 1e-12 * abs(vol) and np.allclose(np.array(got.centroid), np.array(cen), rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", HIERARCHY_SCENES)
+def test_subdivision_through_columns_is_identical(cb, scenes, name):
+    import codecad_b200
+    from codecad_b200 import _lib
+    from codecad_b200.cl_util.buffer import ProgramBuffer
+    L = _lib.lib()
+    s = scenes[name]
+    scene = s.compiled()
+    a, b = _box(s)
+    res = float(max(b - a)) / 200.0
+    scene.program_buffer().wait_specialized(ProgramBuffer.SINK_CLASSIFY)
+    out = []
+    for mode in (1, 0):
+        _lib.check(L.cc_set_columns_mode(mode))
+        r = codecad_b200.subdivision(scene, res, grid_size=16)
+        out.append(r)
+    _lib.check(L.cc_set_columns_mode(1))
+    assert tuple(out[0][1]) == tuple(out[1][1])
+    assert [tuple(map(tuple, (blk[0], blk[1], blk[3]))) + (blk[2], blk[4]) for blk in out[0][2]] == \
+           [tuple(map(tuple, (blk[0], blk[1], blk[3]))) + (blk[2], blk[4]) for blk in out[1][2]]
+    assert len(out[0][2]) > 0
