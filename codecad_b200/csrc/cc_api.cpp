@@ -530,7 +530,7 @@ uint64_t axis_len(const cc_program *prog, const cc_eval_args &a)
 bool columns_apply(int sink_kind, const cc_program *prog, const cc_eval_args &a)
 {
     const int axis = prog->dec.columns.axis;
-    return g.columns_mode && sink_kind == CC_SINK_FLOAT4 && !a.points && !a.blocks && prog->dec.columns.enabled &&
+    return g.columns_mode && sink_kind == CC_SINK_FLOAT4 && !a.points && !a.blocks && prog->dec.columns.enabled && !cc_jit_is_segmented(prog->dec) &&
            (axis == 0 ? a.nx : axis == 1 ? a.ny : a.nz) >= 8 && (uint64_t)a.nx * a.ny * a.nz >= 4096;
 }
 
@@ -551,6 +551,7 @@ int launch(int sink_kind, const cc_program *prog, cc_eval_args &a, uint64_t poin
             return launch_columns(prog, a, points, with_parts);
     }
     if ((sink_kind == CC_SINK_CLASSIFY || sink_kind == CC_SINK_MASS) && g.columns_mode && !a.points && prog->dec.columns.enabled &&
+        !cc_jit_is_segmented(prog->dec) &&
         axis_len(prog, a) >= 8 && (uint64_t)a.nx * a.ny * a.nz >= 512) {
         cc_program *p = const_cast<cc_program *>(prog);
         if (jit_ready(p, CC_SINK_COLUMNS) &&
@@ -558,7 +559,7 @@ int launch(int sink_kind, const cc_program *prog, cc_eval_args &a, uint64_t poin
             return launch_columns_tiles(sink_kind, prog, a, points);
     }
     if (parts_apply(sink_kind, prog, a)) {
-        if (jit_ready(const_cast<cc_program *>(prog), CC_SINK_PARTS)) return launch_parts(prog, a, points, true);
+        if (!cc_jit_is_segmented(prog->dec) && jit_ready(const_cast<cc_program *>(prog), CC_SINK_PARTS)) return launch_parts(prog, a, points, true);
         // interpreter tier: the same culling by walking the segment table (needs the microcode in shared memory)
         if (!prog->dec.parts.table.empty() && prog->dec.parts.n_parts <= 32 &&
             cc_parts_smem_bytes(prog->dec.info.n_slots, prog->dec.info.n_micro_words, 2) * 2 <= (size_t)g.prop.sharedMemPerMultiprocessor)
@@ -1049,8 +1050,10 @@ int cc_program_specialize_wait(cc_program *prog, unsigned sink_mask, double *com
     if (!prog) return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
     if ((sink_mask & CC_SINK_MASK_ALL) == 0) sink_mask = 15u;
     // dense float4 grids of an assembly run on the part-culling kernels: "ready" includes them
-    if ((sink_mask & (1u << CC_SINK_FLOAT4)) && prog->dec.parts.enabled && g.parts_mode) sink_mask |= 1u << CC_SINK_PARTS;
-    if ((sink_mask & ((1u << CC_SINK_FLOAT4) | (1u << CC_SINK_CLASSIFY) | (1u << CC_SINK_MASS))) && prog->dec.columns.enabled && g.columns_mode)
+    const bool small = !cc_jit_is_segmented(prog->dec);
+    if (small && (sink_mask & (1u << CC_SINK_FLOAT4)) && prog->dec.parts.enabled && g.parts_mode) sink_mask |= 1u << CC_SINK_PARTS;
+    if (small && (sink_mask & ((1u << CC_SINK_FLOAT4) | (1u << CC_SINK_CLASSIFY) | (1u << CC_SINK_MASS))) && prog->dec.columns.enabled &&
+        g.columns_mode)
         sink_mask |= 1u << CC_SINK_COLUMNS;
     int ready = 0;
     for (int k = 0; k < CC_N_SINKS; ++k) {

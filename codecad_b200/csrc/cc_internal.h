@@ -119,6 +119,7 @@ struct cc_program {
 
 // cc_jit.cpp
 cc_jit_cfg cc_jit_default_cfg(const cc_decoded &dec, int pts);
+bool cc_jit_is_segmented(const cc_decoded &dec);
 int cc_jit_source(const cc_decoded &dec, int pts, unsigned sink_mask, std::string *src, std::string *err);
 int cc_jit_nvrtc(const std::string &src, std::vector<char> *cubin, std::string *err);
 int cc_jit_compile(cc_program *prog, int pts, unsigned sink_mask, double *seconds, std::string *err);

@@ -823,6 +823,14 @@ cc_jit_cfg cc_jit_default_cfg(const cc_decoded &dec, int pts)
     return c;
 }
 
+// long programs are compiled as segments (generate()); part culling and the column kernels exist for the others
+bool cc_jit_is_segmented(const cc_decoded &dec)
+{
+    const cc_jit_cfg c = cc_jit_default_cfg(dec, 2);
+    const int n = (int)dec.info.n_micro_ops + 1;
+    return c.segment_ops > 0 && n > c.segment_ops + c.segment_ops / 2;
+}
+
 int cc_jit_nvrtc(const std::string &src, std::vector<char> *cubin, std::string *err)
 {
     Nvrtc n;
