@@ -1163,16 +1163,35 @@ cc_jit_cfg cc_jit_render_cfg(const cc_decoded &dec)
     return c;
 }
 
+// Shape of the brick kernels (part culling, columns): a CTA of 512 threads x 2 points is one 8 x 8 x 16 brick,
+// whatever the program's own preference for the linear-tile kernels is.
+static cc_jit_cfg cc_jit_brick_cfg(const cc_decoded &dec)
+{
+    cc_jit_cfg c = cc_jit_default_cfg(dec, 2);
+    if (c.pts != 2 || c.threads != 512) {
+        c.pts = 2;
+        c.threads = 512;
+        c.min_blocks = 2;
+        c.smem_max_cells = std::min(c.smem_max_cells, 6);
+    }
+    return c;
+}
+static cc_jit_cfg cc_jit_cfg_for(const cc_decoded &dec, int sink, int pts)
+{
+    if (sink == CC_SINK_RAY || sink == CC_SINK_BITMAP) return cc_jit_render_cfg(dec);
+    if (sink == CC_SINK_PARTS || sink == CC_SINK_COLUMNS) return cc_jit_brick_cfg(dec);
+    return cc_jit_default_cfg(dec, pts);
+}
+
 // synchronous: build + load every sink of the mask
 int cc_jit_compile(cc_program *prog, int pts, unsigned sink_mask, double *seconds, std::string *err)
 {
     if ((sink_mask & CC_SINK_MASK_ALL) == 0) sink_mask = 15u;  // default: the four grid sinks
-    const cc_jit_cfg grid_cfg = cc_jit_default_cfg(prog->dec, pts), render_cfg = cc_jit_render_cfg(prog->dec);
     auto t0 = std::chrono::steady_clock::now();
     for (int k = 0; k < CC_N_SINKS; ++k) {
         if (!(sink_mask & (1u << k))) continue;
         join_job(prog, k);
-        const cc_jit_cfg &cfg = (k == CC_SINK_RAY || k == CC_SINK_BITMAP) ? render_cfg : grid_cfg;
+        const cc_jit_cfg cfg = cc_jit_cfg_for(prog->dec, k, pts);
         Cubin bin;
         size_t smem = 0;
         int rc = build_cubin(prog->dec, cfg, k, &bin, &smem, nullptr, err);
@@ -1189,7 +1208,7 @@ void cc_jit_start(cc_program *prog, int sink)
 {
     if (prog->jit_kernel[sink] || prog->jit_job[sink] || prog->jit_failed[sink]) return;
     cc_jit_job *j = new cc_jit_job;
-    j->cfg = (sink == CC_SINK_RAY || sink == CC_SINK_BITMAP) ? cc_jit_render_cfg(prog->dec) : cc_jit_default_cfg(prog->dec, 0);
+    j->cfg = cc_jit_cfg_for(prog->dec, sink, 0);
     prog->jit_job[sink] = j;
     const cc_decoded *dec = &prog->dec;  // immutable; outlives the thread (destroy joins it)
     j->th = std::thread([j, dec, sink]() {
@@ -1344,6 +1363,7 @@ int cc_jit_source(const cc_decoded &dec, int pts, unsigned sink_mask, std::strin
     if ((sink_mask & CC_SINK_MASK_ALL) == 0) sink_mask = 15u;
     if (sink_mask & ((1u << CC_SINK_RAY) | (1u << CC_SINK_BITMAP)))
         return generate(dec, cc_jit_render_cfg(dec), sink_mask, src, nullptr, err);
+    if (sink_mask & ((1u << CC_SINK_PARTS) | (1u << CC_SINK_COLUMNS))) return generate(dec, cc_jit_brick_cfg(dec), sink_mask, src, nullptr, err);
     return generate(dec, cc_jit_default_cfg(dec, pts), sink_mask, src, nullptr, err);
 }
 

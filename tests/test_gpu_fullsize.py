@@ -88,6 +88,20 @@ def test_planetary_1024_cubed(cb, scenes):
     _lib.check(L.cc_memcpy_d2h_async(got_mid.ctypes.data, mid.device_ptr, got_mid.nbytes, None))
     _lib.check(L.cc_synchronize())
     assert got_mid.tobytes() == want_mid.tobytes()
+    # tier 4 (the column kernels on top of the part masks: the gears' 2-D profiles once per z-column): same again
+    prog.specialize(0, ProgramBuffer.SINK_COLUMNS)
+    launches0, _ = _lib.counters()
+    _lib.check(L.cc_memset_async(out.device_ptr, 0, n * n * n * 16, None))
+    cb.grid_eval(prog, corner, step, (n, n, n), device_out=out)
+    assert _lib.counters()[0] == launches0 + 4, "the column kernels did not run (centres, column pass, bricks, flagged bricks)"
+    t4 = _planes(L, out, n, sample)
+    crc4 = zlib.crc32(b"".join(np.uint32(zlib.crc32(t4[x].tobytes())).tobytes() for x in sample))
+    assert crc1 == crc4
+    _lib.check(L.cc_memset_async(mid.device_ptr, 0, want_mid.nbytes, None))
+    cb.grid_eval(prog, corner, step, (128, n, n), x_offset=448, device_out=mid)
+    _lib.check(L.cc_memcpy_d2h_async(got_mid.ctypes.data, mid.device_ptr, got_mid.nbytes, None))
+    _lib.check(L.cc_synchronize())
+    assert got_mid.tobytes() == want_mid.tobytes()
     mid.release()
     del got_mid, want_mid
     # z-slab sharding as on 8 GPUs: rank 5 of 8 evaluates x in [640, 768) with an offset
@@ -148,6 +162,26 @@ def test_airfoil_mass_properties_config(cb, scenes):
         assert got.volume == pytest.approx(vol, rel=1e-12)
         assert np.allclose(got.centroid, cen, rtol=1e-12, atol=1e-12)
         assert np.allclose(got.inertia_tensor, inertia, rtol=1e-9, atol=1e-9 * np.abs(inertia).max())
+    # the same call through the specialised kernels, and through the column kernels (the two 163-edge profiles once
+    # per column of every 64^3 block): integer sums, so the same doubles to the last bit
+    from codecad_b200 import _lib
+    from codecad_b200.cl_util.buffer import ProgramBuffer
+    scene = a.compiled()
+    interp = cb.mass_properties(scene, 0.25, 64)
+    scene.program_buffer().specialize(0, ProgramBuffer.SINK_MASS)
+    spec = cb.mass_properties(scene, 0.25, 64)
+    scene.program_buffer().specialize(0, ProgramBuffer.SINK_COLUMNS)
+    n0 = _lib.counters()[0]
+    cols = cb.mass_properties(scene, 0.25, 64)
+    n_cols = _lib.counters()[0] - n0
+    old = _lib.check(_lib.lib().cc_set_columns_mode(0))
+    n0 = _lib.counters()[0]
+    cb.mass_properties(scene, 0.25, 64)
+    assert n_cols > _lib.counters()[0] - n0, "the column pass did not run"
+    _lib.check(_lib.lib().cc_set_columns_mode(old))
+    for other in (spec, cols):
+        assert other.volume == interp.volume and tuple(other.centroid) == tuple(interp.centroid)
+        assert np.array_equal(np.array(other.inertia_tensor), np.array(interp.inertia_tensor))
 
 
 @pytest.mark.parametrize("grid", [128, 16])

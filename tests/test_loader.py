@@ -186,3 +186,35 @@ def test_assemblies_are_cut_into_parts(scenes):
         assert info.n_parts_bounded <= info.n_parts <= 32
         if name in ("cfg_csg_example", "cfg_airfoil", "mp_sphere", "x_smooth_isect"):
             assert info.n_parts == 0, name        # one component, or a rounded combinator at the root
+
+
+def test_profiles_under_extrusions_are_column_invariant(scenes):
+    """cc_program.cpp analyse_columns: which micro-ops cannot see the grid coordinate along the best axis, and
+    that the code generator turns the split into the column kernels (source only: no device needed)."""
+    from codecad_b200 import _lib
+    want_axis = {"cfg_planetary": 2, "x_gear3d": 2, "dsdf2d_gear": 2}
+    for name, s in scenes.items():
+        info, _ = _lib.decode_program(s.words)
+        assert info.column_invariant_percent == 0 or 25 <= info.column_invariant_percent <= 100, name
+        assert info.column_axis in (0, 1, 2)
+        if name in want_axis:
+            assert info.column_invariant_percent >= 40 and info.column_axis == want_axis[name], name
+        if s.dimension == 2 and info.n_micro_ops >= 3:
+            # a 2-D scene never reads z (scenes whose transformations tilt the plane aside)
+            assert info.column_invariant_percent in (0, 100) or info.column_axis != 2, name
+        if name in ("cfg_csg_example", "mp_sphere"):
+            assert info.column_invariant_percent == 0, name   # spheres and boxes in general position: nothing to hoist
+    assert _lib.decode_program(scenes["cfg_airfoil"].words)[0].column_axis != 2     # the wing's span is not the grid's z
+    src = _lib.specialize_source(scenes["cfg_planetary"].words, 2, compile=False, sink_mask=256)
+    src = src[0] if isinstance(src, tuple) else src
+    for kernel in ("cc_jit_columns_centers", "cc_jit_columns_profiles", "cc_jit_columns(", "cc_jit_columns_full", "cc_jit_columns_mass",
+                   "cc_jit_columns_classify"):
+        assert kernel in src, kernel
+    ahead = src[src.index("struct SceneAhead"):src.index("struct SceneEval")]
+    loop = src[src.index("struct SceneEval"):src.index("struct SceneTile")]
+    assert ahead.count("cc_op_gear") == 9 and loop.count("cc_op_gear") == 0        # the nine involute gears leave the per-cell body
+    assert loop.count("cc_extrusion_n") >= 12 and "cc_col_load" in loop and "cc_col_store" in ahead
+    assert "cc_same_bits" in ahead                                                 # the half turns' residue rows are checked per column
+    src = _lib.specialize_source(scenes["x_gear3d"].words, 2, compile=False, sink_mask=256)
+    src = src[0] if isinstance(src, tuple) else src
+    assert "cc_jit_columns_centers" not in src                                     # no parts, no brick centres
