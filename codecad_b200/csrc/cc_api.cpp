@@ -1252,15 +1252,17 @@ static int grid_to_host_share(const cc_program *prog, const float corner[3], flo
     const size_t elem = 16;
     const int layout = CC_LAYOUT_INDEX3_FLOAT4;
     const int RING = Context::kRing;
-    // slab size, measured on the test box against 51.9 GB/s for one bare copy of the whole grid:
-    // 16 MiB slabs 50.6 GB/s, 32 MiB 49.2, 64 MiB 44.7, 128 MiB 37.9, 256 MiB 33.9 — a slab that the
-    // copy engine still finds in the 126 MB L2 is read there instead of in HBM
+    // Slab size.  Measured with the culling kernels (21 ms of compute per 1024^3 grid) against 57.0 GB/s for bare
+    // copies on the same box: 16 MiB slabs 50.5 GB/s, 32 MiB 51.7, 64 MiB 56.8, 128 MiB 56.9, 256 MiB 56.7
+    // (tools/e2e_probe.py).  The brick kernels evaluate 8 x-planes at a time, so a slab is a multiple of 8 planes
+    // where that keeps it under 512 MiB: a one-plane slab would have them compute eight planes to keep one.
     static const uint64_t slab_mib = [] {
         const char *t = getenv("CODECAD_B200_SLAB_MIB");
         const long v = t ? atol(t) : 0;
-        return (uint64_t)(v > 0 ? v : 16);
+        return (uint64_t)(v > 0 ? v : 64);
     }();
     uint32_t slab_x = (uint32_t)std::max<uint64_t>(1, (slab_mib << 20) / (plane * elem));
+    if ((uint64_t)((slab_x + 7u) & ~7u) * plane * elem <= (512ull << 20)) slab_x = (slab_x + 7u) & ~7u;
     slab_x = std::min(slab_x, nx);
     const size_t slab_bytes = (size_t)slab_x * plane * elem;
     if (slab_bytes > g.ring_bytes) {
