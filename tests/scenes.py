@@ -29,7 +29,7 @@ class Scene:
         return np.array(corner, np.float64).astype(np.float32), np.float32(step)
 
 
-FILES = ("scenes.npz", "forest_scenes.npz")  # tools/make_fixtures.py, tools/make_fixtures.py --forests
+FILES = ("scenes.npz", "forest_scenes.npz", "column_scenes.npz")  # tools/make_fixtures.py [--forests | --columns]
 
 
 def load_scenes():
@@ -42,4 +42,5 @@ def load_scenes():
 
 
 ALL_NAMES = sorted(load_scenes())
+COLUMN_NAMES = [n for n in ALL_NAMES if n.startswith("col_")]
 FOREST_NAMES = [n for n in ALL_NAMES if n.startswith("forest_") or n.startswith("cfg_synthetic")]

@@ -102,6 +102,36 @@ def forest_scenes():
     return out
 
 
+def column_scenes():
+    """Extrusions for the column kernels beyond the configs: profiles under mirror / symmetry /
+    offset / shell, nested transformations, extrusion axes along x, y, z and oblique, half turns (whose
+    quaternions leave rounding residue in the matrix), profiles combined with solids that do see every axis,
+    an intersection of two extrusions along different axes, extrusions under repetition and revolution."""
+    out = {}
+    star = s.polygon2d([(0, 3), (0.8, 0.9), (3, 0.7), (1.2, -0.6), (1.9, -2.8), (0, -1.4), (-1.9, -2.8), (-1.2, -0.6), (-3, 0.7),
+                        (-0.8, 0.9)])
+    gear = s.gears.InvoluteGear(11, 0.8)
+    hexagon = s.regular_polygon2d(6, r=2.5)
+    out["col_star_z"] = star.extruded(3)
+    out["col_star_y"] = star.extruded(3).rotated((1, 0, 0), 90)
+    out["col_star_x"] = star.extruded(3).rotated((0, 1, 0), 90).translated(0.5, -0.25, 1)
+    out["col_star_half_turn"] = star.extruded(2).rotated((1, 0, 0), 180).translated(0, 0.5, 0)
+    out["col_star_oblique"] = star.extruded(3).rotated((1, 2, 3), 25)
+    out["col_gear_rot_z"] = gear.extruded(2).rotated((0, 0, 1), 33).translated(1, 2, 0.5)
+    out["col_hexagon_shell"] = hexagon.shell(0.3).extruded(4).translated(0, 0, 1)
+    out["col_offset_mirror"] = (star.offset(0.2).translated(4, 0) + star.mirrored_x().translated(-4, 0)).extruded(2.5)
+    out["col_symmetrical"] = (s.rectangle(2, 1).translated(2, 0.5) + s.circle(d=1.5).translated(3, 2)).symmetrical_x().extruded(1.5)
+    out["col_profile_and_sphere"] = star.extruded(2) + s.sphere(d=3).translated(0, 0, 2) - s.cylinder(h=10, d=0.8)
+    out["col_crossed_extrusions"] = hexagon.extruded(8) & gear.scaled(1.5).extruded(8).rotated((1, 0, 0), 90)
+    out["col_two_levels"] = (star.scaled(0.5).rotated(20).translated(1, 1) & s.circle(d=2.6).translated(1, 1)).extruded(2).rotated((0, 0, 1), 45) \
+        .translated(0, 0, -1).scaled(1.5)
+    out["col_revolved_and_extruded"] = s.rectangle(1, 2).translated(3, 0).revolved() + star.scaled(0.6).extruded(5)
+    out["col_repeated"] = codecad.shapes.unsafe.Repetition(s.circle(d=1.2).extruded(1), (2.5, 2.5, None)) & s.box(9, 9, 3)
+    out["col_assembly"] = s.union([gear.extruded(1).translated(-4, 0, 0), hexagon.extruded(2).translated(4, 0, 0.5),
+                                   star.scaled(0.7).extruded(1.5).rotated((0, 0, 1), 10).translated(0, 5, 0), s.sphere(d=2).translated(0, -5, 0)])
+    return out
+
+
 def collect():
     scenes = {}
 
@@ -157,7 +187,8 @@ def collect():
 def main():
     out = {}
     forests = "--forests" in sys.argv   # the extra file tests/golden/forest_scenes.npz
-    scenes = forest_scenes() if forests else collect()
+    columns = "--columns" in sys.argv   # the extra file tests/golden/column_scenes.npz
+    scenes = forest_scenes() if forests else column_scenes() if columns else collect()
     for name, shape in scenes.items():
         random.seed(0)
         words = codecad.nodes.make_program(shape)
@@ -174,7 +205,7 @@ def main():
         out[name + ".words"] = words
         out[name + ".meta"] = meta
         print("%-46s dim %d  %5d words  bbox %s .. %s" % (name, shape.dimension(), len(words), box.a, box.b))
-    path = os.path.join(REPO, "tests", "golden", "forest_scenes.npz" if forests else "scenes.npz")
+    path = os.path.join(REPO, "tests", "golden", "forest_scenes.npz" if forests else "column_scenes.npz" if columns else "scenes.npz")
     numpy.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")
 
