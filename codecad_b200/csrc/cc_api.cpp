@@ -356,7 +356,9 @@ int launch_forest(const cc_program *prog, cc_eval_args &a, uint64_t points)
     // error budget of the primitives' bounds: 2^-16 of the magnitudes that enter their arithmetic
     const double ext[3] = {std::fabs((double)a.step) * (double)(a.nx + a.x_offset), std::fabs((double)a.step) * a.ny,
                            std::fabs((double)a.step) * a.nz};
-    const double pmax = std::max(std::fabs((double)a.cx) + ext[0], std::max(std::fabs((double)a.cy) + ext[1], std::fabs((double)a.cz) + ext[2]));
+    // (launches over blocks: the caller's bound on every block's coordinates)
+    const double pmax = a.blocks ? (double)a.coord_max + std::max(ext[0], std::max(ext[1], ext[2]))
+                                 : std::max(std::fabs((double)a.cx) + ext[0], std::max(std::fabs((double)a.cy) + ext[1], std::fabs((double)a.cz) + ext[2]));
     f.slack = (float)(((double)prog->dec.forest.err_a + (double)prog->dec.forest.err_b * pmax) / 65536.0);
     if (!std::isfinite(f.slack)) return fail(CC_ERR_INVALID_ARGUMENT, "grid coordinates out of range");
     const size_t ow = cc_forest_overflow_words(a);
@@ -483,40 +485,53 @@ int launch_columns(const cc_program *prog, cc_eval_args &a, uint64_t points, boo
     return CC_OK;
 }
 
-// The hierarchy sinks (ordered hit lists, mass sums) through the column kernels: the column pass covers the
-// columns of every block of the launch, the tile kernel is cc_kernel_body with the per-cell body.
-int launch_columns_tiles(int sink_kind, const cc_program *prog, cc_eval_args &a, uint64_t points)
+// The hierarchy sinks (ordered hit lists, mass sums, PyMCubes fields of blocks) through the brick units' tile
+// kernels: with `columns` the column pass covers the columns of every block of the launch and the tile kernel
+// runs the per-cell body; with `masks` a tile-centre pass writes a part mask per tile first.
+int launch_tiles(int sink_kind, const cc_program *prog, cc_eval_args &a, uint64_t points, bool columns, bool masks)
 {
     const cc_columns_meta &meta = prog->jit_columns;
-    const int sink = CC_SINK_COLUMNS;
+    const int sink = columns ? CC_SINK_COLUMNS : CC_SINK_PARTS;
     const uint32_t tile = (uint32_t)(prog->jit_cfg[sink].threads * prog->jit_cfg[sink].pts);
     const uint64_t cells = (uint64_t)a.nx * a.ny * a.nz;
     a.tiles_per_block = (uint32_t)((cells + tile - 1) / tile);
     const uint64_t tiles = (uint64_t)a.tiles_per_block * a.n_blocks;
     if (tiles >= (1ull << 31)) return fail(CC_ERR_INVALID_ARGUMENT, "too many tiles in one launch");
-    int rc = ensure_status((size_t)tiles);
-    if (rc) return rc;
-    CU(cudaMemsetAsync(g.d_ticket, 0, 4, g.compute));
-    CU(cudaMemsetAsync(g.d_status, 0, (size_t)tiles * sizeof(unsigned long long), g.compute));
-    a.ticket = g.d_ticket;
-    a.tile_status = g.d_status;
-    const int axis = meta.axis;
-    const uint64_t ncol = (uint64_t)a.n_blocks * (axis == 2 ? (uint64_t)a.nx * a.ny : axis == 1 ? (uint64_t)a.nx * a.nz : (uint64_t)a.ny * a.nz);
-    const size_t values = (size_t)ncol * 4 * std::max(1u, meta.n_values) * sizeof(float);
-    const size_t flags_at = (values + 255) & ~(size_t)255;
-    const size_t bytes = meta.checks ? flags_at + ncol : values;
-    if (bytes > g.columns_cap) {
-        if (g.d_columns) CU(cudaFree(g.d_columns));
-        g.d_columns = nullptr;
-        g.columns_cap = 0;
-        CU(cudaMalloc(&g.d_columns, bytes));
-        g.columns_cap = bytes;
+    if (sink_kind == CC_SINK_CLASSIFY || sink_kind == CC_SINK_MASS) {
+        int rc = ensure_status((size_t)tiles);
+        if (rc) return rc;
+        CU(cudaMemsetAsync(g.d_ticket, 0, 4, g.compute));
+        CU(cudaMemsetAsync(g.d_status, 0, (size_t)tiles * sizeof(unsigned long long), g.compute));
+        a.ticket = g.d_ticket;
+        a.tile_status = g.d_status;
     }
-    a.columns = reinterpret_cast<float *>(g.d_columns);
-    a.column_flags = meta.checks ? reinterpret_cast<unsigned char *>(g.d_columns) + flags_at : nullptr;
-    int e = cc_jit_launch_columns_tiles(prog, sink_kind, a, g.compute, g.index);
-    if (e) return cuda_fail((cudaError_t)e, "column tile kernel launch");
-    g.launches += 2;
+    a.columns = nullptr;
+    a.column_flags = nullptr;
+    if (columns) {
+        const int axis = meta.axis;
+        const uint64_t ncol = (uint64_t)a.n_blocks * (axis == 2 ? (uint64_t)a.nx * a.ny : axis == 1 ? (uint64_t)a.nx * a.nz : (uint64_t)a.ny * a.nz);
+        const size_t values = (size_t)ncol * 4 * std::max(1u, meta.n_values) * sizeof(float);
+        const size_t flags_at = (values + 255) & ~(size_t)255;
+        const size_t bytes = meta.checks ? flags_at + ncol : values;
+        if (bytes > g.columns_cap) {
+            if (g.d_columns) CU(cudaFree(g.d_columns));
+            g.d_columns = nullptr;
+            g.columns_cap = 0;
+            CU(cudaMalloc(&g.d_columns, bytes));
+            g.columns_cap = bytes;
+        }
+        a.columns = reinterpret_cast<float *>(g.d_columns);
+        a.column_flags = meta.checks ? reinterpret_cast<unsigned char *>(g.d_columns) + flags_at : nullptr;
+    }
+    a.part_masks = nullptr;
+    if (masks) {
+        int rc = prepare_part_masks(prog, a, tiles);
+        if (rc) return rc;
+    }
+    int n_launches = 0;
+    int e = cc_jit_launch_tiles(prog, columns, sink_kind, a, g.compute, g.index, &n_launches);
+    if (e) return cuda_fail((cudaError_t)e, "tile kernel launch");
+    g.launches += (uint64_t)n_launches;
     g.points += points;
     return CC_OK;
 }
@@ -550,13 +565,15 @@ int launch(int sink_kind, const cc_program *prog, cc_eval_args &a, uint64_t poin
         if (jit_ready(p, CC_SINK_COLUMNS) && (uint64_t)a.nx * a.ny * a.nz / (axis_len(prog, a)) * 16 * std::max(1u, p->jit_columns.n_values) <= (8ull << 30))
             return launch_columns(prog, a, points, with_parts);
     }
-    if ((sink_kind == CC_SINK_CLASSIFY || sink_kind == CC_SINK_MASS) && g.columns_mode && !a.points && prog->dec.columns.enabled &&
-        !cc_jit_is_segmented(prog->dec) &&
-        axis_len(prog, a) >= 8 && (uint64_t)a.nx * a.ny * a.nz >= 512) {
+    if ((sink_kind == CC_SINK_CLASSIFY || sink_kind == CC_SINK_MASS || (sink_kind == CC_SINK_PYMCUBES && a.blocks)) && !a.points &&
+        !cc_jit_is_segmented(prog->dec) && (uint64_t)a.nx * a.ny * a.nz >= 512) {
+        // blocks x linear tiles: the per-cell body of the column kernels and / or a part mask per tile
         cc_program *p = const_cast<cc_program *>(prog);
-        if (jit_ready(p, CC_SINK_COLUMNS) &&
-            (uint64_t)a.n_blocks * a.nx * a.ny * a.nz / axis_len(prog, a) * 16 * std::max(1u, p->jit_columns.n_values) <= (8ull << 30))
-            return launch_columns_tiles(sink_kind, prog, a, points);
+        const bool masks = g.parts_mode && prog->dec.parts.enabled && (!a.blocks || a.coord_max > 0.0f);
+        const bool cols = g.columns_mode && prog->dec.columns.enabled && axis_len(prog, a) >= 8 && jit_ready(p, CC_SINK_COLUMNS) &&
+                          (uint64_t)a.n_blocks * a.nx * a.ny * a.nz / axis_len(prog, a) * 16 * std::max(1u, p->jit_columns.n_values) <= (8ull << 30);
+        if (cols) return launch_tiles(sink_kind, prog, a, points, true, masks);
+        if (masks && jit_ready(p, CC_SINK_PARTS)) return launch_tiles(sink_kind, prog, a, points, false, true);
     }
     if (parts_apply(sink_kind, prog, a)) {
         if (!cc_jit_is_segmented(prog->dec) && jit_ready(const_cast<cc_program *>(prog), CC_SINK_PARTS)) return launch_parts(prog, a, points, true);
@@ -1051,10 +1068,10 @@ int cc_program_specialize_wait(cc_program *prog, unsigned sink_mask, double *com
     if ((sink_mask & CC_SINK_MASK_ALL) == 0) sink_mask = 15u;
     // dense float4 grids of an assembly run on the part-culling kernels: "ready" includes them
     const bool small = !cc_jit_is_segmented(prog->dec);
-    if (small && (sink_mask & (1u << CC_SINK_FLOAT4)) && prog->dec.parts.enabled && g.parts_mode) sink_mask |= 1u << CC_SINK_PARTS;
-    if (small && (sink_mask & ((1u << CC_SINK_FLOAT4) | (1u << CC_SINK_CLASSIFY) | (1u << CC_SINK_MASS))) && prog->dec.columns.enabled &&
-        g.columns_mode)
-        sink_mask |= 1u << CC_SINK_COLUMNS;
+    // the brick units serve the four grid sinks: dense float4 grids by bricks, the others by tiles with masks / columns
+    const unsigned grid_sinks = (1u << CC_SINK_FLOAT4) | (1u << CC_SINK_PYMCUBES) | (1u << CC_SINK_CLASSIFY) | (1u << CC_SINK_MASS);
+    if (small && (sink_mask & grid_sinks) && prog->dec.parts.enabled && g.parts_mode) sink_mask |= 1u << CC_SINK_PARTS;
+    if (small && (sink_mask & grid_sinks) && prog->dec.columns.enabled && g.columns_mode) sink_mask |= 1u << CC_SINK_COLUMNS;
     int ready = 0;
     for (int k = 0; k < CC_N_SINKS; ++k) {
         if (!(sink_mask & (1u << k))) continue;
@@ -1456,6 +1473,13 @@ int subdivide_share(const cc_program *prog, const double origin[3], double resol
     DevBuf *cur = &corners_a, *nxt = &corners_b;
     const uint32_t deal = deal_level_subdiv(n_levels);
     if (dealt_blocks) *dealt_blocks = 0;
+    // every block of every level lies inside the root block: the bound on coordinates the tile masks' rounding budget needs
+    float coord_max = 0.0f;
+    for (int i = 0; i < 3; ++i) {
+        const double n0 = i == 0 ? levels[0].nx : i == 1 ? levels[0].ny : levels[0].nz;
+        const double far = origin[i] + (n0 + 1.0) * (double)levels[0].cell_size * resolution;
+        coord_max = std::max(coord_max, (float)std::max(std::fabs(origin[i]), std::fabs(far)));
+    }
 
     for (uint32_t l = 0; l + 1 < n_levels; ++l) {
         const cc_level &L = levels[l];
@@ -1481,6 +1505,7 @@ int subdivide_share(const cc_program *prog, const double origin[3], double resol
             a.step = (float)box_step;
             a.nx = L.nx; a.ny = L.ny; a.nz = L.nz; a.n_blocks = nb;
             a.blocks = blocks.as<cc_block_desc>();
+            a.coord_max = coord_max;
             a.threshold = thr;
             a.counter = counter.as<uint32_t>();
             a.list = hit_xyz.as<uint8_t>();
@@ -1599,6 +1624,12 @@ int mass_share(const cc_program *prog, const double box_a[3], double resolution,
     DevBuf *cur = &corners_a, *nxt = &corners_b;
     uint64_t n_cur = 1, n_launch = 0, n_cells = 0, n_blocks_total = 0, n_dealt = 0;
     const uint32_t deal = deal_level_mass(n_levels);
+    float coord_max = 0.0f;  // (as in subdivide_share)
+    for (int i = 0; i < 3; ++i) {
+        const double n0 = i == 0 ? levels[0].nx : i == 1 ? levels[0].ny : levels[0].nz;
+        const double far = box_a[i] + (n0 + 1.0) * (double)levels[0].cell_size * resolution;
+        coord_max = std::max(coord_max, (float)std::max(std::fabs(box_a[i]), std::fabs(far)));
+    }
 
     for (uint32_t l = 0; l < n_levels && n_cur; ++l) {
         const cc_level &L = levels[l];
@@ -1630,6 +1661,7 @@ int mass_share(const cc_program *prog, const double box_a[3], double resolution,
             a.step = (float)s;
             a.nx = L.nx; a.ny = L.ny; a.nz = L.nz; a.n_blocks = nb;
             a.blocks = blocks.as<cc_block_desc>();
+            a.coord_max = coord_max;
             a.threshold = thr;
             a.counter = counter.as<uint32_t>();
             a.list = hit_xyz.as<uint8_t>();
@@ -2186,6 +2218,7 @@ int cc_mesh_blocks(const cc_program *prog, const double *corners, double resolut
     if (!resident && (rc = shared_field.reserve((size_t)chunk * cells * 4))) return rc;
     std::vector<cc_block_desc> h_desc(chunk);
     const float step = (float)resolution;  // numpy.float32(box_resolution), rendering/mesh.py:58
+    float mesh_coord_max = 0.0f;  // largest |corner coordinate| seen so far (the tile masks' rounding budget adds the block's extent)
 
     auto phase_a = [&](Chunk &c) -> int {
         int rc2;
@@ -2196,6 +2229,7 @@ int cc_mesh_blocks(const cc_program *prog, const double *corners, double resolut
         for (uint32_t b = 0; b < nb; ++b) {  // Vector.as_float4(): float64 -> float32 per block
             const double *p = corners + 3 * (size_t)(c.b0 + b);
             h_desc[b] = cc_block_desc{(float)p[0], (float)p[1], (float)p[2], 0u};
+            mesh_coord_max = std::max(mesh_coord_max, (float)std::max(std::fabs(p[0]), std::max(std::fabs(p[1]), std::fabs(p[2]))));
         }
         CU(cudaMemcpyAsync(c.descs.p, h_desc.data(), (size_t)nb * sizeof(cc_block_desc), cudaMemcpyHostToDevice, g.compute));
         CU(cudaMemcpyAsync(c.corner.p, corners + 3 * (size_t)c.b0, (size_t)nb * 3 * sizeof(double), cudaMemcpyHostToDevice,
@@ -2206,6 +2240,7 @@ int cc_mesh_blocks(const cc_program *prog, const double *corners, double resolut
         a.step = step;
         a.nx = nx; a.ny = ny; a.nz = nz; a.n_blocks = nb;
         a.blocks = c.descs.as<cc_block_desc>();
+        a.coord_max = mesh_coord_max;
         a.out = field;
         if ((rc2 = launch(CC_SINK_PYMCUBES, prog, a, (uint64_t)nb * cells))) return rc2;
 

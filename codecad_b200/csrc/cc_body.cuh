@@ -17,8 +17,8 @@
 // POINTS: the launch evaluates a list of points (a.points) instead of grid coordinates; a
 // compile-time switch so that the grid kernels carry nothing for it (a run-time branch cost the
 // 64-register specialised kernel 3.5 % more instructions).
-// optional hook: a functor with locate(a, block, ix, iy, iz) is told, before it is called, which cells of which
-// block the thread evaluates (the column kernels look up their columns there, cc_col_locate)
+// optional hook: a functor with locate(a, tile, block, ix, iy, iz) is told, before it is called, which cells of which
+// tile and block the thread evaluates (the tile's part mask; the column kernels look up their columns, cc_col_locate)
 template <class EVAL, class... T> CC_DEV void cc_eval_locate_(long, EVAL &, const T &...) {}
 template <class EVAL, class... T>
 CC_DEV auto cc_eval_locate_(int, EVAL &e, const T &...t) -> decltype(e.locate(t...), void())
@@ -76,7 +76,7 @@ CC_DEV void cc_kernel_body(const cc_eval_args &a, EVAL &eval)
         }
     }
 
-    if (!POINTS) cc_eval_locate_(0, eval, a, block, ix, iy, iz);
+    if (!POINTS) cc_eval_locate_(0, eval, a, tile, block, ix, iy, iz);
     float4 L[PTS];
     {
         V vx[G], vy[G], vz[G];
@@ -384,6 +384,76 @@ template <int PTS, class EVAL>
 CC_DEV void cc_kernel_body_bricks(const cc_eval_args &a, EVAL &eval)
 {
     cc_kernel_body_bricks_at<PTS>(a, eval, blockIdx.x);
+}
+
+// ---- part masks for the linear tiles of cc_kernel_body (the hierarchy sinks, blocks x tiles) -------------
+// A tile is CC_THREADS * PTS consecutive cells of a block in INDEX3 order: inside one x-plane a run of whole
+// y-rows (or a piece of one row); across x-planes every (y, z).  Its index box, conservative:
+CC_DEV void cc_tile_bounds(const cc_eval_args &a, uint32_t tile_in_block, uint32_t tile_cells, float (&lo)[3], float (&hi)[3])
+{
+    const uint32_t cells = a.nx * a.ny * a.nz, nyz = a.ny * a.nz;
+    const uint32_t c0 = min(tile_in_block * tile_cells, cells - 1u), c1 = min(c0 + tile_cells, cells) - 1u;
+    const uint32_t x0 = c0 / nyz, x1 = c1 / nyz;
+    uint32_t y0 = 0, y1 = a.ny - 1u, z0 = 0, z1 = a.nz - 1u;
+    if (x0 == x1) {
+        const uint32_t r0 = c0 - x0 * nyz, r1 = c1 - x0 * nyz;
+        y0 = r0 / a.nz;
+        y1 = r1 / a.nz;
+        if (y0 == y1) {
+            z0 = r0 - y0 * a.nz;
+            z1 = r1 - y1 * a.nz;
+        }
+    }
+    lo[0] = (float)(x0 + a.x_offset); hi[0] = (float)(x1 + a.x_offset);
+    lo[1] = (float)y0; hi[1] = (float)y1;
+    lo[2] = (float)z0; hi[2] = (float)z1;
+}
+
+// Tile-centre pass: thread t evaluates every part at the centres of the index boxes of tiles 2t and 2t + 1 and
+// writes their masks (the rule of cc_part_centers_body with the box's own half diagonal).
+template <int P, int PTS, class EVAL, class V>
+CC_DEV void cc_tile_centers_body(const cc_eval_args &a, EVAL &eval, V *pw, const float *lip)
+{
+    const uint32_t n_tiles = a.tiles_per_block * a.n_blocks;
+    const uint32_t t0 = 2u * (blockIdx.x * CC_THREADS + threadIdx.x);
+    float gx[2], gy[2], gz[2], r[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const uint32_t tile = min(t0 + (uint32_t)j, n_tiles - 1u);
+        const uint32_t block = tile / a.tiles_per_block, tile_in_block = tile - block * a.tiles_per_block;
+        float cx = a.cx, cy = a.cy, cz = a.cz;
+        if (a.blocks) {
+            const cc_block_desc bd = a.blocks[block];
+            cx = bd.cx; cy = bd.cy; cz = bd.cz;
+        }
+        float lo[3], hi[3];
+        cc_tile_bounds(a, tile_in_block, (uint32_t)(CC_THREADS * PTS), lo, hi);
+        gx[j] = cc_fma(a.step, 0.5f * (lo[0] + hi[0]), cx);
+        gy[j] = cc_fma(a.step, 0.5f * (lo[1] + hi[1]), cy);
+        gz[j] = cc_fma(a.step, 0.5f * (lo[2] + hi[2]), cz);
+        const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        r[j] = fabsf(a.step) * (0.5f * 1.0001f) * sqrtf(dx * dx + dy * dy + dz * dz);
+    }
+    V vx[1], vy[1], vz[1];
+    cc_val<V> LV[1];
+    vx[0] = cc_pack<V>(gx);
+    vy[0] = cc_pack<V>(gy);
+    vz[0] = cc_pack<V>(gz);
+#pragma unroll
+    for (int k = 0; k < P; ++k) pw[k] = vbc<V>(__int_as_float(0x7fc00000));  // NaN: "unknown" keeps a part alive
+    eval(vx, vy, vz, LV);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        if (t0 + (uint32_t)j >= n_tiles) break;
+        float upper = __int_as_float(0x7f800000);
+#pragma unroll
+        for (int k = 0; k < P; ++k) upper = fminf(upper, cc_lane_scalar(pw[k], j) + (lip[k] * r[j] + a.part_slack));
+        uint32_t mask = 0;
+#pragma unroll
+        for (int k = 0; k < P; ++k)
+            if (!(cc_lane_scalar(pw[k], j) - (lip[k] * r[j] + a.part_slack) > upper)) mask |= 1u << k;
+        a.part_masks[t0 + (uint32_t)j] = mask;
+    }
 }
 
 // Brick-centre pass.  Thread t evaluates every part at the centres of bricks 2t and 2t + 1 (one packed

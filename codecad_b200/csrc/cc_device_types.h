@@ -68,6 +68,7 @@ struct cc_eval_args {
     // part culling (CC_SINK_PARTS): one mask per brick, bit k = part k can matter there
     uint32_t *part_masks;
     float part_slack;     // bound on |computed - exact| of a part's value over the launch
+    float coord_max;      // launches over blocks: largest |coordinate| any block of the launch can reach (0: unknown, no masks)
     // columns (CC_SINK_COLUMNS, cc_body.cuh): per-column values of the z-invariant micro-ops, columns that
     // failed the run-time check (null: the program has nothing to check), the bricks those send to the full walk
     float *columns;

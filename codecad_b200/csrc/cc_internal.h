@@ -105,7 +105,8 @@ struct cc_program {
     void *jit_library[CC_N_SINKS] = {};
     void *jit_kernel[CC_N_SINKS] = {};
     void *jit_kernel_centers = nullptr;  // CC_SINK_PARTS: the brick-centre pass of the same library
-    void *jit_columns_kernels[5] = {};   // CC_SINK_COLUMNS: centres, profiles, full walk, classify tiles, mass tiles (jit_kernel[]: the brick kernel)
+    void *jit_columns_kernels[7] = {};   // CC_SINK_COLUMNS: centres, profiles, full walk, classify / mass / pymcubes tiles, tile centres (jit_kernel[]: the brick kernel)
+    void *jit_parts_tile_kernels[4] = {};  // CC_SINK_PARTS: tile centres, classify / mass / pymcubes tiles
     cc_columns_meta jit_columns;
     cc_jit_cfg jit_cfg[CC_N_SINKS];
     size_t jit_smem[CC_N_SINKS] = {};  // dynamic shared memory of each specialised kernel
@@ -133,7 +134,7 @@ int cc_jit_launch_parts(const cc_program *prog, const cc_eval_args &a, uint32_t 
                         bool centers_only = false);
 int cc_jit_launch_columns(const cc_program *prog, const cc_eval_args &a, uint32_t n_bricks, int sm_count, void *stream, int dev_index,
                           int *n_launches);
-int cc_jit_launch_columns_tiles(const cc_program *prog, int sink_kind, const cc_eval_args &a, void *stream, int dev_index);
+int cc_jit_launch_tiles(const cc_program *prog, bool columns, int sink_kind, const cc_eval_args &a, void *stream, int dev_index, int *n_launches);
 int cc_jit_launch_render(const cc_program *prog, int sink, const cc_render_args &a, void *stream, int dev_index);
 cc_jit_cfg cc_jit_render_cfg(const cc_decoded &dec);
 #define CC_SINK_MASK_ALL ((1u << CC_N_SINKS) - 1u)

@@ -633,8 +633,10 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
         s << "    }\n};\n";
         s << "// the hierarchy sinks (blocks x linear tiles): the rest per cell, or the full walk for a tile with a flagged column\n"
           << "struct SceneTile {\n    SceneEval loop;\n    SceneFull full;\n    bool use_full;\n"
-          << "    __device__ __forceinline__ void locate(const cc_eval_args &a, unsigned block, const unsigned (&ix)[PTS], const unsigned (&iy)[PTS],\n"
-          << "                                           const unsigned (&iz)[PTS])\n    {\n        use_full = cc_col_locate<PTS>(a, block, ix, iy, iz, loop.cr);\n    }\n"
+          << "    __device__ __forceinline__ void locate(const cc_eval_args &a, unsigned tile, unsigned block, const unsigned (&ix)[PTS],\n"
+          << "                                           const unsigned (&iy)[PTS], const unsigned (&iz)[PTS])\n    {\n"
+          << "        use_full = cc_col_locate<PTS>(a, block, ix, iy, iz, loop.cr);\n"
+          << "        if (a.part_masks) loop.mask = full.mask = a.part_masks[tile];  // (cc_tile_centers_body)\n    }\n"
           << "    __device__ __forceinline__ void operator()" << sig << ", Val (&L)[G]) const\n    {\n"
           << "        if (use_full) full(gx, gy, gz, L);\n        else loop(gx, gy, gz, L);\n    }\n};\n";
         if (columns_meta) {
@@ -697,7 +699,7 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
           << "        const unsigned b = a.brick_list[i];\n"
           << "        SceneFull e{cc_cells + threadIdx.x, a.part_masks ? a.part_masks[b] : 0xffffffffu, nullptr};\n"
           << "        cc_kernel_body_bricks_at<PTS>(a, e, b);\n    }\n}\n";
-        const char *tile_sinks[2][2] = {{"classify", "CC_SINK_CLASSIFY"}, {"mass", "CC_SINK_MASS"}};
+        const char *tile_sinks[3][2] = {{"classify", "CC_SINK_CLASSIFY"}, {"mass", "CC_SINK_MASS"}, {"pymcubes", "CC_SINK_PYMCUBES"}};
         for (auto &ts : tile_sinks)
             s << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_columns_" << ts[0] << head
               << "    SceneTile e;\n    e.loop.sm = e.full.sm = cc_cells + threadIdx.x;\n    e.loop.mask = e.full.mask = 0xffffffffu;\n"
@@ -712,7 +714,10 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
             }
             s << "};\nextern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_columns_centers" << head
               << "    V pw[" << parts.n_parts << "];\n    SceneFull e{cc_cells + threadIdx.x, 0xffffffffu, pw};\n"
-              << "    cc_part_centers_body<" << parts.n_parts << ">(a, e, pw, cc_part_lipschitz);\n}\n";
+              << "    cc_part_centers_body<" << parts.n_parts << ">(a, e, pw, cc_part_lipschitz);\n}\n"
+              << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_columns_tile_centers" << head
+              << "    V pw[" << parts.n_parts << "];\n    SceneFull e{cc_cells + threadIdx.x, 0xffffffffu, pw};\n"
+              << "    cc_tile_centers_body<" << parts.n_parts << ", PTS>(a, e, pw, cc_part_lipschitz);\n}\n";
         }
     }
     if (parts_mode && !columns_mode) {
@@ -733,7 +738,21 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
           << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_part_centers(const cc_eval_args a)\n{\n"
           << "    extern __shared__ float4 cc_cells[];\n    V pw[" << parts.n_parts << "];\n"
           << "    SceneEval e{cc_cells + threadIdx.x, 0xffffffffu, pw};\n"
-          << "    cc_part_centers_body<" << parts.n_parts << ">(a, e, pw, cc_part_lipschitz);\n}\n";
+          << "    cc_part_centers_body<" << parts.n_parts << ">(a, e, pw, cc_part_lipschitz);\n}\n"
+          // the hierarchy sinks (blocks x linear tiles): the same masks per tile
+          << "struct ScenePartsTile {\n    SceneEval e;\n"
+          << "    __device__ __forceinline__ void locate(const cc_eval_args &a, unsigned tile, unsigned, const unsigned (&)[PTS], const unsigned (&)[PTS],\n"
+          << "                                           const unsigned (&)[PTS])\n    {\n        e.mask = a.part_masks[tile];\n    }\n"
+          << "    __device__ __forceinline__ void operator()(const V (&gx)[G], const V (&gy)[G], const V (&gz)[G], Val (&L)[G]) const { e(gx, gy, gz, L); }\n};\n"
+          << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_parts_tile_centers(const cc_eval_args a)\n{\n"
+          << "    extern __shared__ float4 cc_cells[];\n    V pw[" << parts.n_parts << "];\n"
+          << "    SceneEval e{cc_cells + threadIdx.x, 0xffffffffu, pw};\n"
+          << "    cc_tile_centers_body<" << parts.n_parts << ", PTS>(a, e, pw, cc_part_lipschitz);\n}\n";
+        const char *tile_sinks[3][2] = {{"classify", "CC_SINK_CLASSIFY"}, {"mass", "CC_SINK_MASS"}, {"pymcubes", "CC_SINK_PYMCUBES"}};
+        for (auto &ts : tile_sinks)
+            s << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_parts_" << ts[0] << "(const cc_eval_args a)\n{\n"
+              << "    extern __shared__ float4 cc_cells[];\n    ScenePartsTile t{SceneEval{cc_cells + threadIdx.x, 0xffffffffu, nullptr}};\n"
+              << "    cc_kernel_body<PTS, " << ts[1] << ">(a, t);\n}\n";
     }
     if (sink_mask & (1u << CC_SINK_POINTS))
         s << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_points"
@@ -1095,6 +1114,16 @@ static int load_cubin(cc_program *prog, int sink, const Cubin &bin, const cc_jit
             return CC_ERR_CUDA;
         }
         prog->jit_kernel_centers = (void *)centers;
+        const char *tiles[4] = {"cc_jit_parts_tile_centers", "cc_jit_parts_classify", "cc_jit_parts_mass", "cc_jit_parts_pymcubes"};
+        for (int k = 0; k < 4; ++k) {
+            cudaKernel_t kk = nullptr;
+            if ((ce = cudaLibraryGetKernel(&kk, lib, tiles[k])) != cudaSuccess) {
+                *err = std::string("cudaLibraryGetKernel(") + tiles[k] + "): " + cudaGetErrorString(ce);
+                release_library(lib);
+                return CC_ERR_CUDA;
+            }
+            prog->jit_parts_tile_kernels[k] = (void *)kk;
+        }
     }
     if (sink == CC_SINK_COLUMNS) {
         // what the kernels need from the host: the generator's own bookkeeping (a second, source-only pass)
@@ -1105,9 +1134,10 @@ static int load_cubin(cc_program *prog, int sink, const Cubin &bin, const cc_jit
             release_library(lib);
             return CC_ERR_CUDA;
         }
-        const char *extra[5] = {meta.centers ? "cc_jit_columns_centers" : nullptr, "cc_jit_columns_profiles", "cc_jit_columns_full",
-                                "cc_jit_columns_classify", "cc_jit_columns_mass"};
-        for (int k = 0; k < 5; ++k) {
+        const char *extra[7] = {meta.centers ? "cc_jit_columns_centers" : nullptr, "cc_jit_columns_profiles", "cc_jit_columns_full",
+                                "cc_jit_columns_classify", "cc_jit_columns_mass", "cc_jit_columns_pymcubes",
+                                meta.centers ? "cc_jit_columns_tile_centers" : nullptr};
+        for (int k = 0; k < 7; ++k) {
             cudaKernel_t kk = nullptr;
             if (extra[k] && (ce = cudaLibraryGetKernel(&kk, lib, extra[k])) != cudaSuccess) {
                 *err = std::string("cudaLibraryGetKernel(") + extra[k] + "): " + cudaGetErrorString(ce);
@@ -1293,30 +1323,46 @@ int cc_jit_launch_parts(const cc_program *prog, const cc_eval_args &a, uint32_t 
                                  (cudaStream_t)stream);
 }
 
-// the hierarchy sinks through the column kernels: column pass over every block's columns, then the ordered tile kernel
-// (the caller prepared tickets, tile status, a.columns and a.column_flags like cc_jit_launch / cc_jit_launch_columns)
-int cc_jit_launch_columns_tiles(const cc_program *prog, int sink_kind, const cc_eval_args &a, void *stream, int dev_index)
+// The hierarchy sinks (blocks x linear tiles) through the brick units' tile kernels: [tile centres ->] [column pass over
+// every block's columns ->] tile kernel.  `columns`: the unit of CC_SINK_COLUMNS, else the one of CC_SINK_PARTS.  The caller
+// prepared tickets and tile status like cc_jit_launch, a.part_masks (or null) and a.columns / a.column_flags.
+int cc_jit_launch_tiles(const cc_program *prog, bool columns, int sink_kind, const cc_eval_args &a, void *stream, int dev_index, int *n_launches)
 {
-    const int sink = CC_SINK_COLUMNS;
+    const int sink = columns ? CC_SINK_COLUMNS : CC_SINK_PARTS;
     const size_t smem = prog->jit_smem[sink];
     if (int e = ensure_smem_attr(prog, sink, dev_index)) return e;
+    void *const *extra = columns ? prog->jit_columns_kernels : prog->jit_parts_tile_kernels;
+    const int n_extra = columns ? 7 : 4;
     if (smem)
-        for (void *k : prog->jit_columns_kernels)
-            if (k) {
-                cudaError_t ce = cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        for (int k = 0; k < n_extra; ++k)
+            if (extra[k]) {
+                cudaError_t ce = cudaFuncSetAttribute((const void *)extra[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (ce != cudaSuccess) return (int)ce;
             }
     const uint32_t threads = (uint32_t)prog->jit_cfg[sink].threads;
-    const int axis = prog->jit_columns.axis;
-    const uint64_t ncol = (uint64_t)std::max(1u, a.n_blocks) * (axis == 2 ? (uint64_t)a.nx * a.ny : axis == 1 ? (uint64_t)a.nx * a.nz : (uint64_t)a.ny * a.nz);
     const uint64_t tiles = (uint64_t)a.tiles_per_block * a.n_blocks;
+    *n_launches = 0;
     if (tiles == 0) return 0;
     void *args[] = {(void *)&a};
-    cudaError_t ce = cudaLaunchKernel((const void *)prog->jit_columns_kernels[1], dim3((unsigned)((ncol + 2 * threads - 1) / (2 * threads))),
-                                      dim3(threads), args, smem, (cudaStream_t)stream);
-    if (ce != cudaSuccess) return (int)ce;
-    return (int)cudaLaunchKernel((const void *)prog->jit_columns_kernels[sink_kind == CC_SINK_CLASSIFY ? 3 : 4], dim3((unsigned)tiles), dim3(threads),
-                                 args, smem, (cudaStream_t)stream);
+    cudaError_t ce = cudaSuccess;
+    if (a.part_masks) {
+        ce = cudaLaunchKernel((const void *)(columns ? extra[6] : extra[0]), dim3((unsigned)((tiles + 2 * threads - 1) / (2 * threads))), dim3(threads),
+                              args, smem, (cudaStream_t)stream);
+        if (ce != cudaSuccess) return (int)ce;
+        ++*n_launches;
+    }
+    if (columns) {
+        const int axis = prog->jit_columns.axis;
+        const uint64_t ncol = (uint64_t)std::max(1u, a.n_blocks) * (axis == 2 ? (uint64_t)a.nx * a.ny : axis == 1 ? (uint64_t)a.nx * a.nz : (uint64_t)a.ny * a.nz);
+        ce = cudaLaunchKernel((const void *)extra[1], dim3((unsigned)((ncol + 2 * threads - 1) / (2 * threads))), dim3(threads), args, smem,
+                              (cudaStream_t)stream);
+        if (ce != cudaSuccess) return (int)ce;
+        ++*n_launches;
+    }
+    const int which = sink_kind == CC_SINK_CLASSIFY ? 0 : sink_kind == CC_SINK_MASS ? 1 : 2;
+    ++*n_launches;
+    return (int)cudaLaunchKernel((const void *)(columns ? extra[3 + which] : extra[1 + which]), dim3((unsigned)tiles), dim3(threads), args, smem,
+                                 (cudaStream_t)stream);
 }
 
 // CC_SINK_COLUMNS: [brick centres ->] column pass -> brick kernel [-> full walk of the flagged bricks]; the caller

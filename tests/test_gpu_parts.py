@@ -142,3 +142,45 @@ def test_interpreter_parts_equal_the_full_walk(cb, interpreter_only, scenes, nam
         want = np.array(cb.grid_eval(scene, corner, st, dims, x_offset=x_offset))
         _lib.check(L.cc_set_parts_mode(1))
         assert got.tobytes() == want.tobytes(), "%s frac %g" % (name, frac)
+
+
+# ---- the hierarchy sinks (blocks x linear tiles): a part mask per tile (cc_tile_centers_body) ----
+
+HIERARCHY_PART_SCENES = ["cfg_planetary", "cfg_menger_sponge", "dsdf3d_mirror_3d", "col_assembly"]
+
+
+@pytest.mark.parametrize("name", HIERARCHY_PART_SCENES)
+@pytest.mark.parametrize("columns", [0, 1])
+def test_hierarchy_sinks_with_tile_masks_are_identical(cb, scenes, name, columns):
+    """mass_properties (integer sums), subdivision (ordered leaf blocks) and the mesh (triangles of every leaf block)
+    with the per-tile part masks against the same calls without them, with and without the column kernels."""
+    import codecad_b200
+    from codecad_b200 import _lib
+    from codecad_b200.cl_util.buffer import ProgramBuffer
+    from codecad_b200.rendering import mesh
+    L = _lib.lib()
+    s = scenes[name]
+    scene = s.compiled()
+    a, b = np.array(s.box_a), np.array(s.box_b)
+    res = float(max(b - a)) / 120.0
+    scene.program_buffer().wait_specialized(ProgramBuffer.SINK_MASS | ProgramBuffer.SINK_CLASSIFY | ProgramBuffer.SINK_PYMCUBES)
+    old_columns = _lib.check(L.cc_set_columns_mode(columns))
+    results, launches = [], []
+    try:
+        for parts in (1, 0):
+            _lib.check(L.cc_set_parts_mode(parts))
+            n0 = _lib.counters()[0]
+            mp = codecad_b200.mass_properties(scene, res, 32)
+            sub = codecad_b200.subdivision(scene, res, grid_size=16)
+            vertices, block, _ = mesh.mesh_arrays(scene, 32)
+            launches.append(_lib.counters()[0] - n0)
+            results.append((mp.volume, tuple(mp.centroid), np.array(mp.inertia_tensor).tobytes(),
+                            [tuple(map(tuple, (blk[0], blk[1], blk[3]))) + (blk[2], blk[4]) for blk in sub[2]],
+                            np.array(vertices).tobytes(), np.array(block).tobytes()))
+    finally:
+        _lib.check(L.cc_set_parts_mode(1))
+        _lib.check(L.cc_set_columns_mode(old_columns))
+    assert launches[0] > launches[1], "the tile-centre passes did not run"
+    for k in range(6):
+        assert results[0][k] == results[1][k], "%s: result %d differs" % (name, k)
+    assert len(results[0][3]) > 0 and len(results[0][4]) > 0

@@ -218,3 +218,18 @@ def test_profiles_under_extrusions_are_column_invariant(scenes):
     src = _lib.specialize_source(scenes["x_gear3d"].words, 2, compile=False, sink_mask=256)
     src = src[0] if isinstance(src, tuple) else src
     assert "cc_jit_columns_centers" not in src                                     # no parts, no brick centres
+
+
+def test_brick_units_carry_the_tile_kernels(scenes):
+    """The part-culling and column units also serve the hierarchy sinks (blocks x linear tiles): tile-centre pass + the
+    three tile kernels (source only)."""
+    from codecad_b200 import _lib
+    src = _lib.specialize_source(scenes["dsdf3d_mirror_3d"].words, 2, compile=False, sink_mask=128)
+    src = src[0] if isinstance(src, tuple) else src
+    for kernel in ("cc_jit_parts(", "cc_jit_part_centers", "cc_jit_parts_tile_centers", "cc_jit_parts_classify", "cc_jit_parts_mass",
+                   "cc_jit_parts_pymcubes"):
+        assert kernel in src, kernel
+    src = _lib.specialize_source(scenes["cfg_planetary"].words, 2, compile=False, sink_mask=256)
+    src = src[0] if isinstance(src, tuple) else src
+    assert "cc_jit_columns_tile_centers" in src and "cc_jit_columns_pymcubes" in src
+    assert "a.part_masks[tile]" in src
