@@ -81,7 +81,7 @@ def test_view_angle_and_large_program(cb, scenes):
 
 # ---- scene-specialised renderers (NVRTC): same render body, same op library -> same bytes -------
 
-@pytest.mark.parametrize("name", NAMES + ["cfg_planetary", "cfg_menger_sponge"])
+@pytest.mark.parametrize("name", NAMES + ["cfg_planetary", "cfg_menger_sponge", "col_assembly", "dsdf3d_mirror_3d"])
 def test_specialised_renderers_bit_exact(cb, scenes, name):
     from codecad_b200 import CompiledScene
     from codecad_b200.cl_util.buffer import ProgramBuffer
@@ -100,6 +100,22 @@ def test_specialised_renderers_bit_exact(cb, scenes, name):
     # back on the interpreter: same picture
     assert not prog.use_specialized(False)
     assert np.array_equal(image.render_pixels(scene, size), got)
+
+
+@pytest.mark.parametrize("options", [1, 2])
+def test_specialised_ray_caster_of_an_assembly_with_options(cb, scenes, options):
+    """The specialised ray caster on the headline assembly with the false-colour and zebra options: the false-colour
+    picture counts the steps of every ray, so it would show a single evaluation that went differently."""
+    from codecad_b200.cl_util.buffer import ProgramBuffer
+    from codecad_b200.rendering import ray_caster
+    s = scenes["cfg_planetary"]
+    scene = s.compiled()
+    scene.program_buffer().specialize(1, ProgramBuffer.SINK_RAY)
+    size = (257, 190)
+    cam = ray_caster.get_camera_params(scene.bounding_box(), size, None)
+    got = ray_caster.render(scene, size=size, options=ray_caster.RenderOptions(options), *cam)
+    want = oracle_render.ray_cast(s.words, s.box_a, s.box_b, size, options=options)
+    assert np.array_equal(got, want)
 
 
 def test_specialised_segmented_ray_caster(cb, scenes):
