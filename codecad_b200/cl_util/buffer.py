@@ -200,6 +200,7 @@ class ProgramBuffer:
     SINK_POINTS = 64                # evaluate_points()
     SINK_PARTS = 128                  # dense float4 grids of an assembly: the part-culling pair of kernels
     SINK_COLUMNS = 256                # dense float4 grids of extrusions: the column kernels
+    SINK_TILES_PYMCUBES, SINK_TILES_CLASSIFY, SINK_TILES_MASS = 512, 1024, 2048   # the hierarchy sinks of such programs
 
     def specialize(self, points_per_thread=0, sinks=0):
         """Compile scene-specialised kernels for this program (NVRTC, seconds per sink); later

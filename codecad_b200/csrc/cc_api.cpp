@@ -488,10 +488,15 @@ int launch_columns(const cc_program *prog, cc_eval_args &a, uint64_t points, boo
 // The hierarchy sinks (ordered hit lists, mass sums, PyMCubes fields of blocks) through the brick units' tile
 // kernels: with `columns` the column pass covers the columns of every block of the launch and the tile kernel
 // runs the per-cell body; with `masks` a tile-centre pass writes a part mask per tile first.
+int tile_sink_of(int sink_kind)
+{
+    return sink_kind == CC_SINK_PYMCUBES ? CC_SINK_TILES_PYMCUBES : sink_kind == CC_SINK_CLASSIFY ? CC_SINK_TILES_CLASSIFY : CC_SINK_TILES_MASS;
+}
+
 int launch_tiles(int sink_kind, const cc_program *prog, cc_eval_args &a, uint64_t points, bool columns, bool masks)
 {
-    const cc_columns_meta &meta = prog->jit_columns;
-    const int sink = columns ? CC_SINK_COLUMNS : CC_SINK_PARTS;
+    const int sink = tile_sink_of(sink_kind);
+    const cc_columns_meta &meta = prog->jit_tiles[sink - CC_SINK_TILES_PYMCUBES];
     const uint32_t tile = (uint32_t)(prog->jit_cfg[sink].threads * prog->jit_cfg[sink].pts);
     const uint64_t cells = (uint64_t)a.nx * a.ny * a.nz;
     a.tiles_per_block = (uint32_t)((cells + tile - 1) / tile);
@@ -529,7 +534,7 @@ int launch_tiles(int sink_kind, const cc_program *prog, cc_eval_args &a, uint64_
         if (rc) return rc;
     }
     int n_launches = 0;
-    int e = cc_jit_launch_tiles(prog, columns, sink_kind, a, g.compute, g.index, &n_launches);
+    int e = cc_jit_launch_tiles(prog, sink, a, g.compute, g.index, &n_launches);
     if (e) return cuda_fail((cudaError_t)e, "tile kernel launch");
     g.launches += (uint64_t)n_launches;
     g.points += points;
@@ -567,13 +572,16 @@ int launch(int sink_kind, const cc_program *prog, cc_eval_args &a, uint64_t poin
     }
     if ((sink_kind == CC_SINK_CLASSIFY || sink_kind == CC_SINK_MASS || (sink_kind == CC_SINK_PYMCUBES && a.blocks)) && !a.points &&
         !cc_jit_is_segmented(prog->dec) && (uint64_t)a.nx * a.ny * a.nz >= 512) {
-        // blocks x linear tiles: the per-cell body of the column kernels and / or a part mask per tile
+        // blocks x linear tiles: the per-cell body of the column split and / or a part mask per tile (one unit per sink)
         cc_program *p = const_cast<cc_program *>(prog);
         const bool masks = g.parts_mode && prog->dec.parts.enabled && (!a.blocks || a.coord_max > 0.0f);
-        const bool cols = g.columns_mode && prog->dec.columns.enabled && axis_len(prog, a) >= 8 && jit_ready(p, CC_SINK_COLUMNS) &&
-                          (uint64_t)a.n_blocks * a.nx * a.ny * a.nz / axis_len(prog, a) * 16 * std::max(1u, p->jit_columns.n_values) <= (8ull << 30);
-        if (cols) return launch_tiles(sink_kind, prog, a, points, true, masks);
-        if (masks && jit_ready(p, CC_SINK_PARTS)) return launch_tiles(sink_kind, prog, a, points, false, true);
+        const bool cols = g.columns_mode && prog->dec.columns.enabled && axis_len(prog, a) >= 8;
+        if ((masks || cols) && jit_ready(p, tile_sink_of(sink_kind))) {
+            const cc_columns_meta &meta = p->jit_tiles[tile_sink_of(sink_kind) - CC_SINK_TILES_PYMCUBES];
+            const bool fits = (uint64_t)a.n_blocks * a.nx * a.ny * a.nz / axis_len(prog, a) * 16 * std::max(1u, meta.n_values) <= (8ull << 30);
+            // (the unit's per-cell body reads the column buffer whenever the program has a split: no columns, no unit)
+            if (!meta.columns || (cols && fits)) return launch_tiles(sink_kind, prog, a, points, meta.columns, masks);
+        }
     }
     if (parts_apply(sink_kind, prog, a)) {
         if (!cc_jit_is_segmented(prog->dec) && jit_ready(const_cast<cc_program *>(prog), CC_SINK_PARTS)) return launch_parts(prog, a, points, true);
@@ -1068,10 +1076,11 @@ int cc_program_specialize_wait(cc_program *prog, unsigned sink_mask, double *com
     if ((sink_mask & CC_SINK_MASK_ALL) == 0) sink_mask = 15u;
     // dense float4 grids of an assembly run on the part-culling kernels: "ready" includes them
     const bool small = !cc_jit_is_segmented(prog->dec);
-    // the brick units serve the four grid sinks: dense float4 grids by bricks, the others by tiles with masks / columns
-    const unsigned grid_sinks = (1u << CC_SINK_FLOAT4) | (1u << CC_SINK_PYMCUBES) | (1u << CC_SINK_CLASSIFY) | (1u << CC_SINK_MASS);
-    if (small && (sink_mask & grid_sinks) && prog->dec.parts.enabled && g.parts_mode) sink_mask |= 1u << CC_SINK_PARTS;
-    if (small && (sink_mask & grid_sinks) && prog->dec.columns.enabled && g.columns_mode) sink_mask |= 1u << CC_SINK_COLUMNS;
+    const bool parts = small && prog->dec.parts.enabled && g.parts_mode, cols = small && prog->dec.columns.enabled && g.columns_mode;
+    if ((sink_mask & (1u << CC_SINK_FLOAT4)) && parts) sink_mask |= 1u << CC_SINK_PARTS;
+    if ((sink_mask & (1u << CC_SINK_FLOAT4)) && cols) sink_mask |= 1u << CC_SINK_COLUMNS;
+    for (int k : {(int)CC_SINK_PYMCUBES, (int)CC_SINK_CLASSIFY, (int)CC_SINK_MASS})
+        if ((sink_mask & (1u << k)) && (parts || cols)) sink_mask |= 1u << tile_sink_of(k);
     int ready = 0;
     for (int k = 0; k < CC_N_SINKS; ++k) {
         if (!(sink_mask & (1u << k))) continue;

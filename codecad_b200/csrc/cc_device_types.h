@@ -33,7 +33,9 @@ enum cc_sink_kind {
     CC_SINK_RAY, CC_SINK_BITMAP,  // image renderers (cc_render.cuh), one point per thread
     CC_SINK_POINTS,               // FLOAT4 sink fed from a point list (cc_evaluate_points)
     CC_SINK_PARTS,                // FLOAT4 sink over 8 x 8 x 16 bricks with per-brick part masks (cc_jit.cpp)
-    CC_SINK_COLUMNS,              // FLOAT4 sink, one z-column of a brick per lane: what does not depend on z is evaluated once
+    CC_SINK_COLUMNS,              // FLOAT4 sink over bricks with the column-invariant micro-ops evaluated once per column
+    // the hierarchy sinks (blocks x linear tiles) with a part mask per tile and / or the column split: one unit each
+    CC_SINK_TILES_PYMCUBES, CC_SINK_TILES_CLASSIFY, CC_SINK_TILES_MASS,
     CC_N_SINKS
 };
 

@@ -91,6 +91,7 @@ struct cc_columns_meta {
     bool checks = false;    // some transform row is verified per column: flags, brick list and the full-walk kernel exist
     bool centers = false;   // the program has parts: the library has its own brick-centre kernel
     int axis = 2;           // the grid axis of the columns
+    bool columns = false;   // the unit has the column split (a tile unit of a program with parts only has not)
 };
 
 #define CC_MAX_DEVICES 16  // devices one process can drive (cc_init_devices)
@@ -105,8 +106,9 @@ struct cc_program {
     void *jit_library[CC_N_SINKS] = {};
     void *jit_kernel[CC_N_SINKS] = {};
     void *jit_kernel_centers = nullptr;  // CC_SINK_PARTS: the brick-centre pass of the same library
-    void *jit_columns_kernels[7] = {};   // CC_SINK_COLUMNS: centres, profiles, full walk, classify / mass / pymcubes tiles, tile centres (jit_kernel[]: the brick kernel)
-    void *jit_parts_tile_kernels[4] = {};  // CC_SINK_PARTS: tile centres, classify / mass / pymcubes tiles
+    void *jit_columns_kernels[3] = {};   // CC_SINK_COLUMNS: centres, profiles, full walk (jit_kernel[]: the brick kernel)
+    void *jit_tile_kernels[3][2] = {};   // CC_SINK_TILES_*: tile centres, column pass (jit_kernel[]: the tile kernel); null where not applicable
+    cc_columns_meta jit_tiles[3];        // CC_SINK_TILES_*: column buffer layout of that unit (n_values 0: no column split)
     cc_columns_meta jit_columns;
     cc_jit_cfg jit_cfg[CC_N_SINKS];
     size_t jit_smem[CC_N_SINKS] = {};  // dynamic shared memory of each specialised kernel
@@ -134,7 +136,7 @@ int cc_jit_launch_parts(const cc_program *prog, const cc_eval_args &a, uint32_t 
                         bool centers_only = false);
 int cc_jit_launch_columns(const cc_program *prog, const cc_eval_args &a, uint32_t n_bricks, int sm_count, void *stream, int dev_index,
                           int *n_launches);
-int cc_jit_launch_tiles(const cc_program *prog, bool columns, int sink_kind, const cc_eval_args &a, void *stream, int dev_index, int *n_launches);
+int cc_jit_launch_tiles(const cc_program *prog, int sink, const cc_eval_args &a, void *stream, int dev_index, int *n_launches);
 int cc_jit_launch_render(const cc_program *prog, int sink, const cc_render_args &a, void *stream, int dev_index);
 cc_jit_cfg cc_jit_render_cfg(const cc_decoded &dec);
 #define CC_SINK_MASK_ALL ((1u << CC_N_SINKS) - 1u)

@@ -243,10 +243,19 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
     // columns: the micro-ops that cannot see the grid's z (cc_program.cpp analyse_columns) become
     // one functor that runs once per (x, y) column and leaves its results in the column buffer, the rest another
     // that runs per cell and reads them there; a third is the full walk (brick centres, flagged bricks).
-    const bool columns_mode = (sink_mask & (1u << CC_SINK_COLUMNS)) != 0;
     const cc_columns &cols = dec.columns;
     const cc_parts &parts = dec.parts;
-    const bool parts_mode = (sink_mask & (1u << CC_SINK_PARTS)) != 0 || (columns_mode && parts.enabled);
+    // tile units (hierarchy sinks): the column split if the program has one, the part masks if it has parts
+    const int tile_kind = (sink_mask & (1u << CC_SINK_TILES_PYMCUBES)) ? (int)CC_SINK_PYMCUBES
+                        : (sink_mask & (1u << CC_SINK_TILES_CLASSIFY)) ? (int)CC_SINK_CLASSIFY
+                        : (sink_mask & (1u << CC_SINK_TILES_MASS)) ? (int)CC_SINK_MASS : -1;
+    const bool tiles = tile_kind >= 0;
+    if (tiles && !cols.enabled && !parts.enabled) {
+        *err = "tile units need a program with parts or column-invariant micro-ops";
+        return CC_ERR_INVALID_ARGUMENT;
+    }
+    const bool columns_mode = (sink_mask & (1u << CC_SINK_COLUMNS)) != 0 || (tiles && cols.enabled);
+    const bool parts_mode = (sink_mask & (1u << CC_SINK_PARTS)) != 0 || ((columns_mode || tiles) && parts.enabled);
     if (columns_mode && (!cols.enabled || pts != 2 || cfg.threads * pts != CC_BRICK_X * CC_BRICK_Y * CC_BRICK_Z)) {
         *err = "column kernels need a program with column-invariant micro-ops and 512 threads x 2 points";
         return CC_ERR_INVALID_ARGUMENT;
@@ -644,6 +653,7 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
             columns_meta->checks = !chk.str().empty();
             columns_meta->centers = parts_mode;
             columns_meta->axis = cols.axis;
+            columns_meta->columns = true;
         }
     } else if (!segmented) {
         s << "struct SceneEval {\n    float4 *sm;  // this thread's column of the value cells\n";
@@ -686,44 +696,9 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
         s << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_" << names[k]
           << "(const cc_eval_args a)\n{\n    extern __shared__ float4 cc_cells[];\n    SceneEval e{cc_cells + threadIdx.x};\n"
           << "    cc_kernel_body<PTS, " << sinks[k] << ">(a, e);\n}\n";
-    if (columns_mode) {
-        const std::string head = "(const cc_eval_args a)\n{\n    extern __shared__ float4 cc_cells[];\n";
-        s << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_columns_profiles" << head
-          << "    SceneAhead e;\n    e.sm = cc_cells + threadIdx.x;\n"
-          << "    cc_column_profiles_body<PTS>(a, e);\n}\n"
-          << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_columns" << head
-          << "    SceneEval e;\n    e.sm = cc_cells + threadIdx.x;\n    e.mask = a.part_masks ? a.part_masks[blockIdx.x] : 0xffffffffu;\n"
-          << "    cc_kernel_body_brick_columns<PTS>(a, e);\n}\n"
-          << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_columns_full" << head
-          << "    const unsigned n = *a.brick_count;\n    for (unsigned i = blockIdx.x; i < n; i += gridDim.x) {\n"
-          << "        const unsigned b = a.brick_list[i];\n"
-          << "        SceneFull e{cc_cells + threadIdx.x, a.part_masks ? a.part_masks[b] : 0xffffffffu, nullptr};\n"
-          << "        cc_kernel_body_bricks_at<PTS>(a, e, b);\n    }\n}\n";
-        const char *tile_sinks[3][2] = {{"classify", "CC_SINK_CLASSIFY"}, {"mass", "CC_SINK_MASS"}, {"pymcubes", "CC_SINK_PYMCUBES"}};
-        for (auto &ts : tile_sinks)
-            s << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_columns_" << ts[0] << head
-              << "    SceneTile e;\n    e.loop.sm = e.full.sm = cc_cells + threadIdx.x;\n    e.loop.mask = e.full.mask = 0xffffffffu;\n"
-              << "    e.full.pw = nullptr;\n    cc_kernel_body<PTS, " << ts[1] << ">(a, e);\n}\n";
-        if (parts_mode) {
-            s << "__constant__ float cc_part_lipschitz[" << parts.n_parts << "] = {";
-            for (uint32_t k = 0; k < parts.n_parts; ++k) {
-                const float l = parts.lipschitz[k];
-                s << (k ? ", " : "");
-                if (l - l != 0.0f || l > 1e30f) s << "1e30f";
-                else { char buf[48]; std::snprintf(buf, sizeof buf, "%af", (double)l); s << buf; }
-            }
-            s << "};\nextern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_columns_centers" << head
-              << "    V pw[" << parts.n_parts << "];\n    SceneFull e{cc_cells + threadIdx.x, 0xffffffffu, pw};\n"
-              << "    cc_part_centers_body<" << parts.n_parts << ">(a, e, pw, cc_part_lipschitz);\n}\n"
-              << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_columns_tile_centers" << head
-              << "    V pw[" << parts.n_parts << "];\n    SceneFull e{cc_cells + threadIdx.x, 0xffffffffu, pw};\n"
-              << "    cc_tile_centers_body<" << parts.n_parts << ", PTS>(a, e, pw, cc_part_lipschitz);\n}\n";
-        }
-    }
-    if (parts_mode && !columns_mode) {
-        // main kernel: one 8 x 8 x 16 brick per CTA, its mask decides which parts run; centre pass: a
-        // thread evaluates the centres of two bricks (one packed pair), derives the bricks' masks from
-        // the parts' values there and their Lipschitz constants, and writes them for the main kernel
+    const std::string head = "(const cc_eval_args a)\n{\n    extern __shared__ float4 cc_cells[];\n";
+    const char *tile_names[4][2] = {{"", ""}, {"pymcubes", "CC_SINK_PYMCUBES"}, {"classify", "CC_SINK_CLASSIFY"}, {"mass", "CC_SINK_MASS"}};
+    if (parts_mode) {
         s << "__constant__ float cc_part_lipschitz[" << parts.n_parts << "] = {";
         for (uint32_t k = 0; k < parts.n_parts; ++k) {
             const float l = parts.lipschitz[k];
@@ -731,28 +706,59 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
             if (l - l != 0.0f || l > 1e30f) s << "1e30f";  // no bound: lip * r dwarfs every distance, the part always stays
             else { char buf[48]; std::snprintf(buf, sizeof buf, "%af", (double)l); s << buf; }
         }
-        s << "};\n"
-          << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_parts(const cc_eval_args a)\n{\n"
-          << "    extern __shared__ float4 cc_cells[];\n    SceneEval e{cc_cells + threadIdx.x, a.part_masks[blockIdx.x], nullptr};\n"
+        s << "};\n";
+    }
+    // the functor of the full walk in this unit: SceneFull with the column split, the one SceneEval without
+    const std::string full_eval = columns_mode ? "SceneFull" : "SceneEval";
+    if (columns_mode)
+        s << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") " << (tiles ? "cc_jit_tile_profiles" : "cc_jit_columns_profiles") << head
+          << "    SceneAhead e;\n    e.sm = cc_cells + threadIdx.x;\n"
+          << "    cc_column_profiles_body<PTS>(a, e);\n}\n";
+    if (columns_mode && !tiles) {
+        s << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_columns" << head
+          << "    SceneEval e;\n    e.sm = cc_cells + threadIdx.x;\n    e.mask = a.part_masks ? a.part_masks[blockIdx.x] : 0xffffffffu;\n"
+          << "    cc_kernel_body_brick_columns<PTS>(a, e);\n}\n"
+          << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_columns_full" << head
+          << "    const unsigned n = *a.brick_count;\n    for (unsigned i = blockIdx.x; i < n; i += gridDim.x) {\n"
+          << "        const unsigned b = a.brick_list[i];\n"
+          << "        SceneFull e{cc_cells + threadIdx.x, a.part_masks ? a.part_masks[b] : 0xffffffffu, nullptr};\n"
+          << "        cc_kernel_body_bricks_at<PTS>(a, e, b);\n    }\n}\n";
+        if (parts_mode)
+            s << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_columns_centers" << head
+              << "    V pw[" << parts.n_parts << "];\n    SceneFull e{cc_cells + threadIdx.x, 0xffffffffu, pw};\n"
+              << "    cc_part_centers_body<" << parts.n_parts << ">(a, e, pw, cc_part_lipschitz);\n}\n";
+    }
+    if (parts_mode && !columns_mode && !tiles)
+        // main kernel: one 8 x 8 x 16 brick per CTA, its mask decides which parts run; centre pass: a
+        // thread evaluates the centres of two bricks (one packed pair), derives the bricks' masks from
+        // the parts' values there and their Lipschitz constants, and writes them for the main kernel
+        s << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_parts" << head
+          << "    SceneEval e{cc_cells + threadIdx.x, a.part_masks[blockIdx.x], nullptr};\n"
           << "    cc_kernel_body_bricks<PTS>(a, e);\n}\n"
-          << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_part_centers(const cc_eval_args a)\n{\n"
-          << "    extern __shared__ float4 cc_cells[];\n    V pw[" << parts.n_parts << "];\n"
+          << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_part_centers" << head
+          << "    V pw[" << parts.n_parts << "];\n"
           << "    SceneEval e{cc_cells + threadIdx.x, 0xffffffffu, pw};\n"
-          << "    cc_part_centers_body<" << parts.n_parts << ">(a, e, pw, cc_part_lipschitz);\n}\n"
-          // the hierarchy sinks (blocks x linear tiles): the same masks per tile
-          << "struct ScenePartsTile {\n    SceneEval e;\n"
-          << "    __device__ __forceinline__ void locate(const cc_eval_args &a, unsigned tile, unsigned, const unsigned (&)[PTS], const unsigned (&)[PTS],\n"
-          << "                                           const unsigned (&)[PTS])\n    {\n        e.mask = a.part_masks[tile];\n    }\n"
-          << "    __device__ __forceinline__ void operator()(const V (&gx)[G], const V (&gy)[G], const V (&gz)[G], Val (&L)[G]) const { e(gx, gy, gz, L); }\n};\n"
-          << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_parts_tile_centers(const cc_eval_args a)\n{\n"
-          << "    extern __shared__ float4 cc_cells[];\n    V pw[" << parts.n_parts << "];\n"
-          << "    SceneEval e{cc_cells + threadIdx.x, 0xffffffffu, pw};\n"
-          << "    cc_tile_centers_body<" << parts.n_parts << ", PTS>(a, e, pw, cc_part_lipschitz);\n}\n";
-        const char *tile_sinks[3][2] = {{"classify", "CC_SINK_CLASSIFY"}, {"mass", "CC_SINK_MASS"}, {"pymcubes", "CC_SINK_PYMCUBES"}};
-        for (auto &ts : tile_sinks)
-            s << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_parts_" << ts[0] << "(const cc_eval_args a)\n{\n"
-              << "    extern __shared__ float4 cc_cells[];\n    ScenePartsTile t{SceneEval{cc_cells + threadIdx.x, 0xffffffffu, nullptr}};\n"
-              << "    cc_kernel_body<PTS, " << ts[1] << ">(a, t);\n}\n";
+          << "    cc_part_centers_body<" << parts.n_parts << ">(a, e, pw, cc_part_lipschitz);\n}\n";
+    if (tiles) {
+        // the hierarchy sinks (blocks x linear tiles): a mask per tile, the per-cell body of the column split
+        const char *const *tn = tile_names[tile_kind == CC_SINK_PYMCUBES ? 1 : tile_kind == CC_SINK_CLASSIFY ? 2 : 3];
+        if (parts_mode)
+            s << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_tile_centers" << head
+              << "    V pw[" << parts.n_parts << "];\n    " << full_eval << " e{cc_cells + threadIdx.x, 0xffffffffu, pw};\n"
+              << "    cc_tile_centers_body<" << parts.n_parts << ", PTS>(a, e, pw, cc_part_lipschitz);\n}\n";
+        if (columns_mode) {
+            s << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_tile_" << tn[0] << head
+              << "    SceneTile e;\n    e.loop.sm = e.full.sm = cc_cells + threadIdx.x;\n    e.loop.mask = e.full.mask = 0xffffffffu;\n"
+              << "    e.full.pw = nullptr;\n    cc_kernel_body<PTS, " << tn[1] << ">(a, e);\n}\n";
+        } else {
+            s << "struct ScenePartsTile {\n    SceneEval e;\n"
+              << "    __device__ __forceinline__ void locate(const cc_eval_args &a, unsigned tile, unsigned, const unsigned (&)[PTS], const unsigned (&)[PTS],\n"
+              << "                                           const unsigned (&)[PTS])\n    {\n        e.mask = a.part_masks[tile];\n    }\n"
+              << "    __device__ __forceinline__ void operator()(const V (&gx)[G], const V (&gy)[G], const V (&gz)[G], Val (&L)[G]) const { e(gx, gy, gz, L); }\n};\n"
+              << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_tile_" << tn[0] << head
+              << "    ScenePartsTile t{SceneEval{cc_cells + threadIdx.x, 0xffffffffu, nullptr}};\n"
+              << "    cc_kernel_body<PTS, " << tn[1] << ">(a, t);\n}\n";
+        }
     }
     if (sink_mask & (1u << CC_SINK_POINTS))
         s << "extern \"C\" __global__ void __launch_bounds__(" << bounds << ") cc_jit_points"
@@ -1075,7 +1081,8 @@ static int load_cubin(cc_program *prog, int sink, const Cubin &bin, const cc_jit
                       std::string *err)
 {
     static const char *names[CC_N_SINKS] = {"cc_jit_float4", "cc_jit_pymcubes", "cc_jit_classify", "cc_jit_mass",
-                                            "cc_jit_ray_caster", "cc_jit_bitmap", "cc_jit_points", "cc_jit_parts", "cc_jit_columns"};
+                                            "cc_jit_ray_caster", "cc_jit_bitmap", "cc_jit_points", "cc_jit_parts", "cc_jit_columns",
+                                            "cc_jit_tile_pymcubes", "cc_jit_tile_classify", "cc_jit_tile_mass"};
     // A cubin is loaded once per process: programs with the same specialised source (the same scene
     // uploaded again) share the loaded library.  Loading costs milliseconds per megabyte of code.
     cudaLibrary_t lib = nullptr;
@@ -1114,39 +1121,39 @@ static int load_cubin(cc_program *prog, int sink, const Cubin &bin, const cc_jit
             return CC_ERR_CUDA;
         }
         prog->jit_kernel_centers = (void *)centers;
-        const char *tiles[4] = {"cc_jit_parts_tile_centers", "cc_jit_parts_classify", "cc_jit_parts_mass", "cc_jit_parts_pymcubes"};
-        for (int k = 0; k < 4; ++k) {
-            cudaKernel_t kk = nullptr;
-            if ((ce = cudaLibraryGetKernel(&kk, lib, tiles[k])) != cudaSuccess) {
-                *err = std::string("cudaLibraryGetKernel(") + tiles[k] + "): " + cudaGetErrorString(ce);
-                release_library(lib);
-                return CC_ERR_CUDA;
-            }
-            prog->jit_parts_tile_kernels[k] = (void *)kk;
-        }
     }
-    if (sink == CC_SINK_COLUMNS) {
+    const bool tile_unit = sink == CC_SINK_TILES_PYMCUBES || sink == CC_SINK_TILES_CLASSIFY || sink == CC_SINK_TILES_MASS;
+    if (sink == CC_SINK_COLUMNS || tile_unit) {
         // what the kernels need from the host: the generator's own bookkeeping (a second, source-only pass)
         std::string src;
         size_t sm = 0;
         cc_columns_meta meta;
+        meta.centers = prog->dec.parts.enabled;
         if (generate(prog->dec, cfg, 1u << sink, &src, &sm, err, &meta) != CC_OK) {
             release_library(lib);
             return CC_ERR_CUDA;
         }
-        const char *extra[7] = {meta.centers ? "cc_jit_columns_centers" : nullptr, "cc_jit_columns_profiles", "cc_jit_columns_full",
-                                "cc_jit_columns_classify", "cc_jit_columns_mass", "cc_jit_columns_pymcubes",
-                                meta.centers ? "cc_jit_columns_tile_centers" : nullptr};
-        for (int k = 0; k < 7; ++k) {
+        const char *extra[3] = {nullptr, nullptr, nullptr};
+        if (tile_unit) {
+            extra[0] = prog->dec.parts.enabled ? "cc_jit_tile_centers" : nullptr;
+            extra[1] = meta.columns ? "cc_jit_tile_profiles" : nullptr;
+        } else {
+            extra[0] = meta.centers ? "cc_jit_columns_centers" : nullptr;
+            extra[1] = "cc_jit_columns_profiles";
+            extra[2] = "cc_jit_columns_full";
+        }
+        void **dst = tile_unit ? prog->jit_tile_kernels[sink - CC_SINK_TILES_PYMCUBES] : prog->jit_columns_kernels;
+        for (int k = 0; k < (tile_unit ? 2 : 3); ++k) {
             cudaKernel_t kk = nullptr;
             if (extra[k] && (ce = cudaLibraryGetKernel(&kk, lib, extra[k])) != cudaSuccess) {
                 *err = std::string("cudaLibraryGetKernel(") + extra[k] + "): " + cudaGetErrorString(ce);
                 release_library(lib);
                 return CC_ERR_CUDA;
             }
-            prog->jit_columns_kernels[k] = (void *)kk;
+            dst[k] = (void *)kk;
         }
-        prog->jit_columns = meta;
+        if (tile_unit) prog->jit_tiles[sink - CC_SINK_TILES_PYMCUBES] = meta;
+        else prog->jit_columns = meta;
     }
     if (prog->jit_library[sink]) release_library((cudaLibrary_t)prog->jit_library[sink]);
     prog->jit_smem[sink] = smem_bytes;
@@ -1209,7 +1216,9 @@ static cc_jit_cfg cc_jit_brick_cfg(const cc_decoded &dec)
 static cc_jit_cfg cc_jit_cfg_for(const cc_decoded &dec, int sink, int pts)
 {
     if (sink == CC_SINK_RAY || sink == CC_SINK_BITMAP) return cc_jit_render_cfg(dec);
-    if (sink == CC_SINK_PARTS || sink == CC_SINK_COLUMNS) return cc_jit_brick_cfg(dec);
+    if (sink == CC_SINK_PARTS || sink == CC_SINK_COLUMNS || sink == CC_SINK_TILES_PYMCUBES || sink == CC_SINK_TILES_CLASSIFY ||
+        sink == CC_SINK_TILES_MASS)
+        return cc_jit_brick_cfg(dec);
     return cc_jit_default_cfg(dec, pts);
 }
 
@@ -1323,18 +1332,16 @@ int cc_jit_launch_parts(const cc_program *prog, const cc_eval_args &a, uint32_t 
                                  (cudaStream_t)stream);
 }
 
-// The hierarchy sinks (blocks x linear tiles) through the brick units' tile kernels: [tile centres ->] [column pass over
-// every block's columns ->] tile kernel.  `columns`: the unit of CC_SINK_COLUMNS, else the one of CC_SINK_PARTS.  The caller
-// prepared tickets and tile status like cc_jit_launch, a.part_masks (or null) and a.columns / a.column_flags.
-int cc_jit_launch_tiles(const cc_program *prog, bool columns, int sink_kind, const cc_eval_args &a, void *stream, int dev_index, int *n_launches)
+// The hierarchy sinks (blocks x linear tiles) through their tile unit (CC_SINK_TILES_*): [tile centres ->] [column pass
+// over every block's columns ->] tile kernel.  The caller prepared tickets and tile status like cc_jit_launch,
+// a.part_masks (or null) and a.columns / a.column_flags (or null).
+int cc_jit_launch_tiles(const cc_program *prog, int sink, const cc_eval_args &a, void *stream, int dev_index, int *n_launches)
 {
-    const int sink = columns ? CC_SINK_COLUMNS : CC_SINK_PARTS;
     const size_t smem = prog->jit_smem[sink];
     if (int e = ensure_smem_attr(prog, sink, dev_index)) return e;
-    void *const *extra = columns ? prog->jit_columns_kernels : prog->jit_parts_tile_kernels;
-    const int n_extra = columns ? 7 : 4;
+    void *const *extra = prog->jit_tile_kernels[sink - CC_SINK_TILES_PYMCUBES];
     if (smem)
-        for (int k = 0; k < n_extra; ++k)
+        for (int k = 0; k < 2; ++k)
             if (extra[k]) {
                 cudaError_t ce = cudaFuncSetAttribute((const void *)extra[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (ce != cudaSuccess) return (int)ce;
@@ -1346,23 +1353,21 @@ int cc_jit_launch_tiles(const cc_program *prog, bool columns, int sink_kind, con
     void *args[] = {(void *)&a};
     cudaError_t ce = cudaSuccess;
     if (a.part_masks) {
-        ce = cudaLaunchKernel((const void *)(columns ? extra[6] : extra[0]), dim3((unsigned)((tiles + 2 * threads - 1) / (2 * threads))), dim3(threads),
-                              args, smem, (cudaStream_t)stream);
+        ce = cudaLaunchKernel((const void *)extra[0], dim3((unsigned)((tiles + 2 * threads - 1) / (2 * threads))), dim3(threads), args, smem,
+                              (cudaStream_t)stream);
         if (ce != cudaSuccess) return (int)ce;
         ++*n_launches;
     }
-    if (columns) {
-        const int axis = prog->jit_columns.axis;
+    if (a.columns) {
+        const int axis = prog->jit_tiles[sink - CC_SINK_TILES_PYMCUBES].axis;
         const uint64_t ncol = (uint64_t)std::max(1u, a.n_blocks) * (axis == 2 ? (uint64_t)a.nx * a.ny : axis == 1 ? (uint64_t)a.nx * a.nz : (uint64_t)a.ny * a.nz);
         ce = cudaLaunchKernel((const void *)extra[1], dim3((unsigned)((ncol + 2 * threads - 1) / (2 * threads))), dim3(threads), args, smem,
                               (cudaStream_t)stream);
         if (ce != cudaSuccess) return (int)ce;
         ++*n_launches;
     }
-    const int which = sink_kind == CC_SINK_CLASSIFY ? 0 : sink_kind == CC_SINK_MASS ? 1 : 2;
     ++*n_launches;
-    return (int)cudaLaunchKernel((const void *)(columns ? extra[3 + which] : extra[1 + which]), dim3((unsigned)tiles), dim3(threads), args, smem,
-                                 (cudaStream_t)stream);
+    return (int)cudaLaunchKernel((const void *)prog->jit_kernel[sink], dim3((unsigned)tiles), dim3(threads), args, smem, (cudaStream_t)stream);
 }
 
 // CC_SINK_COLUMNS: [brick centres ->] column pass -> brick kernel [-> full walk of the flagged bricks]; the caller
@@ -1409,7 +1414,9 @@ int cc_jit_source(const cc_decoded &dec, int pts, unsigned sink_mask, std::strin
     if ((sink_mask & CC_SINK_MASK_ALL) == 0) sink_mask = 15u;
     if (sink_mask & ((1u << CC_SINK_RAY) | (1u << CC_SINK_BITMAP)))
         return generate(dec, cc_jit_render_cfg(dec), sink_mask, src, nullptr, err);
-    if (sink_mask & ((1u << CC_SINK_PARTS) | (1u << CC_SINK_COLUMNS))) return generate(dec, cc_jit_brick_cfg(dec), sink_mask, src, nullptr, err);
+    if (sink_mask & ((1u << CC_SINK_PARTS) | (1u << CC_SINK_COLUMNS) | (1u << CC_SINK_TILES_PYMCUBES) | (1u << CC_SINK_TILES_CLASSIFY) |
+                     (1u << CC_SINK_TILES_MASS)))
+        return generate(dec, cc_jit_brick_cfg(dec), sink_mask, src, nullptr, err);
     return generate(dec, cc_jit_default_cfg(dec, pts), sink_mask, src, nullptr, err);
 }
 

@@ -170,7 +170,7 @@ def test_airfoil_mass_properties_config(cb, scenes):
     interp = cb.mass_properties(scene, 0.25, 64)
     scene.program_buffer().specialize(0, ProgramBuffer.SINK_MASS)
     spec = cb.mass_properties(scene, 0.25, 64)
-    scene.program_buffer().specialize(0, ProgramBuffer.SINK_COLUMNS)
+    scene.program_buffer().specialize(0, ProgramBuffer.SINK_TILES_MASS)
     n0 = _lib.counters()[0]
     cols = cb.mass_properties(scene, 0.25, 64)
     n_cols = _lib.counters()[0] - n0

@@ -207,8 +207,7 @@ def test_profiles_under_extrusions_are_column_invariant(scenes):
     assert _lib.decode_program(scenes["cfg_airfoil"].words)[0].column_axis != 2     # the wing's span is not the grid's z
     src = _lib.specialize_source(scenes["cfg_planetary"].words, 2, compile=False, sink_mask=256)
     src = src[0] if isinstance(src, tuple) else src
-    for kernel in ("cc_jit_columns_centers", "cc_jit_columns_profiles", "cc_jit_columns(", "cc_jit_columns_full", "cc_jit_columns_mass",
-                   "cc_jit_columns_classify"):
+    for kernel in ("cc_jit_columns_centers", "cc_jit_columns_profiles", "cc_jit_columns(", "cc_jit_columns_full"):
         assert kernel in src, kernel
     ahead = src[src.index("struct SceneAhead"):src.index("struct SceneEval")]
     loop = src[src.index("struct SceneEval"):src.index("struct SceneTile")]
@@ -220,16 +219,23 @@ def test_profiles_under_extrusions_are_column_invariant(scenes):
     assert "cc_jit_columns_centers" not in src                                     # no parts, no brick centres
 
 
-def test_brick_units_carry_the_tile_kernels(scenes):
-    """The part-culling and column units also serve the hierarchy sinks (blocks x linear tiles): tile-centre pass + the
-    three tile kernels (source only)."""
+def test_tile_units_for_the_hierarchy_sinks(scenes):
+    """The hierarchy sinks (blocks x linear tiles) of a program with parts or a column split have a unit each: tile-centre
+    pass and / or column pass + the tile kernel (source only)."""
     from codecad_b200 import _lib
-    src = _lib.specialize_source(scenes["dsdf3d_mirror_3d"].words, 2, compile=False, sink_mask=128)
+    TILES_PYMCUBES, TILES_CLASSIFY, TILES_MASS = 1 << 9, 1 << 10, 1 << 11
+    src = _lib.specialize_source(scenes["dsdf3d_mirror_3d"].words, 2, compile=False, sink_mask=TILES_CLASSIFY)
     src = src[0] if isinstance(src, tuple) else src
-    for kernel in ("cc_jit_parts(", "cc_jit_part_centers", "cc_jit_parts_tile_centers", "cc_jit_parts_classify", "cc_jit_parts_mass",
-                   "cc_jit_parts_pymcubes"):
+    assert "cc_jit_tile_centers" in src and "cc_jit_tile_classify" in src and "cc_jit_tile_profiles" not in src   # parts, no columns
+    src = _lib.specialize_source(scenes["cfg_airfoil"].words, 2, compile=False, sink_mask=TILES_MASS)
+    src = src[0] if isinstance(src, tuple) else src
+    assert "cc_jit_tile_profiles" in src and "cc_jit_tile_mass" in src and "cc_jit_tile_centers" not in src        # columns, no parts
+    src = _lib.specialize_source(scenes["cfg_planetary"].words, 2, compile=False, sink_mask=TILES_PYMCUBES)
+    src = src[0] if isinstance(src, tuple) else src
+    for kernel in ("cc_jit_tile_centers", "cc_jit_tile_profiles", "cc_jit_tile_pymcubes"):
         assert kernel in src, kernel
-    src = _lib.specialize_source(scenes["cfg_planetary"].words, 2, compile=False, sink_mask=256)
-    src = src[0] if isinstance(src, tuple) else src
-    assert "cc_jit_columns_tile_centers" in src and "cc_jit_columns_pymcubes" in src
     assert "a.part_masks[tile]" in src
+    # the dense-grid units carry no tile kernels (compile time)
+    src = _lib.specialize_source(scenes["cfg_planetary"].words, 2, compile=False, sink_mask=128)
+    src = src[0] if isinstance(src, tuple) else src
+    assert "cc_jit_parts(" in src and "cc_jit_part_centers" in src and "cc_jit_tile" not in src
