@@ -42,5 +42,5 @@ def load_scenes():
 
 
 ALL_NAMES = sorted(load_scenes())
-COLUMN_NAMES = [n for n in ALL_NAMES if n.startswith("col_")]
+COLUMN_NAMES = [n for n in ALL_NAMES if n.startswith(("col_", "colr_"))]
 FOREST_NAMES = [n for n in ALL_NAMES if n.startswith("forest_") or n.startswith("cfg_synthetic")]

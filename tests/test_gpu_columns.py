@@ -43,8 +43,9 @@ def _box(s):
 def test_which_scenes_have_columns(scenes):
     from codecad_b200 import _lib
     have = sorted(n for n in ALL_NAMES if _lib.decode_program(scenes[n].words)[0].column_invariant_percent)
-    assert set(COLUMN_SCENES) - {"col_star_oblique", "col_repeated"} <= set(have)
-    assert not {"col_star_oblique", "col_repeated"} & set(have)     # an oblique extrusion axis; a repetition (reads every axis)
+    none = {"col_star_oblique", "col_repeated", "colr_10", "colr_23"}
+    assert set(COLUMN_SCENES) - none <= set(have)
+    assert not none & set(have)     # an oblique extrusion axis; a repetition (reads every axis); solids in general position
     assert _lib.decode_program(scenes["cfg_planetary"].words)[0].column_invariant_percent >= 40
     assert _lib.decode_program(scenes["cfg_csg_example"].words)[0].column_invariant_percent == 0
     assert _lib.decode_program(scenes["cfg_planetary"].words)[0].column_axis == 2       # gears extruded along z
@@ -131,7 +132,7 @@ def test_columns_serve_the_launch(cb, scenes):
 # ---- the hierarchy sinks through the column kernels (blocks x linear tiles) ----
 
 HIERARCHY_SCENES = ["cfg_airfoil", "cfg_planetary", "x_gear3d", "col_star_x", "col_star_half_turn", "col_crossed_extrusions", "col_assembly",
-                    "col_profile_and_sphere", "col_two_levels"]
+                    "col_profile_and_sphere", "col_two_levels", "colr_01", "colr_05", "colr_08", "colr_12", "colr_19", "colr_21", "colr_22"]
 
 
 @pytest.mark.parametrize("name", HIERARCHY_SCENES)

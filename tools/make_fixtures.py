@@ -129,6 +129,82 @@ def column_scenes():
     out["col_repeated"] = codecad.shapes.unsafe.Repetition(s.circle(d=1.2).extruded(1), (2.5, 2.5, None)) & s.box(9, 9, 3)
     out["col_assembly"] = s.union([gear.extruded(1).translated(-4, 0, 0), hexagon.extruded(2).translated(4, 0, 0.5),
                                    star.scaled(0.7).extruded(1.5).rotated((0, 0, 1), 10).translated(0, 5, 0), s.sphere(d=2).translated(0, -5, 0)])
+    out.update(random_column_scenes())
+    return out
+
+
+def random_column_scenes(n=24, seed=4242):
+    """Random compositions for the column analysis: 2-D shapes under random stacks of mirror / symmetry / offset / shell /
+    rotation / translation / scaling and CSG, extruded, turned by multiples of 90 degrees about random axes (half and
+    quarter turns leave rounding residue in the matrices) or by arbitrary angles about z, then combined with other such
+    solids and with spheres / boxes in general position."""
+    rng = random.Random(seed)
+
+    def shape2d(depth=0):
+        k = rng.randrange(6)
+        if k == 0:
+            sh = s.rectangle(rng.uniform(1, 4), rng.uniform(1, 4))
+        elif k == 1:
+            sh = s.circle(d=rng.uniform(1, 4))
+        elif k == 2:
+            sh = s.regular_polygon2d(rng.randrange(3, 9), r=rng.uniform(1, 2.5))
+        elif k == 3:
+            m = rng.randrange(5, 9)
+            pts = [(math.cos(2 * math.pi * i / m) * rng.uniform(1, 3), math.sin(2 * math.pi * i / m) * rng.uniform(1, 3)) for i in range(m)]
+            sh = s.polygon2d(pts)
+        elif k == 4:
+            sh = s.gears.InvoluteGear(rng.randrange(7, 15), rng.uniform(0.4, 0.8))
+        else:
+            sh = s.rectangle(rng.uniform(2, 5), rng.uniform(0.5, 1.5))
+        for _ in range(rng.randrange(0, 3)):
+            t = rng.randrange(7)
+            if t == 0:
+                sh = sh.translated(rng.uniform(-2, 2), rng.uniform(-2, 2))
+            elif t == 1:
+                sh = sh.rotated(rng.choice([90, 180, 270, rng.uniform(0, 360)]))
+            elif t == 2:
+                sh = sh.offset(rng.uniform(0.05, 0.3))
+            elif t == 3:
+                sh = sh.shell(rng.uniform(0.1, 0.3))
+            elif t == 4:
+                sh = sh.mirrored_x()
+            elif t == 5:
+                sh = sh.translated(rng.uniform(1, 3), 0).symmetrical_x()
+            else:
+                sh = sh.scaled(rng.uniform(0.6, 1.5))
+        if depth < 2 and rng.random() < 0.5:
+            other = shape2d(depth + 1).translated(rng.uniform(-1.5, 1.5), rng.uniform(-1.5, 1.5))
+            c = rng.randrange(3)
+            sh = sh + other if c == 0 else (sh & other.scaled(2)) if c == 1 else sh - other.scaled(0.5)
+        return sh
+
+    def solid():
+        sh = shape2d().extruded(rng.uniform(1, 4))
+        k = rng.randrange(5)
+        if k == 0:
+            sh = sh.rotated((0, 0, 1), rng.uniform(0, 360))
+        elif k == 1:
+            sh = sh.rotated(rng.choice([(1, 0, 0), (0, 1, 0), (0, 0, 1)]), rng.choice([90, 180, 270]))
+        elif k == 2:
+            sh = sh.rotated((1, 0, 0), 180).rotated((0, 0, 1), rng.uniform(0, 360))
+        return sh.translated(rng.uniform(-3, 3), rng.uniform(-3, 3), rng.uniform(-1, 1))
+
+    out = {}
+    for i in range(n):
+        sh = solid()
+        for _ in range(rng.randrange(0, 3)):
+            k = rng.randrange(5)
+            if k == 0:
+                sh = sh + solid()
+            elif k == 1:
+                sh = sh - solid().scaled(0.7)
+            elif k == 2:
+                sh = sh & s.sphere(d=rng.uniform(5, 9)).translated(rng.uniform(-1, 1), rng.uniform(-1, 1), 0)
+            elif k == 3:
+                sh = sh + s.box(rng.uniform(1, 2)).rotated((1, 2, 3), rng.uniform(0, 90)).translated(rng.uniform(-4, 4), rng.uniform(-4, 4), 0)
+            else:
+                sh = s.union([sh, solid(), solid()])
+        out["colr_%02d" % i] = sh
     return out
 
 
