@@ -9,7 +9,8 @@ import oracle
 from scenes import ALL_NAMES
 
 pytestmark = pytest.mark.gpu
-PART_SCENES = ["cfg_planetary", "cfg_menger_sponge", "dsdf3d_mirror_3d", "dsdf2d_mirror_2d", "dsdf2d_rotated_pattern_2d"]
+PART_SCENES = ["cfg_planetary", "cfg_menger_sponge", "dsdf3d_mirror_3d", "dsdf2d_mirror_2d", "dsdf2d_rotated_pattern_2d",
+               "col_assembly", "colr_08", "colr_19", "colr_21"]    # (the last four: random unions of extruded solids, tools/make_fixtures.py --columns)
 
 
 @pytest.fixture(scope="module")
@@ -146,7 +147,7 @@ def test_interpreter_parts_equal_the_full_walk(cb, interpreter_only, scenes, nam
 
 # ---- the hierarchy sinks (blocks x linear tiles): a part mask per tile (cc_tile_centers_body) ----
 
-HIERARCHY_PART_SCENES = ["cfg_planetary", "cfg_menger_sponge", "dsdf3d_mirror_3d", "col_assembly"]
+HIERARCHY_PART_SCENES = ["cfg_planetary", "cfg_menger_sponge", "dsdf3d_mirror_3d", "col_assembly", "colr_08", "colr_21"]
 
 
 @pytest.mark.parametrize("name", HIERARCHY_PART_SCENES)
