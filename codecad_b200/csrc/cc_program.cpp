@@ -346,7 +346,7 @@ bool sigma_max(const float *m, double *out)
 // multiplication by zero but an omitted term — the remaining terms never see that operand:
 //   transforms          row r depends on what its non-zero coefficients read
 //   2-D primitives      read x, y; write (nx, ny, 0, d)
-//   mirror/offset/nop   component-wise
+//   mirror/offset/nop   component-wise; repetition too; circular repetition turns (x, y), passes z
 //   everything else     any dependent input makes every output component dependent
 static void analyse_columns_along(const std::vector<uint32_t> &code, int axis, cc_columns *out)
 {
@@ -410,6 +410,10 @@ static void analyse_columns_along(const std::vector<uint32_t> &code, int axis, c
         case MOP_GEAR: o.dep = (dl & (X | Y)) ? (X | Y | W) : 0; o.cost = 200; break;
         case MOP_POLYGON: o.dep = (dl & (X | Y)) ? (X | Y | W) : 0; o.cost = 12u * (uint32_t)fl(pc, 0) + 30u; break;
         case MOP_SYM_FROM: o.dep = (uint8_t)(dl | ((ds & X) ? X : 0)); o.cost = 2; break;
+        // unsafe.cl:1-23: repetition works component by component; the circular one turns (x, y) and passes z (and w) on
+        case MOP_REPETITION: o.dep = (uint8_t)(dl & (X | Y | Z)); o.cost = 30; break;
+        case MOP_CREP_TO: o.dep = (uint8_t)(((dl & (X | Y)) ? (X | Y) : 0) | (dl & Z)); o.cost = 60; break;
+        case MOP_CREP_FROM: o.dep = (uint8_t)((((dl | ds) & (X | Y)) ? (X | Y) : 0) | (dl & (Z | W))); o.cost = 60; break;
         case MOP_PRIM_CIRCLE: case MOP_PRIM_RECT: case MOP_PRIM_CIRCLE_M: case MOP_PRIM_RECT_M: o.dep = ALL; o.cost = 100; break;
         default:
             o.dep = (dl | ds) ? ALL : 0;

@@ -127,6 +127,9 @@ def column_scenes():
         .translated(0, 0, -1).scaled(1.5)
     out["col_revolved_and_extruded"] = s.rectangle(1, 2).translated(3, 0).revolved() + star.scaled(0.6).extruded(5)
     out["col_repeated"] = codecad.shapes.unsafe.Repetition(s.circle(d=1.2).extruded(1), (2.5, 2.5, None)) & s.box(9, 9, 3)
+    out["col_bolt_circle"] = hexagon.scaled(1.6).extruded(1) - codecad.shapes.unsafe.CircularRepetition(s.circle(d=0.9).translated(2.6, 0).extruded(3), 6)
+    out["col_hole_grid"] = s.rectangle(9, 7).extruded(1.2) - codecad.shapes.unsafe.Repetition(s.circle(d=0.8).extruded(4), (1.5, 1.5, None)) \
+        + star.scaled(0.4).extruded(3).translated(0, 0, 1)
     out["col_assembly"] = s.union([gear.extruded(1).translated(-4, 0, 0), hexagon.extruded(2).translated(4, 0, 0.5),
                                    star.scaled(0.7).extruded(1.5).rotated((0, 0, 1), 10).translated(0, 5, 0), s.sphere(d=2).translated(0, -5, 0)])
     out.update(random_column_scenes())
