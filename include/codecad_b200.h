@@ -144,7 +144,10 @@ int cc_set_forest_mode(int mode);
  * components of an assembly, SURVEY.md 8(d) config C4 — gets, next to its specialised kernels, a pair
  * that evaluates dense float4 grids brick by brick and skips in every brick the parts that provably
  * cannot be the nearest there (Lipschitz bound of every part from the brick centre; csrc/cc_body.cuh).
- * Bit-identical to the full evaluation.  mode 1 = on (default; CODECAD_B200_PARTS), 0 = off. */
+ * Bit-identical to the full evaluation.  The interpreter kernels apply the same masks (a program is culled from its
+ * first launch, not from the arrival of its specialised kernels), and the hierarchy kernels — subdivision,
+ * mass_properties, the PyMCubes-layout fields of the mesh export — get a mask per tile of 1024 consecutive cells the
+ * same way.  mode 1 = on (default; CODECAD_B200_PARTS), 0 = off. */
 int cc_set_parts_mode(int mode);
 /* Columns.  On a dense grid the grid's z axis is the z axis of the program's point, and a 2-D profile
  * under an extrusion (transform, polygon2d, involute gear, their CSG: shapes/simple2d.cl, polygons2d.cl,
