@@ -719,7 +719,6 @@ def run_ours(args):
 
     prog = ProgramBuffer(scene.words)
     pinfo = prog.info
-    out = Buffer(FLOAT4, (nx, n, n))   # slab output stays resident in HBM
     c3 = _lib.f3(corner)
     # Tiered execution is the library default: the interpreter serves launches while the
     # scene-specialised kernel compiles in the background.  The headline is measured in steady
@@ -732,9 +731,19 @@ def run_ours(args):
     columns_active = (bool(n_ready) and int(pinfo.column_invariant_percent) > 0 and os.environ.get("CODECAD_B200_COLUMNS", "1") != "0"
                       and (nx if int(pinfo.column_axis) == 0 else n) >= 8)
     kernel_key = "columns" if columns_active else "parts" if parts_active else tier
+    # Kernel-only leg at N > 1: equal x-slabs.  (CODECAD_B200_BENCH_BALANCED_SLABS=1 cuts slabs of about equal WORK
+    # instead — codecad_b200.grid_eval.balanced_slabs, the brick masks' cost estimate; on the planetary grid the
+    # estimate moves the cuts by one layer of eight planes at most, so it is not the default.  The end-to-end leg
+    # keeps equal slabs either way: it is bound by the bytes each rank copies to its host.)
+    slabs = [ge.slab_range(n, r, world) for r in range(world)]
+    if world > 1 and parts_active and os.environ.get("CODECAD_B200_BENCH_BALANCED_SLABS", "0") == "1":
+        slabs = ge.balanced_slabs(prog, corner, step, (n, n, n), world)
+    kx0, kx1 = slabs[rank]
+    knx = kx1 - kx0
+    out = Buffer(FLOAT4, (max(nx, knx), n, n))   # slab output stays resident in HBM
 
     def kernel_step():
-        _lib.check(L.cc_grid_eval(prog.handle, c3, float(step), nx, n, n, x0, 0, out.device_ptr, None))
+        _lib.check(L.cc_grid_eval(prog.handle, c3, float(step), knx, n, n, kx0, 0, out.device_ptr, None))
 
     def timed(fn, steps):
         e0, e1 = ctypes.c_void_p(), ctypes.c_void_p()
@@ -1011,7 +1020,10 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "Gpts/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(n, world), "clocks": clk, "e2e": e2e,
+        "config": dict(workload_config(n, world), x_slabs=[list(sl) for sl in slabs],
+                       x_slab_rule=("equal work by the brick masks' cost estimate (cc_grid_eval_cost_profile)" if slabs != [
+                           ge.slab_range(n, r, world) for r in range(world)] else "equal plane counts")),
+        "clocks": clk, "e2e": e2e,
         "gpu_launches": launches_total, "roofline": roofline, "cpu_baseline": cpu,
         "tier": tier, "specialize_s": specialize_s, "interpreter_tier": interp, "mass_properties": mass, "subdivision": subdiv, "mesh_export": mesh,
         "ray_caster": rays, "polygon2d": outline,

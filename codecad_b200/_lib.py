@@ -70,6 +70,7 @@ SIGNATURES = {
     "cc_set_forest_mode": (_I, [_I]),
     "cc_set_parts_mode": (_I, [_I]),
     "cc_set_columns_mode": (_I, [_I]),
+    "cc_grid_eval_cost_profile": (_I, [_V, c_float_p, ctypes.c_float, _U, _U, _U, _U, ctypes.POINTER(ctypes.c_double), _U]),
     "cc_program_get_forest_info": (_I, [_V, c_u32_p]),
     "cc_program_specialize_wait": (_I, [_V, _U, ctypes.POINTER(ctypes.c_double)]),
     "cc_specialize_source": (_I, [c_float_p, _U, _I, _U, ctypes.c_char_p, _U, _I, ctypes.POINTER(ctypes.c_uint64)]),

@@ -1042,6 +1042,53 @@ int cc_set_forest_mode(int mode)
     return old;
 }
 
+int cc_grid_eval_cost_profile(const cc_program *prog, const float corner[3], float step, uint32_t nx, uint32_t ny, uint32_t nz,
+                              uint32_t x_offset, double *layer_cost, uint32_t n_layers)
+{
+    NEED_INIT();
+    if (!prog || !corner || !layer_cost) return fail(CC_ERR_INVALID_ARGUMENT, "null argument");
+    int rc = check_dims(nx, ny, nz);
+    if (rc) return rc;
+    const uint32_t nbx = (nx + CC_BRICK_X - 1) / CC_BRICK_X, nby = (ny + CC_BRICK_Y - 1) / CC_BRICK_Y, nbz = (nz + CC_BRICK_Z - 1) / CC_BRICK_Z;
+    if (n_layers != nbx) return fail(CC_ERR_INVALID_ARGUMENT, "one cost per layer of 8 x-planes: n_layers must be ceil(nx / 8)");
+    const cc_parts &parts = prog->dec.parts;
+    const uint64_t per_layer = (uint64_t)nby * nbz, nb = per_layer * nbx;
+    if (!g.parts_mode || !parts.enabled || parts.table.empty() || nb >= (1ull << 31)) {
+        for (uint32_t i = 0; i < n_layers; ++i) layer_cost[i] = (double)per_layer;  // nothing known: every layer the same
+        return CC_OK;
+    }
+    cc_eval_args a;
+    FILL_COMMON(a, prog);
+    a.cx = corner[0]; a.cy = corner[1]; a.cz = corner[2]; a.step = step;
+    a.nx = nx; a.ny = ny; a.nz = nz; a.x_offset = x_offset; a.n_blocks = 1;
+    if ((rc = prepare_part_masks(prog, a, nb))) return rc;
+    int e;
+    cc_program *p = const_cast<cc_program *>(prog);
+    if (!cc_jit_is_segmented(prog->dec) && jit_ready(p, CC_SINK_PARTS)) {
+        e = cc_jit_launch_parts(prog, a, (uint32_t)nb, g.compute, g.index, true);
+    } else {
+        const uint32_t *table = nullptr;
+        if ((rc = parts_on_device(prog, &table))) return rc;
+        e = cc_launch_parts_interp(a, table, (uint32_t)nb, g.compute, true);
+    }
+    if (e) return cuda_fail((cudaError_t)e, "brick-centre kernel launch");
+    // weights: a brick costs its set-up and stores plus the micro-ops of the parts it keeps
+    cc_layer_weights w;
+    w.base = 12.0f;
+    for (int k = 0; k < 32; ++k) w.part[k] = 0.0f;
+    for (int part : parts.part_of_op)
+        if (part >= 0 && part < 32) w.part[part] += 1.0f;
+    double *d_cost = nullptr;
+    CU(cudaMallocAsync((void **)&d_cost, (size_t)n_layers * sizeof(double), g.compute));
+    e = cc_launch_layer_cost(a.part_masks, n_layers, (uint32_t)per_layer, w, d_cost, g.compute);
+    cudaError_t ce = e ? (cudaError_t)e : cudaMemcpyAsync(layer_cost, d_cost, (size_t)n_layers * sizeof(double), cudaMemcpyDeviceToHost, g.compute);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(g.compute);
+    cudaFreeAsync(d_cost, g.compute);
+    if (ce != cudaSuccess) return cuda_fail(ce, "layer cost kernel");
+    g.launches += 2;
+    return CC_OK;
+}
+
 int cc_set_columns_mode(int mode)
 {
     const int old = g.columns_mode;

@@ -184,7 +184,13 @@ int cc_launch_forest(const cc_eval_args &a, const cc_forest_launch &f, uint32_t 
 
 // part culling on the interpreter tier (cc_parts.cu): brick-centre pass + one CTA per quarter brick
 size_t cc_parts_smem_bytes(uint32_t n_slots, uint32_t code_words, int pts);
-int cc_launch_parts_interp(const cc_eval_args &a, const uint32_t *d_table, uint32_t n_bricks, void *stream);
+int cc_launch_parts_interp(const cc_eval_args &a, const uint32_t *d_table, uint32_t n_bricks, void *stream, bool centers_only = false);
+struct cc_layer_weights {
+    float base;      // per brick
+    float part[32];  // per part a brick keeps
+};
+int cc_launch_layer_cost(const uint32_t *d_masks, uint32_t n_layers, uint32_t bricks_per_layer, const cc_layer_weights &w, double *d_out,
+                         void *stream);
 
 // hierarchy helper kernels
 struct cc_level_geom {

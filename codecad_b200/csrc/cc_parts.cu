@@ -115,7 +115,41 @@ size_t cc_parts_smem_bytes(uint32_t n_slots, uint32_t code_words, int pts)
     return (size_t)n_slots * pts * CC_THREADS * sizeof(float4) + (size_t)code_words * 4;
 }
 
-int cc_launch_parts_interp(const cc_eval_args &a, const uint32_t *d_table, uint32_t n_bricks, void *stream)
+// cost of every brick layer (8 x-planes) of a dense grid from its bricks' part masks: sum over the bricks of the layer of
+// base + sum of the weights of the parts the brick keeps (load balancing of x-slabs, cc_grid_eval_cost_profile)
+__global__ void __launch_bounds__(256) cc_layer_cost_kernel(const uint32_t *__restrict__ masks, uint32_t bricks_per_layer, cc_layer_weights w,
+                                                            double *__restrict__ out)
+{
+    __shared__ double s_sum[256];
+    const uint32_t *m = masks + (size_t)blockIdx.x * bricks_per_layer;
+    double sum = 0.0;
+    for (uint32_t i = threadIdx.x; i < bricks_per_layer; i += 256) {
+        uint32_t bits = m[i];
+        float c = w.base;
+        while (bits) {
+            c += w.part[__ffs((int)bits) - 1];
+            bits &= bits - 1u;
+        }
+        sum += (double)c;
+    }
+    s_sum[threadIdx.x] = sum;
+    __syncthreads();
+    for (int d = 128; d > 0; d >>= 1) {
+        if ((int)threadIdx.x < d) s_sum[threadIdx.x] += s_sum[threadIdx.x + d];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = s_sum[0];
+}
+
+int cc_launch_layer_cost(const uint32_t *d_masks, uint32_t n_layers, uint32_t bricks_per_layer, const cc_layer_weights &w, double *d_out,
+                         void *stream)
+{
+    if (n_layers == 0) return 0;
+    cc_layer_cost_kernel<<<n_layers, 256, 0, (cudaStream_t)stream>>>(d_masks, bricks_per_layer, w, d_out);
+    return (int)cudaGetLastError();
+}
+
+int cc_launch_parts_interp(const cc_eval_args &a, const uint32_t *d_table, uint32_t n_bricks, void *stream, bool centers_only)
 {
     if (n_bricks == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
@@ -125,7 +159,7 @@ int cc_launch_parts_interp(const cc_eval_args &a, const uint32_t *d_table, uint3
     if (e != cudaSuccess) return (int)e;
     cc_parts_centers_kernel<<<(n_bricks + CC_THREADS - 1) / CC_THREADS, CC_THREADS, smem, st>>>(A);
     e = cudaGetLastError();
-    if (e != cudaSuccess) return (int)e;
+    if (e != cudaSuccess || centers_only) return (int)e;
     smem = cc_parts_smem_bytes(a.n_slots, a.code_words, 2);
     e = cudaFuncSetAttribute(cc_parts_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;

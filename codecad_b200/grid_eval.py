@@ -21,6 +21,34 @@ def slab_range(nx, rank, world):
     return x0, x0 + base + (1 if rank < rem else 0)
 
 
+def balanced_slabs(shape, corner, step, dims, world):
+    """x-ranges [(x0, x1), ...] for `world` ranks with about equal WORK instead of equal plane counts: with part culling
+    the rim of an assembly's grid is cheaper than its middle (cc_grid_eval_cost_profile: the brick masks' estimate per
+    layer of eight planes).  Cuts lie on multiples of 8 planes; every rank computes the same list; the results of
+    grid_eval do not depend on it.  A program without parts gets slab_range()'s equal slabs."""
+    import ctypes
+    program = make_program_buffer(shape)
+    nx, ny, nz = (int(d) for d in dims)
+    world = int(world)
+    n_layers = (nx + 7) // 8
+    if world <= 1 or n_layers < 2 * world:
+        return [slab_range(nx, r, world) for r in range(world)]
+    cost = (ctypes.c_double * n_layers)()
+    _lib.check(_lib.lib().cc_grid_eval_cost_profile(program.handle, _lib.f3(corner), float(np.float32(step)), nx, ny, nz, 0, cost, n_layers))
+    c = np.maximum(np.array(cost[:], dtype=np.float64), 1e-9)
+    if np.all(c == c[0]):
+        return [slab_range(nx, r, world) for r in range(world)]
+    prefix = np.concatenate([[0.0], np.cumsum(c)])
+    cuts = [0]
+    for r in range(1, world):
+        k = int(np.searchsorted(prefix, prefix[-1] * r / world))
+        if k > 0 and abs(prefix[k - 1] - prefix[-1] * r / world) < abs(prefix[k] - prefix[-1] * r / world):
+            k -= 1
+        cuts.append(min(max(k, cuts[-1] + 1), n_layers - (world - r)))   # every rank keeps at least one layer
+    cuts.append(n_layers)
+    return [(8 * cuts[r], min(8 * cuts[r + 1], nx)) for r in range(world)]
+
+
 def _eval(shape, corner, step, dims, layout, x_offset, out, to_host):
     program = make_program_buffer(shape)
     nx, ny, nz = (int(d) for d in dims)

@@ -158,6 +158,14 @@ int cc_set_parts_mode(int mode);
  * rest per cell.  Same arithmetic on the same operands: bit-identical.  Combines with
  * the parts' masks.  mode 1 = on (default; CODECAD_B200_COLUMNS), 0 = off.  Returns the old mode. */
 int cc_set_columns_mode(int mode);
+/* Load balance of x-slabs ("over-decompose"): with part culling the planes of a grid are no longer
+ * equal work — the rim of an assembly's box is emptier than its middle.  Fills layer_cost[i], i < ceil(nx / 8), with an
+ * estimate of the work in the i-th layer of eight x-planes: per brick a constant plus the micro-ops of the parts its
+ * mask keeps (the brick-centre pass of cc_set_parts_mode; a program without parts reports equal layers).  Callers
+ * cut the prefix sums into as many slabs as they have GPUs (codecad_b200.grid_eval.balanced_slabs).  Results of
+ * grid_eval do not depend on where the slabs are cut. */
+int cc_grid_eval_cost_profile(const cc_program *prog, const float corner[3], float step, uint32_t nx, uint32_t ny,
+                              uint32_t nz, uint32_t x_offset, double *layer_cost, uint32_t n_layers);
 int cc_program_get_forest_info(const cc_program *prog, uint32_t out[4]);
 /* Blocks until the specialised kernels of the sinks in `sink_mask` (0 = all) are compiled and
  * loaded, starting their compilation if necessary; returns how many are ready.  compile_seconds

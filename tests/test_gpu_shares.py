@@ -82,3 +82,31 @@ def test_exact_accumulator_matches_a_float64_sum(cb, scenes):
     got = cb.mass_properties(s.compiled(), 1.0, 64)
     assert abs(got.volume - vol) <= 4e-16 * vol
     assert max(abs(g - w) for g, w in zip(got.centroid, cen)) <= 1e-13 * max(map(abs, cen))
+
+
+def test_balanced_slabs_cover_the_grid_and_do_not_change_results(scenes):
+    """grid_eval.balanced_slabs: cuts on multiples of eight planes, every plane exactly once, more planes where the
+    assembly's box is empty; the slabs' results are the unsharded grid."""
+    import importlib
+    import codecad_b200
+    ge = importlib.import_module("codecad_b200.grid_eval")
+    s = scenes["cfg_planetary"]
+    scene = s.compiled()
+    n = 256
+    corner, step = s.grid(n)
+    for world in (2, 3, 8):
+        slabs = ge.balanced_slabs(scene, corner, step, (n, n, n), world)
+        assert len(slabs) == world and slabs[0][0] == 0 and slabs[-1][1] == n
+        assert all(a1 == b0 for (_, a1), (b0, _) in zip(slabs, slabs[1:]))
+        assert all(x1 > x0 and x0 % 8 == 0 for x0, x1 in slabs)
+    slabs = ge.balanced_slabs(scene, corner, step, (n, n, n), 8)
+    widths = [x1 - x0 for x0, x1 in slabs]
+    assert widths[0] > widths[3] and widths[-1] > widths[4]          # the rim slabs are wider than the middle ones
+    whole = np.array(codecad_b200.grid_eval(scene, corner, step, (n, n, n)))
+    for x0, x1 in slabs:
+        part = np.array(codecad_b200.grid_eval(scene, corner, step, (x1 - x0, n, n), x_offset=x0))
+        assert part.tobytes() == whole[x0:x1].tobytes()
+    # a program without parts: equal slabs
+    c = scenes["cfg_csg_example"]
+    cc, cs = c.grid(128)
+    assert ge.balanced_slabs(c.compiled(), cc, cs, (128, 128, 128), 4) == [ge.slab_range(128, r, 4) for r in range(4)]
