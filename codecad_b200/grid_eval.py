@@ -35,18 +35,29 @@ def balanced_slabs(shape, corner, step, dims, world):
         return [slab_range(nx, r, world) for r in range(world)]
     cost = (ctypes.c_double * n_layers)()
     _lib.check(_lib.lib().cc_grid_eval_cost_profile(program.handle, _lib.f3(corner), float(np.float32(step)), nx, ny, nz, 0, cost, n_layers))
-    c = np.maximum(np.array(cost[:], dtype=np.float64), 1e-9)
-    if np.all(c == c[0]):
+    cuts = cut_equal_work(np.array(cost[:], dtype=np.float64), world)
+    if cuts is None:
         return [slab_range(nx, r, world) for r in range(world)]
+    return [(8 * cuts[r], min(8 * cuts[r + 1], nx)) for r in range(world)]
+
+
+def cut_equal_work(cost, world):
+    """Indices 0 = c_0 < c_1 < ... < c_world = len(cost) that split `cost` into `world` runs of about equal sum, every
+    run non-empty; None if the costs are all the same (nothing to balance)."""
+    c = np.maximum(np.asarray(cost, dtype=np.float64), 1e-9)
+    n = len(c)
+    if n < world or np.all(c == c[0]):
+        return None
     prefix = np.concatenate([[0.0], np.cumsum(c)])
     cuts = [0]
     for r in range(1, world):
-        k = int(np.searchsorted(prefix, prefix[-1] * r / world))
-        if k > 0 and abs(prefix[k - 1] - prefix[-1] * r / world) < abs(prefix[k] - prefix[-1] * r / world):
+        target = prefix[-1] * r / world
+        k = int(np.searchsorted(prefix, target))
+        if k > 0 and abs(prefix[k - 1] - target) < abs(prefix[k] - target):
             k -= 1
-        cuts.append(min(max(k, cuts[-1] + 1), n_layers - (world - r)))   # every rank keeps at least one layer
-    cuts.append(n_layers)
-    return [(8 * cuts[r], min(8 * cuts[r + 1], nx)) for r in range(world)]
+        cuts.append(min(max(k, cuts[-1] + 1), n - (world - r)))
+    cuts.append(n)
+    return cuts
 
 
 def _eval(shape, corner, step, dims, layout, x_offset, out, to_host):

@@ -332,3 +332,26 @@ def test_leaf_block_list_built_in_c_equals_the_python_form():
     assert type(b) is tuple and type(b[1]) is Vector and type(b[3]) is Vector
     assert type(b[1].x) is float and type(b[3].z) is int and b[0] is dims and b[4] == 15
     assert sub.LeafBlocks(dims, c[:0], 0.195, ic[:0], 15)._materialise() == []
+
+
+def test_cut_equal_work():
+    """grid_eval.cut_equal_work: the pure part of balanced_slabs."""
+    import importlib
+    ge = importlib.import_module("codecad_b200.grid_eval")
+    assert ge.cut_equal_work([3.0] * 16, 4) is None                       # nothing to balance
+    assert ge.cut_equal_work([1.0, 2.0], 3) is None                       # fewer layers than ranks
+    cost = np.array([1, 1, 1, 1, 4, 4, 4, 4, 1, 1, 1, 1], float)          # a heavy middle
+    cuts = ge.cut_equal_work(cost, 3)
+    assert cuts[0] == 0 and cuts[-1] == len(cost) and all(b > a for a, b in zip(cuts, cuts[1:]))
+    sums = [cost[a:b].sum() for a, b in zip(cuts, cuts[1:])]
+    assert max(sums) <= 1.5 * min(sums)
+    assert cuts[1] > len(cost) // 3 and cuts[2] < 2 * len(cost) // 3      # the rim runs are longer than the middle one
+    rng = np.random.default_rng(5)
+    for _ in range(200):
+        n, w = int(rng.integers(2, 200)), int(rng.integers(1, 17))
+        c = rng.uniform(0.0, 10.0, n) ** 3
+        cuts = ge.cut_equal_work(c, w)
+        if n < w:
+            assert cuts is None
+            continue
+        assert cuts[0] == 0 and cuts[-1] == n and len(cuts) == w + 1 and all(b > a for a, b in zip(cuts, cuts[1:]))
