@@ -1074,10 +1074,16 @@ int cc_grid_eval_cost_profile(const cc_program *prog, const float corner[3], flo
     if (e) return cuda_fail((cudaError_t)e, "brick-centre kernel launch");
     // weights: a brick costs its set-up and stores plus the micro-ops of the parts it keeps
     cc_layer_weights w;
-    w.base = 12.0f;
+    w.base = 60.0f;
     for (int k = 0; k < 32; ++k) w.part[k] = 0.0f;
-    for (int part : parts.part_of_op)
-        if (part >= 0 && part < 32) w.part[part] += 1.0f;
+    const cc_columns &cols = prog->dec.columns;
+    const bool split = g.columns_mode && cols.enabled && !cc_jit_is_segmented(prog->dec);  // (the dense path then runs the per-cell body only)
+    for (size_t v = 0; v < parts.part_of_op.size(); ++v) {
+        const int part = parts.part_of_op[v];
+        if (part < 0 || part >= 32) continue;
+        if (split && v < cols.phase.size() && !(cols.phase[v] & 2)) continue;
+        w.part[part] += v < cols.op_cost.size() ? (float)cols.op_cost[v] : 10.0f;
+    }
     double *d_cost = nullptr;
     CU(cudaMallocAsync((void **)&d_cost, (size_t)n_layers * sizeof(double), g.compute));
     e = cc_launch_layer_cost(a.part_masks, n_layers, (uint32_t)per_layer, w, d_cost, g.compute);

@@ -63,6 +63,7 @@ struct cc_columns {
     int root_restore = -1;             // the program's result itself is column-invariant: op index, else -1
     std::vector<uint32_t> checked_rows;  // (micro-op index * 4 + row) of T_INIT rows whose z coefficient is rounding residue: verified per column
     float invariant_share = 0.0f;      // estimated share of the arithmetic that leaves the loop
+    std::vector<uint32_t> op_cost;     // per micro-op: the rough cost the estimate uses (instructions per point pair)
 };
 
 struct cc_decoded {

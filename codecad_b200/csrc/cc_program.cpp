@@ -449,6 +449,8 @@ static void analyse_columns_along(const std::vector<uint32_t> &code, int axis, c
             if (p >= 0) ahead[(size_t)p] = 1;
     }
     out->phase.assign((size_t)n, 0);
+    out->op_cost.resize((size_t)n);
+    for (int v = 0; v < n; ++v) out->op_cost[(size_t)v] = ops[(size_t)v].cost;
     out->restore_from.assign((size_t)n, -1);
     out->save_l.assign((size_t)n, 0);
     uint64_t total = 0, hoisted = 0, repeated = 0;
