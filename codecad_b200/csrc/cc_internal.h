@@ -49,20 +49,21 @@ struct cc_parts {
 #define CC_SEG_PART 1u
 #define CC_SEG_UNION 2u
 
-// Columns.  On a dense grid the z axis of the grid is the z axis of the program's point;
-// a 2-D profile under an extrusion — transform, polygon, gear, their unions — sees x and y only, so its
-// value is the same for every cell of a z-column.  The loader tracks, op by op and component by component,
-// what can depend on the grid's z, and splits the micro-ops into those that run once per column (before
-// the z loop) and those that run per cell (cc_program.cpp analyse_columns, cc_jit.cpp).
+// Columns.  On a dense grid the axes of the grid are the axes of the program's point; a 2-D profile
+// under an extrusion — transform, polygon, gear, their unions — sees two of them only, so its value is the same for
+// every cell of a column along the third.  The loader tracks, op by op and component by component, what can depend
+// on the grid coordinate along `axis`, and splits the micro-ops into those that run once per column ("ahead": the
+// column pass) and those that run per cell ("loop": the brick / tile kernels) — cc_program.cpp analyse_columns,
+// cc_jit.cpp.
 struct cc_columns {
     bool enabled = false;
     int axis = 2;                      // the grid axis of the columns: 0 = x, 1 = y, 2 = z
-    std::vector<uint8_t> phase;        // per micro-op: bit 0 = runs before the z loop, bit 1 = runs inside it
-    std::vector<int> restore_from;     // per micro-op of the loop: the op (outside the loop) whose result is its running value, else -1
-    std::vector<uint8_t> save_l;       // per micro-op: its result is carried into the loop as a running value
+    std::vector<uint8_t> phase;        // per micro-op: bit 0 = runs in the column pass, bit 1 = runs per cell
+    std::vector<int> restore_from;     // per micro-op of the per-cell body: the op (of the column pass only) whose result is its running value, else -1
+    std::vector<uint8_t> save_l;       // per micro-op: its result is carried into the per-cell body as a running value
     int root_restore = -1;             // the program's result itself is column-invariant: op index, else -1
-    std::vector<uint32_t> checked_rows;  // (micro-op index * 4 + row) of T_INIT rows whose z coefficient is rounding residue: verified per column
-    float invariant_share = 0.0f;      // estimated share of the arithmetic that leaves the loop
+    std::vector<uint32_t> checked_rows;  // (micro-op index * 4 + row) of T_INIT rows whose coefficient along the axis is rounding residue: verified per column
+    float invariant_share = 0.0f;      // estimated share of the arithmetic that leaves the per-cell body
     std::vector<uint32_t> op_cost;     // per micro-op: the rough cost the estimate uses (instructions per point pair)
 };
 
