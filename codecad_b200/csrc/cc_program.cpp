@@ -339,9 +339,9 @@ bool sigma_max(const float *m, double *out)
     return std::isfinite(*out);
 }
 
-// ---- columns: which micro-ops can see the grid's z (cc_internal.h cc_columns) ---------------------
+// ---- columns: which micro-ops can see the grid coordinate along one axis (cc_internal.h cc_columns) ----
 // Forward data flow over the straight-line microcode with one bit per component (x, y, z, w) of the
-// running value and of every slot: "may differ between two cells of one z-column".  The rules below
+// running value and of every slot: "may differ between two cells of one column along the axis".  The rules below
 // follow the op library (cc_ops.cuh) and cc-arith's matrix form, where a zero coefficient is not a
 // multiplication by zero but an omitted term — the remaining terms never see that operand:
 //   transforms          row r depends on what its non-zero coefficients read
