@@ -61,6 +61,8 @@ struct cc_columns {
     std::vector<uint8_t> phase;        // per micro-op: bit 0 = runs in the column pass, bit 1 = runs per cell
     std::vector<int> restore_from;     // per micro-op of the per-cell body: the op (of the column pass only) whose result is its running value, else -1
     std::vector<uint8_t> save_l;       // per micro-op: its result is carried into the per-cell body as a running value
+    std::vector<uint8_t> split_prim;   // per micro-op: a fused extruded circle / rectangle whose 2-D half (transform rows x, y + the profile)
+                                       // cannot see the axis: that half runs in the column pass, extrusion and the rest per cell
     int root_restore = -1;             // the program's result itself is column-invariant: op index, else -1
     std::vector<uint32_t> checked_rows;  // (micro-op index * 4 + row) of T_INIT rows whose coefficient along the axis is rounding residue: verified per column
     float invariant_share = 0.0f;      // estimated share of the arithmetic that leaves the per-cell body

@@ -396,6 +396,7 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
         }
         const uint32_t h = c[pc], op = CC_HDR_OP(h), src_slot = CC_HDR_SRC(h), dst = CC_HDR_DST(h);
         if (columns_mode) o.str(std::string());  // one micro-op at a time: its text goes to one body or both
+        std::string split_fused, split_a, split_b;  // a fused primitive cut in two (cc_columns::split_prim)
         o << "        // pc " << pc << "\n";
         const int my_part = (parts_mode && op != MOP_RETURN && (size_t)op_index < parts.part_of_op.size()) ? parts.part_of_op[(size_t)op_index] : -1;
         const bool tree_union = parts_mode && op == MOP_UNION && (size_t)op_index < parts.union_a.size() &&
@@ -439,13 +440,25 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
                   << ", V>(cc_par + " << off << ", " << X << ", " << Y << ", " << Z << ");\n        }\n";
                 break;
             }
-            o << "        {\n" << coord_load << "          V pz_[G];\n"
-              << "          CC_EACH { L[g] = " << g.transform_to(pc + 1, X, Y, Z) << "; pz_[g] = L[g].z; }\n";
-            if (rect) o << "          cc_rectangle_n(" << g.args(pc, 13, 2) << ", L);\n";
-            else o << "          cc_circle_n(" << g.F(pc + 13) << ", L);\n";
-            o << "          cc_extrusion_n(" << g.F(pc + 15) << ", L, pz_);\n"
-              << "          CC_EACH { L[g].w = vsub(L[g].w, vbc<V>(" << g.F(pc + 16) << ")); const Val t_ = L[g]; L[g] = "
-              << g.transform_from(pc + 17, "t_") << "; }\n        }\n";
+            {
+                const std::string to = g.transform_to(pc + 1, X, Y, Z);
+                const std::string profile = rect ? "          cc_rectangle_n(" + g.args(pc, 13, 2) + ", L);\n"
+                                                 : "          cc_circle_n(" + g.F(pc + 13) + ", L);\n";
+                const std::string tail = "          cc_extrusion_n(" + g.F(pc + 15) + ", L, pz_);\n"
+                                         "          CC_EACH { L[g].w = vsub(L[g].w, vbc<V>(" + g.F(pc + 16) + ")); const Val t_ = L[g]; L[g] = " +
+                                         g.transform_from(pc + 17, "t_") + "; }\n        }\n";
+                const std::string fused = "        {\n" + coord_load + "          V pz_[G];\n          CC_EACH { L[g] = " + to +
+                                          "; pz_[g] = L[g].z; }\n" + profile + tail;
+                o << fused;
+                if (columns_mode && (size_t)op_index < cols.split_prim.size() && cols.split_prim[(size_t)op_index]) {
+                    // columns: the profile half once per column, extrusion / offset / inverse transform per cell (same calls, same operands)
+                    const std::string k = std::to_string(n_carried++);
+                    split_fused = fused;
+                    split_a = "        {\n          CC_EACH L[g] = " + to + ";\n" + profile + "          CC_EACH cc_col_store(cr, " + k + "u, L[g]);\n        }\n";
+                    split_b = "        {\n          V pz_[G];\n          CC_EACH { const Val p_ = " + to + "; pz_[g] = p_.z; L[g] = cc_col_load<V>(cr, " + k +
+                              "u); }\n" + tail;
+                }
+            }
             break;
         }
         case MOP_RECTANGLE: o << "        cc_rectangle_n(" << g.args(pc, 1, 2) << ", L);\n"; break;
@@ -554,11 +567,13 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
             const uint8_t ph = col_phase(op_index);
             const std::string text = o.str();
             put(full, full_open, my_part, text);
+            std::string text_loop = text;  // (the cut primitive: its per-cell half in place of the fused block, the slot store behind it stays)
+            if (!split_fused.empty()) text_loop.replace(text_loop.find(split_fused), split_fused.size(), split_b);
             if (my_part >= 0 && ((size_t)op_index + 1 >= parts.part_of_op.size() || parts.part_of_op[(size_t)op_index + 1] != my_part))
                 put(full, full_open, my_part, "        if (pw) pw[" + std::to_string(my_part) + "] = L[0].w;  // the part's value (brick centres)\n");
             if (carried_l.empty()) { carried_l.assign(cols.phase.size(), -1); carried_interval.assign(iv.size(), -1); }
             if (ph & 1) {
-                ahead << "        {\n" << text;
+                ahead << "        {\n" << (split_a.empty() ? text : split_a);
                 if (cols.save_l[(size_t)op_index]) {
                     carried_l[(size_t)op_index] = (int)n_carried;
                     ahead << "        CC_EACH cc_col_store(cr, " << n_carried++ << "u, L[g]);\n";
@@ -581,7 +596,7 @@ int generate(const cc_decoded &dec, const cc_jit_cfg &cfg, unsigned sink_mask, s
                 if (u >= 0 && iv[u].carried)  // (shadows the register of the same name: this body never defines it)
                     fetch = "        Val I" + std::to_string(u) + "[G]; CC_EACH I" + std::to_string(u) + "[g] = cc_col_load<V>(cr, " +
                             std::to_string(carried_interval[(size_t)u]) + "u);\n";
-                put(in_loop, loop_open, my_part, fetch + text);
+                put(in_loop, loop_open, my_part, fetch + text_loop);
             }
         }
         pc += CC_HDR_LEN(h);

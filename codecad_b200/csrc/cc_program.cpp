@@ -355,6 +355,7 @@ static void analyse_columns_along(const std::vector<uint32_t> &code, int axis, c
     enum { X = 1, Y = 2, Z = 4, W = 8, ALL = 15 };
     struct Op { uint32_t pc, op; int in_l, in_s; uint8_t dep; uint32_t cost; };
     std::vector<Op> ops;
+    std::vector<uint8_t> split_prim;
     std::vector<int> slot_prod(CC_SLOT_NONE + 1, -1);
     int L = -1, root = -1;
     auto fl = [&](uint32_t pc, int k) { float f; std::memcpy(&f, &code[pc + 1 + (uint32_t)k], 4); return f; };
@@ -414,7 +415,27 @@ static void analyse_columns_along(const std::vector<uint32_t> &code, int axis, c
         case MOP_REPETITION: o.dep = (uint8_t)(dl & (X | Y | Z)); o.cost = 30; break;
         case MOP_CREP_TO: o.dep = (uint8_t)(((dl & (X | Y)) ? (X | Y) : 0) | (dl & Z)); o.cost = 60; break;
         case MOP_CREP_FROM: o.dep = (uint8_t)((((dl | ds) & (X | Y)) ? (X | Y) : 0) | (dl & (Z | W))); o.cost = 60; break;
-        case MOP_PRIM_CIRCLE: case MOP_PRIM_RECT: case MOP_PRIM_CIRCLE_M: case MOP_PRIM_RECT_M: o.dep = ALL; o.cost = 100; break;
+        case MOP_PRIM_CIRCLE: case MOP_PRIM_RECT: case MOP_PRIM_CIRCLE_M: case MOP_PRIM_RECT_M: {
+            // fused transform -> circle | rectangle -> extrusion -> offset -> inverse transform: as a whole it sees every axis; its
+            // 2-D half does not when rows x and y of the matrix have no (or only a residue, checked per column) coefficient
+            // along the axis — the extrusion is then along the columns
+            o.dep = ALL;
+            o.cost = 100;
+            bool split = true;
+            std::vector<uint32_t> residue;
+            for (int r = 0; r < 2; ++r) {
+                const float big = std::max(std::fabs(fl(pc, 3 * r + (axis + 1) % 3)), std::fabs(fl(pc, 3 * r + (axis + 2) % 3)));
+                const float mz = std::fabs(fl(pc, 3 * r + axis));
+                if (mz != 0.0f && !(mz <= big * 9.313225746154785e-10f)) split = false;
+                else if (mz != 0.0f) residue.push_back((uint32_t)ops.size() * 4u + (uint32_t)r);
+            }
+            if (split) {
+                split_prim.resize(ops.size() + 1, 0);
+                split_prim[ops.size()] = 1;
+                out->checked_rows.insert(out->checked_rows.end(), residue.begin(), residue.end());
+            }
+            break;
+        }
         default:
             o.dep = (dl | ds) ? ALL : 0;
             o.cost = (op == MOP_UNION || op == MOP_ISECT || op == MOP_SUB) ? 5 : 30;
@@ -454,8 +475,16 @@ static void analyse_columns_along(const std::vector<uint32_t> &code, int axis, c
     out->restore_from.assign((size_t)n, -1);
     out->save_l.assign((size_t)n, 0);
     uint64_t total = 0, hoisted = 0, repeated = 0;
+    split_prim.resize((size_t)n, 0);
+    out->split_prim.assign((size_t)n, 0);
     for (int v = 0; v < n; ++v) {
         out->phase[(size_t)v] = (uint8_t)((ahead[(size_t)v] ? 1 : 0) | (in_loop[(size_t)v] ? 2 : 0));
+        if (split_prim[(size_t)v] && in_loop[(size_t)v] && !ahead[(size_t)v]) {  // its 2-D half joins the column pass
+            // (not counted towards the invariant share: a program of boxes and cylinders alone gains too little from
+            // moving half a primitive to pay for the column pass; with gears or polygons to hoist it comes for free)
+            out->split_prim[(size_t)v] = 1;
+            out->phase[(size_t)v] |= 1;
+        }
         if (ahead[(size_t)v] || in_loop[(size_t)v]) total += ops[(size_t)v].cost;
         if (ahead[(size_t)v] && !in_loop[(size_t)v]) hoisted += ops[(size_t)v].cost;
         if (ahead[(size_t)v] && in_loop[(size_t)v]) repeated += ops[(size_t)v].cost;
