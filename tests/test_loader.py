@@ -239,3 +239,74 @@ def test_tile_units_for_the_hierarchy_sinks(scenes):
     src = _lib.specialize_source(scenes["cfg_planetary"].words, 2, compile=False, sink_mask=128)
     src = src[0] if isinstance(src, tuple) else src
     assert "cc_jit_parts(" in src and "cc_jit_part_centers" in src and "cc_jit_tile" not in src
+
+
+def test_column_split_is_self_consistent():
+    """cc_program.cpp analyse_columns on every fixture: what the per-cell body reads is either computed per cell or handed
+    over by the column pass; nothing the column pass runs can see the axis, except ops that feed it in their invariant
+    components (initial transforms) and the cut primitives; the column pass is closed under its inputs."""
+    import os
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path[:0] = [%r, %r]\n"
+            "from codecad_b200 import _lib\n"
+            "from scenes import load_scenes\n"
+            "for n, s in sorted(load_scenes().items()):\n"
+            "    sys.stderr.write('scene %%s\\n' %% n); sys.stderr.flush()\n"
+            "    _lib.decode_program(s.words)\n") % (root, os.path.join(root, "tests"))
+    env = dict(os.environ, CODECAD_B200_COLUMNS_DEBUG="1")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    pat = re.compile(r"op\s+(\d+)\s+mop\s+(\d+)\s+in_l\s+(-?\d+) in_s\s+(-?\d+)\s+dep (\w+)\s+phase (\d+)\s+save (\d+) restore (-?\d+) cost (\d+)")
+    scenes_seen, tables = 0, 0
+    table = []
+
+    def check(rows):
+        ops = {r[0]: r for r in rows}
+        # ops of the column pass that reach, through column-pass ops, one whose value cannot see the axis
+        feeds_invariant = {r[0] for r in rows if r[5] & 1 and r[4] == 0}
+        for r in reversed(rows):                             # (inputs precede their readers)
+            if r[0] in feeds_invariant:
+                feeds_invariant.update(p for p in (r[2], r[3]) if p >= 0)
+        for i, mop, in_l, in_s, dep, phase, save, restore, cost in rows:
+            if phase & 2:                                   # runs per cell
+                assert dep != 0, "an invariant op in the per-cell body"
+                for p in (in_l, in_s):
+                    if p < 0:
+                        continue
+                    if ops[p][5] & 2:
+                        continue                            # computed per cell as well
+                    assert ops[p][4] == 0, "the per-cell body reads a dependent value it does not compute"
+                    assert ops[p][5] & 1, "... or an invariant one the column pass does not compute"
+                if in_l >= 0 and not ops[in_l][5] & 2:
+                    assert restore == in_l and ops[in_l][6] == 1, "running value not handed over"
+                else:
+                    assert restore == -1
+            if phase & 1:                                   # runs in the column pass
+                for p in (in_l, in_s):
+                    assert p < 0 or ops[p][5] & 1, "the column pass is not closed under its inputs"
+                if dep != 0 and mop not in (32, 33, 37, 38):     # (a cut primitive is there for its profile half)
+                    assert i in feeds_invariant, "a dependent op in the column pass that feeds nothing invariant"
+            if save:
+                assert phase & 1 and not phase & 2 and dep == 0
+
+    for line in out.stderr.splitlines():
+        if line.startswith("scene "):
+            scenes_seen += 1
+            continue
+        m = pat.match(line)
+        if not m:
+            continue
+        row = (int(m.group(1)), int(m.group(2)), int(m.group(3)), int(m.group(4)), int(m.group(5), 16), int(m.group(6)), int(m.group(7)),
+               int(m.group(8)), int(m.group(9)))
+        if row[0] == 0 and table:
+            check(table)
+            tables += 1
+            table = []
+        table.append(row)
+    if table:
+        check(table)
+        tables += 1
+    assert scenes_seen > 100 and tables >= scenes_seen          # (one table per axis and scene that got as far as the split)
