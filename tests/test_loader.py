@@ -310,3 +310,19 @@ def test_column_split_is_self_consistent():
         check(table)
         tables += 1
     assert scenes_seen > 100 and tables >= scenes_seen          # (one table per axis and scene that got as far as the split)
+
+
+@pytest.mark.parametrize("name,sink", [("col_star_x", 256), ("col_star_half_turn", 256), ("col_hole_grid", 256), ("col_hole_grid", 2048),
+                                       ("dsdf3d_mirror_3d", 128), ("dsdf3d_mirror_3d", 1024), ("colr_08", 512), ("cfg_airfoil", 2048)])
+def test_brick_and_tile_units_compile(scenes, name, sink):
+    """The generated source of the part-culling (128), column (256) and tile units (512 / 1024 / 2048: PyMCubes / classify /
+    mass) goes through NVRTC for sm_100a here, without a device: columns along x and y, residue rows with the per-column
+    check, parts with and without a column split, a cut primitive."""
+    from codecad_b200 import _lib
+    try:
+        src, cubin_bytes = _lib.specialize_source(scenes[name].words, 2, compile=True, sink_mask=sink)
+    except _lib.CodecadB200Error as exc:
+        if "NVRTC" in str(exc) and "not found" in str(exc):
+            pytest.skip("no libnvrtc in this environment")
+        raise
+    assert cubin_bytes > 10000 and '__global__' in src
