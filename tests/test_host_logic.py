@@ -355,3 +355,33 @@ def test_cut_equal_work():
             assert cuts is None
             continue
         assert cuts[0] == 0 and cuts[-1] == n and len(cuts) == w + 1 and all(b > a for a, b in zip(cuts, cuts[1:]))
+
+
+def test_row_with_residue_coefficient_is_monotone_along_the_column():
+    """The run-time check of the column kernels: a transform row is a chain of correctly rounded FMAs,
+    hence monotone in the coordinate along the column; equal bits at both ends of a column therefore mean equal bits at
+    every cell between.  Checked here on random rows with a residue coefficient (fp32 FMA emulated exactly in float64:
+    the product of two floats is exact there, and rounding the sum twice keeps it monotone)."""
+    rng = np.random.default_rng(77)
+
+    def fma(a, b, c):
+        return np.float32(np.float64(a) * np.float64(b) + np.float64(c))
+
+    constant = varying = 0
+    for _ in range(400):
+        mx, my = np.float32(rng.uniform(-1, 1)), np.float32(rng.uniform(-1, 1))
+        mz = np.float32(rng.choice([-1, 1]) * 10.0 ** rng.uniform(-18, -9))
+        o = np.float32(rng.choice([0.0, 1e-14, -8.4e-15, rng.uniform(-50, 50)]))
+        step, cz = np.float32(10.0 ** rng.uniform(-3, 0)), np.float32(rng.uniform(-60, 60))
+        x = np.float32(rng.choice([0.0, rng.uniform(-60, 60)]))
+        y = np.float32(rng.choice([0.0, rng.uniform(-60, 60), 10.0 ** rng.uniform(-14, -6)]))
+        zs = [fma(step, np.float32(i), cz) for i in range(64)]
+        row = np.array([fma(mx, x, fma(my, y, fma(mz, z, o))) for z in zs], np.float32)
+        d = np.diff(row.astype(np.float64))
+        assert np.all(d >= 0) or np.all(d <= 0), "not monotone"
+        if row[0].tobytes() == row[-1].tobytes():
+            assert all(v.tobytes() == row[0].tobytes() for v in row)
+            constant += 1
+        else:
+            varying += 1
+    assert constant > 100 and varying > 5          # both outcomes occur: the check is neither vacuous nor always failing
